@@ -1,0 +1,494 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Headless driver around the REFERENCE's own geometry code.  It is compiled together with
+// /root/reference/Src/{Poly,Kdop,VMACH}.cpp and Inc/DT3D.h (from where they lie, see
+// oracle/Makefile) into oracle/_ref/libsurtr_ref.so and exposes a flat C interface for
+// the tests, the golden-fixture generator and bench.py's CPU-baseline leg.
+//
+// Src/Surtr.cpp cannot be compiled here (DX12 + PhysX + voro++ + assimp + Win32), so the
+// few orchestration routines of the hot path are restated below, each citing the lines it
+// follows.  Everything geometric is done by calling the reference functions themselves.
+//
+// Flat polyhedron-set layout (shared with include/surtr_b200.h):
+//   verts    float[4*NV]   xyz + 0 pad, all polyhedra back to back
+//   vert_off u32[n+1]      first vertex of polyhedron i
+//   ring_off u32[NV+1]     first ring entry of (global) vertex v
+//   ring     u16[NE]       neighbour rings, indices LOCAL to the polyhedron
+#include "pch.h"
+
+#include "Poly.h"
+#include "Kdop.h"
+#include "VMACH.h"
+#include "DT3D.h" // non-inline definitions: include from exactly this TU
+
+#include "thread_pool.h"
+
+#include <chrono>
+#include <future>
+
+using DirectX::SimpleMath::Plane;
+using DirectX::SimpleMath::Vector3;
+
+namespace
+{
+struct PolySet
+{
+	std::vector<float> verts;
+	std::vector<uint32_t> vert_off{ 0 };
+	std::vector<uint32_t> ring_off{ 0 };
+	std::vector<uint16_t> ring;
+	// per polyhedron
+	std::vector<uint32_t> cell, piece, nfaces;
+	std::vector<double> volume;
+	std::vector<float> centroid; // 3 per polyhedron
+	// face loops (ExtractFaces order) and face planes (PolygonFace::AddVertex route)
+	std::vector<uint32_t> face_off{ 0 };     // per face: first loop entry
+	std::vector<uint16_t> face_idx;          // local vertex ids
+	std::vector<uint32_t> poly_face_off{ 0 }; // per polyhedron: first face
+	std::vector<float> planes;               // 4 per face
+	double seconds = 0.0;
+
+	size_t count() const { return vert_off.size() - 1; }
+};
+
+Poly::Polyhedron to_poly(const float* verts, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring,
+						 uint32_t i)
+{
+	Poly::Polyhedron p;
+	const uint32_t v0 = vert_off[i], v1 = vert_off[i + 1];
+	std::vector<Vector3> pos;
+	std::vector<std::vector<int>> nei;
+	pos.reserve(v1 - v0);
+	nei.reserve(v1 - v0);
+	for (uint32_t v = v0; v < v1; v++)
+	{
+		pos.emplace_back(verts[4 * v], verts[4 * v + 1], verts[4 * v + 2]);
+		nei.emplace_back(ring + ring_off[v], ring + ring_off[v + 1]);
+	}
+	Poly::InitPolyhedron(p, pos, nei);
+	return p;
+}
+
+// Face plane exactly as a VMACH cell face gets it: PolygonFace(true) + AddVertex per loop vertex
+// (VMACH.cpp:289-310; duplicates closer than 1e-12 dropped; plane from the first three kept vertices).
+bool face_plane(const Poly::Polyhedron& p, const std::vector<int>& loop, Plane& out)
+{
+	VMACH::PolygonFace f(true);
+	for (int v : loop)
+		f.AddVertex(p[v].Position);
+	if (!f.FacePlaneConstructed)
+		return false;
+	out = f.FacePlane;
+	return true;
+}
+
+void append(PolySet& s, const Poly::Polyhedron& p, uint32_t cell, uint32_t piece, bool with_moments = true)
+{
+	for (const auto& v : p)
+	{
+		s.verts.push_back(v.Position.x);
+		s.verts.push_back(v.Position.y);
+		s.verts.push_back(v.Position.z);
+		s.verts.push_back(0.f);
+		for (int n : v.NeighborVertexVec)
+			s.ring.push_back((uint16_t)n);
+		s.ring_off.push_back((uint32_t)s.ring.size());
+	}
+	s.vert_off.push_back((uint32_t)(s.verts.size() / 4));
+	s.cell.push_back(cell);
+	s.piece.push_back(piece);
+
+	Poly::Extract* faces = Poly::ExtractFaces(p); // Poly.cpp:89-126
+	s.nfaces.push_back((uint32_t)faces->size());
+	for (const auto& loop : *faces)
+	{
+		for (int v : loop)
+			s.face_idx.push_back((uint16_t)v);
+		s.face_off.push_back((uint32_t)s.face_idx.size());
+		Plane pl(0, 0, 0, 0);
+		face_plane(p, loop, pl);
+		s.planes.push_back(pl.x);
+		s.planes.push_back(pl.y);
+		s.planes.push_back(pl.z);
+		s.planes.push_back(pl.w);
+	}
+	s.poly_face_off.push_back((uint32_t)(s.face_off.size() - 1));
+	delete faces;
+
+	double vol = 0.0;
+	Vector3 c(0, 0, 0);
+	if (with_moments)
+		Poly::Moments(vol, c, p); // Poly.cpp:55-87
+	s.volume.push_back(vol);
+	s.centroid.push_back(c.x);
+	s.centroid.push_back(c.y);
+	s.centroid.push_back(c.z);
+}
+
+VMACH::Polygon3D planes_to_polygon(const float* planes, uint32_t p0, uint32_t p1)
+{
+	// Poly::ClipPolyhedron(const Polyhedron&, const Polygon3D&) only reads FaceVec[i].FacePlane (Poly.cpp:558-560).
+	VMACH::Polygon3D poly(true);
+	for (uint32_t k = p0; k < p1; k++)
+	{
+		VMACH::PolygonFace f(true);
+		f.ManuallySetFacePlane(Plane(planes[4 * k], planes[4 * k + 1], planes[4 * k + 2], planes[4 * k + 3]));
+		poly.AddFace(f);
+	}
+	return poly;
+}
+
+// Restatement of m_fractureTask, convex branch (Surtr.cpp:1457-1468, 1497-1503): one cell against every piece.
+std::vector<std::pair<uint32_t, Poly::Polyhedron>> fracture_task(const VMACH::Polygon3D& voroPoly,
+																 const std::vector<Poly::Polyhedron>& pieces)
+{
+	std::vector<std::pair<uint32_t, Poly::Polyhedron>> local;
+	for (uint32_t c = 0; c < pieces.size(); c++)
+	{
+		Poly::Polyhedron convex = Poly::ClipPolyhedron(pieces[c], voroPoly);
+		if (convex.empty())
+			continue;
+		local.emplace_back(c, std::move(convex));
+	}
+	return local;
+}
+
+std::vector<std::vector<uint32_t>> dt_neighbors(const std::vector<Vector3>& seeds)
+{
+	const DT3D::Delaunay dt = DT3D::Triangulate(seeds); // DT3D.h:159-267
+	// Tets carry point VALUES; map back by exact equality.
+	auto key = [](const Vector3& v) {
+		uint32_t b[3];
+		std::memcpy(b, &v.x, 12);
+		return std::make_tuple(b[0], b[1], b[2]);
+	};
+	std::map<std::tuple<uint32_t, uint32_t, uint32_t>, uint32_t> index;
+	for (uint32_t i = 0; i < seeds.size(); i++)
+		index[key(seeds[i])] = i;
+	std::vector<std::set<uint32_t>> nb(seeds.size());
+	for (const auto& tet : dt.TetVec)
+	{
+		const Vector3* p[4] = { &tet.p0, &tet.p1, &tet.p2, &tet.p3 };
+		uint32_t id[4];
+		bool ok = true;
+		for (int k = 0; k < 4; k++)
+		{
+			auto it = index.find(key(*p[k]));
+			if (it == index.end()) { ok = false; break; }
+			id[k] = it->second;
+		}
+		if (!ok)
+			continue;
+		for (int a = 0; a < 4; a++)
+			for (int b = 0; b < 4; b++)
+				if (a != b)
+					nb[id[a]].insert(id[b]);
+	}
+	std::vector<std::vector<uint32_t>> out(seeds.size());
+	for (size_t i = 0; i < seeds.size(); i++)
+		out[i].assign(nb[i].begin(), nb[i].end()); // ascending seed index
+	return out;
+}
+
+// NEW derivation (replaces the voro++ call sites Surtr.cpp:2007-2067, dependency absent):
+// cell i = container box clipped by the bisector half-spaces towards its neighbours j (ascending j),
+// plane = Plane((Si+Sj)*0.5, Sj-Si), outward normal, unnormalised.
+Plane bisector(const Vector3& si, const Vector3& sj)
+{
+	const Vector3 mid = (si + sj) * 0.5f;
+	return Plane(mid, sj - si);
+}
+} // namespace
+
+extern "C"
+{
+void* ref_polyset_new() { return new PolySet(); }
+void ref_polyset_free(void* h) { delete (PolySet*)h; }
+
+// sizes: [n_poly, n_verts, n_ring, n_faces, n_face_idx]
+void ref_polyset_sizes(void* h, uint64_t* sizes)
+{
+	PolySet* s = (PolySet*)h;
+	sizes[0] = s->count();
+	sizes[1] = s->verts.size() / 4;
+	sizes[2] = s->ring.size();
+	sizes[3] = s->face_off.size() - 1;
+	sizes[4] = s->face_idx.size();
+}
+
+double ref_polyset_seconds(void* h) { return ((PolySet*)h)->seconds; }
+
+#define COPY_OUT(dst, vec) \
+	if (dst)               \
+	std::memcpy(dst, (vec).data(), (vec).size() * sizeof((vec)[0]))
+
+void ref_polyset_export(void* h, float* verts, uint32_t* vert_off, uint32_t* ring_off, uint16_t* ring, uint32_t* cell,
+						uint32_t* piece, uint32_t* nfaces, double* volume, float* centroid, uint32_t* poly_face_off,
+						uint32_t* face_off, uint16_t* face_idx, float* planes)
+{
+	PolySet* s = (PolySet*)h;
+	COPY_OUT(verts, s->verts);
+	COPY_OUT(vert_off, s->vert_off);
+	COPY_OUT(ring_off, s->ring_off);
+	COPY_OUT(ring, s->ring);
+	COPY_OUT(cell, s->cell);
+	COPY_OUT(piece, s->piece);
+	COPY_OUT(nfaces, s->nfaces);
+	COPY_OUT(volume, s->volume);
+	COPY_OUT(centroid, s->centroid);
+	COPY_OUT(poly_face_off, s->poly_face_off);
+	COPY_OUT(face_off, s->face_off);
+	COPY_OUT(face_idx, s->face_idx);
+	COPY_OUT(planes, s->planes);
+}
+
+// Seeds: Surtr.cpp:1988-1998 (mt19937 + uniform_real_distribution<double>(-0.5,0.5), narrowed at emplace_back).
+void ref_seeds_uniform(uint32_t seed, uint32_t n, float* out)
+{
+	std::mt19937 gen(seed);
+	std::uniform_real_distribution<double> uniformDist(-0.5, 0.5);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		const double x = uniformDist(gen);
+		const double y = uniformDist(gen);
+		const double z = uniformDist(gen);
+		const Vector3 v(x, y, z);
+		out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+	}
+}
+
+// Radial pattern seeds: Surtr.cpp:2072-2096.
+void ref_seeds_radial(uint32_t seed, uint32_t n, double mean, float* out)
+{
+	std::mt19937 gen(seed);
+	std::uniform_real_distribution<double> directionUniformDist(-1.0, 1.0);
+	std::exponential_distribution<double> lengthExpDist(1.0 / mean);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		double len = std::max(std::min(lengthExpDist(gen), 0.5), 1e-12);
+		double x = directionUniformDist(gen);
+		double y = directionUniformDist(gen);
+		double z = directionUniformDist(gen);
+		Vector3 v = Vector3(x, y, z);
+		v.Normalize();
+		v *= len;
+		out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+	}
+}
+
+// The unit cube of Poly::GetBB() (Poly.cpp:587-617) as a one-element polyset.
+void ref_unit_cube(void* out)
+{
+	append(*(PolySet*)out, Poly::GetBB(), 0, 0);
+}
+
+// DT3D neighbour lists (CSR).  Returns total entries; call with idx == nullptr to size.
+uint64_t ref_dt3d_neighbors(const float* seeds, uint32_t n, uint32_t* off, uint32_t* idx, double* seconds)
+{
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n; i++)
+		s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	static thread_local std::vector<std::vector<uint32_t>> cache;
+	static thread_local std::vector<float> cache_key;
+	std::vector<float> k(seeds, seeds + 3 * n);
+	if (k != cache_key)
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		cache = dt_neighbors(s);
+		cache_key = k;
+		if (seconds)
+			*seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		if (off) off[i] = (uint32_t)total;
+		if (idx) std::copy(cache[i].begin(), cache[i].end(), idx + total);
+		total += cache[i].size();
+	}
+	if (off) off[n] = (uint32_t)total;
+	return total;
+}
+
+// Voronoi cells of `seeds` inside the unit container box, clipped with the REFERENCE clipper.
+// nb_off/nb_idx: neighbour CSR (e.g. from ref_dt3d_neighbors); nullptr = brute force (all j != i).
+void ref_voronoi_cells(const float* seeds, uint32_t n, const uint32_t* nb_off, const uint32_t* nb_idx, void* out)
+{
+	PolySet& o = *(PolySet*)out;
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n; i++)
+		s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		std::vector<Plane> planes;
+		if (nb_off)
+			for (uint32_t k = nb_off[i]; k < nb_off[i + 1]; k++)
+				planes.push_back(bisector(s[i], s[nb_idx[k]]));
+		else
+			for (uint32_t j = 0; j < n; j++)
+				if (j != i)
+					planes.push_back(bisector(s[i], s[j]));
+		Poly::Polyhedron cell = Poly::GetBB();
+		Poly::ClipPolyhedron(cell, planes); // Poly.cpp:265
+		append(o, cell, i, 0);
+	}
+}
+
+// Clip every polyhedron of a set by its own plane list (pl_off per polyhedron) -- Poly.cpp:265 in place.
+void ref_clip_each(const float* verts, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring,
+				   uint32_t n, const float* planes, const uint32_t* pl_off, void* out)
+{
+	PolySet& o = *(PolySet*)out;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		Poly::Polyhedron p = to_poly(verts, vert_off, ring_off, ring, i);
+		std::vector<Plane> pls;
+		for (uint32_t k = pl_off[i]; k < pl_off[i + 1]; k++)
+			pls.emplace_back(planes[4 * k], planes[4 * k + 1], planes[4 * k + 2], planes[4 * k + 3]);
+		Poly::ClipPolyhedron(p, pls);
+		append(o, p, i, i);
+	}
+}
+
+// Restatement of Surtr::ApplyFracture (Surtr.cpp:2098-2149), non-partial, convex branch:
+// one task per cell, results consumed in cell order, piece-minor inside a cell.
+// nthreads == 0: run the tasks inline on the calling thread; otherwise dp::thread_pool(nthreads)
+// (the reference uses 16, Surtr.cpp:28).  `seconds` covers enqueue -> last future, like the
+// reference's "ApplyFracture" timer (Surtr.cpp:1917-1924), not the result flattening.
+void ref_apply_fracture(const float* verts, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring,
+						uint32_t n_pieces, const float* planes, const uint32_t* plane_off, uint32_t n_cells,
+						uint32_t nthreads, int with_moments, void* out)
+{
+	PolySet& o = *(PolySet*)out;
+	std::vector<Poly::Polyhedron> pieces;
+	for (uint32_t i = 0; i < n_pieces; i++)
+		pieces.push_back(to_poly(verts, vert_off, ring_off, ring, i));
+	std::vector<VMACH::Polygon3D> cells;
+	for (uint32_t c = 0; c < n_cells; c++)
+		cells.push_back(planes_to_polygon(planes, plane_off[c], plane_off[c + 1]));
+
+	std::vector<std::vector<std::pair<uint32_t, Poly::Polyhedron>>> results(n_cells);
+	const auto t0 = std::chrono::steady_clock::now();
+	if (nthreads == 0)
+	{
+		for (uint32_t c = 0; c < n_cells; c++)
+			results[c] = fracture_task(cells[c], pieces);
+	}
+	else
+	{
+		dp::thread_pool pool(nthreads);
+		std::vector<std::future<std::vector<std::pair<uint32_t, Poly::Polyhedron>>>> futures;
+		for (uint32_t c = 0; c < n_cells; c++)
+			futures.push_back(pool.enqueue(fracture_task, std::cref(cells[c]), std::cref(pieces)));
+		for (uint32_t c = 0; c < n_cells; c++)
+			results[c] = futures[c].get();
+	}
+	o.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+	for (uint32_t c = 0; c < n_cells; c++)
+		for (auto& [piece, poly] : results[c])
+			append(o, poly, c, piece, with_moments != 0);
+}
+
+// Kdop::KdopContainer::Calc(const Poly::Polyhedron&) (Kdop.cpp:92-115) on raw vertices:
+// out_dist[2k] = {MinDist, MaxDist}, out_planes[8k] = {MinPlane, MaxPlane}, out_vtx[6k] = {MinVertex, MaxVertex}.
+void ref_kdop_calc_poly(const float* verts, uint32_t nv, const float* normals, uint32_t k, double* out_dist,
+						float* out_planes, float* out_vtx)
+{
+	std::vector<Vector3> nrm;
+	for (uint32_t i = 0; i < k; i++)
+		nrm.emplace_back(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+	Poly::Polyhedron p(nv);
+	for (uint32_t v = 0; v < nv; v++)
+		p[v].Position = Vector3(verts[4 * v], verts[4 * v + 1], verts[4 * v + 2]);
+	Kdop::KdopContainer kd(nrm);
+	kd.Calc(p);
+	for (uint32_t i = 0; i < k; i++)
+	{
+		const auto& e = kd.ElementVec[i];
+		out_dist[2 * i] = e.MinDist; out_dist[2 * i + 1] = e.MaxDist;
+		const float pl[8] = { e.MinPlane.x, e.MinPlane.y, e.MinPlane.z, e.MinPlane.w,
+							  e.MaxPlane.x, e.MaxPlane.y, e.MaxPlane.z, e.MaxPlane.w };
+		std::memcpy(out_planes + 8 * i, pl, sizeof(pl));
+		const float vx[6] = { e.MinVertex.x, e.MinVertex.y, e.MinVertex.z, e.MaxVertex.x, e.MaxVertex.y, e.MaxVertex.z };
+		std::memcpy(out_vtx + 6 * i, vx, sizeof(vx));
+	}
+}
+
+// Kdop::KdopContainer::Calc(vertices, maxAxisScale, planeGapInv) (Kdop.cpp:15-51), same outputs.
+void ref_kdop_calc_gap(const float* verts, uint32_t nv, const float* normals, uint32_t k, double maxAxisScale,
+					   float planeGapInv, double* out_dist, float* out_planes, float* out_vtx)
+{
+	std::vector<Vector3> nrm, vv;
+	for (uint32_t i = 0; i < k; i++)
+		nrm.emplace_back(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+	for (uint32_t v = 0; v < nv; v++)
+		vv.emplace_back(verts[4 * v], verts[4 * v + 1], verts[4 * v + 2]);
+	Kdop::KdopContainer kd(nrm);
+	kd.Calc(vv, maxAxisScale, planeGapInv);
+	for (uint32_t i = 0; i < k; i++)
+	{
+		const auto& e = kd.ElementVec[i];
+		out_dist[2 * i] = e.MinDist; out_dist[2 * i + 1] = e.MaxDist;
+		const float pl[8] = { e.MinPlane.x, e.MinPlane.y, e.MinPlane.z, e.MinPlane.w,
+							  e.MaxPlane.x, e.MaxPlane.y, e.MaxPlane.z, e.MaxPlane.w };
+		std::memcpy(out_planes + 8 * i, pl, sizeof(pl));
+		const float vx[6] = { e.MinVertex.x, e.MinVertex.y, e.MinVertex.z, e.MaxVertex.x, e.MaxVertex.y, e.MaxVertex.z };
+		std::memcpy(out_vtx + 6 * i, vx, sizeof(vx));
+	}
+}
+
+// Surtr::GenerateICHNormal (Surtr.cpp:1961-1974) over VMACH::ConvexHull (VMACH.cpp:869-1161).
+// Returns the number of normals written (<= cap).
+uint32_t ref_ich_normals(const float* verts, uint32_t nv, int limit, float* out, uint32_t cap)
+{
+	std::vector<Vector3> vv;
+	for (uint32_t v = 0; v < nv; v++)
+		vv.emplace_back(verts[4 * v], verts[4 * v + 1], verts[4 * v + 2]);
+	VMACH::ConvexHull ich(vv, (uint32_t)limit);
+	uint32_t n = 0;
+	for (const VMACH::ConvexHullFace& f : ich.GetFaces())
+	{
+		Vector3 normal = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+		normal.Normalize();
+		if (n < cap)
+		{
+			out[3 * n] = normal.x; out[3 * n + 1] = normal.y; out[3 * n + 2] = normal.z;
+		}
+		n++;
+	}
+	return n;
+}
+
+// Scalar helpers for the unit KATs (Poly.cpp:716-751).
+int ref_compare_plane_point(const float* plane, const float* p)
+{
+	return Poly::ComparePlanePoint(Plane(plane[0], plane[1], plane[2], plane[3]), Vector3(p[0], p[1], p[2]));
+}
+void ref_plane_line_intersection(const float* a, const float* b, const float* plane, float* out)
+{
+	const Vector3 r = Poly::PlaneLineIntersection(Vector3(a[0], a[1], a[2]), Vector3(b[0], b[1], b[2]),
+												   Plane(plane[0], plane[1], plane[2], plane[3]));
+	out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void ref_plane_from_points(const float* a, const float* b, const float* c, float* out)
+{
+	const Plane p(Vector3(a[0], a[1], a[2]), Vector3(b[0], b[1], b[2]), Vector3(c[0], c[1], c[2]));
+	out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = p.w;
+}
+void ref_plane_from_point_normal(const float* a, const float* n, float* out)
+{
+	const Plane p(Vector3(a[0], a[1], a[2]), Vector3(n[0], n[1], n[2]));
+	out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = p.w;
+}
+// VMACH::GetBoxPolygon (VMACH.cpp:1207-1226): the six outward planes of the unit cube.
+void ref_box_planes(float* out24)
+{
+	const VMACH::Polygon3D box = VMACH::GetBoxPolygon();
+	for (int f = 0; f < 6; f++)
+	{
+		out24[4 * f] = box.FaceVec[f].FacePlane.x; out24[4 * f + 1] = box.FaceVec[f].FacePlane.y;
+		out24[4 * f + 2] = box.FaceVec[f].FacePlane.z; out24[4 * f + 3] = box.FaceVec[f].FacePlane.w;
+	}
+}
+}
