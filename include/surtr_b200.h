@@ -1,0 +1,140 @@
+/* surtr_b200.h -- C ABI of the B200-native fracture engine (libsurtr_b200.so).
+ *
+ * Drop-in boundary for ONE path of W298/Surtr: the per-fracture-event cutting of an object's convex
+ * pieces by a Voronoi cell set.  The reference exposes no FFI for this path; the seams this ABI
+ * replaces are (all citations relative to the reference tree):
+ *
+ *   m_fractureTask (convex branch)      Inc/Surtr.h:272, Src/Surtr.cpp:1457-1468, 1497-1503
+ *   Surtr::ApplyFracture                Src/Surtr.cpp:2098-2149   (all cells x all pieces, bind order)
+ *   Surtr::SetExtract                   Src/Surtr.cpp:2151-2155   (face count per fragment)
+ *   Poly::ClipPolyhedron (both)         Inc/Poly.h:40-41, Src/Poly.cpp:265-566
+ *   Poly::ExtractFaces / Poly::Moments  Inc/Poly.h:36-37, Src/Poly.cpp:55-126
+ *   Kdop::KdopContainer::Calc           Inc/Kdop.h:35-37, Src/Kdop.cpp:15-115
+ *   Kdop::KdopContainer::ClipWithPolyhedron  Src/Kdop.cpp:166-179 (plane list [Min0,Max0,Min1,...] -> clip)
+ *   mass properties for InitCompound    Src/Surtr.cpp:2499-2529 (PhysX updateMassAndInertia, :2520)
+ *
+ * The calls are batch-granular (a per-pair call cannot feed a GPU): upload a piece set and a cell set
+ * (optionally many independent fracture events at once), run the event, read fragments back.
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the context owns device memory;
+ *   - every function returns a SURTR_* status, never throws; surtr_last_error() has the text;
+ *   - one context per host thread / GPU / stream; calls on one context are ordered on its stream;
+ *   - there is NO CPU fallback: without a usable CUDA device surtr_ctx_create fails with SURTR_ERR_NO_DEVICE.
+ *
+ * Flat polyhedron-set layout ("pieces", "fragments")
+ *   verts4    float[4*NV]   x y z 0, all polyhedra back to back
+ *   vert_off  u32[n+1]      first vertex of polyhedron i
+ *   ring_off  u32[NV+1]     first ring entry of (global) vertex v
+ *   ring      u16[NE]       neighbour rings (Poly::Vertex::NeighborVertexVec, Inc/Poly.h:18), indices LOCAL
+ *                           to the polyhedron, same cyclic order as the reference
+ * Cell-set layout
+ *   planes4   float[4*NP]   (nx ny nz d) = VMACH::PolygonFace::FacePlane (Inc/VMACH.h:21), outward normals
+ *   plane_off u32[n_cells+1]
+ *   cell_verts4 / cvert_off optional: every vertex of every face loop of the cell (duplicates allowed); used
+ *                           only for the broad-phase bounds.  NULL = cells are unbounded (no culling by cell).
+ * Events
+ *   ev_piece_off / ev_cell_off  u32[n_events+1]: event e cuts pieces [ev_piece_off[e], ev_piece_off[e+1]) by
+ *   cells [ev_cell_off[e], ev_cell_off[e+1]).  NULL = one event covering everything.
+ * Fragment order: event-major, then cell-major, then piece-minor -- the order in which ApplyFracture
+ *   consumes its futures (Src/Surtr.cpp:2133-2146); empty results are dropped exactly as there (:1467).
+ */
+#ifndef SURTR_B200_H
+#define SURTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURTR_OK 0
+#define SURTR_ERR_CUDA 1        /* a CUDA runtime call failed */
+#define SURTR_ERR_INVALID 2     /* bad argument / call order */
+#define SURTR_ERR_NO_DEVICE 3   /* no usable sm_100 device: the product path has no CPU fallback */
+#define SURTR_ERR_OVERFLOW 4    /* a (piece, cell) pair outgrew the largest on-chip clip tier */
+#define SURTR_ERR_NOMEM 5       /* device or pinned-host allocation failed */
+
+typedef struct surtr_ctx surtr_ctx;
+
+/* One record per non-empty fragment (64 bytes). */
+typedef struct surtr_fragment {
+    uint32_t cell;        /* global cell index (into the uploaded cell set) */
+    uint32_t piece;       /* global piece index (into the uploaded piece set) */
+    uint32_t vert_off;    /* first vertex in the fragment vertex array */
+    uint16_t n_verts;     /* Poly::Polyhedron::size() of the result */
+    uint16_t n_faces;     /* Poly::ExtractFaces(result)->size()  (Src/Poly.cpp:89-126) */
+    double volume;        /* Poly::Moments zerothMoment (Src/Poly.cpp:55-87) */
+    float centroid[3];    /* Poly::Moments firstMoment */
+    float inertia[6];     /* Ixx Iyy Izz Ixy Ixz Iyz about the centroid, unit density (replaces Surtr.cpp:2520) */
+    uint32_t n_ring;      /* sum of ring lengths (directed edges) */
+} surtr_fragment;
+
+typedef struct surtr_counts {
+    uint64_t n_pairs;       /* (piece, cell) pairs of all events */
+    uint64_t n_candidates;  /* pairs surviving the k-DOP broad phase */
+    uint64_t n_fragments;   /* non-empty clip results */
+    uint64_t n_verts;       /* total fragment vertices */
+    uint64_t n_ring;        /* total fragment ring entries */
+    uint64_t n_seq_cuts;    /* cuts that took the sequential in-plane/anomaly path (diagnostic) */
+    uint64_t n_tier2;       /* pairs re-run in the large on-chip tier (diagnostic) */
+} surtr_counts;
+
+/* Device-side view of the last event's fragments (pointers stay valid until the next event / upload). */
+typedef struct surtr_device_view {
+    const surtr_fragment* fragments;
+    const float* verts4;
+    const uint32_t* ring_off;   /* n_verts + 1 */
+    const uint16_t* ring;
+} surtr_device_view;
+
+/* --- context ------------------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t to order all work on (e.g. torch's current stream), or NULL for a private one. */
+int surtr_ctx_create(int device, void* stream, surtr_ctx** out);
+void surtr_ctx_destroy(surtr_ctx* ctx);
+const char* surtr_last_error(const surtr_ctx* ctx);   /* ctx may be NULL: last create error */
+const char* surtr_version(void);
+
+/* Broad-phase direction set: k in {3, 7, 13} (AABB, 14-DOP, 26-DOP).  Default 3. */
+int surtr_set_kdop_directions(surtr_ctx* ctx, int k);
+
+/* --- inputs (host -> device; replaces the per-task deep copies of Src/Poly.cpp:562, Surtr.cpp:2129-2131) - */
+int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,
+                        const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events);
+int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4,
+                       const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events);
+/* Recursive re-fracture: make the last event's fragments the piece set of the next event (device side, no
+ * copy through the host).  Every fragment becomes one piece; ev_piece_off (host, n_events+1) regroups them, or
+ * NULL to keep one event. */
+int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events);
+
+/* --- the hot path (replaces Surtr::ApplyFracture + m_fractureTask + SetExtract + mass properties) ------- */
+/* Asynchronous on the context stream: K1 k-DOP extents -> K2 broad phase + ordered compaction ->
+ * K3 one-warp-per-pair half-space clipping -> K4 fragment assembly with moments. */
+int surtr_fracture_event(surtr_ctx* ctx);
+/* Waits for the event; grows internal buffers and re-runs once if a capacity estimate was too small. */
+int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out);
+
+/* --- outputs ------------------------------------------------------------------------------------------ */
+/* Any pointer may be NULL to skip that array.  Sizes come from surtr_event_counts. */
+int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off,
+                             uint16_t* ring);
+int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out);
+
+/* --- k-DOP (replaces Kdop::KdopContainer::Calc(const Poly::Polyhedron&), Src/Kdop.cpp:92-115) ----------- */
+/* For each of k normals: dist[2i] = MinDist, dist[2i+1] = MaxDist (float values), arg[2i], arg[2i+1] = index of
+ * the first extremal vertex (strict </> as the reference), planes8[8i] = MinPlane, MaxPlane
+ * (Plane(v,-n), Plane(v,n)).  Host buffers in and out. */
+int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const float* normals3, uint32_t k,
+                    float* dist, int32_t* arg, float* planes8);
+
+/* Timing of the last surtr_fracture_event in milliseconds (CUDA events on the context stream). */
+int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms);
+/* Number of kernels the last surtr_fracture_event launched. */
+int surtr_last_event_launches(const surtr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,586 @@
+// kernels.cuh -- the four kernels of a fracture event (sm_100a) and their device-side records.
+//
+//   K1  kdop_extents_kernel      slab extents of every piece and every cell (warp-shuffle min/max)
+//   K2  broadphase_mask_kernel   piece x cell k-DOP overlap -> one ballot word per (cell, 32 pieces)
+//       compact_pairs_kernel     ordered compaction of the ballot words into the candidate pair list
+//   K3  clip_kernel<tier>        one warp per candidate pair: half-space clipping + moments (clip_warp.cuh)
+//   K4  assemble_kernel          ordered compaction of the non-empty results into the fragment arrays
+//       kdop_arg_kernel          Kdop::KdopContainer::Calc(Polyhedron) with first-extremal-vertex semantics
+#pragma once
+
+#include "clip_warp.cuh"
+#include "scan.cuh"
+#include "../../include/surtr_b200.h"
+
+namespace surtr
+{
+constexpr int KMAX = 13;
+__constant__ float c_dirs[KMAX][3] = {
+    { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 },                      // k = 3  : AABB
+    { 1, 1, 1 }, { 1, -1, 1 }, { 1, 1, -1 }, { 1, -1, -1 },     // k = 7  : 14-DOP
+    { 1, 1, 0 }, { 1, -1, 0 }, { 1, 0, 1 }, { 1, 0, -1 }, { 0, 1, 1 }, { 0, 1, -1 }   // k = 13 : 26-DOP
+};
+
+struct Ctl   // device-side counters of one event (zeroed before every event)
+{
+    unsigned long long n_cand;
+    unsigned long long n_frag, n_fverts, n_fring;
+    unsigned int n_ovf;         // pairs queued for the large tier
+    unsigned int n_tier2_fail;  // pairs that outgrew the large tier as well
+    unsigned int tile_a, tile_b;
+    unsigned int n_seq_cuts;
+    unsigned int pad;
+};
+
+struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
+{
+    uint32_t piece_begin, n_piece;
+    uint32_t cell_begin, n_cell;
+    uint32_t mask_base;   // index of the ballot word of (cell_begin, warp 0 of piece_begin)
+    uint32_t n_w;         // ballot words per cell row in this event
+};
+
+struct CandRec   // result of K3 for one candidate pair
+{
+    uint32_t nv;        // 0 = empty
+    uint32_t ne;        // ring entries
+    uint32_t nf;
+    uint32_t tier;      // 1 or 2 (ring entry width of the blob), 0 = pending in the large tier
+    double volume;
+    float centroid[3];
+    float inertia[6];
+    uint32_t pad;
+    unsigned long long blob;   // byte offset of the result blob in its tier's scratch
+};
+
+// ---------------------------------------------------------------------------------------------- K1
+template <int K>
+__global__ void kdop_extents_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vert_off,
+                                    uint32_t n_obj, float* __restrict__ ext, int unbounded)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t o = warp; o < n_obj; o += nwarps)
+    {
+        float mn[K], mx[K];
+#pragma unroll
+        for (int d = 0; d < K; d++) { mn[d] = 3.402823466e+38f; mx[d] = -3.402823466e+38f; }
+        if (unbounded)
+        {
+#pragma unroll
+            for (int d = 0; d < K; d++) { mn[d] = -__int_as_float(0x7f800000); mx[d] = __int_as_float(0x7f800000); }
+        }
+        else
+        {
+            const uint32_t v0 = vert_off[o], v1 = vert_off[o + 1];
+            for (uint32_t v = v0 + lane; v < v1; v += 32)
+            {
+                const float4 p = __ldg(verts + v);   // coalesced float4 stream
+#pragma unroll
+                for (int d = 0; d < K; d++)
+                {
+                    const float t = p.x * c_dirs[d][0] + p.y * c_dirs[d][1] + p.z * c_dirs[d][2];
+                    mn[d] = fminf(mn[d], t);
+                    mx[d] = fmaxf(mx[d], t);
+                }
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+                for (int d = 0; d < K; d++)
+                {
+                    mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], s));
+                    mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], s));
+                }
+        }
+        if (lane == 0)
+        {
+#pragma unroll
+            for (int d = 0; d < K; d++)
+            {
+                ext[(size_t)o * 2 * K + 2 * d] = mn[d];
+                ext[(size_t)o * 2 * K + 2 * d + 1] = mx[d];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- K2
+// Conservative separation test: a pair is culled only when some slab is separated by more than a few ulps of
+// the extents' magnitude, so no pair the clipper would keep is ever dropped (slivers).
+__device__ __forceinline__ bool slab_separated(float amin, float amax, float bmin, float bmax)
+{
+    const float scale = fmaxf(fmaxf(fabsf(amin), fabsf(amax)), fmaxf(fabsf(bmin), fabsf(bmax)));
+    const float tol = 4.0e-6f * scale;
+    return (amin - bmax > tol) || (bmin - amax > tol);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) broadphase_mask_kernel(const BpTile* __restrict__ tiles,
+                                                              const float* __restrict__ ext_p,
+                                                              const float* __restrict__ ext_c,
+                                                              unsigned int* __restrict__ masks)
+{
+    __shared__ float s_cell[32 * 2 * K];
+    const BpTile t = tiles[blockIdx.x];
+    for (int i = threadIdx.x; i < (int)t.n_cell * 2 * K; i += 256)
+        s_cell[i] = ext_c[(size_t)t.cell_begin * 2 * K + i];
+    float e[2 * K];
+    const bool valid = threadIdx.x < t.n_piece;
+    if (valid)
+    {
+#pragma unroll
+        for (int i = 0; i < 2 * K; i++) e[i] = ext_p[(size_t)(t.piece_begin + threadIdx.x) * 2 * K + i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp * 32 >= (int)t.n_piece) return;
+    for (int c = 0; c < (int)t.n_cell; c++)
+    {
+        bool hit = valid;
+        if (valid)
+        {
+#pragma unroll
+            for (int d = 0; d < K; d++)
+                hit = hit && !slab_separated(e[2 * d], e[2 * d + 1], s_cell[c * 2 * K + 2 * d], s_cell[c * 2 * K + 2 * d + 1]);
+        }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (lane == 0) masks[(size_t)t.mask_base + (size_t)c * t.n_w + warp] = m;
+    }
+}
+
+struct EventTables
+{
+    const uint32_t* ev_mask_base;   // n_events + 1
+    const uint32_t* ev_piece_off;   // n_events + 1
+    const uint32_t* ev_cell_off;    // n_events + 1
+    uint32_t n_events;
+};
+
+__device__ __forceinline__ void mask_to_pair_base(const EventTables& et, uint32_t m, uint32_t& cell, uint32_t& piece0)
+{
+    uint32_t e = 0;
+    if (et.n_events > 1)
+    {
+        uint32_t lo = 0, hi = et.n_events;   // last e with ev_mask_base[e] <= m
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (et.ev_mask_base[mid] <= m) lo = mid; else hi = mid;
+        }
+        e = lo;
+    }
+    const uint32_t local = m - et.ev_mask_base[e];
+    const uint32_t p0 = et.ev_piece_off[e];
+    const uint32_t n_w = (et.ev_piece_off[e + 1] - p0 + 31u) >> 5;
+    const uint32_t c_local = local / n_w;
+    cell = et.ev_cell_off[e] + c_local;
+    piece0 = p0 + ((local - c_local * n_w) << 5);
+}
+
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 4;   // ballot words per thread
+__global__ void __launch_bounds__(CP_THREADS) compact_pairs_kernel(const unsigned int* __restrict__ masks,
+                                                                    uint32_t n_masks, EventTables et,
+                                                                    ScanState<1> st, Ctl* ctl,
+                                                                    uint2* __restrict__ cand, uint64_t cap_cand)
+{
+    __shared__ int s_tile;
+    __shared__ unsigned int s_warp[CP_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctl->tile_a, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t m0 = (uint32_t)tile * (CP_THREADS * CP_ITEMS) + threadIdx.x * CP_ITEMS;
+    unsigned int w[CP_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; i++)
+    {
+        w[i] = (m0 + i < n_masks) ? masks[m0 + i] : 0u;
+        cnt += __popc(w[i]);
+    }
+    int wtot;
+    const int wex = warp_exscan(cnt, lane, wtot);
+    if (lane == 31) s_warp[warp] = (unsigned)wtot;
+    __syncthreads();
+    unsigned int block_ex = 0, block_tot = 0;
+#pragma unroll
+    for (int i = 0; i < CP_THREADS / 32; i++)
+    {
+        if (i < warp) block_ex += s_warp[i];
+        block_tot += s_warp[i];
+    }
+    if (warp == 0)
+    {
+        unsigned long long agg[1] = { block_tot }, ex[1];
+        tile_lookback<1>(st, tile, agg, ex, lane);
+        if (lane == 0)
+        {
+            s_excl = ex[0];
+            if ((uint32_t)(tile + 1) * (CP_THREADS * CP_ITEMS) >= n_masks) ctl->n_cand = ex[0] + block_tot;
+        }
+    }
+    __syncthreads();
+    unsigned long long out = s_excl + block_ex + wex;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; i++)
+    {
+        unsigned int m = w[i];
+        if (m)
+        {
+            uint32_t cell, piece0;
+            mask_to_pair_base(et, m0 + i, cell, piece0);
+            while (m)
+            {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (out < cap_cand) cand[out] = make_uint2(piece0 + b, cell);
+                out++;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- K3
+struct ClipArgs
+{
+    const float4* p_verts;
+    const uint32_t* p_vert_off;
+    const uint32_t* p_ring_off;
+    const uint16_t* p_ring;
+    const float4* c_planes;
+    const uint32_t* c_plane_off;
+    const uint2* cand;
+    uint64_t cap_cand;
+    CandRec* rec;
+    unsigned char* scratch;       // this tier's blob area
+    uint64_t slot_bytes;
+    uint32_t* ovf_list;           // tier 1 appends, tier 2 consumes
+    uint64_t cap_tier2;           // slots available to tier 2
+    Ctl* ctl;
+};
+
+template <class P>
+__host__ __device__ constexpr size_t blob_bytes()
+{
+    return (size_t)P::CAP * 16 + (size_t)P::CAP * 2 + (size_t)P::CAP * P::DMAX * sizeof(typename P::IdxT);
+}
+
+template <class P, int TIER, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    P& sp = reinterpret_cast<P*>(smem_raw)[threadIdx.x >> 5];
+    using IdxT = typename P::IdxT;
+    constexpr int DMAX = P::DMAX;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long n_items;
+    if (TIER == 1)
+    {
+        n_items = a.ctl->n_cand;
+        if (n_items > a.cap_cand) n_items = a.cap_cand;
+    }
+    else
+    {
+        n_items = a.ctl->n_ovf;
+    }
+    unsigned seq_cuts = 0;
+    for (unsigned long long it = gw; it < n_items; it += nwarps)
+    {
+        const uint32_t q = (TIER == 1) ? (uint32_t)it : a.ovf_list[it];
+        const uint2 pr = a.cand[q];
+        const uint32_t v0 = a.p_vert_off[pr.x];
+        int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+        bool too_big = nv > P::CAP;
+        if (!too_big)
+        {
+            for (int v = lane; v < nv; v += 32)
+            {
+                const float4 p = __ldg(a.p_verts + v0 + v);
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                const uint32_t r0 = a.p_ring_off[v0 + v];
+                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+                if (d > DMAX) { too_big = true; }
+                else
+                {
+                    sp.deg[v] = (uint8_t)d;
+                    for (int j = 0; j < d; j++) sp.ring[v * DMAX + j] = (IdxT)a.p_ring[r0 + j];
+                }
+            }
+        }
+        too_big = __ballot_sync(FULL, too_big) != 0u;
+        __syncwarp();
+        int status = CLIP_OVERFLOW;
+        if (!too_big)
+        {
+            const uint32_t pl0 = a.c_plane_off[pr.y];
+            const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+            status = clip_by_planes(sp, nv, a.c_planes + pl0, npl, lane, seq_cuts);
+        }
+        CandRec* rec = a.rec + q;
+        if (status != CLIP_OK)
+        {
+            if (lane == 0)
+            {
+                rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+                if (TIER == 1)
+                {
+                    const unsigned slot = atomicAdd(&a.ctl->n_ovf, 1u);
+                    a.ovf_list[slot] = q;   // capacity = cap_cand, cannot overflow
+                }
+                else
+                {
+                    atomicAdd(&a.ctl->n_tier2_fail, 1u);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        if (nv == 0)
+        {
+            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = TIER; }
+            __syncwarp();
+            continue;
+        }
+        Moments mo;
+        fragment_moments(sp, nv, lane, mo);
+
+        // result blob: float4 verts[CAP] | u16 ring_start[CAP] | IdxT ring[packed]
+        unsigned long long blob = (TIER == 1) ? (unsigned long long)q * a.slot_bytes : (unsigned long long)it * a.slot_bytes;
+        const bool room = (TIER == 1) || it < a.cap_tier2;
+        int ne = 0;
+        {
+            unsigned char* b = a.scratch + blob;
+            float4* bv = reinterpret_cast<float4*>(b);
+            uint16_t* bo = reinterpret_cast<uint16_t*>(b + (size_t)P::CAP * 16);
+            IdxT* br = reinterpret_cast<IdxT*>(b + (size_t)P::CAP * 18);
+            for (int h = 0; h * 32 < nv; h++)
+            {
+                const int v = lane + 32 * h;
+                const int d = v < nv ? sp.deg[v] : 0;
+                int tot;
+                const int off = ne + warp_exscan(d, lane, tot);
+                ne += tot;
+                if (v < nv && room)
+                {
+                    bv[v] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+                    bo[v] = (uint16_t)off;
+                    for (int j = 0; j < d; j++) br[off + j] = sp.ring[v * DMAX + j];
+                }
+            }
+        }
+        if (lane == 0)
+        {
+            rec->nv = room ? (uint32_t)nv : 0u;
+            rec->ne = (uint32_t)ne;
+            rec->nf = (uint32_t)mo.n_faces;
+            rec->tier = TIER;
+            rec->volume = mo.volume;
+            rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
+#pragma unroll
+            for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
+            rec->blob = blob;
+            if (!room) atomicAdd(&a.ctl->n_tier2_fail, 1u);
+        }
+        __syncwarp();
+    }
+    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+}
+
+// ---------------------------------------------------------------------------------------------- K4
+struct AssembleArgs
+{
+    const uint2* cand;
+    const CandRec* rec;
+    uint64_t cap_cand;
+    const unsigned char* scratch1;
+    const unsigned char* scratch2;
+    int cap1, cap2;             // vertex capacity (blob layout) of tier 1 / tier 2
+    ScanState<3> st;
+    Ctl* ctl;
+    surtr_fragment* f_rec;
+    float4* f_verts;
+    uint32_t* f_ring_off;
+    uint16_t* f_ring;
+    uint64_t cap_frag, cap_fverts, cap_fring;
+};
+
+constexpr int AS_THREADS = 256;
+__global__ void __launch_bounds__(AS_THREADS) assemble_kernel(AssembleArgs a)
+{
+    __shared__ int s_tile;
+    __shared__ unsigned int s_w[AS_THREADS / 32][3];
+    __shared__ unsigned long long s_excl[3];
+    unsigned long long n_cand = a.ctl->n_cand;
+    if (n_cand > a.cap_cand) n_cand = a.cap_cand;
+    const unsigned long long n_tiles = (n_cand + AS_THREADS - 1) / AS_THREADS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&a.ctl->tile_b, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if ((unsigned long long)tile >= n_tiles) break;
+        const unsigned long long q = (unsigned long long)tile * AS_THREADS + threadIdx.x;
+        uint32_t nv = 0, ne = 0;
+        if (q < n_cand) { nv = a.rec[q].nv; ne = a.rec[q].ne; }
+        const int has = nv > 0;
+        int t0, t1, t2;
+        const int e0 = warp_exscan(has, lane, t0);
+        const int e1 = warp_exscan((int)nv, lane, t1);
+        const int e2 = warp_exscan((int)ne, lane, t2);
+        if (lane == 31) { s_w[warp][0] = t0; s_w[warp][1] = t1; s_w[warp][2] = t2; }
+        __syncthreads();
+        unsigned int bex[3] = { 0, 0, 0 }, btot[3] = { 0, 0, 0 };
+#pragma unroll
+        for (int i = 0; i < AS_THREADS / 32; i++)
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                if (i < warp) bex[k] += s_w[i][k];
+                btot[k] += s_w[i][k];
+            }
+        if (warp == 0)
+        {
+            unsigned long long agg[3] = { btot[0], btot[1], btot[2] }, ex[3];
+            tile_lookback<3>(a.st, tile, agg, ex, lane);
+            if (lane == 0)
+            {
+                s_excl[0] = ex[0]; s_excl[1] = ex[1]; s_excl[2] = ex[2];
+                if ((unsigned long long)tile + 1 == n_tiles)
+                {
+                    a.ctl->n_frag = ex[0] + btot[0];
+                    a.ctl->n_fverts = ex[1] + btot[1];
+                    a.ctl->n_fring = ex[2] + btot[2];
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long fi = s_excl[0] + bex[0] + e0;
+        const unsigned long long vb = s_excl[1] + bex[1] + e1;
+        const unsigned long long rb = s_excl[2] + bex[2] + e2;
+
+        // each warp gathers its 32 candidates one after the other, all lanes copying
+        const unsigned live = __ballot_sync(FULL, has);
+        unsigned todo = live;
+        while (todo)
+        {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned long long cq = __shfl_sync(FULL, q, src);
+            const unsigned long long cfi = __shfl_sync(FULL, fi, src);
+            const unsigned long long cvb = __shfl_sync(FULL, vb, src);
+            const unsigned long long crb = __shfl_sync(FULL, rb, src);
+            const int cnv = __shfl_sync(FULL, (int)nv, src);
+            const int cne = __shfl_sync(FULL, (int)ne, src);
+            if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) continue;
+            const CandRec* r = a.rec + cq;
+            const int tier = r->tier;
+            const int cap = tier == 1 ? a.cap1 : a.cap2;
+            const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
+            const float4* bv = reinterpret_cast<const float4*>(b);
+            const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
+            for (int v = lane; v < cnv; v += 32)
+            {
+                a.f_verts[cvb + v] = bv[v];
+                a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+            }
+            if (tier == 1)
+            {
+                const uint8_t* br = b + (size_t)cap * 18;
+                for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+            }
+            else
+            {
+                const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
+                for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+            }
+            if (lane == 0)
+            {
+                const uint2 pr = a.cand[cq];
+                surtr_fragment f;
+                f.cell = pr.y; f.piece = pr.x;
+                f.vert_off = (uint32_t)cvb;
+                f.n_verts = (uint16_t)cnv;
+                f.n_faces = (uint16_t)r->nf;
+                f.volume = r->volume;
+                f.centroid[0] = r->centroid[0]; f.centroid[1] = r->centroid[1]; f.centroid[2] = r->centroid[2];
+#pragma unroll
+                for (int k = 0; k < 6; k++) f.inertia[k] = r->inertia[k];
+                f.n_ring = (uint32_t)cne;
+                a.f_rec[cfi] = f;
+            }
+        }
+    }
+}
+
+// closes the per-vertex ring offsets (ring_off[n_fverts] = n_fring) and the piece tables used by recursion
+__global__ void finish_offsets_kernel(const Ctl* ctl, uint32_t* f_ring_off, uint64_t cap_fverts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && ctl->n_fverts <= cap_fverts)
+        f_ring_off[ctl->n_fverts] = (uint32_t)ctl->n_fring;
+}
+
+// fragment records -> piece vert_off table (surtr_fragments_to_pieces)
+__global__ void fragments_vert_off_kernel(const surtr_fragment* f, uint32_t n, uint32_t n_verts, uint32_t* vert_off)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vert_off[i] = f[i].vert_off;
+    if (i == n) vert_off[n] = n_verts;
+}
+
+// ------------------------------------------------------------------------------- Kdop::Calc(Polyhedron)
+// One block per normal.  t = Dot(v, n) in the reference's float op order; strict < / > so the FIRST extremal
+// vertex wins (Kdop.cpp:98-112); ties across threads are broken towards the lower vertex index.
+__global__ void __launch_bounds__(256) kdop_arg_kernel(const float4* __restrict__ verts, uint32_t nv,
+                                                       const float* __restrict__ normals, float* __restrict__ dist,
+                                                       int32_t* __restrict__ arg, float4* __restrict__ planes)
+{
+    __shared__ float s_min[256], s_max[256];
+    __shared__ int s_imin[256], s_imax[256];
+    const int e = blockIdx.x;
+    const float nx = normals[3 * e], ny = normals[3 * e + 1], nz = normals[3 * e + 2];
+    float mn = 0.f, mx = 0.f;
+    int imin = -1, imax = -1;
+    for (uint32_t v = threadIdx.x; v < nv; v += 256)
+    {
+        const float4 p = __ldg(verts + v);
+        const float t = dot3(p.x, p.y, p.z, nx, ny, nz);
+        if (imin < 0 || mn > t) { mn = t; imin = (int)v; }
+        if (imax < 0 || mx < t) { mx = t; imax = (int)v; }
+    }
+    s_min[threadIdx.x] = mn; s_max[threadIdx.x] = mx; s_imin[threadIdx.x] = imin; s_imax[threadIdx.x] = imax;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1)
+    {
+        if ((int)threadIdx.x < s)
+        {
+            const int o = threadIdx.x + s;
+            const int bi = s_imin[o], ai = s_imin[threadIdx.x];
+            if (bi >= 0 && (ai < 0 || s_min[o] < s_min[threadIdx.x] || (s_min[o] == s_min[threadIdx.x] && bi < ai)))
+            { s_min[threadIdx.x] = s_min[o]; s_imin[threadIdx.x] = bi; }
+            const int bj = s_imax[o], aj = s_imax[threadIdx.x];
+            if (bj >= 0 && (aj < 0 || s_max[o] > s_max[threadIdx.x] || (s_max[o] == s_max[threadIdx.x] && bj < aj)))
+            { s_max[threadIdx.x] = s_max[o]; s_imax[threadIdx.x] = bj; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        dist[2 * e] = s_min[0]; dist[2 * e + 1] = s_max[0];
+        arg[2 * e] = s_imin[0]; arg[2 * e + 1] = s_imax[0];
+        if (s_imin[0] >= 0)
+        {
+            const float4 a = verts[s_imin[0]], b = verts[s_imax[0]];
+            planes[2 * e] = plane_from_point_normal(a.x, a.y, a.z, -nx, -ny, -nz);   // Plane(vert, -Normal)
+            planes[2 * e + 1] = plane_from_point_normal(b.x, b.y, b.z, nx, ny, nz);  // Plane(vert, Normal)
+        }
+    }
+}
+} // namespace surtr

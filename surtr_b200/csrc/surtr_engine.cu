@@ -1,0 +1,614 @@
+// surtr_engine.cu -- context, buffer management and the C ABI of libsurtr_b200.so (include/surtr_b200.h).
+//
+// Host side of the drop-in boundary: it owns device memory, orders K1 -> K2 -> K3 -> K4 on one stream with no
+// host round trip inside an event, and re-runs an event once with larger buffers when a capacity estimate was
+// too small.  There is no CPU implementation of any step behind this ABI.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace surtr;
+
+namespace
+{
+using Tier1 = WarpPoly<64, 8, uint8_t>;
+using Tier2 = WarpPoly<256, 16, uint16_t>;
+constexpr int T1_WARPS = 4;
+constexpr int T2_WARPS = 2;
+
+std::string g_create_error;
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+} // namespace
+
+struct surtr_ctx
+{
+    int device = 0;
+    int num_sm = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int kdirs = 3;
+
+    // inputs
+    uint32_t n_pieces = 0, n_cells = 0, n_events_p = 0, n_events_c = 0;
+    uint64_t n_pverts = 0, n_pring = 0, n_planes = 0, n_cverts = 0;
+    bool cells_bounded = false, have_pieces = false, have_cells = false, tables_dirty = true;
+    DevBuf p_verts, p_vert_off, p_ring_off, p_ring;
+    DevBuf c_planes, c_plane_off, c_verts, c_vert_off;
+    std::vector<uint32_t> h_ev_piece_off, h_ev_cell_off;
+
+    // derived tables
+    DevBuf d_tiles, d_ev_mask_base, d_ev_piece_off, d_ev_cell_off;
+    uint32_t n_tiles = 0, n_masks = 0;
+    uint64_t n_pairs = 0;
+
+    // work buffers
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl;
+    uint64_t cap_cand = 0, cap_tier2 = 0;
+    uint32_t n_tiles_a = 0, n_tiles_b = 0;
+
+    // outputs
+    DevBuf f_rec, f_verts, f_ring_off, f_ring;
+    uint64_t cap_frag = 0, cap_fverts = 0, cap_fring = 0;
+
+    Ctl* h_ctl = nullptr;   // pinned
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    int launches = 0;
+    bool event_launched = false, event_resolved = false;
+    surtr_counts last{};
+};
+
+namespace
+{
+int fail(surtr_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do                                                                                                 \
+    {                                                                                                  \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SURTR_ERR_NOMEM : SURTR_ERR_CUDA,       \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+    } while (0)
+
+size_t ctl_bytes(const surtr_ctx* c)
+{
+    return sizeof(Ctl) + sizeof(unsigned int) * ((size_t)c->n_tiles_a + c->n_tiles_b + 2);
+}
+
+int rebuild_tables(surtr_ctx* ctx)
+{
+    if (!ctx->tables_dirty) return SURTR_OK;
+    if (ctx->n_events_p != ctx->n_events_c)
+        return fail(ctx, SURTR_ERR_INVALID, "pieces and cells were uploaded with different event counts");
+    const uint32_t ne = ctx->n_events_p;
+    std::vector<BpTile> tiles;
+    std::vector<uint32_t> mask_base(ne + 1, 0);
+    uint64_t masks = 0, pairs = 0;
+    for (uint32_t e = 0; e < ne; e++)
+    {
+        mask_base[e] = (uint32_t)masks;
+        const uint32_t p0 = ctx->h_ev_piece_off[e], p1 = ctx->h_ev_piece_off[e + 1];
+        const uint32_t c0 = ctx->h_ev_cell_off[e], c1 = ctx->h_ev_cell_off[e + 1];
+        const uint32_t np = p1 - p0, nc = c1 - c0;
+        const uint32_t n_w = (np + 31) / 32;
+        pairs += (uint64_t)np * nc;
+        for (uint32_t cb = 0; cb < nc; cb += 32)
+            for (uint32_t pb = 0; pb < np; pb += 256)
+            {
+                BpTile t;
+                t.piece_begin = p0 + pb;
+                t.n_piece = std::min(256u, np - pb);
+                t.cell_begin = c0 + cb;
+                t.n_cell = std::min(32u, nc - cb);
+                t.mask_base = (uint32_t)(masks + (uint64_t)cb * n_w + pb / 32);
+                t.n_w = n_w;
+                tiles.push_back(t);
+            }
+        masks += (uint64_t)nc * n_w;
+        if (masks > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "batch too large: split the events");
+    }
+    mask_base[ne] = (uint32_t)masks;
+    ctx->n_tiles = (uint32_t)tiles.size();
+    ctx->n_masks = (uint32_t)masks;
+    ctx->n_pairs = pairs;
+    CK(ctx->d_tiles.reserve(sizeof(BpTile) * std::max<size_t>(1, tiles.size())));
+    CK(ctx->d_ev_mask_base.reserve(4 * (ne + 1)));
+    CK(ctx->d_ev_piece_off.reserve(4 * (ne + 1)));
+    CK(ctx->d_ev_cell_off.reserve(4 * (ne + 1)));
+    // the tables are tiny; synchronous copies keep the std::vectors' lifetime trivial
+    CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(BpTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ev_mask_base.p, mask_base.data(), 4 * (ne + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ev_piece_off.p, ctx->h_ev_piece_off.data(), 4 * (ne + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ev_cell_off.p, ctx->h_ev_cell_off.data(), 4 * (ne + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tables_dirty = false;
+    // first capacity estimates (grown on demand by surtr_event_counts)
+    const uint64_t est = std::min<uint64_t>(pairs, std::max<uint64_t>(4096, 8ull * (ctx->n_pieces + ctx->n_cells)));
+    ctx->cap_cand = std::max(ctx->cap_cand, est);
+    return SURTR_OK;
+}
+
+int ensure_capacity(surtr_ctx* ctx)
+{
+    const int K = ctx->kdirs;
+    ctx->cap_frag = std::max(ctx->cap_frag, ctx->cap_cand);
+    ctx->cap_fverts = std::max(ctx->cap_fverts, ctx->cap_frag * 24);
+    ctx->cap_fring = std::max(ctx->cap_fring, ctx->cap_fverts * 3 + 1024);
+    ctx->cap_tier2 = std::max<uint64_t>(ctx->cap_tier2, 16);
+    ctx->n_tiles_a = (ctx->n_masks + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS);
+    ctx->n_tiles_b = (uint32_t)((ctx->cap_cand + AS_THREADS - 1) / AS_THREADS);
+    CK(ctx->ext_p.reserve(sizeof(float) * 2 * K * std::max(1u, ctx->n_pieces)));
+    CK(ctx->ext_c.reserve(sizeof(float) * 2 * K * std::max(1u, ctx->n_cells)));
+    CK(ctx->masks.reserve(4 * std::max<size_t>(1, ctx->n_masks)));
+    CK(ctx->cand.reserve(sizeof(uint2) * ctx->cap_cand));
+    CK(ctx->cand_rec.reserve(sizeof(CandRec) * ctx->cap_cand));
+    CK(ctx->ovf_list.reserve(4 * ctx->cap_cand));
+    CK(ctx->scratch1.reserve(blob_bytes<Tier1>() * ctx->cap_cand));
+    CK(ctx->scratch2.reserve(blob_bytes<Tier2>() * ctx->cap_tier2));
+    // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
+    const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
+    CK(ctx->ctl.reserve(zero_bytes + 8 * 2 * ((size_t)ctx->n_tiles_a + 1) + 8 * 6 * ((size_t)ctx->n_tiles_b + 1)));
+    CK(ctx->f_rec.reserve(sizeof(surtr_fragment) * ctx->cap_frag));
+    CK(ctx->f_verts.reserve(16 * ctx->cap_fverts));
+    CK(ctx->f_ring_off.reserve(4 * (ctx->cap_fverts + 1)));
+    CK(ctx->f_ring.reserve(2 * ctx->cap_fring));
+    return SURTR_OK;
+}
+
+template <int K>
+void launch_extents(surtr_ctx* ctx)
+{
+    const int threads = 256;
+    if (ctx->n_pieces)
+    {
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)ctx->n_pieces * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
+        kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->p_verts.as<float4>(), ctx->p_vert_off.as<uint32_t>(),
+                                                                    ctx->n_pieces, ctx->ext_p.as<float>(), 0);
+        ctx->launches++;
+    }
+    if (ctx->n_cells)
+    {
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)ctx->n_cells * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
+        kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->c_verts.as<float4>(), ctx->c_vert_off.as<uint32_t>(),
+                                                                    ctx->n_cells, ctx->ext_c.as<float>(),
+                                                                    ctx->cells_bounded ? 0 : 1);
+        ctx->launches++;
+    }
+}
+
+template <int K>
+void launch_masks(surtr_ctx* ctx)
+{
+    if (!ctx->n_tiles) return;
+    broadphase_mask_kernel<K><<<ctx->n_tiles, 256, 0, ctx->stream>>>(ctx->d_tiles.as<BpTile>(), ctx->ext_p.as<float>(),
+                                                                     ctx->ext_c.as<float>(), ctx->masks.as<unsigned int>());
+    ctx->launches++;
+}
+
+int launch_event(surtr_ctx* ctx)
+{
+    int rc = rebuild_tables(ctx);
+    if (rc) return rc;
+    rc = ensure_capacity(ctx);
+    if (rc) return rc;
+    ctx->launches = 0;
+
+    unsigned char* ctl_base = ctx->ctl.as<unsigned char>();
+    const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
+    Ctl* d_ctl = reinterpret_cast<Ctl*>(ctl_base);
+    unsigned int* flags_a = reinterpret_cast<unsigned int*>(ctl_base + sizeof(Ctl));
+    unsigned int* flags_b = flags_a + ctx->n_tiles_a + 1;
+    unsigned long long* agg_a = reinterpret_cast<unsigned long long*>(ctl_base + zero_bytes);
+    unsigned long long* inc_a = agg_a + ctx->n_tiles_a + 1;
+    unsigned long long* agg_b = inc_a + ctx->n_tiles_a + 1;
+    unsigned long long* inc_b = agg_b + 3 * ((size_t)ctx->n_tiles_b + 1);
+
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
+
+    // K1
+    switch (ctx->kdirs)
+    {
+    case 3: launch_extents<3>(ctx); launch_masks<3>(ctx); break;
+    case 7: launch_extents<7>(ctx); launch_masks<7>(ctx); break;
+    default: launch_extents<13>(ctx); launch_masks<13>(ctx); break;
+    }
+    // K2 compaction
+    if (ctx->n_tiles_a)
+    {
+        EventTables et{ ctx->d_ev_mask_base.as<uint32_t>(), ctx->d_ev_piece_off.as<uint32_t>(),
+                        ctx->d_ev_cell_off.as<uint32_t>(), ctx->n_events_p };
+        ScanState<1> st{ flags_a, agg_a, inc_a };
+        compact_pairs_kernel<<<ctx->n_tiles_a, CP_THREADS, 0, ctx->stream>>>(ctx->masks.as<unsigned int>(), ctx->n_masks, et, st,
+                                                                             d_ctl, ctx->cand.as<uint2>(), ctx->cap_cand);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    // K3
+    ClipArgs ca;
+    ca.p_verts = ctx->p_verts.as<float4>();
+    ca.p_vert_off = ctx->p_vert_off.as<uint32_t>();
+    ca.p_ring_off = ctx->p_ring_off.as<uint32_t>();
+    ca.p_ring = ctx->p_ring.as<uint16_t>();
+    ca.c_planes = ctx->c_planes.as<float4>();
+    ca.c_plane_off = ctx->c_plane_off.as<uint32_t>();
+    ca.cand = ctx->cand.as<uint2>();
+    ca.cap_cand = ctx->cap_cand;
+    ca.rec = ctx->cand_rec.as<CandRec>();
+    ca.ovf_list = ctx->ovf_list.as<uint32_t>();
+    ca.cap_tier2 = ctx->cap_tier2;
+    ca.ctl = d_ctl;
+    {
+        ca.scratch = ctx->scratch1.as<unsigned char>();
+        ca.slot_bytes = blob_bytes<Tier1>();
+        const size_t smem = sizeof(Tier1) * T1_WARPS;
+        const uint64_t want = (ctx->cap_cand + T1_WARPS - 1) / T1_WARPS;
+        const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->num_sm * 14));
+        clip_kernel<Tier1, 1, T1_WARPS><<<blocks, T1_WARPS * 32, smem, ctx->stream>>>(ca);
+        ctx->launches++;
+    }
+    {
+        ca.scratch = ctx->scratch2.as<unsigned char>();
+        ca.slot_bytes = blob_bytes<Tier2>();
+        const size_t smem = sizeof(Tier2) * T2_WARPS;
+        clip_kernel<Tier2, 2, T2_WARPS><<<ctx->num_sm, T2_WARPS * 32, smem, ctx->stream>>>(ca);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    // K4
+    {
+        AssembleArgs aa;
+        aa.cand = ctx->cand.as<uint2>();
+        aa.rec = ctx->cand_rec.as<CandRec>();
+        aa.cap_cand = ctx->cap_cand;
+        aa.scratch1 = ctx->scratch1.as<unsigned char>();
+        aa.scratch2 = ctx->scratch2.as<unsigned char>();
+        aa.cap1 = Tier1::CAP;
+        aa.cap2 = Tier2::CAP;
+        aa.st = ScanState<3>{ flags_b, agg_b, inc_b };
+        aa.ctl = d_ctl;
+        aa.f_rec = ctx->f_rec.as<surtr_fragment>();
+        aa.f_verts = ctx->f_verts.as<float4>();
+        aa.f_ring_off = ctx->f_ring_off.as<uint32_t>();
+        aa.f_ring = ctx->f_ring.as<uint16_t>();
+        aa.cap_frag = ctx->cap_frag;
+        aa.cap_fverts = ctx->cap_fverts;
+        aa.cap_fring = ctx->cap_fring;
+        const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
+        assemble_kernel<<<blocks, AS_THREADS, 0, ctx->stream>>>(aa);
+        ctx->launches++;
+        finish_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_ctl, ctx->f_ring_off.as<uint32_t>(), ctx->cap_fverts);
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaGetLastError());
+    ctx->event_launched = true;
+    ctx->event_resolved = false;
+    return SURTR_OK;
+}
+
+int resolve_event(surtr_ctx* ctx)
+{
+    if (!ctx->event_launched) return fail(ctx, SURTR_ERR_INVALID, "no fracture event has been launched");
+    if (ctx->event_resolved) return SURTR_OK;
+    for (int attempt = 0; attempt < 6; attempt++)
+    {
+        CK(cudaStreamSynchronize(ctx->stream));
+        const Ctl c = *ctx->h_ctl;
+        bool grow = false;
+        if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
+        if (c.n_ovf > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf + c.n_ovf / 4 + 16; grow = true; }
+        if (!grow)
+        {
+            if (c.n_frag > ctx->cap_frag) { ctx->cap_frag = c.n_frag + c.n_frag / 8 + 64; grow = true; }
+            if (c.n_fverts > ctx->cap_fverts) { ctx->cap_fverts = c.n_fverts + c.n_fverts / 8 + 64; grow = true; }
+            if (c.n_fring > ctx->cap_fring) { ctx->cap_fring = c.n_fring + c.n_fring / 8 + 64; grow = true; }
+        }
+        if (!grow)
+        {
+            if (c.n_tier2_fail)
+                return fail(ctx, SURTR_ERR_OVERFLOW,
+                            std::to_string(c.n_tier2_fail) + " pair(s) exceed the largest on-chip clip tier (256 vertices, ring degree 16)");
+            ctx->last.n_pairs = ctx->n_pairs;
+            ctx->last.n_candidates = c.n_cand;
+            ctx->last.n_fragments = c.n_frag;
+            ctx->last.n_verts = c.n_fverts;
+            ctx->last.n_ring = c.n_fring;
+            ctx->last.n_seq_cuts = c.n_seq_cuts;
+            ctx->last.n_tier2 = c.n_ovf;
+            ctx->event_resolved = true;
+            return SURTR_OK;
+        }
+        const int rc = launch_event(ctx);
+        if (rc) return rc;
+    }
+    return fail(ctx, SURTR_ERR_NOMEM, "buffers still too small after repeated growth");
+}
+
+int upload(surtr_ctx* ctx, DevBuf& b, const void* src, size_t bytes)
+{
+    CK(b.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SURTR_OK;
+}
+} // namespace
+
+extern "C"
+{
+const char* surtr_version(void) { return "surtr_b200 0.1 (sm_100a)"; }
+
+const char* surtr_last_error(const surtr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
+{
+    surtr_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, SURTR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SURTR_ERR_NO_DEVICE,
+                    std::string("no CUDA device (") + cudaGetErrorString(e) + "): this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, SURTR_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, SURTR_ERR_NO_DEVICE, "device is not compute capability 10.x: kernels are built for sm_100a only");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SURTR_ERR_CUDA, "cudaSetDevice failed");
+    ctx = new surtr_ctx();
+    ctx->device = device;
+    ctx->num_sm = prop.multiProcessorCount;
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else
+    {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+        {
+            delete ctx;
+            return fail(nullptr, SURTR_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        ctx->own_stream = true;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (cudaMallocHost(&ctx->h_ctl, sizeof(Ctl)) != cudaSuccess)
+    {
+        delete ctx;
+        return fail(nullptr, SURTR_ERR_NOMEM, "cudaMallocHost failed");
+    }
+    cudaFuncSetAttribute(clip_kernel<Tier2, 2, T2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(Tier2) * T2_WARPS));
+    *out = ctx;
+    return SURTR_OK;
+}
+
+void surtr_ctx_destroy(surtr_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
+                      &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
+                      &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->f_ring_off, &ctx->f_ring };
+    for (DevBuf* b : all) b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int surtr_set_kdop_directions(surtr_ctx* ctx, int k)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (k != 3 && k != 7 && k != 13) return fail(ctx, SURTR_ERR_INVALID, "k must be 3, 7 or 13");
+    ctx->kdirs = k;
+    return SURTR_OK;
+}
+
+int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,
+                        const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!vert_off || (n_pieces && (!verts4 || !ring_off || !ring))) return fail(ctx, SURTR_ERR_INVALID, "NULL piece array");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nv = vert_off[n_pieces];
+    const uint64_t ne = nv ? ring_off[nv] : 0;
+    int rc;
+    if ((rc = upload(ctx, ctx->p_verts, verts4, 16 * nv))) return rc;
+    if ((rc = upload(ctx, ctx->p_vert_off, vert_off, 4 * ((size_t)n_pieces + 1)))) return rc;
+    if ((rc = upload(ctx, ctx->p_ring_off, ring_off, 4 * (nv + 1)))) return rc;
+    if ((rc = upload(ctx, ctx->p_ring, ring, 2 * ne))) return rc;
+    ctx->n_pieces = n_pieces;
+    ctx->n_pverts = nv;
+    ctx->n_pring = ne;
+    if (ev_piece_off && n_events) ctx->h_ev_piece_off.assign(ev_piece_off, ev_piece_off + n_events + 1);
+    else ctx->h_ev_piece_off = { 0u, n_pieces };
+    ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
+    if (ctx->h_ev_piece_off.back() != n_pieces) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at n_pieces");
+    ctx->have_pieces = true;
+    ctx->tables_dirty = true;
+    ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4,
+                       const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!plane_off || (n_cells && !planes4)) return fail(ctx, SURTR_ERR_INVALID, "NULL cell array");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t np = plane_off[n_cells];
+    int rc;
+    if ((rc = upload(ctx, ctx->c_planes, planes4, 16 * np))) return rc;
+    if ((rc = upload(ctx, ctx->c_plane_off, plane_off, 4 * ((size_t)n_cells + 1)))) return rc;
+    ctx->cells_bounded = cell_verts4 && cvert_off;
+    if (ctx->cells_bounded)
+    {
+        const uint64_t ncv = cvert_off[n_cells];
+        if ((rc = upload(ctx, ctx->c_verts, cell_verts4, 16 * ncv))) return rc;
+        if ((rc = upload(ctx, ctx->c_vert_off, cvert_off, 4 * ((size_t)n_cells + 1)))) return rc;
+        ctx->n_cverts = ncv;
+    }
+    ctx->n_cells = n_cells;
+    ctx->n_planes = np;
+    if (ev_cell_off && n_events) ctx->h_ev_cell_off.assign(ev_cell_off, ev_cell_off + n_events + 1);
+    else ctx->h_ev_cell_off = { 0u, n_cells };
+    ctx->n_events_c = (uint32_t)ctx->h_ev_cell_off.size() - 1;
+    if (ctx->h_ev_cell_off.back() != n_cells) return fail(ctx, SURTR_ERR_INVALID, "ev_cell_off does not end at n_cells");
+    ctx->have_cells = true;
+    ctx->tables_dirty = true;
+    ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_fracture_event(surtr_ctx* ctx)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!ctx->have_pieces || !ctx->have_cells) return fail(ctx, SURTR_ERR_INVALID, "upload pieces and cells first");
+    CK(cudaSetDevice(ctx->device));
+    return launch_event(ctx);
+}
+
+int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    if (out) *out = ctx->last;
+    return SURTR_OK;
+}
+
+int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off, uint16_t* ring)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    const surtr_counts& c = ctx->last;
+    if (fragments && c.n_fragments)
+        CK(cudaMemcpyAsync(fragments, ctx->f_rec.p, sizeof(surtr_fragment) * c.n_fragments, cudaMemcpyDeviceToHost, ctx->stream));
+    if (verts4 && c.n_verts)
+        CK(cudaMemcpyAsync(verts4, ctx->f_verts.p, 16 * c.n_verts, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ring_off)
+        CK(cudaMemcpyAsync(ring_off, ctx->f_ring_off.p, 4 * (c.n_verts + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ring && c.n_ring)
+        CK(cudaMemcpyAsync(ring, ctx->f_ring.p, 2 * c.n_ring, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SURTR_OK;
+}
+
+int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out)
+{
+    if (!ctx || !out) return SURTR_ERR_INVALID;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    out->fragments = ctx->f_rec.as<surtr_fragment>();
+    out->verts4 = ctx->f_verts.as<float>();
+    out->ring_off = ctx->f_ring_off.as<uint32_t>();
+    out->ring = ctx->f_ring.as<uint16_t>();
+    return SURTR_OK;
+}
+
+int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    const surtr_counts c = ctx->last;
+    if (c.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
+    const uint32_t n = (uint32_t)c.n_fragments;
+    CK(ctx->p_vert_off.reserve(4 * ((size_t)n + 1)));
+    fragments_vert_off_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->f_rec.as<surtr_fragment>(), n, (uint32_t)c.n_verts,
+                                                                             ctx->p_vert_off.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->p_verts, ctx->f_verts);
+    std::swap(ctx->p_ring_off, ctx->f_ring_off);
+    std::swap(ctx->p_ring, ctx->f_ring);
+    ctx->cap_fverts = ctx->f_verts.cap / 16;
+    ctx->cap_fring = ctx->f_ring.cap / 2;
+    if (ctx->f_ring_off.cap < 4 * (ctx->cap_fverts + 1)) ctx->cap_fverts = ctx->f_ring_off.cap >= 8 ? ctx->f_ring_off.cap / 4 - 1 : 0;
+    ctx->n_pieces = n;
+    ctx->n_pverts = c.n_verts;
+    ctx->n_pring = c.n_ring;
+    if (ev_piece_off && n_events) ctx->h_ev_piece_off.assign(ev_piece_off, ev_piece_off + n_events + 1);
+    else ctx->h_ev_piece_off = { 0u, n };
+    ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
+    if (ctx->h_ev_piece_off.back() != n) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at the fragment count");
+    ctx->have_pieces = true;
+    ctx->tables_dirty = true;
+    ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const float* normals3, uint32_t k, float* dist,
+                    int32_t* arg, float* planes8)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!verts4 || !normals3 || !dist || !arg || !k) return fail(ctx, SURTR_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf dv, dn, dd, da, dp;
+    int rc = SURTR_OK;
+    auto done = [&](int code) { dv.release(); dn.release(); dd.release(); da.release(); dp.release(); return code; };
+    if (dv.reserve(16 * std::max(1u, n_verts)) || dn.reserve(12 * k) || dd.reserve(8 * k) || da.reserve(8 * k) || dp.reserve(32 * k))
+        return done(fail(ctx, SURTR_ERR_NOMEM, "cudaMalloc failed"));
+    cudaMemcpyAsync(dv.p, verts4, 16 * (size_t)n_verts, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dn.p, normals3, 12 * (size_t)k, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(dp.p, 0, 32 * (size_t)k, ctx->stream);
+    kdop_arg_kernel<<<k, 256, 0, ctx->stream>>>(dv.as<float4>(), n_verts, dn.as<float>(), dd.as<float>(), da.as<int32_t>(), dp.as<float4>());
+    cudaMemcpyAsync(dist, dd.p, 8 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(arg, da.p, 8 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream);
+    if (planes8) cudaMemcpyAsync(planes8, dp.p, 32 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, SURTR_ERR_CUDA, cudaGetErrorString(e));
+    return done(rc);
+}
+
+int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    if (total_ms) CK(cudaEventElapsedTime(total_ms, ctx->ev[0], ctx->ev[3]));
+    if (clip_ms) CK(cudaEventElapsedTime(clip_ms, ctx->ev[1], ctx->ev[2]));
+    return SURTR_OK;
+}
+
+int surtr_last_event_launches(const surtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+}

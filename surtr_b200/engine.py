@@ -1,0 +1,235 @@
+"""ctypes binding of libsurtr_b200.so -- the C ABI declared in include/surtr_b200.h.
+
+This is the thin Python face of the product path (used by bench.py, the tests and __graft_entry__).
+It never computes anything itself and has no CPU fallback: if the CUDA library is missing or no sm_100
+device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsurtr_b200.so")
+
+SURTR_OK = 0
+ERRORS = {1: "SURTR_ERR_CUDA", 2: "SURTR_ERR_INVALID", 3: "SURTR_ERR_NO_DEVICE", 4: "SURTR_ERR_OVERFLOW",
+          5: "SURTR_ERR_NOMEM"}
+
+# include/surtr_b200.h: struct surtr_fragment (64 bytes)
+FRAGMENT_DTYPE = np.dtype([
+    ("cell", np.uint32), ("piece", np.uint32), ("vert_off", np.uint32), ("n_verts", np.uint16),
+    ("n_faces", np.uint16), ("volume", np.float64), ("centroid", np.float32, 3), ("inertia", np.float32, 6),
+    ("n_ring", np.uint32)], align=True)
+assert FRAGMENT_DTYPE.itemsize == 64
+
+# every symbol include/surtr_b200.h declares
+EXPORTS = [
+    "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions",
+    "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
+    "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
+    "surtr_last_event_ms", "surtr_last_event_launches",
+]
+
+
+class SurtrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_candidates", "n_fragments", "n_verts", "n_ring",
+                                          "n_seq_cuts", "n_tier2")]
+
+
+class DeviceView(C.Structure):
+    _fields_ = [("fragments", C.c_void_p), ("verts4", C.c_void_p), ("ring_off", C.c_void_p), ("ring", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsurtr_b200.so; raises if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                           "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    lib.surtr_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
+    lib.surtr_ctx_destroy.argtypes = [vp]
+    lib.surtr_ctx_destroy.restype = None
+    lib.surtr_last_error.argtypes = [vp]
+    lib.surtr_last_error.restype = C.c_char_p
+    lib.surtr_version.restype = C.c_char_p
+    lib.surtr_set_kdop_directions.argtypes = [vp, i32]
+    lib.surtr_upload_pieces.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
+    lib.surtr_upload_cells.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
+    lib.surtr_fragments_to_pieces.argtypes = [vp, vp, u32]
+    lib.surtr_fracture_event.argtypes = [vp]
+    lib.surtr_event_counts.argtypes = [vp, C.POINTER(Counts)]
+    lib.surtr_download_fragments.argtypes = [vp, vp, vp, vp, vp]
+    lib.surtr_device_fragments.argtypes = [vp, C.POINTER(DeviceView)]
+    lib.surtr_kdop_calc.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
+    lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.surtr_last_event_launches.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+@dataclass
+class Fragments:
+    """Host copy of one event's fragments (flat layout of include/surtr_b200.h)."""
+    rec: np.ndarray        # FRAGMENT_DTYPE [n]
+    verts: np.ndarray      # float32 [NV,4]
+    ring_off: np.ndarray   # uint32 [NV+1]
+    ring: np.ndarray       # uint16 [NE]
+
+    @property
+    def n(self) -> int:
+        return len(self.rec)
+
+    @property
+    def vert_off(self) -> np.ndarray:
+        out = np.zeros(self.n + 1, np.uint32)
+        if self.n:
+            out[:-1] = self.rec["vert_off"]
+            out[-1] = len(self.verts)
+        return out
+
+    def poly(self, i):
+        v0 = int(self.rec["vert_off"][i])
+        v1 = v0 + int(self.rec["n_verts"][i])
+        rings = [self.ring[self.ring_off[v]:self.ring_off[v + 1]].tolist() for v in range(v0, v1)]
+        return self.verts[v0:v1, :3].copy(), rings
+
+
+class FractureContext:
+    """One context per GPU / stream.  Mirrors the call sequence of Surtr::ApplyFracture (Surtr.cpp:2098-2149):
+    upload_pieces + upload_cells -> fracture_event -> counts / download."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.surtr_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != SURTR_OK:
+            raise SurtrError(rc, self._lib.surtr_last_error(None).decode())
+        self._h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.surtr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != SURTR_OK:
+            raise SurtrError(rc, self._lib.surtr_last_error(self._h).decode())
+
+    def set_kdop_directions(self, k: int):
+        self._ck(self._lib.surtr_set_kdop_directions(self._h, k))
+
+    def upload_pieces(self, verts4, vert_off, ring_off, ring, ev_piece_off=None):
+        verts4 = _arr(verts4, np.float32)
+        vert_off = _arr(vert_off, np.uint32)
+        ring_off = _arr(ring_off, np.uint32)
+        ring = _arr(ring, np.uint16)
+        ev = _arr(ev_piece_off, np.uint32)
+        self._ck(self._lib.surtr_upload_pieces(self._h, _p(verts4), _p(vert_off), _p(ring_off), _p(ring),
+                                               len(vert_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def upload_cells(self, planes4, plane_off, cell_verts4=None, cvert_off=None, ev_cell_off=None):
+        planes4 = _arr(planes4, np.float32)
+        plane_off = _arr(plane_off, np.uint32)
+        cell_verts4 = _arr(cell_verts4, np.float32)
+        cvert_off = _arr(cvert_off, np.uint32)
+        ev = _arr(ev_cell_off, np.uint32)
+        self._ck(self._lib.surtr_upload_cells(self._h, _p(planes4), _p(plane_off), _p(cell_verts4), _p(cvert_off),
+                                              len(plane_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def fragments_to_pieces(self, ev_piece_off=None):
+        ev = _arr(ev_piece_off, np.uint32)
+        self._ck(self._lib.surtr_fragments_to_pieces(self._h, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def fracture_event(self):
+        self._ck(self._lib.surtr_fracture_event(self._h))
+
+    def counts(self) -> Counts:
+        c = Counts()
+        self._ck(self._lib.surtr_event_counts(self._h, C.byref(c)))
+        return c
+
+    def download(self, geometry: bool = True) -> Fragments:
+        c = self.counts()
+        rec = np.zeros(c.n_fragments, FRAGMENT_DTYPE)
+        if geometry:
+            verts = np.zeros((c.n_verts, 4), np.float32)
+            ring_off = np.zeros(c.n_verts + 1, np.uint32)
+            ring = np.zeros(c.n_ring, np.uint16)
+        else:
+            verts = ring_off = ring = None
+        self._ck(self._lib.surtr_download_fragments(self._h, _p(rec), _p(verts), _p(ring_off), _p(ring)))
+        if not geometry:
+            verts = np.zeros((0, 4), np.float32)
+            ring_off = np.zeros(1, np.uint32)
+            ring = np.zeros(0, np.uint16)
+        return Fragments(rec, verts, ring_off, ring)
+
+    def download_into(self, rec, verts, ring_off, ring):
+        """D2H into caller-owned (e.g. pinned) buffers; sizes from counts()."""
+        self._ck(self._lib.surtr_download_fragments(self._h, C.c_void_p(rec), C.c_void_p(verts), C.c_void_p(ring_off),
+                                                    C.c_void_p(ring)))
+
+    def upload_pieces_ptr(self, verts4, vert_off, ring_off, ring, n_pieces, ev=None, n_events=0):
+        self._ck(self._lib.surtr_upload_pieces(self._h, C.c_void_p(verts4), C.c_void_p(vert_off), C.c_void_p(ring_off),
+                                               C.c_void_p(ring), n_pieces, C.c_void_p(ev) if ev else None, n_events))
+
+    def upload_cells_ptr(self, planes4, plane_off, cell_verts4, cvert_off, n_cells, ev=None, n_events=0):
+        self._ck(self._lib.surtr_upload_cells(self._h, C.c_void_p(planes4), C.c_void_p(plane_off),
+                                              C.c_void_p(cell_verts4) if cell_verts4 else None,
+                                              C.c_void_p(cvert_off) if cvert_off else None, n_cells,
+                                              C.c_void_p(ev) if ev else None, n_events))
+
+    def device_view(self) -> DeviceView:
+        v = DeviceView()
+        self._ck(self._lib.surtr_device_fragments(self._h, C.byref(v)))
+        return v
+
+    def kdop_calc(self, verts4, normals):
+        verts4 = _arr(verts4, np.float32)
+        normals = _arr(normals, np.float32)
+        k = len(normals)
+        dist = np.zeros((k, 2), np.float32)
+        arg = np.zeros((k, 2), np.int32)
+        planes = np.zeros((k, 2, 4), np.float32)
+        self._ck(self._lib.surtr_kdop_calc(self._h, _p(verts4), len(verts4), _p(normals), k, _p(dist), _p(arg), _p(planes)))
+        return dist, arg, planes
+
+    def last_event_ms(self):
+        t, c = C.c_float(0), C.c_float(0)
+        self._ck(self._lib.surtr_last_event_ms(self._h, C.byref(t), C.byref(c)))
+        return t.value, c.value
+
+    def last_event_launches(self) -> int:
+        return self._lib.surtr_last_event_launches(self._h)
