@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- clipped convex fragments per second on N B200s (BASELINE.json metric).
+
+A "step" is one fracture event: the whole hot path (K1 k-DOP extents -> K2 broad phase + compaction -> K3 clip ->
+K4 assembly) over one batch of synthetic input.  Workload at every N: BASELINE.json configs[1], the synthetic
+unit-cube VMACH (1 piece) fractured by 4096 Voronoi seeds, one independent event per rank (rank r uses seed
+46354 + r): events shard across GPUs with no data-path collective (weak scaling).
+
+  value   whole-job fragments/s with inputs resident in HBM, timed per step with CUDA events on the launching stream,
+          L2 flushed between steps (flush outside the events), max over ranks;
+  e2e     the same metric through the C ABI with HOST buffers: pinned-host -> device upload of the event's pieces
+          and cells, the event, and the device -> pinned-host download of every fragment, all inside the timed region;
+  roofline  dominant kernel (K3 clip, tier 1): algorithmic bytes / its CUDA-event duration
+          against the measured HBM peak of MEASURED_PEAKS.json;
+  cpu_baseline  the reference's own CPU path (oracle/_ref, built from the reference sources) timed on this box.
+
+--impl reference times only that CPU path (the reference arm), same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SEEDS = 4096
+BASE_SEED = 46354
+WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fracture event per step per GPU"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(planes, plane_off, budget_s: float, threads: int):
+    """The reference's own CPU fan-out (one task per cell on dp::thread_pool, Surtr.cpp:28, 2129-2131) from
+    oracle/_ref; falls back to the oracle's single-thread C port only if the reference build is absent."""
+    from oracle import portapi, refapi
+    verts, vo, ro, ring = __import__("surtr_b200.synth", fromlist=["x"]).unit_cube()
+    cube = refapi.PolySet(verts, vo, ro, ring)
+    if refapi.available():
+        kind, run = "reference", (lambda: refapi.apply_fracture(cube, planes, plane_off, threads, False))
+        cores = threads
+    else:
+        kind, run = "port", (lambda: portapi.apply_fracture(cube, planes, plane_off))
+        cores = 1
+    run()
+    reps, frags, secs = 0, 0, 0.0
+    t_end = time.perf_counter() + budget_s
+    while True:
+        t0 = time.perf_counter()
+        r = run()
+        # reference build: its own timer around the fan-out + SetExtract (Surtr.cpp:1917-1924 "ApplyFracture" timer);
+        # flattening into flat arrays for the caller is not part of the reference's event
+        secs += r.seconds if kind == "reference" else time.perf_counter() - t0
+        frags += r.n
+        reps += 1
+        if time.perf_counter() >= t_end or reps >= 400:
+            break
+    return {"value": frags / secs, "unit": "fragments/s", "cores": cores, "kind": kind,
+            "sample": f"{reps} full events of the workload ({frags // reps} fragments each), {secs:.2f} s of wall time, "
+                      f"{os.cpu_count()} host threads available"}, secs / reps
+
+
+def load_or_build_cells_cpu(seed):
+    """Cells for the reference arm (no GPU): the oracle's own builder."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import portapi
+    from surtr_b200 import synth
+    s = synth.seeds_uniform(seed, N_SEEDS)
+    off, idx = synth.delaunay_neighbors(s)
+    return portapi.voronoi_cells(s, off, idx)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cells = load_or_build_cells_cpu(BASE_SEED)
+    threads = max(16, os.cpu_count() or 1)
+    from oracle import refapi, portapi
+    verts, vo, ro, ring = __import__("surtr_b200.synth", fromlist=["x"]).unit_cube()
+    cube = refapi.PolySet(verts, vo, ro, ring)
+    use_ref = refapi.available()
+    run = (lambda: refapi.apply_fracture(cube, cells.planes, cells.plane_off, threads, False)) if use_ref else \
+          (lambda: portapi.apply_fracture(cube, cells.planes, cells.plane_off))
+    for _ in range(max(1, args.warmup)):
+        run()
+    t, frags = 0.0, 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        r = run()
+        t += r.seconds if use_ref else time.perf_counter() - t0     # fan-out + SetExtract (see cpu_reference)
+        frags += r.n
+    val = frags / t
+    line = {
+        "metric": "clipped fragments/sec", "value": val, "unit": "fragments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path: each step = one full event on the host cores"},
+        "cpu_baseline": {"value": val, "unit": "fragments/s", "cores": threads if use_ref else 1,
+                         "kind": "reference" if use_ref else "port",
+                         "sample": f"{args.steps} full events, dp::thread_pool({threads}) one task per cell, "
+                                   f"{os.cpu_count()} host threads available"},
+        "e2e": {"value": val, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="surtr_b200", choices=["surtr_b200", "reference"])
+    ap.add_argument("--kdop", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from surtr_b200 import FractureContext, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # a dedicated non-default stream: the engine launches on it and every timing event is recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx = FractureContext(local, stream.cuda_stream)
+    ctx.set_kdop_directions(args.kdop)
+
+    # ---- synthetic input of the named shape, built by the product path (GPU clipper) ----
+    seeds = synth.seeds_uniform(BASE_SEED + rank, N_SEEDS)
+    cells = synth.voronoi_cells(ctx, seeds)
+    cube_v, cube_vo, cube_ro, cube_r = synth.unit_cube()
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_in = {k: pin(v) for k, v in dict(pv=cube_v, pvo=cube_vo, pro=cube_ro, pr=cube_r, planes=cells.planes,
+                                       plane_off=cells.plane_off, cverts=cells.verts, cvo=cells.vert_off).items()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in h_in.values())
+
+    def upload():
+        ctx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
+        ctx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
+                             h_in["cvo"].data_ptr(), N_SEEDS)
+
+    upload()
+    ctx.fracture_event()
+    c0 = ctx.counts()
+    n_frag = int(c0.n_fragments)
+    fr0 = ctx.download()
+    alg_bytes = synth.algorithmic_bytes(cube_vo, cube_ro, cells.plane_off, fr0.rec)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+
+    # ---- warm-up ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)      # let nvidia-smi come up; it keeps sampling through warm-up, timed region and e2e
+    for _ in range(args.warmup):
+        flush_l2()
+        ctx.fracture_event()
+    ctx.counts()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: K steps, device-resident inputs ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clip_ms = []
+    launches = 0
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2()
+        ev[i][0].record(stream)
+        ctx.fracture_event()
+        ev[i][1].record(stream)
+        launches += ctx.last_event_launches()
+        if i % 8 == 7 or i == args.steps - 1:
+            # per-kernel timers are read off the last event of each group of 8 (reading syncs the stream)
+            clip_ms.append(ctx.last_event_ms()[1])
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([float(np.sum(step_ms))], device=dev, dtype=torch.float64)
+    frags = torch.tensor([float(n_frag * args.steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frags, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    value = float(frags.item()) / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, every step ----
+    c = ctx.counts()
+    from surtr_b200 import FRAGMENT_DTYPE
+    h_out = dict(rec=torch.empty(int(c.n_fragments) * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                 verts=torch.empty(int(c.n_verts) * 4, dtype=torch.float32).pin_memory(),
+                 ring_off=torch.empty(int(c.n_verts) + 1, dtype=torch.int32).pin_memory(),
+                 ring=torch.empty(int(c.n_ring), dtype=torch.int16).pin_memory())
+    d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
+
+    def e2e_step():
+        upload()
+        ctx.fracture_event()
+        ctx.download_into(h_out["rec"].data_ptr(), h_out["verts"].data_ptr(), h_out["ring_off"].data_ptr(),
+                          h_out["ring"].data_ptr())
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step()                      # download_into synchronises the stream
+        e2e_s += time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = float(frags.item()) / float(e2e_t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + e2e region (the timed region alone is shorter than one sample)"
+    got = np.frombuffer(h_out["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
+    assert got.tobytes() == fr0.rec.tobytes(), "e2e result differs from the resident-input result"
+
+    # ---- final fragment gather (the only collective; after the hot path, reported separately) ----
+    gather = None
+    if world > 1:
+        view = ctx.device_view()
+        cnt = torch.tensor([int(c.n_fragments), int(c.n_verts)], device=dev, dtype=torch.int64)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        max_v = max(int(x[1]) for x in cnts)
+        payload = torch.zeros(max_v * 4, device=dev, dtype=torch.float32)
+        import ctypes
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(payload.data_ptr()), ctypes.c_void_p(view.verts4),
+                                               ctypes.c_size_t(int(c.n_verts) * 16), 3)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bufs = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+        g0.record()
+        dist.gather(payload, bufs, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank": int(payload.numel() * 4), "backend": "nccl gather to rank 0"}
+
+    # ---- roofline of the dominant kernel + CPU baseline (rank 0) ----
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k3_ms = float(np.mean(clip_ms))
+        achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
+            traffic = prof.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "clip_kernel<tier1> (K3+moments)", "kernel_ms": k3_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+        line = {
+            "metric": "clipped fragments/sec", "value": value, "unit": "fragments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "fragments_per_step_per_gpu": n_frag, "pairs_per_step": int(c0.n_pairs),
+                       "candidates_per_step": int(c0.n_candidates), "kdop_directions": args.kdop,
+                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events)",
+                       "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                       "parallelism": f"events sharded over {world} GPU(s), no data-path collective"},
+            "p50_event_ms": float(np.median(step_ms)), "wall_s_timed_region": t_wall,
+            "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
+                    "timing": "wall clock around upload + event + download through the C ABI, pinned host buffers"},
+            "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
+            "clocks": clocks, "roofline": roofline,
+        }
+        if gather:
+            line["gather"] = gather
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference(cells.planes, cells.plane_off, args.cpu_budget, max(16, os.cpu_count() or 1))
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

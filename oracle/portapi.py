@@ -129,3 +129,81 @@ def apply_fracture(pieces: PolySet, planes, plane_off, moments=True, inertia=Fal
                  centroid=None if cen is None else cen[:n].copy())
     ps.inertia = None if ine is None else ine[:n].copy()
     return ps
+
+
+def _alloc_out(cap_frags, cap_verts, moments=True, inertia=False):
+    cr = cap_verts * 4
+    bufs = dict(
+        verts=np.zeros((cap_verts, 4), np.float32), vert_off=np.zeros(cap_frags + 1, np.uint32),
+        ring_off=np.zeros(cap_verts + 1, np.uint32), ring=np.zeros(cr, np.uint16),
+        rec=np.zeros((cap_frags, 4), np.uint32),
+        vol=np.zeros(cap_frags, np.float64) if moments else None,
+        cen=np.zeros((cap_frags, 3), np.float32) if moments else None,
+        ine=np.zeros((cap_frags, 6), np.float64) if inertia else None)
+    o = _SoOut(_p(bufs["verts"]), cap_verts, _p(bufs["vert_off"]), _p(bufs["ring_off"]), _p(bufs["ring"]), cr,
+               _p(bufs["rec"]), cap_frags, _p(bufs["vol"]), _p(bufs["cen"]), _p(bufs["ine"]))
+    return o, bufs
+
+
+def _collect(n, b) -> PolySet:
+    nv = int(b["vert_off"][n])
+    ne = int(b["ring_off"][nv])
+    ps = PolySet(b["verts"][:nv].copy(), b["vert_off"][:n + 1].copy(), b["ring_off"][:nv + 1].copy(),
+                 b["ring"][:ne].copy(), cell=b["rec"][:n, 0].copy(), piece=b["rec"][:n, 1].copy(),
+                 nfaces=b["rec"][:n, 3].copy(),
+                 volume=None if b["vol"] is None else b["vol"][:n].copy(),
+                 centroid=None if b["cen"] is None else b["cen"][:n].copy())
+    ps.inertia = None if b["ine"] is None else b["ine"][:n].copy()
+    return ps
+
+
+def voronoi_cells(seeds, nb_off, nb_idx) -> PolySet:
+    """Cells of `seeds` in the unit box from neighbour lists (the NEW derivation, see surtr_oracle.h)."""
+    L = lib()
+    L.so_voronoi_cells.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SoOut), C.c_void_p,
+                                   C.c_void_p, C.c_uint64]
+    L.so_voronoi_cells.restype = C.c_int64
+    seeds = np.ascontiguousarray(seeds, np.float32)
+    nb_off = np.ascontiguousarray(nb_off, np.uint32)
+    nb_idx = np.ascontiguousarray(nb_idx, np.uint32)
+    n = len(seeds)
+    o, b = _alloc_out(n, n * 96)
+    cap_pl = n * 96
+    planes = np.zeros((cap_pl, 4), np.float32)
+    plane_off = np.zeros(n + 1, np.uint32)
+    r = L.so_voronoi_cells(_p(seeds), n, _p(nb_off), _p(nb_idx), C.byref(o), _p(plane_off), _p(planes), cap_pl)
+    if r < 0:
+        raise RuntimeError(f"so_voronoi_cells failed: {r}")
+    ps = _collect(int(r), b)
+    ps.planes = planes[:int(plane_off[n])].copy()
+    ps.poly_face_off = plane_off
+    return ps
+
+
+def clip_each(ps: PolySet, planes, pl_off) -> PolySet:
+    L = lib()
+    L.so_clip_each.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(_SoOut)]
+    L.so_clip_each.restype = C.c_int64
+    planes = np.ascontiguousarray(planes, np.float32)
+    pl_off = np.ascontiguousarray(pl_off, np.uint32)
+    nv_in = int(ps.vert_off[-1])
+    o, b = _alloc_out(ps.n + 1, nv_in + 64 * (ps.n + 1) + int(len(planes)) * 4)
+    r = L.so_clip_each(_p(ps.verts), _p(ps.vert_off), _p(ps.ring_off), _p(ps.ring), ps.n, _p(planes), _p(pl_off),
+                       C.byref(o))
+    if r < 0:
+        raise RuntimeError(f"so_clip_each failed: {r}")
+    return _collect(int(r), b)
+
+
+def face_planes(ps: PolySet):
+    """(planes4, plane_off) of every polyhedron, PolygonFace::AddVertex route (VMACH.cpp:289-310)."""
+    L = lib()
+    L.so_face_planes_set.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.so_face_planes_set.restype = C.c_int64
+    cap = int(len(ps.ring)) + 16
+    planes = np.zeros((cap, 4), np.float32)
+    off = np.zeros(ps.n + 1, np.uint32)
+    r = L.so_face_planes_set(_p(ps.verts), _p(ps.vert_off), _p(ps.ring_off), _p(ps.ring), ps.n, _p(off), _p(planes), cap)
+    if r < 0:
+        raise RuntimeError("so_face_planes_set overflow")
+    return planes[:int(r)].copy(), off

@@ -82,7 +82,8 @@ bool face_plane(const Poly::Polyhedron& p, const std::vector<int>& loop, Plane& 
 	return true;
 }
 
-void append(PolySet& s, const Poly::Polyhedron& p, uint32_t cell, uint32_t piece, bool with_moments = true)
+void append(PolySet& s, const Poly::Polyhedron& p, uint32_t cell, uint32_t piece, bool with_moments = true,
+			Poly::Extract* precomputed = nullptr, bool with_planes = true)
 {
 	for (const auto& v : p)
 	{
@@ -98,7 +99,7 @@ void append(PolySet& s, const Poly::Polyhedron& p, uint32_t cell, uint32_t piece
 	s.cell.push_back(cell);
 	s.piece.push_back(piece);
 
-	Poly::Extract* faces = Poly::ExtractFaces(p); // Poly.cpp:89-126
+	Poly::Extract* faces = precomputed ? precomputed : Poly::ExtractFaces(p); // Poly.cpp:89-126
 	s.nfaces.push_back((uint32_t)faces->size());
 	for (const auto& loop : *faces)
 	{
@@ -106,7 +107,8 @@ void append(PolySet& s, const Poly::Polyhedron& p, uint32_t cell, uint32_t piece
 			s.face_idx.push_back((uint16_t)v);
 		s.face_off.push_back((uint32_t)s.face_idx.size());
 		Plane pl(0, 0, 0, 0);
-		face_plane(p, loop, pl);
+		if (with_planes)
+			face_plane(p, loop, pl);
 		s.planes.push_back(pl.x);
 		s.planes.push_back(pl.y);
 		s.planes.push_back(pl.z);
@@ -359,6 +361,7 @@ void ref_apply_fracture(const float* verts, const uint32_t* vert_off, const uint
 						uint32_t n_pieces, const float* planes, const uint32_t* plane_off, uint32_t n_cells,
 						uint32_t nthreads, int with_moments, void* out)
 {
+	// `seconds` = fan-out + SetExtract; flattening into the flat arrays (and the optional moments) is not timed.
 	PolySet& o = *(PolySet*)out;
 	std::vector<Poly::Polyhedron> pieces;
 	for (uint32_t i = 0; i < n_pieces; i++)
@@ -383,11 +386,17 @@ void ref_apply_fracture(const float* verts, const uint32_t* vert_off, const uint
 		for (uint32_t c = 0; c < n_cells; c++)
 			results[c] = futures[c].get();
 	}
+	// Surtr::SetExtract (Surtr.cpp:2151-2155): Poly::ExtractFaces per resulting piece, as DoFracture does right
+	// after ApplyFracture (:1921-1922).  Timed together with the fan-out: that pair is the CPU event.
+	std::vector<std::vector<Poly::Extract*>> extracts(n_cells);
+	for (uint32_t c = 0; c < n_cells; c++)
+		for (auto& [piece, poly] : results[c])
+			extracts[c].push_back(Poly::ExtractFaces(poly));
 	o.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
 	for (uint32_t c = 0; c < n_cells; c++)
-		for (auto& [piece, poly] : results[c])
-			append(o, poly, c, piece, with_moments != 0);
+		for (size_t k = 0; k < results[c].size(); k++)
+			append(o, results[c][k].second, c, results[c][k].first, with_moments != 0, extracts[c][k], false);
 }
 
 // Kdop::KdopContainer::Calc(const Poly::Polyhedron&) (Kdop.cpp:92-115) on raw vertices:

@@ -563,3 +563,158 @@ int64_t so_apply_fracture(const float* verts4, const uint32_t* vert_off, const u
     so_poly_free(&w);
     return (int64_t)nf;
 }
+
+/* Src/VMACH.cpp:289-310 + NearlyEqual (:1205): (v1 - v2).Length() < 1e-12 */
+int so_face_planes(const so_poly* p, float* planes4)
+{
+    int maxf;
+    const int ne = count_face_entries(p, &maxf);
+    uint32_t* foff = (uint32_t*)malloc(sizeof(uint32_t) * (maxf + 2));
+    uint16_t* fidx = (uint16_t*)malloc(sizeof(uint16_t) * (ne + 2));
+    const int nf = so_extract_faces(p, foff, fidx);
+    for (int f = 0; f < nf; f++)
+    {
+        float kept[3][3];
+        int nk = 0;
+        for (uint32_t k = foff[f]; k < foff[f + 1] && nk < 3; k++)
+        {
+            const float* v = p->pos + 3 * fidx[k];
+            int dup = 0;
+            for (int q = 0; q < nk; q++)
+            {
+                const float d[3] = { kept[q][0] - v[0], kept[q][1] - v[1], kept[q][2] - v[2] };
+                if ((double)sqrtf(dot3(d, d)) < 1e-12) { dup = 1; break; }
+            }
+            if (dup) continue;
+            kept[nk][0] = v[0]; kept[nk][1] = v[1]; kept[nk][2] = v[2];
+            nk++;
+        }
+        float* o = planes4 + 4 * f;
+        if (nk == 3) so_plane_from_points(kept[0], kept[1], kept[2], o);
+        else { o[0] = 0.f; o[1] = 1.f; o[2] = 0.f; o[3] = 0.f; }   /* default-constructed Plane */
+    }
+    free(foff);
+    free(fidx);
+    return nf;
+}
+
+static int append_poly(so_out* out, const so_poly* w, uint64_t* nf, uint64_t* nvtx, uint64_t* nring, uint32_t a,
+                       uint32_t b)
+{
+    if (*nf >= out->cap_frags || *nvtx + (uint64_t)w->nv > out->cap_verts) return -1;
+    for (int i = 0; i < w->nv; i++)
+    {
+        float* d = out->verts4 + 4 * (*nvtx + i);
+        d[0] = w->pos[3 * i]; d[1] = w->pos[3 * i + 1]; d[2] = w->pos[3 * i + 2]; d[3] = 0.f;
+        if (*nring + (uint64_t)w->deg[i] > out->cap_ring) return -1;
+        for (int j = 0; j < w->deg[i]; j++)
+            out->ring[(*nring)++] = (uint16_t)w->ring[(size_t)i * SO_MAXDEG + j];
+        out->ring_off[*nvtx + i + 1] = (uint32_t)*nring;
+    }
+    out->rec[4 * *nf] = a;
+    out->rec[4 * *nf + 1] = b;
+    out->rec[4 * *nf + 2] = (uint32_t)w->nv;
+    out->rec[4 * *nf + 3] = w->nv ? (uint32_t)so_extract_faces(w, NULL, NULL) : 0u;
+    if (out->volume) so_moments(w, out->volume + *nf, out->centroid + 3 * *nf);
+    if (out->inertia) so_inertia(w, out->inertia + 6 * *nf);
+    *nvtx += (uint64_t)w->nv;
+    (*nf)++;
+    out->vert_off[*nf] = (uint32_t)*nvtx;
+    return 0;
+}
+
+/* Poly::GetBB (Src/Poly.cpp:587-617) */
+static void load_unit_cube(so_poly* p)
+{
+    static const float pts[8][3] = { { -0.5f, -0.5f, -0.5f }, { 0.5f, -0.5f, -0.5f }, { 0.5f, 0.5f, -0.5f },
+                                     { -0.5f, 0.5f, -0.5f }, { -0.5f, -0.5f, 0.5f }, { 0.5f, -0.5f, 0.5f },
+                                     { 0.5f, 0.5f, 0.5f },   { -0.5f, 0.5f, 0.5f } };
+    static const int nb[8][3] = { { 1, 4, 3 }, { 5, 0, 2 }, { 3, 6, 1 }, { 7, 2, 0 },
+                                  { 5, 7, 0 }, { 1, 6, 4 }, { 5, 2, 7 }, { 4, 6, 3 } };
+    reserve(p, 8);
+    p->nv = 8;
+    for (int i = 0; i < 8; i++)
+    {
+        memcpy(p->pos + 3 * i, pts[i], sizeof(float) * 3);
+        p->deg[i] = 3;
+        for (int j = 0; j < 3; j++) RING(p, i)[j] = nb[i][j];
+        p->comp[i] = 1;
+        p->id[i] = -1;
+    }
+}
+
+int64_t so_voronoi_cells(const float* seeds3, uint32_t n, const uint32_t* nb_off, const uint32_t* nb_idx, so_out* out,
+                         uint32_t* plane_off, float* planes4, uint64_t cap_planes)
+{
+    so_poly w;
+    so_poly_init(&w);
+    uint64_t nf = 0, nvtx = 0, nring = 0, npl = 0;
+    out->vert_off[0] = 0;
+    out->ring_off[0] = 0;
+    plane_off[0] = 0;
+    float* bis = NULL;
+    uint32_t bis_cap = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint32_t k0 = nb_off[i], k1 = nb_off[i + 1];
+        if (k1 - k0 > bis_cap) { bis_cap = 2 * (k1 - k0) + 16; bis = (float*)realloc(bis, sizeof(float) * 4 * bis_cap); }
+        const float* si = seeds3 + 3 * i;
+        for (uint32_t k = k0; k < k1; k++)
+        {
+            const float* sj = seeds3 + 3 * nb_idx[k];
+            const float mid[3] = { (si[0] + sj[0]) * 0.5f, (si[1] + sj[1]) * 0.5f, (si[2] + sj[2]) * 0.5f };
+            const float nrm[3] = { sj[0] - si[0], sj[1] - si[1], sj[2] - si[2] };
+            so_plane_from_point_normal(mid, nrm, bis + 4 * (k - k0));
+        }
+        load_unit_cube(&w);
+        if (so_clip(&w, bis, (int)(k1 - k0)) != 0) { free(bis); so_poly_free(&w); return -2; }
+        if (append_poly(out, &w, &nf, &nvtx, &nring, i, 0)) { free(bis); so_poly_free(&w); return -1; }
+        int maxf;
+        count_face_entries(&w, &maxf);
+        if (npl + (uint64_t)maxf > cap_planes) { free(bis); so_poly_free(&w); return -1; }
+        npl += (uint64_t)(w.nv ? so_face_planes(&w, planes4 + 4 * npl) : 0);
+        plane_off[i + 1] = (uint32_t)npl;
+    }
+    free(bis);
+    so_poly_free(&w);
+    return (int64_t)nf;
+}
+
+int64_t so_clip_each(const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring,
+                     uint32_t n, const float* planes4, const uint32_t* pl_off, so_out* out)
+{
+    so_poly w;
+    so_poly_init(&w);
+    uint64_t nf = 0, nvtx = 0, nring = 0;
+    out->vert_off[0] = 0;
+    out->ring_off[0] = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        so_poly_load(&w, verts4, ring_off, ring, vert_off[i], vert_off[i + 1]);
+        if (so_clip(&w, planes4 + 4 * (size_t)pl_off[i], (int)(pl_off[i + 1] - pl_off[i])) != 0) { so_poly_free(&w); return -2; }
+        if (append_poly(out, &w, &nf, &nvtx, &nring, i, i)) { so_poly_free(&w); return -1; }
+    }
+    so_poly_free(&w);
+    return (int64_t)nf;
+}
+
+/* Face planes of every polyhedron of a flat set (so_face_planes per polyhedron). */
+int64_t so_face_planes_set(const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,
+                           const uint16_t* ring, uint32_t n, uint32_t* plane_off, float* planes4, uint64_t cap_planes)
+{
+    so_poly w;
+    so_poly_init(&w);
+    uint64_t npl = 0;
+    plane_off[0] = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        so_poly_load(&w, verts4, ring_off, ring, vert_off[i], vert_off[i + 1]);
+        int maxf;
+        count_face_entries(&w, &maxf);
+        if (npl + (uint64_t)maxf > cap_planes) { so_poly_free(&w); return -1; }
+        npl += (uint64_t)(w.nv ? so_face_planes(&w, planes4 + 4 * npl) : 0);
+        plane_off[i + 1] = (uint32_t)npl;
+    }
+    so_poly_free(&w);
+    return (int64_t)npl;
+}

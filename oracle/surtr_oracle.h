@@ -80,6 +80,27 @@ int64_t so_apply_fracture(const float* verts4, const uint32_t* vert_off, const u
                           const uint16_t* ring, uint32_t n_pieces, const float* planes4, const uint32_t* plane_off,
                           uint32_t n_cells, so_out* out);
 
+/* Face planes of a polyhedron exactly as a VMACH cell face gets them (Src/VMACH.cpp:289-310): loop vertices
+ * are appended with PolygonFace::AddVertex (duplicates closer than 1e-12 dropped) and the plane is
+ * Plane(v0, v1, v2) of the first three kept vertices.  Returns the face count; planes4 has 4 floats per face
+ * (zeros when fewer than three distinct vertices). */
+int so_face_planes(const so_poly* p, float* planes4);
+
+/* NEW derivation shared with the product's host library (replaces the voro++ call sites Surtr.cpp:2007-2067):
+ * cell i = Poly::GetBB() clipped by Plane((Si+Sj)*0.5, Sj-Si) for every neighbour j in nb (ascending).
+ * Appends the cells to `out` (rec = {i, 0, nv, nf}); plane_off[n+1] / planes4 receive the face planes. */
+int64_t so_voronoi_cells(const float* seeds3, uint32_t n, const uint32_t* nb_off, const uint32_t* nb_idx, so_out* out,
+                         uint32_t* plane_off, float* planes4, uint64_t cap_planes);
+
+/* Clip polyhedron i by its own plane list [pl_off[i], pl_off[i+1]) -- Poly.cpp:265 in place; EVERY input gets
+ * one output entry (possibly with 0 vertices). */
+int64_t so_clip_each(const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring,
+                     uint32_t n, const float* planes4, const uint32_t* pl_off, so_out* out);
+
+/* so_face_planes for every polyhedron of a flat set; returns the plane count or -1 on overflow. */
+int64_t so_face_planes_set(const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,
+                           const uint16_t* ring, uint32_t n, uint32_t* plane_off, float* planes4, uint64_t cap_planes);
+
 #ifdef __cplusplus
 }
 #endif

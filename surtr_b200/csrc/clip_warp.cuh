@@ -191,7 +191,8 @@ __device__ bool all_inplane_box_says_skip(const P& sp, int nv, const float4& pl,
 // Clip the polyhedron held in `sp` (nv vertices) by planes[0..npl).  All 32 lanes call this together.
 // On return nv is the surviving vertex count (0 = no fragment).  seq_cuts counts sequential replays.
 template <class P>
-__device__ int clip_by_planes(P& sp, int& nv, const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts)
+__device__ int clip_by_planes(P& sp, int& nv, const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts,
+                              unsigned& n_cuts)
 {
     using IdxT = typename P::IdxT;
     constexpr int DMAX = P::DMAX;
@@ -252,6 +253,7 @@ __device__ int clip_by_planes(P& sp, int& nv, const float4* __restrict__ planes,
             if (!any_clip) continue;   // "above" (Poly.cpp:328)
 
             // ---- the plane cuts: insert new vertices (Poly.cpp:332-363) ----
+            n_cuts++;
             const int nverts0 = nv;
 #pragma unroll
             for (int h = 0; h < VPL; h++)
@@ -527,7 +529,8 @@ __device__ void fragment_moments(P& sp, int nv, int lane, Moments& out)
     }
 
     // pass 2: emit the fan triangles at their position in the reference's accumulation order
-    double cov[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };   // xx yy zz xy xz yz second moments about the origin vertex
+    // xx yy zz xy xz yz second moments about the origin vertex, then 6V and the first moments (all double)
+    double cov[10] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
 #pragma unroll
     for (int h = 0; h < VPL; h++)
     {
@@ -559,8 +562,10 @@ __device__ void fragment_moments(P& sp, int nv, int lane, Moments& out)
                         const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
                         sp.tri[w++] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
                         {
-                            const double a0 = p0x, a1 = p0y, a2 = p0z, b0 = p1x, b1 = p1y, b2 = p1z, c0 = p2x, c1 = p2y,
-                                         c2 = p2z;
+                            // inertia: independent all-double integral over the same fan (exact differences)
+                            const double a0 = (double)sp.x[v] - ox, a1 = (double)sp.y[v] - oy, a2 = (double)sp.z[v] - oz;
+                            const double b0 = (double)sp.x[prev] - ox, b1 = (double)sp.y[prev] - oy, b2 = (double)sp.z[prev] - oz;
+                            const double c0 = (double)sp.x[at] - ox, c1 = (double)sp.y[at] - oy, c2 = (double)sp.z[at] - oz;
                             const double dd = a0 * (b1 * c2 - b2 * c1) + a1 * (b2 * c0 - b0 * c2) + a2 * (b0 * c1 - b1 * c0);
                             const double s0 = a0 + b0 + c0, s1 = a1 + b1 + c1, s2 = a2 + b2 + c2;
                             cov[0] += dd * (s0 * s0 + a0 * a0 + b0 * b0 + c0 * c0);
@@ -569,6 +574,8 @@ __device__ void fragment_moments(P& sp, int nv, int lane, Moments& out)
                             cov[3] += dd * (s0 * s1 + a0 * a1 + b0 * b1 + c0 * c1);
                             cov[4] += dd * (s0 * s2 + a0 * a2 + b0 * b2 + c0 * c2);
                             cov[5] += dd * (s1 * s2 + a1 * a2 + b1 * b2 + c1 * c2);
+                            cov[6] += dd;
+                            cov[7] += dd * s0; cov[8] += dd * s1; cov[9] += dd * s2;
                         }
                         p1x = p2x; p1y = p2y; p1z = p2z;
                         nxt = face_loop(sp, at, prev);
@@ -599,7 +606,7 @@ __device__ void fragment_moments(P& sp, int nv, int lane, Moments& out)
         fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); fz = __fmul_rn(fz, sc);
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++)
+    for (int k = 0; k < 10; k++)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             cov[k] += __shfl_xor_sync(FULL, cov[k], o);
@@ -611,7 +618,9 @@ __device__ void fragment_moments(P& sp, int nv, int lane, Moments& out)
     out.cx = __fadd_rn(fx, ox); out.cy = __fadd_rn(fy, oy); out.cz = __fadd_rn(fz, oz);
     {
         // shift the second moments from the origin vertex to the centroid, then I = tr(C) 1 - C
-        const double V = zeroth, c0 = fx, c1 = fy, c2 = fz;
+        const double V = cov[6] / 6.0;
+        const double iv = V != 0.0 ? 1.0 / (24.0 * V) : 0.0;
+        const double c0 = cov[7] * iv, c1 = cov[8] * iv, c2 = cov[9] * iv;
         const double Cxx = cov[0] / 120.0 - V * c0 * c0, Cyy = cov[1] / 120.0 - V * c1 * c1,
                      Czz = cov[2] / 120.0 - V * c2 * c2, Cxy = cov[3] / 120.0 - V * c0 * c1,
                      Cxz = cov[4] / 120.0 - V * c0 * c2, Cyz = cov[5] / 120.0 - V * c1 * c2;

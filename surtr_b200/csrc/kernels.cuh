@@ -261,6 +261,7 @@ struct ClipArgs
     uint32_t* ovf_list;           // tier 1 appends, tier 2 consumes
     uint64_t cap_tier2;           // slots available to tier 2
     Ctl* ctl;
+    uint32_t* dbg;                // optional: 8 words per candidate (cycles per phase, cut counts); NULL = off
 };
 
 template <class P>
@@ -292,6 +293,9 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
     unsigned seq_cuts = 0;
     for (unsigned long long it = gw; it < n_items; it += nwarps)
     {
+        const long long t0 = clock64();
+        const unsigned seq0 = seq_cuts;
+        unsigned n_cuts = 0;
         const uint32_t q = (TIER == 1) ? (uint32_t)it : a.ovf_list[it];
         const uint2 pr = a.cand[q];
         const uint32_t v0 = a.p_vert_off[pr.x];
@@ -316,11 +320,22 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
         too_big = __ballot_sync(FULL, too_big) != 0u;
         __syncwarp();
         int status = CLIP_OVERFLOW;
+        const long long t1 = clock64();
+        const int nv_in = nv;
+        int npl_dbg = 0;
         if (!too_big)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-            status = clip_by_planes(sp, nv, a.c_planes + pl0, npl, lane, seq_cuts);
+            npl_dbg = npl;
+            status = clip_by_planes(sp, nv, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
+        }
+        const long long t2 = clock64();
+        if (a.dbg && lane == 0)
+        {
+            uint32_t* d = a.dbg + (size_t)q * 8;
+            d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
+            d[4] = seq_cuts - seq0; d[5] = n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl_dbg;
         }
         CandRec* rec = a.rec + q;
         if (status != CLIP_OK)
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
         }
         Moments mo;
         fragment_moments(sp, nv, lane, mo);
+        const long long t3 = clock64();
 
         // result blob: float4 verts[CAP] | u16 ring_start[CAP] | IdxT ring[packed]
         unsigned long long blob = (TIER == 1) ? (unsigned long long)q * a.slot_bytes : (unsigned long long)it * a.slot_bytes;
@@ -386,6 +402,11 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
             for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
             rec->blob = blob;
             if (!room) atomicAdd(&a.ctl->n_tier2_fail, 1u);
+            if (a.dbg)
+            {
+                a.dbg[(size_t)q * 8 + 2] = (uint32_t)(t3 - t2);
+                a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t3);
+            }
         }
         __syncwarp();
     }

@@ -70,7 +70,8 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl, dbg;
+    bool debug = false;
     uint64_t cap_cand = 0, cap_tier2 = 0;
     uint32_t n_tiles_a = 0, n_tiles_b = 0;
 
@@ -175,6 +176,7 @@ int ensure_capacity(surtr_ctx* ctx)
     CK(ctx->cand.reserve(sizeof(uint2) * ctx->cap_cand));
     CK(ctx->cand_rec.reserve(sizeof(CandRec) * ctx->cap_cand));
     CK(ctx->ovf_list.reserve(4 * ctx->cap_cand));
+    if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
     CK(ctx->scratch1.reserve(blob_bytes<Tier1>() * ctx->cap_cand));
     CK(ctx->scratch2.reserve(blob_bytes<Tier2>() * ctx->cap_tier2));
     // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
@@ -271,6 +273,7 @@ int launch_event(surtr_ctx* ctx)
     ca.ovf_list = ctx->ovf_list.as<uint32_t>();
     ca.cap_tier2 = ctx->cap_tier2;
     ca.ctl = d_ctl;
+    ca.dbg = ctx->debug ? ctx->dbg.as<uint32_t>() : nullptr;
     {
         ca.scratch = ctx->scratch1.as<unsigned char>();
         ca.slot_bytes = blob_bytes<Tier1>();
@@ -422,7 +425,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
-                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->dbg, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -611,4 +614,21 @@ int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
 }
 
 int surtr_last_event_launches(const surtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Development aids (csrc/surtr_debug.h, not part of the drop-in ABI): per-candidate cycle counters of K3.
+int surtr_debug_enable(surtr_ctx* ctx, int on)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    ctx->debug = on != 0;
+    return SURTR_OK;
+}
+
+int surtr_debug_read(surtr_ctx* ctx, uint32_t* out, uint64_t n_cand)
+{
+    if (!ctx || !ctx->debug) return SURTR_ERR_INVALID;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy(out, ctx->dbg.p, 32 * std::min<uint64_t>(n_cand, ctx->cap_cand), cudaMemcpyDeviceToHost));
+    return SURTR_OK;
+}
 }

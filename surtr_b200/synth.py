@@ -1,0 +1,146 @@
+"""Synthetic workloads of the BASELINE.json shapes, built with the PRODUCT path only (no oracle).
+
+Voronoi cell sets are derived from the seeds' Delaunay neighbours: cell i = the container box Poly::GetBB()
+(Poly.cpp:587-617) cut by the bisector half-spaces Plane((Si+Sj)*0.5, Sj-Si) towards its neighbours j (ascending)
+-- the cutting itself runs on the GPU through the C ABI (one "cell" per plane list, one unit-cube piece).  Cell
+faces then get their planes the way a VMACH::PolygonFace does (VMACH.cpp:289-310): Plane(v0, v1, v2) of the first
+three distinct loop vertices.  This replaces the voro++ call sites Surtr.cpp:2007-2067 (dependency not vendored).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+f32 = np.float32
+
+
+@dataclass
+class CellSet:
+    """A Voronoi pattern: polyhedra (usable as convex pieces) + outward face planes (usable as cells)."""
+    verts: np.ndarray       # float32 [NV,4]
+    vert_off: np.ndarray    # uint32 [n+1]
+    ring_off: np.ndarray    # uint32 [NV+1]
+    ring: np.ndarray        # uint16 [NE]
+    planes: np.ndarray      # float32 [NF,4]
+    plane_off: np.ndarray   # uint32 [n+1]
+
+    @property
+    def n(self) -> int:
+        return len(self.vert_off) - 1
+
+
+def seeds_uniform(seed: int, n: int) -> np.ndarray:
+    """Surtr::GenerateVoronoi seeds (Surtr.cpp:1988-1998): std::mt19937(seed), uniform_real_distribution<double>
+    (-0.5, 0.5) in x, y, z order, narrowed to float.  libstdc++ draws two 32-bit words per double."""
+    rs = np.random.RandomState(seed)
+    raw = rs.randint(0, 2 ** 32, size=6 * n, dtype=np.uint64)
+    r = (raw[0::2].astype(np.float64) + raw[1::2].astype(np.float64) * 4294967296.0) / 18446744073709551616.0
+    r = np.minimum(r, np.nextafter(1.0, 0.0))
+    return (r * 1.0 + (-0.5)).reshape(n, 3).astype(f32)
+
+
+def unit_cube():
+    """Poly::GetBB() in the flat layout."""
+    v = np.array([[-.5, -.5, -.5], [.5, -.5, -.5], [.5, .5, -.5], [-.5, .5, -.5],
+                  [-.5, -.5, .5], [.5, -.5, .5], [.5, .5, .5], [-.5, .5, .5]], f32)
+    nb = np.array([[1, 4, 3], [5, 0, 2], [3, 6, 1], [7, 2, 0], [5, 7, 0], [1, 6, 4], [5, 2, 7], [4, 6, 3]], np.uint16)
+    verts = np.zeros((8, 4), f32)
+    verts[:, :3] = v
+    return verts, np.array([0, 8], np.uint32), np.arange(0, 25, 3, dtype=np.uint32), nb.reshape(-1).copy()
+
+
+def delaunay_neighbors(seeds: np.ndarray):
+    """Neighbour CSR (ascending j) of the seeds' 3-D Delaunay triangulation."""
+    from scipy.spatial import Delaunay
+    d = Delaunay(seeds.astype(np.float64))
+    indptr, indices = d.vertex_neighbor_vertices
+    off = indptr.astype(np.uint32)
+    idx = np.concatenate([np.sort(indices[indptr[i]:indptr[i + 1]]) for i in range(len(seeds))]).astype(np.uint32)
+    return off, idx
+
+
+def bisector_planes(seeds: np.ndarray, nb_off: np.ndarray, nb_idx: np.ndarray) -> np.ndarray:
+    """Plane((Si+Sj)*0.5, Sj-Si) = (n, -Dot(mid, n)) with SimpleMath's op order ((x*x' + y*y') + z*z')."""
+    i = np.repeat(np.arange(len(seeds)), np.diff(nb_off).astype(np.int64))
+    si, sj = seeds[i].astype(f32), seeds[nb_idx].astype(f32)
+    mid = (si + sj) * f32(0.5)
+    n = sj - si
+    w = -((mid[:, 0] * n[:, 0] + mid[:, 1] * n[:, 1]) + mid[:, 2] * n[:, 2])
+    return np.concatenate([n, w[:, None]], axis=1).astype(f32)
+
+
+def _plane_from_points(p1, p2, p3):
+    """SimpleMath Plane(p1,p2,p3) (SimpleMath.inl:2773-2780) in float32, one rounding per operation."""
+    a, b = (p1 - p2).astype(f32), (p1 - p3).astype(f32)
+    n = np.array([f32(a[1] * b[2]) - f32(a[2] * b[1]), f32(a[2] * b[0]) - f32(a[0] * b[2]),
+                  f32(a[0] * b[1]) - f32(a[1] * b[0])], f32)
+    lsq = f32(f32(f32(n[0] * n[0]) + f32(n[1] * n[1])) + f32(n[2] * n[2]))
+    if lsq == 0:
+        n = np.zeros(3, f32)
+    else:
+        n = (n / np.sqrt(lsq, dtype=f32)).astype(f32)
+    w = -f32(f32(f32(n[0] * p1[0]) + f32(n[1] * p1[1])) + f32(n[2] * p1[2]))
+    return np.array([n[0], n[1], n[2], w], f32)
+
+
+def face_planes(verts, vert_off, ring_off, ring):
+    """Faces in Poly::ExtractFaces order (Poly.cpp:89-126), plane per face by the PolygonFace::AddVertex route."""
+    planes, plane_off = [], [0]
+    ring = ring.astype(np.int64)
+    for i in range(len(vert_off) - 1):
+        v0, v1 = int(vert_off[i]), int(vert_off[i + 1])
+        rings = [ring[ring_off[v]:ring_off[v + 1]].tolist() for v in range(v0, v1)]
+        pos = verts[v0:v1, :3]
+        visited = set()
+        for a in range(v1 - v0):
+            for b in rings[a]:
+                if (a, b) in visited:
+                    continue
+                loop, prev, cur = [a], a, b
+                while cur != a:
+                    visited.add((prev, cur))
+                    loop.append(cur)
+                    r = rings[cur]
+                    k = r.index(prev)
+                    prev, cur = cur, r[k - 1]
+                visited.add((prev, cur))
+                kept = []
+                for v in loop:
+                    p = pos[v]
+                    if any(float(np.sqrt(np.sum((p - q) ** 2, dtype=f32))) < 1e-12 for q in kept):
+                        continue
+                    kept.append(p)
+                    if len(kept) == 3:
+                        break
+                planes.append(_plane_from_points(*kept) if len(kept) == 3 else np.array([0, 1, 0, 0], f32))
+        plane_off.append(len(planes))
+    return np.asarray(planes, f32).reshape(-1, 4), np.asarray(plane_off, np.uint32)
+
+
+def voronoi_cells(ctx, seeds: np.ndarray, nb_off=None, nb_idx=None) -> CellSet:
+    """Voronoi cells of `seeds` in the unit container box, cut on the GPU (ctx: surtr_b200.FractureContext)."""
+    if nb_off is None:
+        nb_off, nb_idx = delaunay_neighbors(seeds)
+    cv, cvo, cro, cr = unit_cube()
+    ctx.upload_pieces(cv, cvo, cro, cr)
+    ctx.upload_cells(bisector_planes(seeds, nb_off, nb_idx), nb_off)     # unbounded cells: every pair is clipped
+    ctx.fracture_event()
+    fr = ctx.download()
+    if fr.n != len(seeds):
+        raise RuntimeError("degenerate seed set: some Voronoi cell is empty")
+    planes, plane_off = face_planes(fr.verts, fr.vert_off, fr.ring_off, fr.ring)
+    return CellSet(fr.verts, fr.vert_off, fr.ring_off, fr.ring, planes, plane_off)
+
+
+def algorithmic_bytes(pieces_vert_off, pieces_ring_off, plane_off, rec) -> int:
+    """compulsory traffic of the clip + assembly per surviving pair:
+    16*V_in + 4*E2_in + 16*P_cell + 16*V_out + 4*E2_out + 64."""
+    p = rec["piece"].astype(np.int64)
+    c = rec["cell"].astype(np.int64)
+    v_in = (pieces_vert_off[p + 1] - pieces_vert_off[p]).astype(np.int64)
+    e_in = (pieces_ring_off[pieces_vert_off[p + 1]] - pieces_ring_off[pieces_vert_off[p]]).astype(np.int64)
+    pl = (plane_off[c + 1] - plane_off[c]).astype(np.int64)
+    v_out = rec["n_verts"].astype(np.int64)
+    e_out = rec["n_ring"].astype(np.int64)
+    return int(np.sum(16 * v_in + 4 * e_in + 16 * pl + 16 * v_out + 4 * e_out + 64))

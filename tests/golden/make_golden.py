@@ -1,0 +1,171 @@
+"""Generates the committed fixtures under tests/golden/ from the REFERENCE build (oracle/_ref/libsurtr_ref.so =
+the reference's own Src/Poly.cpp, Src/Kdop.cpp, Src/VMACH.cpp, Inc/DT3D.h compiled headless by oracle/Makefile).
+
+Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
+The reference has no tests or golden vectors of its own; these are outputs of the reference
+itself run here, which is what pins the oracle port and the CUDA path.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import common  # noqa: E402
+from oracle import refapi as R  # noqa: E402
+
+REF_MODELS = "/root/reference/Resources/Models"
+
+
+def save_polyset(d, prefix, ps, full=True):
+    d[prefix + "verts"] = ps.verts
+    d[prefix + "vert_off"] = ps.vert_off
+    d[prefix + "ring_off"] = ps.ring_off
+    d[prefix + "ring"] = ps.ring
+    if full:
+        for k in ("cell", "piece", "nfaces", "volume", "centroid"):
+            d[prefix + k] = getattr(ps, k)
+    if ps.planes is not None:
+        d[prefix + "planes"] = ps.planes
+        d[prefix + "plane_off"] = ps.poly_face_off
+
+
+def scalar_kats():
+    rng = np.random.RandomState(7)
+    planes = rng.uniform(-1, 1, (400, 4)).astype(np.float32)
+    pts = rng.uniform(-1, 1, (400, 3)).astype(np.float32)
+    # force exact in-plane / near-plane cases (the |s| < 1e-10 band, Poly.cpp:719)
+    for i in range(0, 100):
+        n = planes[i, :3]
+        p = pts[i]
+        planes[i, 3] = -np.float32((np.float32(n[0] * p[0]) + np.float32(n[1] * p[1])) + np.float32(n[2] * p[2]))
+    planes[100:110] = [[1, 0, 0, -0.5]] * 10
+    pts[100:110, 0] = [0.5, np.nextafter(np.float32(0.5), np.float32(1)), np.nextafter(np.float32(0.5), np.float32(0)),
+                       0.5 + 1e-10, 0.5 - 1e-10, 0.5, 0.5, -0.5, 0.0, 1.0]
+    comp = np.array([R.compare_plane_point(planes[i], pts[i]) for i in range(400)], np.int32)
+    a = rng.uniform(-1, 1, (400, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (400, 3)).astype(np.float32)
+    inter = np.stack([R.plane_line_intersection(a[i], b[i], planes[i]) for i in range(400)])
+    c = rng.uniform(-1, 1, (400, 3)).astype(np.float32)
+    p3 = np.stack([R.plane_from_points(a[i], b[i], c[i]) for i in range(400)])
+    pn = np.stack([R.plane_from_point_normal(a[i], b[i]) for i in range(400)])
+    np.savez_compressed(os.path.join(HERE, "kat_scalar.npz"), planes=planes, pts=pts, comp=comp, a=a, b=b, c=c,
+                        inter=inter, plane3=p3, plane_pn=pn, box_planes=R.box_planes())
+
+
+def small_events():
+    d = {}
+    cube = R.unit_cube()
+    s = R.seeds_uniform(46354, 64)
+    off, idx, _ = R.dt3d_neighbors(s)           # the reference's own DT3D::Triangulate
+    cells = R.voronoi_cells(s, off, idx)
+    d["seeds"] = s
+    d["nb_off"] = off
+    d["nb_idx"] = idx
+    save_polyset(d, "cells_", cells)
+    save_polyset(d, "pieces_", cube, full=False)
+    save_polyset(d, "frag_", R.apply_fracture(cube, cells.planes, cells.plane_off, 0))
+    np.savez_compressed(os.path.join(HERE, "cube_x64.npz"), **d)
+
+    d = {}
+    sp = R.seeds_uniform(1234, 200)
+    po, pi, _ = R.dt3d_neighbors(sp)
+    pieces = R.voronoi_cells(sp, po, pi)
+    sc = R.seeds_uniform(46354, 32)
+    co, ci, _ = R.dt3d_neighbors(sc)
+    cells = R.voronoi_cells(sc, co, ci)
+    d["piece_seeds"] = sp
+    d["cell_seeds"] = sc
+    d["piece_nb_off"], d["piece_nb_idx"], d["cell_nb_off"], d["cell_nb_idx"] = po, pi, co, ci
+    save_polyset(d, "cells_", cells)
+    save_polyset(d, "pieces_", pieces)
+    save_polyset(d, "frag_", R.apply_fracture(pieces, cells.planes, cells.plane_off, 16))   # dp::thread_pool(16)
+    np.savez_compressed(os.path.join(HERE, "pieces200_x32.npz"), **d)
+
+
+def load_obj(path, scale):
+    """Surtr::LoadModelData (Surtr.cpp:2683-2727): v/f only, x negated (:2714), winding flipped."""
+    v, f = [], []
+    for line in open(path):
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "v":
+            v.append([-float(t[1]) * scale, float(t[2]) * scale, float(t[3]) * scale])
+        elif t[0] == "f":
+            idx = [int(x.split("/")[0]) - 1 for x in t[1:]]
+            for k in range(1, len(idx) - 1):
+                f.append([idx[0], idx[k + 1], idx[k]])
+    return np.asarray(v, np.float32), np.asarray(f, np.int32)
+
+
+def config1_kdop():
+    """Config 1 front end on the bundled bunny (scale 70, Surtr.cpp:1400): ICH normals -> k-DOP with gap ->
+    ACH = 2x bbox clipped by [Min0, Max0, Min1, ...] (PrepareFracture steps 1-6, Surtr.cpp:1747-1785)."""
+    d = {}
+    for name, scale in (("lowpoly-bunny-closed", 70.0), ("cube", 3.0), ("highpoly-sphere", 5.0)):
+        path = os.path.join(REF_MODELS, name + ".obj")
+        v, _ = load_obj(path, scale)
+        v4 = np.zeros((len(v), 4), np.float32)
+        v4[:, :3] = v
+        normals = R.ich_normals(v4, 20)
+        lo, hi = v.min(0).astype(np.float64), v.max(0).astype(np.float64)
+        max_axis = float(np.max(hi - lo))
+        dist, planes, vtx = R.kdop_calc_gap(v4, normals, max_axis, 2000.0)
+        dist2, planes2, vtx2 = R.kdop_calc_poly(v4, normals)
+        # ACH seed: GetBB scaled by extent, by 2, translated to the centre (float ops of Poly::Scale/Translate)
+        cube = common.unit_cube()
+        ext = (hi - lo).astype(np.float32)
+        ctr = ((hi + lo) / 2.0).astype(np.float32)
+        cv = cube.verts.copy()
+        cv[:, :3] = (cv[:, :3] * ext) * np.float32(2.0) + ctr
+        cube.verts = cv
+        ach = R.clip_each(cube, planes.reshape(-1, 4), np.array([0, 2 * len(normals)], np.uint32))
+        key = name.split("-")[-2] if "-" in name else name
+        key = {"lowpoly-bunny-closed": "bunny", "cube": "cube", "highpoly-sphere": "sphere"}[name]
+        d[key + "_verts"] = v4
+        d[key + "_normals"] = normals
+        d[key + "_gap_dist"], d[key + "_gap_planes"], d[key + "_gap_vtx"] = dist, planes, vtx
+        d[key + "_poly_dist"], d[key + "_poly_planes"], d[key + "_poly_vtx"] = dist2, planes2, vtx2
+        d[key + "_seedbox_verts"] = cv
+        save_polyset(d, key + "_ach_", ach)
+        print(key, "ICH faces", len(normals), "ACH", ach.nverts, ach.nfaces, ach.volume)
+    np.savez_compressed(os.path.join(HERE, "config1_kdop.npz"), **d)
+
+
+def summaries():
+    out = {}
+    cube = common.unit_cube()
+    # config 2: unit cube x 4096 cells
+    cells = common.voronoi(46354, 4096)
+    out["config2_cube_x4096"] = common.summary_of_polyset(R.apply_fracture(cube, cells.planes, cells.plane_off, 16))
+    # config 4, event 0: 1000 pieces x 64 cells
+    out["config4_e0_1000x64"] = common.summary_of_polyset(
+        R.apply_fracture(common.voronoi(1234, 1000), common.voronoi(46354, 64).planes,
+                         common.voronoi(46354, 64).plane_off, 16))
+    # config 3: 10000 pieces x 256 cells
+    c3 = common.voronoi(46354, 256)
+    out["config3_10000x256"] = common.summary_of_polyset(
+        R.apply_fracture(common.voronoi(1234, 10000), c3.planes, c3.plane_off, 16))
+    # config 5: depth-3 recursion, 64 seeds per level
+    pieces = cube
+    for lvl, cells in enumerate(common.recursion_levels()):
+        fr = R.apply_fracture(pieces, cells.planes, cells.plane_off, 16)
+        out[f"config5_level{lvl}"] = common.summary_of_polyset(fr)
+        pieces = fr
+    json.dump(out, open(os.path.join(HERE, "summaries.json"), "w"), indent=1, sort_keys=True)
+    for k, v in out.items():
+        print(k, v["n"], v["n_verts"], v["sum_volume"])
+
+
+if __name__ == "__main__":
+    assert R.available(), "build oracle/_ref first: make -C oracle ref"
+    scalar_kats()
+    small_events()
+    config1_kdop()
+    summaries()

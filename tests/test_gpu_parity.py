@@ -1,0 +1,237 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on identical inputs.
+
+Bar (BASELINE.json north_star): piece-to-cell assignments and per-fragment vertex/face counts bit-exact; vertex
+positions within 1e-5 relative; volumes closing on the parent.  The kernels reproduce the reference's vertex
+numbering, ring order and accumulation order, so everything below is asserted BITWISE, which implies the bar."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import GOLDEN, bits
+from oracle import portapi as P
+from test_oracle_port import load_polyset
+
+pytestmark = pytest.mark.gpu
+
+
+def _summaries():
+    return json.load(open(os.path.join(GOLDEN, "summaries.json")))
+
+
+@pytest.mark.parametrize("name", ["cube_x64", "pieces200_x32"])
+def test_golden_fixture_events(ctx, name):
+    """Committed outputs of the REFERENCE build (tests/golden/make_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    for k in (3, 7, 13):      # every broad-phase direction set must keep exactly the reference's fragments
+        ctx.set_kdop_directions(k)
+        got = common.run_gpu(ctx, pieces, cells)
+        common.assert_fragments_equal(got, want)
+    ctx.set_kdop_directions(3)
+    got = common.run_gpu(ctx, pieces, cells, bounded=False)     # no cell bounds: every pair reaches the clipper
+    common.assert_fragments_equal(got, want)
+    assert ctx.counts().n_candidates == pieces.n * cells.n
+
+
+def test_config2_cube_x4096(ctx):
+    cells = common.voronoi(46354, 4096)
+    cube = common.unit_cube()
+    got = common.run_gpu(ctx, cube, cells)
+    want = P.apply_fracture(cube, cells.planes, cells.plane_off)
+    common.assert_fragments_equal(got, want)
+    assert common.summary_of_fragments(got) == _summaries()["config2_cube_x4096"]
+    # closure: fragment volumes sum to the parent as closely as the reference's own do
+    assert abs(got.rec["volume"].sum() - 1.0) <= abs(want.volume.sum() - 1.0) + 1e-12
+    assert abs(got.rec["volume"].sum() - 1.0) < 5e-6
+
+
+def test_config3_10000x256(ctx):
+    cells = common.voronoi(46354, 256)
+    pieces = common.voronoi(1234, 10000)
+    got = common.run_gpu(ctx, pieces, cells)
+    want = P.apply_fracture(pieces, cells.planes, cells.plane_off)
+    common.assert_fragments_equal(got, want)
+    assert got.n == 23864 and common.summary_of_fragments(got) == _summaries()["config3_10000x256"]
+    c = ctx.counts()
+    assert c.n_pairs == 2_560_000 and c.n_candidates < 3 * c.n_fragments
+    assert abs(got.rec["volume"].sum() - 1.0) < 1e-6
+
+
+def test_config4_batched_events(ctx):
+    """Independent events in one batch: event e = 1000-seed pieces (mt19937(1234+e)) x 64-seed cells
+    (mt19937(46354+e)); result = the per-event oracle results back to back (event-major order)."""
+    n_ev = 4
+    psets = [common.voronoi(1234 + e, 1000) for e in range(n_ev)]
+    csets = [common.voronoi(46354 + e, 64) for e in range(n_ev)]
+    pieces, ev_p = common.concat(psets)
+    cells, ev_c = common.concat(csets)
+    got = common.run_gpu(ctx, pieces, cells, ev_p, ev_c)
+    f0 = 0
+    for e in range(n_ev):
+        want = P.apply_fracture(psets[e], csets[e].planes, csets[e].plane_off)
+        sl = slice(f0, f0 + want.n)
+        assert np.array_equal(got.rec["cell"][sl], want.cell + ev_c[e])
+        assert np.array_equal(got.rec["piece"][sl], want.piece + ev_p[e])
+        assert np.array_equal(got.rec["n_verts"][sl], want.nverts)
+        assert np.array_equal(got.rec["n_faces"][sl], want.nfaces)
+        v0 = int(got.rec["vert_off"][f0])
+        assert np.array_equal(bits(got.verts[v0:v0 + len(want.verts)]), bits(want.verts))
+        assert np.array_equal(bits(got.rec["volume"][sl]), bits(want.volume))
+        if e == 0:
+            assert want.n == 2841
+        f0 += want.n
+    assert f0 == got.n
+
+
+def test_config5_recursive_refracture(ctx):
+    """Depth-3 re-fracture with fragments staying on the device as the next level's pieces."""
+    pieces = common.unit_cube()
+    levels = common.recursion_levels()
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+    want_pieces = pieces
+    for lvl, cells in enumerate(levels):
+        ctx.upload_cells(cells.planes, cells.plane_off, cells.verts, cells.vert_off)
+        ctx.fracture_event()
+        got = ctx.download()
+        want = P.apply_fracture(want_pieces, cells.planes, cells.plane_off)
+        common.assert_fragments_equal(got, want)
+        assert common.summary_of_fragments(got) == _summaries()[f"config5_level{lvl}"]
+        want_pieces = want
+        ctx.fragments_to_pieces()
+    assert got.n == 1620
+
+
+def test_edge_cases(ctx):
+    cube = common.unit_cube()
+    cells = common.voronoi(46354, 64)
+    # no cells / no pieces -> no fragments
+    empty_cells_off = np.zeros(1, np.uint32)
+    ctx.upload_pieces(cube.verts, cube.vert_off, cube.ring_off, cube.ring)
+    ctx.upload_cells(np.zeros((0, 4), np.float32), empty_cells_off)
+    ctx.fracture_event()
+    assert ctx.download().n == 0
+    ctx.upload_pieces(np.zeros((0, 4), np.float32), np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(0, np.uint16))
+    ctx.upload_cells(cells.planes, cells.plane_off, cells.verts, cells.vert_off)
+    ctx.fracture_event()
+    assert ctx.download().n == 0
+    # a cell with an empty plane list keeps every piece whole; a far-away half-space removes it
+    planes = np.array([[1, 0, 0, 2.0]], np.float32)        # x + 2 <= 0 : everything clipped
+    ctx.upload_pieces(cube.verts, cube.vert_off, cube.ring_off, cube.ring)
+    ctx.upload_cells(planes, np.array([0, 0, 1], np.uint32))
+    ctx.fracture_event()
+    fr = ctx.download()
+    assert fr.n == 1 and int(fr.rec["cell"][0]) == 0 and int(fr.rec["n_verts"][0]) == 8 and fr.rec["volume"][0] == 1.0
+    # ragged batch: events with zero pieces or zero cells in the middle
+    p2, c2 = common.voronoi(7, 40), common.voronoi(8, 12)
+    pieces, _ = common.concat([p2, p2])
+    cells2, _ = common.concat([c2, c2])
+    ev_p = np.array([0, 40, 40, 80, 80], np.uint32)
+    ev_c = np.array([0, 12, 24, 24, 24], np.uint32)
+    got = common.run_gpu(ctx, pieces, cells2, ev_p, ev_c)
+    want = P.apply_fracture(p2, c2.planes, c2.plane_off)
+    assert got.n == want.n and np.array_equal(got.rec["n_verts"], want.nverts)
+    assert np.array_equal(bits(got.verts), bits(want.verts))
+
+
+def test_large_tier_pieces_and_kdop_clip(ctx):
+    """Config-1 front end: ACH = 2x bbox clipped by the 2k k-DOP planes (Kdop.cpp:166-179).  The bunny / sphere
+    ACHs (107 / 135 vertices) then exceed the 64-vertex tier and are cut in the 256-vertex tier."""
+    d = np.load(os.path.join(GOLDEN, "config1_kdop.npz"))
+    for key in ("bunny", "cube", "sphere"):
+        want = load_polyset(d, key + "_ach_")
+        box = common.unit_cube()
+        box.verts = d[key + "_seedbox_verts"]
+        planes = d[key + "_gap_planes"].reshape(-1, 4)
+        ctx.upload_pieces(box.verts, box.vert_off, box.ring_off, box.ring)
+        ctx.upload_cells(planes, np.array([0, len(planes)], np.uint32))
+        ctx.fracture_event()
+        got = ctx.download()
+        assert got.n == 1
+        assert np.array_equal(bits(got.verts), bits(want.verts)) and np.array_equal(got.ring, want.ring)
+        assert int(got.rec["n_faces"][0]) == int(want.nfaces[0])
+        assert np.array_equal(bits(got.rec["volume"]), bits(want.volume))
+        # now cut the ACH itself by a cell set scaled onto it (pieces beyond the small tier)
+        if key != "cube":
+            ach = want
+            lo, hi = ach.verts[:, :3].min(0), ach.verts[:, :3].max(0)
+            cells = common.voronoi(46354, 32)
+            cp = cells.subset(range(cells.n))
+            cp.verts = cells.verts.copy()
+            cp.verts[:, :3] = cells.verts[:, :3] * (hi - lo) + (hi + lo) / 2
+            # planes of the scaled cells, rebuilt from their vertices like Polygon3D::Scale/Translate does
+            # (VMACH.cpp:506-534): PolygonFace::AddVertex route of the oracle
+            scaled = cp
+            planes2, off2 = P.face_planes(scaled)
+            want_fr = P.apply_fracture(ach, planes2, off2)
+            ctx.upload_pieces(ach.verts, ach.vert_off, ach.ring_off, ach.ring)
+            ctx.upload_cells(planes2, off2, scaled.verts, scaled.vert_off)
+            ctx.fracture_event()
+            got = ctx.download()
+            common.assert_fragments_equal(got, want_fr)
+            assert ctx.counts().n_tier2 > 0
+
+
+def test_kdop_calc(ctx):
+    d = np.load(os.path.join(GOLDEN, "config1_kdop.npz"))
+    for key in ("bunny", "cube", "sphere"):
+        v4, normals = d[key + "_verts"], d[key + "_normals"]
+        dist, arg, planes = ctx.kdop_calc(v4, normals)
+        pd, pa, pp = P.kdop_calc(v4, normals)
+        assert np.array_equal(bits(dist), bits(pd)) and np.array_equal(arg, pa) and np.array_equal(bits(planes), bits(pp))
+        assert np.array_equal(dist.astype(np.float64), d[key + "_poly_dist"])
+        assert np.array_equal(bits(planes), bits(d[key + "_poly_planes"]))
+
+
+def test_inertia_against_double_precision_oracle(ctx):
+    """No in-repo reference for inertia (PhysX, Surtr.cpp:2520): compare with the oracle's independent double
+    precision polyhedral integral, tolerance 1e-4 relative to the tensor's scale (float32 vertex data)."""
+    cells = common.voronoi(46354, 64)
+    pieces = common.voronoi(1234, 300)
+    got = common.run_gpu(ctx, pieces, cells)
+    want = P.apply_fracture(pieces, cells.planes, cells.plane_off, inertia=True)
+    assert got.n == want.n
+    scale = np.abs(want.inertia[:, :3]).max(axis=1, keepdims=True)
+    big = want.volume > 1e-9                      # slivers have no meaningful tensor
+    err = np.abs(got.rec["inertia"].astype(np.float64) - want.inertia) / np.maximum(scale, 1e-300)
+    assert err[big].max() < 1e-4
+    cube = common.unit_cube()
+    ctx.upload_pieces(cube.verts, cube.vert_off, cube.ring_off, cube.ring)
+    ctx.upload_cells(np.zeros((0, 4), np.float32), np.array([0, 0], np.uint32))
+    ctx.fracture_event()
+    fr = ctx.download()
+    assert np.allclose(fr.rec["inertia"][0], [1 / 6, 1 / 6, 1 / 6, 0, 0, 0], atol=1e-6)
+
+
+def test_determinism_and_rerun_growth(ctx):
+    """Same event twice -> identical bytes; a fresh context with tiny buffers grows and still matches."""
+    from surtr_b200 import FractureContext
+    cells = common.voronoi(46354, 256)
+    pieces = common.voronoi(1234, 3000)
+    a = common.run_gpu(ctx, pieces, cells)
+    b = common.run_gpu(ctx, pieces, cells)
+    assert a.rec.tobytes() == b.rec.tobytes() and a.verts.tobytes() == b.verts.tobytes()
+    assert a.ring.tobytes() == b.ring.tobytes()
+    c2 = FractureContext(0)
+    small = common.unit_cube()
+    c2.upload_pieces(small.verts, small.vert_off, small.ring_off, small.ring)
+    c2.upload_cells(common.voronoi(5, 8).planes, common.voronoi(5, 8).plane_off)
+    c2.fracture_event()
+    c2.download()
+    c = common.run_gpu(c2, pieces, cells)
+    assert a.rec.tobytes() == c.rec.tobytes() and a.verts.tobytes() == c.verts.tobytes()
+    c2.close()
+
+
+def test_product_voronoi_builder_matches_oracle(ctx):
+    """surtr_b200.synth.voronoi_cells (GPU clipper + host face planes) == the oracle's cell builder, bitwise."""
+    from surtr_b200 import synth
+    s = common.seeds_uniform(46354, 512)
+    assert np.array_equal(s, synth.seeds_uniform(46354, 512))
+    off, idx = common.scipy_neighbors(s)
+    got = synth.voronoi_cells(ctx, s, off, idx)
+    want = P.voronoi_cells(s, off, idx)
+    assert np.array_equal(bits(got.verts), bits(want.verts)) and np.array_equal(got.ring, want.ring)
+    assert np.array_equal(got.plane_off, want.plane_off) and np.array_equal(bits(got.planes), bits(want.planes))
