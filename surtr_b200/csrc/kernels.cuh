@@ -8,7 +8,7 @@
 //       kdop_arg_kernel          Kdop::KdopContainer::Calc(Polyhedron) with first-extremal-vertex semantics
 #pragma once
 
-#include "clip_warp.cuh"
+#include "clip_fast.cuh"
 #include "scan.cuh"
 #include "../../include/surtr_b200.h"
 
@@ -413,7 +413,144 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
     if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
 }
 
+// K3, small tier: one warp per candidate pair (no persistent loop: the hardware scheduler balances the very
+// uneven pair costs), ring words in shared memory (clip_fast.cuh).
+constexpr int FAST_WARPS = 4;
+constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs a)
+{
+    __shared__ FastPoly s_poly[FAST_WARPS];
+    FastPoly& sp = s_poly[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long q64 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long n_items = a.ctl->n_cand;
+    if (n_items > a.cap_cand) n_items = a.cap_cand;
+    if (q64 >= n_items) return;
+    const uint32_t q = (uint32_t)q64;
+    const long long t0 = a.dbg ? clock64() : 0;
+
+    const uint2 pr = a.cand[q];
+    const uint32_t v0 = a.p_vert_off[pr.x];
+    int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+    const uint32_t pl0 = a.c_plane_off[pr.y];
+    const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+    bool bad = nv > 64;
+    if (!bad)
+    {
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+        {
+            const int v = lane + 32 * g;
+            if (v < nv)
+            {
+                const float4 p = __ldg(a.p_verts + v0 + v);
+                const uint32_t r0 = a.p_ring_off[v0 + v];
+                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                u64 rw = ~0ull;
+                if (d > 8 || d == 0) bad = true;
+                else
+                    for (int j = 0; j < d; j++)
+                    {
+                        const int idx = a.p_ring[r0 + j];
+                        bad = bad || idx >= nv;
+                        rw = rset(rw, j, idx);
+                    }
+                sp.ring[v] = rw;
+            }
+        }
+    }
+    bad = __ballot_sync(FULL, bad) != 0u;
+    __syncwarp();
+    const long long t1 = a.dbg ? clock64() : 0;
+    const int nv_in = nv;
+    unsigned seq_cuts = 0, n_cuts = 0;
+    int status = CLIP_OVERFLOW;
+    CutState cs;
+    if (!bad) status = fast_clip_by_planes(sp, cs, nv, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
+    const long long t2 = a.dbg ? clock64() : 0;
+    if (a.dbg && lane == 0)
+    {
+        uint32_t* d = a.dbg + (size_t)q * 8;
+        d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
+        d[4] = seq_cuts; d[5] = n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl;
+    }
+    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+    CandRec* rec = a.rec + q;
+    if (status != CLIP_OK)
+    {
+        // too large for this tier (or a ring outgrew 8 slots): queue the pair for the large tier
+        if (lane == 0)
+        {
+            rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+            a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
+        }
+        return;
+    }
+    if (nv == 0)
+    {
+        if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
+        return;
+    }
+    Moments mo;
+    fast_fragment_moments(sp, cs, lane, mo);
+    const long long t3 = a.dbg ? clock64() : 0;
+
+    // result blob, renumbered to the reference's final order (rank in the live mask):
+    // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
+    const unsigned long long blob = (unsigned long long)q * FAST_BLOB;
+    unsigned char* b = a.scratch + blob;
+    float4* bv = reinterpret_cast<float4*>(b);
+    uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
+    uint8_t* br = b + 64 * 18;
+    const bool live0 = (cs.l0 >> lane) & 1u, live1 = (cs.l1 >> lane) & 1u;
+    const u64 rw0 = live0 ? sp.ring[lane] : ~0ull;
+    const u64 rw1 = live1 ? sp.ring[lane + 32] : ~0ull;
+    const int d0 = rdeg(rw0), d1 = rdeg(rw1);
+    int tot;
+    const int ex = warp_exscan(d0 | (d1 << 16), lane, tot);
+    const int ne0 = tot & 0xffff, ne = ne0 + (tot >> 16);
+    if (live0)
+    {
+        const int t = rank64(cs.l0, cs.l1, lane);
+        bv[t] = make_float4(sp.x[lane], sp.y[lane], sp.z[lane], 0.f);
+        const int off = ex & 0xffff;
+        bo[t] = (uint16_t)off;
+        for (int j = 0; j < d0; j++) br[off + j] = (uint8_t)rank64(cs.l0, cs.l1, rget(rw0, j));
+    }
+    if (live1)
+    {
+        const int v = lane + 32;
+        const int t = rank64(cs.l0, cs.l1, v);
+        bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+        const int off = ne0 + (ex >> 16);
+        bo[t] = (uint16_t)off;
+        for (int j = 0; j < d1; j++) br[off + j] = (uint8_t)rank64(cs.l0, cs.l1, rget(rw1, j));
+    }
+    if (lane == 0)
+    {
+        rec->nv = (uint32_t)nv;
+        rec->ne = (uint32_t)ne;
+        rec->nf = (uint32_t)mo.n_faces;
+        rec->tier = 1;
+        rec->volume = mo.volume;
+        rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
+#pragma unroll
+        for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
+        rec->blob = blob;
+        if (a.dbg)
+        {
+            a.dbg[(size_t)q * 8 + 2] = (uint32_t)(t3 - t2);
+            a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t3);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- K4
+// Fragment assembly = ordered compaction of the non-empty clip results.  Two launches: a scan over the candidate
+// records (decoupled look-back, one thread per candidate) that hands every non-empty candidate its fragment
+// index, first vertex and first ring entry, then a gather with one warp per candidate.
 struct AssembleArgs
 {
     const uint2* cand;
@@ -424,6 +561,7 @@ struct AssembleArgs
     int cap1, cap2;             // vertex capacity (blob layout) of tier 1 / tier 2
     ScanState<3> st;
     Ctl* ctl;
+    uint4* out_off;             // per candidate: fragment index, first vertex, first ring entry
     surtr_fragment* f_rec;
     float4* f_verts;
     uint32_t* f_ring_off;
@@ -432,7 +570,7 @@ struct AssembleArgs
 };
 
 constexpr int AS_THREADS = 256;
-__global__ void __launch_bounds__(AS_THREADS) assemble_kernel(AssembleArgs a)
+__global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs a)
 {
     __shared__ int s_tile;
     __shared__ unsigned int s_w[AS_THREADS / 32][3];
@@ -479,65 +617,65 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_kernel(AssembleArgs a)
                     a.ctl->n_frag = ex[0] + btot[0];
                     a.ctl->n_fverts = ex[1] + btot[1];
                     a.ctl->n_fring = ex[2] + btot[2];
+                    if (ex[1] + btot[1] <= a.cap_fverts) a.f_ring_off[ex[1] + btot[1]] = (uint32_t)(ex[2] + btot[2]);
                 }
             }
         }
         __syncthreads();
-        const unsigned long long fi = s_excl[0] + bex[0] + e0;
-        const unsigned long long vb = s_excl[1] + bex[1] + e1;
-        const unsigned long long rb = s_excl[2] + bex[2] + e2;
+        if (q < n_cand)
+            a.out_off[q] = make_uint4((uint32_t)(s_excl[0] + bex[0] + e0), (uint32_t)(s_excl[1] + bex[1] + e1),
+                                      (uint32_t)(s_excl[2] + bex[2] + e2), 0u);
+    }
+}
 
-        // each warp gathers its 32 candidates one after the other, all lanes copying
-        const unsigned live = __ballot_sync(FULL, has);
-        unsigned todo = live;
-        while (todo)
-        {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const unsigned long long cq = __shfl_sync(FULL, q, src);
-            const unsigned long long cfi = __shfl_sync(FULL, fi, src);
-            const unsigned long long cvb = __shfl_sync(FULL, vb, src);
-            const unsigned long long crb = __shfl_sync(FULL, rb, src);
-            const int cnv = __shfl_sync(FULL, (int)nv, src);
-            const int cne = __shfl_sync(FULL, (int)ne, src);
-            if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) continue;
-            const CandRec* r = a.rec + cq;
-            const int tier = r->tier;
-            const int cap = tier == 1 ? a.cap1 : a.cap2;
-            const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
-            const float4* bv = reinterpret_cast<const float4*>(b);
-            const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
-            for (int v = lane; v < cnv; v += 32)
-            {
-                a.f_verts[cvb + v] = bv[v];
-                a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
-            }
-            if (tier == 1)
-            {
-                const uint8_t* br = b + (size_t)cap * 18;
-                for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
-            }
-            else
-            {
-                const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
-                for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
-            }
-            if (lane == 0)
-            {
-                const uint2 pr = a.cand[cq];
-                surtr_fragment f;
-                f.cell = pr.y; f.piece = pr.x;
-                f.vert_off = (uint32_t)cvb;
-                f.n_verts = (uint16_t)cnv;
-                f.n_faces = (uint16_t)r->nf;
-                f.volume = r->volume;
-                f.centroid[0] = r->centroid[0]; f.centroid[1] = r->centroid[1]; f.centroid[2] = r->centroid[2];
+__global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long n_cand = a.ctl->n_cand;
+    if (n_cand > a.cap_cand) n_cand = a.cap_cand;
+    if (q >= n_cand) return;
+    const CandRec* r = a.rec + q;
+    const int cnv = (int)r->nv;
+    if (cnv == 0) return;
+    const int cne = (int)r->ne;
+    const uint4 off = a.out_off[q];
+    const unsigned long long cfi = off.x, cvb = off.y, crb = off.z;
+    if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) return;
+    const int tier = r->tier;
+    const int cap = tier == 1 ? a.cap1 : a.cap2;
+    const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
+    const float4* bv = reinterpret_cast<const float4*>(b);
+    const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
+    for (int v = lane; v < cnv; v += 32)
+    {
+        a.f_verts[cvb + v] = bv[v];
+        a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+    }
+    if (tier == 1)
+    {
+        const uint8_t* br = b + (size_t)cap * 18;
+        for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+    }
+    else
+    {
+        const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
+        for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+    }
+    if (lane == 0)
+    {
+        const uint2 pr = a.cand[q];
+        surtr_fragment f;
+        f.cell = pr.y; f.piece = pr.x;
+        f.vert_off = (uint32_t)cvb;
+        f.n_verts = (uint16_t)cnv;
+        f.n_faces = (uint16_t)r->nf;
+        f.volume = r->volume;
+        f.centroid[0] = r->centroid[0]; f.centroid[1] = r->centroid[1]; f.centroid[2] = r->centroid[2];
 #pragma unroll
-                for (int k = 0; k < 6; k++) f.inertia[k] = r->inertia[k];
-                f.n_ring = (uint32_t)cne;
-                a.f_rec[cfi] = f;
-            }
-        }
+        for (int k = 0; k < 6; k++) f.inertia[k] = r->inertia[k];
+        f.n_ring = (uint32_t)cne;
+        a.f_rec[cfi] = f;
     }
 }
 

@@ -15,9 +15,7 @@ using namespace surtr;
 
 namespace
 {
-using Tier1 = WarpPoly<64, 8, uint8_t>;
 using Tier2 = WarpPoly<256, 16, uint16_t>;
-constexpr int T1_WARPS = 4;
 constexpr int T2_WARPS = 2;
 
 std::string g_create_error;
@@ -70,7 +68,7 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl, dbg;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl, dbg, out_off;
     bool debug = false;
     uint64_t cap_cand = 0, cap_tier2 = 0;
     uint32_t n_tiles_a = 0, n_tiles_b = 0;
@@ -176,8 +174,9 @@ int ensure_capacity(surtr_ctx* ctx)
     CK(ctx->cand.reserve(sizeof(uint2) * ctx->cap_cand));
     CK(ctx->cand_rec.reserve(sizeof(CandRec) * ctx->cap_cand));
     CK(ctx->ovf_list.reserve(4 * ctx->cap_cand));
+    CK(ctx->out_off.reserve(16 * ctx->cap_cand));
     if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
-    CK(ctx->scratch1.reserve(blob_bytes<Tier1>() * ctx->cap_cand));
+    CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
     CK(ctx->scratch2.reserve(blob_bytes<Tier2>() * ctx->cap_tier2));
     // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
     const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
@@ -276,11 +275,9 @@ int launch_event(surtr_ctx* ctx)
     ca.dbg = ctx->debug ? ctx->dbg.as<uint32_t>() : nullptr;
     {
         ca.scratch = ctx->scratch1.as<unsigned char>();
-        ca.slot_bytes = blob_bytes<Tier1>();
-        const size_t smem = sizeof(Tier1) * T1_WARPS;
-        const uint64_t want = (ctx->cap_cand + T1_WARPS - 1) / T1_WARPS;
-        const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->num_sm * 14));
-        clip_kernel<Tier1, 1, T1_WARPS><<<blocks, T1_WARPS * 32, smem, ctx->stream>>>(ca);
+        ca.slot_bytes = FAST_BLOB;
+        const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + FAST_WARPS - 1) / FAST_WARPS);
+        clip_fast_kernel<<<(unsigned)blocks, FAST_WARPS * 32, 0, ctx->stream>>>(ca);
         ctx->launches++;
     }
     {
@@ -300,7 +297,7 @@ int launch_event(surtr_ctx* ctx)
         aa.cap_cand = ctx->cap_cand;
         aa.scratch1 = ctx->scratch1.as<unsigned char>();
         aa.scratch2 = ctx->scratch2.as<unsigned char>();
-        aa.cap1 = Tier1::CAP;
+        aa.cap1 = 64;
         aa.cap2 = Tier2::CAP;
         aa.st = ScanState<3>{ flags_b, agg_b, inc_b };
         aa.ctl = d_ctl;
@@ -311,10 +308,12 @@ int launch_event(surtr_ctx* ctx)
         aa.cap_frag = ctx->cap_frag;
         aa.cap_fverts = ctx->cap_fverts;
         aa.cap_fring = ctx->cap_fring;
+        aa.out_off = ctx->out_off.as<uint4>();
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
-        assemble_kernel<<<blocks, AS_THREADS, 0, ctx->stream>>>(aa);
+        assemble_scan_kernel<<<blocks, AS_THREADS, 0, ctx->stream>>>(aa);
         ctx->launches++;
-        finish_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_ctl, ctx->f_ring_off.as<uint32_t>(), ctx->cap_fverts);
+        const uint64_t gblocks = std::max<uint64_t>(1, (ctx->cap_cand + 7) / 8);
+        assemble_gather_kernel<<<(unsigned)gblocks, 256, 0, ctx->stream>>>(aa);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -425,7 +424,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
-                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->dbg, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
