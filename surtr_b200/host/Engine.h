@@ -1,0 +1,50 @@
+// Engine.h -- internal glue between the host-side mirror classes and the C ABI (include/surtr_b200.h):
+// AoS (Poly::Polyhedron, VMACH::Polygon3D) <-> the flat layout, and one lazily created context per host thread.
+#pragma once
+
+#include "../../include/surtr_b200.h"
+#include "Poly.h"
+#include "VMACH.h"
+
+#include <cstdint>
+#include <vector>
+
+namespace SurtrHost
+{
+namespace detail
+{
+struct FlatPolys
+{
+	std::vector<float> verts4;
+	std::vector<uint32_t> vert_off{ 0 }, ring_off{ 0 };
+	std::vector<uint16_t> ring;
+	void add(const Poly::Polyhedron& p);
+	uint32_t count() const { return (uint32_t)vert_off.size() - 1; }
+};
+
+struct FlatCells
+{
+	std::vector<float> planes4;
+	std::vector<uint32_t> plane_off{ 0 };
+	std::vector<float> cverts4;       // every vertex of every face loop (bounds for the broad phase)
+	std::vector<uint32_t> cvert_off{ 0 };
+	bool bounded = true;
+	void add(const VMACH::Polygon3D& cell);
+	void add(const std::vector<Poly::Plane>& planes);   // unbounded cell (plain plane list)
+	uint32_t count() const { return (uint32_t)plane_off.size() - 1; }
+};
+
+struct Fragments
+{
+	std::vector<surtr_fragment> rec;
+	std::vector<float> verts4;
+	std::vector<uint32_t> ring_off;
+	std::vector<uint16_t> ring;
+	Poly::Polyhedron polyhedron(size_t i) const;
+};
+
+surtr_ctx* context();                                            // throws std::runtime_error without a B200
+void check(int rc, const char* what);                            // throws std::runtime_error with surtr_last_error
+void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true);
+} // namespace detail
+} // namespace SurtrHost

@@ -1,0 +1,82 @@
+// Fracture.h -- headless mirror of the fracture members of class Surtr (Inc/Surtr.h:89-155, 172-215).
+//
+// The reference keeps these as private members of its DX12 application class; here they are a plain namespace so
+// the path runs without a window, a device or PhysX.  ApplyFracture is the drop-in for Surtr::ApplyFracture
+// (Surtr.cpp:2098-2149): instead of one thread-pool task per cell (m_fractureTask, :1457-1504) it packs the
+// compound's convex pieces and the cell planes once, runs ONE GPU fracture event through the C ABI and unpacks the
+// fragments in the reference's order.  The mesh branch of m_fractureTask (:1470-1500) is the "next" row f-1.
+#pragma once
+
+#include "Poly.h"
+#include "VMACH.h"
+
+#include <set>
+#include <vector>
+
+namespace SurtrHost
+{
+using DirectX::XMFLOAT3;
+using DirectX::SimpleMath::Vector3;
+
+struct FractureArgs   // Inc/Surtr.h:89-110, same defaults
+{
+	int ICHIncludePointLimit = 20;
+	float ACHPlaneGapInverse = 2000.0f;
+	int RefittingPointLimit = 4;
+	int Seed = 46354;
+	XMFLOAT3 ImpactPosition = XMFLOAT3(0.f, 0.f, 0.f);
+	float ImpactRadius = 1.0f;
+	bool RadialMode = true;
+	bool PartialFracture = true;
+	float PartialFracturePatternDist = 0.01f;
+	float GeneralFracturePatternDist = 1.0f;
+	int InitialDecomposeCellCnt = 64;
+	int PartialFracturePatternCellCnt = 128;
+	int GeneralFracturePatternCellCnt = 1024;
+	float TargetAdder = 0.01f;
+};
+
+struct Piece   // Inc/Surtr.h:113-119; always allocated on the heap
+{
+	Poly::Polyhedron Convex;
+	Poly::Polyhedron Mesh;
+	Piece(const Poly::Polyhedron& convex, const Poly::Polyhedron& mesh) : Convex(convex), Mesh(mesh) {}
+};
+
+typedef std::vector<std::vector<int>> Extract;
+
+struct MassProperties   // per piece, unit density; replaces PxRigidBodyExt::updateMassAndInertia (Surtr.cpp:2520)
+{
+	double Volume = 0.0;
+	Vector3 Centroid;
+	float Inertia[6] = { 0, 0, 0, 0, 0, 0 };   // Ixx Iyy Izz Ixy Ixz Iyz about the centroid
+	int FaceCount = 0;
+};
+
+struct CompoundInfo   // Inc/Surtr.h:123-128 (+ the per-piece results K4 computes)
+{
+	std::vector<Piece*> PieceVec;
+	std::vector<Extract*> PieceExtractedConvex;
+	std::vector<std::set<int>> CompoundBind;   // [0] reserved for "outside"; one set per non-empty cell, cell order
+	std::vector<MassProperties> PieceMass;
+	std::vector<int> PieceSourceCell, PieceSourcePiece;
+};
+
+struct Compound   // Inc/Surtr.h:130-134
+{
+	std::vector<Piece*> PieceVec;
+	std::vector<Extract*> PieceExtractedConvex;
+};
+
+// Surtr::GenerateVoronoi(cellCount) seeds (Surtr.cpp:1984-2001): mt19937(seed), U(-0.5, 0.5), x/y/z order.
+std::vector<Vector3> GenerateSeeds(int seed, int cellCount);
+// Radial pattern seeds of Surtr::GenerateFracturePattern (Surtr.cpp:2072-2096).
+std::vector<Vector3> GenerateRadialSeeds(int seed, int cellCount, double mean);
+// Surtr::GenerateVoronoi(points): DT3D-derived cells (voro++ is not vendored).
+std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPointVec);
+
+// Surtr::ApplyFracture, non-partial convex branch.  Throws std::runtime_error on a C-ABI failure.
+CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec);
+// Surtr::SetExtract (Surtr.cpp:2151-2155).
+void SetExtract(CompoundInfo& preResult);
+} // namespace SurtrHost

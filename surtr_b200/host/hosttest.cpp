@@ -1,0 +1,264 @@
+// hosttest.cpp -- flat C entry points over the host-side mirror CLASSES, so the Python tests can drive the
+// class-level API (Poly / Kdop / VMACH / DT3D / SurtrHost) exactly as a C++ caller would.  Test harness only.
+#include "DT3D.h"
+#include "Fracture.h"
+#include "Kdop.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+using DirectX::SimpleMath::Plane;
+using DirectX::SimpleMath::Vector3;
+
+namespace
+{
+std::string g_err;
+
+Poly::Polyhedron to_poly(const float* verts, const uint32_t* ring_off, const uint16_t* ring, uint32_t v0, uint32_t v1)
+{
+	std::vector<Vector3> pos;
+	std::vector<std::vector<int>> nei;
+	for (uint32_t v = v0; v < v1; v++)
+	{
+		pos.emplace_back(verts[4 * v], verts[4 * v + 1], verts[4 * v + 2]);
+		nei.emplace_back(ring + ring_off[v], ring + ring_off[v + 1]);
+	}
+	Poly::Polyhedron p;
+	Poly::InitPolyhedron(p, pos, nei);
+	return p;
+}
+
+struct Out
+{
+	std::vector<float> verts;
+	std::vector<uint32_t> vert_off{ 0 }, ring_off{ 0 }, cell, piece, nfaces, plane_off{ 0 };
+	std::vector<uint16_t> ring;
+	std::vector<double> volume;
+	std::vector<float> centroid, planes;
+	void add(const Poly::Polyhedron& p)
+	{
+		for (const auto& v : p)
+		{
+			verts.insert(verts.end(), { v.Position.x, v.Position.y, v.Position.z, 0.f });
+			for (int n : v.NeighborVertexVec) ring.push_back((uint16_t)n);
+			ring_off.push_back((uint32_t)ring.size());
+		}
+		vert_off.push_back((uint32_t)(verts.size() / 4));
+	}
+};
+Out g_out;
+} // namespace
+
+extern "C"
+{
+const char* hosttest_error() { return g_err.c_str(); }
+
+// sizes: n_poly, n_verts, n_ring, n_planes
+void hosttest_sizes(uint64_t* s)
+{
+	s[0] = g_out.vert_off.size() - 1; s[1] = g_out.verts.size() / 4; s[2] = g_out.ring.size(); s[3] = g_out.planes.size() / 4;
+}
+
+#define CP(dst, vec) if (dst) std::memcpy(dst, (vec).data(), (vec).size() * sizeof((vec)[0]))
+void hosttest_export(float* verts, uint32_t* vert_off, uint32_t* ring_off, uint16_t* ring, uint32_t* cell, uint32_t* piece,
+					 uint32_t* nfaces, double* volume, float* centroid, float* planes, uint32_t* plane_off)
+{
+	CP(verts, g_out.verts); CP(vert_off, g_out.vert_off); CP(ring_off, g_out.ring_off); CP(ring, g_out.ring);
+	CP(cell, g_out.cell); CP(piece, g_out.piece); CP(nfaces, g_out.nfaces); CP(volume, g_out.volume);
+	CP(centroid, g_out.centroid); CP(planes, g_out.planes); CP(plane_off, g_out.plane_off);
+}
+
+// SurtrHost::GenerateSeeds + DT3D::Neighbors (CPU only)
+int hosttest_seeds(int seed, int n, float* out)
+{
+	const auto s = SurtrHost::GenerateSeeds(seed, n);
+	for (int i = 0; i < n; i++) { out[3 * i] = s[i].x; out[3 * i + 1] = s[i].y; out[3 * i + 2] = s[i].z; }
+	return 0;
+}
+
+uint64_t hosttest_dt3d_neighbors(const float* seeds, uint32_t n, uint32_t* off, uint32_t* idx, uint64_t cap)
+{
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n; i++) s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	std::vector<uint32_t> o, x;
+	DT3D::Neighbors(s, o, x);
+	std::memcpy(off, o.data(), 4 * o.size());
+	if (x.size() <= cap) std::memcpy(idx, x.data(), 4 * x.size());
+	return x.size();
+}
+
+// DT3D::Triangulate by value: returns the tet count and the number of tets whose circumsphere contains another seed
+int hosttest_dt3d_triangulate(const float* seeds, uint32_t n, uint32_t* n_tets, uint32_t* n_faces, uint32_t* n_voronoi_edges)
+{
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n; i++) s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	const DT3D::Delaunay dt = DT3D::Triangulate(s);
+	*n_tets = (uint32_t)dt.TetVec.size();
+	*n_faces = (uint32_t)dt.FaceVec.size();
+	*n_voronoi_edges = (uint32_t)DT3D::Voronoi(dt).size();
+	int violations = 0;
+	for (const auto& t : dt.TetVec)
+		for (const auto& p : s)
+			if (!(p == t.p0 || p == t.p1 || p == t.p2 || p == t.p3) && Vector3::Distance(t.sphere.center, p) < t.sphere.radius * (1.f - 1e-4f))
+				violations++;
+	return violations;
+}
+
+// VMACH::GetBoxPolygon planes + PolygonFace semantics (CPU only)
+void hosttest_box_planes(float* out24)
+{
+	const VMACH::Polygon3D box = VMACH::GetBoxPolygon();
+	for (int f = 0; f < 6; f++)
+		std::memcpy(out24 + 4 * f, &box.FaceVec[f].FacePlane.x, 16);
+}
+
+// Poly::ExtractFaces (host bookkeeping) on a flat polyhedron: returns face count, writes loops
+int hosttest_extract_faces(const float* verts, const uint32_t* ring_off, const uint16_t* ring, uint32_t nv, uint32_t* face_off, uint16_t* face_idx)
+{
+	const Poly::Polyhedron p = to_poly(verts, ring_off, ring, 0, nv);
+	Poly::Extract* e = Poly::ExtractFaces(p);
+	uint32_t w = 0;
+	face_off[0] = 0;
+	for (size_t f = 0; f < e->size(); f++)
+	{
+		for (int v : (*e)[f]) face_idx[w++] = (uint16_t)v;
+		face_off[f + 1] = w;
+	}
+	const int n = (int)e->size();
+	delete e;
+	return n;
+}
+
+// Scalar helpers
+int hosttest_compare_plane_point(const float* pl, const float* p) { return Poly::ComparePlanePoint(Plane(pl[0], pl[1], pl[2], pl[3]), Vector3(p[0], p[1], p[2])); }
+void hosttest_plane_line_intersection(const float* a, const float* b, const float* pl, float* out)
+{
+	const Vector3 r = Poly::PlaneLineIntersection(Vector3(a[0], a[1], a[2]), Vector3(b[0], b[1], b[2]), Plane(pl[0], pl[1], pl[2], pl[3]));
+	out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+// ---- GPU-backed class API ----
+// SurtrHost::GenerateVoronoi(seeds) -> cells as polyhedra-free Polygon3D: exports planes + face vertices
+int hosttest_voronoi(const float* seeds, uint32_t n)
+{
+	try
+	{
+		std::vector<Vector3> s;
+		for (uint32_t i = 0; i < n; i++) s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+		const auto cells = SurtrHost::GenerateVoronoi(s);
+		g_out = Out();
+		for (const auto& c : cells)
+		{
+			for (const auto& f : c.FaceVec)
+				g_out.planes.insert(g_out.planes.end(), { f.FacePlane.x, f.FacePlane.y, f.FacePlane.z, f.FacePlane.w });
+			g_out.plane_off.push_back((uint32_t)(g_out.planes.size() / 4));
+		}
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// SurtrHost::ApplyFracture + SetExtract over Compound / Polygon3D objects built from flat inputs.
+// Cells are given as planes + face-vertex streams (one PolygonFace per plane, vertices split evenly is not needed:
+// the clipper reads only FacePlane; the vertex stream of the whole cell is attached to its first face for the bounds).
+int hosttest_apply_fracture(const float* verts, const uint32_t* vert_off, const uint32_t* ring_off, const uint16_t* ring, uint32_t n_pieces,
+							const float* planes, const uint32_t* plane_off, const float* cverts, const uint32_t* cvert_off, uint32_t n_cells)
+{
+	try
+	{
+		SurtrHost::Compound compound;
+		for (uint32_t i = 0; i < n_pieces; i++)
+		{
+			const Poly::Polyhedron p = to_poly(verts, ring_off, ring, vert_off[i], vert_off[i + 1]);
+			compound.PieceVec.push_back(new SurtrHost::Piece(p, p));
+		}
+		std::vector<VMACH::Polygon3D> cells;
+		for (uint32_t c = 0; c < n_cells; c++)
+		{
+			VMACH::Polygon3D poly(true);
+			for (uint32_t k = plane_off[c]; k < plane_off[c + 1]; k++)
+			{
+				VMACH::PolygonFace f(true);
+				if (k == plane_off[c])
+					for (uint32_t v = cvert_off[c]; v < cvert_off[c + 1]; v++)
+						f.VertexVec.emplace_back(cverts[4 * v], cverts[4 * v + 1], cverts[4 * v + 2]);
+				else
+					f.VertexVec.emplace_back(cverts[4 * cvert_off[c]], cverts[4 * cvert_off[c] + 1], cverts[4 * cvert_off[c] + 2]);
+				f.ManuallySetFacePlane(Plane(planes[4 * k], planes[4 * k + 1], planes[4 * k + 2], planes[4 * k + 3]));
+				poly.AddFace(f);
+			}
+			cells.push_back(poly);
+		}
+		SurtrHost::CompoundInfo info = SurtrHost::ApplyFracture(compound, cells);
+		SurtrHost::SetExtract(info);
+		g_out = Out();
+		for (size_t i = 0; i < info.PieceVec.size(); i++)
+		{
+			g_out.add(info.PieceVec[i]->Convex);
+			g_out.cell.push_back((uint32_t)info.PieceSourceCell[i]);
+			g_out.piece.push_back((uint32_t)info.PieceSourcePiece[i]);
+			g_out.nfaces.push_back((uint32_t)info.PieceExtractedConvex[i]->size());
+			// Poly::Moments through the class API for the first few pieces, K4's record for all
+			g_out.volume.push_back(info.PieceMass[i].Volume);
+			g_out.centroid.insert(g_out.centroid.end(), { info.PieceMass[i].Centroid.x, info.PieceMass[i].Centroid.y, info.PieceMass[i].Centroid.z });
+			if ((int)info.PieceExtractedConvex[i]->size() != info.PieceMass[i].FaceCount) { g_err = "face count mismatch between ExtractFaces and K4"; return 2; }
+		}
+		// bind sets: consecutive, one per non-empty cell
+		size_t expect = 0;
+		for (size_t b = 1; b < info.CompoundBind.size(); b++)
+			for (int idx : info.CompoundBind[b])
+				if ((size_t)idx != expect++) { g_err = "CompoundBind order"; return 3; }
+		for (auto* p : compound.PieceVec) delete p;
+		for (auto* p : info.PieceVec) delete p;
+		for (auto* e : info.PieceExtractedConvex) delete e;
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Poly::ClipPolyhedron (in place) + Poly::Moments + Kdop::KdopContainer through the class API
+int hosttest_clip_and_moments(const float* verts, const uint32_t* ring_off, const uint16_t* ring, uint32_t nv, const float* planes, uint32_t npl,
+							  double* volume, float* centroid)
+{
+	try
+	{
+		Poly::Polyhedron p = to_poly(verts, ring_off, ring, 0, nv);
+		std::vector<Plane> pls;
+		for (uint32_t k = 0; k < npl; k++) pls.emplace_back(planes[4 * k], planes[4 * k + 1], planes[4 * k + 2], planes[4 * k + 3]);
+		Poly::ClipPolyhedron(p, pls);
+		g_out = Out();
+		g_out.add(p);
+		Vector3 c;
+		Poly::Moments(*volume, c, p);
+		centroid[0] = c.x; centroid[1] = c.y; centroid[2] = c.z;
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+int hosttest_kdop_ach(const float* verts, uint32_t nv, const float* normals, uint32_t k, double maxAxisScale, float gapInv,
+					  const float* boxverts, float* out_planes)
+{
+	try
+	{
+		std::vector<Vector3> vv, nn;
+		for (uint32_t i = 0; i < nv; i++) vv.emplace_back(verts[4 * i], verts[4 * i + 1], verts[4 * i + 2]);
+		for (uint32_t i = 0; i < k; i++) nn.emplace_back(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+		Kdop::KdopContainer kd(nn);
+		kd.Calc(vv, maxAxisScale, gapInv);
+		for (uint32_t i = 0; i < k; i++)
+		{
+			std::memcpy(out_planes + 8 * i, &kd.ElementVec[i].MinPlane.x, 16);
+			std::memcpy(out_planes + 8 * i + 4, &kd.ElementVec[i].MaxPlane.x, 16);
+		}
+		Poly::Polyhedron box = Poly::GetBB();
+		for (int i = 0; i < 8; i++) box[i].Position = Vector3(boxverts[4 * i], boxverts[4 * i + 1], boxverts[4 * i + 2]);
+		const Poly::Polyhedron ach = kd.ClipWithPolyhedron(box);
+		g_out = Out();
+		g_out.add(ach);
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+}

@@ -33,6 +33,9 @@ def save_polyset(d, prefix, ps, full=True):
     if ps.planes is not None:
         d[prefix + "planes"] = ps.planes
         d[prefix + "plane_off"] = ps.poly_face_off
+    if ps.face_idx is not None:     # Poly::ExtractFaces loops of the reference build
+        d[prefix + "face_off"] = ps.face_off
+        d[prefix + "face_idx"] = ps.face_idx
 
 
 def scalar_kats():

@@ -1,0 +1,135 @@
+"""ctypes binding of surtr_b200/libsurtr_hosttest.so: flat entry points over the C++ host-side mirror classes
+(Poly / Kdop / VMACH / DT3D / SurtrHost), used by the tests to drive the class-level API like a C++ caller."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle.refapi import PolySet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "surtr_b200", "libsurtr_hosttest.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH)
+        _lib.hosttest_error.restype = C.c_char_p
+        _lib.hosttest_dt3d_neighbors.restype = C.c_uint64
+        _lib.hosttest_dt3d_neighbors.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+        _lib.hosttest_kdop_ach.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_float,
+                                           C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _err():
+    return lib().hosttest_error().decode()
+
+
+def export() -> PolySet:
+    L = lib()
+    sizes = np.zeros(4, np.uint64)
+    L.hosttest_sizes(_p(sizes))
+    n, nv, ne, npl = (int(x) for x in sizes)
+    ps = PolySet(np.zeros((nv, 4), np.float32), np.zeros(n + 1, np.uint32), np.zeros(nv + 1, np.uint32),
+                 np.zeros(ne, np.uint16), cell=np.zeros(n, np.uint32), piece=np.zeros(n, np.uint32),
+                 nfaces=np.zeros(n, np.uint32), volume=np.zeros(n, np.float64), centroid=np.zeros((n, 3), np.float32))
+    ps.planes = np.zeros((npl, 4), np.float32)
+    L.hosttest_export(_p(ps.verts), _p(ps.vert_off), _p(ps.ring_off), _p(ps.ring), _p(ps.cell), _p(ps.piece),
+                      _p(ps.nfaces), _p(ps.volume), _p(ps.centroid), _p(ps.planes), None)
+    return ps
+
+
+def seeds(seed, n):
+    out = np.zeros((n, 3), np.float32)
+    lib().hosttest_seeds(seed, n, _p(out))
+    return out
+
+
+def dt3d_neighbors(s):
+    s = np.ascontiguousarray(s, np.float32)
+    off = np.zeros(len(s) + 1, np.uint32)
+    idx = np.zeros(64 * len(s) + 64, np.uint32)
+    n = lib().hosttest_dt3d_neighbors(_p(s), len(s), _p(off), _p(idx), len(idx))
+    return off, idx[:int(n)].copy()
+
+
+def dt3d_triangulate(s):
+    s = np.ascontiguousarray(s, np.float32)
+    nt, nf, ne = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    viol = lib().hosttest_dt3d_triangulate(_p(s), len(s), C.byref(nt), C.byref(nf), C.byref(ne))
+    return nt.value, nf.value, ne.value, viol
+
+
+def box_planes():
+    out = np.zeros((6, 4), np.float32)
+    lib().hosttest_box_planes(_p(out))
+    return out
+
+
+def extract_faces(verts4, ring_off, ring):
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    ro = np.ascontiguousarray(ring_off - ring_off[0], np.uint32)
+    ring = np.ascontiguousarray(ring, np.uint16)
+    fo = np.zeros(len(ring) + 2, np.uint32)
+    fi = np.zeros(len(ring) + 2, np.uint16)
+    n = lib().hosttest_extract_faces(_p(verts4), _p(ro), _p(ring), len(verts4), _p(fo), _p(fi))
+    return [fi[fo[f]:fo[f + 1]].tolist() for f in range(n)]
+
+
+def compare_plane_point(plane, p):
+    plane, p = np.ascontiguousarray(plane, np.float32), np.ascontiguousarray(p, np.float32)
+    return lib().hosttest_compare_plane_point(_p(plane), _p(p))
+
+
+def plane_line_intersection(a, b, plane):
+    a, b, plane = (np.ascontiguousarray(x, np.float32) for x in (a, b, plane))
+    out = np.zeros(3, np.float32)
+    lib().hosttest_plane_line_intersection(_p(a), _p(b), _p(plane), _p(out))
+    return out
+
+
+def voronoi_planes(s):
+    s = np.ascontiguousarray(s, np.float32)
+    if lib().hosttest_voronoi(_p(s), len(s)):
+        raise RuntimeError(_err())
+    sizes = np.zeros(4, np.uint64)
+    lib().hosttest_sizes(_p(sizes))
+    planes = np.zeros((int(sizes[3]), 4), np.float32)
+    off = np.zeros(len(s) + 1, np.uint32)
+    lib().hosttest_export(None, None, None, None, None, None, None, None, None, _p(planes), _p(off))
+    return planes, off
+
+
+def apply_fracture(pieces: PolySet, cells: PolySet) -> PolySet:
+    rc = lib().hosttest_apply_fracture(_p(pieces.verts), _p(pieces.vert_off), _p(pieces.ring_off), _p(pieces.ring), pieces.n,
+                                       _p(cells.planes), _p(cells.plane_off), _p(cells.verts), _p(cells.vert_off), cells.n)
+    if rc:
+        raise RuntimeError(_err())
+    return export()
+
+
+def clip_and_moments(ps: PolySet, planes):
+    planes = np.ascontiguousarray(planes, np.float32)
+    vol = C.c_double(0)
+    cen = np.zeros(3, np.float32)
+    rc = lib().hosttest_clip_and_moments(_p(ps.verts), _p(ps.ring_off), _p(ps.ring), len(ps.verts), _p(planes), len(planes),
+                                         C.byref(vol), _p(cen))
+    if rc:
+        raise RuntimeError(_err())
+    return export(), vol.value, cen
+
+
+def kdop_ach(verts4, normals, max_axis, gap_inv, boxverts4):
+    verts4, normals, boxverts4 = (np.ascontiguousarray(x, np.float32) for x in (verts4, normals, boxverts4))
+    planes = np.zeros((len(normals), 2, 4), np.float32)
+    rc = lib().hosttest_kdop_ach(_p(verts4), len(verts4), _p(normals), len(normals), max_axis, gap_inv, _p(boxverts4), _p(planes))
+    if rc:
+        raise RuntimeError(_err())
+    return planes, export()

@@ -1,0 +1,91 @@
+"""Host-side mirror of the reference interfaces (surtr_b200/host: Poly / Kdop / VMACH / DT3D / SurtrHost).
+CPU tests cover the pure host logic; GPU tests drive the class-level API end to end against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+import hostapi as H
+from common import GOLDEN, bits
+from oracle import portapi as P
+from test_oracle_port import load_polyset
+
+
+def test_host_seeds_match_reference_recipe():
+    assert np.array_equal(H.seeds(46354, 4096), common.seeds_uniform(46354, 4096))
+
+
+def test_host_scalar_helpers_match_reference():
+    d = np.load(os.path.join(GOLDEN, "kat_scalar.npz"))
+    n = len(d["planes"])
+    assert np.array_equal(np.array([H.compare_plane_point(d["planes"][i], d["pts"][i]) for i in range(n)], np.int32), d["comp"])
+    inter = np.stack([H.plane_line_intersection(d["a"][i], d["b"][i], d["planes"][i]) for i in range(n)])
+    assert np.array_equal(bits(inter), bits(d["inter"]))
+    assert np.array_equal(bits(H.box_planes()), bits(d["box_planes"]))     # VMACH::GetBoxPolygon, incl. -0.0 signs
+
+
+def test_host_dt3d_against_reference_and_qhull():
+    d = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
+    off, idx = H.dt3d_neighbors(d["seeds"])
+    ref = [set(d["nb_idx"][d["nb_off"][i]:d["nb_off"][i + 1]]) for i in range(64)]      # the reference's own DT3D
+    mine = [set(idx[off[i]:off[i + 1]]) for i in range(64)]
+    assert all(r <= m for r, m in zip(ref, mine))          # a far super-tetrahedron only ADDS hull-adjacent edges
+    for n in (64, 256, 2000):
+        s = common.seeds_uniform(46354, n)
+        off, idx = H.dt3d_neighbors(s)
+        o2, i2 = common.scipy_neighbors(s)
+        assert np.array_equal(off, o2) and np.array_equal(idx, i2)
+    nt, nf, ne, viol = H.dt3d_triangulate(common.seeds_uniform(46354, 256))
+    assert viol == 0 and nf == 3 * nt and nt > 1400 and ne > nt
+    assert H.dt3d_triangulate(common.seeds_uniform(1, 2))[0] == 0     # < 3 points -> empty (DT3D.h:161-162)
+
+
+def test_host_extract_faces_matches_reference_loops():
+    d = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
+    fr = load_polyset(d, "frag_")
+    foff, fidx = d["frag_face_off"], d["frag_face_idx"]
+    f0 = 0
+    for i in range(fr.n):
+        v0, v1 = int(fr.vert_off[i]), int(fr.vert_off[i + 1])
+        r0, r1 = int(fr.ring_off[v0]), int(fr.ring_off[v1])
+        got = H.extract_faces(fr.verts[v0:v1], fr.ring_off[v0:v1 + 1], fr.ring[r0:r1])
+        nf = int(fr.nfaces[i])
+        want = [fidx[foff[f]:foff[f + 1]].tolist() for f in range(f0, f0 + nf)]
+        assert got == want
+        f0 += nf
+
+
+@pytest.mark.gpu
+def test_host_apply_fracture_class_api():
+    for name in ("cube_x64", "pieces200_x32"):
+        d = np.load(os.path.join(GOLDEN, name + ".npz"))
+        cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+        got = H.apply_fracture(pieces, cells)
+        for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece", "nfaces", "volume", "centroid"):
+            assert np.array_equal(bits(getattr(got, f)), bits(getattr(want, f))), (name, f)
+
+
+@pytest.mark.gpu
+def test_host_voronoi_cells_and_clip_moments_kdop():
+    s = common.seeds_uniform(46354, 300)
+    planes, off = H.voronoi_planes(s)
+    o2, i2 = common.scipy_neighbors(s)
+    want = P.voronoi_cells(s, o2, i2)
+    assert np.array_equal(off, want.plane_off) and np.array_equal(bits(planes), bits(want.planes))
+    # Poly::ClipPolyhedron (in place) + Poly::Moments
+    cube = common.unit_cube()
+    pl = P.plane_from_point_normal([0.1, 0.05, 0.0], [1, 1, 1])
+    got, vol, cen = H.clip_and_moments(cube, pl[None])
+    w = P.clip_each(cube, pl[None], [0, 1])
+    assert np.array_equal(bits(got.verts), bits(w.verts)) and np.array_equal(got.ring, w.ring)
+    assert vol == w.volume[0] and np.array_equal(bits(cen), bits(w.centroid[0]))
+    # Kdop::KdopContainer::Calc(vertices, maxAxisScale, gapInv) + ClipWithPolyhedron = the ACH of config 1
+    d = np.load(os.path.join(GOLDEN, "config1_kdop.npz"))
+    for key in ("bunny", "cube"):
+        v4 = d[key + "_verts"]
+        ext = v4[:, :3].max(0).astype(np.float64) - v4[:, :3].min(0).astype(np.float64)
+        planes, ach = H.kdop_ach(v4, d[key + "_normals"], float(ext.max()), 2000.0, d[key + "_seedbox_verts"])
+        assert np.array_equal(bits(planes), bits(d[key + "_gap_planes"]))
+        wa = load_polyset(d, key + "_ach_")
+        assert np.array_equal(bits(ach.verts), bits(wa.verts)) and np.array_equal(ach.ring, wa.ring)
