@@ -129,8 +129,11 @@ int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out);
 int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const float* normals3, uint32_t k,
                     float* dist, int32_t* arg, float* planes8);
 
-/* Timing of the last surtr_fracture_event in milliseconds (CUDA events on the context stream). */
+/* Timing of the last surtr_fracture_event in milliseconds (CUDA events on the context stream).  clip_ms (the K3
+ * small-tier kernel alone) is only measured while profiling is on: the extra events sit between the kernels of an
+ * event and serialise their programmatic dependent launches, so they are off by default. */
 int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms);
+int surtr_set_profiling(surtr_ctx* ctx, int on);
 /* Number of kernels the last surtr_fracture_event launched. */
 int surtr_last_event_launches(const surtr_ctx* ctx);
 

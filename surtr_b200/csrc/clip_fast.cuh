@@ -438,10 +438,13 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
         if (bit64(s.l0, s.l1, v))
         {
             const u64 rw = sp.ring[v];
-            for (int j = 0; j < 8; j++)
+            const int d = rdeg(rw);
+            for (int j = 0; j < d; j++)
             {
                 int at = rget(rw, j);
-                if (at == R_NONE) break;
+                // v can only be the smallest vertex of the loop through (v -> at) if both loop neighbours of v are
+                // larger: `at`, and the vertex the loop arrives from = the ring entry after `at` (FaceLoop inverted)
+                if (at < v || rget(rw, j + 1 == d ? 0 : j + 1) < v) continue;
                 int prev = v, n = 1;
                 bool is_start = true;
                 while (at != v)
@@ -515,27 +518,31 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
     }
     __syncwarp();
 
-    // ordered accumulation (Poly.cpp:77-85) by one lane; the inertia sums are a fixed-shape tree
+    // ordered accumulation (Poly.cpp:77-85): lane c < 4 owns component c of the triangle records (dV, mx, my, mz)
+    // and adds them in the reference's order -- dV into a double, the first moments in float.  Four lanes share one
+    // instruction stream, so the serial chain costs a quarter of a single-lane loop.
     double zeroth = 0.0;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (lane == 0)
+    float fsum = 0.f;
+    if (lane < 4)
     {
+        const float* comp = reinterpret_cast<const float*>(sp.tri) + lane;
         int t = 0;
         for (; t + 4 <= n_tri; t += 4)   // the loads do not depend on the accumulation chain
         {
-            const float4 r0 = sp.tri[t], r1 = sp.tri[t + 1], r2 = sp.tri[t + 2], r3 = sp.tri[t + 3];
-            zeroth += (double)r0.x; zeroth += (double)r1.x; zeroth += (double)r2.x; zeroth += (double)r3.x;
-            fx = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fx, r0.y), r1.y), r2.y), r3.y);
-            fy = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fy, r0.z), r1.z), r2.z), r3.z);
-            fz = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fz, r0.w), r1.w), r2.w), r3.w);
+            const float r0 = comp[4 * t], r1 = comp[4 * t + 4], r2 = comp[4 * t + 8], r3 = comp[4 * t + 12];
+            zeroth += (double)r0; zeroth += (double)r1; zeroth += (double)r2; zeroth += (double)r3;
+            fsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fsum, r0), r1), r2), r3);
         }
         for (; t < n_tri; t++)
         {
-            const float4 r = sp.tri[t];
-            zeroth += (double)r.x;
-            fx = __fadd_rn(fx, r.y); fy = __fadd_rn(fy, r.z); fz = __fadd_rn(fz, r.w);
+            const float r = comp[4 * t];
+            zeroth += (double)r;
+            fsum = __fadd_rn(fsum, r);
         }
-        zeroth /= 6.0;
+    }
+    zeroth = __shfl_sync(FULL, zeroth, 0) / 6.0;
+    float fx = __shfl_sync(FULL, fsum, 1), fy = __shfl_sync(FULL, fsum, 2), fz = __shfl_sync(FULL, fsum, 3);
+    {
         const double q = 24.0 * zeroth;
         const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));   // safeInv, Poly.cpp:33
         const float sc = (float)inv;
@@ -546,8 +553,6 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             cov[k] += __shfl_xor_sync(FULL, cov[k], o);
-    zeroth = __shfl_sync(FULL, zeroth, 0);
-    fx = __shfl_sync(FULL, fx, 0); fy = __shfl_sync(FULL, fy, 0); fz = __shfl_sync(FULL, fz, 0);
 
     out.n_faces = n_faces;
     out.volume = zeroth;

@@ -14,6 +14,12 @@
 
 namespace surtr
 {
+// Programmatic dependent launch (sm_90+): every kernel of an event lets its successor's CTAs be scheduled as soon
+// as its own CTAs have all started, and waits for its predecessor's completion (and memory flush) before it
+// touches any data.  This hides the launch latency between the dependent kernels of an event.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int KMAX = 13;
 __constant__ float c_dirs[KMAX][3] = {
     { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 },                      // k = 3  : AABB
@@ -60,6 +66,8 @@ __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const ui
                                     const uint32_t* __restrict__ c_vert_off, uint32_t n_cells, float* __restrict__ ext_c,
                                     int cells_unbounded)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     // one warp per object; objects = the pieces followed by the cells (one launch for both)
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -130,6 +138,8 @@ __global__ void __launch_bounds__(256) broadphase_mask_kernel(const BpTile* __re
                                                               const float* __restrict__ ext_c,
                                                               unsigned int* __restrict__ masks)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_cell[32 * 2 * K];
     const BpTile t = tiles[blockIdx.x];
     for (int i = threadIdx.x; i < (int)t.n_cell * 2 * K; i += 256)
@@ -194,6 +204,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_pairs_kernel(const unsigne
                                                                     ScanState<1> st, Ctl* ctl,
                                                                     uint2* __restrict__ cand, uint64_t cap_cand)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_tile;
     __shared__ unsigned int s_warp[CP_THREADS / 32];
     __shared__ unsigned long long s_excl;
@@ -281,6 +293,8 @@ __host__ __device__ constexpr size_t blob_bytes()
 template <class P, int TIER, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P& sp = reinterpret_cast<P*>(smem_raw)[threadIdx.x >> 5];
     using IdxT = typename P::IdxT;
@@ -428,6 +442,8 @@ constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | 
 
 __global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ FastPoly s_poly[FAST_WARPS];
     FastPoly& sp = s_poly[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -580,6 +596,8 @@ struct AssembleArgs
 constexpr int AS_THREADS = 256;
 __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int s_tile;
     __shared__ unsigned int s_w[AS_THREADS / 32][3];
     __shared__ unsigned long long s_excl[3];
@@ -638,6 +656,8 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs 
 
 __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long n_cand = a.ctl->n_cand;

@@ -20,6 +20,24 @@ constexpr int T2_WARPS = 2;
 
 std::string g_create_error;
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled while its
+// predecessor in the stream is still draining; the kernels call griddepcontrol.wait before reading its output.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct DevBuf
 {
     void* p = nullptr;
@@ -82,6 +100,8 @@ struct surtr_ctx
     int launches = 0;
     uint32_t ctl_layout_a = 0xffffffffu, ctl_layout_b = 0xffffffffu;
     void* ctl_ptr = nullptr;
+    bool profile = false;         // per-kernel CUDA events inside an event (they serialise the PDL chain)
+    bool profiled_last = false;
     bool tier2_enabled = false;   // the large tier is launched once an event needed it
     bool event_launched = false, event_resolved = false;
     surtr_counts last{};
@@ -198,10 +218,9 @@ void launch_extents(surtr_ctx* ctx)
     if (!n_obj) return;
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((n_obj * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
-    kdop_extents_kernel<K><<<blocks, threads, 0, ctx->stream>>>(ctx->p_verts.as<float4>(), ctx->p_vert_off.as<uint32_t>(),
-                                                                ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
-                                                                ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(),
-                                                                ctx->cells_bounded ? 0 : 1);
+    launch_pdl(kdop_extents_kernel<K>, dim3(blocks), dim3(threads), 0, ctx->stream, ctx->p_verts.as<float4>(),
+               ctx->p_vert_off.as<uint32_t>(), ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
+               ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(), ctx->cells_bounded ? 0 : 1);
     ctx->launches++;
 }
 
@@ -209,8 +228,8 @@ template <int K>
 void launch_masks(surtr_ctx* ctx)
 {
     if (!ctx->n_tiles) return;
-    broadphase_mask_kernel<K><<<ctx->n_tiles, 256, 0, ctx->stream>>>(ctx->d_tiles.as<BpTile>(), ctx->ext_p.as<float>(),
-                                                                     ctx->ext_c.as<float>(), ctx->masks.as<unsigned int>());
+    launch_pdl(broadphase_mask_kernel<K>, dim3(ctx->n_tiles), dim3(256), 0, ctx->stream, ctx->d_tiles.as<BpTile>(),
+               ctx->ext_p.as<float>(), ctx->ext_c.as<float>(), ctx->masks.as<unsigned int>());
     ctx->launches++;
 }
 
@@ -256,11 +275,11 @@ int launch_event(surtr_ctx* ctx)
         EventTables et{ ctx->d_ev_mask_base.as<uint32_t>(), ctx->d_ev_piece_off.as<uint32_t>(),
                         ctx->d_ev_cell_off.as<uint32_t>(), ctx->n_events_p };
         ScanState<1> st{ flags_a, agg_a, inc_a };
-        compact_pairs_kernel<<<ctx->n_tiles_a, CP_THREADS, 0, ctx->stream>>>(ctx->masks.as<unsigned int>(), ctx->n_masks, et, st,
-                                                                             d_ctl, ctx->cand.as<uint2>(), ctx->cap_cand);
+        launch_pdl(compact_pairs_kernel, dim3(ctx->n_tiles_a), dim3(CP_THREADS), 0, ctx->stream, ctx->masks.as<unsigned int>(),
+                   ctx->n_masks, et, st, d_ctl, ctx->cand.as<uint2>(), ctx->cap_cand);
         ctx->launches++;
     }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     // K3
     ClipArgs ca;
@@ -281,7 +300,7 @@ int launch_event(surtr_ctx* ctx)
         ca.scratch = ctx->scratch1.as<unsigned char>();
         ca.slot_bytes = FAST_BLOB;
         const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + FAST_WARPS - 1) / FAST_WARPS);
-        clip_fast_kernel<<<(unsigned)blocks, FAST_WARPS * 32, 0, ctx->stream>>>(ca);
+        launch_pdl(clip_fast_kernel, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->tier2_enabled)
@@ -289,10 +308,10 @@ int launch_event(surtr_ctx* ctx)
         ca.scratch = ctx->scratch2.as<unsigned char>();
         ca.slot_bytes = blob_bytes<Tier2>();
         const size_t smem = sizeof(Tier2) * T2_WARPS;
-        clip_kernel<Tier2, 2, T2_WARPS><<<ctx->num_sm, T2_WARPS * 32, smem, ctx->stream>>>(ca);
+        launch_pdl(clip_kernel<Tier2, 2, T2_WARPS>, dim3(ctx->num_sm), dim3(T2_WARPS * 32), smem, ctx->stream, ca);
         ctx->launches++;
     }
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
 
     // K4
     {
@@ -315,16 +334,17 @@ int launch_event(surtr_ctx* ctx)
         aa.cap_fring = ctx->cap_fring;
         aa.out_off = ctx->out_off.as<uint4>();
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
-        assemble_scan_kernel<<<blocks, AS_THREADS, 0, ctx->stream>>>(aa);
+        launch_pdl(assemble_scan_kernel, dim3(blocks), dim3(AS_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
         const uint64_t gblocks = std::max<uint64_t>(1, (ctx->cap_cand + 7) / 8);
-        assemble_gather_kernel<<<(unsigned)gblocks, 256, 0, ctx->stream>>>(aa);
+        launch_pdl(assemble_gather_kernel, dim3((unsigned)gblocks), dim3(256), 0, ctx->stream, aa);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
     CK(cudaGetLastError());
+    ctx->profiled_last = ctx->profile;
     ctx->event_launched = true;
     ctx->event_resolved = false;
     return SURTR_OK;
@@ -615,11 +635,22 @@ int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
     const int rc = resolve_event(ctx);
     if (rc) return rc;
     if (total_ms) CK(cudaEventElapsedTime(total_ms, ctx->ev[0], ctx->ev[3]));
-    if (clip_ms) CK(cudaEventElapsedTime(clip_ms, ctx->ev[1], ctx->ev[2]));
+    if (clip_ms)
+    {
+        *clip_ms = 0.f;
+        if (ctx->profiled_last) CK(cudaEventElapsedTime(clip_ms, ctx->ev[1], ctx->ev[2]));
+    }
     return SURTR_OK;
 }
 
 int surtr_last_event_launches(const surtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int surtr_set_profiling(surtr_ctx* ctx, int on)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    ctx->profile = on != 0;
+    return SURTR_OK;
+}
 
 // Development aids (csrc/surtr_debug.h, not part of the drop-in ABI): per-candidate cycle counters of K3.
 int surtr_debug_enable(surtr_ctx* ctx, int on)

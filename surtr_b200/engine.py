@@ -31,7 +31,7 @@ EXPORTS = [
     "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions",
     "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
-    "surtr_last_event_ms", "surtr_last_event_launches",
+    "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
     lib.surtr_kdop_calc.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.surtr_last_event_launches.argtypes = [vp]
+    lib.surtr_set_profiling.argtypes = [vp, i32]
     _lib = lib
     return lib
 
@@ -230,6 +231,9 @@ class FractureContext:
         t, c = C.c_float(0), C.c_float(0)
         self._ck(self._lib.surtr_last_event_ms(self._h, C.byref(t), C.byref(c)))
         return t.value, c.value
+
+    def set_profiling(self, on: bool):
+        self._ck(self._lib.surtr_set_profiling(self._h, int(on)))
 
     def last_event_launches(self) -> int:
         return self._lib.surtr_last_event_launches(self._h)
