@@ -1,19 +1,23 @@
-// clip_fast.cuh -- small-tier clipper: one warp, <= 64 vertex slots, ring degree <= 8, register/ballot based.
+// clip_sub.cuh -- small-tier clipper: L lanes (a warp, half-warp or quarter-warp) clip one pair; <= 64 vertex
+// slots, ring degree <= 8, everything register/ballot based.
 //
-// Same algorithm and the same exactness argument as clip_warp.cuh (which stays as the large tier), restated for
-// the common case with a layout chosen for the warp:
+// Same algorithm and the same exactness argument as clip_warp.cuh (which stays as the large tier):
 //   * a vertex ring is ONE 64-bit shared-memory word: eight u8 neighbour indices, 0xFF padded.  FaceLoop
 //     (Poly.cpp:34-41), find-and-replace (Poly.cpp:350-353) and the degree are byte-compare instructions on a
 //     register (__vcmpeq4 / __ffs / PRMT) after a single LDS.64 -- no dependent chain of shared-memory reads;
-//   * the per-vertex classification `comp` (Poly.cpp:303-319) never touches memory: the warp ballots of
-//     "clipped" and "kept" are held by every lane and comp(j) is a bit test;
+//   * the per-vertex classification `comp` (Poly.cpp:303-319) never touches memory: the ballots of "clipped" and
+//     "kept" are held by every lane as 64-bit masks and comp(j) is a bit test;
 //   * new vertices are created one per lane from a list of straddling half-edges written in the reference's
 //     append order (vertex ascending, ring slot ascending; Poly.cpp:333-357);
 //   * compaction (Poly.cpp:464-499) is LAZY: clipped vertices just leave the live mask and new ones are appended.
 //     The reference's compaction is stable, so the relative order of live vertices is the same with or without
 //     it; indices are renumbered (popc on the live mask) only when the 64 slots run out and once at the end,
 //     which yields exactly the reference's numbering.
-// Sequential replays (in-plane vertices, walk anomalies, degree-2 splice) run on lane 0 over the same words.
+// Sequential replays (in-plane vertices, walk anomalies, degree-2 splice) run on one lane over the same words.
+//
+// Lane count: ncu on the one-warp-per-pair version showed 6-14 of 32 lanes active in every phase but the
+// classification (profiles/), so the kernel is instantiated with L = 16: two pairs per warp, each half-warp using
+// its own member mask for ballots / shuffles / __syncwarp, which roughly halves the warp-instructions per pair.
 #pragma once
 
 #include "clip_warp.cuh"
@@ -22,7 +26,7 @@ namespace surtr
 {
 typedef unsigned long long u64;
 
-struct FastPoly   // one per warp in shared memory (4032 bytes)
+struct SubPoly   // one per pair in shared memory (4032 bytes)
 {
     float x[64], y[64], z[64];
     u64 ring[64];         // 8 x u8, 0xFF = empty slot
@@ -74,56 +78,96 @@ __device__ __forceinline__ int rface_loop(u64 w, int vprev)
     return rget(w, (k == 0 ? d : k) - 1);
 }
 
-__device__ __forceinline__ bool bit64(unsigned m0, unsigned m1, int j) { return (((j & 32) ? m1 : m0) >> (j & 31)) & 1u; }
-__device__ __forceinline__ unsigned lowmask(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
-__device__ __forceinline__ int rank64(unsigned s0, unsigned s1, int u)   // set bits with index < u
-{
-    return u < 32 ? __popc(s0 & lowmask(u)) : __popc(s0) + __popc(s1 & lowmask(u - 32));
-}
+__device__ __forceinline__ bool bit64(u64 m, int j) { return (m >> j) & 1ull; }
+__device__ __forceinline__ u64 lowmask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
+__device__ __forceinline__ int rank64(u64 m, int u) { return __popcll(m & lowmask64(u)); }   // set bits below u
 
-struct CutState   // warp-uniform
+struct CutState   // uniform across the lanes of one pair
 {
-    unsigned l0, l1;   // live vertices
-    unsigned c0, c1;   // clipped by the current plane (comp == -1)
-    unsigned k0, k1;   // kept by the current plane (comp == +1)
-    int hi;            // allocated vertex slots
+    u64 live;   // live vertex slots
+    u64 c;      // clipped by the current plane (comp == -1)
+    u64 k;      // kept by the current plane (comp == +1)
+    int hi;     // allocated vertex slots
+};
+
+// The lanes that work on one pair: L consecutive lanes of a warp with their own member mask.
+template <int L>
+struct Sub
+{
+    static constexpr int G = 64 / L;   // vertex slots per lane: lane sl owns slots sl, sl + L, ...
+    int sl;
+    unsigned shift, smask;
+    __device__ __forceinline__ explicit Sub(int lane)
+    {
+        sl = lane % L;
+        shift = (unsigned)(lane / L) * L;
+        smask = L == 32 ? 0xffffffffu : (((1u << (L & 31)) - 1u) << shift);
+    }
+    __device__ __forceinline__ unsigned ballot(bool p) const
+    {
+        const unsigned b = __ballot_sync(smask, p);
+        return L == 32 ? b : ((b >> shift) & ((1u << (L & 31)) - 1u));
+    }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(smask, v, src, L); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(smask, v, d, L); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int d) const { return __shfl_xor_sync(smask, v, d, L); }
+    __device__ __forceinline__ void sync() const { __syncwarp(smask); }
+    template <class T> __device__ __forceinline__ T exscan(T v, T& total) const
+    {
+        T inc = v;
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1)
+        {
+            const T t = shfl_up(inc, o);
+            if (sl >= o) inc += t;
+        }
+        total = shfl(inc, L - 1);
+        return inc - v;
+    }
+    __device__ __forceinline__ int sum(int v) const
+    {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) v += shfl_xor(v, o);
+        return v;
+    }
 };
 
 // comp of the reference for the sequential replays: 2 = new, -1 clipped / gone, +1 kept, 0 in-plane
-__device__ __forceinline__ int comp_of(const CutState& s, int hi0, unsigned d0, unsigned d1, int j)
+__device__ __forceinline__ int comp_of(const CutState& s, int hi0, u64 dead, int j)
 {
-    if (bit64(d0, d1, j)) return -1;   // spliced away (Poly.cpp:459)
+    if (bit64(dead, j)) return -1;   // spliced away (Poly.cpp:459)
     if (j >= hi0) return 2;
-    if (bit64(s.c0, s.c1, j) || !bit64(s.l0, s.l1, j)) return -1;
-    return bit64(s.k0, s.k1, j) ? 1 : 0;
+    if (bit64(s.c, j) || !bit64(s.live, j)) return -1;
+    return bit64(s.k, j) ? 1 : 0;
 }
 
-// Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) by lane 0 after the new vertices
+// Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) by one lane after the new vertices
 // have been inserted.  Visiting order = the reference's: new vertices first, then the pre-existing ones, both
-// ascending.  Returns 0 on ring overflow; d0/d1 receive the vertices spliced away.
-__device__ __noinline__ int fast_seq_cut(FastPoly& sp, const CutState s, int hi0, int nnew, int lane, unsigned& d0, unsigned& d1)
+// ascending.  Returns 0 on ring overflow; `dead` receives the vertices spliced away.
+template <int L>
+__device__ __noinline__ int sub_seq_cut(SubPoly& sp, const CutState s, int hi0, int nnew, const Sub<L> sub, u64& dead)
 {
     const int hi1 = hi0 + nnew;
-    if (lane < hi1) sp.old_ring[lane] = sp.ring[lane];
-    if (lane + 32 < hi1) sp.old_ring[lane + 32] = sp.ring[lane + 32];
-    __syncwarp();
+    for (int v = sub.sl; v < hi1; v += L) sp.old_ring[v] = sp.ring[v];
+    sub.sync();
     int ok = 1;
-    unsigned dd0 = 0u, dd1 = 0u;
-    if (lane == 0)
+    unsigned dlo = 0u, dhi = 0u;
+    if (sub.sl == 0)
     {
-        const int nverts = __popc(s.l0) + __popc(s.l1) + nnew;   // the reference's vertex count (walk bound)
+        u64 dd = 0ull;
+        const int nverts = __popcll(s.live) + nnew;   // the reference's vertex count (walk bound)
         for (int ii = 0; ii < hi1 && ok; ii++)
         {
             const int i = ii < nnew ? hi0 + ii : ii - nnew;
-            const int ci = comp_of(s, hi0, 0u, 0u, i);
+            const int ci = comp_of(s, hi0, 0ull, i);
             if (!(ci == 0 || ci == 2)) continue;
             const int nneigh = rdeg(sp.ring[i]);
             for (int j = 0; j < nneigh; j++)
             {
                 const int jn = rget(sp.ring[i], j);
-                if (jn >= R_MARK || comp_of(s, hi0, 0u, 0u, jn) != -1) continue;
+                if (jn >= R_MARK || comp_of(s, hi0, 0ull, jn) != -1) continue;
                 int iprev = i, inext = jn, itmp, k = 0;
-                while (comp_of(s, hi0, 0u, 0u, inext) == -1 && k++ < nverts)
+                while (comp_of(s, hi0, 0ull, inext) == -1 && k++ < nverts)
                 {
                     itmp = inext;
                     inext = rface_loop(sp.ring[inext], iprev);
@@ -140,7 +184,7 @@ __device__ __noinline__ int fast_seq_cut(FastPoly& sp, const CutState s, int hi0
                     const u64 wn = sp.ring[inext], on = sp.old_ring[inext];
                     if (rdeg(wn) >= 8 || rdeg(on) >= 8) { ok = 0; break; }
                     int off = 0, mark = i;
-                    if (comp_of(s, hi0, 0u, 0u, inext) == 2) mark = R_MARK;   // Poly.cpp:409 inserts -1 in the snapshot
+                    if (comp_of(s, hi0, 0ull, inext) == 2) mark = R_MARK;   // Poly.cpp:409 inserts -1 in the snapshot
                     else { off = rfind(on, iprev); if (off > rdeg(on)) off = rdeg(on); }
                     sp.ring[inext] = rinsert(wn, off, i);
                     sp.old_ring[inext] = rinsert(on, off, mark);
@@ -166,7 +210,7 @@ __device__ __noinline__ int fast_seq_cut(FastPoly& sp, const CutState s, int hi0
             updated = false;
             for (int i = 0; i < hi1; i++)
             {
-                if (comp_of(s, hi0, dd0, dd1, i) >= 0 && rdeg(sp.ring[i]) == 2)
+                if (comp_of(s, hi0, dd, i) >= 0 && rdeg(sp.ring[i]) == 2)
                 {
                     updated = true;
                     const int iprev = rget(sp.ring[i], 0), inext = rget(sp.ring[i], 1);
@@ -174,31 +218,35 @@ __device__ __noinline__ int fast_seq_cut(FastPoly& sp, const CutState s, int hi0
                     if (k < rdeg(sp.ring[iprev])) sp.ring[iprev] = rset(sp.ring[iprev], k, inext);
                     k = rfind(sp.ring[inext], i);
                     if (k < rdeg(sp.ring[inext])) sp.ring[inext] = rset(sp.ring[inext], k, iprev);
-                    if (i & 32) dd1 |= 1u << (i & 31); else dd0 |= 1u << i;
+                    dd |= 1ull << i;
                 }
             }
         }
+        dlo = (unsigned)dd;
+        dhi = (unsigned)(dd >> 32);
     }
-    ok = __shfl_sync(FULL, ok, 0);
-    d0 = __shfl_sync(FULL, dd0, 0);
-    d1 = __shfl_sync(FULL, dd1, 0);
-    __syncwarp();
+    ok = sub.shfl(ok, 0);
+    dlo = sub.shfl(dlo, 0);
+    dhi = sub.shfl(dhi, 0);
+    dead = ((u64)dhi << 32) | dlo;
+    sub.sync();
     return ok;
 }
 
 // Renumber the live vertices to 0..n-1 keeping their order (the reference's compaction, Poly.cpp:464-495).
 // Positions are read from / written to shared memory; the caller reloads its register copies.
-__device__ __noinline__ void fast_compact(FastPoly& sp, CutState& s, int lane)
+template <int L>
+__device__ __noinline__ void sub_compact(SubPoly& sp, CutState& s, const Sub<L> sub)
 {
-    u64 r[2] = { ~0ull, ~0ull };
-    float vx[2], vy[2], vz[2];
-    bool live[2];
+    constexpr int G = Sub<L>::G;
+    u64 r[G];
+    float vx[G], vy[G], vz[G];
 #pragma unroll
-    for (int g = 0; g < 2; g++)
+    for (int g = 0; g < G; g++)
     {
-        const int v = lane + 32 * g;
-        live[g] = bit64(s.l0, s.l1, v);
-        if (live[g])
+        const int v = sub.sl + L * g;
+        r[g] = ~0ull;
+        if (bit64(s.live, v))
         {
             vx[g] = sp.x[v]; vy[g] = sp.y[v]; vz[g] = sp.z[v];
             const u64 rw = sp.ring[v];
@@ -206,128 +254,142 @@ __device__ __noinline__ void fast_compact(FastPoly& sp, CutState& s, int lane)
             {
                 const int b = rget(rw, j);
                 if (b == R_NONE) break;
-                r[g] = rset(r[g], j, rank64(s.l0, s.l1, b));
+                r[g] = rset(r[g], j, rank64(s.live, b));
             }
         }
     }
-    __syncwarp();
+    sub.sync();
 #pragma unroll
-    for (int g = 0; g < 2; g++)
+    for (int g = 0; g < G; g++)
     {
-        if (live[g])
+        const int v = sub.sl + L * g;
+        if (bit64(s.live, v))
         {
-            const int t = rank64(s.l0, s.l1, lane + 32 * g);
+            const int t = rank64(s.live, v);
             sp.x[t] = vx[g]; sp.y[t] = vy[g]; sp.z[t] = vz[g]; sp.ring[t] = r[g];
         }
     }
-    __syncwarp();
-    const int n = __popc(s.l0) + __popc(s.l1);
+    sub.sync();
+    const int n = __popcll(s.live);
     s.hi = n;
-    s.l0 = lowmask(n);
-    s.l1 = lowmask(n - 32);
+    s.live = lowmask64(n);
 }
 
 // Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).
-__device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly& sp, const CutState s, const float4 pl, int lane)
+template <int L>
+__device__ __noinline__ bool sub_all_inplane_box_says_skip(const SubPoly& sp, const CutState s, const float4 pl, const Sub<L> sub)
 {
     float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
     float hi[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
-    for (int v = lane; v < s.hi; v += 32)
+    for (int v = sub.sl; v < s.hi; v += L)
     {
-        if (!bit64(s.l0, s.l1, v)) continue;
+        if (!bit64(s.live, v)) continue;
         lo[0] = fminf(lo[0], sp.x[v]); hi[0] = fmaxf(hi[0], sp.x[v]);
         lo[1] = fminf(lo[1], sp.y[v]); hi[1] = fmaxf(hi[1], sp.y[v]);
         lo[2] = fminf(lo[2], sp.z[v]); hi[2] = fmaxf(hi[2], sp.z[v]);
     }
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = L / 2; o > 0; o >>= 1)
         for (int k = 0; k < 3; k++)
         {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+            lo[k] = fminf(lo[k], sub.shfl_xor(lo[k], o));
+            hi[k] = fmaxf(hi[k], sub.shfl_xor(hi[k], o));
         }
-    const int k = lane & 7;
+    const int k = sub.sl & 7;   // L >= 8: every corner is tested by at least one lane
     const int c = classify(signed_dist(pl, (k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]));
-    return __ballot_sync(FULL, c == -1) == 0u;
+    return sub.ballot(c == -1) == 0u;
 }
 
-// Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1; lanes own slots lane and lane + 32) by
-// planes[0..npl).  On return s.l0/s.l1 are the live slots (not renumbered) and nv their count (0 = no fragment).
-__device__ int fast_clip_by_planes(FastPoly& sp, CutState& s, int& nv, const float4* __restrict__ planes, int npl, int lane,
-                                   unsigned& seq_cuts, unsigned& n_cuts)
+// Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1) by planes[0..npl).  On return s.live are the live
+// slots (not renumbered) and nv their count (0 = no fragment).
+template <int L>
+__device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float4* __restrict__ planes, int npl, const Sub<L> sub,
+                                  unsigned& seq_cuts, unsigned& n_cuts)
 {
-    float px[2] = { 0.f, 0.f }, py[2] = { 0.f, 0.f }, pz[2] = { 0.f, 0.f };
+    constexpr int G = Sub<L>::G;
+    constexpr int FW = G <= 4 ? 32 / G : 8;                               // bits per group in the packed scans
+    using ScanT = typename std::conditional<(G <= 4), unsigned, u64>::type;
+    constexpr ScanT FM = (ScanT)((FW == 32) ? ~0u : ((1ull << (FW & 63)) - 1ull));
+    float px[G], py[G], pz[G];
     s.hi = nv;
-    s.l0 = lowmask(nv);
-    s.l1 = lowmask(nv - 32);
-    if (lane < nv) { px[0] = sp.x[lane]; py[0] = sp.y[lane]; pz[0] = sp.z[lane]; }
-    if (lane + 32 < nv) { px[1] = sp.x[lane + 32]; py[1] = sp.y[lane + 32]; pz[1] = sp.z[lane + 32]; }
+    s.live = lowmask64(nv);
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        const int v = sub.sl + L * g;
+        px[g] = py[g] = pz[g] = 0.f;
+        if (v < nv) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+    }
 
-    for (int kb = 0; kb < npl && nv > 0; kb += 32)
+    for (int kb = 0; kb < npl && nv > 0; kb += L)
     {
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kb + lane < npl) mine = __ldg(planes + kb + lane);   // lane l holds plane kb + l
-        const int kend = min(32, npl - kb);
+        if (kb + sub.sl < npl) mine = __ldg(planes + kb + sub.sl);   // lane sl holds plane kb + sl
+        const int kend = min(L, npl - kb);
         for (int kk = 0; kk < kend && nv > 0; kk++)
         {
             float4 pl;
-            pl.x = __shfl_sync(FULL, mine.x, kk);
-            pl.y = __shfl_sync(FULL, mine.y, kk);
-            pl.z = __shfl_sync(FULL, mine.z, kk);
-            pl.w = __shfl_sync(FULL, mine.w, kk);
+            pl.x = sub.shfl(mine.x, kk);
+            pl.y = sub.shfl(mine.y, kk);
+            pl.z = sub.shfl(mine.z, kk);
+            pl.w = sub.shfl(mine.w, kk);
 
             // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per group ----
-            int c0 = 3, c1 = 3;
-            if ((s.l0 >> lane) & 1u) c0 = classify(signed_dist(pl, px[0], py[0], pz[0]));
-            s.c0 = __ballot_sync(FULL, c0 == -1);
-            s.k0 = __ballot_sync(FULL, c0 == 1);
-            s.c1 = s.k1 = 0u;
-            if (s.l1)
+            s.c = s.k = 0ull;
+#pragma unroll
+            for (int g = 0; g < G; g++)
             {
-                if ((s.l1 >> lane) & 1u) c1 = classify(signed_dist(pl, px[1], py[1], pz[1]));
-                s.c1 = __ballot_sync(FULL, c1 == -1);
-                s.k1 = __ballot_sync(FULL, c1 == 1);
+                if (g * L < s.hi)
+                {
+                    int c = 3;
+                    if (bit64(s.live, sub.sl + L * g)) c = classify(signed_dist(pl, px[g], py[g], pz[g]));
+                    s.c |= (u64)sub.ballot(c == -1) << (g * L);
+                    s.k |= (u64)sub.ballot(c == 1) << (g * L);
+                }
             }
-            if (!(s.k0 | s.k1))
+            if (!s.k)
             {
                 // "below" (Poly.cpp:322-327) -- unless every vertex is in-plane and the box test says "above"
-                if (!(s.c0 | s.c1) && fast_all_inplane_box_says_skip(sp, s, pl, lane)) continue;
+                if (!s.c && sub_all_inplane_box_says_skip<L>(sp, s, pl, sub)) continue;
                 nv = 0;
                 break;
             }
-            if (!(s.c0 | s.c1)) continue;   // "above" (Poly.cpp:328)
+            if (!s.c) continue;   // "above" (Poly.cpp:328)
 
             // ---- the plane cuts ----
             n_cuts++;
-            __syncwarp();   // ring words composed by the previous cut are visible from here on
+            sub.sync();   // ring words composed by the previous cut are visible from here on
             // straddling half-edges (clipped vertex -> kept neighbour) in the reference's append order
-            unsigned smask = 0u;   // bits 0-7: slots of vertex `lane`, bits 8-15: slots of vertex `lane + 32`
-            int cnt = 0;           // low half: group 0, high half: group 1
-#pragma unroll 1
-            for (int g = 0; g < 2; g++)
+            u64 smk = 0ull;    // 8 slot bits per owned group
+            ScanT cnt = 0;     // FW-bit counter per owned group
+#pragma unroll
+            for (int g = 0; g < G; g++)
             {
-                if (((g ? s.c1 : s.c0) >> lane) & 1u)
+                const int v = sub.sl + L * g;
+                if (g * L < s.hi && bit64(s.c, v))
                 {
-                    const u64 rw = sp.ring[lane + 32 * g];
+                    const u64 rw = sp.ring[v];
                     for (int j = 0; j < 8; j++)
                     {
                         const int b = rget(rw, j);
                         if (b == R_NONE) break;
-                        if (bit64(s.k0, s.k1, b)) { smask |= 1u << (j + 8 * g); cnt += 1 << (16 * g); }
+                        if (bit64(s.k, b)) { smk |= 1ull << (j + 8 * g); cnt += (ScanT)1 << (FW * g); }
                     }
                 }
             }
-            int tot;
-            const int ex = warp_exscan(cnt, lane, tot);
-            const int tot0 = tot & 0xffff, nnew = tot0 + (tot >> 16);
+            ScanT tot;
+            const ScanT ex = sub.exscan(cnt, tot);
+            int nnew = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++) nnew += (int)((tot >> (FW * g)) & FM);
             if (s.hi + nnew > 64)
             {
                 // out of slots: renumber the live vertices (exactly the reference's compaction) and redo this plane
-                if (__popc(s.l0) + __popc(s.l1) + nnew > 64) return CLIP_OVERFLOW;
-                fast_compact(sp, s, lane);
+                if (__popcll(s.live) + nnew > 64) return CLIP_OVERFLOW;
+                sub_compact<L>(sp, s, sub);
 #pragma unroll
-                for (int g = 0; g < 2; g++)
+                for (int g = 0; g < G; g++)
                 {
-                    const int v = lane + 32 * g;
+                    const int v = sub.sl + L * g;
                     if (v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
                 }
                 n_cuts--;
@@ -335,17 +397,21 @@ __device__ int fast_clip_by_planes(FastPoly& sp, CutState& s, int& nv, const flo
                 continue;
             }
             const int hi0 = s.hi;
+            if (smk)
             {
-                int w = ex & 0xffff;
-                unsigned m = smask & 0xffu;
-                while (m) { const int j = __ffs(m) - 1; m &= m - 1; sp.list[w++] = (uint16_t)(lane | (j << 8)); }
-                w = tot0 + (ex >> 16);
-                m = smask >> 8;
-                while (m) { const int j = __ffs(m) - 1; m &= m - 1; sp.list[w++] = (uint16_t)((lane + 32) | (j << 8)); }
+                int gbase = 0;
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                {
+                    unsigned m = (unsigned)(smk >> (8 * g)) & 0xffu;
+                    int w = gbase + (int)((ex >> (FW * g)) & FM);
+                    while (m) { const int j = __ffs(m) - 1; m &= m - 1; sp.list[w++] = (uint16_t)((sub.sl + L * g) | (j << 8)); }
+                    gbase += (int)((tot >> (FW * g)) & FM);
+                }
             }
-            __syncwarp();
+            sub.sync();
             // insert: one new vertex per lane (Poly.cpp:345-354)
-            for (int t = lane; t < nnew; t += 32)
+            for (int t = sub.sl; t < nnew; t += L)
             {
                 const int e = sp.list[t], v = e & 0xff, j = e >> 8, w = hi0 + t;
                 const int jn = rget(sp.ring[v], j);
@@ -359,19 +425,18 @@ __device__ int fast_clip_by_planes(FastPoly& sp, CutState& s, int& nv, const flo
                 const int k = rfind(sp.ring[jn], v);
                 if (k < 8) reinterpret_cast<uint8_t*>(&sp.ring[jn])[k] = (uint8_t)w;
             }
-            __syncwarp();
+            sub.sync();
 
             // patch (Poly.cpp:365-431): walk from each new vertex through clipped vertices to the next new one
-            const bool any_zero = ((s.l0 & ~(s.c0 | s.k0)) | (s.l1 & ~(s.c1 | s.k1))) != 0u;
-            bool need_seq = any_zero;
+            bool need_seq = (s.live & ~(s.c | s.k)) != 0ull;   // an in-plane vertex
             if (!need_seq)
             {
                 bool ok = true;
-                for (int t = lane; t < nnew; t += 32)
+                for (int t = sub.sl; t < nnew; t += L)
                 {
                     const int w = hi0 + t;
                     int iprev = w, inext = rget(sp.ring[w], 0), itmp, k = 0;
-                    while (inext < hi0 && bit64(s.c0, s.c1, inext) && k++ < 64)
+                    while (inext < hi0 && bit64(s.c, inext) && k++ < 64)
                     {
                         itmp = inext;
                         inext = rface_loop(sp.ring[inext], iprev);
@@ -382,14 +447,14 @@ __device__ int fast_clip_by_planes(FastPoly& sp, CutState& s, int& nv, const flo
                     sp.list[t] = (uint16_t)inext;
                     ok = ok && okt;
                 }
-                __syncwarp();
-                for (int t = lane; t < nnew; t += 32)
+                sub.sync();
+                for (int t = sub.sl; t < nnew; t += L)
                     if (ok) ok = sp.id[sp.list[t]] == (uint8_t)(hi0 + t);
-                need_seq = __ballot_sync(FULL, !ok) != 0u;
+                need_seq = sub.ballot(!ok) != 0u;
                 if (!need_seq)
                 {
                     // the walk targets are a permutation of the new vertices: ring(w) = [pusher, walked, kept]
-                    for (int t = lane; t < nnew; t += 32)
+                    for (int t = sub.sl; t < nnew; t += L)
                     {
                         const int w = hi0 + t;
                         const int kept = rget(sp.ring[w], 1);
@@ -397,45 +462,48 @@ __device__ int fast_clip_by_planes(FastPoly& sp, CutState& s, int& nv, const flo
                     }
                 }
             }
-            unsigned dead0 = 0u, dead1 = 0u;
+            u64 dead = 0ull;
             if (need_seq)
             {
                 seq_cuts++;
-                if (!fast_seq_cut(sp, s, hi0, nnew, lane, dead0, dead1)) return CLIP_OVERFLOW;
+                if (!sub_seq_cut<L>(sp, s, hi0, nnew, sub, dead)) return CLIP_OVERFLOW;
             }
             // lazy compaction: clipped vertices leave the live set, new ones join it
             s.hi = hi0 + nnew;
-            s.l0 = ((s.l0 & ~s.c0) | (lowmask(s.hi) & ~lowmask(hi0))) & ~dead0;
-            s.l1 = ((s.l1 & ~s.c1) | (lowmask(s.hi - 32) & ~lowmask(hi0 - 32))) & ~dead1;
-            nv = __popc(s.l0) + __popc(s.l1);
+            s.live = ((s.live & ~s.c) | (lowmask64(s.hi) & ~lowmask64(hi0))) & ~dead;
+            nv = __popcll(s.live);
             if (nv < 4) nv = 0;   // Poly.cpp:498-499
 #pragma unroll
-            for (int g = 0; g < 2; g++)
+            for (int g = 0; g < G; g++)
             {
-                const int v = lane + 32 * g;
+                const int v = sub.sl + L * g;
                 if (v >= hi0 && v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
             }
         }
     }
-    __syncwarp();
+    sub.sync();
     return CLIP_OK;
 }
 
 // Poly::ExtractFaces + Poly::Moments in the reference's accumulation order (Poly.cpp:55-126) + inertia, on the
 // live (not renumbered) slots: vertex order = slot order, origin = first live vertex.  See fragment_moments in
 // clip_warp.cuh for the derivation.
-__device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane, Moments& out)
+template <int L>
+__device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L> sub, Moments& out)
 {
-    const int first = s.l0 ? __ffs(s.l0) - 1 : 32 + __ffs(s.l1) - 1;
+    constexpr int G = Sub<L>::G;
+    const int first = __ffsll((long long)s.live) - 1;
     const float ox = sp.x[first], oy = sp.y[first], oz = sp.z[first];
-    const int nv = __popc(s.l0) + __popc(s.l1);
-    unsigned start_mask = 0u;   // bits 0-7 group 0, 8-15 group 1
-    int cnt = 0, faces = 0;
-#pragma unroll 1
-    for (int g = 0; g < 2; g++)
+    const int nv = __popcll(s.live);
+    u64 start_mask = 0ull;   // 8 slot bits per owned group
+    int faces = 0, cnt = 0;  // triangles of the faces this lane starts (all groups: one lane = one scan entry per group)
+    int cntg[G];
+#pragma unroll
+    for (int g = 0; g < G; g++)
     {
-        const int v = lane + 32 * g;
-        if (bit64(s.l0, s.l1, v))
+        cntg[g] = 0;
+        const int v = sub.sl + L * g;
+        if (g * L < s.hi && bit64(s.live, v))
         {
             const u64 rw = sp.ring[v];
             const int d = rdeg(rw);
@@ -457,27 +525,39 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
                 }
                 if (is_start)
                 {
-                    start_mask |= 1u << (j + 8 * g);
+                    start_mask |= 1ull << (j + 8 * g);
                     faces++;
-                    cnt += max(n - 2, 0) << (16 * g);
+                    cntg[g] += max(n - 2, 0);
                 }
             }
         }
+        cnt += cntg[g];
     }
-    int tot;
-    const int ex = warp_exscan(cnt, lane, tot);   // both groups in one scan
-    const int n_tri0 = tot & 0xffff;
-    const int n_faces = __reduce_add_sync(FULL, faces);
-    const int n_tri = min(n_tri0 + (tot >> 16), 128);
+    // triangle order = vertex order = group-major, lane-minor: one scan per group that has vertices
+    int tri_base[G];
+    int n_tri = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        tri_base[g] = 0;
+        if (g * L < s.hi)
+        {
+            int tot;
+            tri_base[g] = n_tri + sub.exscan(cntg[g], tot);
+            n_tri += tot;
+        }
+    }
+    const int n_faces = sub.sum(faces);
+    n_tri = min(n_tri, 128);
 
     float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
-#pragma unroll 1
-    for (int g = 0; g < 2; g++)
+#pragma unroll
+    for (int g = 0; g < G; g++)
     {
-        unsigned m = (start_mask >> (8 * g)) & 0xffu;
+        unsigned m = (unsigned)(start_mask >> (8 * g)) & 0xffu;
         if (!m) continue;
-        const int v = lane + 32 * g;
-        int w = g ? n_tri0 + (ex >> 16) : (ex & 0xffff);
+        const int v = sub.sl + L * g;
+        int w = tri_base[g];
         const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
         const u64 rw = sp.ring[v];
         while (m)
@@ -516,16 +596,16 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
             }
         }
     }
-    __syncwarp();
+    sub.sync();
 
     // ordered accumulation (Poly.cpp:77-85): lane c < 4 owns component c of the triangle records (dV, mx, my, mz)
     // and adds them in the reference's order -- dV into a double, the first moments in float.  Four lanes share one
     // instruction stream, so the serial chain costs a quarter of a single-lane loop.
     double zeroth = 0.0;
     float fsum = 0.f;
-    if (lane < 4)
+    if (sub.sl < 4)
     {
-        const float* comp = reinterpret_cast<const float*>(sp.tri) + lane;
+        const float* comp = reinterpret_cast<const float*>(sp.tri) + sub.sl;
         int t = 0;
         for (; t + 4 <= n_tri; t += 4)   // the loads do not depend on the accumulation chain
         {
@@ -540,8 +620,8 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
             fsum = __fadd_rn(fsum, r);
         }
     }
-    zeroth = __shfl_sync(FULL, zeroth, 0) / 6.0;
-    float fx = __shfl_sync(FULL, fsum, 1), fy = __shfl_sync(FULL, fsum, 2), fz = __shfl_sync(FULL, fsum, 3);
+    zeroth = sub.shfl(zeroth, 0) / 6.0;
+    float fx = sub.shfl(fsum, 1), fy = sub.shfl(fsum, 2), fz = sub.shfl(fsum, 3);
     {
         const double q = 24.0 * zeroth;
         const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));   // safeInv, Poly.cpp:33
@@ -551,8 +631,8 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
 #pragma unroll
     for (int k = 0; k < 10; k++)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            cov[k] += __shfl_xor_sync(FULL, cov[k], o);
+        for (int o = L / 2; o > 0; o >>= 1)
+            cov[k] += sub.shfl_xor(cov[k], o);
 
     out.n_faces = n_faces;
     out.volume = zeroth;
@@ -571,5 +651,6 @@ __device__ void fast_fragment_moments(FastPoly& sp, const CutState& s, int lane,
         out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
         out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
     }
+    (void)cnt;
 }
 } // namespace surtr

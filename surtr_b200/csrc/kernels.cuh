@@ -8,7 +8,9 @@
 //       kdop_arg_kernel          Kdop::KdopContainer::Calc(Polyhedron) with first-extremal-vertex semantics
 #pragma once
 
-#include "clip_fast.cuh"
+#include "clip_sub.cuh"
+
+#include <type_traits>
 #include "scan.cuh"
 #include "../../include/surtr_b200.h"
 
@@ -435,19 +437,23 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
     if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
 }
 
-// K3, small tier: one warp per candidate pair (no persistent loop: the hardware scheduler balances the very
-// uneven pair costs), ring words in shared memory (clip_fast.cuh).
+// K3, small tier: L lanes per candidate pair (clip_sub.cuh), one pair per sub-warp, no persistent loop (the
+// hardware scheduler balances the very uneven pair costs).
 constexpr int FAST_WARPS = 4;
+constexpr int FAST_LANES = 32;   // lanes per pair: 32 = one warp per pair (16 = two pairs per warp measured slower, see clip_sub.cuh)
 constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
 
-__global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs a)
+template <int L>
+__global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ FastPoly s_poly[FAST_WARPS];
-    FastPoly& sp = s_poly[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned long long q64 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int G = Sub<L>::G;
+    constexpr int PAIRS = FAST_WARPS * 32 / L;
+    __shared__ SubPoly s_poly[PAIRS];
+    SubPoly& sp = s_poly[threadIdx.x / L];
+    const Sub<L> sub(threadIdx.x & 31);
+    const unsigned long long q64 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
     unsigned long long n_items = a.ctl->n_cand;
     if (n_items > a.cap_cand) n_items = a.cap_cand;
     if (q64 >= n_items) return;
@@ -462,50 +468,45 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs 
     bool bad = nv > 64;
     if (!bad)
     {
-#pragma unroll
-        for (int g = 0; g < 2; g++)
+        for (int v = sub.sl; v < nv; v += L)
         {
-            const int v = lane + 32 * g;
-            if (v < nv)
-            {
-                const float4 p = __ldg(a.p_verts + v0 + v);
-                const uint32_t r0 = a.p_ring_off[v0 + v];
-                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
-                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
-                u64 rw = ~0ull;
-                if (d > 8 || d == 0) bad = true;
-                else
-                    for (int j = 0; j < d; j++)
-                    {
-                        const int idx = a.p_ring[r0 + j];
-                        bad = bad || idx >= nv;
-                        rw = rset(rw, j, idx);
-                    }
-                sp.ring[v] = rw;
-            }
+            const float4 p = __ldg(a.p_verts + v0 + v);
+            const uint32_t r0 = a.p_ring_off[v0 + v];
+            const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+            sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+            u64 rw = ~0ull;
+            if (d > 8 || d == 0) bad = true;
+            else
+                for (int j = 0; j < d; j++)
+                {
+                    const int idx = a.p_ring[r0 + j];
+                    bad = bad || idx >= nv;
+                    rw = rset(rw, j, idx);
+                }
+            sp.ring[v] = rw;
         }
     }
-    bad = __ballot_sync(FULL, bad) != 0u;
-    __syncwarp();
+    bad = sub.ballot(bad) != 0u;
+    sub.sync();
     const long long t1 = a.dbg ? clock64() : 0;
     const int nv_in = nv;
     unsigned seq_cuts = 0, n_cuts = 0;
     int status = CLIP_OVERFLOW;
     CutState cs;
-    if (!bad) status = fast_clip_by_planes(sp, cs, nv, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
+    if (!bad) status = sub_clip_by_planes<L>(sp, cs, nv, a.c_planes + pl0, npl, sub, seq_cuts, n_cuts);
     const long long t2 = a.dbg ? clock64() : 0;
-    if (a.dbg && lane == 0)
+    if (a.dbg && sub.sl == 0)
     {
         uint32_t* d = a.dbg + (size_t)q * 8;
         d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
         d[4] = seq_cuts; d[5] = n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl;
     }
-    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+    if (seq_cuts && sub.sl == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
     CandRec* rec = a.rec + q;
     if (status != CLIP_OK)
     {
         // too large for this tier (or a ring outgrew 8 slots): queue the pair for the large tier
-        if (lane == 0)
+        if (sub.sl == 0)
         {
             rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
             a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
@@ -514,11 +515,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs 
     }
     if (nv == 0)
     {
-        if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
+        if (sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
         return;
     }
     Moments mo;
-    fast_fragment_moments(sp, cs, lane, mo);
+    sub_fragment_moments<L>(sp, cs, sub, mo);
     const long long t3 = a.dbg ? clock64() : 0;
 
     // result blob, renumbered to the reference's final order (rank in the live mask):
@@ -528,31 +529,27 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 7) clip_fast_kernel(ClipArgs 
     float4* bv = reinterpret_cast<float4*>(b);
     uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
     uint8_t* br = b + 64 * 18;
-    const bool live0 = (cs.l0 >> lane) & 1u, live1 = (cs.l1 >> lane) & 1u;
-    const u64 rw0 = live0 ? sp.ring[lane] : ~0ull;
-    const u64 rw1 = live1 ? sp.ring[lane + 32] : ~0ull;
-    const int d0 = rdeg(rw0), d1 = rdeg(rw1);
-    int tot;
-    const int ex = warp_exscan(d0 | (d1 << 16), lane, tot);
-    const int ne0 = tot & 0xffff, ne = ne0 + (tot >> 16);
-    if (live0)
+    int ne = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++)
     {
-        const int t = rank64(cs.l0, cs.l1, lane);
-        bv[t] = make_float4(sp.x[lane], sp.y[lane], sp.z[lane], 0.f);
-        const int off = ex & 0xffff;
-        bo[t] = (uint16_t)off;
-        for (int j = 0; j < d0; j++) br[off + j] = (uint8_t)rank64(cs.l0, cs.l1, rget(rw0, j));
+        if (g * L >= cs.hi) break;
+        const int v = sub.sl + L * g;
+        const bool live = bit64(cs.live, v);
+        const u64 rw = live ? sp.ring[v] : ~0ull;
+        const int d = rdeg(rw);
+        int tot;
+        const int off = ne + sub.exscan(d, tot);
+        ne += tot;
+        if (live)
+        {
+            const int t = rank64(cs.live, v);
+            bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+            bo[t] = (uint16_t)off;
+            for (int j = 0; j < d; j++) br[off + j] = (uint8_t)rank64(cs.live, rget(rw, j));
+        }
     }
-    if (live1)
-    {
-        const int v = lane + 32;
-        const int t = rank64(cs.l0, cs.l1, v);
-        bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
-        const int off = ne0 + (ex >> 16);
-        bo[t] = (uint16_t)off;
-        for (int j = 0; j < d1; j++) br[off + j] = (uint8_t)rank64(cs.l0, cs.l1, rget(rw1, j));
-    }
-    if (lane == 0)
+    if (sub.sl == 0)
     {
         rec->nv = (uint32_t)nv;
         rec->ne = (uint32_t)ne;

@@ -299,8 +299,9 @@ int launch_event(surtr_ctx* ctx)
     {
         ca.scratch = ctx->scratch1.as<unsigned char>();
         ca.slot_bytes = FAST_BLOB;
-        const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + FAST_WARPS - 1) / FAST_WARPS);
-        launch_pdl(clip_fast_kernel, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
+        constexpr uint64_t pairs_per_block = FAST_WARPS * 32 / FAST_LANES;
+        const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + pairs_per_block - 1) / pairs_per_block);
+        launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->tier2_enabled)
