@@ -24,6 +24,8 @@ def gather_variable(t: torch.Tensor, dst: int = 0, group=None):
     Returns the list of per-rank tensors on `dst`, None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    dtype = t.dtype
+    t = t.contiguous().view(torch.uint8)      # ship raw bytes: NCCL has no 16-bit integer type
     n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n, group=group)
@@ -35,7 +37,7 @@ def gather_variable(t: torch.Tensor, dst: int = 0, group=None):
     dist.gather(pad, bufs, dst=dst, group=group)
     if rank != dst:
         return None
-    return [b[:c] for b, c in zip(bufs, counts)]
+    return [b[:c].view(dtype) for b, c in zip(bufs, counts)]
 
 
 def gather_fragments(rec_bytes: torch.Tensor, verts: torch.Tensor, ring_off: torch.Tensor, ring: torch.Tensor, dst: int = 0,
