@@ -129,6 +129,12 @@ int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out);
 int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const float* normals3, uint32_t k,
                     float* dist, int32_t* arg, float* planes8);
 
+/* Batched form for many small objects (the refitting pass, Surtr::Refitting, Src/Surtr.cpp:2405-2413 over
+ * m_refittingTask :1449-1455): object i has vertices [vert_off[i], vert_off[i+1]) and its own normals
+ * [normal_off[i], normal_off[i+1]); outputs are indexed by global normal index, arg is local to the object. */
+int surtr_kdop_calc_batch(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, uint32_t n_objects,
+                          const float* normals3, const uint32_t* normal_off, float* dist, int32_t* arg, float* planes8);
+
 /* Timing of the last surtr_fracture_event in milliseconds (CUDA events on the context stream).  clip_ms (the K3
  * small-tier kernel alone) is only measured while profiling is on: the extra events sit between the kernels of an
  * event and serialise their programmatic dependent launches, so they are off by default. */

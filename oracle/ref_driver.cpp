@@ -469,6 +469,39 @@ uint32_t ref_ich_normals(const float* verts, uint32_t nv, int limit, float* out,
 	return n;
 }
 
+// Restatement of m_refittingTask (Surtr.cpp:1449-1455) for every piece i: ICH normals of the mesh points (limit =
+// min(#points, RefittingPointLimit)) -> KdopContainer::Calc(mesh) -> convex = ClipWithPolyhedron(convex).
+// Every piece gets one output entry (possibly empty).
+void ref_refit(const float* cverts, const uint32_t* cvert_off, const uint32_t* cring_off, const uint16_t* cring, uint32_t n,
+			   const float* mverts, const uint32_t* mvert_off, int limit, void* out)
+{
+	PolySet& o = *(PolySet*)out;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		Poly::Polyhedron convex = to_poly(cverts, cvert_off, cring_off, cring, i);
+		std::vector<Vector3> pts;
+		Poly::Polyhedron mesh;
+		for (uint32_t v = mvert_off[i]; v < mvert_off[i + 1]; v++)
+		{
+			pts.emplace_back(mverts[4 * v], mverts[4 * v + 1], mverts[4 * v + 2]);
+			mesh.push_back(Poly::Vertex(pts.back()));
+		}
+		// Surtr::GenerateICHNormal (Surtr.cpp:1961-1974)
+		VMACH::ConvexHull ich(pts, (uint32_t)std::min((int)pts.size(), limit));
+		std::vector<Vector3> normals;
+		for (const VMACH::ConvexHullFace& f : ich.GetFaces())
+		{
+			Vector3 normal = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+			normal.Normalize();
+			normals.push_back(normal);
+		}
+		Kdop::KdopContainer kdop(normals);
+		kdop.Calc(mesh);
+		convex = kdop.ClipWithPolyhedron(convex);
+		append(o, convex, i, i);
+	}
+}
+
 // Scalar helpers for the unit KATs (Poly.cpp:716-751).
 int ref_compare_plane_point(const float* plane, const float* p)
 {

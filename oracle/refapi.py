@@ -40,6 +40,7 @@ def lib():
         _lib.ref_clip_each.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ref_apply_fracture.argtypes = ([C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                                                  C.c_uint32, C.c_int, C.c_void_p])
+        _lib.ref_refit.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.ref_seeds_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.ref_seeds_radial.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_void_p]
         _lib.ref_unit_cube.argtypes = [C.c_void_p]
@@ -250,3 +251,13 @@ def box_planes() -> np.ndarray:
     out = np.zeros((6, 4), np.float32)
     lib().ref_box_planes(_p(out))
     return out
+
+
+def refit(convex: PolySet, mesh_verts4: np.ndarray, mesh_vert_off: np.ndarray, limit: int = 4) -> PolySet:
+    """m_refittingTask (Surtr.cpp:1449-1455) per piece with the reference's own ConvexHull / Kdop / clipper."""
+    mesh_verts4 = np.ascontiguousarray(mesh_verts4, np.float32)
+    mesh_vert_off = np.ascontiguousarray(mesh_vert_off, np.uint32)
+    h = lib().ref_polyset_new()
+    lib().ref_refit(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring), convex.n,
+                    _p(mesh_verts4), _p(mesh_vert_off), limit, h)
+    return _export(h)

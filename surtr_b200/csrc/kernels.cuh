@@ -767,4 +767,53 @@ __global__ void __launch_bounds__(256) kdop_arg_kernel(const float4* __restrict_
         }
     }
 }
+
+// Batched Kdop::Calc(Polyhedron): one warp per (object, normal).  normal_obj[e] = object of normal e.
+__global__ void __launch_bounds__(256) kdop_arg_batch_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ vert_off,
+                                                             const float* __restrict__ normals, const uint32_t* __restrict__ normal_obj,
+                                                             uint32_t n_normals, float* __restrict__ dist, int32_t* __restrict__ arg,
+                                                             float4* __restrict__ planes)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = warp; e < n_normals; e += nwarps)
+    {
+        const uint32_t o = normal_obj[e];
+        const uint32_t v0 = vert_off[o], nv = vert_off[o + 1] - v0;
+        const float nx = normals[3 * e], ny = normals[3 * e + 1], nz = normals[3 * e + 2];
+        float mn = 0.f, mx = 0.f;
+        int imin = -1, imax = -1;
+        for (uint32_t v = lane; v < nv; v += 32)
+        {
+            const float4 p = __ldg(verts + v0 + v);
+            const float t = dot3(p.x, p.y, p.z, nx, ny, nz);
+            if (imin < 0 || mn > t) { mn = t; imin = (int)v; }
+            if (imax < 0 || mx < t) { mx = t; imax = (int)v; }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1)
+        {
+            const float omn = __shfl_xor_sync(FULL, mn, s), omx = __shfl_xor_sync(FULL, mx, s);
+            const int oimin = __shfl_xor_sync(FULL, imin, s), oimax = __shfl_xor_sync(FULL, imax, s);
+            if (oimin >= 0 && (imin < 0 || omn < mn || (omn == mn && oimin < imin))) { mn = omn; imin = oimin; }
+            if (oimax >= 0 && (imax < 0 || omx > mx || (omx == mx && oimax < imax))) { mx = omx; imax = oimax; }
+        }
+        if (lane == 0)
+        {
+            dist[2 * e] = mn; dist[2 * e + 1] = mx;
+            arg[2 * e] = imin; arg[2 * e + 1] = imax;
+            if (imin >= 0)
+            {
+                const float4 a = verts[v0 + imin], b = verts[v0 + imax];
+                planes[2 * e] = plane_from_point_normal(a.x, a.y, a.z, -nx, -ny, -nz);   // Plane(vert, -Normal)
+                planes[2 * e + 1] = plane_from_point_normal(b.x, b.y, b.z, nx, ny, nz);  // Plane(vert, Normal)
+            }
+            else
+            {
+                planes[2 * e] = planes[2 * e + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
 } // namespace surtr

@@ -630,6 +630,39 @@ int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const
     return done(rc);
 }
 
+int surtr_kdop_calc_batch(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, uint32_t n_objects, const float* normals3,
+                          const uint32_t* normal_off, float* dist, int32_t* arg, float* planes8)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!vert_off || !normal_off || !dist || !arg) return fail(ctx, SURTR_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nv = vert_off[n_objects], nn = normal_off[n_objects];
+    if (!nn) return SURTR_OK;
+    if (!normals3 || (nv && !verts4)) return fail(ctx, SURTR_ERR_INVALID, "NULL argument");
+    std::vector<uint32_t> obj(nn);
+    for (uint32_t o = 0; o < n_objects; o++)
+        for (uint32_t e = normal_off[o]; e < normal_off[o + 1]; e++) obj[e] = o;
+    DevBuf dv, dvo, dn, dobj, dd, da, dp;
+    int rc = SURTR_OK;
+    auto done = [&](int code) { dv.release(); dvo.release(); dn.release(); dobj.release(); dd.release(); da.release(); dp.release(); return code; };
+    if (dv.reserve(16 * std::max<uint64_t>(1, nv)) || dvo.reserve(4 * ((size_t)n_objects + 1)) || dn.reserve(12 * nn) || dobj.reserve(4 * nn) ||
+        dd.reserve(8 * nn) || da.reserve(8 * nn) || dp.reserve(32 * nn))
+        return done(fail(ctx, SURTR_ERR_NOMEM, "cudaMalloc failed"));
+    cudaMemcpyAsync(dv.p, verts4, 16 * nv, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dvo.p, vert_off, 4 * ((size_t)n_objects + 1), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dn.p, normals3, 12 * nn, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dobj.p, obj.data(), 4 * nn, cudaMemcpyHostToDevice, ctx->stream);
+    const int blocks = (int)std::min<uint64_t>((nn * 32 + 255) / 256, (uint64_t)ctx->num_sm * 8);
+    kdop_arg_batch_kernel<<<blocks, 256, 0, ctx->stream>>>(dv.as<float4>(), dvo.as<uint32_t>(), dn.as<float>(), dobj.as<uint32_t>(),
+                                                           (uint32_t)nn, dd.as<float>(), da.as<int32_t>(), dp.as<float4>());
+    cudaMemcpyAsync(dist, dd.p, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(arg, da.p, 8 * nn, cudaMemcpyDeviceToHost, ctx->stream);
+    if (planes8) cudaMemcpyAsync(planes8, dp.p, 32 * nn, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, SURTR_ERR_CUDA, cudaGetErrorString(e));
+    return done(rc);
+}
+
 int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
 {
     if (!ctx) return SURTR_ERR_INVALID;

@@ -31,7 +31,7 @@ EXPORTS = [
     "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions",
     "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
-    "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling",
+    "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library():
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.surtr_last_event_launches.argtypes = [vp]
     lib.surtr_set_profiling.argtypes = [vp, i32]
+    lib.surtr_kdop_calc_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -225,6 +226,17 @@ class FractureContext:
         arg = np.zeros((k, 2), np.int32)
         planes = np.zeros((k, 2, 4), np.float32)
         self._ck(self._lib.surtr_kdop_calc(self._h, _p(verts4), len(verts4), _p(normals), k, _p(dist), _p(arg), _p(planes)))
+        return dist, arg, planes
+
+    def kdop_calc_batch(self, verts4, vert_off, normals, normal_off):
+        verts4, normals = _arr(verts4, np.float32), _arr(normals, np.float32)
+        vert_off, normal_off = _arr(vert_off, np.uint32), _arr(normal_off, np.uint32)
+        k = len(normals)
+        dist = np.zeros((k, 2), np.float32)
+        arg = np.zeros((k, 2), np.int32)
+        planes = np.zeros((k, 2, 4), np.float32)
+        self._ck(self._lib.surtr_kdop_calc_batch(self._h, _p(verts4), _p(vert_off), len(vert_off) - 1, _p(normals), _p(normal_off),
+                                                 _p(dist), _p(arg), _p(planes)))
         return dist, arg, planes
 
     def last_event_ms(self):

@@ -1,5 +1,6 @@
 #include "Fracture.h"
 
+#include "ConvexHull.h"
 #include "DT3D.h"
 #include "Engine.h"
 
@@ -80,6 +81,70 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 		info.PieceSourcePiece.push_back((int)r.piece);
 	}
 	return info;
+}
+
+void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args)
+{
+	const uint32_t n = (uint32_t)targetPieceVec.size();
+	if (!n)
+		return;
+	// 1. ICH normals per piece (host; <= 4 points by default)
+	std::vector<float> verts4, normals3;
+	std::vector<uint32_t> vert_off{ 0 }, normal_off{ 0 };
+	for (const Piece* p : targetPieceVec)
+	{
+		std::vector<Vector3> pts;
+		for (const Poly::Vertex& v : p->Mesh)
+		{
+			pts.push_back(v.Position);
+			verts4.insert(verts4.end(), { v.Position.x, v.Position.y, v.Position.z, 0.f });
+		}
+		vert_off.push_back((uint32_t)(verts4.size() / 4));
+		const std::vector<Vector3> nrm = VMACH::GenerateICHNormal(pts, std::min((int)pts.size(), args.RefittingPointLimit));
+		for (const Vector3& nv : nrm)
+			normals3.insert(normals3.end(), { nv.x, nv.y, nv.z });
+		normal_off.push_back((uint32_t)(normals3.size() / 3));
+	}
+	// 2. k-DOP extents of every piece->Mesh on the GPU (Kdop::Calc(Polyhedron), Kdop.cpp:92-115)
+	const size_t nn = normals3.size() / 3;
+	std::vector<float> dist(2 * nn), planes8(8 * nn);
+	std::vector<int32_t> arg(2 * nn);
+	detail::check(surtr_kdop_calc_batch(detail::context(), verts4.data(), vert_off.data(), n, normals3.data(), normal_off.data(),
+										dist.data(), arg.data(), planes8.data()), "surtr_kdop_calc_batch");
+	// 3. clip piece->Convex by its own plane list: n independent events of one piece x one cell
+	detail::FlatPolys pieces;
+	detail::FlatCells cells;
+	std::vector<uint32_t> ev(n + 1);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		pieces.add(targetPieceVec[i]->Convex);
+		std::vector<Poly::Plane> pl;
+		for (uint32_t e = normal_off[i]; e < normal_off[i + 1]; e++)
+		{
+			pl.emplace_back(planes8[8 * e], planes8[8 * e + 1], planes8[8 * e + 2], planes8[8 * e + 3]);       // MinPlane
+			pl.emplace_back(planes8[8 * e + 4], planes8[8 * e + 5], planes8[8 * e + 6], planes8[8 * e + 7]);   // MaxPlane
+		}
+		cells.add(pl);
+		ev[i] = i;
+	}
+	ev[n] = n;
+	surtr_ctx* c = detail::context();
+	detail::check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(), n, ev.data(), n),
+				  "surtr_upload_pieces");
+	detail::check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), nullptr, nullptr, n, ev.data(), n), "surtr_upload_cells");
+	detail::check(surtr_fracture_event(c), "surtr_fracture_event");
+	surtr_counts cnt;
+	detail::check(surtr_event_counts(c, &cnt), "surtr_event_counts");
+	detail::Fragments fr;
+	fr.rec.resize(cnt.n_fragments);
+	fr.verts4.resize(4 * cnt.n_verts);
+	fr.ring_off.resize(cnt.n_verts + 1);
+	fr.ring.resize(cnt.n_ring);
+	detail::check(surtr_download_fragments(c, fr.rec.data(), fr.verts4.data(), fr.ring_off.data(), fr.ring.data()), "surtr_download_fragments");
+	for (Piece* p : targetPieceVec)
+		p->Convex.clear();
+	for (size_t f = 0; f < fr.rec.size(); f++)
+		targetPieceVec[fr.rec[f].piece]->Convex = fr.polyhedron(f);
 }
 
 void SetExtract(CompoundInfo& preResult)

@@ -79,4 +79,9 @@ std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPo
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec);
 // Surtr::SetExtract (Surtr.cpp:2151-2155).
 void SetExtract(CompoundInfo& preResult);
+// Surtr::Refitting (Surtr.cpp:2405-2413) = m_refittingTask (:1449-1455) for every piece, batched: the ICH normals of
+// piece->Mesh (<= RefittingPointLimit points, host, VMACH::ConvexHull) -> k-DOP extents of piece->Mesh (one batched GPU
+// call) -> piece->Convex clipped by its own [Min0, Max0, Min1, ...] plane list (one GPU event, one (piece, cell) pair per
+// piece).  A piece whose convex is clipped away ends up with an empty Convex, as in the reference.
+void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args = FractureArgs());
 } // namespace SurtrHost

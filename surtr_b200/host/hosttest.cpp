@@ -1,5 +1,6 @@
 // hosttest.cpp -- flat C entry points over the host-side mirror CLASSES, so the Python tests can drive the
 // class-level API (Poly / Kdop / VMACH / DT3D / SurtrHost) exactly as a C++ caller would.  Test harness only.
+#include "ConvexHull.h"
 #include "DT3D.h"
 #include "Fracture.h"
 #include "Kdop.h"
@@ -138,7 +139,42 @@ void hosttest_plane_line_intersection(const float* a, const float* b, const floa
 	out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 
+// VMACH::GenerateICHNormal (host ICH): returns the number of normals
+uint32_t hosttest_ich_normals(const float* verts4, uint32_t nv, int limit, float* out, uint32_t cap)
+{
+	std::vector<Vector3> vv;
+	for (uint32_t i = 0; i < nv; i++) vv.emplace_back(verts4[4 * i], verts4[4 * i + 1], verts4[4 * i + 2]);
+	const std::vector<Vector3> n = VMACH::GenerateICHNormal(vv, limit);
+	for (uint32_t i = 0; i < n.size() && i < cap; i++) { out[3 * i] = n[i].x; out[3 * i + 1] = n[i].y; out[3 * i + 2] = n[i].z; }
+	return (uint32_t)n.size();
+}
+
 // ---- GPU-backed class API ----
+// SurtrHost::Refitting over pieces {Convex = polyset A, Mesh = point sets B}
+int hosttest_refit(const float* cverts, const uint32_t* cvert_off, const uint32_t* cring_off, const uint16_t* cring, uint32_t n,
+				   const float* mverts, const uint32_t* mvert_off, int limit)
+{
+	try
+	{
+		std::vector<SurtrHost::Piece*> pieces;
+		for (uint32_t i = 0; i < n; i++)
+		{
+			const Poly::Polyhedron convex = to_poly(cverts, cring_off, cring, cvert_off[i], cvert_off[i + 1]);
+			Poly::Polyhedron mesh(mvert_off[i + 1] - mvert_off[i]);
+			for (uint32_t v = mvert_off[i]; v < mvert_off[i + 1]; v++)
+				mesh[v - mvert_off[i]].Position = Vector3(mverts[4 * v], mverts[4 * v + 1], mverts[4 * v + 2]);
+			pieces.push_back(new SurtrHost::Piece(convex, mesh));
+		}
+		SurtrHost::FractureArgs args;
+		args.RefittingPointLimit = limit;
+		SurtrHost::Refitting(pieces, args);
+		g_out = Out();
+		for (auto* p : pieces) { g_out.add(p->Convex); delete p; }
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
 // SurtrHost::GenerateVoronoi(seeds) -> cells as polyhedra-free Polygon3D: exports planes + face vertices
 int hosttest_voronoi(const float* seeds, uint32_t n)
 {

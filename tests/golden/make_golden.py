@@ -166,9 +166,42 @@ def summaries():
         print(k, v["n"], v["n_verts"], v["sum_volume"])
 
 
+def refit_fixture():
+    """Refitting (m_refittingTask, Surtr.cpp:1449-1455) on 96 fragments of the 200x32 event; the "mesh" of a piece
+    is its convex shrunk towards its centroid by a per-piece factor (the real mesh branch is the next row f-1)."""
+    d0 = np.load(os.path.join(HERE, "pieces200_x32.npz"))
+    from test_oracle_port import load_polyset
+    fr = load_polyset(d0, "frag_")
+    sel = [i for i in range(fr.n) if fr.nverts[i] >= 6][:96]
+    convex = fr.subset(sel)
+    rng = np.random.RandomState(3)
+    mverts = convex.verts.copy()
+    for i in range(convex.n):
+        v0, v1 = int(convex.vert_off[i]), int(convex.vert_off[i + 1])
+        c = convex.verts[v0:v1, :3].mean(0, dtype=np.float32)
+        f = np.float32(rng.uniform(0.6, 0.98))
+        mverts[v0:v1, :3] = ((convex.verts[v0:v1, :3] - c) * f + c).astype(np.float32)
+    out = R.refit(convex, mverts, convex.vert_off, 4)
+    d = {"mesh_verts": mverts, "mesh_vert_off": convex.vert_off}
+    save_polyset(d, "convex_", convex, full=False)
+    save_polyset(d, "out_", out)
+    # the ICH normals of the first pieces, for the host ConvexHull mirror
+    nrm, noff = [], [0]
+    for i in range(convex.n):
+        v0, v1 = int(convex.vert_off[i]), int(convex.vert_off[i + 1])
+        n = R.ich_normals(mverts[v0:v1], min(v1 - v0, 4))
+        nrm.append(n)
+        noff.append(noff[-1] + len(n))
+    d["ich_normals"] = np.concatenate(nrm)
+    d["ich_normal_off"] = np.asarray(noff, np.uint32)
+    np.savez_compressed(os.path.join(HERE, "refit96.npz"), **d)
+    print("refit: out verts", out.nverts[:10], "empty", int((out.nverts == 0).sum()))
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     scalar_kats()
     small_events()
     config1_kdop()
+    refit_fixture()
     summaries()

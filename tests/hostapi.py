@@ -133,3 +133,25 @@ def kdop_ach(verts4, normals, max_axis, gap_inv, boxverts4):
     if rc:
         raise RuntimeError(_err())
     return planes, export()
+
+
+def ich_normals(verts4, limit):
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    out = np.zeros((4096, 3), np.float32)
+    L = lib()
+    L.hosttest_ich_normals.restype = C.c_uint32
+    L.hosttest_ich_normals.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
+    n = L.hosttest_ich_normals(_p(verts4), len(verts4), limit, _p(out), len(out))
+    return out[:n].copy()
+
+
+def refit(convex: PolySet, mesh_verts4, mesh_vert_off, limit=4) -> PolySet:
+    mesh_verts4 = np.ascontiguousarray(mesh_verts4, np.float32)
+    mesh_vert_off = np.ascontiguousarray(mesh_vert_off, np.uint32)
+    L = lib()
+    L.hosttest_refit.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.hosttest_refit(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring), convex.n,
+                          _p(mesh_verts4), _p(mesh_vert_off), limit)
+    if rc:
+        raise RuntimeError(_err())
+    return export()

@@ -89,3 +89,39 @@ def test_host_voronoi_cells_and_clip_moments_kdop():
         assert np.array_equal(bits(planes), bits(d[key + "_gap_planes"]))
         wa = load_polyset(d, key + "_ach_")
         assert np.array_equal(bits(ach.verts), bits(wa.verts)) and np.array_equal(ach.ring, wa.ring)
+
+
+def test_host_ich_normals_match_reference():
+    """VMACH::ConvexHull mirror (greedy incremental hull): same faces in the same order as the reference build."""
+    d = np.load(os.path.join(GOLDEN, "config1_kdop.npz"))
+    for key, n in (("bunny", 28), ("cube", 12), ("sphere", 36)):
+        got = H.ich_normals(d[key + "_verts"], 20)
+        assert len(got) == n and np.array_equal(bits(got), bits(d[key + "_normals"])), key
+    r = np.load(os.path.join(GOLDEN, "refit96.npz"))
+    off = r["mesh_vert_off"]
+    for i in range(len(off) - 1):
+        pts = r["mesh_verts"][off[i]:off[i + 1]]
+        got = H.ich_normals(pts, min(len(pts), 4))
+        want = r["ich_normals"][r["ich_normal_off"][i]:r["ich_normal_off"][i + 1]]
+        assert np.array_equal(bits(got), bits(want)), i
+
+
+@pytest.mark.gpu
+def test_host_refitting_matches_reference():
+    """SurtrHost::Refitting (m_refittingTask, Surtr.cpp:1449-1455) batched on the GPU == the reference per piece."""
+    r = np.load(os.path.join(GOLDEN, "refit96.npz"))
+    convex, want = load_polyset(r, "convex_"), load_polyset(r, "out_")
+    got = H.refit(convex, r["mesh_verts"], r["mesh_vert_off"], 4)
+    assert np.array_equal(got.vert_off, want.vert_off)
+    assert np.array_equal(bits(got.verts), bits(want.verts)) and np.array_equal(got.ring, want.ring)
+
+
+@pytest.mark.gpu
+def test_kdop_calc_batch_matches_oracle(ctx):
+    r = np.load(os.path.join(GOLDEN, "refit96.npz"))
+    dist, arg, planes = ctx.kdop_calc_batch(r["mesh_verts"], r["mesh_vert_off"], r["ich_normals"], r["ich_normal_off"])
+    off, noff = r["mesh_vert_off"], r["ich_normal_off"]
+    for i in range(len(off) - 1):
+        d, a, p = P.kdop_calc(r["mesh_verts"][off[i]:off[i + 1]], r["ich_normals"][noff[i]:noff[i + 1]])
+        sl = slice(noff[i], noff[i + 1])
+        assert np.array_equal(bits(dist[sl]), bits(d)) and np.array_equal(arg[sl], a) and np.array_equal(bits(planes[sl]), bits(p))
