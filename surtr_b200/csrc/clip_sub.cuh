@@ -16,8 +16,11 @@
 // Sequential replays (in-plane vertices, walk anomalies, degree-2 splice) run on one lane over the same words.
 //
 // Lane count: ncu on the one-warp-per-pair version showed 6-14 of 32 lanes active in every phase but the
-// classification (profiles/), so the kernel is instantiated with L = 16: two pairs per warp, each half-warp using
-// its own member mask for ballots / shuffles / __syncwarp, which roughly halves the warp-instructions per pair.
+// classification (profiles/).  With L < 32 a warp works on 32/L pairs in LOCK STEP: every collective (ballot, shuffle,
+// __syncwarp) is executed by all 32 lanes with the full member mask (shuffles confined to the pair's lanes by their
+// width argument), every branch that contains a collective is decided by a warp-wide vote, and the pair-specific work
+// inside is predicated.  (Per-pair member masks were measured first: they split the warp into serially executed
+// groups at every collective and were slower than one warp per pair.)
 #pragma once
 
 #include "clip_warp.cuh"
@@ -90,28 +93,29 @@ struct CutState   // uniform across the lanes of one pair
     int hi;     // allocated vertex slots
 };
 
-// The lanes that work on one pair: L consecutive lanes of a warp with their own member mask.
+// The L consecutive lanes of a warp that work on one pair.  All collectives use the full member mask (lock step).
 template <int L>
 struct Sub
 {
     static constexpr int G = 64 / L;   // vertex slots per lane: lane sl owns slots sl, sl + L, ...
     int sl;
-    unsigned shift, smask;
+    unsigned shift;
     __device__ __forceinline__ explicit Sub(int lane)
     {
         sl = lane % L;
         shift = (unsigned)(lane / L) * L;
-        smask = L == 32 ? 0xffffffffu : (((1u << (L & 31)) - 1u) << shift);
     }
     __device__ __forceinline__ unsigned ballot(bool p) const
     {
-        const unsigned b = __ballot_sync(smask, p);
+        const unsigned b = __ballot_sync(FULL, p);
         return L == 32 ? b : ((b >> shift) & ((1u << (L & 31)) - 1u));
     }
-    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(smask, v, src, L); }
-    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(smask, v, d, L); }
-    template <class T> __device__ __forceinline__ T shfl_xor(T v, int d) const { return __shfl_xor_sync(smask, v, d, L); }
-    __device__ __forceinline__ void sync() const { __syncwarp(smask); }
+    __device__ __forceinline__ bool any_warp(bool p) const { return __any_sync(FULL, p); }   // warp-uniform vote
+    __device__ __forceinline__ int max_warp(int v) const { return __reduce_max_sync(FULL, v); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(FULL, v, src, L); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(FULL, v, d, L); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int d) const { return __shfl_xor_sync(FULL, v, d, L); }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
     template <class T> __device__ __forceinline__ T exscan(T v, T& total) const
     {
         T inc = v;
@@ -143,16 +147,17 @@ __device__ __forceinline__ int comp_of(const CutState& s, int hi0, u64 dead, int
 
 // Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) by one lane after the new vertices
 // have been inserted.  Visiting order = the reference's: new vertices first, then the pre-existing ones, both
-// ascending.  Returns 0 on ring overflow; `dead` receives the vertices spliced away.
+// ascending.  Called by all lanes of the warp; only pairs with `pred` do anything.  Returns 0 on ring overflow;
+// `dead` receives the vertices spliced away.
 template <int L>
-__device__ __noinline__ int sub_seq_cut(SubPoly& sp, const CutState s, int hi0, int nnew, const Sub<L> sub, u64& dead)
+__device__ __noinline__ int sub_seq_cut(SubPoly& sp, const CutState s, int hi0, int nnew, const Sub<L> sub, bool pred, u64& dead)
 {
-    const int hi1 = hi0 + nnew;
+    const int hi1 = pred ? hi0 + nnew : 0;
     for (int v = sub.sl; v < hi1; v += L) sp.old_ring[v] = sp.ring[v];
     sub.sync();
     int ok = 1;
     unsigned dlo = 0u, dhi = 0u;
-    if (sub.sl == 0)
+    if (pred && sub.sl == 0)
     {
         u64 dd = 0ull;
         const int nverts = __popcll(s.live) + nnew;   // the reference's vertex count (walk bound)
@@ -234,9 +239,10 @@ __device__ __noinline__ int sub_seq_cut(SubPoly& sp, const CutState s, int hi0, 
 }
 
 // Renumber the live vertices to 0..n-1 keeping their order (the reference's compaction, Poly.cpp:464-495).
-// Positions are read from / written to shared memory; the caller reloads its register copies.
+// Called by all lanes of the warp; only pairs with `pred` do anything.  Positions are read from / written to shared
+// memory; the caller reloads its register copies.
 template <int L>
-__device__ __noinline__ void sub_compact(SubPoly& sp, CutState& s, const Sub<L> sub)
+__device__ __noinline__ void sub_compact(SubPoly& sp, CutState& s, const Sub<L> sub, bool pred)
 {
     constexpr int G = Sub<L>::G;
     u64 r[G];
@@ -246,7 +252,8 @@ __device__ __noinline__ void sub_compact(SubPoly& sp, CutState& s, const Sub<L> 
     {
         const int v = sub.sl + L * g;
         r[g] = ~0ull;
-        if (bit64(s.live, v))
+        vx[g] = vy[g] = vz[g] = 0.f;
+        if (pred && bit64(s.live, v))
         {
             vx[g] = sp.x[v]; vy[g] = sp.y[v]; vz[g] = sp.z[v];
             const u64 rw = sp.ring[v];
@@ -263,19 +270,22 @@ __device__ __noinline__ void sub_compact(SubPoly& sp, CutState& s, const Sub<L> 
     for (int g = 0; g < G; g++)
     {
         const int v = sub.sl + L * g;
-        if (bit64(s.live, v))
+        if (pred && bit64(s.live, v))
         {
             const int t = rank64(s.live, v);
             sp.x[t] = vx[g]; sp.y[t] = vy[g]; sp.z[t] = vz[g]; sp.ring[t] = r[g];
         }
     }
     sub.sync();
-    const int n = __popcll(s.live);
-    s.hi = n;
-    s.live = lowmask64(n);
+    if (pred)
+    {
+        const int n = __popcll(s.live);
+        s.hi = n;
+        s.live = lowmask64(n);
+    }
 }
 
-// Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).
+// Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).  Called by all lanes.
 template <int L>
 __device__ __noinline__ bool sub_all_inplane_box_says_skip(const SubPoly& sp, const CutState s, const float4 pl, const Sub<L> sub)
 {
@@ -299,19 +309,22 @@ __device__ __noinline__ bool sub_all_inplane_box_says_skip(const SubPoly& sp, co
     return sub.ballot(c == -1) == 0u;
 }
 
-// Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1) by planes[0..npl).  On return s.live are the live
-// slots (not renumbered) and nv their count (0 = no fragment).
+// Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1) by planes[0..npl).  Called by all 32 lanes; a pair
+// with alive == false just takes part in the collectives.  On return s.live are the live slots (not renumbered),
+// nv their count (0 = no fragment) and the return value the pair's status.
 template <int L>
 __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float4* __restrict__ planes, int npl, const Sub<L> sub,
-                                  unsigned& seq_cuts, unsigned& n_cuts)
+                                  bool alive, unsigned& seq_cuts, unsigned& n_cuts)
 {
     constexpr int G = Sub<L>::G;
     constexpr int FW = G <= 4 ? 32 / G : 8;                               // bits per group in the packed scans
     using ScanT = typename std::conditional<(G <= 4), unsigned, u64>::type;
     constexpr ScanT FM = (ScanT)((FW == 32) ? ~0u : ((1ull << (FW & 63)) - 1ull));
     float px[G], py[G], pz[G];
+    if (!alive) { nv = 0; npl = 0; }
     s.hi = nv;
     s.live = lowmask64(nv);
+    s.c = s.k = 0ull;
 #pragma unroll
     for (int g = 0; g < G; g++)
     {
@@ -320,59 +333,69 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
         if (v < nv) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
     }
 
-    for (int kb = 0; kb < npl && nv > 0; kb += L)
+    int status = CLIP_OK;
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = 0, loaded = -1;
+    while (true)
     {
-        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kb + sub.sl < npl) mine = __ldg(planes + kb + sub.sl);   // lane sl holds plane kb + sl
-        const int kend = min(L, npl - kb);
-        for (int kk = 0; kk < kend && nv > 0; kk++)
+        const bool run = p < npl && nv > 0 && status == CLIP_OK;   // this pair still has a plane to apply
+        if (!sub.any_warp(run)) break;
+        if (run && p / L != loaded)
         {
-            float4 pl;
-            pl.x = sub.shfl(mine.x, kk);
-            pl.y = sub.shfl(mine.y, kk);
-            pl.z = sub.shfl(mine.z, kk);
-            pl.w = sub.shfl(mine.w, kk);
+            loaded = p / L;
+            mine = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (loaded * L + sub.sl < npl) mine = __ldg(planes + loaded * L + sub.sl);   // lane sl holds plane loaded*L + sl
+        }
+        float4 pl;
+        pl.x = sub.shfl(mine.x, p % L);
+        pl.y = sub.shfl(mine.y, p % L);
+        pl.z = sub.shfl(mine.z, p % L);
+        pl.w = sub.shfl(mine.w, p % L);
 
-            // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per group ----
-            s.c = s.k = 0ull;
+        // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per group ----
+        const int gmax = L == 32 ? (s.hi + L - 1) / L : sub.max_warp(run ? (s.hi + L - 1) / L : 0);
+        s.c = s.k = 0ull;
 #pragma unroll
-            for (int g = 0; g < G; g++)
+        for (int g = 0; g < G; g++)
+        {
+            if (g < gmax)
             {
-                if (g * L < s.hi)
-                {
-                    int c = 3;
-                    if (bit64(s.live, sub.sl + L * g)) c = classify(signed_dist(pl, px[g], py[g], pz[g]));
-                    s.c |= (u64)sub.ballot(c == -1) << (g * L);
-                    s.k |= (u64)sub.ballot(c == 1) << (g * L);
-                }
+                int c = 3;
+                if (run && bit64(s.live, sub.sl + L * g)) c = classify(signed_dist(pl, px[g], py[g], pz[g]));
+                s.c |= (u64)sub.ballot(c == -1) << (g * L);
+                s.k |= (u64)sub.ballot(c == 1) << (g * L);
             }
-            if (!s.k)
-            {
-                // "below" (Poly.cpp:322-327) -- unless every vertex is in-plane and the box test says "above"
-                if (!s.c && sub_all_inplane_box_says_skip<L>(sp, s, pl, sub)) continue;
-                nv = 0;
-                break;
-            }
-            if (!s.c) continue;   // "above" (Poly.cpp:328)
+        }
+        // "below" (Poly.cpp:322-327) -- unless every vertex is in-plane and the box test says "above"
+        const bool need_box = run && !s.k && !s.c;
+        bool box_skip = false;
+        if (sub.any_warp(need_box)) box_skip = sub_all_inplane_box_says_skip<L>(sp, s, pl, sub);
+        if (run && !s.k && !(need_box && box_skip)) nv = 0;
+        const bool cut = run && s.k != 0ull && s.c != 0ull;   // otherwise "above" (Poly.cpp:328) or removed
+        bool redo = false;
 
-            // ---- the plane cuts ----
-            n_cuts++;
+        if (sub.any_warp(cut))
+        {
+            // ---- the plane cuts (some pair of this warp) ----
             sub.sync();   // ring words composed by the previous cut are visible from here on
             // straddling half-edges (clipped vertex -> kept neighbour) in the reference's append order
             u64 smk = 0ull;    // 8 slot bits per owned group
             ScanT cnt = 0;     // FW-bit counter per owned group
-#pragma unroll
-            for (int g = 0; g < G; g++)
+            if (cut)
             {
-                const int v = sub.sl + L * g;
-                if (g * L < s.hi && bit64(s.c, v))
+#pragma unroll
+                for (int g = 0; g < G; g++)
                 {
-                    const u64 rw = sp.ring[v];
-                    for (int j = 0; j < 8; j++)
+                    const int v = sub.sl + L * g;
+                    if (g * L < s.hi && bit64(s.c, v))
                     {
-                        const int b = rget(rw, j);
-                        if (b == R_NONE) break;
-                        if (bit64(s.k, b)) { smk |= 1ull << (j + 8 * g); cnt += (ScanT)1 << (FW * g); }
+                        const u64 rw = sp.ring[v];
+                        for (int j = 0; j < 8; j++)
+                        {
+                            const int b = rget(rw, j);
+                            if (b == R_NONE) break;
+                            if (bit64(s.k, b)) { smk |= 1ull << (j + 8 * g); cnt += (ScanT)1 << (FW * g); }
+                        }
                     }
                 }
             }
@@ -381,23 +404,30 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
             int nnew = 0;
 #pragma unroll
             for (int g = 0; g < G; g++) nnew += (int)((tot >> (FW * g)) & FM);
-            if (s.hi + nnew > 64)
+            bool docut = cut;
+            const bool full = cut && s.hi + nnew > 64;
+            if (sub.any_warp(full))
             {
                 // out of slots: renumber the live vertices (exactly the reference's compaction) and redo this plane
-                if (__popcll(s.live) + nnew > 64) return CLIP_OVERFLOW;
-                sub_compact<L>(sp, s, sub);
-#pragma unroll
-                for (int g = 0; g < G; g++)
+                const bool ovf = full && __popcll(s.live) + nnew > 64;
+                if (ovf) status = CLIP_OVERFLOW;
+                sub_compact<L>(sp, s, sub, full && !ovf);
+                if (full && !ovf)
                 {
-                    const int v = sub.sl + L * g;
-                    if (v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                    {
+                        const int v = sub.sl + L * g;
+                        if (v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+                    }
+                    redo = true;
                 }
-                n_cuts--;
-                kk--;
-                continue;
+                docut = cut && !full;
             }
+            if (!docut) nnew = 0;
+            if (docut) n_cuts++;
             const int hi0 = s.hi;
-            if (smk)
+            if (docut && smk)
             {
                 int gbase = 0;
 #pragma unroll
@@ -428,10 +458,10 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
             sub.sync();
 
             // patch (Poly.cpp:365-431): walk from each new vertex through clipped vertices to the next new one
-            bool need_seq = (s.live & ~(s.c | s.k)) != 0ull;   // an in-plane vertex
+            bool need_seq = docut && (s.live & ~(s.c | s.k)) != 0ull;   // an in-plane vertex
+            bool ok = true;
             if (!need_seq)
             {
-                bool ok = true;
                 for (int t = sub.sl; t < nnew; t += L)
                 {
                     const int w = hi0 + t;
@@ -447,54 +477,66 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
                     sp.list[t] = (uint16_t)inext;
                     ok = ok && okt;
                 }
-                sub.sync();
+            }
+            sub.sync();
+            if (!need_seq)
                 for (int t = sub.sl; t < nnew; t += L)
                     if (ok) ok = sp.id[sp.list[t]] == (uint8_t)(hi0 + t);
-                need_seq = sub.ballot(!ok) != 0u;
-                if (!need_seq)
+            const bool anomaly = sub.ballot(!ok) != 0u;
+            need_seq = need_seq || (docut && anomaly);
+            if (docut && !need_seq)
+            {
+                // the walk targets are a permutation of the new vertices: ring(w) = [pusher, walked, kept]
+                for (int t = sub.sl; t < nnew; t += L)
                 {
-                    // the walk targets are a permutation of the new vertices: ring(w) = [pusher, walked, kept]
-                    for (int t = sub.sl; t < nnew; t += L)
-                    {
-                        const int w = hi0 + t;
-                        const int kept = rget(sp.ring[w], 1);
-                        sp.ring[w] = 0xffffffffff000000ull | (u64)sp.id[w] | ((u64)sp.list[t] << 8) | ((u64)(unsigned)kept << 16);
-                    }
+                    const int w = hi0 + t;
+                    const int kept = rget(sp.ring[w], 1);
+                    sp.ring[w] = 0xffffffffff000000ull | (u64)sp.id[w] | ((u64)sp.list[t] << 8) | ((u64)(unsigned)kept << 16);
                 }
             }
             u64 dead = 0ull;
-            if (need_seq)
+            if (sub.any_warp(need_seq))
             {
-                seq_cuts++;
-                if (!sub_seq_cut<L>(sp, s, hi0, nnew, sub, dead)) return CLIP_OVERFLOW;
+                const int r = sub_seq_cut<L>(sp, s, hi0, nnew, sub, need_seq, dead);
+                if (need_seq)
+                {
+                    seq_cuts++;
+                    if (!r) status = CLIP_OVERFLOW;
+                }
+                else dead = 0ull;
             }
-            // lazy compaction: clipped vertices leave the live set, new ones join it
-            s.hi = hi0 + nnew;
-            s.live = ((s.live & ~s.c) | (lowmask64(s.hi) & ~lowmask64(hi0))) & ~dead;
-            nv = __popcll(s.live);
-            if (nv < 4) nv = 0;   // Poly.cpp:498-499
-#pragma unroll
-            for (int g = 0; g < G; g++)
+            if (docut)
             {
-                const int v = sub.sl + L * g;
-                if (v >= hi0 && v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+                // lazy compaction: clipped vertices leave the live set, new ones join it
+                s.hi = hi0 + nnew;
+                s.live = ((s.live & ~s.c) | (lowmask64(s.hi) & ~lowmask64(hi0))) & ~dead;
+                nv = __popcll(s.live);
+                if (nv < 4) nv = 0;   // Poly.cpp:498-499
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                {
+                    const int v = sub.sl + L * g;
+                    if (v >= hi0 && v < s.hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+                }
             }
         }
+        if (run && !redo) p++;
     }
     sub.sync();
-    return CLIP_OK;
+    return status;
 }
 
 // Poly::ExtractFaces + Poly::Moments in the reference's accumulation order (Poly.cpp:55-126) + inertia, on the
 // live (not renumbered) slots: vertex order = slot order, origin = first live vertex.  See fragment_moments in
-// clip_warp.cuh for the derivation.
+// clip_warp.cuh for the derivation.  Called by all lanes of the warp; pairs without a fragment (`has` false) idle.
 template <int L>
-__device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L> sub, Moments& out)
+__device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L> sub, bool has, Moments& out)
 {
     constexpr int G = Sub<L>::G;
-    const int first = __ffsll((long long)s.live) - 1;
+    const int first = has ? __ffsll((long long)s.live) - 1 : 0;
+    const int gmax = L == 32 ? (s.hi + L - 1) / L : sub.max_warp(has ? (s.hi + L - 1) / L : 0);
     const float ox = sp.x[first], oy = sp.y[first], oz = sp.z[first];
-    const int nv = __popcll(s.live);
+    const int nv = has ? __popcll(s.live) : 0;
     u64 start_mask = 0ull;   // 8 slot bits per owned group
     int faces = 0, cnt = 0;  // triangles of the faces this lane starts (all groups: one lane = one scan entry per group)
     int cntg[G];
@@ -503,7 +545,7 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
     {
         cntg[g] = 0;
         const int v = sub.sl + L * g;
-        if (g * L < s.hi && bit64(s.live, v))
+        if (has && g * L < s.hi && bit64(s.live, v))
         {
             const u64 rw = sp.ring[v];
             const int d = rdeg(rw);
@@ -540,7 +582,7 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
     for (int g = 0; g < G; g++)
     {
         tri_base[g] = 0;
-        if (g * L < s.hi)
+        if (g < gmax)
         {
             int tot;
             tri_base[g] = n_tri + sub.exscan(cntg[g], tot);

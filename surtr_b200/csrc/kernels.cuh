@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
 // K3, small tier: L lanes per candidate pair (clip_sub.cuh), one pair per sub-warp, no persistent loop (the
 // hardware scheduler balances the very uneven pair costs).
 constexpr int FAST_WARPS = 4;
-constexpr int FAST_LANES = 32;   // lanes per pair: 32 = one warp per pair (16 = two pairs per warp measured slower, see clip_sub.cuh)
+constexpr int FAST_LANES = 32;   // lanes per pair; 16 (two pairs per warp in lock step) is correct but measured slower, see DESIGN.md section 7
 constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
 
 template <int L>
@@ -456,34 +456,42 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_ker
     const unsigned long long q64 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
     unsigned long long n_items = a.ctl->n_cand;
     if (n_items > a.cap_cand) n_items = a.cap_cand;
-    if (q64 >= n_items) return;
-    const uint32_t q = (uint32_t)q64;
+    // All lanes of a warp stay in the kernel to the end (the pairs of a warp run in lock step); a sub-warp without
+    // a pair, or whose pair is finished, just takes part in the collectives.
+    const bool have = q64 < n_items;
+    const uint32_t q = have ? (uint32_t)q64 : 0u;
     const long long t0 = a.dbg ? clock64() : 0;
 
-    const uint2 pr = a.cand[q];
-    const uint32_t v0 = a.p_vert_off[pr.x];
-    int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
-    const uint32_t pl0 = a.c_plane_off[pr.y];
-    const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-    bool bad = nv > 64;
-    if (!bad)
+    int nv = 0, npl = 0;
+    uint32_t pl0 = 0;
+    bool bad = false;
+    if (have)
     {
-        for (int v = sub.sl; v < nv; v += L)
+        const uint2 pr = a.cand[q];
+        const uint32_t v0 = a.p_vert_off[pr.x];
+        nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+        pl0 = a.c_plane_off[pr.y];
+        npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+        bad = nv > 64;
+        if (!bad)
         {
-            const float4 p = __ldg(a.p_verts + v0 + v);
-            const uint32_t r0 = a.p_ring_off[v0 + v];
-            const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
-            sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
-            u64 rw = ~0ull;
-            if (d > 8 || d == 0) bad = true;
-            else
-                for (int j = 0; j < d; j++)
-                {
-                    const int idx = a.p_ring[r0 + j];
-                    bad = bad || idx >= nv;
-                    rw = rset(rw, j, idx);
-                }
-            sp.ring[v] = rw;
+            for (int v = sub.sl; v < nv; v += L)
+            {
+                const float4 p = __ldg(a.p_verts + v0 + v);
+                const uint32_t r0 = a.p_ring_off[v0 + v];
+                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                u64 rw = ~0ull;
+                if (d > 8 || d == 0) bad = true;
+                else
+                    for (int j = 0; j < d; j++)
+                    {
+                        const int idx = a.p_ring[r0 + j];
+                        bad = bad || idx >= nv;
+                        rw = rset(rw, j, idx);
+                    }
+                sp.ring[v] = rw;
+            }
         }
     }
     bad = sub.ballot(bad) != 0u;
@@ -491,11 +499,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_ker
     const long long t1 = a.dbg ? clock64() : 0;
     const int nv_in = nv;
     unsigned seq_cuts = 0, n_cuts = 0;
-    int status = CLIP_OVERFLOW;
     CutState cs;
-    if (!bad) status = sub_clip_by_planes<L>(sp, cs, nv, a.c_planes + pl0, npl, sub, seq_cuts, n_cuts);
+    int status = sub_clip_by_planes<L>(sp, cs, nv, a.c_planes + pl0, npl, sub, have && !bad, seq_cuts, n_cuts);
+    if (bad) status = CLIP_OVERFLOW;
     const long long t2 = a.dbg ? clock64() : 0;
-    if (a.dbg && sub.sl == 0)
+    if (a.dbg && have && sub.sl == 0)
     {
         uint32_t* d = a.dbg + (size_t)q * 8;
         d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
@@ -503,23 +511,17 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_ker
     }
     if (seq_cuts && sub.sl == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
     CandRec* rec = a.rec + q;
-    if (status != CLIP_OK)
+    if (have && status != CLIP_OK && sub.sl == 0)
     {
         // too large for this tier (or a ring outgrew 8 slots): queue the pair for the large tier
-        if (sub.sl == 0)
-        {
-            rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-            a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
-        }
-        return;
+        rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+        a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
     }
-    if (nv == 0)
-    {
-        if (sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
-        return;
-    }
+    if (have && status == CLIP_OK && nv == 0 && sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
+    const bool has = have && status == CLIP_OK && nv > 0;
+    if (!sub.any_warp(has)) return;
     Moments mo;
-    sub_fragment_moments<L>(sp, cs, sub, mo);
+    sub_fragment_moments<L>(sp, cs, sub, has, mo);
     const long long t3 = a.dbg ? clock64() : 0;
 
     // result blob, renumbered to the reference's final order (rank in the live mask):
@@ -529,27 +531,30 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_ker
     float4* bv = reinterpret_cast<float4*>(b);
     uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
     uint8_t* br = b + 64 * 18;
+    const int gmax = L == 32 ? (cs.hi + L - 1) / L : sub.max_warp(has ? (cs.hi + L - 1) / L : 0);
     int ne = 0;
 #pragma unroll
     for (int g = 0; g < G; g++)
     {
-        if (g * L >= cs.hi) break;
-        const int v = sub.sl + L * g;
-        const bool live = bit64(cs.live, v);
-        const u64 rw = live ? sp.ring[v] : ~0ull;
-        const int d = rdeg(rw);
-        int tot;
-        const int off = ne + sub.exscan(d, tot);
-        ne += tot;
-        if (live)
+        if (g < gmax)
         {
-            const int t = rank64(cs.live, v);
-            bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
-            bo[t] = (uint16_t)off;
-            for (int j = 0; j < d; j++) br[off + j] = (uint8_t)rank64(cs.live, rget(rw, j));
+            const int v = sub.sl + L * g;
+            const bool live = has && bit64(cs.live, v);
+            const u64 rw = live ? sp.ring[v] : ~0ull;
+            const int d = rdeg(rw);
+            int tot;
+            const int off = ne + sub.exscan(d, tot);
+            ne += tot;
+            if (live)
+            {
+                const int t = rank64(cs.live, v);
+                bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+                bo[t] = (uint16_t)off;
+                for (int j = 0; j < d; j++) br[off + j] = (uint8_t)rank64(cs.live, rget(rw, j));
+            }
         }
     }
-    if (sub.sl == 0)
+    if (has && sub.sl == 0)
     {
         rec->nv = (uint32_t)nv;
         rec->ne = (uint32_t)ne;
