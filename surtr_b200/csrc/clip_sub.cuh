@@ -44,10 +44,8 @@ constexpr int R_MARK = 0xfe;   // the reference's "-1, to be removed" (Poly.cpp:
 
 __device__ __forceinline__ int rdeg(u64 w)
 {
-    const unsigned mlo = __vcmpeq4((unsigned)w, 0xffffffffu);
-    if (mlo) return (__ffs(mlo) - 1) >> 3;
-    const unsigned mhi = __vcmpeq4((unsigned)(w >> 32), 0xffffffffu);
-    return mhi ? 4 + ((__ffs(mhi) - 1) >> 3) : 8;
+    // empty slots (0xFF) are the trailing bytes; every other value (< 64, or the 0xFE mark) has a zero bit
+    return 8 - (__clzll((long long)~w) >> 3);
 }
 __device__ __forceinline__ int rfind(u64 w, int val)   // first slot holding val, 8 if absent
 {
@@ -465,7 +463,11 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
                 for (int t = sub.sl; t < nnew; t += L)
                 {
                     const int w = hi0 + t;
-                    int iprev = w, inext = rget(sp.ring[w], 0), itmp, k = 0;
+                    // first step without a search: w sits in slot j of its clipped end point v, so FaceLoop(v, w)
+                    // is simply the slot before j (list[t] still holds v | j << 8 from the insertion)
+                    const int e = sp.list[t], v = e & 0xff, j = e >> 8;
+                    const u64 rv = sp.ring[v];
+                    int iprev = v, inext = rget(rv, (j == 0 ? rdeg(rv) : j) - 1), itmp, k = 1;
                     while (inext < hi0 && bit64(s.c, inext) && k++ < 64)
                     {
                         itmp = inext;
