@@ -502,6 +502,84 @@ void ref_refit(const float* cverts, const uint32_t* cvert_off, const uint32_t* c
 	}
 }
 
+// Config 1, convex branch: restatement of Surtr::PrepareFracture steps 1-6, 8, 10 (Surtr.cpp:1747-1811) on a vertex
+// cloud: ICH normals (limit) -> bbox -> k-DOP with gap -> ACH = 2x bbox clipped -> Voronoi cells of `seeds`
+// (unit box) scaled by the bbox extent and translated to its centre (Polygon3D::Scale/Translate re-derive every
+// plane, VMACH.cpp:506-534) -> ApplyFracture on the single ACH piece.  out_ach gets the ACH, out the fragments.
+void ref_config1_convex(const float* verts4, uint32_t nv, int ich_limit, float gap_inv, const float* seeds, uint32_t n_seeds,
+						const uint32_t* nb_off, const uint32_t* nb_idx, void* out_ach, void* out)
+{
+	std::vector<Vector3> vertices;
+	for (uint32_t v = 0; v < nv; v++)
+		vertices.emplace_back(verts4[4 * v], verts4[4 * v + 1], verts4[4 * v + 2]);
+	VMACH::ConvexHull ich(vertices, (uint32_t)ich_limit);
+	std::vector<Vector3> normals;
+	for (const VMACH::ConvexHullFace& f : ich.GetFaces())
+	{
+		Vector3 normal = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+		normal.Normalize();
+		normals.push_back(normal);
+	}
+	double minX, maxX, minY, maxY, minZ, maxZ;
+	{
+		const auto x = std::minmax_element(vertices.begin(), vertices.end(), [](const Vector3& p1, const Vector3& p2) { return p1.x < p2.x; });
+		const auto y = std::minmax_element(vertices.begin(), vertices.end(), [](const Vector3& p1, const Vector3& p2) { return p1.y < p2.y; });
+		const auto z = std::minmax_element(vertices.begin(), vertices.end(), [](const Vector3& p1, const Vector3& p2) { return p1.z < p2.z; });
+		minX = (*x.first).x; maxX = (*x.second).x;
+		minY = (*y.first).y; maxY = (*y.second).y;
+		minZ = (*z.first).z; maxZ = (*z.second).z;
+	}
+	const Vector3 BBCenter((maxX + minX) / 2.0, (maxY + minY) / 2.0, (maxZ + minZ) / 2.0);
+	const float MaxAxisScale = std::max(std::max(maxX - minX, maxY - minY), maxZ - minZ);   // stored as float (Surtr.h:154)
+	Kdop::KdopContainer achKdop(normals);
+	achKdop.Calc(vertices, MaxAxisScale, gap_inv);
+	Poly::Polyhedron ach = Poly::GetBB();
+	Poly::Scale(ach, Vector3((maxX - minX), (maxY - minY), (maxZ - minZ)));
+	Poly::Scale(ach, Vector3(2.0, 2.0, 2.0));
+	Poly::Translate(ach, BBCenter);
+	ach = achKdop.ClipWithPolyhedron(ach);
+	append(*(PolySet*)out_ach, ach, 0, 0);
+
+	// cells: the new derivation (unit box), as VMACH::Polygon3D built through PolygonFace::AddVertex
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n_seeds; i++)
+		s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	std::vector<VMACH::Polygon3D> voroPolyVec;
+	for (uint32_t i = 0; i < n_seeds; i++)
+	{
+		std::vector<Plane> planes;
+		for (uint32_t k = nb_off[i]; k < nb_off[i + 1]; k++)
+			planes.push_back(bisector(s[i], s[nb_idx[k]]));
+		Poly::Polyhedron cell = Poly::GetBB();
+		Poly::ClipPolyhedron(cell, planes);
+		Poly::Extract* faces = Poly::ExtractFaces(cell);
+		VMACH::Polygon3D poly(true);
+		for (const auto& loop : *faces)
+		{
+			VMACH::PolygonFace f(true);
+			for (int v : loop)
+				f.AddVertex(cell[v].Position);
+			poly.AddFace(f);
+		}
+		delete faces;
+		voroPolyVec.push_back(poly);
+	}
+	for (VMACH::Polygon3D& voro : voroPolyVec)
+	{
+		voro.Scale(Vector3((maxX - minX), (maxY - minY), (maxZ - minZ)));
+		voro.Translate(BBCenter);
+	}
+	// ApplyFracture, convex branch, single piece
+	PolySet& o = *(PolySet*)out;
+	for (uint32_t c = 0; c < n_seeds; c++)
+	{
+		Poly::Polyhedron convex = Poly::ClipPolyhedron(ach, voroPolyVec[c]);
+		if (convex.empty())
+			continue;
+		append(o, convex, c, 0);
+	}
+}
+
 // Scalar helpers for the unit KATs (Poly.cpp:716-751).
 int ref_compare_plane_point(const float* plane, const float* p)
 {

@@ -261,3 +261,17 @@ def refit(convex: PolySet, mesh_verts4: np.ndarray, mesh_vert_off: np.ndarray, l
     lib().ref_refit(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring), convex.n,
                     _p(mesh_verts4), _p(mesh_vert_off), limit, h)
     return _export(h)
+
+
+def config1_convex(verts4, seeds, nb_off, nb_idx, ich_limit=20, gap_inv=2000.0):
+    """PrepareFracture's convex branch on a vertex cloud (see ref_driver.cpp).  Returns (ACH, fragments)."""
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    seeds = np.ascontiguousarray(seeds, np.float32)
+    nb_off = np.ascontiguousarray(nb_off, np.uint32)
+    nb_idx = np.ascontiguousarray(nb_idx, np.uint32)
+    L = lib()
+    L.ref_config1_convex.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    h1, h2 = L.ref_polyset_new(), L.ref_polyset_new()
+    L.ref_config1_convex(_p(verts4), len(verts4), ich_limit, gap_inv, _p(seeds), len(seeds), _p(nb_off), _p(nb_idx), h1, h2)
+    return _export(h1), _export(h2)

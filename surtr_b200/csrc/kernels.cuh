@@ -337,7 +337,13 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
                 else
                 {
                     sp.deg[v] = (uint8_t)d;
-                    for (int j = 0; j < d; j++) sp.ring[v * DMAX + j] = (IdxT)a.p_ring[r0 + j];
+                    if (d == 0) too_big = true;   // a vertex without neighbours is not a polyhedron vertex
+                    for (int j = 0; j < d; j++)
+                    {
+                        const int idx = a.p_ring[r0 + j];
+                        if (idx >= nv) too_big = true;   // malformed input: reported as a failed pair, never indexed
+                        sp.ring[v * DMAX + j] = (IdxT)idx;
+                    }
                 }
             }
         }

@@ -373,7 +373,7 @@ int resolve_event(surtr_ctx* ctx)
         {
             if (c.n_tier2_fail)
                 return fail(ctx, SURTR_ERR_OVERFLOW,
-                            std::to_string(c.n_tier2_fail) + " pair(s) exceed the largest on-chip clip tier (256 vertices, ring degree 16)");
+                            std::to_string(c.n_tier2_fail) + " pair(s) exceed the largest on-chip clip tier (256 vertices, ring degree 16) or have malformed rings");
             ctx->last.n_pairs = ctx->n_pairs;
             ctx->last.n_candidates = c.n_cand;
             ctx->last.n_fragments = c.n_frag;

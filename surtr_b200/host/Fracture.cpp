@@ -3,6 +3,7 @@
 #include "ConvexHull.h"
 #include "DT3D.h"
 #include "Engine.h"
+#include "Kdop.h"
 
 #include <algorithm>
 #include <random>
@@ -45,6 +46,47 @@ std::vector<Vector3> GenerateRadialSeeds(int seed, int cellCount, double mean)
 }
 
 std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPointVec) { return DT3D::VoronoiCells(cellPointVec); }
+
+PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<Vector3>& seeds, const FractureArgs& args)
+{
+	PreparedObject r;
+	// 1-2. intermediate convex hull with limit count -> face normals
+	const std::vector<Vector3> normals = VMACH::GenerateICHNormal(vertices, args.ICHIncludePointLimit);
+	r.ICHFaceCnt = (int)normals.size();
+	// 3. bounding box (doubles holding float values, as the reference)
+	double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+	for (const Vector3& v : vertices)
+	{
+		const double c[3] = { v.x, v.y, v.z };
+		for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], c[k]); hi[k] = std::max(hi[k], c[k]); }
+	}
+	r.BBCenter = Vector3((hi[0] + lo[0]) / 2.0, (hi[1] + lo[1]) / 2.0, (hi[2] + lo[2]) / 2.0);
+	r.MinBB = Vector3(lo[0], lo[1], lo[2]);
+	r.MaxBB = Vector3(hi[0], hi[1], hi[2]);
+	r.MaxAxisScale = (float)std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+	// 4. min/max planes of the k-DOP (GPU)
+	Kdop::KdopContainer achKdop(normals);
+	achKdop.Calc(vertices, r.MaxAxisScale, args.ACHPlaneGapInverse);
+	// 5-6. ACH seed box, clipped by the k-DOP (GPU)
+	Poly::Polyhedron ach = Poly::GetBB();
+	Poly::Scale(ach, Vector3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]));
+	Poly::Scale(ach, Vector3(2.0, 2.0, 2.0));
+	Poly::Translate(ach, r.BBCenter);
+	r.ACH = achKdop.ClipWithPolyhedron(ach);
+	// 8. Voronoi cells for the initial decomposition, placed on the object
+	r.Cells = GenerateVoronoi(seeds);
+	for (VMACH::Polygon3D& voro : r.Cells)
+	{
+		voro.Scale(Vector3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]));
+		voro.Translate(r.BBCenter);
+	}
+	// 10. initial pieces
+	Compound pre;
+	Piece ach_piece(r.ACH, r.ACH);
+	pre.PieceVec.push_back(&ach_piece);
+	r.Initial = ApplyFracture(pre, r.Cells);
+	return r;
+}
 
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec)
 {

@@ -75,6 +75,21 @@ std::vector<Vector3> GenerateRadialSeeds(int seed, int cellCount, double mean);
 // Surtr::GenerateVoronoi(points): DT3D-derived cells (voro++ is not vendored).
 std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPointVec);
 
+// Surtr::PrepareFracture, convex branch (Surtr.cpp:1747-1827 steps 1-6, 8, 10): ICH normals -> bounding box -> k-DOP
+// with gap -> ACH (2x bbox clipped by the k-DOP) -> Voronoi cells of `seeds` scaled by the bbox extent and translated
+// to its centre -> ApplyFracture on the single ACH piece.  The mesh polyhedron (step 7) and the pattern caches (step 9)
+// belong to the "next" rows.
+struct PreparedObject
+{
+	Vector3 BBCenter, MinBB, MaxBB;
+	float MaxAxisScale = 0.f;
+	int ICHFaceCnt = 0;
+	Poly::Polyhedron ACH;
+	std::vector<VMACH::Polygon3D> Cells;
+	CompoundInfo Initial;
+};
+PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<Vector3>& seeds, const FractureArgs& args = FractureArgs());
+
 // Surtr::ApplyFracture, non-partial convex branch.  Throws std::runtime_error on a C-ABI failure.
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec);
 // Surtr::SetExtract (Surtr.cpp:2151-2155).

@@ -253,6 +253,32 @@ int hosttest_apply_fracture(const float* verts, const uint32_t* vert_off, const 
 	catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// SurtrHost::PrepareFracture (config 1, convex branch): exports the fragments; ach_out gets {nv, nf-unused}
+int hosttest_config1(const float* verts4, uint32_t nv, const float* seeds, uint32_t n_seeds, uint32_t* ach_nv)
+{
+	try
+	{
+		std::vector<Vector3> vv, ss;
+		for (uint32_t i = 0; i < nv; i++) vv.emplace_back(verts4[4 * i], verts4[4 * i + 1], verts4[4 * i + 2]);
+		for (uint32_t i = 0; i < n_seeds; i++) ss.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+		SurtrHost::PreparedObject r = SurtrHost::PrepareFracture(vv, ss);
+		*ach_nv = (uint32_t)r.ACH.size();
+		g_out = Out();
+		for (size_t i = 0; i < r.Initial.PieceVec.size(); i++)
+		{
+			g_out.add(r.Initial.PieceVec[i]->Convex);
+			g_out.cell.push_back((uint32_t)r.Initial.PieceSourceCell[i]);
+			g_out.piece.push_back((uint32_t)r.Initial.PieceSourcePiece[i]);
+			g_out.nfaces.push_back((uint32_t)r.Initial.PieceMass[i].FaceCount);
+			g_out.volume.push_back(r.Initial.PieceMass[i].Volume);
+			g_out.centroid.insert(g_out.centroid.end(), { r.Initial.PieceMass[i].Centroid.x, r.Initial.PieceMass[i].Centroid.y, r.Initial.PieceMass[i].Centroid.z });
+			delete r.Initial.PieceVec[i];
+		}
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
 // Poly::ClipPolyhedron (in place) + Poly::Moments + Kdop::KdopContainer through the class API
 int hosttest_clip_and_moments(const float* verts, const uint32_t* ring_off, const uint16_t* ring, uint32_t nv, const float* planes, uint32_t npl,
 							  double* volume, float* centroid)

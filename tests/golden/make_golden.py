@@ -198,10 +198,26 @@ def refit_fixture():
     print("refit: out verts", out.nverts[:10], "empty", int((out.nverts == 0).sum()))
 
 
+def config1_fixture():
+    """BASELINE config 1, convex branch: bundled bunny (scale 70), 32 seeds mt19937(46354), one ApplyFracture on the
+    ACH piece (see ref_config1_convex in oracle/ref_driver.cpp).  Neighbour lists = the product's host DT3D."""
+    import hostapi
+    d0 = np.load(os.path.join(HERE, "config1_kdop.npz"))
+    s = R.seeds_uniform(46354, 32)
+    off, idx = hostapi.dt3d_neighbors(s)
+    ach, fr = R.config1_convex(d0["bunny_verts"], s, off, idx)
+    d = {"verts": d0["bunny_verts"], "seeds": s, "nb_off": off, "nb_idx": idx}
+    save_polyset(d, "ach_", ach)
+    save_polyset(d, "frag_", fr)
+    np.savez_compressed(os.path.join(HERE, "config1_bunny32.npz"), **d)
+    print("config1: ACH", ach.nverts, ach.nfaces, "fragments", fr.n, "sum vol", fr.volume.sum())
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     scalar_kats()
     small_events()
     config1_kdop()
     refit_fixture()
+    config1_fixture()
     summaries()

@@ -155,3 +155,15 @@ def refit(convex: PolySet, mesh_verts4, mesh_vert_off, limit=4) -> PolySet:
     if rc:
         raise RuntimeError(_err())
     return export()
+
+
+def config1(verts4, seeds) -> PolySet:
+    verts4, seeds = np.ascontiguousarray(verts4, np.float32), np.ascontiguousarray(seeds, np.float32)
+    L = lib()
+    L.hosttest_config1.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    ach_nv = C.c_uint32(0)
+    if L.hosttest_config1(_p(verts4), len(verts4), _p(seeds), len(seeds), C.byref(ach_nv)):
+        raise RuntimeError(_err())
+    ps = export()
+    ps.ach_nv = ach_nv.value
+    return ps

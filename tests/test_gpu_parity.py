@@ -235,3 +235,31 @@ def test_product_voronoi_builder_matches_oracle(ctx):
     want = P.voronoi_cells(s, off, idx)
     assert np.array_equal(bits(got.verts), bits(want.verts)) and np.array_equal(got.ring, want.ring)
     assert np.array_equal(got.plane_off, want.plane_off) and np.array_equal(bits(got.planes), bits(want.planes))
+
+
+def test_malformed_and_oversize_inputs_fail_loudly(ctx):
+    """Invalid rings / pieces beyond the largest tier are reported (SURTR_ERR_OVERFLOW), never read out of bounds."""
+    from surtr_b200 import SurtrError
+    cube = common.unit_cube()
+    cells = common.voronoi(46354, 8)
+    bad = cube.subset([0])
+    bad.ring = cube.ring.copy()
+    bad.ring[5] = 200                      # neighbour index beyond the piece's vertex count
+    ctx.upload_pieces(bad.verts, bad.vert_off, bad.ring_off, bad.ring)
+    ctx.upload_cells(cells.planes, cells.plane_off, cells.verts, cells.vert_off)
+    ctx.fracture_event()
+    with pytest.raises(SurtrError) as e:
+        ctx.counts()
+    assert e.value.code == 4
+    # a 300-vertex "piece" (beyond 256 slots): same error, no crash; the context stays usable afterwards
+    n = 300
+    verts = np.zeros((n, 4), np.float32)
+    verts[:, :3] = np.random.RandomState(0).uniform(-0.4, 0.4, (n, 3))
+    ring = np.stack([(np.arange(n) + 1) % n, (np.arange(n) + 2) % n, (np.arange(n) + n - 1) % n], 1).astype(np.uint16).reshape(-1)
+    ctx.upload_pieces(verts, np.array([0, n], np.uint32), np.arange(0, 3 * n + 1, 3, dtype=np.uint32), ring)
+    ctx.fracture_event()
+    with pytest.raises(SurtrError):
+        ctx.counts()
+    got = common.run_gpu(ctx, cube, cells)
+    want = P.apply_fracture(cube, cells.planes, cells.plane_off)
+    common.assert_fragments_equal(got, want)

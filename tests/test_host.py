@@ -125,3 +125,16 @@ def test_kdop_calc_batch_matches_oracle(ctx):
         d, a, p = P.kdop_calc(r["mesh_verts"][off[i]:off[i + 1]], r["ich_normals"][noff[i]:noff[i + 1]])
         sl = slice(noff[i], noff[i + 1])
         assert np.array_equal(bits(dist[sl]), bits(d)) and np.array_equal(arg[sl], a) and np.array_equal(bits(planes[sl]), bits(p))
+
+
+@pytest.mark.gpu
+def test_config1_bunny_convex_branch():
+    """BASELINE config 1 (bundled bunny, 32 seeds), convex branch of PrepareFracture through the host classes:
+    ICH -> k-DOP -> ACH -> DT3D cells scaled/translated onto the object -> ApplyFracture == the reference build."""
+    d = np.load(os.path.join(GOLDEN, "config1_bunny32.npz"))
+    got = H.config1(d["verts"], d["seeds"])
+    want = load_polyset(d, "frag_")
+    assert got.ach_nv == int(load_polyset(d, "ach_").nverts[0]) == 107
+    assert got.n == want.n == 28
+    for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece", "nfaces", "volume", "centroid"):
+        assert np.array_equal(bits(getattr(got, f)), bits(getattr(want, f))), f
