@@ -25,6 +25,8 @@
 
 #include <chrono>
 #include <future>
+#include <set>
+#include <unordered_map>
 
 using DirectX::SimpleMath::Plane;
 using DirectX::SimpleMath::Vector3;
@@ -399,6 +401,88 @@ void ref_apply_fracture(const float* verts, const uint32_t* vert_off, const uint
 			append(o, results[c][k].second, c, results[c][k].first, with_moments != 0, extracts[c][k], false);
 }
 
+// Restatement of Surtr::_MeshIslandLoop / CheckMeshIsland (Surtr.cpp:2157-2199): connected components of the ring
+// graph, each a sorted set, discovered from the lowest vertex not yet in a group.  (The reference recurses; an explicit
+// stack visits the same sets.)
+static std::vector<std::set<int>> check_mesh_island(const Poly::Polyhedron& polyhedron)
+{
+	std::vector<std::set<int>> groupVec;
+	std::vector<char> seen(polyhedron.size(), 0);
+	int start = 0;
+	while (true)
+	{
+		std::set<int> group;
+		std::vector<int> stack{ start };
+		while (!stack.empty())
+		{
+			const int v = stack.back();
+			stack.pop_back();
+			for (const int a : polyhedron[v].NeighborVertexVec)
+				if (group.insert(a).second)
+					stack.push_back(a);
+		}
+		groupVec.push_back(group);
+		for (const int v : group)
+			seen[v] = 1;
+		bool remain = false;
+		for (int v = 0; v < (int)polyhedron.size(); v++)
+			if (!seen[v]) { remain = true; start = v; break; }
+		if (!remain)
+			break;
+	}
+	return groupVec;
+}
+
+// Restatement of the full m_fractureTask (Surtr.cpp:1457-1504), convex AND mesh branch, cells in order (inline, one
+// thread): out_convex / out_mesh receive the Piece::Convex / Piece::Mesh of every resulting piece, in PieceVec order.
+void ref_apply_fracture_mesh(const float* cverts, const uint32_t* cvert_off, const uint32_t* cring_off, const uint16_t* cring,
+							 const float* mverts, const uint32_t* mvert_off, const uint32_t* mring_off, const uint16_t* mring,
+							 uint32_t n_pieces, const float* planes, const uint32_t* plane_off, uint32_t n_cells,
+							 void* out_convex, void* out_mesh)
+{
+	PolySet& oc = *(PolySet*)out_convex;
+	PolySet& om = *(PolySet*)out_mesh;
+	const auto t0 = std::chrono::steady_clock::now();
+	for (uint32_t c = 0; c < n_cells; c++)
+	{
+		const VMACH::Polygon3D voroPoly = planes_to_polygon(planes, plane_off[c], plane_off[c + 1]);
+		for (uint32_t i = 0; i < n_pieces; i++)
+		{
+			const Poly::Polyhedron convex = Poly::ClipPolyhedron(to_poly(cverts, cvert_off, cring_off, cring, i), voroPoly);
+			if (convex.empty())
+				continue;
+			const Poly::Polyhedron mesh = Poly::ClipPolyhedron(to_poly(mverts, mvert_off, mring_off, mring, i), voroPoly);
+			if (mesh.empty())
+				continue;
+			const auto groupVec = check_mesh_island(mesh);
+			if (groupVec.size() >= 2)
+			{
+				for (const auto& group : groupVec)
+				{
+					Poly::Polyhedron island;
+					std::unordered_map<int, int> mapping;
+					for (const int iVert : group)
+					{
+						mapping[iVert] = (int)island.size();
+						island.push_back(mesh[iVert]);
+					}
+					for (auto& vert : island)
+						for (int& iAdj : vert.NeighborVertexVec)
+							iAdj = mapping[iAdj];
+					append(oc, convex, c, i);
+					append(om, island, c, i);
+				}
+			}
+			else
+			{
+				append(oc, convex, c, i);
+				append(om, mesh, c, i);
+			}
+		}
+	}
+	oc.seconds = om.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // Kdop::KdopContainer::Calc(const Poly::Polyhedron&) (Kdop.cpp:92-115) on raw vertices:
 // out_dist[2k] = {MinDist, MaxDist}, out_planes[8k] = {MinPlane, MaxPlane}, out_vtx[6k] = {MinVertex, MaxVertex}.
 void ref_kdop_calc_poly(const float* verts, uint32_t nv, const float* normals, uint32_t k, double* out_dist,
@@ -506,8 +590,8 @@ void ref_refit(const float* cverts, const uint32_t* cvert_off, const uint32_t* c
 // cloud: ICH normals (limit) -> bbox -> k-DOP with gap -> ACH = 2x bbox clipped -> Voronoi cells of `seeds`
 // (unit box) scaled by the bbox extent and translated to its centre (Polygon3D::Scale/Translate re-derive every
 // plane, VMACH.cpp:506-534) -> ApplyFracture on the single ACH piece.  out_ach gets the ACH, out the fragments.
-void ref_config1_convex(const float* verts4, uint32_t nv, int ich_limit, float gap_inv, const float* seeds, uint32_t n_seeds,
-						const uint32_t* nb_off, const uint32_t* nb_idx, void* out_ach, void* out)
+static void config1(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx, int ich_limit, float gap_inv, int refit_limit,
+					const float* seeds, uint32_t n_seeds, const uint32_t* nb_off, const uint32_t* nb_idx, void* out_ach, void* out, void* out_mesh)
 {
 	std::vector<Vector3> vertices;
 	for (uint32_t v = 0; v < nv; v++)
@@ -569,15 +653,104 @@ void ref_config1_convex(const float* verts4, uint32_t nv, int ich_limit, float g
 		voro.Scale(Vector3((maxX - minX), (maxY - minY), (maxZ - minZ)));
 		voro.Translate(BBCenter);
 	}
-	// ApplyFracture, convex branch, single piece
 	PolySet& o = *(PolySet*)out;
-	for (uint32_t c = 0; c < n_seeds; c++)
+	if (!indices)
 	{
-		Poly::Polyhedron convex = Poly::ClipPolyhedron(ach, voroPolyVec[c]);
-		if (convex.empty())
-			continue;
-		append(o, convex, c, 0);
+		// ApplyFracture, convex branch, single piece
+		for (uint32_t c = 0; c < n_seeds; c++)
+		{
+			Poly::Polyhedron convex = Poly::ClipPolyhedron(ach, voroPolyVec[c]);
+			if (convex.empty())
+				continue;
+			append(o, convex, c, 0);
+		}
+		return;
 	}
+	// step 7 (Surtr.cpp:1788-1795) + step 10: full m_fractureTask on the (ACH, mesh) piece, then Refitting (:1813)
+	Poly::Polyhedron meshPolyhedron;
+	{
+		std::vector<int> idx(indices, indices + n_idx);
+		const std::vector<std::vector<int>> nei = Poly::ExtractNeighborFromMesh(vertices, idx);
+		Poly::InitPolyhedron(meshPolyhedron, vertices, nei);
+	}
+	PolySet pre_convex, pre_mesh;
+	{
+		PolySet a, m;
+		append(a, ach, 0, 0);
+		append(m, meshPolyhedron, 0, 0);
+		std::vector<float> planes;
+		std::vector<uint32_t> plane_off{ 0 };
+		for (const VMACH::Polygon3D& voro : voroPolyVec)
+		{
+			for (const VMACH::PolygonFace& f : voro.FaceVec)
+				planes.insert(planes.end(), { f.FacePlane.x, f.FacePlane.y, f.FacePlane.z, f.FacePlane.w });
+			plane_off.push_back((uint32_t)(planes.size() / 4));
+		}
+		ref_apply_fracture_mesh(a.verts.data(), a.vert_off.data(), a.ring_off.data(), a.ring.data(),
+								m.verts.data(), m.vert_off.data(), m.ring_off.data(), m.ring.data(), 1,
+								planes.data(), plane_off.data(), n_seeds, &pre_convex, &pre_mesh);
+	}
+	PolySet& om = *(PolySet*)out_mesh;
+	const uint32_t n = (uint32_t)pre_convex.vert_off.size() - 1;
+	for (uint32_t i = 0; i < n; i++)
+	{
+		Poly::Polyhedron convex = to_poly(pre_convex.verts.data(), pre_convex.vert_off.data(), pre_convex.ring_off.data(), pre_convex.ring.data(), i);
+		const Poly::Polyhedron mesh = to_poly(pre_mesh.verts.data(), pre_mesh.vert_off.data(), pre_mesh.ring_off.data(), pre_mesh.ring.data(), i);
+		// m_refittingTask (Surtr.cpp:1449-1455)
+		std::vector<Vector3> pts;
+		for (const Poly::Vertex& v : mesh)
+			pts.push_back(v.Position);
+		VMACH::ConvexHull ich(pts, (uint32_t)std::min((int)pts.size(), refit_limit));
+		std::vector<Vector3> nrm;
+		for (const VMACH::ConvexHullFace& f : ich.GetFaces())
+		{
+			Vector3 normal = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+			normal.Normalize();
+			nrm.push_back(normal);
+		}
+		Kdop::KdopContainer kdop(nrm);
+		kdop.Calc(mesh);
+		convex = kdop.ClipWithPolyhedron(convex);
+		append(o, convex, pre_convex.cell[i], pre_convex.piece[i]);
+		append(om, mesh, pre_mesh.cell[i], pre_mesh.piece[i]);
+	}
+}
+
+void ref_config1_convex(const float* verts4, uint32_t nv, int ich_limit, float gap_inv, const float* seeds, uint32_t n_seeds,
+						const uint32_t* nb_off, const uint32_t* nb_idx, void* out_ach, void* out)
+{
+	config1(verts4, nv, nullptr, 0, ich_limit, gap_inv, 0, seeds, n_seeds, nb_off, nb_idx, out_ach, out, nullptr);
+}
+
+// Surtr::PrepareFracture in full (Surtr.cpp:1747-1827): as above plus the mesh polyhedron, the mesh branch of the
+// fracture task with its island split, and Refitting.  out = Piece::Convex after the refit, out_mesh = Piece::Mesh.
+void ref_config1_full(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx, int ich_limit, float gap_inv, int refit_limit,
+					  const float* seeds, uint32_t n_seeds, const uint32_t* nb_off, const uint32_t* nb_idx, void* out_ach, void* out, void* out_mesh)
+{
+	config1(verts4, nv, indices, n_idx, ich_limit, gap_inv, refit_limit, seeds, n_seeds, nb_off, nb_idx, out_ach, out, out_mesh);
+}
+
+// Triangle mesh -> vertex-ring polyhedron, as PrepareFracture step 7 does (Surtr.cpp:1788-1795):
+// Poly::ExtractNeighborFromMesh (Poly.cpp:128-263) + InitPolyhedron.  Returns 0, or 1 if the reference throws
+// (asymmetric adjacency, Poly.cpp:253-260).
+int ref_mesh_polyhedron(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx, void* out)
+{
+	std::vector<Vector3> vertices;
+	for (uint32_t v = 0; v < nv; v++)
+		vertices.emplace_back(verts4[4 * v], verts4[4 * v + 1], verts4[4 * v + 2]);
+	std::vector<int> idx(indices, indices + n_idx);
+	try
+	{
+		const std::vector<std::vector<int>> nei = Poly::ExtractNeighborFromMesh(vertices, idx);
+		Poly::Polyhedron mesh;
+		Poly::InitPolyhedron(mesh, vertices, nei);
+		append(*(PolySet*)out, mesh, 0, 0);
+	}
+	catch (const std::exception&)
+	{
+		return 1;
+	}
+	return 0;
 }
 
 // Scalar helpers for the unit KATs (Poly.cpp:716-751).

@@ -41,6 +41,10 @@ def lib():
         _lib.ref_apply_fracture.argtypes = ([C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                                                  C.c_uint32, C.c_int, C.c_void_p])
         _lib.ref_refit.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.ref_apply_fracture_mesh.argtypes = [C.c_void_p] * 8 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.ref_mesh_polyhedron.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib.ref_config1_full.argtypes = ([C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_void_p,
+                                           C.c_uint32] + [C.c_void_p] * 5)
         _lib.ref_seeds_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.ref_seeds_radial.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_void_p]
         _lib.ref_unit_cube.argtypes = [C.c_void_p]
@@ -275,3 +279,42 @@ def config1_convex(verts4, seeds, nb_off, nb_idx, ich_limit=20, gap_inv=2000.0):
     h1, h2 = L.ref_polyset_new(), L.ref_polyset_new()
     L.ref_config1_convex(_p(verts4), len(verts4), ich_limit, gap_inv, _p(seeds), len(seeds), _p(nb_off), _p(nb_idx), h1, h2)
     return _export(h1), _export(h2)
+
+
+def mesh_polyhedron(verts4, indices) -> PolySet:
+    """Poly::ExtractNeighborFromMesh + InitPolyhedron (Surtr.cpp:1788-1795) on a triangle mesh."""
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32).reshape(-1)
+    L = lib()
+    h = L.ref_polyset_new()
+    if L.ref_mesh_polyhedron(_p(verts4), len(verts4), _p(indices), len(indices), h):
+        L.ref_polyset_free(h)
+        raise RuntimeError("ExtractNeighborFromMesh: asymmetric adjacency")
+    return _export(h)
+
+
+def apply_fracture_mesh(convex: PolySet, mesh: PolySet, planes, plane_off):
+    """Full m_fractureTask (Surtr.cpp:1457-1504) per cell: convex clip, mesh clip, island split.
+    Returns (Piece::Convex set, Piece::Mesh set), both in PieceVec order."""
+    assert convex.n == mesh.n
+    planes = np.ascontiguousarray(planes, np.float32)
+    plane_off = np.ascontiguousarray(plane_off, np.uint32)
+    L = lib()
+    hc, hm = L.ref_polyset_new(), L.ref_polyset_new()
+    L.ref_apply_fracture_mesh(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring),
+                              _p(mesh.verts), _p(mesh.vert_off), _p(mesh.ring_off), _p(mesh.ring), convex.n,
+                              _p(planes), _p(plane_off), len(plane_off) - 1, hc, hm)
+    return _export(hc), _export(hm)
+
+
+def config1_full(verts4, indices, seeds, nb_off, nb_idx, ich_limit=20, gap_inv=2000.0, refit_limit=4):
+    """Surtr::PrepareFracture in full (Surtr.cpp:1747-1827).  Returns (ACH, Piece::Convex set after Refitting,
+    Piece::Mesh set)."""
+    verts4, seeds = np.ascontiguousarray(verts4, np.float32), np.ascontiguousarray(seeds, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32).reshape(-1)
+    nb_off, nb_idx = np.ascontiguousarray(nb_off, np.uint32), np.ascontiguousarray(nb_idx, np.uint32)
+    L = lib()
+    ha, hc, hm = L.ref_polyset_new(), L.ref_polyset_new(), L.ref_polyset_new()
+    L.ref_config1_full(_p(verts4), len(verts4), _p(indices), len(indices), ich_limit, gap_inv, refit_limit, _p(seeds), len(seeds),
+                       _p(nb_off), _p(nb_idx), ha, hc, hm)
+    return _export(ha), _export(hc), _export(hm)

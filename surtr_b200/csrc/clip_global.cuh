@@ -1,0 +1,477 @@
+// clip_global.cuh -- the unbounded tier of K3: one warp per pair, polyhedron in a global-memory workspace.
+//
+// Same algorithm and exactness argument as clip_warp.cuh (see there and DESIGN.md section 5), written with strided
+// loops instead of per-lane register arrays so that the vertex count is bounded only by the workspace: this is the
+// path of non-convex piece MESHES (2.5K-5K vertices, ring degree up to 13; m_fractureTask's second clip,
+// Surtr.cpp:1470) and of any convex piece beyond 256 vertices.  The workspace of a warp (117 bytes per vertex slot)
+// stays L2-resident; throughput is not the point of this tier, never failing is.
+#pragma once
+
+#include "clip_warp.cuh"
+
+namespace surtr
+{
+constexpr int GD = 16;                  // ring slots per vertex in this tier
+constexpr uint16_t G_NONE = 0xffffu;    // the reference's "-1" ring mark
+
+struct GlobalPoly   // views into one warp's workspace
+{
+    float *x, *y, *z;
+    uint16_t *ring, *old_ring;   // GD per vertex
+    uint8_t *deg, *old_deg;
+    int8_t* comp;
+    uint16_t* id;                // renumbering / walk-target probe / face-start masks
+    uint32_t* list;              // straddling half-edges (v | slot << 16), then walk targets; triangle bases
+    float4* tri;                 // 2 per vertex slot: ordered fan-triangle records
+    int cap;
+};
+
+__host__ __device__ constexpr size_t global_poly_bytes(size_t cap)
+{
+    return cap * (3 * 4 + 2 * GD * 2 + 3 + 2 + 4 + 2 * 16) + 256;
+}
+
+__device__ inline GlobalPoly global_poly_carve(unsigned char* base, int cap)
+{
+    GlobalPoly g;
+    g.cap = cap;
+    unsigned char* p = base;
+    g.tri = reinterpret_cast<float4*>(p); p += (size_t)cap * 32;
+    g.x = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
+    g.y = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
+    g.z = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
+    g.list = reinterpret_cast<uint32_t*>(p); p += (size_t)cap * 4;
+    g.ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * GD * 2;
+    g.old_ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * GD * 2;
+    g.id = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * 2;
+    g.deg = p; p += cap;
+    g.old_deg = p; p += cap;
+    g.comp = reinterpret_cast<int8_t*>(p);
+    return g;
+}
+
+// FaceLoop (Src/Poly.cpp:34-41)
+__device__ __forceinline__ int g_face_loop(const GlobalPoly& g, int v, int vprev)
+{
+    const uint16_t* r = g.ring + (size_t)v * GD;
+    const int d = g.deg[v];
+    if (d == 0) return vprev;
+    int k = 0;
+    while (k < d && r[k] != (uint16_t)vprev) k++;
+    return k == 0 ? r[d - 1] : r[k - 1];
+}
+
+// Sequential replay of Poly.cpp:365-462 by lane 0 (patch, erase marks, splice).  false = ring overflow.
+__device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int nverts)
+{
+    for (int ii = 0; ii < nverts; ii++)
+    {
+        const int i = (ii + nverts0) % nverts;
+        const int ci = g.comp[i];
+        if (!(ci == 0 || ci == 2)) continue;
+        const int nneigh = g.deg[i];
+        for (int j = 0; j < nneigh; j++)
+        {
+            const uint16_t jn = g.ring[(size_t)i * GD + j];
+            if (jn == G_NONE || g.comp[jn] != -1) continue;
+            int iprev = i, inext = jn, itmp, k = 0;
+            while (g.comp[inext] == -1 && k++ < nverts)
+            {
+                itmp = inext;
+                inext = g_face_loop(g, inext, iprev);
+                iprev = itmp;
+            }
+            if (g.ring[(size_t)i * GD + (j + 1) % g.deg[i]] == (uint16_t)inext || inext == i)
+            {
+                g.ring[(size_t)i * GD + j] = G_NONE;
+            }
+            else
+            {
+                g.ring[(size_t)i * GD + j] = (uint16_t)inext;
+                const int dn = g.deg[inext], od = g.old_deg[inext];
+                if (dn >= GD || od >= GD) return false;
+                uint16_t* rn = g.ring + (size_t)inext * GD;
+                uint16_t* on = g.old_ring + (size_t)inext * GD;
+                int off = 0;
+                uint16_t mark = (uint16_t)i;
+                if (g.comp[inext] == 2) mark = G_NONE;   // Poly.cpp:409 inserts -1 into the snapshot
+                else while (off < od && on[off] != (uint16_t)iprev) off++;
+                for (int q = dn; q > off; q--) rn[q] = rn[q - 1];
+                rn[off] = (uint16_t)i;
+                g.deg[inext] = (uint8_t)(dn + 1);
+                for (int q = od; q > off; q--) on[q] = on[q - 1];
+                on[off] = mark;
+                g.old_deg[inext] = (uint8_t)(od + 1);
+            }
+        }
+    }
+    for (int i = 0; i < nverts; i++)   // Poly.cpp:426-431
+    {
+        uint16_t* r = g.ring + (size_t)i * GD;
+        int w = 0;
+        const int d = g.deg[i];
+        for (int k = 0; k < d; k++)
+            if (r[k] != G_NONE) r[w++] = r[k];
+        g.deg[i] = (uint8_t)w;
+    }
+    bool updated = true;   // Poly.cpp:433-462
+    while (updated)
+    {
+        updated = false;
+        for (int i = 0; i < nverts; i++)
+        {
+            if (g.comp[i] >= 0 && g.deg[i] == 2)
+            {
+                updated = true;
+                const int iprev = g.ring[(size_t)i * GD], inext = g.ring[(size_t)i * GD + 1];
+                int k = 0;
+                while (k < g.deg[iprev] && g.ring[(size_t)iprev * GD + k] != (uint16_t)i) ++k;
+                if (k < g.deg[iprev]) g.ring[(size_t)iprev * GD + k] = (uint16_t)inext;
+                k = 0;
+                while (k < g.deg[inext] && g.ring[(size_t)inext * GD + k] != (uint16_t)i) ++k;
+                if (k < g.deg[inext]) g.ring[(size_t)inext * GD + k] = (uint16_t)iprev;
+                g.comp[i] = -1;
+            }
+        }
+    }
+    return true;
+}
+
+__device__ bool g_all_inplane_box_says_skip(const GlobalPoly& g, int nv, const float4& pl, int lane)
+{
+    float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
+    float hi[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
+    for (int v = lane; v < nv; v += 32)
+    {
+        lo[0] = fminf(lo[0], g.x[v]); hi[0] = fmaxf(hi[0], g.x[v]);
+        lo[1] = fminf(lo[1], g.y[v]); hi[1] = fmaxf(hi[1], g.y[v]);
+        lo[2] = fminf(lo[2], g.z[v]); hi[2] = fmaxf(hi[2], g.z[v]);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++)
+        {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+    const int k = lane & 7;
+    const int c = classify(signed_dist(pl, (k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]));
+    return __ballot_sync(FULL, c == -1) == 0u;
+}
+
+// Clip the polyhedron in the workspace (nv vertices) by planes[0..npl).  All 32 lanes call this together.
+__device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    for (int kb = 0; kb < npl && nv > 0; kb += 32)
+    {
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kb + lane < npl) mine = __ldg(planes + kb + lane);
+        const int kend = min(32, npl - kb);
+        for (int kk = 0; kk < kend && nv > 0; kk++)
+        {
+            float4 pl;
+            pl.x = __shfl_sync(FULL, mine.x, kk);
+            pl.y = __shfl_sync(FULL, mine.y, kk);
+            pl.z = __shfl_sync(FULL, mine.z, kk);
+            pl.w = __shfl_sync(FULL, mine.w, kk);
+
+            // classify (Poly.cpp:303-319)
+            bool any_clip = false, any_keep = false, any_zero = false;
+            for (int base = 0; base < nv; base += 32)
+            {
+                const int v = base + lane;
+                int c = 3;
+                if (v < nv)
+                {
+                    c = classify(signed_dist(pl, g.x[v], g.y[v], g.z[v]));
+                    g.comp[v] = (int8_t)c;
+                }
+                any_clip |= __ballot_sync(FULL, c == -1) != 0u;
+                any_keep |= __ballot_sync(FULL, c == 1) != 0u;
+                any_zero |= __ballot_sync(FULL, c == 0) != 0u;
+            }
+            if (!any_keep)
+            {
+                if (!any_clip && g_all_inplane_box_says_skip(g, nv, pl, lane)) continue;
+                nv = 0;
+                break;
+            }
+            if (!any_clip) continue;
+            __syncwarp();
+
+            // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
+            const int nverts0 = nv;
+            int nnew = 0;
+            for (int base = 0; base < nverts0; base += 32)
+            {
+                const int v = base + lane;
+                int cnt = 0;
+                unsigned smask = 0u;
+                if (v < nverts0 && g.comp[v] == -1)
+                {
+                    const int d = g.deg[v];
+                    for (int j = 0; j < d; j++)
+                        if (g.comp[g.ring[(size_t)v * GD + j]] > 0) { cnt++; smask |= 1u << j; }
+                }
+                int tot;
+                int w = nnew + warp_exscan(cnt, lane, tot);
+                if (nverts0 + nnew + tot > g.cap) return CLIP_OVERFLOW;
+                while (smask) { const int j = __ffs(smask) - 1; smask &= smask - 1; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
+                nnew += tot;
+            }
+            const int nverts = nverts0 + nnew;
+            __syncwarp();
+            // insert (Poly.cpp:345-354): one new vertex per lane and iteration
+            for (int t = lane; t < nnew; t += 32)
+            {
+                const uint32_t e = g.list[t];
+                const int v = (int)(e & 0xffffu), j = (int)(e >> 16), w = nverts0 + t;
+                const int jn = g.ring[(size_t)v * GD + j];
+                const float ax = g.x[v], ay = g.y[v], az = g.z[v], bx = g.x[jn], by = g.y[jn], bz = g.z[jn];
+                const float sa = signed_dist(pl, ax, ay, az), sb = signed_dist(pl, bx, by, bz);
+                float ox, oy, oz;
+                plane_line_intersection(ax, ay, az, sa, bx, by, bz, sb, ox, oy, oz);
+                g.x[w] = ox; g.y[w] = oy; g.z[w] = oz;
+                g.comp[w] = 2;
+                g.deg[w] = 2;
+                g.ring[(size_t)w * GD] = (uint16_t)v;
+                g.ring[(size_t)w * GD + 1] = (uint16_t)jn;
+                uint16_t* rj = g.ring + (size_t)jn * GD;
+                const int dj = g.deg[jn];
+                int k = 0;
+                while (k < dj && rj[k] != (uint16_t)v) k++;
+                if (k < dj) rj[k] = (uint16_t)w;
+                g.ring[(size_t)v * GD + j] = (uint16_t)w;
+            }
+            __syncwarp();
+
+            // patch (Poly.cpp:365-431)
+            bool need_seq = any_zero;
+            if (!need_seq)
+            {
+                bool ok = true;
+                for (int t = lane; t < nnew; t += 32)
+                {
+                    const int w = nverts0 + t;
+                    int iprev = w, inext = g.ring[(size_t)w * GD], itmp, k = 0;
+                    while (g.comp[inext] == -1 && k++ < nverts)
+                    {
+                        itmp = inext;
+                        inext = g_face_loop(g, inext, iprev);
+                        iprev = itmp;
+                    }
+                    const bool okt = g.comp[inext] == 2 && inext != w;
+                    if (okt) g.id[inext] = (uint16_t)w;
+                    g.list[t] = (uint32_t)inext;
+                    ok = ok && okt;
+                }
+                __syncwarp();
+                for (int t = lane; t < nnew; t += 32)
+                    if (ok) ok = g.id[g.list[t]] == (uint16_t)(nverts0 + t);
+                need_seq = __ballot_sync(FULL, !ok) != 0u;
+                if (!need_seq)
+                {
+                    for (int t = lane; t < nnew; t += 32)   // ring(w) = [pusher, walked, kept]
+                    {
+                        const int w = nverts0 + t;
+                        const uint16_t kept = g.ring[(size_t)w * GD + 1];
+                        g.ring[(size_t)w * GD] = g.id[w];
+                        g.ring[(size_t)w * GD + 1] = (uint16_t)g.list[t];
+                        g.ring[(size_t)w * GD + 2] = kept;
+                        g.deg[w] = 3;
+                    }
+                }
+            }
+            if (need_seq)
+            {
+                seq_cuts++;
+                for (int v = lane; v < nverts; v += 32)
+                {
+                    const int d = g.deg[v];
+                    g.old_deg[v] = (uint8_t)d;
+                    for (int j = 0; j < d; j++) g.old_ring[(size_t)v * GD + j] = g.ring[(size_t)v * GD + j];
+                }
+                __syncwarp();
+                int okflag = 1;
+                if (lane == 0) okflag = g_seq_patch_splice(g, nverts0, nverts) ? 1 : 0;
+                okflag = __shfl_sync(FULL, okflag, 0);
+                if (!okflag) return CLIP_OVERFLOW;
+            }
+            __syncwarp();
+
+            // compaction (Poly.cpp:464-499)
+            int kept_before = 0;
+            for (int base = 0; base < nverts; base += 32)
+            {
+                const int v = base + lane;
+                const bool live = v < nverts && g.comp[v] >= 0;
+                const unsigned m = __ballot_sync(FULL, live);
+                if (v < nverts) g.id[v] = live ? (uint16_t)(kept_before + __popc(m & lt)) : G_NONE;
+                kept_before += __popc(m);
+            }
+            __syncwarp();
+            bool dangling = false;   // a live ring pointing at an erased vertex: not a polyhedron (the reference would store -1)
+            for (int base = 0; base < nverts; base += 32)
+            {
+                const int v = base + lane;
+                const bool live = v < nverts && g.comp[v] >= 0;
+                float vx = 0.f, vy = 0.f, vz = 0.f;
+                uint16_t r[GD];
+                int d = 0, t = 0;
+                if (live)
+                {
+                    vx = g.x[v]; vy = g.y[v]; vz = g.z[v];
+                    d = g.deg[v];
+                    t = g.id[v];
+#pragma unroll
+                    for (int j = 0; j < GD; j++)
+                        if (j < d)
+                        {
+                            r[j] = g.id[g.ring[(size_t)v * GD + j]];
+                            dangling |= r[j] == G_NONE;
+                        }
+                }
+                __syncwarp();
+                if (live)
+                {
+                    g.x[t] = vx; g.y[t] = vy; g.z[t] = vz;
+                    g.deg[t] = (uint8_t)d;
+#pragma unroll
+                    for (int j = 0; j < GD; j++)
+                        if (j < d) g.ring[(size_t)t * GD + j] = r[j];
+                }
+                __syncwarp();
+            }
+            if (__ballot_sync(FULL, dangling) != 0u) return CLIP_OVERFLOW;   // keeps every later index inside the workspace
+            nv = kept_before < 4 ? 0 : kept_before;   // Poly.cpp:498-499
+        }
+    }
+    __syncwarp();
+    return CLIP_OK;
+}
+
+// Face count + moments in the reference's order (Poly.cpp:55-126) on the workspace; see fragment_moments.
+__device__ void global_fragment_moments(GlobalPoly& g, int nv, int lane, Moments& out)
+{
+    const float ox = g.x[0], oy = g.y[0], oz = g.z[0];
+    int n_faces = 0, n_tri = 0;
+    // pass 1: face starts (bit mask per vertex in g.id) and the first triangle slot of every vertex (g.list)
+    for (int base = 0; base < nv; base += 32)
+    {
+        const int v = base + lane;
+        int cnt = 0, faces = 0;
+        unsigned mask = 0u;
+        if (v < nv)
+        {
+            const int d = g.deg[v];
+            for (int j = 0; j < d; j++)
+            {
+                int at = g.ring[(size_t)v * GD + j];
+                if (at < v || (int)g.ring[(size_t)v * GD + (j + 1 == d ? 0 : j + 1)] < v) continue;
+                int prev = v, n = 1;
+                bool is_start = true;
+                while (at != v)
+                {
+                    if (at < v || n > nv) { is_start = false; break; }
+                    const int nxt = g_face_loop(g, at, prev);
+                    prev = at;
+                    at = nxt;
+                    n++;
+                }
+                if (is_start) { mask |= 1u << j; faces++; cnt += max(n - 2, 0); }
+            }
+            g.id[v] = (uint16_t)mask;
+        }
+        int tot, ftot;
+        const int ex = warp_exscan(cnt, lane, tot);
+        warp_exscan(faces, lane, ftot);
+        if (v < nv) g.list[v] = (uint32_t)(n_tri + ex);
+        n_tri += tot;
+        n_faces += ftot;
+    }
+    n_tri = min(n_tri, 2 * g.cap);
+    __syncwarp();
+    float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    for (int v = lane; v < nv; v += 32)
+    {
+        unsigned m = g.id[v];
+        if (!m) continue;
+        int w = (int)g.list[v];
+        const float p0x = __fsub_rn(g.x[v], ox), p0y = __fsub_rn(g.y[v], oy), p0z = __fsub_rn(g.z[v], oz);
+        while (m)
+        {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            int prev = v, at = g.ring[(size_t)v * GD + j];
+            float p1x = __fsub_rn(g.x[at], ox), p1y = __fsub_rn(g.y[at], oy), p1z = __fsub_rn(g.z[at], oz);
+            int nxt = g_face_loop(g, at, prev);
+            prev = at;
+            at = nxt;
+            while (at != v)
+            {
+                const float p2x = __fsub_rn(g.x[at], ox), p2y = __fsub_rn(g.y[at], oy), p2z = __fsub_rn(g.z[at], oz);
+                float cx, cy, cz;
+                cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
+                const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
+                const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
+                const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
+                const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
+                if (w < 2 * g.cap) g.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
+                w++;
+                cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
+                cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
+                cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
+                cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
+                cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
+                cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
+                cov[6] += dV;
+                cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
+                p1x = p2x; p1y = p2y; p1z = p2z;
+                nxt = g_face_loop(g, at, prev);
+                prev = at;
+                at = nxt;
+            }
+        }
+    }
+    __syncwarp();
+    double zeroth = 0.0;
+    float fsum = 0.f;
+    if (lane < 4)
+    {
+        const float* comp = reinterpret_cast<const float*>(g.tri) + lane;
+        for (int t = 0; t < n_tri; t++)
+        {
+            const float r = comp[4 * (size_t)t];
+            zeroth += (double)r;
+            fsum = __fadd_rn(fsum, r);
+        }
+    }
+    zeroth = __shfl_sync(FULL, zeroth, 0) / 6.0;
+    float fx = __shfl_sync(FULL, fsum, 1), fy = __shfl_sync(FULL, fsum, 2), fz = __shfl_sync(FULL, fsum, 3);
+    {
+        const double q = 24.0 * zeroth;
+        const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));
+        const float sc = (float)inv;
+        fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); fz = __fmul_rn(fz, sc);
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            cov[k] += __shfl_xor_sync(FULL, cov[k], o);
+    out.n_faces = n_faces;
+    out.volume = zeroth;
+    out.cx = __fadd_rn(fx, ox); out.cy = __fadd_rn(fy, oy); out.cz = __fadd_rn(fz, oz);
+    const float V = cov[6] * (1.f / 6.f);
+    const float iv = V != 0.f ? 1.f / (24.f * V) : 0.f;
+    const float c0 = cov[7] * iv, c1 = cov[8] * iv, c2 = cov[9] * iv;
+    const float k120 = 1.f / 120.f;
+    const float Cxx = cov[0] * k120 - V * c0 * c0, Cyy = cov[1] * k120 - V * c1 * c1, Czz = cov[2] * k120 - V * c2 * c2;
+    out.inertia[0] = Cyy + Czz;
+    out.inertia[1] = Cxx + Czz;
+    out.inertia[2] = Cxx + Cyy;
+    out.inertia[3] = -(cov[3] * k120 - V * c0 * c1);
+    out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
+    out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
+}
+} // namespace surtr

@@ -9,6 +9,7 @@
 #pragma once
 
 #include "clip_sub.cuh"
+#include "clip_global.cuh"
 
 #include <type_traits>
 #include "scan.cuh"
@@ -33,11 +34,11 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
 {
     unsigned long long n_cand;
     unsigned long long n_frag, n_fverts, n_fring;
-    unsigned int n_ovf;         // pairs queued for the large tier
-    unsigned int n_tier2_fail;  // pairs that outgrew the large tier as well
+    unsigned int n_ovf;         // pairs queued for the large on-chip tier (256 vertices, degree 16)
+    unsigned int n_fail;        // pairs that cannot be cut: malformed rings, or beyond the workspace of the last tier
     unsigned int tile_a, tile_b;
     unsigned int n_seq_cuts;
-    unsigned int pad;
+    unsigned int n_ovf3;        // pairs queued for the global-memory tier
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -282,6 +283,11 @@ struct ClipArgs
     uint64_t slot_bytes;
     uint32_t* ovf_list;           // tier 1 appends, tier 2 consumes
     uint64_t cap_tier2;           // slots available to tier 2
+    uint32_t* ovf3_list;          // tier 2 appends, tier 3 consumes
+    unsigned char* ws3;           // tier 3: one workspace per warp
+    uint64_t ws3_stride;
+    int cap3;                     // tier 3: vertex slots per workspace
+    uint64_t cap_tier3;           // result slots available to tier 3
     Ctl* ctl;
     uint32_t* dbg;                // optional: 8 words per candidate (cycles per phase, cut counts); NULL = off
 };
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
         const uint2 pr = a.cand[q];
         const uint32_t v0 = a.p_vert_off[pr.x];
         int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
-        bool too_big = nv > P::CAP;
+        bool too_big = nv > P::CAP, malformed = false;
         if (!too_big)
         {
             for (int v = lane; v < nv; v += 32)
@@ -337,17 +343,18 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
                 else
                 {
                     sp.deg[v] = (uint8_t)d;
-                    if (d == 0) too_big = true;   // a vertex without neighbours is not a polyhedron vertex
+                    if (d == 0) malformed = true;   // a vertex without neighbours is not a polyhedron vertex
                     for (int j = 0; j < d; j++)
                     {
                         const int idx = a.p_ring[r0 + j];
-                        if (idx >= nv) too_big = true;   // malformed input: reported as a failed pair, never indexed
+                        if (idx >= nv) malformed = true;   // reported as a failed pair, never used as an index
                         sp.ring[v * DMAX + j] = (IdxT)idx;
                     }
                 }
             }
         }
-        too_big = __ballot_sync(FULL, too_big) != 0u;
+        malformed = __ballot_sync(FULL, malformed) != 0u;
+        too_big = __ballot_sync(FULL, too_big) != 0u || malformed;
         __syncwarp();
         int status = CLIP_OVERFLOW;
         const long long t1 = clock64();
@@ -378,9 +385,13 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
                     const unsigned slot = atomicAdd(&a.ctl->n_ovf, 1u);
                     a.ovf_list[slot] = q;   // capacity = cap_cand, cannot overflow
                 }
+                else if (malformed)
+                {
+                    atomicAdd(&a.ctl->n_fail, 1u);
+                }
                 else
                 {
-                    atomicAdd(&a.ctl->n_tier2_fail, 1u);
+                    a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier
                 }
             }
             __syncwarp();
@@ -431,12 +442,120 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
 #pragma unroll
             for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
             rec->blob = blob;
-            if (!room) atomicAdd(&a.ctl->n_tier2_fail, 1u);
+            if (!room) atomicAdd(&a.ctl->n_fail, 1u);
             if (a.dbg)
             {
                 a.dbg[(size_t)q * 8 + 2] = (uint32_t)(t3 - t2);
                 a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t3);
             }
+        }
+        __syncwarp();
+    }
+    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+}
+
+// K3, unbounded tier: persistent warps over the pairs the on-chip tiers handed on (clip_global.cuh).
+constexpr int T3_WARPS = 4;
+__host__ __device__ constexpr size_t blob3_bytes(size_t cap) { return cap * (16 + 4 + GD * 2); }   // float4 verts | u32 ring_start | u16 ring
+
+__global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned long long n_items = a.ctl->n_ovf3;
+    GlobalPoly g = global_poly_carve(a.ws3 + (size_t)gw * a.ws3_stride, a.cap3);
+    unsigned seq_cuts = 0;
+    for (unsigned long long it = gw; it < n_items; it += nwarps)
+    {
+        const uint32_t q = a.ovf3_list[it];
+        const uint2 pr = a.cand[q];
+        const uint32_t v0 = a.p_vert_off[pr.x];
+        int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+        bool bad = nv > g.cap;
+        if (!bad)
+        {
+            for (int v = lane; v < nv; v += 32)
+            {
+                const float4 p = __ldg(a.p_verts + v0 + v);
+                g.x[v] = p.x; g.y[v] = p.y; g.z[v] = p.z;
+                const uint32_t r0 = a.p_ring_off[v0 + v];
+                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+                if (d > GD || d == 0) bad = true;
+                else
+                {
+                    g.deg[v] = (uint8_t)d;
+                    for (int j = 0; j < d; j++)
+                    {
+                        const int idx = a.p_ring[r0 + j];
+                        if (idx >= nv) bad = true;
+                        g.ring[(size_t)v * GD + j] = (uint16_t)idx;
+                    }
+                }
+            }
+        }
+        bad = __ballot_sync(FULL, bad) != 0u;
+        __syncwarp();
+        int status = CLIP_OVERFLOW;
+        if (!bad)
+        {
+            const uint32_t pl0 = a.c_plane_off[pr.y];
+            const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+            status = global_clip_by_planes(g, nv, a.c_planes + pl0, npl, lane, seq_cuts);
+        }
+        CandRec* rec = a.rec + q;
+        const bool room = it < a.cap_tier3;
+        if (status != CLIP_OK || !room)
+        {
+            if (lane == 0)
+            {
+                rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+                if (status != CLIP_OK) atomicAdd(&a.ctl->n_fail, 1u);   // !room alone: the host grows the slots and re-runs
+            }
+            __syncwarp();
+            continue;
+        }
+        if (nv == 0)
+        {
+            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 3; }
+            __syncwarp();
+            continue;
+        }
+        Moments mo;
+        global_fragment_moments(g, nv, lane, mo);
+        const unsigned long long blob = it * a.slot_bytes;
+        unsigned char* b = a.scratch + blob;
+        float4* bv = reinterpret_cast<float4*>(b);
+        uint32_t* bo = reinterpret_cast<uint32_t*>(b + (size_t)g.cap * 16);
+        uint16_t* br = reinterpret_cast<uint16_t*>(b + (size_t)g.cap * 20);
+        int ne = 0;
+        for (int base = 0; base < nv; base += 32)
+        {
+            const int v = base + lane;
+            const int d = v < nv ? g.deg[v] : 0;
+            int tot;
+            const int off = ne + warp_exscan(d, lane, tot);
+            ne += tot;
+            if (v < nv)
+            {
+                bv[v] = make_float4(g.x[v], g.y[v], g.z[v], 0.f);
+                bo[v] = (uint32_t)off;
+                for (int j = 0; j < d; j++) br[off + j] = g.ring[(size_t)v * GD + j];
+            }
+        }
+        if (lane == 0)
+        {
+            rec->nv = (uint32_t)nv;
+            rec->ne = (uint32_t)ne;
+            rec->nf = (uint32_t)mo.n_faces;
+            rec->tier = 3;
+            rec->volume = mo.volume;
+            rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
+#pragma unroll
+            for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
+            rec->blob = blob;
         }
         __syncwarp();
     }
@@ -590,7 +709,8 @@ struct AssembleArgs
     uint64_t cap_cand;
     const unsigned char* scratch1;
     const unsigned char* scratch2;
-    int cap1, cap2;             // vertex capacity (blob layout) of tier 1 / tier 2
+    const unsigned char* scratch3;
+    int cap1, cap2, cap3;       // vertex capacity (blob layout) of tiers 1 / 2 / 3
     ScanState<3> st;
     Ctl* ctl;
     uint4* out_off;             // per candidate: fragment index, first vertex, first ring entry
@@ -679,24 +799,40 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
     const unsigned long long cfi = off.x, cvb = off.y, crb = off.z;
     if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) return;
     const int tier = r->tier;
-    const int cap = tier == 1 ? a.cap1 : a.cap2;
-    const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
-    const float4* bv = reinterpret_cast<const float4*>(b);
-    const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
-    for (int v = lane; v < cnv; v += 32)
+    if (tier == 3)
     {
-        a.f_verts[cvb + v] = bv[v];
-        a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
-    }
-    if (tier == 1)
-    {
-        const uint8_t* br = b + (size_t)cap * 18;
+        const unsigned char* b = a.scratch3 + r->blob;
+        const float4* bv = reinterpret_cast<const float4*>(b);
+        const uint32_t* bo = reinterpret_cast<const uint32_t*>(b + (size_t)a.cap3 * 16);
+        const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)a.cap3 * 20);
+        for (int v = lane; v < cnv; v += 32)
+        {
+            a.f_verts[cvb + v] = bv[v];
+            a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+        }
         for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
     }
     else
     {
-        const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
-        for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+        const int cap = tier == 1 ? a.cap1 : a.cap2;
+        const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
+        const float4* bv = reinterpret_cast<const float4*>(b);
+        const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
+        for (int v = lane; v < cnv; v += 32)
+        {
+            a.f_verts[cvb + v] = bv[v];
+            a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+        }
+        if (tier == 1)
+        {
+            const uint8_t* br = b + (size_t)cap * 18;
+            for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+        }
+        else
+        {
+            const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
+            for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+        }
     }
     if (lane == 0)
     {

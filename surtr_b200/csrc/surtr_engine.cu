@@ -86,9 +86,11 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ctl, dbg, out_off;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off;
     bool debug = false;
-    uint64_t cap_cand = 0, cap_tier2 = 0;
+    uint64_t cap_cand = 0, cap_tier2 = 0, cap_tier3 = 0;
+    int cap3 = 0;                 // vertex slots of a tier-3 workspace (from the largest uploaded piece)
+    uint32_t max_piece_verts = 0;
     uint32_t n_tiles_a = 0, n_tiles_b = 0;
 
     // outputs
@@ -102,7 +104,8 @@ struct surtr_ctx
     void* ctl_ptr = nullptr;
     bool profile = false;         // per-kernel CUDA events inside an event (they serialise the PDL chain)
     bool profiled_last = false;
-    bool tier2_enabled = false;   // the large tier is launched once an event needed it
+    bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
+    bool tier3_enabled = false;   // likewise the global-memory tier
     bool event_launched = false, event_resolved = false;
     surtr_counts last{};
 };
@@ -201,6 +204,18 @@ int ensure_capacity(surtr_ctx* ctx)
     if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
     CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
     CK(ctx->scratch2.reserve(blob_bytes<Tier2>() * ctx->cap_tier2));
+    if (ctx->tier2_enabled) CK(ctx->ovf3_list.reserve(4 * ctx->cap_cand));   // tier 2 hands pairs on through this list
+    if (ctx->tier3_enabled)
+    {
+        // workspace: twice the largest piece (a cut adds at most one vertex per straddling edge), at least 4096 slots
+        // (a multiple of 16 keeps every array of the workspace and of the result blobs 16-byte aligned)
+        const uint64_t want = std::min<uint64_t>(65520, (std::max<uint64_t>(4096, 2ull * ctx->max_piece_verts + 1024) + 15) / 16 * 16);
+        ctx->cap3 = std::max<int>(ctx->cap3, (int)want);
+        ctx->cap_tier3 = std::max<uint64_t>(ctx->cap_tier3, 8);
+        const size_t stride = (global_poly_bytes((size_t)ctx->cap3) + 255) / 256 * 256;
+        CK(ctx->ws3.reserve(stride * (size_t)ctx->num_sm * T3_WARPS));
+        CK(ctx->scratch3.reserve(blob3_bytes((size_t)ctx->cap3) * ctx->cap_tier3));
+    }
     // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
     const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
     CK(ctx->ctl.reserve(zero_bytes + 8 * 2 * ((size_t)ctx->n_tiles_a + 1) + 8 * 6 * ((size_t)ctx->n_tiles_b + 1)));
@@ -294,6 +309,11 @@ int launch_event(surtr_ctx* ctx)
     ca.rec = ctx->cand_rec.as<CandRec>();
     ca.ovf_list = ctx->ovf_list.as<uint32_t>();
     ca.cap_tier2 = ctx->cap_tier2;
+    ca.ovf3_list = ctx->ovf3_list.as<uint32_t>();
+    ca.ws3 = ctx->ws3.as<unsigned char>();
+    ca.ws3_stride = (global_poly_bytes((size_t)std::max(1, ctx->cap3)) + 255) / 256 * 256;
+    ca.cap3 = ctx->cap3;
+    ca.cap_tier3 = ctx->cap_tier3;
     ca.ctl = d_ctl;
     ca.dbg = ctx->debug ? ctx->dbg.as<uint32_t>() : nullptr;
     {
@@ -312,6 +332,13 @@ int launch_event(surtr_ctx* ctx)
         launch_pdl(clip_kernel<Tier2, 2, T2_WARPS>, dim3(ctx->num_sm), dim3(T2_WARPS * 32), smem, ctx->stream, ca);
         ctx->launches++;
     }
+    if (ctx->tier3_enabled)
+    {
+        ca.scratch = ctx->scratch3.as<unsigned char>();
+        ca.slot_bytes = blob3_bytes((size_t)ctx->cap3);
+        launch_pdl(clip_global_kernel, dim3(ctx->num_sm), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
+        ctx->launches++;
+    }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
 
     // K4
@@ -322,6 +349,8 @@ int launch_event(surtr_ctx* ctx)
         aa.cap_cand = ctx->cap_cand;
         aa.scratch1 = ctx->scratch1.as<unsigned char>();
         aa.scratch2 = ctx->scratch2.as<unsigned char>();
+        aa.scratch3 = ctx->scratch3.as<unsigned char>();
+        aa.cap3 = ctx->cap3;
         aa.cap1 = 64;
         aa.cap2 = Tier2::CAP;
         aa.st = ScanState<3>{ flags_b, agg_b, inc_b };
@@ -363,6 +392,8 @@ int resolve_event(surtr_ctx* ctx)
         if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
         if (c.n_ovf > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf + c.n_ovf / 4 + 16; grow = true; }
         if (c.n_ovf && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
+        if (c.n_ovf3 > ctx->cap_tier3) { ctx->cap_tier3 = (uint64_t)c.n_ovf3 + c.n_ovf3 / 4 + 8; grow = true; }
+        if (c.n_ovf3 && !ctx->tier3_enabled) { ctx->tier3_enabled = true; grow = true; }  // re-run with the global tier
         if (!grow)
         {
             if (c.n_frag > ctx->cap_frag) { ctx->cap_frag = c.n_frag + c.n_frag / 8 + 64; grow = true; }
@@ -371,9 +402,10 @@ int resolve_event(surtr_ctx* ctx)
         }
         if (!grow)
         {
-            if (c.n_tier2_fail)
+            if (c.n_fail)
                 return fail(ctx, SURTR_ERR_OVERFLOW,
-                            std::to_string(c.n_tier2_fail) + " pair(s) exceed the largest on-chip clip tier (256 vertices, ring degree 16) or have malformed rings");
+                            std::to_string(c.n_fail) + " pair(s) cannot be cut: malformed rings, ring degree above 16, or more than " +
+                                std::to_string(ctx->cap3 ? ctx->cap3 : 65520) + " vertex slots needed");
             ctx->last.n_pairs = ctx->n_pairs;
             ctx->last.n_candidates = c.n_cand;
             ctx->last.n_fragments = c.n_frag;
@@ -381,6 +413,7 @@ int resolve_event(surtr_ctx* ctx)
             ctx->last.n_ring = c.n_fring;
             ctx->last.n_seq_cuts = c.n_seq_cuts;
             ctx->last.n_tier2 = c.n_ovf;
+            ctx->last.n_tier3 = c.n_ovf3;
             ctx->event_resolved = true;
             return SURTR_OK;
         }
@@ -452,7 +485,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
-                      &ctx->scratch1, &ctx->scratch2, &ctx->ovf_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -485,6 +518,8 @@ int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* ver
     ctx->n_pieces = n_pieces;
     ctx->n_pverts = nv;
     ctx->n_pring = ne;
+    ctx->max_piece_verts = 0;
+    for (uint32_t i = 0; i < n_pieces; i++) ctx->max_piece_verts = std::max(ctx->max_piece_verts, vert_off[i + 1] - vert_off[i]);
     if (ev_piece_off && n_events) ctx->h_ev_piece_off.assign(ev_piece_off, ev_piece_off + n_events + 1);
     else ctx->h_ev_piece_off = { 0u, n_pieces };
     ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
@@ -594,6 +629,7 @@ int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint
     ctx->cap_fverts = ctx->f_verts.cap / 16;
     ctx->cap_fring = ctx->f_ring.cap / 2;
     if (ctx->f_ring_off.cap < 4 * (ctx->cap_fverts + 1)) ctx->cap_fverts = ctx->f_ring_off.cap >= 8 ? ctx->f_ring_off.cap / 4 - 1 : 0;
+    ctx->max_piece_verts = std::min<uint32_t>(32000u, 2u * std::max(ctx->max_piece_verts, 64u));   // fragments can outgrow their piece
     ctx->n_pieces = n;
     ctx->n_pverts = c.n_verts;
     ctx->n_pring = c.n_ring;

@@ -100,13 +100,14 @@ surtr_ctx* context()
 	return h.ctx;
 }
 
-void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry)
+void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry, bool upload_cells)
 {
 	surtr_ctx* c = context();
 	check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
 							  pieces.count(), nullptr, 0), "surtr_upload_pieces");
-	check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
-							 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(), nullptr, 0), "surtr_upload_cells");
+	if (upload_cells)
+		check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
+								 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(), nullptr, 0), "surtr_upload_cells");
 	check(surtr_fracture_event(c), "surtr_fracture_event");
 	surtr_counts n;
 	check(surtr_event_counts(c, &n), "surtr_event_counts");

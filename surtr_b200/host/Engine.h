@@ -45,6 +45,7 @@ struct Fragments
 
 surtr_ctx* context();                                            // throws std::runtime_error without a B200
 void check(int rc, const char* what);                            // throws std::runtime_error with surtr_last_error
-void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true);
+// upload_cells = false: the cells of the previous event on this thread's context are still resident and are reused
+void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true, bool upload_cells = true);
 } // namespace detail
 } // namespace SurtrHost

@@ -47,7 +47,8 @@ std::vector<Vector3> GenerateRadialSeeds(int seed, int cellCount, double mean)
 
 std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPointVec) { return DT3D::VoronoiCells(cellPointVec); }
 
-PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<Vector3>& seeds, const FractureArgs& args)
+static PreparedObject prepare(const std::vector<Vector3>& vertices, const std::vector<int>* indices, const std::vector<Vector3>& seeds,
+							  const FractureArgs& args)
 {
 	PreparedObject r;
 	// 1-2. intermediate convex hull with limit count -> face normals
@@ -80,15 +81,69 @@ PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::
 		voro.Scale(Vector3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]));
 		voro.Translate(r.BBCenter);
 	}
+	// 7. mesh polyhedron
+	if (indices)
+	{
+		const std::vector<std::vector<int>> nei = Poly::ExtractNeighborFromMesh(vertices, *indices);
+		Poly::InitPolyhedron(r.Mesh, vertices, nei);
+	}
 	// 10. initial pieces
 	Compound pre;
-	Piece ach_piece(r.ACH, r.ACH);
-	pre.PieceVec.push_back(&ach_piece);
-	r.Initial = ApplyFracture(pre, r.Cells);
+	Piece first_piece(r.ACH, indices ? r.Mesh : r.ACH);
+	pre.PieceVec.push_back(&first_piece);
+	r.Initial = ApplyFracture(pre, r.Cells, indices != nullptr);
+	if (indices)
+	{
+		Refitting(r.Initial.PieceVec, args);
+		SetExtract(r.Initial);
+	}
 	return r;
 }
 
-CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec)
+PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<Vector3>& seeds, const FractureArgs& args)
+{
+	return prepare(vertices, nullptr, seeds, args);
+}
+
+PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<int>& indices, const std::vector<Vector3>& seeds,
+							   const FractureArgs& args)
+{
+	return prepare(vertices, &indices, seeds, args);
+}
+
+std::vector<std::set<int>> CheckMeshIsland(const Poly::Polyhedron& polyhedron)
+{
+	// Surtr.cpp:2157-2199 recurses from an arbitrary vertex; an explicit stack reaches the same sets.  Groups come
+	// out in order of their lowest not-yet-grouped vertex, each as a sorted set.
+	std::vector<std::set<int>> groupVec;
+	std::vector<char> grouped(polyhedron.size(), 0);
+	std::vector<int> stack;
+	int start = 0;
+	for (;;)
+	{
+		std::set<int> group;
+		stack.assign(1, start);
+		while (!stack.empty())
+		{
+			const int v = stack.back();
+			stack.pop_back();
+			for (const int a : polyhedron[v].NeighborVertexVec)
+				if (group.insert(a).second)
+					stack.push_back(a);
+		}
+		for (const int v : group)
+			grouped[v] = 1;
+		groupVec.push_back(std::move(group));
+		grouped[start] = 1;   // a start vertex without neighbours is in no group (the reference would spin on it)
+		const auto rest = std::find(grouped.begin() + start, grouped.end(), 0);
+		if (rest == grouped.end())
+			break;
+		start = (int)(rest - grouped.begin());
+	}
+	return groupVec;
+}
+
+CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch)
 {
 	detail::FlatPolys pieces;
 	for (const Piece* p : compound.PieceVec)
@@ -96,31 +151,77 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 	detail::FlatCells cells;
 	for (const VMACH::Polygon3D& cell : voroPolyVec)
 		cells.add(cell);
-	detail::Fragments fr;
+	detail::Fragments fr, mfr;
 	detail::run_event(pieces, cells, fr);
+	if (meshBranch)
+	{
+		// second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident cells, one more
+		// GPU event.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
+		// its convex and its mesh fragment exist (:1466-1472).
+		detail::FlatPolys meshes;
+		for (const Piece* p : compound.PieceVec)
+			meshes.add(p->Mesh);
+		detail::run_event(meshes, cells, mfr, true, false);
+	}
 
 	CompoundInfo info;
 	info.CompoundBind.push_back(std::set<int>());   // 0-th element is reserved (Surtr.cpp:2126)
 	int current_cell = -1;
+	size_t m = 0;
+	const auto key = [](const surtr_fragment& r) { return ((uint64_t)r.cell << 32) | r.piece; };
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
 		const surtr_fragment& r = fr.rec[f];
 		const Poly::Polyhedron convex = fr.polyhedron(f);
-		info.PieceVec.push_back(new Piece(convex, convex));   // mesh branch: "next" row f-1
-		if ((int)r.cell != current_cell)   // fragments arrive cell-major: one bind set per non-empty cell (Surtr.cpp:2133-2146)
+		std::vector<Poly::Polyhedron> meshes;
+		if (meshBranch)
 		{
-			info.CompoundBind.push_back(std::set<int>());
-			current_cell = (int)r.cell;
+			while (m < mfr.rec.size() && key(mfr.rec[m]) < key(r))   // both lists are cell-major, piece-minor
+				m++;
+			if (m == mfr.rec.size() || key(mfr.rec[m]) != key(r))
+				continue;   // mesh clipped away (Surtr.cpp:1471)
+			const Poly::Polyhedron mesh = mfr.polyhedron(m);
+			const std::vector<std::set<int>> groupVec = CheckMeshIsland(mesh);
+			if (groupVec.size() >= 2)
+			{
+				std::vector<int> mapping(mesh.size(), -1);
+				for (const std::set<int>& group : groupVec)   // Surtr.cpp:1475-1495
+				{
+					Poly::Polyhedron island;
+					for (const int iVert : group)
+					{
+						mapping[iVert] = (int)island.size();
+						island.push_back(mesh[iVert]);
+					}
+					for (Poly::Vertex& vert : island)
+						for (int& iAdj : vert.NeighborVertexVec)
+							iAdj = mapping[iAdj];
+					meshes.push_back(std::move(island));
+				}
+			}
+			else
+				meshes.push_back(mesh);
 		}
-		info.CompoundBind.back().insert((int)f);
-		MassProperties m;
-		m.Volume = r.volume;
-		m.Centroid = Vector3(r.centroid[0], r.centroid[1], r.centroid[2]);
-		std::copy(r.inertia, r.inertia + 6, m.Inertia);
-		m.FaceCount = r.n_faces;
-		info.PieceMass.push_back(m);
-		info.PieceSourceCell.push_back((int)r.cell);
-		info.PieceSourcePiece.push_back((int)r.piece);
+		else
+			meshes.push_back(convex);
+		for (Poly::Polyhedron& mesh : meshes)
+		{
+			if ((int)r.cell != current_cell)   // one bind set per cell that produced pieces, cell order (Surtr.cpp:2133-2146)
+			{
+				info.CompoundBind.push_back(std::set<int>());
+				current_cell = (int)r.cell;
+			}
+			info.CompoundBind.back().insert((int)info.PieceVec.size());
+			info.PieceVec.push_back(new Piece(convex, mesh));
+			MassProperties mp;
+			mp.Volume = r.volume;
+			mp.Centroid = Vector3(r.centroid[0], r.centroid[1], r.centroid[2]);
+			std::copy(r.inertia, r.inertia + 6, mp.Inertia);
+			mp.FaceCount = r.n_faces;
+			info.PieceMass.push_back(mp);
+			info.PieceSourceCell.push_back((int)r.cell);
+			info.PieceSourcePiece.push_back((int)r.piece);
+		}
 	}
 	return info;
 }

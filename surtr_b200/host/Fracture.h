@@ -4,7 +4,8 @@
 // the path runs without a window, a device or PhysX.  ApplyFracture is the drop-in for Surtr::ApplyFracture
 // (Surtr.cpp:2098-2149): instead of one thread-pool task per cell (m_fractureTask, :1457-1504) it packs the
 // compound's convex pieces and the cell planes once, runs ONE GPU fracture event through the C ABI and unpacks the
-// fragments in the reference's order.  The mesh branch of m_fractureTask (:1470-1500) is the "next" row f-1.
+// fragments in the reference's order.  The mesh branch of m_fractureTask (:1470-1500) is a second event over the same
+// resident cells (Piece::Mesh polyhedra, cut in the global-memory tier of K3) followed by the island split on the host.
 #pragma once
 
 #include "Poly.h"
@@ -75,23 +76,30 @@ std::vector<Vector3> GenerateRadialSeeds(int seed, int cellCount, double mean);
 // Surtr::GenerateVoronoi(points): DT3D-derived cells (voro++ is not vendored).
 std::vector<VMACH::Polygon3D> GenerateVoronoi(const std::vector<Vector3>& cellPointVec);
 
-// Surtr::PrepareFracture, convex branch (Surtr.cpp:1747-1827 steps 1-6, 8, 10): ICH normals -> bounding box -> k-DOP
-// with gap -> ACH (2x bbox clipped by the k-DOP) -> Voronoi cells of `seeds` scaled by the bbox extent and translated
-// to its centre -> ApplyFracture on the single ACH piece.  The mesh polyhedron (step 7) and the pattern caches (step 9)
-// belong to the "next" rows.
+// Surtr::PrepareFracture (Surtr.cpp:1747-1827): ICH normals -> bounding box -> k-DOP with gap -> ACH (2x bbox clipped by
+// the k-DOP) -> [mesh polyhedron from the triangle list, step 7] -> Voronoi cells of `seeds` scaled by the bbox extent
+// and translated to its centre -> ApplyFracture on the single (ACH, mesh) piece -> Refitting -> SetExtract.
+// The overload without indices runs the convex branch only (Piece::Mesh = Piece::Convex, no refit): the configuration
+// BASELINE.json's throughput metric is quoted on.  The pattern caches (step 9) are GenerateRadialSeeds + GenerateVoronoi,
+// built by the caller when it fractures again.
 struct PreparedObject
 {
 	Vector3 BBCenter, MinBB, MaxBB;
 	float MaxAxisScale = 0.f;
 	int ICHFaceCnt = 0;
-	Poly::Polyhedron ACH;
+	Poly::Polyhedron ACH, Mesh;
 	std::vector<VMACH::Polygon3D> Cells;
 	CompoundInfo Initial;
 };
 PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<Vector3>& seeds, const FractureArgs& args = FractureArgs());
+PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<int>& indices, const std::vector<Vector3>& seeds,
+							   const FractureArgs& args = FractureArgs());
 
-// Surtr::ApplyFracture, non-partial convex branch.  Throws std::runtime_error on a C-ABI failure.
-CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec);
+// Surtr::ApplyFracture, non-partial.  meshBranch = false skips the second clip and hands every piece its convex as mesh.
+// Throws std::runtime_error on a C-ABI failure.
+CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch = true);
+// Surtr::CheckMeshIsland (Surtr.cpp:2171-2199): connected components of the ring graph.
+std::vector<std::set<int>> CheckMeshIsland(const Poly::Polyhedron& polyhedron);
 // Surtr::SetExtract (Surtr.cpp:2151-2155).
 void SetExtract(CompoundInfo& preResult);
 // Surtr::Refitting (Surtr.cpp:2405-2413) = m_refittingTask (:1449-1455) for every piece, batched: the ICH normals of

@@ -4,6 +4,7 @@
 #include "VMACH.h"
 
 #include <algorithm>
+#include <stdexcept>
 
 using SurtrHost::detail::FlatCells;
 using SurtrHost::detail::FlatPolys;
@@ -19,6 +20,100 @@ void InitPolyhedron(Polyhedron& polyhedron, const std::vector<Vector3>& position
 		polyhedron[i].Position = positionVec[i];
 		polyhedron[i].NeighborVertexVec = neighborVec[i];
 	}
+}
+
+std::vector<std::vector<int>> ExtractNeighborFromMesh(const std::vector<Vector3>& vertices, const std::vector<int>& indices)
+{
+	// The reference builds per-triangle adjacency lists and walks each vertex's triangle fan through them
+	// (Poly.cpp:131-212).  Same walk here over a CSR of incident triangles: the fan's next triangle is the first one,
+	// in the order "edges (0,1), (1,2), (2,0) of the current triangle, ascending triangle index across an edge", that
+	// touches the vertex and is not yet part of the fan -- which is what candidate[0] of Poly.cpp:183-210 selects.
+	const int n_tri = (int)indices.size() / 3;
+	const int n_vert = (int)vertices.size();
+	std::vector<int> inc_off(n_vert + 1, 0);
+	for (int i = 0; i < 3 * n_tri; i++)
+		inc_off[indices[i] + 1]++;
+	for (int v = 0; v < n_vert; v++)
+		inc_off[v + 1] += inc_off[v];
+	std::vector<int> inc(inc_off[n_vert]), fill(inc_off.begin(), inc_off.end() - 1);
+	for (int t = 0; t < n_tri; t++)   // ascending triangle index per vertex, repeats kept (as push_back does at :145-147)
+		for (int k = 0; k < 3; k++)
+			inc[fill[indices[3 * t + k]]++] = t;
+	const auto touches = [&](const int t, const int v) { return indices[3 * t] == v || indices[3 * t + 1] == v || indices[3 * t + 2] == v; };
+
+	std::vector<std::vector<int>> nei(n_vert);
+	std::vector<int> fan, across;
+	for (int iVert = 0; iVert < n_vert; iVert++)
+	{
+		if (inc_off[iVert] == inc_off[iVert + 1])
+			continue;   // a vertex no triangle uses keeps an empty ring
+		fan.assign(1, inc[inc_off[iVert]]);
+		for (int curr = fan[0];;)
+		{
+			int next = -1, n_candidates = 0;
+			across.clear();   // curr's adjacency list, duplicates removed in first-seen order (:163-168)
+			for (int e = 0; e < 3; e++)
+			{
+				const int a = indices[3 * curr + e], b = indices[3 * curr + (e + 1) % 3];
+				const int* pa = &inc[inc_off[a]], * ea = &inc[inc_off[a + 1]];
+				const int* pb = &inc[inc_off[b]], * eb = &inc[inc_off[b + 1]];
+				while (pa != ea && pb != eb)   // std::set_intersection of two ascending lists (:156-158)
+				{
+					if (*pa < *pb) ++pa;
+					else if (*pb < *pa) ++pb;
+					else
+					{
+						const int t = *pa;
+						++pa; ++pb;
+						if (t != curr && across.end() == std::find(across.begin(), across.end(), t))
+							across.push_back(t);
+					}
+				}
+			}
+			for (const int t : across)
+				if (fan.end() == std::find(fan.begin(), fan.end(), t) && touches(t, iVert))
+				{
+					if (n_candidates++ == 0)
+						next = t;
+				}
+			if (n_candidates == 0)
+				break;
+			if (n_candidates > 2)
+				throw std::runtime_error("ExtractNeighborFromMesh: non-manifold fan (the reference does not terminate here)");
+			fan.push_back(next);
+			curr = next;
+		}
+
+		std::vector<int> collection;
+		for (const int t : fan)
+		{
+			int start = 0;
+			for (int k = 0; k < 3; k++)
+				if (indices[3 * t + k] == iVert) { start = k; break; }
+			collection.push_back(indices[3 * t + (start + 1) % 3]);
+			collection.push_back(indices[3 * t + (start + 2) % 3]);
+		}
+		if (collection.size() >= 3)
+		{
+			const bool isCCW = collection[1] != collection[2];   // :236
+			if (isCCW)
+				for (size_t i = 0; i + 1 < collection.size(); i += 2)
+					std::swap(collection[i], collection[i + 1]);
+			std::vector<int> unique;
+			for (const int v : collection)
+				if (unique.end() == std::find(unique.begin(), unique.end(), v))
+					unique.push_back(v);
+			if (isCCW)
+				std::reverse(unique.begin(), unique.end());
+			collection.swap(unique);
+		}
+		nei[iVert].swap(collection);
+	}
+	for (int v = 0; v < n_vert; v++)   // :253-260
+		for (const int a : nei[v])
+			if (nei[a].end() == std::find(nei[a].begin(), nei[a].end(), v))
+				throw std::runtime_error("ExtractNeighborFromMesh: asymmetric adjacency");
+	return nei;
 }
 
 void Moments(double& zerothMoment, Vector3& firstMoment, const Polyhedron& polyhedron)

@@ -40,6 +40,10 @@ typedef std::vector<Poly::Vertex> Polyhedron;   // empty vector <=> "no polyhedr
 typedef std::vector<std::vector<int>> Extract;
 
 void InitPolyhedron(Polyhedron& polyhedron, const std::vector<Vector3>& positionVec, const std::vector<std::vector<int>>& neighborVec);
+// Triangle list -> CCW neighbour ring per vertex (Poly.cpp:128-263), the input of InitPolyhedron for Piece::Mesh
+// (Surtr.cpp:1788-1795).  Index bookkeeping only (once per object, host).  Throws std::runtime_error where the reference
+// throws (asymmetric adjacency) or would not terminate (an edge fan with three or more continuations).
+std::vector<std::vector<int>> ExtractNeighborFromMesh(const std::vector<Vector3>& vertices, const std::vector<int>& indices);
 // Volume and centroid (Poly.cpp:55-87), computed by kernel K4 on the GPU.
 void Moments(double& zerothMoment, Vector3& firstMoment, const Polyhedron& polyhedron);
 // Face loops (Poly.cpp:89-126); caller owns the result.  Pure index bookkeeping over the rings (no arithmetic):

@@ -48,7 +48,7 @@ struct Out
 		vert_off.push_back((uint32_t)(verts.size() / 4));
 	}
 };
-Out g_out;
+Out g_out, g_mesh;   // g_mesh: Piece::Mesh of the same pieces (mesh-branch entry points)
 } // namespace
 
 extern "C"
@@ -226,7 +226,7 @@ int hosttest_apply_fracture(const float* verts, const uint32_t* vert_off, const 
 			}
 			cells.push_back(poly);
 		}
-		SurtrHost::CompoundInfo info = SurtrHost::ApplyFracture(compound, cells);
+		SurtrHost::CompoundInfo info = SurtrHost::ApplyFracture(compound, cells, false);
 		SurtrHost::SetExtract(info);
 		g_out = Out();
 		for (size_t i = 0; i < info.PieceVec.size(); i++)
@@ -248,6 +248,104 @@ int hosttest_apply_fracture(const float* verts, const uint32_t* vert_off, const 
 		for (auto* p : compound.PieceVec) delete p;
 		for (auto* p : info.PieceVec) delete p;
 		for (auto* e : info.PieceExtractedConvex) delete e;
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// select which set hosttest_sizes / hosttest_export read: 0 = convex (default), 1 = mesh
+void hosttest_swap_sets() { std::swap(g_out, g_mesh); }
+
+// Poly::ExtractNeighborFromMesh (CPU only): rings into g_out as one polyhedron
+int hosttest_mesh_polyhedron(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx)
+{
+	try
+	{
+		std::vector<Vector3> vv;
+		for (uint32_t i = 0; i < nv; i++) vv.emplace_back(verts4[4 * i], verts4[4 * i + 1], verts4[4 * i + 2]);
+		const std::vector<int> idx(indices, indices + n_idx);
+		Poly::Polyhedron mesh;
+		Poly::InitPolyhedron(mesh, vv, Poly::ExtractNeighborFromMesh(vv, idx));
+		g_out = Out();
+		g_out.add(mesh);
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+static void export_pieces(const SurtrHost::CompoundInfo& info)
+{
+	g_out = Out();
+	g_mesh = Out();
+	for (size_t i = 0; i < info.PieceVec.size(); i++)
+	{
+		g_out.add(info.PieceVec[i]->Convex);
+		g_mesh.add(info.PieceVec[i]->Mesh);
+		for (Out* o : { &g_out, &g_mesh })
+		{
+			o->cell.push_back((uint32_t)info.PieceSourceCell[i]);
+			o->piece.push_back((uint32_t)info.PieceSourcePiece[i]);
+			o->nfaces.push_back(i < info.PieceExtractedConvex.size() ? (uint32_t)info.PieceExtractedConvex[i]->size() : 0u);
+			o->volume.push_back(info.PieceMass[i].Volume);
+			o->centroid.insert(o->centroid.end(), { info.PieceMass[i].Centroid.x, info.PieceMass[i].Centroid.y, info.PieceMass[i].Centroid.z });
+		}
+	}
+}
+
+// SurtrHost::ApplyFracture with the mesh branch (full m_fractureTask): pieces = (convex_i, mesh_i); cells as plane lists
+// with their vertex streams.  g_out = Piece::Convex, g_mesh = Piece::Mesh of the result, PieceVec order.
+int hosttest_apply_fracture_mesh(const float* cv, const uint32_t* cvo, const uint32_t* cro, const uint16_t* cr,
+								 const float* mv, const uint32_t* mvo, const uint32_t* mro, const uint16_t* mr, uint32_t n_pieces,
+								 const float* planes, const uint32_t* plane_off, const float* cverts, const uint32_t* cvert_off, uint32_t n_cells)
+{
+	try
+	{
+		SurtrHost::Compound compound;
+		for (uint32_t i = 0; i < n_pieces; i++)
+			compound.PieceVec.push_back(new SurtrHost::Piece(to_poly(cv, cro, cr, cvo[i], cvo[i + 1]), to_poly(mv, mro, mr, mvo[i], mvo[i + 1])));
+		std::vector<VMACH::Polygon3D> cells;
+		for (uint32_t c = 0; c < n_cells; c++)
+		{
+			VMACH::Polygon3D poly(true);
+			for (uint32_t k = plane_off[c]; k < plane_off[c + 1]; k++)
+			{
+				VMACH::PolygonFace f(true);
+				if (k == plane_off[c])
+					for (uint32_t v = cvert_off[c]; v < cvert_off[c + 1]; v++)
+						f.VertexVec.emplace_back(cverts[4 * v], cverts[4 * v + 1], cverts[4 * v + 2]);
+				else
+					f.VertexVec.emplace_back(cverts[4 * cvert_off[c]], cverts[4 * cvert_off[c] + 1], cverts[4 * cvert_off[c] + 2]);
+				f.ManuallySetFacePlane(Plane(planes[4 * k], planes[4 * k + 1], planes[4 * k + 2], planes[4 * k + 3]));
+				poly.AddFace(f);
+			}
+			cells.push_back(poly);
+		}
+		SurtrHost::CompoundInfo info = SurtrHost::ApplyFracture(compound, cells, true);
+		SurtrHost::SetExtract(info);
+		export_pieces(info);
+		for (auto* p : compound.PieceVec) delete p;
+		for (auto* p : info.PieceVec) delete p;
+		for (auto* e : info.PieceExtractedConvex) delete e;
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// SurtrHost::PrepareFracture in full (mesh polyhedron, mesh branch, Refitting, SetExtract)
+int hosttest_config1_full(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx, const float* seeds, uint32_t n_seeds,
+						  uint32_t* ach_nv)
+{
+	try
+	{
+		std::vector<Vector3> vv, ss;
+		for (uint32_t i = 0; i < nv; i++) vv.emplace_back(verts4[4 * i], verts4[4 * i + 1], verts4[4 * i + 2]);
+		for (uint32_t i = 0; i < n_seeds; i++) ss.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+		const std::vector<int> idx(indices, indices + n_idx);
+		SurtrHost::PreparedObject r = SurtrHost::PrepareFracture(vv, idx, ss);
+		*ach_nv = (uint32_t)r.ACH.size();
+		export_pieces(r.Initial);
+		for (auto* p : r.Initial.PieceVec) delete p;
+		for (auto* e : r.Initial.PieceExtractedConvex) delete e;
 		return 0;
 	}
 	catch (const std::exception& e) { g_err = e.what(); return 1; }

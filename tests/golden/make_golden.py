@@ -213,6 +213,57 @@ def config1_fixture():
     print("config1: ACH", ach.nverts, ach.nfaces, "fragments", fr.n, "sum vol", fr.volume.sum())
 
 
+def mesh_fixture():
+    """Row f-1 input: the bundled bunny as a vertex-ring polyhedron (ExtractNeighborFromMesh) cut by 32 Voronoi cells
+    placed on it -- the second clip of m_fractureTask (Surtr.cpp:1470).  2503 vertices, ring degree up to 13: the
+    global-memory tier of K3."""
+    from oracle import portapi as P
+    v, f = load_obj(os.path.join(REF_MODELS, "lowpoly-bunny-closed.obj"), 70.0)
+    v4 = np.zeros((len(v), 4), np.float32)
+    v4[:, :3] = v
+    mesh = R.mesh_polyhedron(v4, f)
+    lo, hi = v.min(0), v.max(0)
+    cells = common.voronoi(46354, 32)
+    placed = cells.subset(range(cells.n))
+    placed.verts = cells.verts.copy()
+    placed.verts[:, :3] = (cells.verts[:, :3] * (hi - lo).astype(np.float32) + ((hi + lo) / 2).astype(np.float32)).astype(np.float32)
+    planes, plane_off = P.face_planes(placed)
+    want = R.apply_fracture(mesh, planes, plane_off, 16)
+    port = P.apply_fracture(mesh, planes, plane_off, cap_frags=64, cap_verts=200000)
+    assert port.n == want.n and np.array_equal(port.verts.view(np.uint32), want.verts.view(np.uint32)) and np.array_equal(port.ring, want.ring)
+    d = {"planes": planes, "plane_off": plane_off, "cell_verts": placed.verts, "cell_vert_off": placed.vert_off}
+    save_polyset(d, "mesh_", mesh, full=False)
+    save_polyset(d, "frag_", want)
+    for k in list(d):
+        if k.endswith("face_off") or k.endswith("face_idx"):
+            del d[k]
+    np.savez_compressed(os.path.join(HERE, "bunny_mesh_x32.npz"), **d)
+    deg = np.diff(mesh.ring_off)
+    print("mesh: verts", mesh.nverts, "max degree", int(deg.max()), "fragments", want.n, "verts per fragment", want.nverts[:8], "max", int(want.nverts.max()))
+
+
+def config1_full_fixture():
+    """BASELINE config 1 in full: Surtr::PrepareFracture (Surtr.cpp:1747-1827) on the bundled bunny with its triangle
+    list -- ACH, mesh polyhedron, 32 cells, convex + mesh clip with island split, Refitting (ref_config1_full)."""
+    import hostapi
+    v, f = load_obj(os.path.join(REF_MODELS, "lowpoly-bunny-closed.obj"), 70.0)
+    v4 = np.zeros((len(v), 4), np.float32)
+    v4[:, :3] = v
+    s = R.seeds_uniform(46354, 32)
+    off, idx = hostapi.dt3d_neighbors(s)
+    ach, convex, mesh = R.config1_full(v4, f, s, off, idx)
+    d = {"verts": v4, "indices": np.asarray(f, np.int32).reshape(-1), "seeds": s}
+    save_polyset(d, "convex_", convex)
+    save_polyset(d, "mesh_", mesh)
+    for k in list(d):
+        if k.endswith("face_off") or k.endswith("face_idx") or k.endswith("planes") or k.endswith("plane_off"):
+            del d[k]
+    np.savez_compressed(os.path.join(HERE, "config1_full_bunny32.npz"), **d)
+    keys = list(zip(convex.cell.tolist(), convex.piece.tolist()))
+    print("config1 full: pieces", convex.n, "pairs with islands", len(keys) - len(set(keys)), "convex verts", convex.nverts[:6],
+          "mesh verts", mesh.nverts[:6], "empty convex after refit", int((convex.nverts == 0).sum()))
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     scalar_kats()
@@ -220,4 +271,6 @@ if __name__ == "__main__":
     config1_kdop()
     refit_fixture()
     config1_fixture()
+    mesh_fixture()
+    config1_full_fixture()
     summaries()

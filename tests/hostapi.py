@@ -115,6 +115,43 @@ def apply_fracture(pieces: PolySet, cells: PolySet) -> PolySet:
     return export()
 
 
+def export_mesh() -> PolySet:
+    lib().hosttest_swap_sets()
+    try:
+        return export()
+    finally:
+        lib().hosttest_swap_sets()
+
+
+def mesh_polyhedron(verts4, indices) -> PolySet:
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32).reshape(-1)
+    if lib().hosttest_mesh_polyhedron(_p(verts4), len(verts4), _p(indices), len(indices)):
+        raise RuntimeError(_err())
+    return export()
+
+
+def apply_fracture_mesh(convex: PolySet, mesh: PolySet, planes, plane_off, cell_verts, cell_vert_off):
+    planes, cell_verts = np.ascontiguousarray(planes, np.float32), np.ascontiguousarray(cell_verts, np.float32)
+    plane_off, cell_vert_off = np.ascontiguousarray(plane_off, np.uint32), np.ascontiguousarray(cell_vert_off, np.uint32)
+    rc = lib().hosttest_apply_fracture_mesh(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring),
+                                            _p(mesh.verts), _p(mesh.vert_off), _p(mesh.ring_off), _p(mesh.ring), convex.n,
+                                            _p(planes), _p(plane_off), _p(cell_verts), _p(cell_vert_off), len(plane_off) - 1)
+    if rc:
+        raise RuntimeError(_err())
+    return export(), export_mesh()
+
+
+def config1_full(verts4, indices, seeds):
+    verts4, seeds = np.ascontiguousarray(verts4, np.float32), np.ascontiguousarray(seeds, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32).reshape(-1)
+    ach_nv = C.c_uint32(0)
+    rc = lib().hosttest_config1_full(_p(verts4), len(verts4), _p(indices), len(indices), _p(seeds), len(seeds), C.byref(ach_nv))
+    if rc:
+        raise RuntimeError(_err())
+    return export(), export_mesh(), ach_nv.value
+
+
 def clip_and_moments(ps: PolySet, planes):
     planes = np.ascontiguousarray(planes, np.float32)
     vol = C.c_double(0)

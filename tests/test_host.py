@@ -138,3 +138,37 @@ def test_config1_bunny_convex_branch():
     assert got.n == want.n == 28
     for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece", "nfaces", "volume", "centroid"):
         assert np.array_equal(bits(getattr(got, f)), bits(getattr(want, f))), f
+
+
+def test_host_mesh_polyhedron_matches_reference():
+    """Poly::ExtractNeighborFromMesh mirror (host, index bookkeeping) == the reference build's rings for the bunny
+    (2503 vertices, 4968 triangles), order included; then CheckMeshIsland finds one island."""
+    d = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    want = load_polyset(np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz")), "mesh_")
+    got = H.mesh_polyhedron(d["verts"], d["indices"])
+    assert np.array_equal(got.ring_off, want.ring_off) and np.array_equal(got.ring, want.ring)
+    assert np.array_equal(bits(got.verts), bits(want.verts))
+    # a triangle list whose fan orientation is inconsistent must throw like the reference does
+    bad = d["indices"].copy().reshape(-1, 3)
+    bad = bad[: len(bad) // 2]          # half a surface: open fans still give symmetric rings or throw, never crash
+    try:
+        H.mesh_polyhedron(d["verts"], bad)
+    except RuntimeError as e:
+        assert "ExtractNeighborFromMesh" in str(e)
+
+
+@pytest.mark.gpu
+def test_config1_bunny_full_prepare_fracture():
+    """BASELINE config 1 in full through the host classes: mesh polyhedron -> ApplyFracture with the mesh branch (two GPU
+    events, the 2503-vertex mesh in the global-memory tier, island split on the host) -> Refitting -> SetExtract ==
+    the reference build (ref_config1_full), piece by piece."""
+    d = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    convex, mesh, ach_nv = H.config1_full(d["verts"], d["indices"], d["seeds"])
+    want_c, want_m = load_polyset(d, "convex_"), load_polyset(d, "mesh_")
+    assert ach_nv == 107 and convex.n == want_c.n == 27
+    for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece"):
+        assert np.array_equal(bits(getattr(convex, f)), bits(getattr(want_c, f))), "convex " + f
+        assert np.array_equal(bits(getattr(mesh, f)), bits(getattr(want_m, f))), "mesh " + f
+    assert np.array_equal(convex.nfaces, want_c.nfaces)     # SetExtract after the refit
+    keys = list(zip(want_c.cell.tolist(), want_c.piece.tolist()))
+    assert len(keys) - len(set(keys)) == 2                   # two (cell, piece) pairs split into islands
