@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 N_SEEDS = 4096
 BASE_SEED = 46354
 WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fracture event per step per GPU"
+E2E_DEPTH = 4     # events in flight in the end-to-end loop (contexts driven round-robin)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -173,7 +174,9 @@ def main():
     ap.add_argument("--kdop", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events in flight in the end-to-end loop")
     args = ap.parse_args()
+    globals()["E2E_DEPTH"] = max(1, args.e2e_depth)
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
@@ -281,32 +284,78 @@ def main():
     value = float(frags.item()) / (total_ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, every step ----
+    # A caller that streams events keeps a few of them in flight: E2E_DEPTH contexts (one stream each) are driven
+    # round-robin from this one host thread through the C ABI -- download step i-DEPTH (blocks on that stream only),
+    # then upload + launch step i -- so the PCIe copies of one event overlap the kernels of the others.  Every step
+    # still moves its own inputs host->device and its own fragments device->host, and each stream first rewrites the
+    # 256 MiB flush buffer so that no step finds its working set in L2.
     c = ctx.counts()
     from surtr_b200 import FRAGMENT_DTYPE
-    h_out = dict(rec=torch.empty(int(c.n_fragments) * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
-                 verts=torch.empty(int(c.n_verts) * 4, dtype=torch.float32).pin_memory(),
-                 ring_off=torch.empty(int(c.n_verts) + 1, dtype=torch.int32).pin_memory(),
-                 ring=torch.empty(int(c.n_ring), dtype=torch.int16).pin_memory())
+
+    def out_buffers():
+        return dict(rec=torch.empty(int(c.n_fragments) * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                    verts=torch.empty(int(c.n_verts) * 4, dtype=torch.float32).pin_memory(),
+                    ring_off=torch.empty(int(c.n_verts) + 1, dtype=torch.int32).pin_memory(),
+                    ring=torch.empty(int(c.n_ring), dtype=torch.int16).pin_memory())
+
+    h_out = out_buffers()
     d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
 
-    def e2e_step():
-        upload()
-        ctx.fracture_event()
-        ctx.download_into(h_out["rec"].data_ptr(), h_out["verts"].data_ptr(), h_out["ring_off"].data_ptr(),
-                          h_out["ring"].data_ptr())
+    def upload_to(cx):
+        cx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
+        cx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
+                            h_in["cvo"].data_ptr(), N_SEEDS)
 
+    def download_from(cx, ho):
+        cx.download_into(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
+
+    # (1) one event at a time: the latency a single synchronous caller sees
     for _ in range(3):
-        e2e_step()
+        upload_to(ctx); ctx.fracture_event(); download_from(ctx, h_out)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e2e_s = 0.0
+    sync_s = 0.0
     for _ in range(args.steps):
         flush_l2()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_step()                      # download_into synchronises the stream
-        e2e_s += time.perf_counter() - t0
+        upload_to(ctx); ctx.fracture_event(); download_from(ctx, h_out)     # download synchronises the stream
+        sync_s += time.perf_counter() - t0
+    got = np.frombuffer(h_out["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
+    assert got.tobytes() == fr0.rec.tobytes(), "e2e result differs from the resident-input result"
+
+    # (2) E2E_DEPTH events in flight: the throughput number
+    pipes = []
+    for d in range(E2E_DEPTH):
+        st = stream if d == 0 else torch.cuda.Stream(device=dev)
+        cx = ctx if d == 0 else FractureContext(local, st.cuda_stream)
+        cx.set_kdop_directions(args.kdop)
+        pipes.append((cx, st, h_out if d == 0 else out_buffers()))
+
+    def pipelined(n_steps):
+        for i in range(n_steps + E2E_DEPTH):
+            cx, st, ho = pipes[i % E2E_DEPTH]
+            if i >= E2E_DEPTH:
+                download_from(cx, ho)
+            if i < n_steps:
+                with torch.cuda.stream(st):
+                    flush.zero_()
+                upload_to(cx)
+                cx.fracture_event()
+
+    pipelined(2 * E2E_DEPTH)                # warm-up: every context grows its buffers once
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    torch.cuda.set_stream(stream)
+    for cx, st, ho in pipes:
+        got = np.frombuffer(ho["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
+        assert got.tobytes() == fr0.rec.tobytes(), "pipelined e2e result differs from the resident-input result"
+    for cx, st, ho in pipes[1:]:
+        cx.close()
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -314,9 +363,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + e2e region (the timed region alone is shorter than one sample)"
-    got = np.frombuffer(h_out["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
-    assert got.tobytes() == fr0.rec.tobytes(), "e2e result differs from the resident-input result"
-
     # ---- final fragment gather (the only collective; after the hot path, reported separately) ----
     gather = None
     if world > 1:
@@ -367,7 +413,10 @@ def main():
             "p50_event_ms": float(np.median(step_ms)), "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
-                    "timing": "wall clock around upload + event + download through the C ABI, pinned host buffers"},
+                    "events_in_flight": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
+                    "timing": "wall clock around K x (upload + event + download) through the C ABI, pinned host buffers, "
+                              f"{E2E_DEPTH} contexts round-robin from one host thread, L2 flush on every stream inside the "
+                              "timed region; single_event_ms = the same with one event at a time"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
             "clocks": clocks, "roofline": roofline,
         }

@@ -520,12 +520,19 @@ int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* ver
     ctx->n_pring = ne;
     ctx->max_piece_verts = 0;
     for (uint32_t i = 0; i < n_pieces; i++) ctx->max_piece_verts = std::max(ctx->max_piece_verts, vert_off[i + 1] - vert_off[i]);
-    if (ev_piece_off && n_events) ctx->h_ev_piece_off.assign(ev_piece_off, ev_piece_off + n_events + 1);
-    else ctx->h_ev_piece_off = { 0u, n_pieces };
+    // the tile tables depend only on the event layout: an upload of the same shape (the steady state of a caller
+    // that streams events) keeps them, and with them the whole upload -> event sequence free of host synchronisation
+    std::vector<uint32_t> layout;
+    if (ev_piece_off && n_events) layout.assign(ev_piece_off, ev_piece_off + n_events + 1);
+    else layout = { 0u, n_pieces };
+    if (layout.back() != n_pieces) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at n_pieces");
+    if (layout != ctx->h_ev_piece_off)
+    {
+        ctx->h_ev_piece_off.swap(layout);
+        ctx->tables_dirty = true;
+    }
     ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
-    if (ctx->h_ev_piece_off.back() != n_pieces) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at n_pieces");
     ctx->have_pieces = true;
-    ctx->tables_dirty = true;
     ctx->event_launched = false;
     return SURTR_OK;
 }
@@ -550,12 +557,17 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
     }
     ctx->n_cells = n_cells;
     ctx->n_planes = np;
-    if (ev_cell_off && n_events) ctx->h_ev_cell_off.assign(ev_cell_off, ev_cell_off + n_events + 1);
-    else ctx->h_ev_cell_off = { 0u, n_cells };
+    std::vector<uint32_t> layout;
+    if (ev_cell_off && n_events) layout.assign(ev_cell_off, ev_cell_off + n_events + 1);
+    else layout = { 0u, n_cells };
+    if (layout.back() != n_cells) return fail(ctx, SURTR_ERR_INVALID, "ev_cell_off does not end at n_cells");
+    if (layout != ctx->h_ev_cell_off)
+    {
+        ctx->h_ev_cell_off.swap(layout);
+        ctx->tables_dirty = true;
+    }
     ctx->n_events_c = (uint32_t)ctx->h_ev_cell_off.size() - 1;
-    if (ctx->h_ev_cell_off.back() != n_cells) return fail(ctx, SURTR_ERR_INVALID, "ev_cell_off does not end at n_cells");
     ctx->have_cells = true;
-    ctx->tables_dirty = true;
     ctx->event_launched = false;
     return SURTR_OK;
 }
