@@ -730,6 +730,294 @@ void ref_config1_full(const float* verts4, uint32_t nv, const int32_t* indices, 
 	config1(verts4, nv, indices, n_idx, ich_limit, gap_inv, refit_limit, seeds, n_seeds, nb_off, nb_idx, out_ach, out, out_mesh);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Restatement of Surtr::DoFracture (Surtr.cpp:1885-1959) and the members it calls, which live in the DX12 application
+// class and cannot be compiled here: ApplyFracture with the partial mode (:2098-2149), the full m_fractureTask
+// (:1457-1504), SetExtract (:2151-2155), MergeOutOfImpact (:2368-2403), ConvexOutOfSphere (:2415-2458),
+// HandleConvexIsland (:2203-2366), m_refittingTask (:1449-1455).  Geometry is done by the reference's own compiled
+// Poly / Kdop / VMACH code.
+namespace
+{
+struct RPiece
+{
+	Poly::Polyhedron Convex, Mesh;
+};
+
+bool convex_out_of_sphere(const Poly::Polyhedron& polyhedron, const Poly::Extract* extract, const std::vector<Vector3>& cloud,
+						  const Vector3 origin, const float radius)
+{
+	for (const auto& v : polyhedron)
+		if ((origin - v.Position).Length() < radius)
+			return false;
+	for (const auto& po : cloud)
+	{
+		bool contain = true;
+		for (const auto& f : *extract)
+		{
+			Vector3 normal = (polyhedron[f[1]].Position - polyhedron[f[0]].Position).Cross(polyhedron[f[2]].Position - polyhedron[f[0]].Position);
+			normal.Normalize();
+			const float d = -polyhedron[f[0]].Position.Dot(normal);
+			const float dist = normal.Dot(po) + d;
+			if (dist > 0) { contain = false; break; }
+		}
+		if (contain)
+			return false;
+	}
+	return true;
+}
+
+bool face_point_inside(const std::vector<Vector3>& pts, const std::vector<Vector3>& outline, const Vector3& n)
+{
+	const int m = (int)outline.size();
+	for (const Vector3& p : pts)
+	{
+		bool included = true;
+		for (int v = 0; v < m; v++)
+			if (!VMACH::OnYourRight(outline[v], outline[(v + 1) % m], p, n)) { included = false; break; }
+		if (included)
+			return true;
+	}
+	return false;
+}
+
+void handle_convex_island(std::vector<std::set<int>>& bind, const std::vector<RPiece*>& pieces, const std::vector<Poly::Extract*>& extracts)
+{
+	struct FaceNode { int CID; double AbsD; Plane FacePlane; std::vector<Vector3> FacePoints; };
+	std::vector<std::set<int>> newBind;
+	for (auto& localBind : bind)
+	{
+		if (localBind.size() <= 1)
+			continue;
+		std::vector<FaceNode> nodes;
+		for (const int cid : localBind)
+			for (const auto& poly : *extracts[cid])
+			{
+				std::vector<Vector3> points;
+				for (const int v : poly)
+					points.push_back(pieces[cid]->Convex[v].Position);
+				Plane p(points[0], points[1], points[2]);
+				nodes.push_back(FaceNode{ cid, std::abs(p.D()), p, points });
+			}
+		std::sort(nodes.begin(), nodes.end(), [](const FaceNode& a, const FaceNode& b) { return a.AbsD < b.AbsD; });
+		std::unordered_map<int, std::set<int>> nei;
+		for (int i = 0; i + 1 < (int)nodes.size(); i++)
+		{
+			bool lowerBoundFound = false;
+			for (int j = i + 1; j < (int)nodes.size(); j++)   // quadratic, exactly as :2232-2318 (no window)
+			{
+				if (lowerBoundFound && nodes[i].AbsD > nodes[j].AbsD)
+					break;
+				if (std::abs(nodes[i].AbsD - nodes[j].AbsD) > 1e-3)
+					continue;
+				lowerBoundFound = true;
+				Vector3 in = nodes[i].FacePlane.Normal(), jn = nodes[j].FacePlane.Normal();
+				in.Normalize(); jn.Normalize();
+				if (!(std::abs(1 + in.Dot(jn)) < 1e-4))
+					continue;
+				if (face_point_inside(nodes[i].FacePoints, nodes[j].FacePoints, jn) || face_point_inside(nodes[j].FacePoints, nodes[i].FacePoints, in))
+				{
+					nei[nodes[i].CID].insert(nodes[j].CID);
+					nei[nodes[j].CID].insert(nodes[i].CID);
+				}
+			}
+		}
+		std::set<int> remain(localBind.begin(), localBind.end());
+		std::vector<std::set<int>> splitGroup;
+		while (!remain.empty())
+		{
+			std::set<int> split;
+			std::vector<int> queue{ *remain.begin() };
+			for (size_t q = 0; q < queue.size(); q++)
+			{
+				const int curr = queue[q];
+				if (remain.count(curr))
+				{
+					split.insert(curr);
+					remain.erase(curr);
+					for (const int a : nei[curr])
+						queue.push_back(a);
+				}
+			}
+			splitGroup.push_back(split);
+		}
+		if (splitGroup.size() >= 2)
+		{
+			localBind = splitGroup[0];
+			newBind.insert(newBind.end(), std::next(splitGroup.begin()), splitGroup.end());
+		}
+	}
+	bind.insert(bind.end(), newBind.begin(), newBind.end());
+}
+
+std::vector<VMACH::Polygon3D> unit_box_cells(const float* seeds, uint32_t n_seeds, const uint32_t* nb_off, const uint32_t* nb_idx)
+{
+	// cells of the unit container from neighbour bisectors, as VMACH::Polygon3D through PolygonFace::AddVertex
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n_seeds; i++)
+		s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	std::vector<VMACH::Polygon3D> out;
+	for (uint32_t i = 0; i < n_seeds; i++)
+	{
+		std::vector<Plane> planes;
+		for (uint32_t k = nb_off[i]; k < nb_off[i + 1]; k++)
+			planes.push_back(bisector(s[i], s[nb_idx[k]]));
+		Poly::Polyhedron cell = Poly::GetBB();
+		Poly::ClipPolyhedron(cell, planes);
+		Poly::Extract* faces = Poly::ExtractFaces(cell);
+		VMACH::Polygon3D poly(true);
+		for (const auto& loop : *faces)
+		{
+			VMACH::PolygonFace f(true);
+			for (int v : loop)
+				f.AddVertex(cell[v].Position);
+			poly.AddFace(f);
+		}
+		delete faces;
+		out.push_back(poly);
+	}
+	return out;
+}
+} // namespace
+
+// pieces: the target compound (convex_i, mesh_i) in world space.  pattern: seeds + neighbour CSR of the pattern cells
+// in the unit box.  cloud3: m_spherePointCloud (unit sphere samples, already scaled by 0.5 as at Surtr.cpp:1508).
+// Outputs in second.PieceVec order: Piece::Convex after Refitting (cell field = index of the bind set / compound the
+// piece ends up in, piece field = 1 when the piece is one of the caller's untouched pieces), Piece::Mesh likewise.
+void ref_do_fracture(const float* cverts, const uint32_t* cvert_off, const uint32_t* cring_off, const uint16_t* cring,
+					 const float* mverts, const uint32_t* mvert_off, const uint32_t* mring_off, const uint16_t* mring, uint32_t n_pieces,
+					 const float* seeds, uint32_t n_seeds, const uint32_t* nb_off, const uint32_t* nb_idx,
+					 const float* cloud3, uint32_t n_cloud, const float* impact3, float impact_radius, float max_axis_scale,
+					 int partial, int refit_limit, void* out_convex, void* out_mesh, uint32_t* n_compounds)
+{
+	std::vector<RPiece*> target;
+	std::vector<Poly::Extract*> targetExtract;
+	for (uint32_t i = 0; i < n_pieces; i++)
+	{
+		target.push_back(new RPiece{ to_poly(cverts, cvert_off, cring_off, cring, i), to_poly(mverts, mvert_off, mring_off, mring, i) });
+		targetExtract.push_back(Poly::ExtractFaces(target.back()->Convex));
+	}
+	const Vector3 impact(impact3[0], impact3[1], impact3[2]);
+	// DoFracture: pattern placement (:1887-1896) and sphere samples (:1911-1916)
+	std::vector<VMACH::Polygon3D> pattern = unit_box_cells(seeds, n_seeds, nb_off, nb_idx);
+	for (VMACH::Polygon3D& voro : pattern)
+		voro.Scale(Vector3(max_axis_scale, max_axis_scale, max_axis_scale) * 2);
+	for (VMACH::Polygon3D& voro : pattern)
+		voro.Translate(impact);
+	std::vector<Vector3> cloud;
+	for (uint32_t i = 0; i < n_cloud; i++)
+	{
+		Vector3 v(cloud3[3 * i], cloud3[3 * i + 1], cloud3[3 * i + 2]);
+		v *= impact_radius;
+		v += impact;
+		cloud.push_back(v);
+	}
+	// ApplyFracture (:2098-2149)
+	std::vector<RPiece*> decompose;
+	std::vector<std::set<int>> bind;
+	std::set<int> outside, outsideBind;
+	if (partial)
+		for (int c = 0; c < (int)target.size(); c++)
+			if (convex_out_of_sphere(target[c]->Convex, targetExtract[c], cloud, impact, impact_radius))
+			{
+				outside.insert(c);
+				outsideBind.insert((int)decompose.size());
+				decompose.push_back(target[c]);
+			}
+	const size_t n_untouched = decompose.size();
+	bind.push_back(outsideBind);
+	for (const VMACH::Polygon3D& voroPoly : pattern)
+	{
+		std::set<int> localBind;
+		for (int c = 0; c < (int)target.size(); c++)   // m_fractureTask (:1457-1504)
+		{
+			if (outside.count(c))
+				continue;
+			const Poly::Polyhedron convex = Poly::ClipPolyhedron(target[c]->Convex, voroPoly);
+			if (convex.empty())
+				continue;
+			const Poly::Polyhedron mesh = Poly::ClipPolyhedron(target[c]->Mesh, voroPoly);
+			if (mesh.empty())
+				continue;
+			const auto groupVec = check_mesh_island(mesh);
+			if (groupVec.size() >= 2)
+			{
+				for (const auto& group : groupVec)
+				{
+					Poly::Polyhedron island;
+					std::unordered_map<int, int> mapping;
+					for (const int iVert : group)
+					{
+						mapping[iVert] = (int)island.size();
+						island.push_back(mesh[iVert]);
+					}
+					for (auto& vert : island)
+						for (int& iAdj : vert.NeighborVertexVec)
+							iAdj = mapping[iAdj];
+					localBind.insert((int)decompose.size());
+					decompose.push_back(new RPiece{ convex, island });
+				}
+			}
+			else
+			{
+				localBind.insert((int)decompose.size());
+				decompose.push_back(new RPiece{ convex, mesh });
+			}
+		}
+		if (!localBind.empty())
+			bind.push_back(localBind);
+	}
+	// SetExtract
+	std::vector<Poly::Extract*> extracts;
+	for (const RPiece* p : decompose)
+		extracts.push_back(Poly::ExtractFaces(p->Convex));
+	// MergeOutOfImpact
+	if (partial)
+	{
+		for (size_t i = 1; i < bind.size(); i++)
+		{
+			std::set<int> out;
+			for (const int c : bind[i])
+				if (convex_out_of_sphere(decompose[c]->Convex, extracts[c], cloud, impact, impact_radius))
+					out.insert(c);
+			for (const int c : out)
+			{
+				bind[i].erase(c);
+				bind[0].insert(c);
+			}
+		}
+		bind.erase(std::remove_if(std::next(bind.begin()), bind.end(), [](const std::set<int>& b) { return b.empty(); }), bind.end());
+	}
+	handle_convex_island(bind, decompose, extracts);
+	// Refitting (m_refittingTask) on every piece
+	for (RPiece* piece : decompose)
+	{
+		std::vector<Vector3> pts;
+		for (const Poly::Vertex& v : piece->Mesh)
+			pts.push_back(v.Position);
+		VMACH::ConvexHull ich(pts, (uint32_t)std::min((int)pts.size(), refit_limit));
+		std::vector<Vector3> nrm;
+		for (const VMACH::ConvexHullFace& f : ich.GetFaces())
+		{
+			Vector3 normal = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+			normal.Normalize();
+			nrm.push_back(normal);
+		}
+		Kdop::KdopContainer kdop(nrm);
+		kdop.Calc(piece->Mesh);
+		piece->Convex = kdop.ClipWithPolyhedron(piece->Convex);
+	}
+	std::vector<uint32_t> compound_of(decompose.size(), 0xffffffffu);
+	for (size_t b = 0; b < bind.size(); b++)
+		for (const int c : bind[b])
+			compound_of[c] = (uint32_t)b;
+	*n_compounds = (uint32_t)bind.size();
+	for (size_t i = 0; i < decompose.size(); i++)
+	{
+		append(*(PolySet*)out_convex, decompose[i]->Convex, compound_of[i], i < n_untouched ? 1u : 0u);
+		append(*(PolySet*)out_mesh, decompose[i]->Mesh, compound_of[i], i < n_untouched ? 1u : 0u);
+	}
+}
+
 // Triangle mesh -> vertex-ring polyhedron, as PrepareFracture step 7 does (Surtr.cpp:1788-1795):
 // Poly::ExtractNeighborFromMesh (Poly.cpp:128-263) + InitPolyhedron.  Returns 0, or 1 if the reference throws
 // (asymmetric adjacency, Poly.cpp:253-260).

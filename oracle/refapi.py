@@ -45,6 +45,9 @@ def lib():
         _lib.ref_mesh_polyhedron.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.ref_config1_full.argtypes = ([C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                            C.c_uint32] + [C.c_void_p] * 5)
+        _lib.ref_do_fracture.argtypes = ([C.c_void_p] * 8 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_uint32, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p])
         _lib.ref_seeds_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.ref_seeds_radial.argtypes = [C.c_uint32, C.c_uint32, C.c_double, C.c_void_p]
         _lib.ref_unit_cube.argtypes = [C.c_void_p]
@@ -318,3 +321,20 @@ def config1_full(verts4, indices, seeds, nb_off, nb_idx, ich_limit=20, gap_inv=2
     L.ref_config1_full(_p(verts4), len(verts4), _p(indices), len(indices), ich_limit, gap_inv, refit_limit, _p(seeds), len(seeds),
                        _p(nb_off), _p(nb_idx), ha, hc, hm)
     return _export(ha), _export(hc), _export(hm)
+
+
+def do_fracture(convex: PolySet, mesh: PolySet, seeds, nb_off, nb_idx, cloud, impact, impact_radius, max_axis_scale,
+                partial: bool, refit_limit: int = 4):
+    """Surtr::DoFracture (Surtr.cpp:1885-1959) on one compound.  Returns (Piece::Convex set, Piece::Mesh set,
+    number of compounds); .cell = compound index of every piece, .piece = 1 for the caller's untouched pieces."""
+    seeds, cloud = np.ascontiguousarray(seeds, np.float32), np.ascontiguousarray(cloud, np.float32)
+    nb_off, nb_idx = np.ascontiguousarray(nb_off, np.uint32), np.ascontiguousarray(nb_idx, np.uint32)
+    impact = np.ascontiguousarray(impact, np.float32)
+    L = lib()
+    hc, hm = L.ref_polyset_new(), L.ref_polyset_new()
+    ncomp = C.c_uint32(0)
+    L.ref_do_fracture(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring),
+                      _p(mesh.verts), _p(mesh.vert_off), _p(mesh.ring_off), _p(mesh.ring), convex.n,
+                      _p(seeds), len(seeds), _p(nb_off), _p(nb_idx), _p(cloud), len(cloud), _p(impact),
+                      impact_radius, max_axis_scale, int(partial), refit_limit, hc, hm, C.byref(ncomp))
+    return _export(hc), _export(hm), ncomp.value

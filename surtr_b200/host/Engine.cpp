@@ -47,6 +47,21 @@ void FlatCells::add(const VMACH::Polygon3D& cell)
 	cvert_off.push_back((uint32_t)(cverts4.size() / 4));
 }
 
+void FlatCells::add_keep_all()
+{
+	// bounds only (the clipper never reads cell vertices): the eight corners of a box that contains any finite piece,
+	// so that every slab direction of the broad phase sees the full range
+	for (int k = 0; k < 8; k++)
+	{
+		cverts4.push_back((k & 1) ? 1.0e30f : -1.0e30f);
+		cverts4.push_back((k & 2) ? 1.0e30f : -1.0e30f);
+		cverts4.push_back((k & 4) ? 1.0e30f : -1.0e30f);
+		cverts4.push_back(0.f);
+	}
+	plane_off.push_back((uint32_t)(planes4.size() / 4));
+	cvert_off.push_back((uint32_t)(cverts4.size() / 4));
+}
+
 void FlatCells::add(const std::vector<Poly::Plane>& planes)
 {
 	for (const Poly::Plane& p : planes)
@@ -104,10 +119,13 @@ void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, 
 {
 	surtr_ctx* c = context();
 	check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
-							  pieces.count(), nullptr, 0), "surtr_upload_pieces");
+							  pieces.count(), pieces.ev_off.empty() ? nullptr : pieces.ev_off.data(),
+							  pieces.ev_off.empty() ? 0u : (uint32_t)pieces.ev_off.size() - 1), "surtr_upload_pieces");
 	if (upload_cells)
 		check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
-								 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(), nullptr, 0), "surtr_upload_cells");
+								 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(),
+								 cells.ev_off.empty() ? nullptr : cells.ev_off.data(),
+								 cells.ev_off.empty() ? 0u : (uint32_t)cells.ev_off.size() - 1), "surtr_upload_cells");
 	check(surtr_fracture_event(c), "surtr_fracture_event");
 	surtr_counts n;
 	check(surtr_event_counts(c, &n), "surtr_event_counts");

@@ -18,6 +18,7 @@ struct FlatPolys
 	std::vector<float> verts4;
 	std::vector<uint32_t> vert_off{ 0 }, ring_off{ 0 };
 	std::vector<uint16_t> ring;
+	std::vector<uint32_t> ev_off;     // optional: independent events in one batch (empty = one event)
 	void add(const Poly::Polyhedron& p);
 	uint32_t count() const { return (uint32_t)vert_off.size() - 1; }
 };
@@ -29,7 +30,9 @@ struct FlatCells
 	std::vector<float> cverts4;       // every vertex of every face loop (bounds for the broad phase)
 	std::vector<uint32_t> cvert_off{ 0 };
 	bool bounded = true;
+	std::vector<uint32_t> ev_off;     // optional, as in FlatPolys
 	void add(const VMACH::Polygon3D& cell);
+	void add_keep_all();              // a cell without planes whose bounds contain everything: returns pieces uncut
 	void add(const std::vector<Poly::Plane>& planes);   // unbounded cell (plain plane list)
 	uint32_t count() const { return (uint32_t)plane_off.size() - 1; }
 };

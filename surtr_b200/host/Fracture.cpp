@@ -6,6 +6,7 @@
 #include "Kdop.h"
 
 #include <algorithm>
+#include <map>
 #include <random>
 
 namespace SurtrHost
@@ -94,7 +95,7 @@ static PreparedObject prepare(const std::vector<Vector3>& vertices, const std::v
 	r.Initial = ApplyFracture(pre, r.Cells, indices != nullptr);
 	if (indices)
 	{
-		Refitting(r.Initial.PieceVec, args);
+		Refitting(r.Initial.PieceVec, args, &r.Initial.PieceMass);
 		SetExtract(r.Initial);
 	}
 	return r;
@@ -143,35 +144,128 @@ std::vector<std::set<int>> CheckMeshIsland(const Poly::Polyhedron& polyhedron)
 	return groupVec;
 }
 
+bool ConvexOutOfSphere(const Poly::Polyhedron& polyhedron, const Extract* extract, const std::vector<Vector3>& spherePointCloud,
+					   const Vector3 origin, const float radius)
+{
+	// approximate test of Surtr.cpp:2415-2458: no vertex inside the sphere, and no sample point of the sphere's
+	// surface inside the convex
+	for (const Poly::Vertex& v : polyhedron)
+		if ((origin - v.Position).Length() < radius)
+			return false;
+	std::vector<Vector3> normals;
+	std::vector<float> offsets;
+	for (const std::vector<int>& f : *extract)   // hoisted out of the point loop; same values, same order per point
+	{
+		Vector3 normal = (polyhedron[f[1]].Position - polyhedron[f[0]].Position).Cross(polyhedron[f[2]].Position - polyhedron[f[0]].Position);
+		normal.Normalize();
+		normals.push_back(normal);
+		offsets.push_back(-polyhedron[f[0]].Position.Dot(normal));
+	}
+	for (const Vector3& po : spherePointCloud)
+	{
+		bool contain = true;
+		for (size_t k = 0; k < normals.size(); k++)
+		{
+			const float dist = normals[k].Dot(po) + offsets[k];
+			if (dist > 0)
+			{
+				contain = false;
+				break;
+			}
+		}
+		if (contain)
+			return false;
+	}
+	return true;
+}
+
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch)
 {
+	return ApplyFracture(compound, voroPolyVec, std::vector<Vector3>(), false, FractureArgs(), meshBranch);
+}
+
+CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec,
+						   const std::vector<Vector3>& spherePointCloud, bool partial, const FractureArgs& args, bool meshBranch)
+{
+	const std::vector<Piece*>& targetPieceVec = compound.PieceVec;
+	// pieces that lie outside the impact sphere are not cut (Surtr.cpp:2109-2124)
+	std::vector<int> inside, outside;
+	for (int c = 0; c < (int)targetPieceVec.size(); c++)
+	{
+		bool out = false;
+		if (partial)
+		{
+			const Extract* extract = c < (int)compound.PieceExtractedConvex.size() ? compound.PieceExtractedConvex[c] : nullptr;
+			Extract* own = extract ? nullptr : Poly::ExtractFaces(targetPieceVec[c]->Convex);
+			out = ConvexOutOfSphere(targetPieceVec[c]->Convex, extract ? extract : own, spherePointCloud, args.ImpactPosition, args.ImpactRadius);
+			delete own;
+		}
+		(out ? outside : inside).push_back(c);
+	}
+	const uint32_t n_in = (uint32_t)inside.size(), n_out = (uint32_t)outside.size(), n_cells = (uint32_t)voroPolyVec.size();
+
+	// One batch: event 0 = pieces inside the sphere x the cells (one task per cell in the reference, :2129-2131);
+	// event 1 = the untouched pieces x one cell without planes, which hands them back uncut -- only so that K3/K4
+	// compute their face counts and mass properties in the same launches.
 	detail::FlatPolys pieces;
-	for (const Piece* p : compound.PieceVec)
-		pieces.add(p->Convex);
+	for (const int c : inside)
+		pieces.add(targetPieceVec[c]->Convex);
+	for (const int c : outside)
+		pieces.add(targetPieceVec[c]->Convex);
 	detail::FlatCells cells;
 	for (const VMACH::Polygon3D& cell : voroPolyVec)
 		cells.add(cell);
+	if (n_out)
+	{
+		cells.add_keep_all();
+		pieces.ev_off = { 0u, n_in, n_in + n_out };
+		cells.ev_off = { 0u, n_cells, n_cells + 1u };
+	}
 	detail::Fragments fr, mfr;
 	detail::run_event(pieces, cells, fr);
-	if (meshBranch)
+	if (meshBranch && n_in)
 	{
 		// second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident cells, one more
 		// GPU event.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
 		// its convex and its mesh fragment exist (:1466-1472).
 		detail::FlatPolys meshes;
-		for (const Piece* p : compound.PieceVec)
-			meshes.add(p->Mesh);
+		for (const int c : inside)
+			meshes.add(targetPieceVec[c]->Mesh);
+		if (n_out)
+			meshes.ev_off = { 0u, n_in, n_in };
 		detail::run_event(meshes, cells, mfr, true, false);
 	}
 
 	CompoundInfo info;
-	info.CompoundBind.push_back(std::set<int>());   // 0-th element is reserved (Surtr.cpp:2126)
+	const auto mass_of = [](const surtr_fragment& r) {
+		MassProperties mp;
+		mp.Volume = r.volume;
+		mp.Centroid = Vector3(r.centroid[0], r.centroid[1], r.centroid[2]);
+		std::copy(r.inertia, r.inertia + 6, mp.Inertia);
+		mp.FaceCount = r.n_faces;
+		return mp;
+	};
+	// untouched pieces first, bound together in the reserved 0-th set (Surtr.cpp:2116-2126)
+	info.CompoundBind.push_back(std::set<int>());
+	for (uint32_t k = 0; k < n_out; k++)
+	{
+		info.CompoundBind[0].insert((int)info.PieceVec.size());
+		info.PieceVec.push_back(targetPieceVec[outside[k]]);
+		info.PieceMass.push_back(MassProperties());
+		info.PieceSourceCell.push_back(-1);
+		info.PieceSourcePiece.push_back(outside[k]);
+	}
 	int current_cell = -1;
 	size_t m = 0;
 	const auto key = [](const surtr_fragment& r) { return ((uint64_t)r.cell << 32) | r.piece; };
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
 		const surtr_fragment& r = fr.rec[f];
+		if (r.cell >= n_cells)   // event 1: the uncut piece itself, only its record is of interest
+		{
+			info.PieceMass[r.piece - n_in] = mass_of(r);
+			continue;
+		}
 		const Poly::Polyhedron convex = fr.polyhedron(f);
 		std::vector<Poly::Polyhedron> meshes;
 		if (meshBranch)
@@ -213,20 +307,215 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 			}
 			info.CompoundBind.back().insert((int)info.PieceVec.size());
 			info.PieceVec.push_back(new Piece(convex, mesh));
-			MassProperties mp;
-			mp.Volume = r.volume;
-			mp.Centroid = Vector3(r.centroid[0], r.centroid[1], r.centroid[2]);
-			std::copy(r.inertia, r.inertia + 6, mp.Inertia);
-			mp.FaceCount = r.n_faces;
-			info.PieceMass.push_back(mp);
+			info.PieceMass.push_back(mass_of(r));
 			info.PieceSourceCell.push_back((int)r.cell);
-			info.PieceSourcePiece.push_back((int)r.piece);
+			info.PieceSourcePiece.push_back(inside[r.piece]);
 		}
 	}
 	return info;
 }
 
-void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args)
+void SetExtract(CompoundInfo& preResult)
+{
+	for (Extract* e : preResult.PieceExtractedConvex)
+		delete e;   // the reference leaks the previous lists (Surtr.cpp:2151-2155 overwrites the pointers)
+	preResult.PieceExtractedConvex.assign(preResult.PieceVec.size(), nullptr);
+	for (size_t i = 0; i < preResult.PieceVec.size(); i++)
+		preResult.PieceExtractedConvex[i] = Poly::ExtractFaces(preResult.PieceVec[i]->Convex);
+}
+
+void MergeOutOfImpact(CompoundInfo& compoundInfo, const std::vector<Vector3>& spherePointCloud, const FractureArgs& args)
+{
+	// Surtr.cpp:2368-2403; the 0-th set is skipped, emptied sets are dropped
+	for (size_t i = 1; i < compoundInfo.CompoundBind.size(); i++)
+	{
+		std::set<int>& local = compoundInfo.CompoundBind[i];
+		std::set<int> outside;
+		for (const int c : local)
+			if (ConvexOutOfSphere(compoundInfo.PieceVec[c]->Convex, compoundInfo.PieceExtractedConvex[c], spherePointCloud,
+								  args.ImpactPosition, args.ImpactRadius))
+				outside.insert(c);
+		for (const int c : outside)
+		{
+			local.erase(c);
+			compoundInfo.CompoundBind[0].insert(c);
+		}
+	}
+	compoundInfo.CompoundBind.erase(std::remove_if(std::next(compoundInfo.CompoundBind.begin()), compoundInfo.CompoundBind.end(),
+												   [](const std::set<int>& local) { return local.empty(); }),
+									compoundInfo.CompoundBind.end());
+}
+
+void HandleConvexIsland(CompoundInfo& compoundInfo)
+{
+	// Surtr.cpp:2203-2366.  Two pieces of a bind set are neighbours when they own a pair of faces with (almost) the same
+	// plane offset, opposite normals and overlapping outlines; every bind set is split into its connected groups.
+	struct FaceNode
+	{
+		int CID;
+		double AbsD;
+		Vector3 Normal;   // FacePlane.Normal(), normalised once (the reference renormalises per pair: same value)
+		std::vector<Vector3> FacePoints;
+	};
+	const auto any_point_inside = [](const FaceNode& of, const FaceNode& in) {
+		const int n = (int)in.FacePoints.size();
+		for (const Vector3& p : of.FacePoints)
+		{
+			bool included = true;
+			for (int v = 0; v < n && included; v++)
+				included = VMACH::OnYourRight(in.FacePoints[v], in.FacePoints[(v + 1) % n], p, in.Normal);
+			if (included)
+				return true;
+		}
+		return false;
+	};
+
+	std::vector<std::set<int>> newBind;
+	for (std::set<int>& localBind : compoundInfo.CompoundBind)
+	{
+		if (localBind.size() <= 1)
+			continue;
+		std::vector<FaceNode> nodes;
+		for (const int cid : localBind)
+			for (const std::vector<int>& poly : *compoundInfo.PieceExtractedConvex[cid])
+			{
+				FaceNode node;
+				node.CID = cid;
+				for (const int v : poly)
+					node.FacePoints.push_back(compoundInfo.PieceVec[cid]->Convex[v].Position);
+				const DirectX::SimpleMath::Plane p(node.FacePoints[0], node.FacePoints[1], node.FacePoints[2]);
+				node.AbsD = std::abs(p.D());
+				node.Normal = p.Normal();
+				node.Normal.Normalize();
+				nodes.push_back(std::move(node));
+			}
+		// sorted by offset, so that the candidates of a face are one contiguous window instead of every later face
+		// (the reference's early exit at :2237 never fires on a sorted list, its scan is quadratic)
+		std::sort(nodes.begin(), nodes.end(), [](const FaceNode& a, const FaceNode& b) { return a.AbsD < b.AbsD; });
+		std::map<int, std::set<int>> nei;
+		for (size_t i = 0; i + 1 < nodes.size(); i++)
+			for (size_t j = i + 1; j < nodes.size(); j++)
+			{
+				if (std::abs(nodes[i].AbsD - nodes[j].AbsD) > 1e-3)
+					break;   // later faces are farther still
+				if (!(std::abs(1 + nodes[i].Normal.Dot(nodes[j].Normal)) < 1e-4))
+					continue;
+				if (any_point_inside(nodes[i], nodes[j]) || any_point_inside(nodes[j], nodes[i]))
+				{
+					nei[nodes[i].CID].insert(nodes[j].CID);
+					nei[nodes[j].CID].insert(nodes[i].CID);
+				}
+			}
+		// flood fill (:2321-2350): groups come out by their lowest remaining piece id
+		std::set<int> remain(localBind.begin(), localBind.end());
+		std::vector<std::set<int>> splitGroup;
+		while (!remain.empty())
+		{
+			std::set<int> split;
+			std::vector<int> stack{ *remain.begin() };
+			while (!stack.empty())
+			{
+				const int curr = stack.back();
+				stack.pop_back();
+				if (remain.erase(curr))
+				{
+					split.insert(curr);
+					for (const int iAdj : nei[curr])
+						stack.push_back(iAdj);
+				}
+			}
+			splitGroup.push_back(std::move(split));
+		}
+		if (splitGroup.size() >= 2)
+		{
+			localBind = splitGroup[0];
+			newBind.insert(newBind.end(), std::next(splitGroup.begin()), splitGroup.end());
+		}
+	}
+	compoundInfo.CompoundBind.insert(compoundInfo.CompoundBind.end(), newBind.begin(), newBind.end());
+}
+
+std::vector<VMACH::Polygon3D> GenerateFracturePattern(int seed, int cellCount, double mean)
+{
+	return GenerateVoronoi(GenerateRadialSeeds(seed, cellCount, mean));
+}
+
+std::vector<Compound> DoFracture(const Compound& targetCompound, const FractureStorage& storage, const std::vector<Vector3>& spherePointCloud,
+								 const FractureArgs& args, CompoundInfo* out_info)
+{
+	// Surtr.cpp:1885-1959
+	std::vector<VMACH::Polygon3D> localFracturePattern = args.PartialFracture ? storage.PartialFracturePattern : storage.GeneralFracturePattern;
+	std::vector<Vector3> localSpherePointCloud = spherePointCloud;
+	for (VMACH::Polygon3D& voro : localFracturePattern)
+		voro.Scale(Vector3(storage.MaxAxisScale, storage.MaxAxisScale, storage.MaxAxisScale) * 2);
+	for (VMACH::Polygon3D& voro : localFracturePattern)
+		voro.Translate(args.ImpactPosition);
+	for (Vector3& v : localSpherePointCloud)
+	{
+		v *= args.ImpactRadius;
+		v += args.ImpactPosition;
+	}
+	CompoundInfo second = ApplyFracture(targetCompound, localFracturePattern, localSpherePointCloud, args.PartialFracture, args);
+	SetExtract(second);
+	if (args.PartialFracture)
+		MergeOutOfImpact(second, localSpherePointCloud, args);
+	HandleConvexIsland(second);
+	Refitting(second.PieceVec, args, &second.PieceMass);
+	SetExtract(second);
+
+	std::vector<Compound> result;
+	for (const std::set<int>& iComp : second.CompoundBind)
+	{
+		Compound c;
+		for (const int iPiece : iComp)
+		{
+			c.PieceVec.push_back(second.PieceVec[iPiece]);
+			c.PieceExtractedConvex.push_back(second.PieceExtractedConvex[iPiece]);
+		}
+		result.push_back(std::move(c));
+	}
+	if (out_info)
+		*out_info = second;
+	return result;
+}
+
+MassProperties CombineMass(const std::vector<MassProperties>& pieces, float density)
+{
+	// what PxRigidBodyExt::updateMassAndInertia(body, density) (Surtr.cpp:2520) derives from the compound's shapes:
+	// total mass, centre of mass, and the inertia tensor about it by the parallel-axis theorem.  `Volume` of the result
+	// holds the MASS; `Inertia` is scaled by the density.
+	MassProperties total;
+	double mass = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+	for (const MassProperties& p : pieces)
+	{
+		const double m = density * p.Volume;
+		mass += m;
+		cx += m * p.Centroid.x; cy += m * p.Centroid.y; cz += m * p.Centroid.z;
+	}
+	if (mass == 0.0)
+		return total;
+	cx /= mass; cy /= mass; cz /= mass;
+	double I[6] = { 0, 0, 0, 0, 0, 0 };
+	for (const MassProperties& p : pieces)
+	{
+		const double m = density * p.Volume;
+		const double dx = p.Centroid.x - cx, dy = p.Centroid.y - cy, dz = p.Centroid.z - cz;
+		I[0] += density * p.Inertia[0] + m * (dy * dy + dz * dz);
+		I[1] += density * p.Inertia[1] + m * (dx * dx + dz * dz);
+		I[2] += density * p.Inertia[2] + m * (dx * dx + dy * dy);
+		I[3] += density * p.Inertia[3] - m * dx * dy;
+		I[4] += density * p.Inertia[4] - m * dx * dz;
+		I[5] += density * p.Inertia[5] - m * dy * dz;
+		total.FaceCount += p.FaceCount;
+	}
+	total.Volume = mass;
+	total.Centroid = Vector3((float)cx, (float)cy, (float)cz);
+	for (int k = 0; k < 6; k++)
+		total.Inertia[k] = (float)I[k];
+	return total;
+}
+
+void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, std::vector<MassProperties>* mass)
 {
 	const uint32_t n = (uint32_t)targetPieceVec.size();
 	if (!n)
@@ -286,14 +575,21 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args)
 	detail::check(surtr_download_fragments(c, fr.rec.data(), fr.verts4.data(), fr.ring_off.data(), fr.ring.data()), "surtr_download_fragments");
 	for (Piece* p : targetPieceVec)
 		p->Convex.clear();
+	if (mass)
+		mass->assign(n, MassProperties());   // a convex that the refit clips away has no mass left
 	for (size_t f = 0; f < fr.rec.size(); f++)
-		targetPieceVec[fr.rec[f].piece]->Convex = fr.polyhedron(f);
+	{
+		const surtr_fragment& r = fr.rec[f];
+		targetPieceVec[r.piece]->Convex = fr.polyhedron(f);
+		if (mass)
+		{
+			MassProperties& mp = (*mass)[r.piece];
+			mp.Volume = r.volume;
+			mp.Centroid = Vector3(r.centroid[0], r.centroid[1], r.centroid[2]);
+			std::copy(r.inertia, r.inertia + 6, mp.Inertia);
+			mp.FaceCount = r.n_faces;
+		}
+	}
 }
 
-void SetExtract(CompoundInfo& preResult)
-{
-	preResult.PieceExtractedConvex.resize(preResult.PieceVec.size(), nullptr);
-	std::transform(preResult.PieceVec.begin(), preResult.PieceVec.end(), preResult.PieceExtractedConvex.begin(),
-				   [](const Piece* p) { return Poly::ExtractFaces(p->Convex); });
-}
 } // namespace SurtrHost

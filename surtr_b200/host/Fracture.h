@@ -95,9 +95,36 @@ PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::
 PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::vector<int>& indices, const std::vector<Vector3>& seeds,
 							   const FractureArgs& args = FractureArgs());
 
-// Surtr::ApplyFracture, non-partial.  meshBranch = false skips the second clip and hands every piece its convex as mesh.
+// Surtr::ApplyFracture (Surtr.cpp:2098-2149).  partial = true keeps the pieces that ConvexOutOfSphere puts outside the
+// impact sphere uncut, first in PieceVec and bound in CompoundBind[0] (they are the caller's Piece objects, not copies).
+// meshBranch = false skips the second clip and hands every piece its convex as mesh.
 // Throws std::runtime_error on a C-ABI failure.
+CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec,
+						   const std::vector<Vector3>& spherePointCloud, bool partial, const FractureArgs& args = FractureArgs(),
+						   bool meshBranch = true);
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch = true);
+// Surtr::ConvexOutOfSphere (Surtr.cpp:2415-2458), MergeOutOfImpact (:2368-2403), HandleConvexIsland (:2203-2366).
+bool ConvexOutOfSphere(const Poly::Polyhedron& polyhedron, const Extract* extract, const std::vector<Vector3>& spherePointCloud,
+					   const Vector3 origin, const float radius);
+void MergeOutOfImpact(CompoundInfo& compoundInfo, const std::vector<Vector3>& spherePointCloud, const FractureArgs& args = FractureArgs());
+void HandleConvexIsland(CompoundInfo& compoundInfo);
+// Surtr::GenerateFracturePattern (Surtr.cpp:2072-2096): radial seeds -> cells in the unit box.
+std::vector<VMACH::Polygon3D> GenerateFracturePattern(int seed, int cellCount, double mean);
+
+struct FractureStorage   // the members of Inc/Surtr.h:136-155 that DoFracture reads
+{
+	float MaxAxisScale = 1.f;
+	std::vector<VMACH::Polygon3D> PartialFracturePattern, GeneralFracturePattern;
+};
+// Surtr::DoFracture (Surtr.cpp:1885-1959): place the pattern at the impact point (scale 2 x MaxAxisScale), ApplyFracture,
+// SetExtract, [MergeOutOfImpact], HandleConvexIsland, Refitting, SetExtract -> one Compound per bind set (the reserved 0-th
+// set included, even when empty, as in the reference).  The pieces are expected in world space (ExecuteFractureRoutine
+// transforms them first, :1846-1852; use Poly::Transform).  out_info receives the flat piece list with its mass properties.
+std::vector<Compound> DoFracture(const Compound& targetCompound, const FractureStorage& storage, const std::vector<Vector3>& spherePointCloud,
+								 const FractureArgs& args = FractureArgs(), CompoundInfo* out_info = nullptr);
+// Mass, centre of mass and inertia about it of a compound of pieces at uniform density (parallel-axis theorem): the
+// quantities PxRigidBodyExt::updateMassAndInertia(body, 10.0f) derives at Surtr.cpp:2520.  Result.Volume holds the mass.
+MassProperties CombineMass(const std::vector<MassProperties>& pieces, float density = 10.0f);
 // Surtr::CheckMeshIsland (Surtr.cpp:2171-2199): connected components of the ring graph.
 std::vector<std::set<int>> CheckMeshIsland(const Poly::Polyhedron& polyhedron);
 // Surtr::SetExtract (Surtr.cpp:2151-2155).
@@ -106,5 +133,5 @@ void SetExtract(CompoundInfo& preResult);
 // piece->Mesh (<= RefittingPointLimit points, host, VMACH::ConvexHull) -> k-DOP extents of piece->Mesh (one batched GPU
 // call) -> piece->Convex clipped by its own [Min0, Max0, Min1, ...] plane list (one GPU event, one (piece, cell) pair per
 // piece).  A piece whose convex is clipped away ends up with an empty Convex, as in the reference.
-void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args = FractureArgs());
+void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args = FractureArgs(), std::vector<MassProperties>* mass = nullptr);
 } // namespace SurtrHost

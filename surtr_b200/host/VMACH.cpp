@@ -100,4 +100,5 @@ Polygon3D GetBoxPolygon()
 	}
 	return box;
 }
+bool OnYourRight(const Vector3& a, const Vector3& b, const Vector3& c, const Vector3& n) { return (b - a).Cross(c - a).Dot(n) > 0; }
 } // namespace VMACH

@@ -56,4 +56,6 @@ struct Polygon3D   // Inc/VMACH.h:60-86
 };
 
 Polygon3D GetBoxPolygon();   // the six outward planes of the unit cube (VMACH.cpp:1207-1226)
+// (b - a) x (c - a) . n > 0 (VMACH.cpp:1240-1243): c lies to the left of a->b seen against n
+bool OnYourRight(const Vector3& a, const Vector3& b, const Vector3& c, const Vector3& n);
 } // namespace VMACH

@@ -331,6 +331,77 @@ int hosttest_apply_fracture_mesh(const float* cv, const uint32_t* cvo, const uin
 	catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
 
+// SurtrHost::CombineMass (CPU only): per piece volume, centroid[3], inertia[6] -> {mass, c[3], I[6]}
+void hosttest_combine_mass(uint32_t n, const double* volume, const float* centroid3, const float* inertia6, float density, float* out10)
+{
+	std::vector<SurtrHost::MassProperties> parts(n);
+	for (uint32_t i = 0; i < n; i++)
+	{
+		parts[i].Volume = volume[i];
+		parts[i].Centroid = Vector3(centroid3[3 * i], centroid3[3 * i + 1], centroid3[3 * i + 2]);
+		std::memcpy(parts[i].Inertia, inertia6 + 6 * i, 6 * sizeof(float));
+	}
+	const SurtrHost::MassProperties m = SurtrHost::CombineMass(parts, density);
+	const float row[10] = { (float)m.Volume, m.Centroid.x, m.Centroid.y, m.Centroid.z, m.Inertia[0], m.Inertia[1], m.Inertia[2],
+							m.Inertia[3], m.Inertia[4], m.Inertia[5] };
+	std::memcpy(out10, row, sizeof(row));
+}
+
+// SurtrHost::DoFracture on one compound (convex_i, mesh_i).  g_out / g_mesh = Piece::Convex / Piece::Mesh in PieceVec order;
+// cell = index of the compound (bind set) a piece ends up in, piece = 1 for the caller's untouched pieces.
+// mass10 (optional, 10 floats per compound): CombineMass at density 10 = {mass, cx, cy, cz, Ixx, Iyy, Izz, Ixy, Ixz, Iyz}.
+int hosttest_do_fracture(const float* cv, const uint32_t* cvo, const uint32_t* cro, const uint16_t* cr,
+						 const float* mv, const uint32_t* mvo, const uint32_t* mro, const uint16_t* mr, uint32_t n_pieces,
+						 const float* seeds, uint32_t n_seeds, const float* cloud3, uint32_t n_cloud, const float* impact3,
+						 float impact_radius, float max_axis_scale, int partial, uint32_t* n_compounds, float* mass10, uint32_t mass_cap)
+{
+	try
+	{
+		SurtrHost::Compound compound;
+		for (uint32_t i = 0; i < n_pieces; i++)
+		{
+			compound.PieceVec.push_back(new SurtrHost::Piece(to_poly(cv, cro, cr, cvo[i], cvo[i + 1]), to_poly(mv, mro, mr, mvo[i], mvo[i + 1])));
+			compound.PieceExtractedConvex.push_back(Poly::ExtractFaces(compound.PieceVec.back()->Convex));
+		}
+		std::vector<Vector3> ss, cloud;
+		for (uint32_t i = 0; i < n_seeds; i++) ss.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+		for (uint32_t i = 0; i < n_cloud; i++) cloud.emplace_back(cloud3[3 * i], cloud3[3 * i + 1], cloud3[3 * i + 2]);
+		SurtrHost::FractureStorage storage;
+		storage.MaxAxisScale = max_axis_scale;
+		storage.PartialFracturePattern = storage.GeneralFracturePattern = SurtrHost::GenerateVoronoi(ss);
+		SurtrHost::FractureArgs args;
+		args.ImpactPosition = DirectX::XMFLOAT3(impact3[0], impact3[1], impact3[2]);
+		args.ImpactRadius = impact_radius;
+		args.PartialFracture = partial != 0;
+		SurtrHost::CompoundInfo info;
+		const std::vector<SurtrHost::Compound> result = SurtrHost::DoFracture(compound, storage, cloud, args, &info);
+		*n_compounds = (uint32_t)result.size();
+		std::vector<uint32_t> compound_of(info.PieceVec.size(), 0xffffffffu);
+		for (size_t b = 0; b < info.CompoundBind.size(); b++)
+			for (const int c : info.CompoundBind[b])
+				compound_of[c] = (uint32_t)b;
+		export_pieces(info);
+		for (Out* o : { &g_out, &g_mesh })
+			for (size_t i = 0; i < info.PieceVec.size(); i++)
+			{
+				o->cell[i] = compound_of[i];
+				o->piece[i] = info.PieceSourceCell[i] < 0 ? 1u : 0u;
+			}
+		for (size_t b = 0; b < result.size() && mass10 && b < mass_cap; b++)
+		{
+			std::vector<SurtrHost::MassProperties> parts;
+			for (const int c : info.CompoundBind[b])
+				parts.push_back(info.PieceMass[c]);
+			const SurtrHost::MassProperties m = SurtrHost::CombineMass(parts, 10.0f);
+			const float row[10] = { (float)m.Volume, m.Centroid.x, m.Centroid.y, m.Centroid.z, m.Inertia[0], m.Inertia[1], m.Inertia[2],
+									m.Inertia[3], m.Inertia[4], m.Inertia[5] };
+			std::memcpy(mass10 + 10 * b, row, sizeof(row));
+		}
+		return 0;
+	}
+	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
 // SurtrHost::PrepareFracture in full (mesh polyhedron, mesh branch, Refitting, SetExtract)
 int hosttest_config1_full(const float* verts4, uint32_t nv, const int32_t* indices, uint32_t n_idx, const float* seeds, uint32_t n_seeds,
 						  uint32_t* ach_nv)

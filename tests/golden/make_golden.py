@@ -264,6 +264,36 @@ def config1_full_fixture():
           "mesh verts", mesh.nverts[:6], "empty convex after refit", int((convex.nverts == 0).sum()))
 
 
+def do_fracture_fixture():
+    """Row f-3: Surtr::DoFracture (Surtr.cpp:1885-1959) on the compound PrepareFracture produced for the bunny (the 27
+    pieces of config1_full_bunny32.npz), with a 32-cell radial pattern (GenerateFracturePattern, :2072-2096) at an
+    impact point on the surface -- once general, once partial (pieces outside the impact sphere stay whole)."""
+    import hostapi
+    d0 = np.load(os.path.join(HERE, "config1_full_bunny32.npz"))
+    from test_oracle_port import load_polyset
+    convex, mesh = load_polyset(d0, "convex_"), load_polyset(d0, "mesh_")
+    v = d0["verts"][:, :3]
+    max_axis = float((v.max(0) - v.min(0)).max())
+    cloud, _ = load_obj(os.path.join(REF_MODELS, "sphere.obj"), 0.5)        # m_spherePointCloud (Surtr.cpp:1508)
+    impact = v[int(np.argmax(v[:, 2]))].copy()                               # a surface point of the bunny
+    d = {"cloud": cloud, "impact": impact, "max_axis_scale": np.float32(max_axis)}
+    for name, partial, mean, radius in (("general", False, 1.0, 1.0), ("partial", True, 0.05, 3.0)):
+        s = R.seeds_radial(46354, 32, mean)
+        off, idx = hostapi.dt3d_neighbors(s)
+        c, m, ncomp = R.do_fracture(convex, mesh, s, off, idx, cloud, impact, radius, max_axis, partial)
+        d[name + "_seeds"] = s
+        d[name + "_radius"] = np.float32(radius)
+        d[name + "_ncomp"] = np.int32(ncomp)
+        save_polyset(d, name + "_convex_", c)
+        save_polyset(d, name + "_mesh_", m)
+        print("do_fracture", name, "pieces", c.n, "compounds", ncomp, "untouched", int(c.piece.sum()),
+              "pieces per compound", np.bincount(c.cell, minlength=ncomp)[:12], "empty convex", int((c.nverts == 0).sum()))
+    for k in list(d):
+        if k.endswith("face_off") or k.endswith("face_idx") or k.endswith("planes") or k.endswith("plane_off"):
+            del d[k]
+    np.savez_compressed(os.path.join(HERE, "do_fracture_bunny.npz"), **d)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle ref"
     scalar_kats()
@@ -273,4 +303,5 @@ if __name__ == "__main__":
     config1_fixture()
     mesh_fixture()
     config1_full_fixture()
+    do_fracture_fixture()
     summaries()

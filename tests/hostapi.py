@@ -142,6 +142,32 @@ def apply_fracture_mesh(convex: PolySet, mesh: PolySet, planes, plane_off, cell_
     return export(), export_mesh()
 
 
+def do_fracture(convex: PolySet, mesh: PolySet, seeds, cloud, impact, impact_radius, max_axis_scale, partial):
+    seeds, cloud, impact = (np.ascontiguousarray(x, np.float32) for x in (seeds, cloud, impact))
+    ncomp = C.c_uint32(0)
+    mass = np.zeros((4096, 10), np.float32)
+    L = lib()
+    L.hosttest_do_fracture.argtypes = ([C.c_void_p] * 8 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32])
+    rc = L.hosttest_do_fracture(_p(convex.verts), _p(convex.vert_off), _p(convex.ring_off), _p(convex.ring),
+                                _p(mesh.verts), _p(mesh.vert_off), _p(mesh.ring_off), _p(mesh.ring), convex.n,
+                                _p(seeds), len(seeds), _p(cloud), len(cloud), _p(impact), impact_radius, max_axis_scale,
+                                int(partial), C.byref(ncomp), _p(mass), len(mass))
+    if rc:
+        raise RuntimeError(_err())
+    return export(), export_mesh(), ncomp.value, mass[:ncomp.value].copy()
+
+
+def combine_mass(volume, centroid, inertia, density=10.0):
+    volume = np.ascontiguousarray(volume, np.float64)
+    centroid, inertia = np.ascontiguousarray(centroid, np.float32), np.ascontiguousarray(inertia, np.float32)
+    out = np.zeros(10, np.float32)
+    L = lib()
+    L.hosttest_combine_mass.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.hosttest_combine_mass(len(volume), _p(volume), _p(centroid), _p(inertia), density, _p(out))
+    return out
+
+
 def config1_full(verts4, indices, seeds):
     verts4, seeds = np.ascontiguousarray(verts4, np.float32), np.ascontiguousarray(seeds, np.float32)
     indices = np.ascontiguousarray(indices, np.int32).reshape(-1)

@@ -172,3 +172,49 @@ def test_config1_bunny_full_prepare_fracture():
     assert np.array_equal(convex.nfaces, want_c.nfaces)     # SetExtract after the refit
     keys = list(zip(want_c.cell.tolist(), want_c.piece.tolist()))
     assert len(keys) - len(set(keys)) == 2                   # two (cell, piece) pairs split into islands
+
+
+def test_host_combine_mass_parallel_axis():
+    """CombineMass = what PxRigidBodyExt::updateMassAndInertia(body, 10) derives (Surtr.cpp:2520): eight octant boxes of
+    the unit cube, each with its analytic inertia about its own centre, must combine to the unit cube's mass 10,
+    centre 0 and inertia 10/6 * identity."""
+    cen = np.array([[x, y, z] for x in (-.25, .25) for y in (-.25, .25) for z in (-.25, .25)], np.float32)
+    vol = np.full(8, 0.125)
+    i_box = 0.125 * (0.25 + 0.25) / 12.0                      # V (b^2 + c^2) / 12 of a 0.5-cube at unit density
+    inertia = np.tile(np.array([i_box, i_box, i_box, 0, 0, 0], np.float32), (8, 1))
+    out = H.combine_mass(vol, cen, inertia, 10.0)
+    assert abs(out[0] - 10.0) < 1e-6 and np.abs(out[1:4]).max() < 1e-7
+    assert np.allclose(out[4:7], 10.0 / 6.0, rtol=1e-6) and np.abs(out[7:]).max() < 1e-7
+    # an off-centre pair: products of inertia follow the sign convention Ixy = -sum m x y
+    out = H.combine_mass([1.0, 1.0], [[1, 1, 0], [-1, -1, 0]], np.zeros((2, 6), np.float32), 1.0)
+    assert np.allclose(out[4:], [2, 2, 4, -2, 0, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["general", "partial"])
+def test_do_fracture_bunny(mode):
+    """Row f-3: SurtrHost::DoFracture (pattern placement, ApplyFracture incl. partial mode and mesh branch, SetExtract,
+    MergeOutOfImpact, HandleConvexIsland, Refitting) on the 27-piece bunny compound == the restatement over the
+    reference build (ref_do_fracture): same pieces in the same order, bit for bit, and the same compounds."""
+    d = np.load(os.path.join(GOLDEN, "do_fracture_bunny.npz"))
+    d0 = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    convex, mesh = load_polyset(d0, "convex_"), load_polyset(d0, "mesh_")
+    want_c, want_m = load_polyset(d, mode + "_convex_"), load_polyset(d, mode + "_mesh_")
+    got_c, got_m, ncomp, mass = H.do_fracture(convex, mesh, d[mode + "_seeds"], d["cloud"], d["impact"], float(d[mode + "_radius"]),
+                                              float(d["max_axis_scale"]), mode == "partial")
+    assert ncomp == int(d[mode + "_ncomp"]) and got_c.n == want_c.n
+    for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece"):
+        assert np.array_equal(bits(getattr(got_c, f)), bits(getattr(want_c, f))), "convex " + f
+        assert np.array_equal(bits(getattr(got_m, f)), bits(getattr(want_m, f))), "mesh " + f
+    assert np.array_equal(got_c.nfaces, want_c.nfaces)
+    if mode == "partial":
+        assert int(want_c.piece.sum()) == 20 and np.all(want_c.cell[want_c.piece == 1] == 0)   # untouched pieces stay in bind[0]
+    # compound mass properties at density 10 from K4's per-piece records (after the refit) vs the reference's Moments
+    for b in range(ncomp):
+        sel = want_c.cell == b
+        m_ref = 10.0 * want_c.volume[sel].sum()
+        assert abs(mass[b, 0] - m_ref) <= 1e-5 * max(1.0, m_ref)
+        if m_ref > 0:
+            c_ref = (want_c.volume[sel, None] * want_c.centroid[sel]).sum(0) / want_c.volume[sel].sum()
+            assert np.abs(mass[b, 1:4] - c_ref).max() < 1e-4
+            assert mass[b, 4:7].min() > 0
