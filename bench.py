@@ -370,6 +370,9 @@ def main():
         d_out = {k: v.to(dev, non_blocking=True) for k, v in h_out.items()}
         torch.cuda.synchronize()
         dist.barrier()
+        sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_off"], d_out["ring"], dst=0)   # NCCL warm-up
+        torch.cuda.synchronize()
+        dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         parts = sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_off"], d_out["ring"], dst=0)
