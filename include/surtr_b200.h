@@ -110,6 +110,20 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
  * NULL to keep one event. */
 int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events);
 
+/* A fracture pattern kept on the device in its own frame and placed per event.  Replaces the host loop
+ * Surtr::DoFracture runs over a copy of the pattern before every event (Src/Surtr.cpp:1887-1896): Polygon3D::Scale
+ * + Polygon3D::Translate (Src/VMACH.cpp:506-534), which move every face vertex and re-derive every face plane from
+ * the face's first three vertices (PolygonFace::ConstructFacePlane, VMACH.cpp:303-310).
+ * face_verts4: the VertexVec of every face of every cell, back to back (xyz + pad); face_vert_off[n_faces+1];
+ * cell_face_off[n_cells+1].  Every face needs >= 3 vertices. */
+int surtr_upload_pattern(surtr_ctx* ctx, const float* face_verts4, const uint32_t* face_vert_off, uint32_t n_faces,
+                         const uint32_t* cell_face_off, uint32_t n_cells);
+/* Places the resident pattern n_placements times: vertex' = (vertex * scale) + translate per component, planes
+ * rebuilt on the device.  The result becomes the cell set of the next event(s), one independent event per placement
+ * (pair it with surtr_upload_pieces(..., ev_piece_off, n_placements)); scale3 / translate3 hold 3 floats per
+ * placement.  Asynchronous on the context stream. */
+int surtr_place_pattern(surtr_ctx* ctx, const float* scale3, const float* translate3, uint32_t n_placements);
+
 /* --- the hot path (replaces Surtr::ApplyFracture + m_fractureTask + SetExtract + mass properties) ------- */
 /* Asynchronous on the context stream: K1 k-DOP extents -> K2 broad phase + ordered compaction ->
  * K3 one-warp-per-pair half-space clipping -> K4 fragment assembly with moments. */

@@ -125,6 +125,34 @@ __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const ui
     }
 }
 
+// ---------------------------------------------------------------------------------------------- pattern placement
+// Polygon3D::Scale(Vector3) then Translate(Vector3) over a whole cell set (VMACH.cpp:506-534), for n_place placements
+// of one resident pattern: every face vertex becomes (v * s) + t (two roundings, like the two host passes) and every
+// face plane is rebuilt from the face's first three moved vertices (PolygonFace::ConstructFacePlane, :303-310).
+// One thread per (placement, face).  Output = the cell arrays of the event batch: placement p owns cells
+// [p * n_cells, (p + 1) * n_cells).
+__global__ void __launch_bounds__(256) place_pattern_kernel(const float4* __restrict__ pat_verts, const uint32_t* __restrict__ face_vert_off,
+                                                            uint32_t n_faces, uint32_t n_fverts, const float* __restrict__ xform6,
+                                                            uint32_t n_place, float4* __restrict__ c_planes, float4* __restrict__ c_verts)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)n_faces * n_place) return;
+    const uint32_t p = (uint32_t)(i / n_faces), f = (uint32_t)(i - (uint64_t)p * n_faces);
+    const float sx = xform6[6 * p], sy = xform6[6 * p + 1], sz = xform6[6 * p + 2];
+    const float tx = xform6[6 * p + 3], ty = xform6[6 * p + 4], tz = xform6[6 * p + 5];
+    const uint32_t v0 = face_vert_off[f], v1 = face_vert_off[f + 1];
+    float4* out = c_verts + (size_t)p * n_fverts;
+    float q[9];
+    for (uint32_t v = v0; v < v1; v++)
+    {
+        const float4 a = __ldg(pat_verts + v);
+        const float x = __fadd_rn(__fmul_rn(a.x, sx), tx), y = __fadd_rn(__fmul_rn(a.y, sy), ty), z = __fadd_rn(__fmul_rn(a.z, sz), tz);
+        out[v] = make_float4(x, y, z, 0.f);
+        if (v - v0 < 3) { q[3 * (v - v0)] = x; q[3 * (v - v0) + 1] = y; q[3 * (v - v0) + 2] = z; }
+    }
+    c_planes[(size_t)p * n_faces + f] = plane_from_points(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8]);
+}
+
 // ---------------------------------------------------------------------------------------------- K2
 // Conservative separation test: a pair is culled only when some slab is separated by more than a few ulps of
 // the extents' magnitude, so no pair the clipper would keep is ever dropped (slivers).

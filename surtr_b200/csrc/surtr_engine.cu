@@ -80,6 +80,12 @@ struct surtr_ctx
     DevBuf c_planes, c_plane_off, c_verts, c_vert_off;
     std::vector<uint32_t> h_ev_piece_off, h_ev_cell_off;
 
+    // resident pattern (surtr_upload_pattern / surtr_place_pattern)
+    DevBuf pat_verts, pat_face_off, pat_xform;
+    std::vector<uint32_t> h_pat_cell_face_off, h_pat_cell_vert_off, h_off_scratch;
+    std::vector<float> h_xform;
+    uint32_t pat_faces = 0, pat_cells = 0, pat_fverts = 0;
+
     // derived tables
     DevBuf d_tiles, d_ev_mask_base, d_ev_piece_off, d_ev_cell_off;
     uint32_t n_tiles = 0, n_masks = 0;
@@ -618,6 +624,82 @@ int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out)
     out->verts4 = ctx->f_verts.as<float>();
     out->ring_off = ctx->f_ring_off.as<uint32_t>();
     out->ring = ctx->f_ring.as<uint16_t>();
+    return SURTR_OK;
+}
+
+int surtr_upload_pattern(surtr_ctx* ctx, const float* face_verts4, const uint32_t* face_vert_off, uint32_t n_faces,
+                         const uint32_t* cell_face_off, uint32_t n_cells)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!face_verts4 || !face_vert_off || !cell_face_off || !n_faces || !n_cells) return fail(ctx, SURTR_ERR_INVALID, "NULL or empty pattern");
+    if (cell_face_off[n_cells] != n_faces) return fail(ctx, SURTR_ERR_INVALID, "cell_face_off does not end at n_faces");
+    for (uint32_t f = 0; f < n_faces; f++)
+        if (face_vert_off[f + 1] < face_vert_off[f] + 3) return fail(ctx, SURTR_ERR_INVALID, "pattern face with fewer than 3 vertices");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t nfv = face_vert_off[n_faces];
+    int rc;
+    if ((rc = upload(ctx, ctx->pat_verts, face_verts4, 16 * (size_t)nfv))) return rc;
+    if ((rc = upload(ctx, ctx->pat_face_off, face_vert_off, 4 * ((size_t)n_faces + 1)))) return rc;
+    ctx->h_pat_cell_face_off.assign(cell_face_off, cell_face_off + n_cells + 1);
+    ctx->h_pat_cell_vert_off.resize(n_cells + 1);
+    for (uint32_t c = 0; c <= n_cells; c++) ctx->h_pat_cell_vert_off[c] = face_vert_off[cell_face_off[c]];
+    ctx->pat_faces = n_faces;
+    ctx->pat_cells = n_cells;
+    ctx->pat_fverts = nfv;
+    return SURTR_OK;
+}
+
+int surtr_place_pattern(surtr_ctx* ctx, const float* scale3, const float* translate3, uint32_t n_place)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!ctx->pat_cells) return fail(ctx, SURTR_ERR_INVALID, "no pattern uploaded");
+    if (!scale3 || !translate3 || !n_place) return fail(ctx, SURTR_ERR_INVALID, "NULL or empty placement list");
+    const uint64_t nf = (uint64_t)ctx->pat_faces * n_place, nv = (uint64_t)ctx->pat_fverts * n_place, nc = (uint64_t)ctx->pat_cells * n_place;
+    if (nf > 0xfffffff0ull || nv > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many placements for one batch");
+    CK(cudaSetDevice(ctx->device));
+    // a stream-ordered copy out of these host vectors must have left before they are rewritten (pageable -> staged
+    // copies return only after the staging, so this is cheap; it also orders the placement after the previous event)
+    ctx->h_xform.resize(6 * (size_t)n_place);
+    for (uint32_t p = 0; p < n_place; p++)
+    {
+        for (int k = 0; k < 3; k++) { ctx->h_xform[6 * p + k] = scale3[3 * p + k]; ctx->h_xform[6 * p + 3 + k] = translate3[3 * p + k]; }
+    }
+    int rc;
+    if ((rc = upload(ctx, ctx->pat_xform, ctx->h_xform.data(), 4 * ctx->h_xform.size()))) return rc;
+    CK(ctx->c_planes.reserve(16 * nf));
+    CK(ctx->c_verts.reserve(16 * nv));
+    // offsets: placement p repeats the pattern's offsets shifted by p * (faces | face vertices)
+    std::vector<uint32_t>& off = ctx->h_off_scratch;
+    off.resize(2 * (nc + 1));
+    for (uint32_t p = 0; p < n_place; p++)
+        for (uint32_t c = 0; c < ctx->pat_cells; c++)
+        {
+            off[(size_t)p * ctx->pat_cells + c] = p * ctx->pat_faces + ctx->h_pat_cell_face_off[c];
+            off[nc + 1 + (size_t)p * ctx->pat_cells + c] = p * ctx->pat_fverts + ctx->h_pat_cell_vert_off[c];
+        }
+    off[nc] = (uint32_t)nf;
+    off[2 * nc + 1] = (uint32_t)nv;
+    if ((rc = upload(ctx, ctx->c_plane_off, off.data(), 4 * (nc + 1)))) return rc;
+    if ((rc = upload(ctx, ctx->c_vert_off, off.data() + nc + 1, 4 * (nc + 1)))) return rc;
+    const unsigned blocks = (unsigned)((nf + 255) / 256);
+    place_pattern_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pat_verts.as<float4>(), ctx->pat_face_off.as<uint32_t>(), ctx->pat_faces,
+                                                         ctx->pat_fverts, ctx->pat_xform.as<float>(), n_place, ctx->c_planes.as<float4>(),
+                                                         ctx->c_verts.as<float4>());
+    CK(cudaGetLastError());
+    ctx->cells_bounded = true;
+    ctx->n_cverts = nv;
+    ctx->n_cells = (uint32_t)nc;
+    ctx->n_planes = nf;
+    std::vector<uint32_t> layout(n_place + 1);
+    for (uint32_t p = 0; p <= n_place; p++) layout[p] = p * ctx->pat_cells;
+    if (layout != ctx->h_ev_cell_off)
+    {
+        ctx->h_ev_cell_off.swap(layout);
+        ctx->tables_dirty = true;
+    }
+    ctx->n_events_c = n_place;
+    ctx->have_cells = true;
+    ctx->event_launched = false;
     return SURTR_OK;
 }
 

@@ -57,4 +57,21 @@ __device__ __forceinline__ float4 plane_from_point_normal(float px, float py, fl
 {
     return make_float4(nx, ny, nz, -dot3(px, py, pz, nx, ny, nz));
 }
+
+// Plane(p1, p2, p3) (SimpleMath.inl:2773-2780 = XMPlaneFromPoints): n = normalize((p1 - p2) x (p1 - p3)), d = -n.p1;
+// XMVector3Normalize divides by sqrt(dot) and maps zero length to 0.
+__device__ __forceinline__ float4 plane_from_points(float ax, float ay, float az, float bx, float by, float bz, float cx, float cy,
+                                                    float cz)
+{
+    float nx, ny, nz;
+    cross3(__fsub_rn(ax, bx), __fsub_rn(ay, by), __fsub_rn(az, bz), __fsub_rn(ax, cx), __fsub_rn(ay, cy), __fsub_rn(az, cz), nx, ny, nz);
+    const float lsq = dot3(nx, ny, nz, nx, ny, nz);
+    if (lsq == 0.f) { nx = ny = nz = 0.f; }
+    else
+    {
+        const float len = __fsqrt_rn(lsq);
+        nx = __fdiv_rn(nx, len); ny = __fdiv_rn(ny, len); nz = __fdiv_rn(nz, len);
+    }
+    return make_float4(nx, ny, nz, -dot3(nx, ny, nz, ax, ay, az));
+}
 } // namespace surtr

@@ -32,6 +32,7 @@ EXPORTS = [
     "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
+    "surtr_upload_pattern", "surtr_place_pattern",
 ]
 
 
@@ -73,6 +74,8 @@ def load_library():
     lib.surtr_upload_pieces.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
     lib.surtr_upload_cells.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
     lib.surtr_fragments_to_pieces.argtypes = [vp, vp, u32]
+    lib.surtr_upload_pattern.argtypes = [vp, vp, vp, u32, vp, u32]
+    lib.surtr_place_pattern.argtypes = [vp, vp, vp, u32]
     lib.surtr_fracture_event.argtypes = [vp]
     lib.surtr_event_counts.argtypes = [vp, C.POINTER(Counts)]
     lib.surtr_download_fragments.argtypes = [vp, vp, vp, vp, vp]
@@ -169,6 +172,21 @@ class FractureContext:
         ev = _arr(ev_cell_off, np.uint32)
         self._ck(self._lib.surtr_upload_cells(self._h, _p(planes4), _p(plane_off), _p(cell_verts4), _p(cvert_off),
                                               len(plane_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def upload_pattern(self, face_verts4, face_vert_off, cell_face_off):
+        """Resident fracture pattern: the VertexVec of every face of every cell (see include/surtr_b200.h)."""
+        face_verts4 = _arr(face_verts4, np.float32)
+        face_vert_off = _arr(face_vert_off, np.uint32)
+        cell_face_off = _arr(cell_face_off, np.uint32)
+        self._ck(self._lib.surtr_upload_pattern(self._h, _p(face_verts4), _p(face_vert_off), len(face_vert_off) - 1,
+                                                _p(cell_face_off), len(cell_face_off) - 1))
+
+    def place_pattern(self, scale3, translate3):
+        """Polygon3D::Scale + Translate on the device, one placement (= one event) per row of scale3 / translate3."""
+        scale3 = _arr(np.atleast_2d(scale3), np.float32)
+        translate3 = _arr(np.atleast_2d(translate3), np.float32)
+        assert scale3.shape == translate3.shape and scale3.shape[1] == 3
+        self._ck(self._lib.surtr_place_pattern(self._h, _p(scale3), _p(translate3), len(scale3)))
 
     def fragments_to_pieces(self, ev_piece_off=None):
         ev = _arr(ev_piece_off, np.uint32)

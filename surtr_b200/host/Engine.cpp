@@ -1,5 +1,7 @@
 #include "Engine.h"
 
+#include <atomic>
+
 #include <stdexcept>
 #include <string>
 
@@ -76,6 +78,25 @@ void FlatCells::add(const std::vector<Poly::Plane>& planes)
 	bounded = false;
 }
 
+void FlatPattern::build(const std::vector<VMACH::Polygon3D>& cells)
+{
+	static std::atomic<uint64_t> next_id{ 1 };
+	face_verts4.clear();
+	face_vert_off.assign(1, 0u);
+	cell_face_off.assign(1, 0u);
+	for (const VMACH::Polygon3D& cell : cells)
+	{
+		for (const VMACH::PolygonFace& f : cell.FaceVec)
+		{
+			for (const Vector3& v : f.VertexVec)
+				face_verts4.insert(face_verts4.end(), { v.x, v.y, v.z, 0.f });
+			face_vert_off.push_back((uint32_t)(face_verts4.size() / 4));
+		}
+		cell_face_off.push_back((uint32_t)face_vert_off.size() - 1);
+	}
+	id = next_id++;
+}
+
 Poly::Polyhedron Fragments::polyhedron(size_t i) const
 {
 	const surtr_fragment& f = rec[i];
@@ -113,6 +134,20 @@ surtr_ctx* context()
 			throw std::runtime_error(std::string("surtr_ctx_create: ") + surtr_last_error(nullptr));   // no CPU fallback
 	}
 	return h.ctx;
+}
+
+void place_pattern(const FlatPattern& pattern, const Vector3& scale, const Vector3& translate)
+{
+	static thread_local uint64_t resident_id = 0;
+	surtr_ctx* c = context();
+	if (resident_id != pattern.id)
+	{
+		check(surtr_upload_pattern(c, pattern.face_verts4.data(), pattern.face_vert_off.data(), (uint32_t)pattern.face_vert_off.size() - 1,
+								   pattern.cell_face_off.data(), pattern.count()), "surtr_upload_pattern");
+		resident_id = pattern.id;
+	}
+	const float s3[3] = { scale.x, scale.y, scale.z }, t3[3] = { translate.x, translate.y, translate.z };
+	check(surtr_place_pattern(c, s3, t3, 1), "surtr_place_pattern");
 }
 
 void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry, bool upload_cells)

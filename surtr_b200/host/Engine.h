@@ -37,6 +37,17 @@ struct FlatCells
 	uint32_t count() const { return (uint32_t)plane_off.size() - 1; }
 };
 
+// A cell set in its own frame, kept on the device and placed per event (surtr_upload_pattern / surtr_place_pattern):
+// the VertexVec of every face of every cell.
+struct FlatPattern
+{
+	std::vector<float> face_verts4;
+	std::vector<uint32_t> face_vert_off{ 0 }, cell_face_off{ 0 };
+	uint64_t id = 0;                  // 0 = empty; a fresh id per build, so a context knows which pattern it holds
+	void build(const std::vector<VMACH::Polygon3D>& cells);
+	uint32_t count() const { return (uint32_t)cell_face_off.size() - 1; }
+};
+
 struct Fragments
 {
 	std::vector<surtr_fragment> rec;
@@ -48,6 +59,9 @@ struct Fragments
 
 surtr_ctx* context();                                            // throws std::runtime_error without a B200
 void check(int rc, const char* what);                            // throws std::runtime_error with surtr_last_error
+// Makes `pattern` the resident pattern of this thread's context (no-op when it already is) and installs it, scaled and
+// translated on the device, as the cell set of the next event (Polygon3D::Scale + Translate, VMACH.cpp:506-534).
+void place_pattern(const FlatPattern& pattern, const DirectX::SimpleMath::Vector3& scale, const DirectX::SimpleMath::Vector3& translate);
 // upload_cells = false: the cells of the previous event on this thread's context are still resident and are reused
 void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true, bool upload_cells = true);
 } // namespace detail

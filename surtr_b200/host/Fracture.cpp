@@ -179,6 +179,22 @@ bool ConvexOutOfSphere(const Poly::Polyhedron& polyhedron, const Extract* extrac
 	return true;
 }
 
+namespace
+{
+// where the cells of an event come from: a host-side Polygon3D list (packed and uploaded), or the context's resident
+// pattern placed on the device
+struct CellSource
+{
+	const std::vector<VMACH::Polygon3D>* polys = nullptr;
+	const detail::FlatPattern* pattern = nullptr;
+	Vector3 scale, translate;
+	uint32_t count() const { return polys ? (uint32_t)polys->size() : pattern->count(); }
+};
+
+CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, const std::vector<Vector3>& spherePointCloud, bool partial,
+							const FractureArgs& args, bool meshBranch);
+} // namespace
+
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch)
 {
 	return ApplyFracture(compound, voroPolyVec, std::vector<Vector3>(), false, FractureArgs(), meshBranch);
@@ -186,6 +202,16 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec,
 						   const std::vector<Vector3>& spherePointCloud, bool partial, const FractureArgs& args, bool meshBranch)
+{
+	CellSource source;
+	source.polys = &voroPolyVec;
+	return apply_fracture(compound, source, spherePointCloud, partial, args, meshBranch);
+}
+
+namespace
+{
+CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, const std::vector<Vector3>& spherePointCloud, bool partial,
+							const FractureArgs& args, bool meshBranch)
 {
 	const std::vector<Piece*>& targetPieceVec = compound.PieceVec;
 	// pieces that lie outside the impact sphere are not cut (Surtr.cpp:2109-2124)
@@ -202,38 +228,43 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 		}
 		(out ? outside : inside).push_back(c);
 	}
-	const uint32_t n_in = (uint32_t)inside.size(), n_out = (uint32_t)outside.size(), n_cells = (uint32_t)voroPolyVec.size();
+	const uint32_t n_in = (uint32_t)inside.size(), n_out = (uint32_t)outside.size(), n_cells = source.count();
 
-	// One batch: event 0 = pieces inside the sphere x the cells (one task per cell in the reference, :2129-2131);
-	// event 1 = the untouched pieces x one cell without planes, which hands them back uncut -- only so that K3/K4
-	// compute their face counts and mass properties in the same launches.
-	detail::FlatPolys pieces;
-	for (const int c : inside)
-		pieces.add(targetPieceVec[c]->Convex);
-	for (const int c : outside)
-		pieces.add(targetPieceVec[c]->Convex);
+	// event 1: the pieces inside the sphere x the cells (one pool task per cell in the reference, :2129-2131)
+	detail::Fragments fr, mfr, ofr;
 	detail::FlatCells cells;
-	for (const VMACH::Polygon3D& cell : voroPolyVec)
-		cells.add(cell);
+	if (n_in)
+	{
+		detail::FlatPolys pieces;
+		for (const int c : inside)
+			pieces.add(targetPieceVec[c]->Convex);
+		if (source.polys)
+			for (const VMACH::Polygon3D& cell : *source.polys)
+				cells.add(cell);
+		else
+			detail::place_pattern(*source.pattern, source.scale, source.translate);
+		detail::run_event(pieces, cells, fr, true, source.polys != nullptr);
+		if (meshBranch)
+		{
+			// event 2, the second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident
+			// cells.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
+			// its convex and its mesh fragment exist (:1466-1472).
+			detail::FlatPolys meshes;
+			for (const int c : inside)
+				meshes.add(targetPieceVec[c]->Mesh);
+			detail::run_event(meshes, cells, mfr, true, false);
+		}
+	}
 	if (n_out)
 	{
-		cells.add_keep_all();
-		pieces.ev_off = { 0u, n_in, n_in + n_out };
-		cells.ev_off = { 0u, n_cells, n_cells + 1u };
-	}
-	detail::Fragments fr, mfr;
-	detail::run_event(pieces, cells, fr);
-	if (meshBranch && n_in)
-	{
-		// second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident cells, one more
-		// GPU event.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
-		// its convex and its mesh fragment exist (:1466-1472).
-		detail::FlatPolys meshes;
-		for (const int c : inside)
-			meshes.add(targetPieceVec[c]->Mesh);
-		if (n_out)
-			meshes.ev_off = { 0u, n_in, n_in };
-		detail::run_event(meshes, cells, mfr, true, false);
+		// event 3: the untouched pieces x one cell without planes, which hands them back uncut -- only so that K3/K4
+		// compute their face counts and mass properties like everybody else's
+		detail::FlatPolys pieces;
+		for (const int c : outside)
+			pieces.add(targetPieceVec[c]->Convex);
+		detail::FlatCells keep;
+		keep.add_keep_all();
+		detail::run_event(pieces, keep, ofr, false);
 	}
 
 	CompoundInfo info;
@@ -255,17 +286,15 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 		info.PieceSourceCell.push_back(-1);
 		info.PieceSourcePiece.push_back(outside[k]);
 	}
+	for (const surtr_fragment& r : ofr.rec)
+		info.PieceMass[r.piece] = mass_of(r);
+	(void)n_cells;
 	int current_cell = -1;
 	size_t m = 0;
 	const auto key = [](const surtr_fragment& r) { return ((uint64_t)r.cell << 32) | r.piece; };
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
 		const surtr_fragment& r = fr.rec[f];
-		if (r.cell >= n_cells)   // event 1: the uncut piece itself, only its record is of interest
-		{
-			info.PieceMass[r.piece - n_in] = mass_of(r);
-			continue;
-		}
 		const Poly::Polyhedron convex = fr.polyhedron(f);
 		std::vector<Poly::Polyhedron> meshes;
 		if (meshBranch)
@@ -314,6 +343,7 @@ CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Po
 	}
 	return info;
 }
+} // namespace
 
 void SetExtract(CompoundInfo& preResult)
 {
@@ -435,6 +465,20 @@ void HandleConvexIsland(CompoundInfo& compoundInfo)
 	compoundInfo.CompoundBind.insert(compoundInfo.CompoundBind.end(), newBind.begin(), newBind.end());
 }
 
+const detail::FlatPattern& FractureStorage::Resident(bool partial) const
+{
+	detail::FlatPattern& flat = m_flat[partial ? 0 : 1];
+	if (!flat.id)
+		flat.build(partial ? PartialFracturePattern : GeneralFracturePattern);
+	return flat;
+}
+
+void FractureStorage::PatternsChanged()
+{
+	m_flat[0] = detail::FlatPattern();
+	m_flat[1] = detail::FlatPattern();
+}
+
 std::vector<VMACH::Polygon3D> GenerateFracturePattern(int seed, int cellCount, double mean)
 {
 	return GenerateVoronoi(GenerateRadialSeeds(seed, cellCount, mean));
@@ -444,18 +488,20 @@ std::vector<Compound> DoFracture(const Compound& targetCompound, const FractureS
 								 const FractureArgs& args, CompoundInfo* out_info)
 {
 	// Surtr.cpp:1885-1959
-	std::vector<VMACH::Polygon3D> localFracturePattern = args.PartialFracture ? storage.PartialFracturePattern : storage.GeneralFracturePattern;
+	// The pattern stays on the device in its own frame; scale (:1889-1891) and alignment (:1893-1896) happen there,
+	// together with the re-derivation of every face plane that Polygon3D::Scale / Translate do on the host.
+	const detail::FlatPattern& pattern = storage.Resident(args.PartialFracture);
 	std::vector<Vector3> localSpherePointCloud = spherePointCloud;
-	for (VMACH::Polygon3D& voro : localFracturePattern)
-		voro.Scale(Vector3(storage.MaxAxisScale, storage.MaxAxisScale, storage.MaxAxisScale) * 2);
-	for (VMACH::Polygon3D& voro : localFracturePattern)
-		voro.Translate(args.ImpactPosition);
 	for (Vector3& v : localSpherePointCloud)
 	{
 		v *= args.ImpactRadius;
 		v += args.ImpactPosition;
 	}
-	CompoundInfo second = ApplyFracture(targetCompound, localFracturePattern, localSpherePointCloud, args.PartialFracture, args);
+	CellSource source;
+	source.pattern = &pattern;
+	source.scale = Vector3(storage.MaxAxisScale, storage.MaxAxisScale, storage.MaxAxisScale) * 2;
+	source.translate = args.ImpactPosition;
+	CompoundInfo second = apply_fracture(targetCompound, source, localSpherePointCloud, args.PartialFracture, args, true);
 	SetExtract(second);
 	if (args.PartialFracture)
 		MergeOutOfImpact(second, localSpherePointCloud, args);

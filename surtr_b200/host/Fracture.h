@@ -8,6 +8,7 @@
 // resident cells (Piece::Mesh polyhedra, cut in the global-memory tier of K3) followed by the island split on the host.
 #pragma once
 
+#include "Engine.h"
 #include "Poly.h"
 #include "VMACH.h"
 
@@ -114,7 +115,14 @@ std::vector<VMACH::Polygon3D> GenerateFracturePattern(int seed, int cellCount, d
 struct FractureStorage   // the members of Inc/Surtr.h:136-155 that DoFracture reads
 {
 	float MaxAxisScale = 1.f;
-	std::vector<VMACH::Polygon3D> PartialFracturePattern, GeneralFracturePattern;
+	std::vector<VMACH::Polygon3D> PartialFracturePattern, GeneralFracturePattern;   // in the unit box, as generated
+
+	// Flat copy of a pattern for the device (built on first use; it is uploaded once per context and then only placed).
+	const detail::FlatPattern& Resident(bool partial) const;
+	void PatternsChanged();   // call after editing a pattern
+
+private:
+	mutable detail::FlatPattern m_flat[2];
 };
 // Surtr::DoFracture (Surtr.cpp:1885-1959): place the pattern at the impact point (scale 2 x MaxAxisScale), ApplyFracture,
 // SetExtract, [MergeOutOfImpact], HandleConvexIsland, Refitting, SetExtract -> one Compound per bind set (the reserved 0-th

@@ -84,15 +84,17 @@ def _plane_from_points(p1, p2, p3):
     return np.array([n[0], n[1], n[2], w], f32)
 
 
-def face_planes(verts, vert_off, ring_off, ring):
-    """Faces in Poly::ExtractFaces order (Poly.cpp:89-126), plane per face by the PolygonFace::AddVertex route."""
-    planes, plane_off = [], [0]
+def _face_vertex_lists(verts, vert_off, ring_off, ring):
+    """Per polyhedron, the vertex list of every face as VMACH::PolygonFace would hold it: loops in Poly::ExtractFaces
+    order (Poly.cpp:89-126) fed through PolygonFace::AddVertex, which drops a vertex closer than 1e-12 to one already
+    in the face (VMACH.cpp:289-301)."""
     ring = ring.astype(np.int64)
     for i in range(len(vert_off) - 1):
         v0, v1 = int(vert_off[i]), int(vert_off[i + 1])
         rings = [ring[ring_off[v]:ring_off[v + 1]].tolist() for v in range(v0, v1)]
         pos = verts[v0:v1, :3]
         visited = set()
+        faces = []
         for a in range(v1 - v0):
             for b in rings[a]:
                 if (a, b) in visited:
@@ -111,11 +113,31 @@ def face_planes(verts, vert_off, ring_off, ring):
                     if any(float(np.sqrt(np.sum((p - q) ** 2, dtype=f32))) < 1e-12 for q in kept):
                         continue
                     kept.append(p)
-                    if len(kept) == 3:
-                        break
-                planes.append(_plane_from_points(*kept) if len(kept) == 3 else np.array([0, 1, 0, 0], f32))
+                faces.append(kept)
+        yield faces
+
+
+def face_planes(verts, vert_off, ring_off, ring):
+    """Faces in Poly::ExtractFaces order (Poly.cpp:89-126), plane per face by the PolygonFace::AddVertex route."""
+    planes, plane_off = [], [0]
+    for faces in _face_vertex_lists(verts, vert_off, ring_off, ring):
+        for kept in faces:
+            planes.append(_plane_from_points(*kept[:3]) if len(kept) >= 3 else np.array([0, 1, 0, 0], f32))
         plane_off.append(len(planes))
     return np.asarray(planes, f32).reshape(-1, 4), np.asarray(plane_off, np.uint32)
+
+
+def pattern_arrays(verts, vert_off, ring_off, ring):
+    """A cell set as the flat pattern of surtr_upload_pattern: (face_verts4, face_vert_off, cell_face_off)."""
+    fv, fvo, cfo = [], [0], [0]
+    for faces in _face_vertex_lists(verts, vert_off, ring_off, ring):
+        for kept in faces:
+            fv.extend(kept)
+            fvo.append(len(fv))
+        cfo.append(len(fvo) - 1)
+    out = np.zeros((len(fv), 4), f32)
+    out[:, :3] = np.asarray(fv, f32).reshape(-1, 3)
+    return out, np.asarray(fvo, np.uint32), np.asarray(cfo, np.uint32)
 
 
 def voronoi_cells(ctx, seeds: np.ndarray, nb_off=None, nb_idx=None) -> CellSet:

@@ -295,3 +295,44 @@ def test_malformed_and_oversize_inputs_fail_loudly(ctx):
     got = common.run_gpu(ctx, cube, cells)
     want = P.apply_fracture(cube, cells.planes, cells.plane_off)
     common.assert_fragments_equal(got, want)
+
+
+def test_resident_pattern_placement(ctx):
+    """Row f-4: a pattern uploaded once in its own frame and placed on the device (surtr_place_pattern = Polygon3D::Scale +
+    Translate with the face planes re-derived from the moved vertices, VMACH.cpp:303-310, 506-534), three placements in
+    one batch of independent events.  Expected: the oracle on cells moved in numpy float32 (one rounding per operation)
+    with planes from the PolygonFace::AddVertex route."""
+    from surtr_b200 import synth
+    cells = common.voronoi(46354, 64)
+    ctx.upload_pattern(*synth.pattern_arrays(cells.verts, cells.vert_off, cells.ring_off, cells.ring))
+    scale = np.array([[2, 2, 2], [1.5, 0.7, 3.0], [21.72226, 21.72226, 21.72226]], np.float32)
+    trans = np.array([[0, 0, 0], [0.3, -1.25, 4.0], [-1.1729, 12.41, 3.53]], np.float32)
+    cube = common.unit_cube()
+    psets, wants = [], []
+    for s, t in zip(scale, trans):
+        piece = cube.subset([0])
+        piece.verts = cube.verts.copy()
+        piece.verts[:, :3] = (cube.verts[:, :3] * (s * np.float32(0.6))).astype(np.float32) + (t + s * np.float32(0.1)).astype(np.float32)
+        placed = cells.subset(range(cells.n))
+        placed.verts = cells.verts.copy()
+        placed.verts[:, :3] = (cells.verts[:, :3] * s).astype(np.float32) + t
+        planes, off = P.face_planes(placed)
+        psets.append(piece)
+        wants.append(P.apply_fracture(piece, planes, off))
+    pieces, ev_p = common.concat(psets)
+    for rep in range(2):                          # the second pass re-places the resident pattern, nothing is re-uploaded
+        ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring, ev_p)
+        ctx.place_pattern(scale, trans)
+        ctx.fracture_event()
+        got = ctx.download()
+        f0 = 0
+        for e, want in enumerate(wants):
+            assert 10 < want.n < 64               # the piece covers part of the pattern: both culling and cutting happen
+            sl = slice(f0, f0 + want.n)
+            assert np.array_equal(got.rec["cell"][sl], want.cell + 64 * e) and np.array_equal(got.rec["piece"][sl], want.piece + e)
+            assert np.array_equal(got.rec["n_verts"][sl], want.nverts) and np.array_equal(got.rec["n_faces"][sl], want.nfaces)
+            v0 = int(got.rec["vert_off"][f0])
+            assert np.array_equal(bits(got.verts[v0:v0 + len(want.verts)]), bits(want.verts))
+            assert np.array_equal(bits(got.rec["volume"][sl]), bits(want.volume))
+            f0 += want.n
+        assert f0 == got.n
