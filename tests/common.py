@@ -155,3 +155,27 @@ def recursion_levels(depth=3, seeds_per_level=64, base_seed=1000):
 
 def fragments_as_polyset(fr) -> PolySet:
     return PolySet(fr.verts, fr.vert_off, fr.ring_off, fr.ring)
+
+
+def degenerate_large_inputs():
+    """In-plane cuts for the large tiers: the bunny ACH (107 vertices: shared-memory large tier) and the bunny mesh
+    polyhedron (2503 vertices: global-memory tier) against 48 sequences of 1-4 axis-aligned planes, each through the
+    exact coordinate of a random vertex of one of the two pieces (signed distance exactly 0 there)."""
+    a = np.load(os.path.join(GOLDEN, "config1_bunny32.npz"))
+    m = np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz"))
+    ach = PolySet(a["ach_verts"], a["ach_vert_off"], a["ach_ring_off"], a["ach_ring"])
+    mesh = PolySet(m["mesh_verts"], m["mesh_vert_off"], m["mesh_ring_off"], m["mesh_ring"])
+    pieces, _ = concat([ach, mesh])
+    rng = np.random.RandomState(5)
+    planes, off = [], [0]
+    for _ in range(48):
+        for _ in range(rng.randint(1, 5)):
+            src = ach if rng.rand() < 0.5 else mesh
+            v = src.verts[rng.randint(len(src.verts)), :3]
+            ax = rng.randint(3)
+            sgn = np.float32(1.0 if rng.rand() < 0.5 else -1.0)
+            n = np.zeros(3, np.float32)
+            n[ax] = sgn
+            planes.append([n[0], n[1], n[2], -sgn * v[ax]])
+        off.append(len(planes))
+    return pieces, np.asarray(planes, np.float32), np.asarray(off, np.uint32)

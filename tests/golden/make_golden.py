@@ -161,6 +161,14 @@ def summaries():
         fr = R.apply_fracture(pieces, cells.planes, cells.plane_off, 16)
         out[f"config5_level{lvl}"] = common.summary_of_polyset(fr)
         pieces = fr
+    # in-plane cuts on the large tiers (bunny ACH + bunny mesh), see common.degenerate_large_inputs
+    from oracle import portapi as P
+    pieces, planes, off = common.degenerate_large_inputs()
+    want = R.apply_fracture(pieces, planes, off, 16)
+    port = P.apply_fracture(pieces, planes, off, cap_frags=256, cap_verts=400000)
+    assert common.summary_of_polyset(port) == common.summary_of_polyset(want) and np.array_equal(port.ring, want.ring)
+    out["degenerate_large"] = common.summary_of_polyset(want)
+    out["degenerate_large"]["ring"] = common.digest(np.asarray(want.ring, np.uint16))
     json.dump(out, open(os.path.join(HERE, "summaries.json"), "w"), indent=1, sort_keys=True)
     for k, v in out.items():
         print(k, v["n"], v["n_verts"], v["sum_volume"])
@@ -264,6 +272,61 @@ def config1_full_fixture():
           "mesh verts", mesh.nverts[:6], "empty convex after refit", int((convex.nverts == 0).sum()))
 
 
+def degenerate_planes():
+    """Cutting planes that hit the unit cube's vertices, edges and faces exactly (all values exact in float32, normals
+    deliberately not normalised): the comp == 0 / in-plane band of Poly.cpp:303-319 and the patch cases around it."""
+    menu = []
+    for ax in range(3):
+        for d in (0.5, -0.5, 0.0, 0.25):
+            for sgn in (1.0, -1.0):
+                n = [0.0, 0.0, 0.0]
+                n[ax] = sgn
+                menu.append(n + [d])                       # coincident with a face / through the centre / generic
+    for a, b in ((0, 1), (0, 2), (1, 2)):
+        for sa in (1.0, -1.0):
+            for sb in (1.0, -1.0):
+                for d in (0.0, -1.0, 1.0, 0.5):            # through 4 vertices / touching an edge / generic
+                    n = [0.0, 0.0, 0.0]
+                    n[a], n[b] = sa, sb
+                    menu.append(n + [d])
+    for sx in (1.0, -1.0):
+        for sy in (1.0, -1.0):
+            for sz in (1.0, -1.0):
+                for d in (-0.5, 0.5, -1.5, 1.5, 0.0):      # through 3 vertices / touching one vertex / hexagonal cut
+                    menu.append([sx, sy, sz, d])
+    return np.asarray(menu, np.float32)
+
+
+def degenerate_fixture():
+    """In-plane and touching cuts: the unit cube and a truncated cube against 400 random sequences of 1-6 planes from
+    degenerate_planes(); expected fragments from the reference build."""
+    from oracle import portapi as P
+    menu = degenerate_planes()
+    rng = np.random.RandomState(11)
+    planes, off = [], [0]
+    for _ in range(400):
+        k = rng.randint(1, 7)
+        planes.append(menu[rng.randint(0, len(menu), k)])
+        off.append(off[-1] + k)
+    planes, off = np.concatenate(planes), np.asarray(off, np.uint32)
+    cube = common.unit_cube()
+    corners = np.asarray([[sx, sy, sz, -1.0] for sx in (1, -1) for sy in (1, -1) for sz in (1, -1)], np.float32)
+    trunc = R.clip_each(cube, corners, np.array([0, 8], np.uint32))           # cuboctahedron-like: vertices on edge midpoints
+    pieces, _ = common.concat([cube, trunc.subset([0])])
+    want = R.apply_fracture(pieces, planes, off, 0)
+    port = P.apply_fracture(pieces, planes, off)
+    assert port.n == want.n and np.array_equal(port.verts.view(np.uint32), want.verts.view(np.uint32)) and np.array_equal(port.ring, want.ring)
+    assert np.array_equal(port.volume.view(np.uint64), want.volume.view(np.uint64)) and np.array_equal(port.nfaces, want.nfaces)
+    d = {"planes": planes, "plane_off": off}
+    save_polyset(d, "pieces_", pieces, full=False)
+    save_polyset(d, "frag_", want)
+    for k in list(d):
+        if k.endswith("face_off") or k.endswith("face_idx") or k.startswith("frag_plane"):
+            del d[k]
+    np.savez_compressed(os.path.join(HERE, "degenerate_x400.npz"), **d)
+    print("degenerate: pieces", pieces.nverts, "fragments", want.n, "of", 2 * 400, "pairs; verts", int(want.nverts.min()), "-", int(want.nverts.max()))
+
+
 def do_fracture_fixture():
     """Row f-3: Surtr::DoFracture (Surtr.cpp:1885-1959) on the compound PrepareFracture produced for the bunny (the 27
     pieces of config1_full_bunny32.npz), with a 32-cell radial pattern (GenerateFracturePattern, :2072-2096) at an
@@ -303,5 +366,6 @@ if __name__ == "__main__":
     config1_fixture()
     mesh_fixture()
     config1_full_fixture()
+    degenerate_fixture()
     do_fracture_fixture()
     summaries()

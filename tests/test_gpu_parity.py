@@ -336,3 +336,31 @@ def test_resident_pattern_placement(ctx):
             assert np.array_equal(bits(got.rec["volume"][sl]), bits(want.volume))
             f0 += want.n
         assert f0 == got.n
+
+
+def test_degenerate_cuts(ctx):
+    """Planes exactly through vertices, along edges and coincident with faces of the unit cube and of a truncated cube
+    (400 random sequences): the in-plane band and the sequential patch path.  Expected = the reference build's output."""
+    d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+    pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+    ctx.upload_cells(d["planes"], d["plane_off"])
+    ctx.fracture_event()
+    got = ctx.download()
+    common.assert_fragments_equal(got, want)
+    assert ctx.counts().n_seq_cuts > 100          # the in-plane cases really took the sequential replay
+
+
+def test_degenerate_cuts_large_tiers(ctx):
+    """The same in-plane situations on the 107-vertex ACH (shared-memory large tier) and the 2503-vertex mesh
+    (global-memory tier), whose sequential patch paths are separate code: fingerprint of the reference build."""
+    pieces, planes, off = common.degenerate_large_inputs()
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+    ctx.upload_cells(planes, off)
+    ctx.fracture_event()
+    got = ctx.download()
+    s = common.summary_of_fragments(got)
+    s["ring"] = common.digest(np.asarray(got.ring, np.uint16))
+    assert s == _summaries()["degenerate_large"]
+    c = ctx.counts()
+    assert c.n_tier2 == 96 and c.n_tier3 == 48 and c.n_seq_cuts > 50

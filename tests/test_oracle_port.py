@@ -172,3 +172,21 @@ def test_port_matches_reference_build_directly():
         assert set(idx[off[i]:off[i + 1]]) <= set(i2[o2[i]:o2[i + 1]])
     c1, c2 = R.voronoi_cells(s, off, idx), P.voronoi_cells(s, o2, i2)
     assert np.array_equal(c1.nverts, c2.nverts) and np.array_equal(c1.nfaces, c2.nfaces)
+
+
+def test_port_degenerate_cuts_match_reference_fixture():
+    """Planes through vertices, edges and faces (comp == 0 band, Poly.cpp:303-319, 365-462): port == reference build."""
+    d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+    pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    got = P.apply_fracture(pieces, d["planes"], d["plane_off"])
+    assert_polysets_equal(got, want)
+
+
+def test_port_degenerate_cuts_on_large_pieces_match_reference_summary():
+    import json
+    pieces, planes, off = common.degenerate_large_inputs()
+    got = P.apply_fracture(pieces, planes, off, cap_frags=256, cap_verts=400000)
+    want = json.load(open(os.path.join(GOLDEN, "summaries.json")))["degenerate_large"]
+    s = common.summary_of_polyset(got)
+    s["ring"] = common.digest(np.asarray(got.ring, np.uint16))
+    assert s == want
