@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 N_SEEDS = 4096
 BASE_SEED = 46354
 WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fracture event per step per GPU"
+FLUSH_MIB = 160   # L2 flush buffer (B200 L2 = 126 MB), rewritten before every step
 E2E_DEPTH = 4     # events in flight in the end-to-end loop (contexts driven round-robin)
 
 
@@ -218,19 +219,19 @@ def main():
                                        plane_off=cells.plane_off, cverts=cells.verts, cvo=cells.vert_off).items()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in h_in.values())
 
-    def upload():
-        ctx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
-        ctx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
-                             h_in["cvo"].data_ptr(), N_SEEDS)
+    def upload_to(cx):
+        cx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
+        cx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
+                            h_in["cvo"].data_ptr(), N_SEEDS)
 
-    upload()
+    upload_to(ctx)
     ctx.fracture_event()
     c0 = ctx.counts()
     n_frag = int(c0.n_fragments)
     fr0 = ctx.download()
     alg_bytes = synth.algorithmic_bytes(cube_vo, cube_ro, cells.plane_off, fr0.rec)
 
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    flush = torch.empty(FLUSH_MIB * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def flush_l2():
         flush.zero_()
@@ -248,23 +249,64 @@ def main():
     if world > 1:
         dist.barrier()
 
-    # ---- timed region: K steps, device-resident inputs ----
+    # ---- contexts for the throughput loops: E2E_DEPTH events in flight, one context (= one stream) each ----
+    pipes = [(ctx, stream)]
+    for d in range(1, E2E_DEPTH):
+        st = torch.cuda.Stream(device=dev)
+        cx = FractureContext(local, st.cuda_stream)
+        cx.set_kdop_directions(args.kdop)
+        pipes.append((cx, st))
+
+    for cx, st in pipes[1:]:
+        upload_to(cx)
+        for _ in range(args.warmup):
+            cx.fracture_event()
+        assert int(cx.counts().n_fragments) == n_frag
+    torch.cuda.synchronize()
+
+    # ---- latency: K single events back to back on one stream, device-resident inputs ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     clip_ms = []
-    launches = 0
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush_l2()
         ev[i][0].record(stream)
         ctx.fracture_event()
         ev[i][1].record(stream)
-        launches += ctx.last_event_launches()
+    torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+
+    # ---- timed region: K steps, device-resident inputs, E2E_DEPTH events in flight ----
+    # One event does not fill the GPU (4096 warps of K3 = 28 per SM, issue-latency bound), so a job of K independent
+    # events is issued round-robin over the contexts.  Every stream rewrites the flush buffer before each of its steps
+    # (inside the timed region), so no step finds its inputs in L2.  Timed with CUDA events on stream 0: the start
+    # event gates the other streams, the stop event waits for all of them.
+    launches = 0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    t0_ev, t1_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0_ev.record(stream)
+    for cx, st in pipes[1:]:
+        st.wait_event(t0_ev)
+    for i in range(args.steps):
+        cx, st = pipes[i % E2E_DEPTH]
+        with torch.cuda.stream(st):
+            flush.zero_()
+        cx.fracture_event()
+        launches += cx.last_event_launches()
+    for cx, st in pipes[1:]:
+        done = torch.cuda.Event()
+        done.record(st)
+        stream.wait_event(done)
+    t1_ev.record(stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    # dominant-kernel duration for the roofline: same steps again with the engine's per-kernel CUDA events on
+    for cx, st in pipes:
+        assert int(cx.counts().n_fragments) == n_frag
+    # dominant-kernel duration for the roofline: single events again with the engine's per-kernel CUDA events on
     # (they sit between the kernels of an event and serialise the programmatic dependent launches, so the
-    # headline loop above runs without them)
+    # loops above run without them)
     ctx.set_profiling(True)
     for i in range(min(args.steps, 64)):
         flush_l2()
@@ -274,8 +316,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([float(np.sum(step_ms))], device=dev, dtype=torch.float64)
+    total_ms = torch.tensor([float(t0_ev.elapsed_time(t1_ev))], device=dev, dtype=torch.float64)
     frags = torch.tensor([float(n_frag * args.steps)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -288,7 +329,7 @@ def main():
     # round-robin from this one host thread through the C ABI -- download step i-DEPTH (blocks on that stream only),
     # then upload + launch step i -- so the PCIe copies of one event overlap the kernels of the others.  Every step
     # still moves its own inputs host->device and its own fragments device->host, and each stream first rewrites the
-    # 256 MiB flush buffer so that no step finds its working set in L2.
+    # flush buffer so that no step finds its working set in L2.
     c = ctx.counts()
     from surtr_b200 import FRAGMENT_DTYPE
 
@@ -300,11 +341,6 @@ def main():
 
     h_out = out_buffers()
     d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
-
-    def upload_to(cx):
-        cx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
-        cx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
-                            h_in["cvo"].data_ptr(), N_SEEDS)
 
     def download_from(cx, ho):
         cx.download_into(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
@@ -324,23 +360,22 @@ def main():
     assert got.tobytes() == fr0.rec.tobytes(), "e2e result differs from the resident-input result"
 
     # (2) E2E_DEPTH events in flight: the throughput number
-    pipes = []
-    for d in range(E2E_DEPTH):
-        st = stream if d == 0 else torch.cuda.Stream(device=dev)
-        cx = ctx if d == 0 else FractureContext(local, st.cuda_stream)
-        cx.set_kdop_directions(args.kdop)
-        pipes.append((cx, st, h_out if d == 0 else out_buffers()))
+    pipes = [(cx, st, h_out if d == 0 else out_buffers()) for d, (cx, st) in enumerate(pipes)]
 
     def pipelined(n_steps):
         for i in range(n_steps + E2E_DEPTH):
             cx, st, ho = pipes[i % E2E_DEPTH]
             if i >= E2E_DEPTH:
-                download_from(cx, ho)
+                # waits for event i-DEPTH (long finished when the depth is enough), then only ENQUEUES its device->host
+                # copies: the next upload + event are ordered behind them on the stream, the host moves on
+                cx.download_into_async(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
             if i < n_steps:
                 with torch.cuda.stream(st):
                     flush.zero_()
                 upload_to(cx)
                 cx.fracture_event()
+        for cx, st, ho in pipes:
+            cx.sync()                       # drain: the last copies have landed in the host buffers
 
     pipelined(2 * E2E_DEPTH)                # warm-up: every context grows its buffers once
     torch.cuda.synchronize()
@@ -354,8 +389,6 @@ def main():
     for cx, st, ho in pipes:
         got = np.frombuffer(ho["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
         assert got.tobytes() == fr0.rec.tobytes(), "pipelined e2e result differs from the resident-input result"
-    for cx, st, ho in pipes[1:]:
-        cx.close()
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -410,16 +443,20 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "fragments_per_step_per_gpu": n_frag, "pairs_per_step": int(c0.n_pairs),
                        "candidates_per_step": int(c0.n_candidates), "kdop_directions": args.kdop,
-                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events)",
-                       "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                       "events_in_flight": E2E_DEPTH,
+                       "l2": f"flushed before every step ({FLUSH_MIB} MiB rewritten on the step's own stream, inside the timed region)",
+                       "timing": "CUDA events on stream 0 around the K steps (start gates, stop joins all streams), max over ranks",
                        "parallelism": f"events sharded over {world} GPU(s), no data-path collective"},
-            "p50_event_ms": float(np.median(step_ms)), "wall_s_timed_region": t_wall,
+            "p50_event_ms": float(np.median(step_ms)),
+            "single_stream": {"value": n_frag * world / (float(np.mean(step_ms)) * 1e-3), "ms_per_step": float(np.mean(step_ms)),
+                              "note": "one event at a time, per-step CUDA events, L2 flushed between steps outside the events"},
+            "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
                     "events_in_flight": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
                     "timing": "wall clock around K x (upload + event + download) through the C ABI, pinned host buffers, "
                               f"{E2E_DEPTH} contexts round-robin from one host thread, L2 flush on every stream inside the "
-                              "timed region; single_event_ms = the same with one event at a time"},
+                              "timed region; single_event_ms = the same with one event at a time (flush outside)"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
             "clocks": clocks, "roofline": roofline,
         }
@@ -432,6 +469,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    for cx, st, ho in pipes[1:]:
+        cx.close()
     ctx.close()
 
 

@@ -596,7 +596,7 @@ int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out)
     return SURTR_OK;
 }
 
-int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off, uint16_t* ring)
+int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off, uint16_t* ring)
 {
     if (!ctx) return SURTR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -611,8 +611,21 @@ int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* v
         CK(cudaMemcpyAsync(ring_off, ctx->f_ring_off.p, 4 * (c.n_verts + 1), cudaMemcpyDeviceToHost, ctx->stream));
     if (ring && c.n_ring)
         CK(cudaMemcpyAsync(ring, ctx->f_ring.p, 2 * c.n_ring, cudaMemcpyDeviceToHost, ctx->stream));
+    return SURTR_OK;
+}
+
+int surtr_sync(surtr_ctx* ctx)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return SURTR_OK;
+}
+
+int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off, uint16_t* ring)
+{
+    const int rc = surtr_download_fragments_async(ctx, fragments, verts4, ring_off, ring);
+    return rc ? rc : surtr_sync(ctx);
 }
 
 int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out)

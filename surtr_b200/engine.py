@@ -32,7 +32,7 @@ EXPORTS = [
     "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
-    "surtr_upload_pattern", "surtr_place_pattern",
+    "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
 ]
 
 
@@ -79,6 +79,8 @@ def load_library():
     lib.surtr_fracture_event.argtypes = [vp]
     lib.surtr_event_counts.argtypes = [vp, C.POINTER(Counts)]
     lib.surtr_download_fragments.argtypes = [vp, vp, vp, vp, vp]
+    lib.surtr_download_fragments_async.argtypes = [vp, vp, vp, vp, vp]
+    lib.surtr_sync.argtypes = [vp]
     lib.surtr_device_fragments.argtypes = [vp, C.POINTER(DeviceView)]
     lib.surtr_kdop_calc.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -220,6 +222,14 @@ class FractureContext:
         """D2H into caller-owned (e.g. pinned) buffers; sizes from counts()."""
         self._ck(self._lib.surtr_download_fragments(self._h, C.c_void_p(rec), C.c_void_p(verts), C.c_void_p(ring_off),
                                                     C.c_void_p(ring)))
+
+    def download_into_async(self, rec, verts, ring_off, ring):
+        """Enqueue the D2H copies only; the buffers are complete after sync() (or the next counts())."""
+        self._ck(self._lib.surtr_download_fragments_async(self._h, C.c_void_p(rec), C.c_void_p(verts), C.c_void_p(ring_off),
+                                                          C.c_void_p(ring)))
+
+    def sync(self):
+        self._ck(self._lib.surtr_sync(self._h))
 
     def upload_pieces_ptr(self, verts4, vert_off, ring_off, ring, n_pieces, ev=None, n_events=0):
         self._ck(self._lib.surtr_upload_pieces(self._h, C.c_void_p(verts4), C.c_void_p(vert_off), C.c_void_p(ring_off),
