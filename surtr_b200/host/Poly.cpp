@@ -41,8 +41,35 @@ std::vector<std::vector<int>> ExtractNeighborFromMesh(const std::vector<Vector3>
 			inc[fill[indices[3 * t + k]]++] = t;
 	const auto touches = [&](const int t, const int v) { return indices[3 * t] == v || indices[3 * t + 1] == v || indices[3 * t + 2] == v; };
 
+	// per-triangle adjacency, duplicates removed in first-seen order (:150-170), as one CSR
+	std::vector<int> adj_off(n_tri + 1, 0), adj;
+	adj.reserve(4 * (size_t)n_tri);
+	for (int curr = 0; curr < n_tri; curr++)
+	{
+		const size_t begin = adj.size();
+		for (int e = 0; e < 3; e++)
+		{
+			const int a = indices[3 * curr + e], b = indices[3 * curr + (e + 1) % 3];
+			const int* pa = &inc[inc_off[a]], * ea = &inc[inc_off[a + 1]];
+			const int* pb = &inc[inc_off[b]], * eb = &inc[inc_off[b + 1]];
+			while (pa != ea && pb != eb)   // std::set_intersection of two ascending lists (:156-158)
+			{
+				if (*pa < *pb) ++pa;
+				else if (*pb < *pa) ++pb;
+				else
+				{
+					const int t = *pa;
+					++pa; ++pb;
+					if (t != curr && adj.end() == std::find(adj.begin() + begin, adj.end(), t))
+						adj.push_back(t);
+				}
+			}
+		}
+		adj_off[curr + 1] = (int)adj.size();
+	}
+
 	std::vector<std::vector<int>> nei(n_vert);
-	std::vector<int> fan, across;
+	std::vector<int> fan;
 	for (int iVert = 0; iVert < n_vert; iVert++)
 	{
 		if (inc_off[iVert] == inc_off[iVert + 1])
@@ -51,30 +78,13 @@ std::vector<std::vector<int>> ExtractNeighborFromMesh(const std::vector<Vector3>
 		for (int curr = fan[0];;)
 		{
 			int next = -1, n_candidates = 0;
-			across.clear();   // curr's adjacency list, duplicates removed in first-seen order (:163-168)
-			for (int e = 0; e < 3; e++)
-			{
-				const int a = indices[3 * curr + e], b = indices[3 * curr + (e + 1) % 3];
-				const int* pa = &inc[inc_off[a]], * ea = &inc[inc_off[a + 1]];
-				const int* pb = &inc[inc_off[b]], * eb = &inc[inc_off[b + 1]];
-				while (pa != ea && pb != eb)   // std::set_intersection of two ascending lists (:156-158)
-				{
-					if (*pa < *pb) ++pa;
-					else if (*pb < *pa) ++pb;
-					else
-					{
-						const int t = *pa;
-						++pa; ++pb;
-						if (t != curr && across.end() == std::find(across.begin(), across.end(), t))
-							across.push_back(t);
-					}
-				}
-			}
-			for (const int t : across)
-				if (fan.end() == std::find(fan.begin(), fan.end(), t) && touches(t, iVert))
+			const int* across_begin = adj.data() + adj_off[curr];
+			const int* across_end = adj.data() + adj_off[curr + 1];
+			for (const int* it = across_begin; it != across_end; ++it)
+				if (fan.end() == std::find(fan.begin(), fan.end(), *it) && touches(*it, iVert))
 				{
 					if (n_candidates++ == 0)
-						next = t;
+						next = *it;
 				}
 			if (n_candidates == 0)
 				break;

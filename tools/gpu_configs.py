@@ -1,12 +1,66 @@
-"""Dev/measurement: BASELINE configs 3, 4, 5 at (or near) full size on one GPU: parity fingerprints + timings."""
-import json, sys, time, numpy as np
+"""Measurement: BASELINE configs 1, 3, 4, 5 at (or near) full size on one GPU -- parity fingerprints, GPU timings and the
+reference build's CPU timings (oracle/_ref, dp::thread_pool(16) fan-out + SetExtract, the reference's own timer) on
+the same box.  Writes gpurun_out/configs_r1.json (copied to profiles/)."""
+import json, os, sys, time, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import torch
 from surtr_b200 import FractureContext, synth
 import common
+from oracle import refapi as R
 
-out = {}
+HAVE_REF = R.available()
+CPU_THREADS = max(16, os.cpu_count() or 1)
+
+
+def cpu_seconds(pieces, cells, reps=1):
+    """Reference CPU time of one event (fan-out + SetExtract), best of reps."""
+    if not HAVE_REF:
+        return None
+    return min(R.apply_fracture(pieces, cells.planes, cells.plane_off, CPU_THREADS, moments=False).seconds for _ in range(reps))
+
+out = {"host": {"nproc": os.cpu_count(), "cpu_threads_used": CPU_THREADS, "reference_build": HAVE_REF}}
+try:
+    out["host"]["cpu_model"] = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+except Exception:
+    pass
 ctx = FractureContext(0)
+
+# config 1: bunny, 32 seeds, full PrepareFracture through the host classes (two GPU events + refit) vs the restatement
+# over the reference build
+import hostapi
+d1 = np.load("tests/golden/config1_full_bunny32.npz")
+hostapi.config1_full(d1["verts"], d1["indices"], d1["seeds"])            # warm-up (context creation, tier enabling)
+ts = []
+for _ in range(5):
+    t0 = time.perf_counter(); c1, m1, _ = hostapi.config1_full(d1["verts"], d1["indices"], d1["seeds"]); ts.append(time.perf_counter() - t0)
+off1, idx1 = hostapi.dt3d_neighbors(d1["seeds"])
+cpu1 = None
+if HAVE_REF:
+    t0 = time.perf_counter(); R.config1_full(d1["verts"], d1["indices"], d1["seeds"], off1, idx1); cpu1 = time.perf_counter() - t0
+out["config1"] = {"pieces": c1.n, "host_classes_wall_ms": 1e3 * float(np.median(ts)), "reference_cpu_wall_ms": None if cpu1 is None else 1e3 * cpu1,
+                  "note": "wall clock of the whole PrepareFracture (ICH, k-DOP, ACH, mesh rings, DT3D cells, convex + mesh clip, islands, refit, extract); reference: single thread, inline"}
+print(out["config1"], flush=True)
+
+# config 1, second stage: the reference's real event path, one DoFracture (32-cell radial pattern at an impact point) on
+# the 27-piece compound PrepareFracture produced
+from test_oracle_port import load_polyset
+dd = np.load("tests/golden/do_fracture_bunny.npz")
+cvx, msh = load_polyset(d1, "convex_"), load_polyset(d1, "mesh_")
+for mode in ("general", "partial"):
+    a = (cvx, msh, dd[mode + "_seeds"], dd["cloud"], dd["impact"], float(dd[mode + "_radius"]), float(dd["max_axis_scale"]), mode == "partial")
+    hostapi.do_fracture(*a)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); r = hostapi.do_fracture(*a); ts.append(time.perf_counter() - t0)
+    cpu = None
+    if HAVE_REF:
+        o, i = hostapi.dt3d_neighbors(dd[mode + "_seeds"])
+        t0 = time.perf_counter()
+        R.do_fracture(cvx, msh, dd[mode + "_seeds"], o, i, dd["cloud"], dd["impact"], float(dd[mode + "_radius"]), float(dd["max_axis_scale"]), mode == "partial")
+        cpu = time.perf_counter() - t0
+    out["config1_do_fracture_" + mode] = {"pieces": r[0].n, "compounds": r[2], "host_classes_wall_ms": 1e3 * float(np.median(ts)),
+                                          "reference_cpu_wall_ms": None if cpu is None else 1e3 * cpu}
+    print(mode, out["config1_do_fracture_" + mode], flush=True)
 def timed_events(n=30):
     ts = []
     for _ in range(n):
@@ -20,7 +74,8 @@ p50, best = timed_events(100)
 c = ctx.counts()
 out["config3"] = {"pieces": 10000, "cells": 256, "pairs": int(c.n_pairs), "candidates": int(c.n_candidates), "fragments": fr.n,
                   "p50_event_ms": p50, "min_event_ms": best, "fragments_per_s": fr.n / (p50 * 1e-3),
-                  "fingerprint_matches_reference": common.summary_of_fragments(fr) == json.load(open("tests/golden/summaries.json"))["config3_10000x256"]}
+                  "fingerprint_matches_reference": common.summary_of_fragments(fr) == json.load(open("tests/golden/summaries.json"))["config3_10000x256"],
+                  "reference_cpu_event_ms": None if not HAVE_REF else 1e3 * cpu_seconds(pieces, cells, 2)}
 print(out["config3"], flush=True)
 
 # config 4: N independent events (1000 pieces x 64 cells each) in one batch on one GPU
@@ -39,7 +94,8 @@ c = ctx.counts()
 per_event = [common.run_gpu(FractureContext(0), base_p[e], base_c[e]).n for e in range(2)]
 out["config4"] = {"events": n_ev, "pairs": int(c.n_pairs), "candidates": int(c.n_candidates), "fragments": fr.n,
                   "p50_batch_ms": p50, "fragments_per_s": fr.n / (p50 * 1e-3), "events_per_s": n_ev / (p50 * 1e-3),
-                  "event0_fragments": per_event[0]}
+                  "event0_fragments": per_event[0],
+                  "reference_cpu_event0_ms": None if not HAVE_REF else 1e3 * cpu_seconds(base_p[0], base_c[0], 3)}
 print(out["config4"], flush=True)
 
 # config 5: depth-3 recursion for many objects at once (objects = events; fragments stay on the device)
@@ -62,7 +118,14 @@ for lvl, cells in enumerate(levels):
     ev_of_frag = np.searchsorted(ev_c, rec["cell"], side="right") - 1
     new_ev = np.concatenate([[0], np.cumsum(np.bincount(ev_of_frag, minlength=n_obj))]).astype(np.uint32)
     ctx2.fragments_to_pieces(new_ev)
-out["config5"] = {"objects": n_obj, "fragments_per_level": counts, "per_object": [x // n_obj for x in counts],
+cpu5 = None
+if HAVE_REF:
+    cpu5, pcs = 0.0, cube
+    for cells in levels:
+        r = R.apply_fracture(pcs, cells.planes, cells.plane_off, CPU_THREADS, moments=False)
+        cpu5 += r.seconds
+        pcs = r
+out["config5"] = {"objects": n_obj, "reference_cpu_per_object_ms": None if cpu5 is None else 1e3 * cpu5, "fragments_per_level": counts, "per_object": [x // n_obj for x in counts],
                   "sum_event_ms": tot_ms, "final_fragments_per_s": counts[-1] / (tot_ms * 1e-3)}
 print(out["config5"], flush=True)
 json.dump(out, open("gpurun_out/configs_r1.json", "w"), indent=1)
