@@ -1,6 +1,12 @@
 #include "Engine.h"
 
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <exception>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 #include <stdexcept>
 #include <string>
@@ -117,6 +123,122 @@ void check(int rc, const char* what)
 	surtr_ctx* c = nullptr;
 	try { c = context(); } catch (...) {}
 	throw std::runtime_error(std::string(what) + ": " + surtr_last_error(c));
+}
+
+namespace
+{
+class WorkerPool
+{
+	// one object per parallel_for call: a worker that wakes up late finds either a finished job (nothing left to take)
+	// or the current one, never a mixture of the two
+	struct Job
+	{
+		const std::function<void(size_t)>* fn;
+		size_t n;
+		std::atomic<size_t> next{ 0 };
+		size_t done = 0;              // guarded by the pool mutex
+		std::exception_ptr error;     // likewise
+	};
+
+public:
+	WorkerPool()
+	{
+		const unsigned hw = std::thread::hardware_concurrency();
+		const unsigned n = std::min(16u, hw ? hw : 1u);   // the reference's pool has 16 threads
+		for (unsigned i = 1; i < n; i++)
+			m_threads.emplace_back([this] { loop(); });
+	}
+	~WorkerPool()
+	{
+		{
+			std::lock_guard<std::mutex> lock(m_mutex);
+			m_quit = true;
+		}
+		m_wake.notify_all();
+		for (std::thread& t : m_threads)
+			t.join();
+	}
+	void run(size_t n, const std::function<void(size_t)>& fn)
+	{
+		auto job = std::make_shared<Job>();
+		job->fn = &fn;
+		job->n = n;
+		{
+			std::lock_guard<std::mutex> lock(m_mutex);
+			m_job = job;
+			m_generation++;
+		}
+		m_wake.notify_all();
+		work(*job);
+		std::unique_lock<std::mutex> lock(m_mutex);
+		m_done.wait(lock, [&] { return job->done == n; });   // every index was taken AND finished; fn stays alive until here
+		if (m_job == job)
+			m_job.reset();
+		if (job->error)
+			std::rethrow_exception(job->error);
+	}
+
+private:
+	void work(Job& job)
+	{
+		size_t finished = 0;
+		std::exception_ptr err;
+		for (;;)
+		{
+			const size_t i = job.next.fetch_add(1);
+			if (i >= job.n)
+				break;
+			try { (*job.fn)(i); }
+			catch (...) { if (!err) err = std::current_exception(); }
+			finished++;
+		}
+		if (!finished)
+			return;
+		{
+			std::lock_guard<std::mutex> lock(m_mutex);
+			job.done += finished;
+			if (err && !job.error)
+				job.error = err;
+		}
+		m_done.notify_all();
+	}
+	void loop()
+	{
+		uint64_t seen = 0;
+		for (;;)
+		{
+			std::shared_ptr<Job> job;
+			{
+				std::unique_lock<std::mutex> lock(m_mutex);
+				m_wake.wait(lock, [&] { return m_quit || m_generation != seen; });
+				if (m_quit)
+					return;
+				seen = m_generation;
+				job = m_job;
+			}
+			if (job)
+				work(*job);
+		}
+	}
+	std::vector<std::thread> m_threads;
+	std::mutex m_mutex;
+	std::condition_variable m_wake, m_done;
+	std::shared_ptr<Job> m_job;
+	uint64_t m_generation = 0;
+	bool m_quit = false;
+};
+} // namespace
+
+void parallel_for(size_t n, const std::function<void(size_t)>& fn)
+{
+	if (n < 8)
+	{
+		for (size_t i = 0; i < n; i++)
+			fn(i);
+		return;
+	}
+	static WorkerPool pool;
+	pool.run(n, fn);
 }
 
 surtr_ctx* context()

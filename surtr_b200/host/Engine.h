@@ -7,6 +7,7 @@
 #include "VMACH.h"
 
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace SurtrHost
@@ -56,6 +57,11 @@ struct Fragments
 	std::vector<uint16_t> ring;
 	Poly::Polyhedron polyhedron(size_t i) const;
 };
+
+// Host worker pool for the per-piece bookkeeping around an event (the reference's g_threadPool, Surtr.cpp:28: one task
+// per piece for refitting, :2405-2413).  Calls fn(i) for every i in [0, n), the caller's thread included; returns when
+// all are done; the first exception thrown by a task is rethrown here.  Small n runs inline.
+void parallel_for(size_t n, const std::function<void(size_t)>& fn);
 
 surtr_ctx* context();                                            // throws std::runtime_error without a B200
 void check(int rc, const char* what);                            // throws std::runtime_error with surtr_last_error

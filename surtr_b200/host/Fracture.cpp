@@ -6,11 +6,37 @@
 #include "Kdop.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
+#include <memory>
 #include <random>
 
 namespace SurtrHost
 {
+namespace
+{
+// SURTR_TRACE=1 prints the wall time of every orchestration phase to stderr (the reference's TIMER_START_NAME /
+// TIMER_STOP_PRINT around the same phases, Surtr.cpp:1917-1944).
+struct Phase
+{
+	const char* name;
+	std::chrono::steady_clock::time_point t0;
+	static bool enabled()
+	{
+		static const bool on = std::getenv("SURTR_TRACE") != nullptr;
+		return on;
+	}
+	explicit Phase(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+	~Phase()
+	{
+		if (enabled())
+			std::fprintf(stderr, "[surtr] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+} // namespace
+
 std::vector<Vector3> GenerateSeeds(int seed, int cellCount)
 {
 	std::vector<Vector3> cellPointVec;
@@ -243,9 +269,13 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 				cells.add(cell);
 		else
 			detail::place_pattern(*source.pattern, source.scale, source.translate);
-		detail::run_event(pieces, cells, fr, true, source.polys != nullptr);
+		{
+			Phase ph("  convex event");
+			detail::run_event(pieces, cells, fr, true, source.polys != nullptr);
+		}
 		if (meshBranch)
 		{
+			Phase ph("  mesh event");
 			// event 2, the second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident
 			// cells.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
 			// its convex and its mesh fragment exist (:1466-1472).
@@ -267,6 +297,7 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 		detail::run_event(pieces, keep, ofr, false);
 	}
 
+	Phase ph_unpack("  unpack + islands");
 	CompoundInfo info;
 	const auto mass_of = [](const surtr_fragment& r) {
 		MassProperties mp;
@@ -289,53 +320,67 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	for (const surtr_fragment& r : ofr.rec)
 		info.PieceMass[r.piece] = mass_of(r);
 	(void)n_cells;
-	int current_cell = -1;
-	size_t m = 0;
+	// match every convex fragment with its mesh fragment (both lists are cell-major, piece-minor) ...
 	const auto key = [](const surtr_fragment& r) { return ((uint64_t)r.cell << 32) | r.piece; };
+	std::vector<std::pair<size_t, size_t>> matched;   // (convex fragment, mesh fragment)
+	size_t m = 0;
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
-		const surtr_fragment& r = fr.rec[f];
-		const Poly::Polyhedron convex = fr.polyhedron(f);
-		std::vector<Poly::Polyhedron> meshes;
-		if (meshBranch)
+		if (!meshBranch)
 		{
-			while (m < mfr.rec.size() && key(mfr.rec[m]) < key(r))   // both lists are cell-major, piece-minor
-				m++;
-			if (m == mfr.rec.size() || key(mfr.rec[m]) != key(r))
-				continue;   // mesh clipped away (Surtr.cpp:1471)
-			const Poly::Polyhedron mesh = mfr.polyhedron(m);
-			const std::vector<std::set<int>> groupVec = CheckMeshIsland(mesh);
-			if (groupVec.size() >= 2)
+			matched.emplace_back(f, f);
+			continue;
+		}
+		while (m < mfr.rec.size() && key(mfr.rec[m]) < key(fr.rec[f]))
+			m++;
+		if (m < mfr.rec.size() && key(mfr.rec[m]) == key(fr.rec[f]))   // otherwise: mesh clipped away (Surtr.cpp:1471)
+			matched.emplace_back(f, m);
+	}
+	// ... build the pieces of every pair on the worker pool (AoS conversion + island split, Surtr.cpp:1474-1500) ...
+	std::vector<std::vector<Piece*>> built(matched.size());
+	detail::parallel_for(matched.size(), [&](size_t k) {
+		const Poly::Polyhedron convex = fr.polyhedron(matched[k].first);
+		if (!meshBranch)
+		{
+			built[k].push_back(new Piece(convex, convex));
+			return;
+		}
+		const Poly::Polyhedron mesh = mfr.polyhedron(matched[k].second);
+		const std::vector<std::set<int>> groupVec = CheckMeshIsland(mesh);
+		if (groupVec.size() >= 2)
+		{
+			std::vector<int> mapping(mesh.size(), -1);
+			for (const std::set<int>& group : groupVec)
 			{
-				std::vector<int> mapping(mesh.size(), -1);
-				for (const std::set<int>& group : groupVec)   // Surtr.cpp:1475-1495
+				Poly::Polyhedron island;
+				for (const int iVert : group)
 				{
-					Poly::Polyhedron island;
-					for (const int iVert : group)
-					{
-						mapping[iVert] = (int)island.size();
-						island.push_back(mesh[iVert]);
-					}
-					for (Poly::Vertex& vert : island)
-						for (int& iAdj : vert.NeighborVertexVec)
-							iAdj = mapping[iAdj];
-					meshes.push_back(std::move(island));
+					mapping[iVert] = (int)island.size();
+					island.push_back(mesh[iVert]);
 				}
+				for (Poly::Vertex& vert : island)
+					for (int& iAdj : vert.NeighborVertexVec)
+						iAdj = mapping[iAdj];
+				built[k].push_back(new Piece(convex, island));
 			}
-			else
-				meshes.push_back(mesh);
 		}
 		else
-			meshes.push_back(convex);
-		for (Poly::Polyhedron& mesh : meshes)
+			built[k].push_back(new Piece(convex, mesh));
+	});
+	// ... and bind them in order: one set per cell that produced pieces, cell order (Surtr.cpp:2133-2146)
+	int current_cell = -1;
+	for (size_t k = 0; k < matched.size(); k++)
+	{
+		const surtr_fragment& r = fr.rec[matched[k].first];
+		for (Piece* piece : built[k])
 		{
-			if ((int)r.cell != current_cell)   // one bind set per cell that produced pieces, cell order (Surtr.cpp:2133-2146)
+			if ((int)r.cell != current_cell)
 			{
 				info.CompoundBind.push_back(std::set<int>());
 				current_cell = (int)r.cell;
 			}
 			info.CompoundBind.back().insert((int)info.PieceVec.size());
-			info.PieceVec.push_back(new Piece(convex, mesh));
+			info.PieceVec.push_back(piece);
 			info.PieceMass.push_back(mass_of(r));
 			info.PieceSourceCell.push_back((int)r.cell);
 			info.PieceSourcePiece.push_back(inside[r.piece]);
@@ -350,8 +395,7 @@ void SetExtract(CompoundInfo& preResult)
 	for (Extract* e : preResult.PieceExtractedConvex)
 		delete e;   // the reference leaks the previous lists (Surtr.cpp:2151-2155 overwrites the pointers)
 	preResult.PieceExtractedConvex.assign(preResult.PieceVec.size(), nullptr);
-	for (size_t i = 0; i < preResult.PieceVec.size(); i++)
-		preResult.PieceExtractedConvex[i] = Poly::ExtractFaces(preResult.PieceVec[i]->Convex);
+	detail::parallel_for(preResult.PieceVec.size(), [&](size_t i) { preResult.PieceExtractedConvex[i] = Poly::ExtractFaces(preResult.PieceVec[i]->Convex); });
 }
 
 void MergeOutOfImpact(CompoundInfo& compoundInfo, const std::vector<Vector3>& spherePointCloud, const FractureArgs& args)
@@ -501,13 +545,26 @@ std::vector<Compound> DoFracture(const Compound& targetCompound, const FractureS
 	source.pattern = &pattern;
 	source.scale = Vector3(storage.MaxAxisScale, storage.MaxAxisScale, storage.MaxAxisScale) * 2;
 	source.translate = args.ImpactPosition;
-	CompoundInfo second = apply_fracture(targetCompound, source, localSpherePointCloud, args.PartialFracture, args, true);
-	SetExtract(second);
+	CompoundInfo second;
+	{
+		Phase ph("ApplyFracture");
+		second = apply_fracture(targetCompound, source, localSpherePointCloud, args.PartialFracture, args, true);
+		SetExtract(second);
+	}
 	if (args.PartialFracture)
+	{
+		Phase ph("MergeOutOfImpact");
 		MergeOutOfImpact(second, localSpherePointCloud, args);
-	HandleConvexIsland(second);
-	Refitting(second.PieceVec, args, &second.PieceMass);
-	SetExtract(second);
+	}
+	{
+		Phase ph("HandleConvexIsland");
+		HandleConvexIsland(second);
+	}
+	{
+		Phase ph("Refitting");
+		Refitting(second.PieceVec, args, &second.PieceMass);
+		SetExtract(second);
+	}
 
 	std::vector<Compound> result;
 	for (const std::set<int>& iComp : second.CompoundBind)
@@ -567,28 +624,36 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, st
 	if (!n)
 		return;
 	// 1. ICH normals per piece (host; <= 4 points by default)
+	Phase* ph = new Phase("  refit: ICH normals");
+	std::vector<std::vector<Vector3>> piece_normals(n);
+	detail::parallel_for(n, [&](size_t i) {   // one task per piece, like the reference's pool (Surtr.cpp:2405-2413)
+		std::vector<Vector3> pts;
+		pts.reserve(targetPieceVec[i]->Mesh.size());
+		for (const Poly::Vertex& v : targetPieceVec[i]->Mesh)
+			pts.push_back(v.Position);
+		piece_normals[i] = VMACH::GenerateICHNormal(pts, std::min((int)pts.size(), args.RefittingPointLimit));
+	});
 	std::vector<float> verts4, normals3;
 	std::vector<uint32_t> vert_off{ 0 }, normal_off{ 0 };
-	for (const Piece* p : targetPieceVec)
+	for (uint32_t i = 0; i < n; i++)
 	{
-		std::vector<Vector3> pts;
-		for (const Poly::Vertex& v : p->Mesh)
-		{
-			pts.push_back(v.Position);
+		for (const Poly::Vertex& v : targetPieceVec[i]->Mesh)
 			verts4.insert(verts4.end(), { v.Position.x, v.Position.y, v.Position.z, 0.f });
-		}
 		vert_off.push_back((uint32_t)(verts4.size() / 4));
-		const std::vector<Vector3> nrm = VMACH::GenerateICHNormal(pts, std::min((int)pts.size(), args.RefittingPointLimit));
-		for (const Vector3& nv : nrm)
+		for (const Vector3& nv : piece_normals[i])
 			normals3.insert(normals3.end(), { nv.x, nv.y, nv.z });
 		normal_off.push_back((uint32_t)(normals3.size() / 3));
 	}
+	delete ph;
+	ph = new Phase("  refit: k-DOP batch");
 	// 2. k-DOP extents of every piece->Mesh on the GPU (Kdop::Calc(Polyhedron), Kdop.cpp:92-115)
 	const size_t nn = normals3.size() / 3;
 	std::vector<float> dist(2 * nn), planes8(8 * nn);
 	std::vector<int32_t> arg(2 * nn);
 	detail::check(surtr_kdop_calc_batch(detail::context(), verts4.data(), vert_off.data(), n, normals3.data(), normal_off.data(),
 										dist.data(), arg.data(), planes8.data()), "surtr_kdop_calc_batch");
+	delete ph;
+	ph = new Phase("  refit: clip event + unpack");
 	// 3. clip piece->Convex by its own plane list: n independent events of one piece x one cell
 	detail::FlatPolys pieces;
 	detail::FlatCells cells;
@@ -623,10 +688,11 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, st
 		p->Convex.clear();
 	if (mass)
 		mass->assign(n, MassProperties());   // a convex that the refit clips away has no mass left
+	std::unique_ptr<Phase> ph_guard(ph);
+	detail::parallel_for(fr.rec.size(), [&](size_t f) { targetPieceVec[fr.rec[f].piece]->Convex = fr.polyhedron(f); });   // one fragment per piece
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
 		const surtr_fragment& r = fr.rec[f];
-		targetPieceVec[r.piece]->Convex = fr.polyhedron(f);
 		if (mass)
 		{
 			MassProperties& mp = (*mass)[r.piece];
