@@ -5,7 +5,11 @@
 #include "Fracture.h"
 #include "Kdop.h"
 
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <thread>
 #include <stdexcept>
 #include <string>
 
@@ -329,6 +333,36 @@ int hosttest_apply_fracture_mesh(const float* cv, const uint32_t* cvo, const uin
 		return 0;
 	}
 	catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// detail::parallel_for (CPU only): every index exactly once, from more than one thread for large n; a throwing task
+// surfaces as the call's exception after all other tasks ran.  Returns 0 on success.
+int hosttest_parallel_for(uint32_t n, uint32_t throw_at, uint32_t* n_threads_seen)
+{
+	std::vector<std::atomic<int>> hits(n);
+	for (auto& h : hits) h.store(0);
+	std::mutex mu;
+	std::set<std::thread::id> ids;
+	bool thrown = false;
+	try
+	{
+		SurtrHost::detail::parallel_for(n, [&](size_t i) {
+			hits[i].fetch_add(1);
+			{
+				std::lock_guard<std::mutex> lock(mu);
+				ids.insert(std::this_thread::get_id());
+			}
+			volatile double x = 0;
+			for (int k = 0; k < 2000; k++) x = x + k * 0.5;
+			if (i == throw_at) throw std::runtime_error("task failed");
+		});
+	}
+	catch (const std::runtime_error&) { thrown = true; }
+	*n_threads_seen = (uint32_t)ids.size();
+	for (uint32_t i = 0; i < n; i++)
+		if (hits[i].load() != 1) { g_err = "index not visited exactly once"; return 1; }
+	if (thrown != (throw_at < n)) { g_err = "exception not propagated"; return 2; }
+	return 0;
 }
 
 // SurtrHost::CombineMass (CPU only): per piece volume, centroid[3], inertia[6] -> {mass, c[3], I[6]}

@@ -218,3 +218,13 @@ def test_do_fracture_bunny(mode):
             c_ref = (want_c.volume[sel, None] * want_c.centroid[sel]).sum(0) / want_c.volume[sel].sum()
             assert np.abs(mass[b, 1:4] - c_ref).max() < 1e-4
             assert mass[b, 4:7].min() > 0
+
+
+def test_host_worker_pool():
+    """detail::parallel_for: every index exactly once, repeated jobs of different sizes, exceptions propagate."""
+    import ctypes as C
+    L = H.lib()
+    seen = C.c_uint32(0)
+    for n, throw_at in ((3, 99), (64, 99), (1000, 99), (17, 5), (1000, 999), (8, 99), (5000, 99)):
+        assert L.hosttest_parallel_for(n, throw_at, C.byref(seen)) == 0, H._err()
+    assert seen.value >= 1
