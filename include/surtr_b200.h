@@ -110,6 +110,16 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
  * NULL to keep one event. */
 int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events);
 
+/* World transform of the resident pieces, in place: replaces the host loop of Surtr::ExecuteFractureRoutine
+ * (Src/Surtr.cpp:1846-1852) that runs Poly::Transform (Src/Poly.cpp:580-585) over every piece before DoFracture.
+ * matrices16: n_matrices row-major 4x4 matrices exactly as the reference hands them to Poly::Transform (it transposes
+ * them itself); piece_matrix[n_pieces] selects the matrix of each piece, NULL = matrix 0 for every piece.  Together
+ * with surtr_fragments_to_pieces this keeps a compound on the device across events: only 64 bytes per rigid body
+ * travel per event. */
+int surtr_transform_pieces(surtr_ctx* ctx, const float* matrices16, const uint32_t* piece_matrix, uint32_t n_matrices);
+/* Vertex positions of the resident pieces (after transforms), n_verts x float4, synchronous. */
+int surtr_download_pieces(surtr_ctx* ctx, float* verts4);
+
 /* A fracture pattern kept on the device in its own frame and placed per event.  Replaces the host loop
  * Surtr::DoFracture runs over a copy of the pattern before every event (Src/Surtr.cpp:1887-1896): Polygon3D::Scale
  * + Polygon3D::Translate (Src/VMACH.cpp:506-534), which move every face vertex and re-derive every face plane from

@@ -1041,6 +1041,21 @@ int ref_mesh_polyhedron(const float* verts4, uint32_t nv, const int32_t* indices
 	return 0;
 }
 
+// Poly::Transform (Poly.cpp:580-585) on a vertex list with one row-major matrix.
+void ref_transform(const float* verts4, uint32_t nv, const float* matrix16, float* out4)
+{
+	Poly::Polyhedron p(nv);
+	for (uint32_t v = 0; v < nv; v++)
+		p[v].Position = Vector3(verts4[4 * v], verts4[4 * v + 1], verts4[4 * v + 2]);
+	DirectX::XMMATRIX m;
+	std::memcpy(m.r, matrix16, 64);
+	Poly::Transform(p, m);
+	for (uint32_t v = 0; v < nv; v++)
+	{
+		out4[4 * v] = p[v].Position.x; out4[4 * v + 1] = p[v].Position.y; out4[4 * v + 2] = p[v].Position.z; out4[4 * v + 3] = verts4[4 * v + 3];
+	}
+}
+
 // Scalar helpers for the unit KATs (Poly.cpp:716-751).
 int ref_compare_plane_point(const float* plane, const float* p)
 {

@@ -338,3 +338,14 @@ def do_fracture(convex: PolySet, mesh: PolySet, seeds, nb_off, nb_idx, cloud, im
                       _p(seeds), len(seeds), _p(nb_off), _p(nb_idx), _p(cloud), len(cloud), _p(impact),
                       impact_radius, max_axis_scale, int(partial), refit_limit, hc, hm, C.byref(ncomp))
     return _export(hc), _export(hm), ncomp.value
+
+
+def transform(verts4, matrix16) -> np.ndarray:
+    """Poly::Transform (Poly.cpp:580-585): row-major world matrix, transposed inside like the reference does."""
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    m = np.ascontiguousarray(matrix16, np.float32).reshape(16)
+    out = np.zeros_like(verts4)
+    L = lib()
+    L.ref_transform.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.ref_transform(_p(verts4), len(verts4), _p(m), _p(out))
+    return out

@@ -153,6 +153,31 @@ __global__ void __launch_bounds__(256) place_pattern_kernel(const float4* __rest
     c_planes[(size_t)p * n_faces + f] = plane_from_points(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8]);
 }
 
+// Poly::Transform (Poly.cpp:580-585) over the resident pieces: position = XMVector3TransformCoord(position, M^T) with the
+// piece's world matrix M (row-major as the caller holds it; the reference transposes before use), i.e. per output
+// component c: ((z*M[c][2] + M[c][3]) + y*M[c][1]) + x*M[c][0], then a division by the w component.  One warp per piece.
+__global__ void __launch_bounds__(256) transform_pieces_kernel(float4* __restrict__ p_verts, const uint32_t* __restrict__ p_vert_off,
+                                                               uint32_t n_pieces, const float* __restrict__ matrices16,
+                                                               const uint32_t* __restrict__ piece_matrix)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t piece = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (piece >= n_pieces) return;
+    const float* M = matrices16 + 16 * (size_t)(piece_matrix ? piece_matrix[piece] : 0u);
+    float m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = __ldg(M + k);
+    for (uint32_t v = p_vert_off[piece] + lane; v < p_vert_off[piece + 1]; v += 32)
+    {
+        const float4 p = p_verts[v];
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            o[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.z, m[4 * c + 2]), m[4 * c + 3]), __fmul_rn(p.y, m[4 * c + 1])), __fmul_rn(p.x, m[4 * c]));
+        p_verts[v] = make_float4(__fdiv_rn(o[0], o[3]), __fdiv_rn(o[1], o[3]), __fdiv_rn(o[2], o[3]), p.w);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- K2
 // Conservative separation test: a pair is culled only when some slab is separated by more than a few ulps of
 // the extents' magnitude, so no pair the clipper would keep is ever dropped (slivers).

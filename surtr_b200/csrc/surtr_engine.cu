@@ -81,7 +81,7 @@ struct surtr_ctx
     std::vector<uint32_t> h_ev_piece_off, h_ev_cell_off;
 
     // resident pattern (surtr_upload_pattern / surtr_place_pattern)
-    DevBuf pat_verts, pat_face_off, pat_xform;
+    DevBuf pat_verts, pat_face_off, pat_xform, xf_mat, xf_idx;
     std::vector<uint32_t> h_pat_cell_face_off, h_pat_cell_vert_off, h_off_scratch;
     std::vector<float> h_xform;
     uint32_t pat_faces = 0, pat_cells = 0, pat_fverts = 0;
@@ -713,6 +713,37 @@ int surtr_place_pattern(surtr_ctx* ctx, const float* scale3, const float* transl
     ctx->n_events_c = n_place;
     ctx->have_cells = true;
     ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_transform_pieces(surtr_ctx* ctx, const float* matrices16, const uint32_t* piece_matrix, uint32_t n_matrices)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!ctx->have_pieces) return fail(ctx, SURTR_ERR_INVALID, "no pieces resident");
+    if (!matrices16 || !n_matrices) return fail(ctx, SURTR_ERR_INVALID, "NULL or empty matrix list");
+    if (piece_matrix)
+        for (uint32_t i = 0; i < ctx->n_pieces; i++)
+            if (piece_matrix[i] >= n_matrices) return fail(ctx, SURTR_ERR_INVALID, "piece_matrix entry out of range");
+    if (!ctx->n_pieces) return SURTR_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload(ctx, ctx->xf_mat, matrices16, 64 * (size_t)n_matrices))) return rc;
+    if (piece_matrix && (rc = upload(ctx, ctx->xf_idx, piece_matrix, 4 * (size_t)ctx->n_pieces))) return rc;
+    const unsigned blocks = (ctx->n_pieces + 7) / 8;
+    transform_pieces_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->p_verts.as<float4>(), ctx->p_vert_off.as<uint32_t>(), ctx->n_pieces,
+                                                            ctx->xf_mat.as<float>(), piece_matrix ? ctx->xf_idx.as<uint32_t>() : nullptr);
+    CK(cudaGetLastError());
+    ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_download_pieces(surtr_ctx* ctx, float* verts4)
+{
+    if (!ctx || !verts4) return SURTR_ERR_INVALID;
+    if (!ctx->have_pieces) return fail(ctx, SURTR_ERR_INVALID, "no pieces resident");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_pverts) CK(cudaMemcpyAsync(verts4, ctx->p_verts.p, 16 * ctx->n_pverts, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return SURTR_OK;
 }
 

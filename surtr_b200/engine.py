@@ -33,6 +33,7 @@ EXPORTS = [
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
+    "surtr_transform_pieces", "surtr_download_pieces",
 ]
 
 
@@ -81,6 +82,8 @@ def load_library():
     lib.surtr_download_fragments.argtypes = [vp, vp, vp, vp, vp]
     lib.surtr_download_fragments_async.argtypes = [vp, vp, vp, vp, vp]
     lib.surtr_sync.argtypes = [vp]
+    lib.surtr_transform_pieces.argtypes = [vp, vp, vp, u32]
+    lib.surtr_download_pieces.argtypes = [vp, vp]
     lib.surtr_device_fragments.argtypes = [vp, C.POINTER(DeviceView)]
     lib.surtr_kdop_calc.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -174,6 +177,17 @@ class FractureContext:
         ev = _arr(ev_cell_off, np.uint32)
         self._ck(self._lib.surtr_upload_cells(self._h, _p(planes4), _p(plane_off), _p(cell_verts4), _p(cvert_off),
                                               len(plane_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def transform_pieces(self, matrices, piece_matrix=None):
+        """Poly::Transform on the resident pieces (row-major 4x4 world matrices, see include/surtr_b200.h)."""
+        matrices = _arr(np.asarray(matrices, np.float32).reshape(-1, 16), np.float32)
+        piece_matrix = _arr(piece_matrix, np.uint32)
+        self._ck(self._lib.surtr_transform_pieces(self._h, _p(matrices), _p(piece_matrix), len(matrices)))
+
+    def download_pieces(self, n_verts):
+        out = np.zeros((n_verts, 4), np.float32)
+        self._ck(self._lib.surtr_download_pieces(self._h, _p(out)))
+        return out
 
     def upload_pattern(self, face_verts4, face_vert_off, cell_face_off):
         """Resident fracture pattern: the VertexVec of every face of every cell (see include/surtr_b200.h)."""

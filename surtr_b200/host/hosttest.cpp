@@ -365,6 +365,20 @@ int hosttest_parallel_for(uint32_t n, uint32_t throw_at, uint32_t* n_threads_see
 	return 0;
 }
 
+// Poly::Transform (CPU only)
+void hosttest_transform(const float* verts4, uint32_t nv, const float* matrix16, float* out4)
+{
+	Poly::Polyhedron p(nv);
+	for (uint32_t v = 0; v < nv; v++) p[v].Position = Vector3(verts4[4 * v], verts4[4 * v + 1], verts4[4 * v + 2]);
+	DirectX::XMMATRIX m;
+	std::memcpy(m.r, matrix16, 64);
+	Poly::Transform(p, m);
+	for (uint32_t v = 0; v < nv; v++)
+	{
+		out4[4 * v] = p[v].Position.x; out4[4 * v + 1] = p[v].Position.y; out4[4 * v + 2] = p[v].Position.z; out4[4 * v + 3] = verts4[4 * v + 3];
+	}
+}
+
 // SurtrHost::CombineMass (CPU only): per piece volume, centroid[3], inertia[6] -> {mass, c[3], I[6]}
 void hosttest_combine_mass(uint32_t n, const double* volume, const float* centroid3, const float* inertia6, float density, float* out10)
 {

@@ -327,6 +327,31 @@ def degenerate_fixture():
     print("degenerate: pieces", pieces.nverts, "fragments", want.n, "of", 2 * 400, "pairs; verts", int(want.nverts.min()), "-", int(want.nverts.max()))
 
 
+def transform_fixture():
+    """Poly::Transform (Poly.cpp:580-585) KAT: the vertices of three Voronoi pieces under a rigid world matrix, a
+    scale + shear, and a projective matrix (w != 1), row-major as the caller holds them."""
+    pieces = common.voronoi(7, 40).subset([3, 11, 29])
+    rng = np.random.RandomState(9)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    rigid = np.eye(4)
+    rigid[:3, :3] = q
+    rigid[:3, 3] = [1.25, -3.5, 0.75]
+    shear = np.eye(4)
+    shear[:3, :3] = [[2.0, 0.3, 0.0], [0.0, 0.5, -0.2], [0.1, 0.0, 1.5]]
+    shear[:3, 3] = [0.0, 10.0, -2.0]
+    proj = rigid.copy()
+    proj[3, :] = [0.05, -0.02, 0.01, 1.5]
+    mats = np.stack([rigid, shear, proj]).astype(np.float32)
+    out = np.concatenate([R.transform(pieces.verts[pieces.vert_off[i]:pieces.vert_off[i + 1]], mats[i]) for i in range(3)])
+    d = {"matrices": mats, "out": out}
+    save_polyset(d, "pieces_", pieces, full=False)
+    for k in list(d):
+        if k.endswith("face_off") or k.endswith("face_idx") or k.endswith("planes") or k.endswith("plane_off"):
+            del d[k]
+    np.savez_compressed(os.path.join(HERE, "transform_kat.npz"), **d)
+    print("transform: verts", len(out), "max |delta|", float(np.abs(out[:, :3] - pieces.verts[:, :3]).max()))
+
+
 def do_fracture_fixture():
     """Row f-3: Surtr::DoFracture (Surtr.cpp:1885-1959) on the compound PrepareFracture produced for the bunny (the 27
     pieces of config1_full_bunny32.npz), with a 32-cell radial pattern (GenerateFracturePattern, :2072-2096) at an
@@ -367,5 +392,6 @@ if __name__ == "__main__":
     mesh_fixture()
     config1_full_fixture()
     degenerate_fixture()
+    transform_fixture()
     do_fracture_fixture()
     summaries()

@@ -158,6 +158,16 @@ def do_fracture(convex: PolySet, mesh: PolySet, seeds, cloud, impact, impact_rad
     return export(), export_mesh(), ncomp.value, mass[:ncomp.value].copy()
 
 
+def transform(verts4, matrix16):
+    verts4 = np.ascontiguousarray(verts4, np.float32)
+    m = np.ascontiguousarray(matrix16, np.float32).reshape(16)
+    out = np.zeros_like(verts4)
+    L = lib()
+    L.hosttest_transform.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.hosttest_transform(_p(verts4), len(verts4), _p(m), _p(out))
+    return out
+
+
 def combine_mass(volume, centroid, inertia, density=10.0):
     volume = np.ascontiguousarray(volume, np.float64)
     centroid, inertia = np.ascontiguousarray(centroid, np.float32), np.ascontiguousarray(inertia, np.float32)

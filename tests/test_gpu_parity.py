@@ -364,3 +364,25 @@ def test_degenerate_cuts_large_tiers(ctx):
     assert s == _summaries()["degenerate_large"]
     c = ctx.counts()
     assert c.n_tier2 == 96 and c.n_tier3 == 48 and c.n_seq_cuts > 50
+
+
+def test_transform_pieces_on_device(ctx):
+    """Row f-4: world transform of resident pieces (surtr_transform_pieces = Poly::Transform, Poly.cpp:580-585), one matrix
+    per piece; then an event on the moved pieces equals the oracle on the reference-transformed pieces."""
+    d = np.load(os.path.join(GOLDEN, "transform_kat.npz"))
+    pieces = load_polyset(d, "pieces_")
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+    ctx.transform_pieces(d["matrices"], np.array([0, 1, 2], np.uint32))
+    got = ctx.download_pieces(len(pieces.verts))
+    assert np.array_equal(bits(got), bits(d["out"]))
+    moved = pieces.subset(range(3))
+    moved.verts = d["out"]
+    lo, hi = d["out"][:, :3].min(0), d["out"][:, :3].max(0)
+    cells = common.voronoi(46354, 64)
+    placed = cells.subset(range(cells.n))
+    placed.verts = cells.verts.copy()
+    placed.verts[:, :3] = (cells.verts[:, :3] * (hi - lo)).astype(np.float32) + ((hi + lo) / 2).astype(np.float32)
+    planes, off = P.face_planes(placed)
+    ctx.upload_cells(planes, off, placed.verts, placed.vert_off)
+    ctx.fracture_event()
+    common.assert_fragments_equal(ctx.download(), P.apply_fracture(moved, planes, off))

@@ -228,3 +228,12 @@ def test_host_worker_pool():
     for n, throw_at in ((3, 99), (64, 99), (1000, 99), (17, 5), (1000, 999), (8, 99), (5000, 99)):
         assert L.hosttest_parallel_for(n, throw_at, C.byref(seen)) == 0, H._err()
     assert seen.value >= 1
+
+
+def test_host_transform_matches_reference():
+    """Poly::Transform mirror (world matrix, transposed inside, TransformCoord with the w division) == reference build."""
+    d = np.load(os.path.join(GOLDEN, "transform_kat.npz"))
+    pieces = load_polyset(d, "pieces_")
+    for i in range(3):
+        sl = slice(int(pieces.vert_off[i]), int(pieces.vert_off[i + 1]))
+        assert np.array_equal(bits(H.transform(pieces.verts[sl], d["matrices"][i])), bits(d["out"][sl]))
