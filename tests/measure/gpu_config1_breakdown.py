@@ -1,6 +1,6 @@
 """Dev: where the 13 ms of config 1 (full PrepareFracture through the host classes) go."""
 import sys, time, numpy as np
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 import hostapi as H, common
 from surtr_b200 import FractureContext
 from test_oracle_port import load_polyset

@@ -2,7 +2,7 @@
 reference build's CPU timings (oracle/_ref, dp::thread_pool(16) fan-out + SetExtract, the reference's own timer) on
 the same box.  Writes gpurun_out/configs_r1.json (copied to profiles/)."""
 import json, os, sys, time, numpy as np
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 import torch
 from surtr_b200 import FractureContext, synth
 import common

@@ -1,6 +1,6 @@
 """Dev: per-candidate cycle histogram of K3 (surtr_debug.h)."""
 import ctypes as C, sys, numpy as np
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 from surtr_b200 import FractureContext, engine
 import common
 lib = engine.load_library()

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 from oracle import refapi as R, portapi as P
 from surtr_b200 import FractureContext
 import common

@@ -1,7 +1,7 @@
 """Dev: phase times of SurtrHost::DoFracture on the bunny compound (SURTR_TRACE=1)."""
 import os, sys, time, numpy as np
 os.environ["SURTR_TRACE"] = "1"
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 import hostapi
 from test_oracle_port import load_polyset
 d1 = np.load("tests/golden/config1_full_bunny32.npz"); dd = np.load("tests/golden/do_fracture_bunny.npz")
