@@ -28,7 +28,9 @@ __device__ __forceinline__ float signed_dist(const float4& pl, float x, float y,
 // A NaN distance (degenerate zero-area cell face -> NaN plane) gives 0, exactly as sgn0(-NaN) does (Poly.cpp:32).
 __device__ __forceinline__ int classify(float s)
 {
-    if ((double)fabsf(s) < 1.0e-10)
+    // (double)|s| < 1e-10 holds exactly for the floats below 0x2EDBE6FF (= 1.0000000134e-10f, the float next above the
+    // double 1e-10; 0x2EDBE6FE is the largest float under it) -- one float compare, no FP64 round trip
+    if (fabsf(s) < __uint_as_float(0x2EDBE6FFu))
         return 0;
     return s < 0.f ? 1 : (s > 0.f ? -1 : 0);
 }
