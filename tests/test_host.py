@@ -237,3 +237,22 @@ def test_host_transform_matches_reference():
     for i in range(3):
         sl = slice(int(pieces.vert_off[i]), int(pieces.vert_off[i + 1]))
         assert np.array_equal(bits(H.transform(pieces.verts[sl], d["matrices"][i])), bits(d["out"][sl]))
+
+
+@pytest.mark.gpu
+def test_cpp_example_runs_the_reference_flow(tmp_path):
+    """examples/fracture_demo.cpp: PrepareFracture + DoFracture written against the host classes like a C++ caller would;
+    on the bunny it must report the reference's 27 initial pieces (config1_full fixture)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "examples")], check=True, capture_output=True)
+    d = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    obj = tmp_path / "bunny.obj"
+    with open(obj, "w") as f:
+        for v in d["verts"]:
+            f.write(f"v {-float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")      # the loader negates x again
+        for t in d["indices"].reshape(-1, 3):
+            f.write(f"f {t[0] + 1} {t[2] + 1} {t[1] + 1}\n")                        # and flips the winding back
+    r = subprocess.run([os.path.join(root, "examples", "fracture_demo"), str(obj), "1.0", "32"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "-> 27 pieces" in r.stdout and "DoFracture(partial)" in r.stdout
