@@ -617,12 +617,12 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 
 // K3, small tier: L lanes per candidate pair (clip_sub.cuh), one pair per sub-warp, no persistent loop (the
 // hardware scheduler balances the very uneven pair costs).
-constexpr int FAST_WARPS = 4;
+constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
 constexpr int FAST_LANES = 32;   // lanes per pair; 16 (two pairs per warp in lock step) is correct but measured slower, see DESIGN.md section 7
 constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
 
 template <int L>
-__global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 7 : 4) clip_sub_kernel(ClipArgs a)
+__global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4) clip_sub_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
