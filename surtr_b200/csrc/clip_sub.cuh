@@ -438,7 +438,11 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
                 }
             }
             sub.sync();
-            // insert: one new vertex per lane (Poly.cpp:345-354)
+            // insert: one new vertex per lane (Poly.cpp:345-354).  Lanes may touch the same ring WORD concurrently, but
+            // never the same BYTE: lane t replaces exactly slot j of ring[v] and the slot of ring[jn] that holds v, and no
+            // other lane reads or writes those two slots (another lane's search in ring[jn] looks for its own v' != v and
+            // can only meet values that are neither v' before nor after this lane's store).  compute-sanitizer racecheck
+            // reports these word-level overlaps as warnings (profiles/r1_sanitizer.txt); memcheck and synccheck are clean.
             for (int t = sub.sl; t < nnew; t += L)
             {
                 const int e = sp.list[t], v = e & 0xff, j = e >> 8, w = hi0 + t;

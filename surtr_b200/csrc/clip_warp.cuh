@@ -308,6 +308,9 @@ __device__ int clip_by_planes(P& sp, int& nv, const float4* __restrict__ planes,
                             sp.deg[w] = 2;
                             sp.ring[w * DMAX] = (IdxT)v;
                             sp.ring[w * DMAX + 1] = (IdxT)jn;
+                            // several lanes may patch the ring of the same kept vertex jn at once: each replaces only the
+                            // entry holding ITS clipped vertex v, and an entry another lane is rewriting (v' -> w') equals
+                            // v neither before nor after -- entry-disjoint by construction (racecheck warns, word-level)
                             IdxT* rj = sp.ring + jn * DMAX;
                             const int dj = sp.deg[jn];
                             int k = 0;
