@@ -544,12 +544,15 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
     const float ox = sp.x[first], oy = sp.y[first], oz = sp.z[first];
     const int nv = has ? __popcll(s.live) : 0;
     u64 start_mask = 0ull;   // 8 slot bits per owned group
-    int faces = 0, cnt = 0;  // triangles of the faces this lane starts (all groups: one lane = one scan entry per group)
-    int cntg[G];
+    int faces = 0;           // faces this lane starts
+    int cntg[G];             // their fan triangles, per owned group (one lane = one scan entry per group)
 #pragma unroll
+    for (int g = 0; g < G; g++) cntg[g] = 0;
+    // (rolled: the body is large and runs once per pair -- two copies of it only cost instruction-cache space)
+#pragma unroll 1
     for (int g = 0; g < G; g++)
     {
-        cntg[g] = 0;
+        int tris = 0;
         const int v = sub.sl + L * g;
         if (has && g * L < s.hi && bit64(s.live, v))
         {
@@ -575,11 +578,13 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
                 {
                     start_mask |= 1ull << (j + 8 * g);
                     faces++;
-                    cntg[g] += max(n - 2, 0);
+                    tris += max(n - 2, 0);
                 }
             }
         }
-        cnt += cntg[g];
+#pragma unroll
+        for (int h = 0; h < G; h++)
+            if (h == g) cntg[h] = tris;
     }
     // triangle order = vertex order = group-major, lane-minor: one scan per group that has vertices
     int tri_base[G];
@@ -599,13 +604,16 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
     n_tri = min(n_tri, 128);
 
     float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
-#pragma unroll
+#pragma unroll 1
     for (int g = 0; g < G; g++)
     {
         unsigned m = (unsigned)(start_mask >> (8 * g)) & 0xffu;
         if (!m) continue;
         const int v = sub.sl + L * g;
-        int w = tri_base[g];
+        int w = 0;
+#pragma unroll
+        for (int h = 0; h < G; h++)
+            if (h == g) w = tri_base[h];
         const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
         const u64 rw = sp.ring[v];
         while (m)
@@ -699,6 +707,5 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
         out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
         out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
     }
-    (void)cnt;
 }
 } // namespace surtr

@@ -698,9 +698,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4
     if (have && status == CLIP_OK && nv == 0 && sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
     const bool has = have && status == CLIP_OK && nv > 0;
     if (!sub.any_warp(has)) return;
-    Moments mo;
-    sub_fragment_moments<L>(sp, cs, sub, has, mo);
     const long long t3 = a.dbg ? clock64() : 0;
+    // Face count and moments of a small-tier fragment are computed by K4's gather (assemble_gather_kernel) from the
+    // blob written below: the clip loop and the moments code together do not fit the SM's instruction cache, and with
+    // 28 warps per SM each in a different phase they kept evicting each other (profiles/README.md).
 
     // result blob, renumbered to the reference's final order (rank in the live mask):
     // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
@@ -736,12 +737,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4
     {
         rec->nv = (uint32_t)nv;
         rec->ne = (uint32_t)ne;
-        rec->nf = (uint32_t)mo.n_faces;
+        rec->nf = 0;
         rec->tier = 1;
-        rec->volume = mo.volume;
-        rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
-#pragma unroll
-        for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
         rec->blob = blob;
         if (a.dbg)
         {
@@ -839,6 +836,7 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ SubPoly s_poly[8];   // one per warp: a small-tier fragment is rebuilt here for its face count and moments
     const int lane = threadIdx.x & 31;
     const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long n_cand = a.ctl->n_cand;
@@ -852,6 +850,8 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
     const unsigned long long cfi = off.x, cvb = off.y, crb = off.z;
     if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) return;
     const int tier = r->tier;
+    Moments mo;
+    bool have_mo = false;
     if (tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
@@ -880,6 +880,25 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
         {
             const uint8_t* br = b + (size_t)cap * 18;
             for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+            // Poly::ExtractFaces count + Poly::Moments + inertia (Poly.cpp:55-126) on the final polyhedron: positions
+            // and ring words back into shared memory, numbered as in the result (live slots = 0..nv-1)
+            SubPoly& sp = s_poly[threadIdx.x >> 5];
+            for (int v = lane; v < cnv; v += 32)
+            {
+                const float4 p = bv[v];
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                const int r0 = bo[v], r1 = v + 1 < cnv ? (int)bo[v + 1] : cne;
+                u64 rw = ~0ull;
+                for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, br[r0 + j]);
+                sp.ring[v] = rw;
+            }
+            __syncwarp();
+            CutState cs;
+            cs.hi = cnv;
+            cs.live = lowmask64(cnv);
+            cs.c = cs.k = 0ull;
+            sub_fragment_moments<32>(sp, cs, Sub<32>(lane), true, mo);
+            have_mo = true;
         }
         else
         {
@@ -894,11 +913,22 @@ __global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
         f.cell = pr.y; f.piece = pr.x;
         f.vert_off = (uint32_t)cvb;
         f.n_verts = (uint16_t)cnv;
-        f.n_faces = (uint16_t)r->nf;
-        f.volume = r->volume;
-        f.centroid[0] = r->centroid[0]; f.centroid[1] = r->centroid[1]; f.centroid[2] = r->centroid[2];
+        if (have_mo)
+        {
+            f.n_faces = (uint16_t)mo.n_faces;
+            f.volume = mo.volume;
+            f.centroid[0] = mo.cx; f.centroid[1] = mo.cy; f.centroid[2] = mo.cz;
 #pragma unroll
-        for (int k = 0; k < 6; k++) f.inertia[k] = r->inertia[k];
+            for (int k = 0; k < 6; k++) f.inertia[k] = mo.inertia[k];
+        }
+        else
+        {
+            f.n_faces = (uint16_t)r->nf;
+            f.volume = r->volume;
+            f.centroid[0] = r->centroid[0]; f.centroid[1] = r->centroid[1]; f.centroid[2] = r->centroid[2];
+#pragma unroll
+            for (int k = 0; k < 6; k++) f.inertia[k] = r->inertia[k];
+        }
         f.n_ring = (uint32_t)cne;
         a.f_rec[cfi] = f;
     }
