@@ -80,8 +80,19 @@ __device__ __forceinline__ int rface_loop(u64 w, int vprev)
 }
 
 __device__ __forceinline__ bool bit64(u64 m, int j) { return (m >> j) & 1ull; }
-__device__ __forceinline__ u64 lowmask64(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
-__device__ __forceinline__ int rank64(u64 m, int u) { return __popcll(m & lowmask64(u)); }   // set bits below u
+// bits [0, n) set, 0 <= n <= 64, on 32-bit halves (a 64-bit shift costs a handful of instructions and is inlined at every use)
+__device__ __forceinline__ u64 lowmask64(int n)
+{
+    const unsigned lo = n >= 32 ? 0xffffffffu : ((1u << (n & 31)) - 1u);
+    const unsigned hi = n >= 64 ? 0xffffffffu : (n > 32 ? ((1u << (n & 31)) - 1u) : 0u);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ int rank64(u64 m, int u)   // set bits below u, 0 <= u < 64
+{
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const unsigned below = (1u << (u & 31)) - 1u;
+    return u < 32 ? __popc(lo & below) : __popc(lo) + __popc(hi & below);
+}
 
 struct CutState   // uniform across the lanes of one pair
 {
@@ -388,6 +399,7 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
                     if (g * L < s.hi && bit64(s.c, v))
                     {
                         const u64 rw = sp.ring[v];
+#pragma unroll 1
                         for (int j = 0; j < 8; j++)
                         {
                             const int b = rget(rw, j);
@@ -486,8 +498,11 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
             }
             sub.sync();
             if (!need_seq)
+            {
+#pragma unroll 1
                 for (int t = sub.sl; t < nnew; t += L)
                     if (ok) ok = sp.id[sp.list[t]] == (uint8_t)(hi0 + t);
+            }
             const bool anomaly = sub.ballot(!ok) != 0u;
             need_seq = need_seq || (docut && anomaly);
             if (docut && !need_seq)

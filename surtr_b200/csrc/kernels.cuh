@@ -711,8 +711,16 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4
     uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
     uint8_t* br = b + 64 * 18;
     const int gmax = L == 32 ? (cs.hi + L - 1) / L : sub.max_warp(has ? (cs.hi + L - 1) / L : 0);
-    int ne = 0;
+    // final number of every live slot once (rank in the live mask), looked up per ring entry below
 #pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        const int v = sub.sl + L * g;
+        if (g < gmax && has && bit64(cs.live, v)) sp.id[v] = (uint8_t)rank64(cs.live, v);
+    }
+    sub.sync();
+    int ne = 0;
+#pragma unroll 1
     for (int g = 0; g < G; g++)
     {
         if (g < gmax)
@@ -726,10 +734,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4
             ne += tot;
             if (live)
             {
-                const int t = rank64(cs.live, v);
+                const int t = sp.id[v];
                 bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
                 bo[t] = (uint16_t)off;
-                for (int j = 0; j < d; j++) br[off + j] = (uint8_t)rank64(cs.live, rget(rw, j));
+#pragma unroll 1
+                for (int j = 0; j < d; j++) br[off + j] = sp.id[rget(rw, j)];
             }
         }
     }
