@@ -35,7 +35,7 @@ N_SEEDS = 4096
 BASE_SEED = 46354
 WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fracture event per step per GPU"
 FLUSH_MIB = 160   # L2 flush buffer (B200 L2 = 126 MB), rewritten before every step
-E2E_DEPTH = 4     # events in flight in the end-to-end loop (contexts driven round-robin)
+E2E_DEPTH = 6     # events in flight in the end-to-end loop (contexts driven round-robin)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -434,7 +434,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "clip_kernel<tier1> (K3+moments)", "kernel_ms": k3_ms,
+                    "traffic": traffic, "kernel": "clip_sub_kernel<32> (K3, small tier: one warp per pair)", "kernel_ms": k3_ms,
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
         line = {

@@ -399,7 +399,6 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
                     if (g * L < s.hi && bit64(s.c, v))
                     {
                         const u64 rw = sp.ring[v];
-#pragma unroll 1
                         for (int j = 0; j < 8; j++)
                         {
                             const int b = rget(rw, j);
