@@ -841,88 +841,103 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs 
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_gather_kernel(AssembleArgs a)
+// L lanes per candidate (L = 16: two candidates per warp, in lock step -- every candidate that reaches the moments is a
+// live fragment of similar size, so the lock step costs little and the face walks of sub_fragment_moments use twice the
+// lanes).  All lanes stay to the end: the collectives of the moments use the full warp mask.
+constexpr int GATHER_LANES = 16;
+constexpr int GATHER_THREADS = 128;
+template <int L>
+__global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(AssembleArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ SubPoly s_poly[8];   // one per warp: a small-tier fragment is rebuilt here for its face count and moments
-    const int lane = threadIdx.x & 31;
-    const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ SubPoly s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
+    const Sub<L> sub(threadIdx.x & 31);
+    const int lane = sub.sl;
+    const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
     unsigned long long n_cand = a.ctl->n_cand;
     if (n_cand > a.cap_cand) n_cand = a.cap_cand;
-    if (q >= n_cand) return;
-    const CandRec* r = a.rec + q;
-    const int cnv = (int)r->nv;
-    if (cnv == 0) return;
-    const int cne = (int)r->ne;
-    const uint4 off = a.out_off[q];
-    const unsigned long long cfi = off.x, cvb = off.y, crb = off.z;
-    if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) return;
-    const int tier = r->tier;
-    Moments mo;
-    bool have_mo = false;
-    if (tier == 3)
+    bool have = q < n_cand;
+    const CandRec* r = a.rec + (have ? q : 0);
+    const int cnv = have ? (int)r->nv : 0;
+    const int cne = have ? (int)r->ne : 0;
+    have = have && cnv > 0;
+    unsigned long long cfi = 0, cvb = 0, crb = 0;
+    if (have)
+    {
+        const uint4 off = a.out_off[q];
+        cfi = off.x; cvb = off.y; crb = off.z;
+        if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) have = false;   // the host grows and re-runs
+    }
+    const int tier = have ? (int)r->tier : 0;
+    SubPoly& sp = s_poly[threadIdx.x / L];
+    if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
         const float4* bv = reinterpret_cast<const float4*>(b);
         const uint32_t* bo = reinterpret_cast<const uint32_t*>(b + (size_t)a.cap3 * 16);
         const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)a.cap3 * 20);
-        for (int v = lane; v < cnv; v += 32)
+        for (int v = lane; v < cnv; v += L)
         {
             a.f_verts[cvb + v] = bv[v];
             a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
         }
-        for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+        for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
     }
-    else
+    else if (have)
     {
         const int cap = tier == 1 ? a.cap1 : a.cap2;
         const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
         const float4* bv = reinterpret_cast<const float4*>(b);
         const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
-        for (int v = lane; v < cnv; v += 32)
-        {
-            a.f_verts[cvb + v] = bv[v];
-            a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
-        }
         if (tier == 1)
         {
+            // copy out, and at the same time put positions and ring words back into shared memory, numbered as in the
+            // result (live slots = 0..nv-1), for Poly::ExtractFaces' count + Poly::Moments + inertia (Poly.cpp:55-126)
             const uint8_t* br = b + (size_t)cap * 18;
-            for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
-            // Poly::ExtractFaces count + Poly::Moments + inertia (Poly.cpp:55-126) on the final polyhedron: positions
-            // and ring words back into shared memory, numbered as in the result (live slots = 0..nv-1)
-            SubPoly& sp = s_poly[threadIdx.x >> 5];
-            for (int v = lane; v < cnv; v += 32)
+            for (int v = lane; v < cnv; v += L)
             {
                 const float4 p = bv[v];
-                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
                 const int r0 = bo[v], r1 = v + 1 < cnv ? (int)bo[v + 1] : cne;
+                a.f_verts[cvb + v] = p;
+                a.f_ring_off[cvb + v] = (uint32_t)(crb + r0);
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
                 u64 rw = ~0ull;
                 for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, br[r0 + j]);
                 sp.ring[v] = rw;
             }
-            __syncwarp();
-            CutState cs;
-            cs.hi = cnv;
-            cs.live = lowmask64(cnv);
-            cs.c = cs.k = 0ull;
-            sub_fragment_moments<32>(sp, cs, Sub<32>(lane), true, mo);
-            have_mo = true;
+            for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
         }
         else
         {
             const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
-            for (int k = lane; k < cne; k += 32) a.f_ring[crb + k] = br[k];
+            for (int v = lane; v < cnv; v += L)
+            {
+                a.f_verts[cvb + v] = bv[v];
+                a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+            }
+            for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
         }
     }
-    if (lane == 0)
+    const bool do_mo = have && tier == 1;
+    Moments mo;
+    if (sub.any_warp(do_mo))
+    {
+        sub.sync();
+        CutState cs;
+        cs.hi = do_mo ? cnv : 0;
+        cs.live = lowmask64(cs.hi);
+        cs.c = cs.k = 0ull;
+        sub_fragment_moments<L>(sp, cs, sub, do_mo, mo);
+    }
+    if (have && lane == 0)
     {
         const uint2 pr = a.cand[q];
         surtr_fragment f;
         f.cell = pr.y; f.piece = pr.x;
         f.vert_off = (uint32_t)cvb;
         f.n_verts = (uint16_t)cnv;
-        if (have_mo)
+        if (do_mo)
         {
             f.n_faces = (uint16_t)mo.n_faces;
             f.volume = mo.volume;

@@ -372,8 +372,9 @@ int launch_event(surtr_ctx* ctx)
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
         launch_pdl(assemble_scan_kernel, dim3(blocks), dim3(AS_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
-        const uint64_t gblocks = std::max<uint64_t>(1, (ctx->cap_cand + 7) / 8);
-        launch_pdl(assemble_gather_kernel, dim3((unsigned)gblocks), dim3(256), 0, ctx->stream, aa);
+        constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
+        const uint64_t gblocks = std::max<uint64_t>(1, (ctx->cap_cand + cand_per_block - 1) / cand_per_block);
+        launch_pdl(assemble_gather_kernel<GATHER_LANES>, dim3((unsigned)gblocks), dim3(GATHER_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
