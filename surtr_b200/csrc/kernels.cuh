@@ -622,7 +622,7 @@ constexpr int FAST_LANES = 32;   // lanes per pair; 16 (two pairs per warp in lo
 constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
 
 template <int L>
-__global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 28 / FAST_WARPS : 4) clip_sub_kernel(ClipArgs a)
+__global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 32 / FAST_WARPS : 4) clip_sub_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
