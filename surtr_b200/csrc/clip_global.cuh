@@ -1,10 +1,13 @@
-// clip_global.cuh -- the unbounded tier of K3: one warp per pair, polyhedron in a global-memory workspace.
+// clip_global.cuh -- the large and the unbounded tier of K3: one warp per pair, polyhedron in a per-warp workspace.
 //
-// Same algorithm and exactness argument as clip_warp.cuh (see there and DESIGN.md section 5), written with strided
-// loops instead of per-lane register arrays so that the vertex count is bounded only by the workspace: this is the
-// path of non-convex piece MESHES (2.5K-5K vertices, ring degree up to 13; m_fractureTask's second clip,
-// Surtr.cpp:1470) and of any convex piece beyond 256 vertices.  The workspace of a warp (117 bytes per vertex slot)
-// stays L2-resident; throughput is not the point of this tier, never failing is.
+// Algorithm and exactness argument: see clip_warp.cuh and DESIGN.md section 5.  Written with strided (rolled) loops
+// over arrays in memory instead of per-lane register arrays, so the vertex count is bounded only by the workspace
+// and the code stays small (an unrolled register-array version of the large tier was 179 KB of SASS and stalled on
+// instruction fetch).  The workspace (117 bytes per vertex slot) is reached through plain pointers:
+//   * clip_shared_kernel carves it from shared memory (256 slots): pieces / intermediate results beyond the small
+//     tier's 64 slots or ring degree 8 -- ACH-sized convex pieces, mesh fragments;
+//   * clip_global_kernel carves it from global memory (L2-resident): non-convex piece MESHES (2.5K-5K vertices, ring
+//     degree up to 13; m_fractureTask's second clip, Surtr.cpp:1470) and anything beyond 256 slots.
 #pragma once
 
 #include "clip_warp.cuh"

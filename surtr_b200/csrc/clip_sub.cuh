@@ -1,7 +1,7 @@
 // clip_sub.cuh -- small-tier clipper: L lanes (a warp, half-warp or quarter-warp) clip one pair; <= 64 vertex
 // slots, ring degree <= 8, everything register/ballot based.
 //
-// Same algorithm and the same exactness argument as clip_warp.cuh (which stays as the large tier):
+// Same algorithm and the same exactness argument as the other tiers (clip_warp.cuh):
 //   * a vertex ring is ONE 64-bit shared-memory word: eight u8 neighbour indices, 0xFF padded.  FaceLoop
 //     (Poly.cpp:34-41), find-and-replace (Poly.cpp:350-353) and the degree are byte-compare instructions on a
 //     register (__vcmpeq4 / __ffs / PRMT) after a single LDS.64 -- no dependent chain of shared-memory reads;
@@ -547,8 +547,8 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
 }
 
 // Poly::ExtractFaces + Poly::Moments in the reference's accumulation order (Poly.cpp:55-126) + inertia, on the
-// live (not renumbered) slots: vertex order = slot order, origin = first live vertex.  See fragment_moments in
-// clip_warp.cuh for the derivation.  Called by all lanes of the warp; pairs without a fragment (`has` false) idle.
+// live (not renumbered) slots: vertex order = slot order, origin = first live vertex.  See DESIGN.md section 5
+// for the derivation.  Called by all lanes of the warp; pairs without a fragment (`has` false) idle.
 template <int L>
 __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L> sub, bool has, Moments& out)
 {

@@ -3,7 +3,7 @@
 //   K1  kdop_extents_kernel      slab extents of every piece and every cell (warp-shuffle min/max)
 //   K2  broadphase_mask_kernel   piece x cell k-DOP overlap -> one ballot word per (cell, 32 pieces)
 //       compact_pairs_kernel     ordered compaction of the ballot words into the candidate pair list
-//   K3  clip_kernel<tier>        one warp per candidate pair: half-space clipping + moments (clip_warp.cuh)
+//   K3  clip_sub_kernel / clip_shared_kernel / clip_global_kernel   one warp per candidate pair: half-space clipping
 //   K4  assemble_kernel          ordered compaction of the non-empty results into the fragment arrays
 //       kdop_arg_kernel          Kdop::KdopContainer::Calc(Polyhedron) with first-extremal-vertex semantics
 #pragma once
@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_pairs_kernel(const unsigne
 }
 
 // ---------------------------------------------------------------------------------------------- K3
+constexpr size_t FAST_BLOB_BYTES = 64 * 16 + 64 * 2 + 64 * 8;   // small-tier result blob: float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
+
 struct ClipArgs
 {
     const float4* p_verts;
@@ -334,6 +336,7 @@ struct ClipArgs
     CandRec* rec;
     unsigned char* scratch;       // this tier's blob area
     uint64_t slot_bytes;
+    unsigned char* scratch1;      // small-tier blob area (one slot per candidate): tier 2 hands small results to K4's moments
     uint32_t* ovf_list;           // tier 1 appends, tier 2 consumes
     uint64_t cap_tier2;           // slots available to tier 2
     uint32_t* ovf3_list;          // tier 2 appends, tier 3 consumes
@@ -345,87 +348,64 @@ struct ClipArgs
     uint32_t* dbg;                // optional: 8 words per candidate (cycles per phase, cut counts); NULL = off
 };
 
-template <class P>
-__host__ __device__ constexpr size_t blob_bytes()
-{
-    return (size_t)P::CAP * 16 + (size_t)P::CAP * 2 + (size_t)P::CAP * P::DMAX * sizeof(typename P::IdxT);
-}
+// K3, large on-chip tier: pieces / intermediate results of up to 256 vertex slots and ring degree 16, one warp per pair,
+// persistent warps over the pairs the small tier handed on.  Same rolled code as the unbounded tier (clip_global.cuh)
+// with the per-warp workspace in shared memory: the unrolled register-array version this replaces was 179 KB of
+// SASS and spent 16 stalled cycles per issued instruction on instruction fetch (profiles/README.md).
+constexpr int T2_CAP = 256;
+constexpr int T2_WARPS = 2;
+__host__ __device__ constexpr size_t blob2_bytes() { return (size_t)T2_CAP * (16 + 2 + GD * 2); }   // float4 verts | u16 ring_start | u16 ring
+__host__ __device__ constexpr size_t t2_ws_bytes() { return (global_poly_bytes(T2_CAP) + 15) / 16 * 16; }
 
-template <class P, int TIER, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
+__global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    P& sp = reinterpret_cast<P*>(smem_raw)[threadIdx.x >> 5];
-    using IdxT = typename P::IdxT;
-    constexpr int DMAX = P::DMAX;
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    unsigned long long n_items;
-    if (TIER == 1)
-    {
-        n_items = a.ctl->n_cand;
-        if (n_items > a.cap_cand) n_items = a.cap_cand;
-    }
-    else
-    {
-        n_items = a.ctl->n_ovf;
-    }
+    const unsigned long long n_items = a.ctl->n_ovf;
+    GlobalPoly g = global_poly_carve(smem_raw + (size_t)(threadIdx.x >> 5) * t2_ws_bytes(), T2_CAP);
     unsigned seq_cuts = 0;
     for (unsigned long long it = gw; it < n_items; it += nwarps)
     {
-        const long long t0 = clock64();
-        const unsigned seq0 = seq_cuts;
-        unsigned n_cuts = 0;
-        const uint32_t q = (TIER == 1) ? (uint32_t)it : a.ovf_list[it];
+        const uint32_t q = a.ovf_list[it];
         const uint2 pr = a.cand[q];
         const uint32_t v0 = a.p_vert_off[pr.x];
         int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
-        bool too_big = nv > P::CAP, malformed = false;
+        bool too_big = nv > T2_CAP, malformed = false;
         if (!too_big)
         {
             for (int v = lane; v < nv; v += 32)
             {
                 const float4 p = __ldg(a.p_verts + v0 + v);
-                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                g.x[v] = p.x; g.y[v] = p.y; g.z[v] = p.z;
                 const uint32_t r0 = a.p_ring_off[v0 + v];
                 const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
-                if (d > DMAX) { too_big = true; }
+                if (d > GD) too_big = true;
                 else
                 {
-                    sp.deg[v] = (uint8_t)d;
+                    g.deg[v] = (uint8_t)d;
                     if (d == 0) malformed = true;   // a vertex without neighbours is not a polyhedron vertex
                     for (int j = 0; j < d; j++)
                     {
                         const int idx = a.p_ring[r0 + j];
                         if (idx >= nv) malformed = true;   // reported as a failed pair, never used as an index
-                        sp.ring[v * DMAX + j] = (IdxT)idx;
+                        g.ring[(size_t)v * GD + j] = (uint16_t)idx;
                     }
                 }
             }
         }
         malformed = __ballot_sync(FULL, malformed) != 0u;
-        too_big = __ballot_sync(FULL, too_big) != 0u || malformed;
+        too_big = __ballot_sync(FULL, too_big) != 0u;
         __syncwarp();
         int status = CLIP_OVERFLOW;
-        const long long t1 = clock64();
-        const int nv_in = nv;
-        int npl_dbg = 0;
-        if (!too_big)
+        if (!too_big && !malformed)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-            npl_dbg = npl;
-            status = clip_by_planes(sp, nv, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
-        }
-        const long long t2 = clock64();
-        if (a.dbg && lane == 0)
-        {
-            uint32_t* d = a.dbg + (size_t)q * 8;
-            d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
-            d[4] = seq_cuts - seq0; d[5] = n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl_dbg;
+            status = global_clip_by_planes(g, nv, a.c_planes + pl0, npl, lane, seq_cuts);
         }
         CandRec* rec = a.rec + q;
         if (status != CLIP_OK)
@@ -433,74 +413,77 @@ __global__ void __launch_bounds__(WARPS * 32) clip_kernel(ClipArgs a)
             if (lane == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-                if (TIER == 1)
-                {
-                    const unsigned slot = atomicAdd(&a.ctl->n_ovf, 1u);
-                    a.ovf_list[slot] = q;   // capacity = cap_cand, cannot overflow
-                }
-                else if (malformed)
-                {
-                    atomicAdd(&a.ctl->n_fail, 1u);
-                }
-                else
-                {
-                    a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier
-                }
+                if (malformed) atomicAdd(&a.ctl->n_fail, 1u);
+                else a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier
             }
             __syncwarp();
             continue;
         }
         if (nv == 0)
         {
-            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = TIER; }
+            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 2; }
             __syncwarp();
             continue;
         }
-        Moments mo;
-        fragment_moments(sp, nv, lane, mo);
-        const long long t3 = clock64();
-
-        // result blob: float4 verts[CAP] | u16 ring_start[CAP] | IdxT ring[packed]
-        unsigned long long blob = (TIER == 1) ? (unsigned long long)q * a.slot_bytes : (unsigned long long)it * a.slot_bytes;
-        const bool room = (TIER == 1) || it < a.cap_tier2;
-        int ne = 0;
+        // ring entries of the result, and whether it fits the small tier's blob (<= 64 vertices, degree <= 8): then K4's
+        // gather computes its face count and moments like for every small fragment
+        int ne = 0, maxd = 0;
+        for (int base = 0; base < nv; base += 32)
         {
-            unsigned char* b = a.scratch + blob;
-            float4* bv = reinterpret_cast<float4*>(b);
-            uint16_t* bo = reinterpret_cast<uint16_t*>(b + (size_t)P::CAP * 16);
-            IdxT* br = reinterpret_cast<IdxT*>(b + (size_t)P::CAP * 18);
-            for (int h = 0; h * 32 < nv; h++)
+            const int d = base + lane < nv ? g.deg[base + lane] : 0;
+            maxd = max(maxd, d);
+            ne += d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            ne += __shfl_xor_sync(FULL, ne, o);
+            maxd = max(maxd, __shfl_xor_sync(FULL, maxd, o));
+        }
+        const bool small = nv <= 64 && maxd <= 8;
+        Moments mo;
+        if (!small) global_fragment_moments(g, nv, lane, mo);
+        const bool room = small || it < a.cap_tier2;
+        const unsigned long long blob = small ? (unsigned long long)q * FAST_BLOB_BYTES : it * a.slot_bytes;
+        unsigned char* b = (small ? a.scratch1 : a.scratch) + blob;
+        float4* bv = reinterpret_cast<float4*>(b);
+        uint16_t* bo = reinterpret_cast<uint16_t*>(b + (size_t)(small ? 64 : T2_CAP) * 16);
+        uint8_t* br8 = b + 64 * 18;
+        uint16_t* br16 = reinterpret_cast<uint16_t*>(b + (size_t)T2_CAP * 18);
+        int run = 0;
+        for (int base = 0; base < nv; base += 32)
+        {
+            const int v = base + lane;
+            const int d = v < nv ? g.deg[v] : 0;
+            int tot;
+            const int off = run + warp_exscan(d, lane, tot);
+            run += tot;
+            if (v < nv && room)
             {
-                const int v = lane + 32 * h;
-                const int d = v < nv ? sp.deg[v] : 0;
-                int tot;
-                const int off = ne + warp_exscan(d, lane, tot);
-                ne += tot;
-                if (v < nv && room)
-                {
-                    bv[v] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
-                    bo[v] = (uint16_t)off;
-                    for (int j = 0; j < d; j++) br[off + j] = sp.ring[v * DMAX + j];
-                }
+                bv[v] = make_float4(g.x[v], g.y[v], g.z[v], 0.f);
+                bo[v] = (uint16_t)off;
+                if (small)
+                    for (int j = 0; j < d; j++) br8[off + j] = (uint8_t)g.ring[(size_t)v * GD + j];
+                else
+                    for (int j = 0; j < d; j++) br16[off + j] = g.ring[(size_t)v * GD + j];
             }
         }
         if (lane == 0)
         {
             rec->nv = room ? (uint32_t)nv : 0u;
             rec->ne = (uint32_t)ne;
-            rec->nf = (uint32_t)mo.n_faces;
-            rec->tier = TIER;
-            rec->volume = mo.volume;
-            rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
-#pragma unroll
-            for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
+            rec->tier = small ? 1 : 2;
             rec->blob = blob;
-            if (!room) atomicAdd(&a.ctl->n_fail, 1u);
-            if (a.dbg)
+            rec->nf = 0;
+            if (!small)
             {
-                a.dbg[(size_t)q * 8 + 2] = (uint32_t)(t3 - t2);
-                a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t3);
+                rec->nf = (uint32_t)mo.n_faces;
+                rec->volume = mo.volume;
+                rec->centroid[0] = mo.cx; rec->centroid[1] = mo.cy; rec->centroid[2] = mo.cz;
+#pragma unroll
+                for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
             }
+            if (!room) atomicAdd(&a.ctl->n_fail, 1u);
         }
         __syncwarp();
     }
@@ -619,7 +602,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 // hardware scheduler balances the very uneven pair costs).
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
 constexpr int FAST_LANES = 32;   // lanes per pair; 16 (two pairs per warp in lock step) is correct but measured slower, see DESIGN.md section 7
-constexpr size_t FAST_BLOB = 64 * 16 + 64 * 2 + 64 * 8;   // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
+constexpr size_t FAST_BLOB = FAST_BLOB_BYTES;
 
 template <int L>
 __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 32 / FAST_WARPS : 4) clip_sub_kernel(ClipArgs a)

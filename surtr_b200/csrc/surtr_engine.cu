@@ -15,8 +15,6 @@ using namespace surtr;
 
 namespace
 {
-using Tier2 = WarpPoly<256, 16, uint16_t>;
-constexpr int T2_WARPS = 2;
 
 std::string g_create_error;
 
@@ -209,7 +207,7 @@ int ensure_capacity(surtr_ctx* ctx)
     CK(ctx->out_off.reserve(16 * ctx->cap_cand));
     if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
     CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
-    CK(ctx->scratch2.reserve(blob_bytes<Tier2>() * ctx->cap_tier2));
+    CK(ctx->scratch2.reserve(blob2_bytes() * ctx->cap_tier2));
     if (ctx->tier2_enabled) CK(ctx->ovf3_list.reserve(4 * ctx->cap_cand));   // tier 2 hands pairs on through this list
     if (ctx->tier3_enabled)
     {
@@ -324,6 +322,7 @@ int launch_event(surtr_ctx* ctx)
     ca.dbg = ctx->debug ? ctx->dbg.as<uint32_t>() : nullptr;
     {
         ca.scratch = ctx->scratch1.as<unsigned char>();
+        ca.scratch1 = ctx->scratch1.as<unsigned char>();
         ca.slot_bytes = FAST_BLOB;
         constexpr uint64_t pairs_per_block = FAST_WARPS * 32 / FAST_LANES;
         const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + pairs_per_block - 1) / pairs_per_block);
@@ -333,9 +332,9 @@ int launch_event(surtr_ctx* ctx)
     if (ctx->tier2_enabled)
     {
         ca.scratch = ctx->scratch2.as<unsigned char>();
-        ca.slot_bytes = blob_bytes<Tier2>();
-        const size_t smem = sizeof(Tier2) * T2_WARPS;
-        launch_pdl(clip_kernel<Tier2, 2, T2_WARPS>, dim3(ctx->num_sm), dim3(T2_WARPS * 32), smem, ctx->stream, ca);
+        ca.slot_bytes = blob2_bytes();
+        const size_t smem = t2_ws_bytes() * T2_WARPS;
+        launch_pdl(clip_shared_kernel, dim3(ctx->num_sm), dim3(T2_WARPS * 32), smem, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->tier3_enabled)
@@ -358,7 +357,7 @@ int launch_event(surtr_ctx* ctx)
         aa.scratch3 = ctx->scratch3.as<unsigned char>();
         aa.cap3 = ctx->cap3;
         aa.cap1 = 64;
-        aa.cap2 = Tier2::CAP;
+        aa.cap2 = T2_CAP;
         aa.st = ScanState<3>{ flags_b, agg_b, inc_b };
         aa.ctl = d_ctl;
         aa.f_rec = ctx->f_rec.as<surtr_fragment>();
@@ -478,8 +477,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
         delete ctx;
         return fail(nullptr, SURTR_ERR_NOMEM, "cudaMallocHost failed");
     }
-    cudaFuncSetAttribute(clip_kernel<Tier2, 2, T2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(Tier2) * T2_WARPS));
+    cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(t2_ws_bytes() * T2_WARPS));
     *out = ctx;
     return SURTR_OK;
 }
