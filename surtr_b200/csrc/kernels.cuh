@@ -674,9 +674,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 32 / FAST_WARPS : 4
     CandRec* rec = a.rec + q;
     if (have && status != CLIP_OK && sub.sl == 0)
     {
-        // too large for this tier (or a ring outgrew 8 slots): queue the pair for the large tier
+        // too large for this tier (or a ring outgrew 8 slots): queue the pair for the large tier, or straight for the
+        // global-memory tier when the piece cannot fit the large tier's 256 slots either
         rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-        a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
+        if (nv_in > T2_CAP) a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;
+        else a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
     }
     if (have && status == CLIP_OK && nv == 0 && sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
     const bool has = have && status == CLIP_OK && nv > 0;

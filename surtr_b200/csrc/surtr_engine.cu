@@ -208,7 +208,7 @@ int ensure_capacity(surtr_ctx* ctx)
     if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
     CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
     CK(ctx->scratch2.reserve(blob2_bytes() * ctx->cap_tier2));
-    if (ctx->tier2_enabled) CK(ctx->ovf3_list.reserve(4 * ctx->cap_cand));   // tier 2 hands pairs on through this list
+    CK(ctx->ovf3_list.reserve(4 * ctx->cap_cand));   // tiers 1 and 2 hand pairs on to the global tier through this list
     if (ctx->tier3_enabled)
     {
         // workspace: twice the largest piece (a cut adds at most one vertex per straddling edge), at least 4096 slots

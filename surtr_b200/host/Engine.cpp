@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <exception>
 #include <memory>
 #include <mutex>
@@ -286,6 +288,15 @@ void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, 
 	check(surtr_fracture_event(c), "surtr_fracture_event");
 	surtr_counts n;
 	check(surtr_event_counts(c, &n), "surtr_event_counts");
+	static const bool trace = std::getenv("SURTR_TRACE") != nullptr;
+	if (trace)
+	{
+		float total_ms = 0.f;
+		surtr_last_event_ms(c, &total_ms, nullptr);
+		std::fprintf(stderr, "[surtr]     event: %llu pairs, %llu candidates (large tier %llu, global tier %llu), %llu fragments, %.3f ms on the device\n",
+					 (unsigned long long)n.n_pairs, (unsigned long long)n.n_candidates, (unsigned long long)n.n_tier2, (unsigned long long)n.n_tier3,
+					 (unsigned long long)n.n_fragments, total_ms);
+	}
 	out.rec.resize(n.n_fragments);
 	if (geometry)
 	{

@@ -363,7 +363,7 @@ def test_degenerate_cuts_large_tiers(ctx):
     s["ring"] = common.digest(np.asarray(got.ring, np.uint16))
     assert s == _summaries()["degenerate_large"]
     c = ctx.counts()
-    assert c.n_tier2 == 96 and c.n_tier3 == 48 and c.n_seq_cuts > 50
+    assert c.n_tier2 == 48 and c.n_tier3 == 48 and c.n_seq_cuts > 50     # ACH pairs: large tier; mesh pairs: straight to the global tier
 
 
 def test_transform_pieces_on_device(ctx):
