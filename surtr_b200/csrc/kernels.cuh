@@ -758,6 +758,7 @@ struct AssembleArgs
     ScanState<3> st;
     Ctl* ctl;
     uint4* out_off;             // per candidate: fragment index, first vertex, first ring entry
+    uint32_t* frag_cand;        // per fragment: its candidate (the gather runs over fragments, not candidates)
     surtr_fragment* f_rec;
     float4* f_verts;
     uint32_t* f_ring_off;
@@ -821,8 +822,11 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs 
         }
         __syncthreads();
         if (q < n_cand)
-            a.out_off[q] = make_uint4((uint32_t)(s_excl[0] + bex[0] + e0), (uint32_t)(s_excl[1] + bex[1] + e1),
-                                      (uint32_t)(s_excl[2] + bex[2] + e2), 0u);
+        {
+            const unsigned long long fi = s_excl[0] + bex[0] + e0;
+            a.out_off[q] = make_uint4((uint32_t)fi, (uint32_t)(s_excl[1] + bex[1] + e1), (uint32_t)(s_excl[2] + bex[2] + e2), 0u);
+            if (has && fi < a.cap_frag) a.frag_cand[fi] = (uint32_t)q;
+        }
     }
 }
 
@@ -839,11 +843,14 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
     __shared__ SubPoly s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
-    const unsigned long long q = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-    unsigned long long n_cand = a.ctl->n_cand;
-    if (n_cand > a.cap_cand) n_cand = a.cap_cand;
-    bool have = q < n_cand;
-    const CandRec* r = a.rec + (have ? q : 0);
+    // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
+    // fragments that share a warp are of similar size
+    const unsigned long long f = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+    unsigned long long n_frag = a.ctl->n_frag;
+    if (n_frag > a.cap_frag) n_frag = a.cap_frag;
+    bool have = f < n_frag;
+    const unsigned long long q = have ? a.frag_cand[f] : 0ull;
+    const CandRec* r = a.rec + q;
     const int cnv = have ? (int)r->nv : 0;
     const int cne = have ? (int)r->ne : 0;
     have = have && cnv > 0;

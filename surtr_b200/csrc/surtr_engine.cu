@@ -90,7 +90,7 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off, frag_cand;
     bool debug = false;
     uint64_t cap_cand = 0, cap_tier2 = 0, cap_tier3 = 0;
     int cap3 = 0;                 // vertex slots of a tier-3 workspace (from the largest uploaded piece)
@@ -224,6 +224,7 @@ int ensure_capacity(surtr_ctx* ctx)
     const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
     CK(ctx->ctl.reserve(zero_bytes + 8 * 2 * ((size_t)ctx->n_tiles_a + 1) + 8 * 6 * ((size_t)ctx->n_tiles_b + 1)));
     CK(ctx->f_rec.reserve(sizeof(surtr_fragment) * ctx->cap_frag));
+    CK(ctx->frag_cand.reserve(4 * ctx->cap_frag));
     CK(ctx->f_verts.reserve(16 * ctx->cap_fverts));
     CK(ctx->f_ring_off.reserve(4 * (ctx->cap_fverts + 1)));
     CK(ctx->f_ring.reserve(2 * ctx->cap_fring));
@@ -368,11 +369,12 @@ int launch_event(surtr_ctx* ctx)
         aa.cap_fverts = ctx->cap_fverts;
         aa.cap_fring = ctx->cap_fring;
         aa.out_off = ctx->out_off.as<uint4>();
+        aa.frag_cand = ctx->frag_cand.as<uint32_t>();
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
         launch_pdl(assemble_scan_kernel, dim3(blocks), dim3(AS_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
         constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
-        const uint64_t gblocks = std::max<uint64_t>(1, (ctx->cap_cand + cand_per_block - 1) / cand_per_block);
+        const uint64_t gblocks = std::max<uint64_t>(1, (std::min(ctx->cap_cand, ctx->cap_frag) + cand_per_block - 1) / cand_per_block);
         launch_pdl(assemble_gather_kernel<GATHER_LANES>, dim3((unsigned)gblocks), dim3(GATHER_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
     }
