@@ -546,11 +546,25 @@ __device__ int sub_clip_by_planes(SubPoly& sp, CutState& s, int& nv, const float
     return status;
 }
 
+// Shared-memory image of one finished small-tier fragment for its face count and moments (K4 gather).
+struct MomPoly   // 4096 bytes
+{
+    float x[64], y[64], z[64];
+    u64 ring[64];          // 8 x u8, 0xFF = empty slot
+    float4 tri[128];       // ordered fan-triangle records (dV, mx, my, mz)
+    uint16_t flist[128];   // one entry per face, in Poly::ExtractFaces order: start vertex | start slot << 6 | first triangle << 9
+    uint8_t fcnt[512];     // [vertex * 8 + slot]: fan triangles of the face that starts there
+};
+
 // Poly::ExtractFaces + Poly::Moments in the reference's accumulation order (Poly.cpp:55-126) + inertia, on the
 // live (not renumbered) slots: vertex order = slot order, origin = first live vertex.  See DESIGN.md section 5
 // for the derivation.  Called by all lanes of the warp; pairs without a fragment (`has` false) idle.
+// Three steps: (1) lane = vertex: which ring slots start a face (the vertex is the smallest of the loop) and how many
+// fan triangles it has; (2) two prefix sums give every face its position in ExtractFaces order and its first triangle
+// slot, and the faces are LISTED; (3) lane = face: the fan triangles of a face are written to their slots.  Listing the
+// faces balances step 3 -- the lowest-numbered vertices start three faces each and used to walk them one after another.
 template <int L>
-__device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L> sub, bool has, Moments& out)
+__device__ void sub_fragment_moments(MomPoly& sp, const CutState& s, const Sub<L> sub, bool has, Moments& out)
 {
     constexpr int G = Sub<L>::G;
     const int first = has ? __ffsll((long long)s.live) - 1 : 0;
@@ -558,15 +572,14 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
     const float ox = sp.x[first], oy = sp.y[first], oz = sp.z[first];
     const int nv = has ? __popcll(s.live) : 0;
     u64 start_mask = 0ull;   // 8 slot bits per owned group
-    int faces = 0;           // faces this lane starts
-    int cntg[G];             // their fan triangles, per owned group (one lane = one scan entry per group)
+    int cntg[G], facg[G];    // fan triangles / faces started per owned group (one lane = one scan entry per group)
 #pragma unroll
-    for (int g = 0; g < G; g++) cntg[g] = 0;
-    // (rolled: the body is large and runs once per pair -- two copies of it only cost instruction-cache space)
+    for (int g = 0; g < G; g++) cntg[g] = facg[g] = 0;
+    // (rolled: the body is large and runs once per fragment -- copies of it only cost instruction-cache space)
 #pragma unroll 1
     for (int g = 0; g < G; g++)
     {
-        int tris = 0;
+        int tris = 0, faces = 0;
         const int v = sub.sl + L * g;
         if (has && g * L < s.hi && bit64(s.live, v))
         {
@@ -593,77 +606,83 @@ __device__ void sub_fragment_moments(SubPoly& sp, const CutState& s, const Sub<L
                     start_mask |= 1ull << (j + 8 * g);
                     faces++;
                     tris += max(n - 2, 0);
+                    sp.fcnt[v * 8 + j] = (uint8_t)max(n - 2, 0);
                 }
             }
         }
 #pragma unroll
         for (int h = 0; h < G; h++)
-            if (h == g) cntg[h] = tris;
+            if (h == g) { cntg[h] = tris; facg[h] = faces; }
     }
-    // triangle order = vertex order = group-major, lane-minor: one scan per group that has vertices
-    int tri_base[G];
-    int n_tri = 0;
-#pragma unroll
-    for (int g = 0; g < G; g++)
-    {
-        tri_base[g] = 0;
-        if (g < gmax)
-        {
-            int tot;
-            tri_base[g] = n_tri + sub.exscan(cntg[g], tot);
-            n_tri += tot;
-        }
-    }
-    const int n_faces = sub.sum(faces);
-    n_tri = min(n_tri, 128);
-
-    float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
+    // face and triangle order = vertex order = group-major, lane-minor: one scan pair per group that has vertices
+    int n_tri = 0, n_faces = 0;
 #pragma unroll 1
     for (int g = 0; g < G; g++)
     {
-        unsigned m = (unsigned)(start_mask >> (8 * g)) & 0xffu;
-        if (!m) continue;
-        const int v = sub.sl + L * g;
-        int w = 0;
-#pragma unroll
-        for (int h = 0; h < G; h++)
-            if (h == g) w = tri_base[h];
-        const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
-        const u64 rw = sp.ring[v];
-        while (m)
+        if (g < gmax)
         {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            int prev = v, at = rget(rw, j);
-            float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
-            int nxt = rface_loop(sp.ring[at], prev);
+            int tris = 0, faces = 0;
+#pragma unroll
+            for (int h = 0; h < G; h++)
+                if (h == g) { tris = cntg[h]; faces = facg[h]; }
+            int ttot, ftot;
+            int tpos = n_tri + sub.exscan(tris, ttot);
+            int fpos = n_faces + sub.exscan(faces, ftot);
+            n_tri += ttot;
+            n_faces += ftot;
+            unsigned m = (unsigned)(start_mask >> (8 * g)) & 0xffu;
+            const int v = sub.sl + L * g;
+            while (m)
+            {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (fpos < 128) sp.flist[fpos] = (uint16_t)(v | (j << 6) | (min(tpos, 127) << 9));
+                fpos++;
+                tpos += sp.fcnt[v * 8 + j];
+            }
+        }
+    }
+    n_tri = min(n_tri, 128);
+    sub.sync();
+
+    float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
+    const int n_listed = has ? min(n_faces, 128) : 0;
+#pragma unroll 1
+    for (int t = sub.sl; t < n_listed; t += L)
+    {
+        const unsigned e = sp.flist[t];
+        const int v = (int)(e & 63u), j = (int)((e >> 6) & 7u);
+        int w = (int)(e >> 9);
+        const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
+        int prev = v, at = rget(sp.ring[v], j);
+        float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
+        int nxt = rface_loop(sp.ring[at], prev);
+        prev = at;
+        at = nxt;
+        while (at != v)
+        {
+            const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
+            float cx, cy, cz;
+            cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
+            const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
+            const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
+            const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
+            const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
+            if (w < 128) sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
+            w++;
+            // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
+            cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
+            cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
+            cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
+            cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
+            cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
+            cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
+            cov[6] += dV;
+            cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
+            p1x = p2x; p1y = p2y; p1z = p2z;
+            nxt = rface_loop(sp.ring[at], prev);
             prev = at;
             at = nxt;
-            while (at != v)
-            {
-                const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
-                float cx, cy, cz;
-                cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
-                const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
-                const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
-                const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
-                const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
-                if (w < 128) sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
-                w++;
-                // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
-                cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
-                cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
-                cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
-                cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
-                cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
-                cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
-                cov[6] += dV;
-                cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
-                p1x = p2x; p1y = p2y; p1z = p2z;
-                nxt = rface_loop(sp.ring[at], prev);
-                prev = at;
-                at = nxt;
-            }
         }
     }
     sub.sync();

@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
 {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ SubPoly s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
+    __shared__ MomPoly s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
     // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) have = false;   // the host grows and re-runs
     }
     const int tier = have ? (int)r->tier : 0;
-    SubPoly& sp = s_poly[threadIdx.x / L];
+    MomPoly& sp = s_poly[threadIdx.x / L];
     if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
