@@ -386,3 +386,43 @@ def test_transform_pieces_on_device(ctx):
     ctx.upload_cells(planes, off, placed.verts, placed.vert_off)
     ctx.fracture_event()
     common.assert_fragments_equal(ctx.download(), P.apply_fracture(moved, planes, off))
+
+
+def test_async_download_and_contexts_in_flight():
+    """surtr_download_fragments_async + surtr_sync: three contexts driven round-robin from one host thread, each
+    launching its next event right behind the enqueued copies of the previous one; every result equals the oracle."""
+    import torch
+    from surtr_b200 import FractureContext, FRAGMENT_DTYPE
+    cube = common.unit_cube()
+    sets = [common.voronoi(46354 + k, 64) for k in range(3)]
+    wants = [P.apply_fracture(cube, c.planes, c.plane_off) for c in sets]
+    pipes = []
+    for k in range(3):
+        st = torch.cuda.Stream()
+        cx = FractureContext(0, st.cuda_stream)
+        want = wants[k]
+        bufs = dict(rec=torch.zeros(want.n * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                    verts=torch.zeros(len(want.verts) * 4, dtype=torch.float32).pin_memory(),
+                    ring_off=torch.zeros(len(want.verts) + 1, dtype=torch.int32).pin_memory(),
+                    ring=torch.zeros(len(want.ring), dtype=torch.int16).pin_memory())
+        pipes.append((cx, st, bufs))
+    try:
+        for step in range(9):
+            k = step % 3
+            cx, st, b = pipes[k]
+            if step >= 3:
+                cx.download_into_async(b["rec"].data_ptr(), b["verts"].data_ptr(), b["ring_off"].data_ptr(), b["ring"].data_ptr())
+            cx.upload_pieces(cube.verts, cube.vert_off, cube.ring_off, cube.ring)
+            cx.upload_cells(sets[k].planes, sets[k].plane_off, sets[k].verts, sets[k].vert_off)
+            cx.fracture_event()
+        for k, (cx, st, b) in enumerate(pipes):
+            cx.download_into_async(b["rec"].data_ptr(), b["verts"].data_ptr(), b["ring_off"].data_ptr(), b["ring"].data_ptr())
+            cx.sync()
+            rec = np.frombuffer(b["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
+            assert len(rec) == wants[k].n and np.array_equal(rec["n_verts"], wants[k].nverts)
+            assert np.array_equal(bits(b["verts"].numpy().reshape(-1, 4)), bits(wants[k].verts))
+            assert np.array_equal(b["ring"].numpy().view(np.uint16), wants[k].ring)
+            assert np.array_equal(bits(rec["volume"]), bits(wants[k].volume))
+    finally:
+        for cx, st, b in pipes:
+            cx.close()
