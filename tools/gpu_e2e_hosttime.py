@@ -27,10 +27,14 @@ for d in range(D):
 T = collections.Counter()
 def timed(name, f, *a):
     t0 = time.perf_counter(); f(*a); T[name] += time.perf_counter() - t0
+import os
+NO_UP, NO_DOWN = bool(os.environ.get('NO_UP')), bool(os.environ.get('NO_DOWN'))
 def run(n, with_flush):
     for i in range(n + D):
         cx, st, ho = pipes[i % D]
-        if i >= D:
+        if i >= D and NO_DOWN:
+            timed("counts only", cx.counts)
+        elif i >= D:
             timed("download_async (incl. wait for the event)", cx.download_into_async, ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
         if i < n:
             if with_flush:
@@ -38,8 +42,8 @@ def run(n, with_flush):
                     with torch.cuda.stream(st):
                         flush.zero_()
                 timed("flush launch", fl)
-            timed("upload_pieces", cx.upload_pieces_ptr, h["pv"].data_ptr(), h["pvo"].data_ptr(), h["pro"].data_ptr(), h["pr"].data_ptr(), 1)
-            timed("upload_cells", cx.upload_cells_ptr, h["planes"].data_ptr(), h["plane_off"].data_ptr(), h["cverts"].data_ptr(), h["cvo"].data_ptr(), N)
+            if not NO_UP: timed("upload_pieces", cx.upload_pieces_ptr, h["pv"].data_ptr(), h["pvo"].data_ptr(), h["pro"].data_ptr(), h["pr"].data_ptr(), 1)
+            if not NO_UP: timed("upload_cells", cx.upload_cells_ptr, h["planes"].data_ptr(), h["plane_off"].data_ptr(), h["cverts"].data_ptr(), h["cvo"].data_ptr(), N)
             timed("fracture_event (6 launches)", cx.fracture_event)
     for cx, st, ho in pipes:
         cx.sync()
