@@ -145,11 +145,12 @@ int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out);
 /* Any pointer may be NULL to skip that array.  Sizes come from surtr_event_counts. */
 int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off,
                              uint16_t* ring);
-/* Same, but returns once the copies are enqueued on the context stream (after waiting for the event itself, which
- * sizes them).  The host buffers (pinned, for the copies to be asynchronous) are complete when surtr_sync, or any later
- * call on this context that waits for its stream (surtr_event_counts of the next event, ...), has returned.  The next
- * event may be uploaded and launched right away: it is ordered behind the copies on the stream.  Lets one host
- * thread keep several contexts busy without ever blocking on PCIe. */
+/* Same, but returns once the copies are enqueued (after waiting for the event itself, which sizes them).  They run
+ * on a copy stream of the context: the next event may be uploaded and launched right away -- its uploads and its
+ * K1-K3 overlap the copies, only K4 (which rewrites the fragment arrays) is ordered behind them.  The host buffers
+ * (pinned, for the copies to be asynchronous) are complete when surtr_sync has returned, or any call that waits for an
+ * event launched after this one (its surtr_event_counts / download).  Lets one host thread keep several contexts busy
+ * without ever blocking on PCIe. */
 int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off,
                                    uint16_t* ring);
 int surtr_sync(surtr_ctx* ctx);

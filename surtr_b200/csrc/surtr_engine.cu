@@ -67,6 +67,11 @@ struct surtr_ctx
     int num_sm = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // asynchronous downloads run on their own stream so that the next event's uploads and K1-K3 need not queue behind
+    // them; only K4 (which rewrites the fragment arrays) waits for the copies (copy_done)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    bool copy_pending = false;
     std::string err;
     int kdirs = 3;
 
@@ -371,6 +376,12 @@ int launch_event(surtr_ctx* ctx)
         aa.out_off = ctx->out_off.as<uint4>();
         aa.frag_cand = ctx->frag_cand.as<uint32_t>();
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>(ctx->n_tiles_b, (uint32_t)ctx->num_sm * 4));
+        if (ctx->copy_pending)
+        {
+            // K4 rewrites the fragment arrays: the asynchronous download of the previous event must have left them
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+            ctx->copy_pending = false;
+        }
         launch_pdl(assemble_scan_kernel, dim3(blocks), dim3(AS_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
         constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
@@ -391,7 +402,11 @@ int launch_event(surtr_ctx* ctx)
 int resolve_event(surtr_ctx* ctx)
 {
     if (!ctx->event_launched) return fail(ctx, SURTR_ERR_INVALID, "no fracture event has been launched");
-    if (ctx->event_resolved) return SURTR_OK;
+    if (ctx->event_resolved)
+    {
+        if (ctx->copy_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
+        return SURTR_OK;
+    }
     for (int attempt = 0; attempt < 6; attempt++)
     {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -474,6 +489,8 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
         ctx->own_stream = true;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming);
     if (cudaMallocHost(&ctx->h_ctl, sizeof(Ctl)) != cudaSuccess)
     {
         delete ctx;
@@ -489,14 +506,18 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
-                      &ctx->f_ring_off, &ctx->f_ring };
+                      &ctx->f_ring_off, &ctx->f_ring, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
+                      &ctx->xf_idx };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -601,17 +622,24 @@ int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, fl
 {
     if (!ctx) return SURTR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    const int rc = resolve_event(ctx);
+    if (ctx->event_resolved && ctx->copy_pending) ctx->copy_pending = false;   // (re-issued below; the stream keeps them ordered)
+    const int rc = resolve_event(ctx);   // the event is complete on the main stream from here on
     if (rc) return rc;
     const surtr_counts& c = ctx->last;
+    cudaStream_t cs = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
     if (fragments && c.n_fragments)
-        CK(cudaMemcpyAsync(fragments, ctx->f_rec.p, sizeof(surtr_fragment) * c.n_fragments, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(fragments, ctx->f_rec.p, sizeof(surtr_fragment) * c.n_fragments, cudaMemcpyDeviceToHost, cs));
     if (verts4 && c.n_verts)
-        CK(cudaMemcpyAsync(verts4, ctx->f_verts.p, 16 * c.n_verts, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(verts4, ctx->f_verts.p, 16 * c.n_verts, cudaMemcpyDeviceToHost, cs));
     if (ring_off)
-        CK(cudaMemcpyAsync(ring_off, ctx->f_ring_off.p, 4 * (c.n_verts + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ring_off, ctx->f_ring_off.p, 4 * (c.n_verts + 1), cudaMemcpyDeviceToHost, cs));
     if (ring && c.n_ring)
-        CK(cudaMemcpyAsync(ring, ctx->f_ring.p, 2 * c.n_ring, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ring, ctx->f_ring.p, 2 * c.n_ring, cudaMemcpyDeviceToHost, cs));
+    if (ctx->copy_stream)
+    {
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        ctx->copy_pending = true;
+    }
     return SURTR_OK;
 }
 
@@ -620,6 +648,8 @@ int surtr_sync(surtr_ctx* ctx)
     if (!ctx) return SURTR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending = false;
     return SURTR_OK;
 }
 
