@@ -41,84 +41,86 @@ std::vector<std::vector<int>> ExtractNeighborFromMesh(const std::vector<Vector3>
 			inc[fill[indices[3 * t + k]]++] = t;
 	const auto touches = [&](const int t, const int v) { return indices[3 * t] == v || indices[3 * t + 1] == v || indices[3 * t + 2] == v; };
 
-	// per-triangle adjacency, duplicates removed in first-seen order (:150-170), as one CSR
-	std::vector<int> adj_off(n_tri + 1, 0), adj;
-	adj.reserve(4 * (size_t)n_tri);
-	for (int curr = 0; curr < n_tri; curr++)
-	{
-		const size_t begin = adj.size();
-		for (int e = 0; e < 3; e++)
+	// per-triangle adjacency, duplicates removed in first-seen order (:150-170); triangles are independent -> worker pool
+	constexpr int CHUNK = 256;
+	std::vector<std::vector<int>> adj(n_tri);
+	SurtrHost::detail::parallel_for((size_t)(n_tri + CHUNK - 1) / CHUNK, [&](size_t chunk) {
+		for (int curr = (int)chunk * CHUNK; curr < std::min(n_tri, ((int)chunk + 1) * CHUNK); curr++)
 		{
-			const int a = indices[3 * curr + e], b = indices[3 * curr + (e + 1) % 3];
-			const int* pa = &inc[inc_off[a]], * ea = &inc[inc_off[a + 1]];
-			const int* pb = &inc[inc_off[b]], * eb = &inc[inc_off[b + 1]];
-			while (pa != ea && pb != eb)   // std::set_intersection of two ascending lists (:156-158)
+			std::vector<int>& out = adj[curr];
+			for (int e = 0; e < 3; e++)
 			{
-				if (*pa < *pb) ++pa;
-				else if (*pb < *pa) ++pb;
-				else
+				const int a = indices[3 * curr + e], b = indices[3 * curr + (e + 1) % 3];
+				const int* pa = &inc[inc_off[a]], * ea = &inc[inc_off[a + 1]];
+				const int* pb = &inc[inc_off[b]], * eb = &inc[inc_off[b + 1]];
+				while (pa != ea && pb != eb)   // std::set_intersection of two ascending lists (:156-158)
 				{
-					const int t = *pa;
-					++pa; ++pb;
-					if (t != curr && adj.end() == std::find(adj.begin() + begin, adj.end(), t))
-						adj.push_back(t);
+					if (*pa < *pb) ++pa;
+					else if (*pb < *pa) ++pb;
+					else
+					{
+						const int t = *pa;
+						++pa; ++pb;
+						if (t != curr && out.end() == std::find(out.begin(), out.end(), t))
+							out.push_back(t);
+					}
 				}
 			}
 		}
-		adj_off[curr + 1] = (int)adj.size();
-	}
+	});
 
+	// one fan walk per vertex (:172-251), independent of each other -> worker pool
 	std::vector<std::vector<int>> nei(n_vert);
-	std::vector<int> fan;
-	for (int iVert = 0; iVert < n_vert; iVert++)
-	{
-		if (inc_off[iVert] == inc_off[iVert + 1])
-			continue;   // a vertex no triangle uses keeps an empty ring
-		fan.assign(1, inc[inc_off[iVert]]);
-		for (int curr = fan[0];;)
+	SurtrHost::detail::parallel_for((size_t)(n_vert + CHUNK - 1) / CHUNK, [&](size_t chunk) {
+		std::vector<int> fan;
+		for (int iVert = (int)chunk * CHUNK; iVert < std::min(n_vert, ((int)chunk + 1) * CHUNK); iVert++)
 		{
-			int next = -1, n_candidates = 0;
-			const int* across_begin = adj.data() + adj_off[curr];
-			const int* across_end = adj.data() + adj_off[curr + 1];
-			for (const int* it = across_begin; it != across_end; ++it)
-				if (fan.end() == std::find(fan.begin(), fan.end(), *it) && touches(*it, iVert))
-				{
-					if (n_candidates++ == 0)
-						next = *it;
-				}
-			if (n_candidates == 0)
-				break;
-			if (n_candidates > 2)
-				throw std::runtime_error("ExtractNeighborFromMesh: non-manifold fan (the reference does not terminate here)");
-			fan.push_back(next);
-			curr = next;
-		}
+			if (inc_off[iVert] == inc_off[iVert + 1])
+				continue;   // a vertex no triangle uses keeps an empty ring
+			fan.assign(1, inc[inc_off[iVert]]);
+			for (int curr = fan[0];;)
+			{
+				int next = -1, n_candidates = 0;
+				for (const int t : adj[curr])
+					if (fan.end() == std::find(fan.begin(), fan.end(), t) && touches(t, iVert))
+					{
+						if (n_candidates++ == 0)
+							next = t;
+					}
+				if (n_candidates == 0)
+					break;
+				if (n_candidates > 2)
+					throw std::runtime_error("ExtractNeighborFromMesh: non-manifold fan (the reference does not terminate here)");
+				fan.push_back(next);
+				curr = next;
+			}
 
-		std::vector<int> collection;
-		for (const int t : fan)
-		{
-			int start = 0;
-			for (int k = 0; k < 3; k++)
-				if (indices[3 * t + k] == iVert) { start = k; break; }
-			collection.push_back(indices[3 * t + (start + 1) % 3]);
-			collection.push_back(indices[3 * t + (start + 2) % 3]);
+			std::vector<int> collection;
+			for (const int t : fan)
+			{
+				int start = 0;
+				for (int k = 0; k < 3; k++)
+					if (indices[3 * t + k] == iVert) { start = k; break; }
+				collection.push_back(indices[3 * t + (start + 1) % 3]);
+				collection.push_back(indices[3 * t + (start + 2) % 3]);
+			}
+			if (collection.size() >= 3)
+			{
+				const bool isCCW = collection[1] != collection[2];   // :236
+				if (isCCW)
+					for (size_t i = 0; i + 1 < collection.size(); i += 2)
+						std::swap(collection[i], collection[i + 1]);
+				std::vector<int> unique;
+				for (const int v : collection)
+					if (unique.end() == std::find(unique.begin(), unique.end(), v))
+						unique.push_back(v);
+				if (isCCW)
+					std::reverse(unique.begin(), unique.end());
+				collection.swap(unique);
+			}
+			nei[iVert].swap(collection);
 		}
-		if (collection.size() >= 3)
-		{
-			const bool isCCW = collection[1] != collection[2];   // :236
-			if (isCCW)
-				for (size_t i = 0; i + 1 < collection.size(); i += 2)
-					std::swap(collection[i], collection[i + 1]);
-			std::vector<int> unique;
-			for (const int v : collection)
-				if (unique.end() == std::find(unique.begin(), unique.end(), v))
-					unique.push_back(v);
-			if (isCCW)
-				std::reverse(unique.begin(), unique.end());
-			collection.swap(unique);
-		}
-		nei[iVert].swap(collection);
-	}
+	});
 	for (int v = 0; v < n_vert; v++)   // :253-260
 		for (const int a : nei[v])
 			if (nei[a].end() == std::find(nei[a].begin(), nei[a].end(), v))
