@@ -239,6 +239,9 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
                 g.deg[w] = 2;
                 g.ring[(size_t)w * GD] = (uint16_t)v;
                 g.ring[(size_t)w * GD + 1] = (uint16_t)jn;
+                // several lanes may patch the ring of the same kept vertex jn at once: each replaces only the entry holding
+                // ITS clipped vertex v, and an entry another lane is rewriting (v' -> w') equals v neither before nor after
+                // -- entry-disjoint by construction (compute-sanitizer racecheck warns at word level, profiles/r1_sanitizer.txt)
                 uint16_t* rj = g.ring + (size_t)jn * GD;
                 const int dj = g.deg[jn];
                 int k = 0;
