@@ -230,6 +230,8 @@ def main():
     n_frag = int(c0.n_fragments)
     fr0 = ctx.download()
     alg_bytes = synth.algorithmic_bytes(cube_vo, cube_ro, cells.plane_off, fr0.rec)
+    alg_flops = synth.algorithmic_flops(cube_vo, cells.plane_off, fr0.rec)
+    fp32_peak_tflops = ctx.measure_fp32_peak()
 
     flush = torch.empty(FLUSH_MIB * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -459,6 +461,11 @@ def main():
                               "timed region; single_event_ms = the same with one event at a time (flush outside)"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
             "clocks": clocks, "roofline": roofline,
+            # secondary roofline the north star asks for: algorithmic FP32 work of the whole job against the FFMA rate
+            # measured in this run (both tiny by design: the path is topology work, not arithmetic)
+            "fp32": {"algorithmic_flops_per_step": alg_flops, "achieved_gflops": alg_flops / (total_ms / args.steps * 1e-3) / 1e9,
+                     "peak_tflops_measured": fp32_peak_tflops,
+                     "frac": alg_flops / (total_ms / args.steps * 1e-3) / 1e12 / fp32_peak_tflops if fp32_peak_tflops else None},
         }
         if gather:
             line["gather"] = gather

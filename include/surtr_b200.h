@@ -175,6 +175,9 @@ int surtr_kdop_calc_batch(surtr_ctx* ctx, const float* verts4, const uint32_t* v
 int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms);
 int surtr_set_profiling(surtr_ctx* ctx, int on);
 /* Number of kernels the last surtr_fracture_event launched. */
+/* Measurement helper: FP32 FMA throughput of the device (TFLOP/s) from a register-resident FFMA kernel on the context
+ * stream -- the denominator of the secondary (FP32 pipe) roofline in bench.py. */
+int surtr_measure_fp32_peak(surtr_ctx* ctx, float* tflops);
 int surtr_last_event_launches(const surtr_ctx* ctx);
 
 #ifdef __cplusplus

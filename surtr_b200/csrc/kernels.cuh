@@ -178,6 +178,22 @@ __global__ void __launch_bounds__(256) transform_pieces_kernel(float4* __restric
     }
 }
 
+// FP32 FMA microbenchmark (measurement only; SURVEY section 8d asks for the FP32 pipe peak measured in the same run as
+// the bench): 8 independent FFMA chains per thread, explicit __fmaf_rn (the TU is built with -fmad=false).
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, int iters, float a, float b)
+{
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = (float)(threadIdx.x + k) * 1.0e-3f;
+    for (int i = 0; i < iters; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = __fmaf_rn(x[k], a, b);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += x[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains alive
+}
+
 // ---------------------------------------------------------------------------------------------- K2
 // Conservative separation test: a pair is culled only when some slab is separated by more than a few ulps of
 // the extents' magnitude, so no pair the clipper would keep is ever dropped (slivers).

@@ -882,6 +882,28 @@ int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
     return SURTR_OK;
 }
 
+int surtr_measure_fp32_peak(surtr_ctx* ctx, float* tflops)
+{
+    if (!ctx || !tflops) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dbg.reserve(4));
+    const int iters = 8192, blocks = ctx->num_sm * 16, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->dbg.as<float>(), 64, 0.999f, 1.0e-6f);   // warm-up
+    CK(cudaEventRecord(e0, ctx->stream));
+    fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->dbg.as<float>(), iters, 0.999f, 1.0e-6f);
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = (float)(2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+    return SURTR_OK;
+}
+
 int surtr_last_event_launches(const surtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int surtr_set_profiling(surtr_ctx* ctx, int on)

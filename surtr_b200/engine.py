@@ -33,7 +33,7 @@ EXPORTS = [
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
-    "surtr_transform_pieces", "surtr_download_pieces",
+    "surtr_transform_pieces", "surtr_download_pieces", "surtr_measure_fp32_peak",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     lib.surtr_sync.argtypes = [vp]
     lib.surtr_transform_pieces.argtypes = [vp, vp, vp, u32]
     lib.surtr_download_pieces.argtypes = [vp, vp]
+    lib.surtr_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_float)]
     lib.surtr_device_fragments.argtypes = [vp, C.POINTER(DeviceView)]
     lib.surtr_kdop_calc.argtypes = [vp, vp, u32, vp, u32, vp, vp, vp]
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -188,6 +189,12 @@ class FractureContext:
         out = np.zeros((n_verts, 4), np.float32)
         self._ck(self._lib.surtr_download_pieces(self._h, _p(out)))
         return out
+
+    def measure_fp32_peak(self) -> float:
+        """FP32 FMA throughput of the device in TFLOP/s (measurement helper)."""
+        t = C.c_float(0)
+        self._ck(self._lib.surtr_measure_fp32_peak(self._h, C.byref(t)))
+        return float(t.value)
 
     def upload_pattern(self, face_verts4, face_vert_off, cell_face_off):
         """Resident fracture pattern: the VertexVec of every face of every cell (see include/surtr_b200.h)."""

@@ -166,3 +166,16 @@ def algorithmic_bytes(pieces_vert_off, pieces_ring_off, plane_off, rec) -> int:
     v_out = rec["n_verts"].astype(np.int64)
     e_out = rec["n_ring"].astype(np.int64)
     return int(np.sum(16 * v_in + 4 * e_in + 16 * pl + 16 * v_out + 4 * e_out + 64))
+
+
+def algorithmic_flops(pieces_vert_off, plane_off, rec) -> int:
+    """FP32 operations the path needs per surviving pair -- classification 6*P*V (three
+    multiplies and three adds per vertex per plane, V = mean of the piece's and the fragment's vertex counts),
+    13 per new vertex (one intersection; about one new vertex per result vertex and cut generation, counted as
+    2*V_out), and 24 + 60 per fan triangle for volume / centroid and inertia over 2*V_out - 4 triangles."""
+    p = rec["piece"].astype(np.int64)
+    c = rec["cell"].astype(np.int64)
+    v_in = (pieces_vert_off[p + 1] - pieces_vert_off[p]).astype(np.int64)
+    pl = (plane_off[c + 1] - plane_off[c]).astype(np.int64)
+    v_out = rec["n_verts"].astype(np.int64)
+    return int(np.sum(6 * pl * (v_in + v_out) // 2 + 13 * 2 * v_out + 84 * np.maximum(2 * v_out - 4, 0)))
