@@ -180,6 +180,8 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
 
             // classify (Poly.cpp:303-319)
             bool any_clip = false, any_keep = false, any_zero = false;
+            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+#pragma unroll 4
             for (int base = 0; base < nv; base += 32)
             {
                 const int v = base + lane;
@@ -205,6 +207,8 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
             const int nverts0 = nv;
             int nnew = 0;
+            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+#pragma unroll 2
             for (int base = 0; base < nverts0; base += 32)
             {
                 const int v = base + lane;
@@ -307,6 +311,8 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
 
             // compaction (Poly.cpp:464-499)
             int kept_before = 0;
+            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+#pragma unroll 4
             for (int base = 0; base < nverts; base += 32)
             {
                 const int v = base + lane;
@@ -317,6 +323,8 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             }
             __syncwarp();
             bool dangling = false;   // a live ring pointing at an erased vertex: not a polyhedron (the reference would store -1)
+            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+#pragma unroll 2
             for (int base = 0; base < nverts; base += 32)
             {
                 const int v = base + lane;
