@@ -190,3 +190,18 @@ def test_port_degenerate_cuts_on_large_pieces_match_reference_summary():
     s = common.summary_of_polyset(got)
     s["ring"] = common.digest(np.asarray(got.ring, np.uint16))
     assert s == want
+
+
+@pytest.mark.skipif(not common.have_ref(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("seed", [1, 9])
+def test_port_matches_reference_on_random_pairs(seed):
+    """The randomised sweep of tests/test_gpu_fuzz.py checks the GPU against the PORT; here the port is checked against
+    the reference build on inputs of the same generator (rotated pieces, in-plane planes, long plane lists)."""
+    import test_gpu_fuzz as F
+    rng = np.random.RandomState(1000 + seed)
+    pieces = F.random_pieces(rng, seed)
+    planes, off = F.random_cells(rng, pieces, 120)
+    want = R.apply_fracture(pieces, planes, off, 8)
+    got = P.apply_fracture(pieces, planes, off, cap_frags=pieces.n * 120 + 16)
+    assert_polysets_equal(got, want)
+    assert want.n > 3000
