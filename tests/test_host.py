@@ -256,3 +256,48 @@ def test_cpp_example_runs_the_reference_flow(tmp_path):
     r = subprocess.run([os.path.join(root, "examples", "fracture_demo"), str(obj), "1.0", "32"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "-> 27 pieces" in r.stdout and "DoFracture(partial)" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not common.have_ref(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("case", list(range(8)))
+def test_do_fracture_random_impacts_match_reference(case):
+    """DoFracture with random impact points, radii, pattern seeds and modes on the bunny compound: the host classes (GPU
+    events + host orchestration) against the restatement over the reference build, live (oracle/_ref travels to the
+    GPU box): pieces, order and compounds bit for bit."""
+    from oracle import refapi as R
+    d = np.load(os.path.join(GOLDEN, "do_fracture_bunny.npz"))
+    d0 = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    convex, mesh = load_polyset(d0, "convex_"), load_polyset(d0, "mesh_")
+    rng = np.random.RandomState(300 + case)
+    v = d0["verts"][:, :3]
+    impact = v[rng.randint(len(v))].copy()
+    partial = bool(case % 2)
+    radius = float(rng.uniform(1.0, 5.0))
+    n_seeds = int(rng.choice([16, 32, 48]))
+    seeds = R.seeds_radial(int(rng.randint(1, 10 ** 6)), n_seeds, float(rng.choice([0.02, 0.05, 0.3, 1.0])))
+    off, idx = H.dt3d_neighbors(seeds)
+    max_axis = float(d["max_axis_scale"])
+    want_c, want_m, want_n = R.do_fracture(convex, mesh, seeds, off, idx, d["cloud"], impact, radius, max_axis, partial)
+    got_c, got_m, got_n, _ = H.do_fracture(convex, mesh, seeds, d["cloud"], impact, radius, max_axis, partial)
+    assert got_n == want_n and got_c.n == want_c.n
+    for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece"):
+        assert np.array_equal(bits(getattr(got_c, f)), bits(getattr(want_c, f))), "convex " + f
+        assert np.array_equal(bits(getattr(got_m, f)), bits(getattr(want_m, f))), "mesh " + f
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not common.have_ref(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_prepare_fracture_random_seeds_match_reference(case):
+    """Full PrepareFracture on the bunny with other seed sets (16 / 48 / 64 cells) against the live reference restatement."""
+    from oracle import refapi as R
+    d = np.load(os.path.join(GOLDEN, "config1_full_bunny32.npz"))
+    seeds = R.seeds_uniform(7000 + case, (16, 48, 64)[case])
+    off, idx = H.dt3d_neighbors(seeds)
+    _, want_c, want_m = R.config1_full(d["verts"], d["indices"], seeds, off, idx)
+    got_c, got_m, _ = H.config1_full(d["verts"], d["indices"], seeds)
+    assert got_c.n == want_c.n
+    for f in ("verts", "vert_off", "ring_off", "ring", "cell", "piece"):
+        assert np.array_equal(bits(getattr(got_c, f)), bits(getattr(want_c, f))), "convex " + f
+        assert np.array_equal(bits(getattr(got_m, f)), bits(getattr(want_m, f))), "mesh " + f
