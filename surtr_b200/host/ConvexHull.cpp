@@ -1,5 +1,7 @@
 #include "ConvexHull.h"
 
+#include "Engine.h"
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -173,13 +175,19 @@ void ConvexHull::CreateConvexHull()
 {
 	if (!BuildFirstHull())
 		return;
-	for (size_t i = 0; i < m_pointCloud.size(); i++)
-	{
-		if (m_pointCloud[i].Processed)
-			continue;
-		for (const ConvexHullFace& f : m_faceList)
-			m_pointVolume[i] += std::max(0.0f, Volume(f, m_pointCloud[i]));
-	}
+	// every point's outside volume is its own sequential sum: the points are spread over the worker pool, the order
+	// of the additions per point is the reference's
+	constexpr size_t CHUNK = 256;
+	const size_t n_chunks = (m_pointCloud.size() + CHUNK - 1) / CHUNK;
+	SurtrHost::detail::parallel_for(n_chunks, [&](size_t c) {
+		for (size_t i = c * CHUNK; i < std::min(m_pointCloud.size(), (c + 1) * CHUNK); i++)
+		{
+			if (m_pointCloud[i].Processed)
+				continue;
+			for (const ConvexHullFace& f : m_faceList)
+				m_pointVolume[i] += std::max(0.0f, Volume(f, m_pointCloud[i]));
+		}
+	});
 	if (m_limitCnt == 0)
 		m_limitCnt = (uint32_t)m_pointCloud.size();
 	while (m_processedPointCnt < m_limitCnt)
@@ -190,18 +198,20 @@ void ConvexHull::CreateConvexHull()
 		m_pointCloud[k].Processed = true;
 		m_pointVolume[k] = -FLT_MAX;
 		m_processedPointCnt++;
-		for (size_t i = 0; i < m_pointCloud.size(); i++)
-		{
-			if (m_pointCloud[i].Processed)
-				continue;
-			float removed = 0.0f, added = 0.0f;
-			for (ConvexHullFace* f : m_visibleFaceVec)
-				removed += std::max(0.0f, Volume(*f, m_pointCloud[i]));
-			for (ConvexHullFace* f : m_addedFaceVec)
-				added += std::max(0.0f, Volume(*f, m_pointCloud[i]));
-			m_pointVolume[i] -= removed;
-			m_pointVolume[i] += added;
-		}
+		SurtrHost::detail::parallel_for(n_chunks, [&](size_t c) {
+			for (size_t i = c * CHUNK; i < std::min(m_pointCloud.size(), (c + 1) * CHUNK); i++)
+			{
+				if (m_pointCloud[i].Processed)
+					continue;
+				float removed = 0.0f, added = 0.0f;
+				for (ConvexHullFace* f : m_visibleFaceVec)
+					removed += std::max(0.0f, Volume(*f, m_pointCloud[i]));
+				for (ConvexHullFace* f : m_addedFaceVec)
+					added += std::max(0.0f, Volume(*f, m_pointCloud[i]));
+				m_pointVolume[i] -= removed;
+				m_pointVolume[i] += added;
+			}
+		});
 		CleanUp();
 	}
 }

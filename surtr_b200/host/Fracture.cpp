@@ -79,8 +79,10 @@ static PreparedObject prepare(const std::vector<Vector3>& vertices, const std::v
 {
 	PreparedObject r;
 	// 1-2. intermediate convex hull with limit count -> face normals
+	std::unique_ptr<Phase> ph(new Phase("ICH normals"));
 	const std::vector<Vector3> normals = VMACH::GenerateICHNormal(vertices, args.ICHIncludePointLimit);
 	r.ICHFaceCnt = (int)normals.size();
+	ph.reset(new Phase("bbox + k-DOP + ACH"));
 	// 3. bounding box (doubles holding float values, as the reference)
 	double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
 	for (const Vector3& v : vertices)
@@ -101,6 +103,7 @@ static PreparedObject prepare(const std::vector<Vector3>& vertices, const std::v
 	Poly::Scale(ach, Vector3(2.0, 2.0, 2.0));
 	Poly::Translate(ach, r.BBCenter);
 	r.ACH = achKdop.ClipWithPolyhedron(ach);
+	ph.reset(new Phase("Voronoi cells (DT3D + clip)"));
 	// 8. Voronoi cells for the initial decomposition, placed on the object
 	r.Cells = GenerateVoronoi(seeds);
 	for (VMACH::Polygon3D& voro : r.Cells)
@@ -108,17 +111,20 @@ static PreparedObject prepare(const std::vector<Vector3>& vertices, const std::v
 		voro.Scale(Vector3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]));
 		voro.Translate(r.BBCenter);
 	}
+	ph.reset(new Phase("mesh polyhedron"));
 	// 7. mesh polyhedron
 	if (indices)
 	{
 		const std::vector<std::vector<int>> nei = Poly::ExtractNeighborFromMesh(vertices, *indices);
 		Poly::InitPolyhedron(r.Mesh, vertices, nei);
 	}
+	ph.reset(new Phase("ApplyFracture (initial)"));
 	// 10. initial pieces
 	Compound pre;
 	Piece first_piece(r.ACH, indices ? r.Mesh : r.ACH);
 	pre.PieceVec.push_back(&first_piece);
 	r.Initial = ApplyFracture(pre, r.Cells, indices != nullptr);
+	ph.reset(new Phase("Refitting + SetExtract"));
 	if (indices)
 	{
 		Refitting(r.Initial.PieceVec, args, &r.Initial.PieceMass);
