@@ -140,239 +140,287 @@ __device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int 
     return true;
 }
 
-__device__ bool g_all_inplane_box_says_skip(const GlobalPoly& g, int nv, const float4& pl, int lane)
+// The NW warps that work on one pair: one warp (large tier, workspace in shared memory, several pairs per block) or a
+// whole block of NW warps (unbounded tier, workspace in global memory, one pair per block -- a 2500-vertex mesh is 79
+// strided iterations per phase for one warp, 10 for eight).  All group-wide decisions are uniform, so every thread of
+// the group takes the same branches and meets the same barriers.
+template <int NW>
+struct Grp
 {
-    float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
-    float hi[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
-    for (int v = lane; v < nv; v += 32)
+    static constexpr int N = NW * 32;
+    int tid, lane;
+    int* scratch;   // NW > 1: shared int[NW + 1]
+
+    __device__ __forceinline__ void sync() const
     {
-        lo[0] = fminf(lo[0], g.x[v]); hi[0] = fmaxf(hi[0], g.x[v]);
-        lo[1] = fminf(lo[1], g.y[v]); hi[1] = fmaxf(hi[1], g.y[v]);
-        lo[2] = fminf(lo[2], g.z[v]); hi[2] = fmaxf(hi[2], g.z[v]);
+        if (NW == 1) __syncwarp(); else __syncthreads();
     }
-    for (int o = 16; o > 0; o >>= 1)
-        for (int k = 0; k < 3; k++)
+    __device__ __forceinline__ bool any(bool p) const
+    {
+        if (NW == 1) return __ballot_sync(FULL, p) != 0u;
+        return __syncthreads_or(p ? 1 : 0) != 0;
+    }
+    __device__ __forceinline__ int exscan(int v, int& total) const   // exclusive prefix over the group, thread order
+    {
+        int wt;
+        const int ex = warp_exscan(v, lane, wt);
+        if (NW == 1) { total = wt; return ex; }
+        const int w = tid >> 5;
+        if (lane == 0) scratch[w] = wt;
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < NW; i++)
         {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+            const int t = scratch[i];
+            if (i < w) before += t;
+            tot += t;
         }
-    const int k = lane & 7;
-    const int c = classify(signed_dist(pl, (k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]));
-    return __ballot_sync(FULL, c == -1) == 0u;
+        __syncthreads();
+        total = tot;
+        return before + ex;
+    }
+    __device__ __forceinline__ int bcast0(int v) const   // thread 0's value
+    {
+        if (NW == 1) return __shfl_sync(FULL, v, 0);
+        if (tid == 0) scratch[NW] = v;
+        __syncthreads();
+        const int r = scratch[NW];
+        __syncthreads();
+        return r;
+    }
+};
+
+// Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).  Rare; the first warp does it.
+template <int NW>
+__device__ bool g_all_inplane_box_says_skip(const GlobalPoly& g, int nv, const float4& pl, const Grp<NW>& grp)
+{
+    int skip = 0;
+    if (grp.tid < 32)
+    {
+        const int lane = grp.lane;
+        float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
+        float hi[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
+        for (int v = lane; v < nv; v += 32)
+        {
+            lo[0] = fminf(lo[0], g.x[v]); hi[0] = fmaxf(hi[0], g.x[v]);
+            lo[1] = fminf(lo[1], g.y[v]); hi[1] = fmaxf(hi[1], g.y[v]);
+            lo[2] = fminf(lo[2], g.z[v]); hi[2] = fmaxf(hi[2], g.z[v]);
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            for (int k = 0; k < 3; k++)
+            {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+            }
+        const int k = lane & 7;
+        const int c = classify(signed_dist(pl, (k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2]));
+        skip = __ballot_sync(FULL, c == -1) == 0u ? 1 : 0;
+    }
+    return grp.bcast0(skip) != 0;
 }
 
-// Clip the polyhedron in the workspace (nv vertices) by planes[0..npl).  All 32 lanes call this together.
-__device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts)
+// Clip the polyhedron in the workspace (nv vertices) by planes[0..npl).  All threads of the group call this together.
+template <int NW>
+__device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __restrict__ planes, int npl, const Grp<NW>& grp, unsigned& seq_cuts)
 {
-    const unsigned lt = (1u << lane) - 1u;
-    for (int kb = 0; kb < npl && nv > 0; kb += 32)
+    constexpr int N = Grp<NW>::N;
+    const int tid = grp.tid;
+    for (int kp = 0; kp < npl && nv > 0; kp++)
     {
-        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kb + lane < npl) mine = __ldg(planes + kb + lane);
-        const int kend = min(32, npl - kb);
-        for (int kk = 0; kk < kend && nv > 0; kk++)
-        {
-            float4 pl;
-            pl.x = __shfl_sync(FULL, mine.x, kk);
-            pl.y = __shfl_sync(FULL, mine.y, kk);
-            pl.z = __shfl_sync(FULL, mine.z, kk);
-            pl.w = __shfl_sync(FULL, mine.w, kk);
+        const float4 pl = __ldg(planes + kp);
 
-            // classify (Poly.cpp:303-319)
-            bool any_clip = false, any_keep = false, any_zero = false;
-            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+        // classify (Poly.cpp:303-319)
+        bool t_clip = false, t_keep = false, t_zero = false;
+        // (unrolled a little: the iterations are independent loads -- memory-level parallelism)
 #pragma unroll 4
-            for (int base = 0; base < nv; base += 32)
-            {
-                const int v = base + lane;
-                int c = 3;
-                if (v < nv)
-                {
-                    c = classify(signed_dist(pl, g.x[v], g.y[v], g.z[v]));
-                    g.comp[v] = (int8_t)c;
-                }
-                any_clip |= __ballot_sync(FULL, c == -1) != 0u;
-                any_keep |= __ballot_sync(FULL, c == 1) != 0u;
-                any_zero |= __ballot_sync(FULL, c == 0) != 0u;
-            }
-            if (!any_keep)
-            {
-                if (!any_clip && g_all_inplane_box_says_skip(g, nv, pl, lane)) continue;
-                nv = 0;
-                break;
-            }
-            if (!any_clip) continue;
-            __syncwarp();
+        for (int v = tid; v < nv; v += N)
+        {
+            const int c = classify(signed_dist(pl, g.x[v], g.y[v], g.z[v]));
+            g.comp[v] = (int8_t)c;
+            t_clip |= c == -1;
+            t_keep |= c == 1;
+            t_zero |= c == 0;
+        }
+        const bool any_keep = grp.any(t_keep);
+        const bool any_clip = grp.any(t_clip);
+        const bool any_zero = grp.any(t_zero);
+        if (!any_keep)
+        {
+            if (!any_clip && g_all_inplane_box_says_skip<NW>(g, nv, pl, grp)) continue;
+            nv = 0;
+            break;
+        }
+        if (!any_clip) continue;
 
-            // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
-            const int nverts0 = nv;
-            int nnew = 0;
-            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
+        // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
+        const int nverts0 = nv;
+        int nnew = 0;
 #pragma unroll 2
-            for (int base = 0; base < nverts0; base += 32)
+        for (int base = 0; base < nverts0; base += N)
+        {
+            const int v = base + tid;
+            int cnt = 0;
+            unsigned smask = 0u;
+            if (v < nverts0 && g.comp[v] == -1)
             {
-                const int v = base + lane;
-                int cnt = 0;
-                unsigned smask = 0u;
-                if (v < nverts0 && g.comp[v] == -1)
-                {
-                    const int d = g.deg[v];
-                    for (int j = 0; j < d; j++)
-                        if (g.comp[g.ring[(size_t)v * GD + j]] > 0) { cnt++; smask |= 1u << j; }
-                }
-                int tot;
-                int w = nnew + warp_exscan(cnt, lane, tot);
-                if (nverts0 + nnew + tot > g.cap) return CLIP_OVERFLOW;
-                while (smask) { const int j = __ffs(smask) - 1; smask &= smask - 1; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
-                nnew += tot;
+                const int d = g.deg[v];
+                for (int j = 0; j < d; j++)
+                    if (g.comp[g.ring[(size_t)v * GD + j]] > 0) { cnt++; smask |= 1u << j; }
             }
-            const int nverts = nverts0 + nnew;
-            __syncwarp();
-            // insert (Poly.cpp:345-354): one new vertex per lane and iteration
-            for (int t = lane; t < nnew; t += 32)
-            {
-                const uint32_t e = g.list[t];
-                const int v = (int)(e & 0xffffu), j = (int)(e >> 16), w = nverts0 + t;
-                const int jn = g.ring[(size_t)v * GD + j];
-                const float ax = g.x[v], ay = g.y[v], az = g.z[v], bx = g.x[jn], by = g.y[jn], bz = g.z[jn];
-                const float sa = signed_dist(pl, ax, ay, az), sb = signed_dist(pl, bx, by, bz);
-                float ox, oy, oz;
-                plane_line_intersection(ax, ay, az, sa, bx, by, bz, sb, ox, oy, oz);
-                g.x[w] = ox; g.y[w] = oy; g.z[w] = oz;
-                g.comp[w] = 2;
-                g.deg[w] = 2;
-                g.ring[(size_t)w * GD] = (uint16_t)v;
-                g.ring[(size_t)w * GD + 1] = (uint16_t)jn;
-                // several lanes may patch the ring of the same kept vertex jn at once: each replaces only the entry holding
-                // ITS clipped vertex v, and an entry another lane is rewriting (v' -> w') equals v neither before nor after
-                // -- entry-disjoint by construction (compute-sanitizer racecheck warns at word level, profiles/r1_sanitizer.txt)
-                uint16_t* rj = g.ring + (size_t)jn * GD;
-                const int dj = g.deg[jn];
-                int k = 0;
-                while (k < dj && rj[k] != (uint16_t)v) k++;
-                if (k < dj) rj[k] = (uint16_t)w;
-                g.ring[(size_t)v * GD + j] = (uint16_t)w;
-            }
-            __syncwarp();
+            int tot;
+            int w = nnew + grp.exscan(cnt, tot);
+            if (nverts0 + nnew + tot > g.cap) return CLIP_OVERFLOW;
+            while (smask) { const int j = __ffs(smask) - 1; smask &= smask - 1; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
+            nnew += tot;
+        }
+        const int nverts = nverts0 + nnew;
+        grp.sync();
+        // insert (Poly.cpp:345-354): one new vertex per thread and iteration
+        for (int t = tid; t < nnew; t += N)
+        {
+            const uint32_t e = g.list[t];
+            const int v = (int)(e & 0xffffu), j = (int)(e >> 16), w = nverts0 + t;
+            const int jn = g.ring[(size_t)v * GD + j];
+            const float ax = g.x[v], ay = g.y[v], az = g.z[v], bx = g.x[jn], by = g.y[jn], bz = g.z[jn];
+            const float sa = signed_dist(pl, ax, ay, az), sb = signed_dist(pl, bx, by, bz);
+            float ox, oy, oz;
+            plane_line_intersection(ax, ay, az, sa, bx, by, bz, sb, ox, oy, oz);
+            g.x[w] = ox; g.y[w] = oy; g.z[w] = oz;
+            g.comp[w] = 2;
+            g.deg[w] = 2;
+            g.ring[(size_t)w * GD] = (uint16_t)v;
+            g.ring[(size_t)w * GD + 1] = (uint16_t)jn;
+            // several threads may patch the ring of the same kept vertex jn at once: each replaces only the entry holding
+            // ITS clipped vertex v, and an entry another thread is rewriting (v' -> w') equals v neither before nor after
+            // -- entry-disjoint by construction (compute-sanitizer racecheck warns at word level, profiles/r1_sanitizer.txt)
+            uint16_t* rj = g.ring + (size_t)jn * GD;
+            const int dj = g.deg[jn];
+            int k = 0;
+            while (k < dj && rj[k] != (uint16_t)v) k++;
+            if (k < dj) rj[k] = (uint16_t)w;
+            g.ring[(size_t)v * GD + j] = (uint16_t)w;
+        }
+        grp.sync();
 
-            // patch (Poly.cpp:365-431)
-            bool need_seq = any_zero;
+        // patch (Poly.cpp:365-431)
+        bool need_seq = any_zero;
+        if (!need_seq)
+        {
+            bool ok = true;
+            for (int t = tid; t < nnew; t += N)
+            {
+                const int w = nverts0 + t;
+                int iprev = w, inext = g.ring[(size_t)w * GD], itmp, k = 0;
+                while (g.comp[inext] == -1 && k++ < nverts)
+                {
+                    itmp = inext;
+                    inext = g_face_loop(g, inext, iprev);
+                    iprev = itmp;
+                }
+                const bool okt = g.comp[inext] == 2 && inext != w;
+                if (okt) g.id[inext] = (uint16_t)w;
+                g.list[t] = (uint32_t)inext;
+                ok = ok && okt;
+            }
+            grp.sync();
+            for (int t = tid; t < nnew; t += N)
+                if (ok) ok = g.id[g.list[t]] == (uint16_t)(nverts0 + t);
+            need_seq = grp.any(!ok);
             if (!need_seq)
             {
-                bool ok = true;
-                for (int t = lane; t < nnew; t += 32)
+                for (int t = tid; t < nnew; t += N)   // ring(w) = [pusher, walked, kept]
                 {
                     const int w = nverts0 + t;
-                    int iprev = w, inext = g.ring[(size_t)w * GD], itmp, k = 0;
-                    while (g.comp[inext] == -1 && k++ < nverts)
-                    {
-                        itmp = inext;
-                        inext = g_face_loop(g, inext, iprev);
-                        iprev = itmp;
-                    }
-                    const bool okt = g.comp[inext] == 2 && inext != w;
-                    if (okt) g.id[inext] = (uint16_t)w;
-                    g.list[t] = (uint32_t)inext;
-                    ok = ok && okt;
-                }
-                __syncwarp();
-                for (int t = lane; t < nnew; t += 32)
-                    if (ok) ok = g.id[g.list[t]] == (uint16_t)(nverts0 + t);
-                need_seq = __ballot_sync(FULL, !ok) != 0u;
-                if (!need_seq)
-                {
-                    for (int t = lane; t < nnew; t += 32)   // ring(w) = [pusher, walked, kept]
-                    {
-                        const int w = nverts0 + t;
-                        const uint16_t kept = g.ring[(size_t)w * GD + 1];
-                        g.ring[(size_t)w * GD] = g.id[w];
-                        g.ring[(size_t)w * GD + 1] = (uint16_t)g.list[t];
-                        g.ring[(size_t)w * GD + 2] = kept;
-                        g.deg[w] = 3;
-                    }
+                    const uint16_t kept = g.ring[(size_t)w * GD + 1];
+                    g.ring[(size_t)w * GD] = g.id[w];
+                    g.ring[(size_t)w * GD + 1] = (uint16_t)g.list[t];
+                    g.ring[(size_t)w * GD + 2] = kept;
+                    g.deg[w] = 3;
                 }
             }
-            if (need_seq)
-            {
-                seq_cuts++;
-                for (int v = lane; v < nverts; v += 32)
-                {
-                    const int d = g.deg[v];
-                    g.old_deg[v] = (uint8_t)d;
-                    for (int j = 0; j < d; j++) g.old_ring[(size_t)v * GD + j] = g.ring[(size_t)v * GD + j];
-                }
-                __syncwarp();
-                int okflag = 1;
-                if (lane == 0) okflag = g_seq_patch_splice(g, nverts0, nverts) ? 1 : 0;
-                okflag = __shfl_sync(FULL, okflag, 0);
-                if (!okflag) return CLIP_OVERFLOW;
-            }
-            __syncwarp();
-
-            // compaction (Poly.cpp:464-499)
-            int kept_before = 0;
-            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
-#pragma unroll 4
-            for (int base = 0; base < nverts; base += 32)
-            {
-                const int v = base + lane;
-                const bool live = v < nverts && g.comp[v] >= 0;
-                const unsigned m = __ballot_sync(FULL, live);
-                if (v < nverts) g.id[v] = live ? (uint16_t)(kept_before + __popc(m & lt)) : G_NONE;
-                kept_before += __popc(m);
-            }
-            __syncwarp();
-            bool dangling = false;   // a live ring pointing at an erased vertex: not a polyhedron (the reference would store -1)
-            // (unrolled a little: the iterations are independent loads -- memory-level parallelism for the one warp)
-#pragma unroll 2
-            for (int base = 0; base < nverts; base += 32)
-            {
-                const int v = base + lane;
-                const bool live = v < nverts && g.comp[v] >= 0;
-                float vx = 0.f, vy = 0.f, vz = 0.f;
-                uint16_t r[GD];
-                int d = 0, t = 0;
-                if (live)
-                {
-                    vx = g.x[v]; vy = g.y[v]; vz = g.z[v];
-                    d = g.deg[v];
-                    t = g.id[v];
-#pragma unroll
-                    for (int j = 0; j < GD; j++)
-                        if (j < d)
-                        {
-                            r[j] = g.id[g.ring[(size_t)v * GD + j]];
-                            dangling |= r[j] == G_NONE;
-                        }
-                }
-                __syncwarp();
-                if (live)
-                {
-                    g.x[t] = vx; g.y[t] = vy; g.z[t] = vz;
-                    g.deg[t] = (uint8_t)d;
-#pragma unroll
-                    for (int j = 0; j < GD; j++)
-                        if (j < d) g.ring[(size_t)t * GD + j] = r[j];
-                }
-                __syncwarp();
-            }
-            if (__ballot_sync(FULL, dangling) != 0u) return CLIP_OVERFLOW;   // keeps every later index inside the workspace
-            nv = kept_before < 4 ? 0 : kept_before;   // Poly.cpp:498-499
         }
+        if (need_seq)
+        {
+            if (tid == 0) seq_cuts++;
+            for (int v = tid; v < nverts; v += N)
+            {
+                const int d = g.deg[v];
+                g.old_deg[v] = (uint8_t)d;
+                for (int j = 0; j < d; j++) g.old_ring[(size_t)v * GD + j] = g.ring[(size_t)v * GD + j];
+            }
+            grp.sync();
+            int okflag = 1;
+            if (tid == 0) okflag = g_seq_patch_splice(g, nverts0, nverts) ? 1 : 0;
+            okflag = grp.bcast0(okflag);
+            if (!okflag) return CLIP_OVERFLOW;
+        }
+        grp.sync();
+
+        // compaction (Poly.cpp:464-499)
+        int kept_before = 0;
+#pragma unroll 2
+        for (int base = 0; base < nverts; base += N)
+        {
+            const int v = base + tid;
+            const bool live = v < nverts && g.comp[v] >= 0;
+            int tot;
+            const int ex = grp.exscan(live ? 1 : 0, tot);
+            if (v < nverts) g.id[v] = live ? (uint16_t)(kept_before + ex) : G_NONE;
+            kept_before += tot;
+        }
+        grp.sync();
+        bool dangling = false;   // a live ring pointing at an erased vertex: not a polyhedron (the reference would store -1)
+        for (int base = 0; base < nverts; base += N)
+        {
+            const int v = base + tid;
+            const bool live = v < nverts && g.comp[v] >= 0;
+            float vx = 0.f, vy = 0.f, vz = 0.f;
+            uint16_t r[GD];
+            int d = 0, t = 0;
+            if (live)
+            {
+                vx = g.x[v]; vy = g.y[v]; vz = g.z[v];
+                d = g.deg[v];
+                t = g.id[v];
+#pragma unroll
+                for (int j = 0; j < GD; j++)
+                    if (j < d)
+                    {
+                        r[j] = g.id[g.ring[(size_t)v * GD + j]];
+                        dangling |= r[j] == G_NONE;
+                    }
+            }
+            grp.sync();
+            if (live)
+            {
+                g.x[t] = vx; g.y[t] = vy; g.z[t] = vz;
+                g.deg[t] = (uint8_t)d;
+#pragma unroll
+                for (int j = 0; j < GD; j++)
+                    if (j < d) g.ring[(size_t)t * GD + j] = r[j];
+            }
+            grp.sync();
+        }
+        if (grp.any(dangling)) return CLIP_OVERFLOW;   // keeps every later index inside the workspace
+        nv = kept_before < 4 ? 0 : kept_before;   // Poly.cpp:498-499
     }
-    __syncwarp();
+    grp.sync();
     return CLIP_OK;
 }
 
-// Face count + moments in the reference's order (Poly.cpp:55-126) on the workspace; see fragment_moments.
-__device__ void global_fragment_moments(GlobalPoly& g, int nv, int lane, Moments& out)
+// Face count + moments in the reference's order (Poly.cpp:55-126) on the workspace; see sub_fragment_moments.
+template <int NW>
+__device__ void global_fragment_moments(GlobalPoly& g, int nv, const Grp<NW>& grp, Moments& out, float* fscratch)
 {
+    constexpr int N = Grp<NW>::N;
+    const int tid = grp.tid, lane = grp.lane;
     const float ox = g.x[0], oy = g.y[0], oz = g.z[0];
     int n_faces = 0, n_tri = 0;
     // pass 1: face starts (bit mask per vertex in g.id) and the first triangle slot of every vertex (g.list)
-    for (int base = 0; base < nv; base += 32)
+    for (int base = 0; base < nv; base += N)
     {
-        const int v = base + lane;
+        const int v = base + tid;
         int cnt = 0, faces = 0;
         unsigned mask = 0u;
         if (v < nv)
@@ -397,16 +445,16 @@ __device__ void global_fragment_moments(GlobalPoly& g, int nv, int lane, Moments
             g.id[v] = (uint16_t)mask;
         }
         int tot, ftot;
-        const int ex = warp_exscan(cnt, lane, tot);
-        warp_exscan(faces, lane, ftot);
+        const int ex = grp.exscan(cnt, tot);
+        grp.exscan(faces, ftot);
         if (v < nv) g.list[v] = (uint32_t)(n_tri + ex);
         n_tri += tot;
         n_faces += ftot;
     }
     n_tri = min(n_tri, 2 * g.cap);
-    __syncwarp();
+    grp.sync();
     float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-    for (int v = lane; v < nv; v += 32)
+    for (int v = tid; v < nv; v += N)
     {
         unsigned m = g.id[v];
         if (!m) continue;
@@ -447,12 +495,13 @@ __device__ void global_fragment_moments(GlobalPoly& g, int nv, int lane, Moments
             }
         }
     }
-    __syncwarp();
+    grp.sync();
+    // ordered accumulation (Poly.cpp:77-85) by the first four lanes of the group, fixed-shape reduction of the rest
     double zeroth = 0.0;
     float fsum = 0.f;
-    if (lane < 4)
+    if (tid < 4)
     {
-        const float* comp = reinterpret_cast<const float*>(g.tri) + lane;
+        const float* comp = reinterpret_cast<const float*>(g.tri) + tid;
         for (int t = 0; t < n_tri; t++)
         {
             const float r = comp[4 * (size_t)t];
@@ -460,32 +509,50 @@ __device__ void global_fragment_moments(GlobalPoly& g, int nv, int lane, Moments
             fsum = __fadd_rn(fsum, r);
         }
     }
-    zeroth = __shfl_sync(FULL, zeroth, 0) / 6.0;
-    float fx = __shfl_sync(FULL, fsum, 1), fy = __shfl_sync(FULL, fsum, 2), fz = __shfl_sync(FULL, fsum, 3);
-    {
-        const double q = 24.0 * zeroth;
-        const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));
-        const float sc = (float)inv;
-        fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); fz = __fmul_rn(fz, sc);
-    }
 #pragma unroll
     for (int k = 0; k < 10; k++)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             cov[k] += __shfl_xor_sync(FULL, cov[k], o);
-    out.n_faces = n_faces;
-    out.volume = zeroth;
-    out.cx = __fadd_rn(fx, ox); out.cy = __fadd_rn(fy, oy); out.cz = __fadd_rn(fz, oz);
-    const float V = cov[6] * (1.f / 6.f);
-    const float iv = V != 0.f ? 1.f / (24.f * V) : 0.f;
-    const float c0 = cov[7] * iv, c1 = cov[8] * iv, c2 = cov[9] * iv;
-    const float k120 = 1.f / 120.f;
-    const float Cxx = cov[0] * k120 - V * c0 * c0, Cyy = cov[1] * k120 - V * c1 * c1, Czz = cov[2] * k120 - V * c2 * c2;
-    out.inertia[0] = Cyy + Czz;
-    out.inertia[1] = Cxx + Czz;
-    out.inertia[2] = Cxx + Cyy;
-    out.inertia[3] = -(cov[3] * k120 - V * c0 * c1);
-    out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
-    out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
+    if (NW > 1)
+    {
+        // warp partials -> shared memory -> summed in warp order by every thread (same value everywhere, deterministic)
+        if (lane == 0)
+            for (int k = 0; k < 10; k++) fscratch[(tid >> 5) * 10 + k] = cov[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 10; k++)
+        {
+            float sum = 0.f;
+            for (int w = 0; w < NW; w++) sum += fscratch[w * 10 + k];
+            cov[k] = sum;
+        }
+        __syncthreads();
+    }
+    if (tid < 32)
+    {
+        zeroth = __shfl_sync(FULL, zeroth, 0) / 6.0;
+        float fx = __shfl_sync(FULL, fsum, 1), fy = __shfl_sync(FULL, fsum, 2), fz = __shfl_sync(FULL, fsum, 3);
+        {
+            const double q = 24.0 * zeroth;
+            const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));
+            const float sc = (float)inv;
+            fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); fz = __fmul_rn(fz, sc);
+        }
+        out.n_faces = n_faces;
+        out.volume = zeroth;
+        out.cx = __fadd_rn(fx, ox); out.cy = __fadd_rn(fy, oy); out.cz = __fadd_rn(fz, oz);
+        const float V = cov[6] * (1.f / 6.f);
+        const float iv = V != 0.f ? 1.f / (24.f * V) : 0.f;
+        const float c0 = cov[7] * iv, c1 = cov[8] * iv, c2 = cov[9] * iv;
+        const float k120 = 1.f / 120.f;
+        const float Cxx = cov[0] * k120 - V * c0 * c0, Cyy = cov[1] * k120 - V * c1 * c1, Czz = cov[2] * k120 - V * c2 * c2;
+        out.inertia[0] = Cyy + Czz;
+        out.inertia[1] = Cxx + Czz;
+        out.inertia[2] = Cxx + Cyy;
+        out.inertia[3] = -(cov[3] * k120 - V * c0 * c1);
+        out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
+        out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
+    }
 }
 } // namespace surtr

@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned long long n_items = a.ctl->n_ovf;
     GlobalPoly g = global_poly_carve(smem_raw + (size_t)(threadIdx.x >> 5) * t2_ws_bytes(), T2_CAP);
+    const Grp<1> grp{ lane, lane, nullptr };
     unsigned seq_cuts = 0;
     for (unsigned long long it = gw; it < n_items; it += nwarps)
     {
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-            status = global_clip_by_planes(g, nv, a.c_planes + pl0, npl, lane, seq_cuts);
+            status = global_clip_by_planes<1>(g, nv, a.c_planes + pl0, npl, grp, seq_cuts);
         }
         CandRec* rec = a.rec + q;
         if (status != CLIP_OK)
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
         }
         const bool small = nv <= 64 && maxd <= 8;
         Moments mo;
-        if (!small) global_fragment_moments(g, nv, lane, mo);
+        if (!small) global_fragment_moments<1>(g, nv, grp, mo, nullptr);
         const bool room = small || it < a.cap_tier2;
         const unsigned long long blob = small ? (unsigned long long)q * FAST_BLOB_BYTES : it * a.slot_bytes;
         unsigned char* b = (small ? a.scratch1 : a.scratch) + blob;
@@ -507,20 +508,23 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
 }
 
 // K3, unbounded tier: persistent warps over the pairs the on-chip tiers handed on (clip_global.cuh).
-constexpr int T3_WARPS = 4;
+constexpr int T3_WARPS = 8;            // warps per pair (= per block) in the unbounded tier
+constexpr int T3_BLOCKS_PER_SM = 2;    // persistent blocks, one workspace each
 __host__ __device__ constexpr size_t blob3_bytes(size_t cap) { return cap * (16 + 4 + GD * 2); }   // float4 verts | u32 ring_start | u16 ring
 
 __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int N = T3_WARPS * 32;
+    __shared__ int s_scan[T3_WARPS + 1];
+    __shared__ float s_cov[T3_WARPS * 10];
+    const int tid = threadIdx.x;
+    const Grp<T3_WARPS> grp{ tid, tid & 31, s_scan };
     const unsigned long long n_items = a.ctl->n_ovf3;
-    GlobalPoly g = global_poly_carve(a.ws3 + (size_t)gw * a.ws3_stride, a.cap3);
+    GlobalPoly g = global_poly_carve(a.ws3 + (size_t)blockIdx.x * a.ws3_stride, a.cap3);
     unsigned seq_cuts = 0;
-    for (unsigned long long it = gw; it < n_items; it += nwarps)
+    for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
     {
         const uint32_t q = a.ovf3_list[it];
         const uint2 pr = a.cand[q];
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
         bool bad = nv > g.cap;
         if (!bad)
         {
-            for (int v = lane; v < nv; v += 32)
+            for (int v = tid; v < nv; v += N)
             {
                 const float4 p = __ldg(a.p_verts + v0 + v);
                 g.x[v] = p.x; g.y[v] = p.y; g.z[v] = p.z;
@@ -548,47 +552,47 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
                 }
             }
         }
-        bad = __ballot_sync(FULL, bad) != 0u;
-        __syncwarp();
+        bad = grp.any(bad);
+        grp.sync();
         int status = CLIP_OVERFLOW;
         if (!bad)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-            status = global_clip_by_planes(g, nv, a.c_planes + pl0, npl, lane, seq_cuts);
+            status = global_clip_by_planes<T3_WARPS>(g, nv, a.c_planes + pl0, npl, grp, seq_cuts);
         }
         CandRec* rec = a.rec + q;
         const bool room = it < a.cap_tier3;
         if (status != CLIP_OK || !room)
         {
-            if (lane == 0)
+            if (tid == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
                 if (status != CLIP_OK) atomicAdd(&a.ctl->n_fail, 1u);   // !room alone: the host grows the slots and re-runs
             }
-            __syncwarp();
+            grp.sync();
             continue;
         }
         if (nv == 0)
         {
-            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 3; }
-            __syncwarp();
+            if (tid == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 3; }
+            grp.sync();
             continue;
         }
         Moments mo;
-        global_fragment_moments(g, nv, lane, mo);
+        global_fragment_moments<T3_WARPS>(g, nv, grp, mo, s_cov);
         const unsigned long long blob = it * a.slot_bytes;
         unsigned char* b = a.scratch + blob;
         float4* bv = reinterpret_cast<float4*>(b);
         uint32_t* bo = reinterpret_cast<uint32_t*>(b + (size_t)g.cap * 16);
         uint16_t* br = reinterpret_cast<uint16_t*>(b + (size_t)g.cap * 20);
         int ne = 0;
-        for (int base = 0; base < nv; base += 32)
+        for (int base = 0; base < nv; base += N)
         {
-            const int v = base + lane;
+            const int v = base + tid;
             const int d = v < nv ? g.deg[v] : 0;
             int tot;
-            const int off = ne + warp_exscan(d, lane, tot);
+            const int off = ne + grp.exscan(d, tot);
             ne += tot;
             if (v < nv)
             {
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
                 for (int j = 0; j < d; j++) br[off + j] = g.ring[(size_t)v * GD + j];
             }
         }
-        if (lane == 0)
+        if (tid == 0)
         {
             rec->nv = (uint32_t)nv;
             rec->ne = (uint32_t)ne;
@@ -609,9 +613,9 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
             for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
             rec->blob = blob;
         }
-        __syncwarp();
+        grp.sync();
     }
-    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+    if (seq_cuts && tid == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
 }
 
 // K3, small tier: L lanes per candidate pair (clip_sub.cuh), one pair per sub-warp, no persistent loop (the

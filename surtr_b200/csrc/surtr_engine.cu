@@ -222,7 +222,7 @@ int ensure_capacity(surtr_ctx* ctx)
         ctx->cap3 = std::max<int>(ctx->cap3, (int)want);
         ctx->cap_tier3 = std::max<uint64_t>(ctx->cap_tier3, 8);
         const size_t stride = (global_poly_bytes((size_t)ctx->cap3) + 255) / 256 * 256;
-        CK(ctx->ws3.reserve(stride * (size_t)ctx->num_sm * T3_WARPS));
+        CK(ctx->ws3.reserve(stride * (size_t)ctx->num_sm * T3_BLOCKS_PER_SM));
         CK(ctx->scratch3.reserve(blob3_bytes((size_t)ctx->cap3) * ctx->cap_tier3));
     }
     // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
@@ -347,7 +347,7 @@ int launch_event(surtr_ctx* ctx)
     {
         ca.scratch = ctx->scratch3.as<unsigned char>();
         ca.slot_bytes = blob3_bytes((size_t)ctx->cap3);
-        launch_pdl(clip_global_kernel, dim3(ctx->num_sm), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
+        launch_pdl(clip_global_kernel, dim3(ctx->num_sm * T3_BLOCKS_PER_SM), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
