@@ -1,4 +1,4 @@
-// clip_global.cuh -- the large and the unbounded tier of K3: one warp per pair, polyhedron in a per-warp workspace.
+// clip_global.cuh -- the large and the unbounded tier of K3: one warp or one block per pair, polyhedron in a workspace.
 //
 // Algorithm and exactness argument: see clip_warp.cuh and DESIGN.md section 5.  Written with strided (rolled) loops
 // over arrays in memory instead of per-lane register arrays, so the vertex count is bounded only by the workspace
