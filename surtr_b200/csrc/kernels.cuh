@@ -364,12 +364,13 @@ struct ClipArgs
     uint32_t* dbg;                // optional: 8 words per candidate (cycles per phase, cut counts); NULL = off
 };
 
-// K3, large on-chip tier: pieces / intermediate results of up to 256 vertex slots and ring degree 16, one warp per pair,
-// persistent warps over the pairs the small tier handed on.  Same rolled code as the unbounded tier (clip_global.cuh)
-// with the per-warp workspace in shared memory: the unrolled register-array version this replaces was 179 KB of
+// K3, large on-chip tier: pieces / intermediate results of up to 256 vertex slots and ring degree 16, one block of
+// T2_WARPS warps per pair, persistent blocks over the pairs the small tier handed on.  Same rolled code as the unbounded tier (clip_global.cuh)
+// with the pair's workspace in shared memory: the unrolled register-array version this replaces was 179 KB of
 // SASS and spent 16 stalled cycles per issued instruction on instruction fetch (profiles/README.md).
 constexpr int T2_CAP = 256;
-constexpr int T2_WARPS = 2;
+constexpr int T2_WARPS = 4;            // warps per pair (= per block) in the large tier
+constexpr int T2_BLOCKS_PER_SM = 4;
 __host__ __device__ constexpr size_t blob2_bytes() { return (size_t)T2_CAP * (16 + 2 + GD * 2); }   // float4 verts | u16 ring_start | u16 ring
 __host__ __device__ constexpr size_t t2_ws_bytes() { return (global_poly_bytes(T2_CAP) + 15) / 16 * 16; }
 
@@ -378,14 +379,15 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int N = T2_WARPS * 32;
+    __shared__ int s_scan[T2_WARPS + 1];
+    __shared__ float s_cov[T2_WARPS * 10];
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const unsigned long long n_items = a.ctl->n_ovf;
-    GlobalPoly g = global_poly_carve(smem_raw + (size_t)(threadIdx.x >> 5) * t2_ws_bytes(), T2_CAP);
-    const Grp<1> grp{ lane, lane, nullptr };
+    GlobalPoly g = global_poly_carve(smem_raw, T2_CAP);   // one pair per block: the block's T2_WARPS warps share the workspace
+    const Grp<T2_WARPS> grp{ tid, lane, s_scan };
     unsigned seq_cuts = 0;
-    for (unsigned long long it = gw; it < n_items; it += nwarps)
+    for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
     {
         const uint32_t q = a.ovf_list[it];
         const uint2 pr = a.cand[q];
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
         bool too_big = nv > T2_CAP, malformed = false;
         if (!too_big)
         {
-            for (int v = lane; v < nv; v += 32)
+            for (int v = tid; v < nv; v += N)
             {
                 const float4 p = __ldg(a.p_verts + v0 + v);
                 g.x[v] = p.x; g.y[v] = p.y; g.z[v] = p.z;
@@ -414,52 +416,49 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
                 }
             }
         }
-        malformed = __ballot_sync(FULL, malformed) != 0u;
-        too_big = __ballot_sync(FULL, too_big) != 0u;
-        __syncwarp();
+        malformed = grp.any(malformed);
+        too_big = grp.any(too_big);
+        grp.sync();
         int status = CLIP_OVERFLOW;
         if (!too_big && !malformed)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
-            status = global_clip_by_planes<1>(g, nv, a.c_planes + pl0, npl, grp, seq_cuts);
+            status = global_clip_by_planes<T2_WARPS>(g, nv, a.c_planes + pl0, npl, grp, seq_cuts);
         }
         CandRec* rec = a.rec + q;
         if (status != CLIP_OK)
         {
-            if (lane == 0)
+            if (tid == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
                 if (malformed) atomicAdd(&a.ctl->n_fail, 1u);
                 else a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier
             }
-            __syncwarp();
+            grp.sync();
             continue;
         }
         if (nv == 0)
         {
-            if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 2; }
-            __syncwarp();
+            if (tid == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 2; }
+            grp.sync();
             continue;
         }
         // ring entries of the result, and whether it fits the small tier's blob (<= 64 vertices, degree <= 8): then K4's
         // gather computes its face count and moments like for every small fragment
-        int ne = 0, maxd = 0;
-        for (int base = 0; base < nv; base += 32)
+        int ne = 0;
+        bool wide = false;
+        for (int base = 0; base < nv; base += N)
         {
-            const int d = base + lane < nv ? g.deg[base + lane] : 0;
-            maxd = max(maxd, d);
-            ne += d;
+            const int d = base + tid < nv ? g.deg[base + tid] : 0;
+            wide |= d > 8;
+            int tot;
+            grp.exscan(d, tot);
+            ne += tot;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            ne += __shfl_xor_sync(FULL, ne, o);
-            maxd = max(maxd, __shfl_xor_sync(FULL, maxd, o));
-        }
-        const bool small = nv <= 64 && maxd <= 8;
+        const bool small = nv <= 64 && !grp.any(wide);
         Moments mo;
-        if (!small) global_fragment_moments<1>(g, nv, grp, mo, nullptr);
+        if (!small) global_fragment_moments<T2_WARPS>(g, nv, grp, mo, s_cov);
         const bool room = small || it < a.cap_tier2;
         const unsigned long long blob = small ? (unsigned long long)q * FAST_BLOB_BYTES : it * a.slot_bytes;
         unsigned char* b = (small ? a.scratch1 : a.scratch) + blob;
@@ -468,12 +467,12 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
         uint8_t* br8 = b + 64 * 18;
         uint16_t* br16 = reinterpret_cast<uint16_t*>(b + (size_t)T2_CAP * 18);
         int run = 0;
-        for (int base = 0; base < nv; base += 32)
+        for (int base = 0; base < nv; base += N)
         {
-            const int v = base + lane;
+            const int v = base + tid;
             const int d = v < nv ? g.deg[v] : 0;
             int tot;
-            const int off = run + warp_exscan(d, lane, tot);
+            const int off = run + grp.exscan(d, tot);
             run += tot;
             if (v < nv && room)
             {
@@ -485,7 +484,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
                     for (int j = 0; j < d; j++) br16[off + j] = g.ring[(size_t)v * GD + j];
             }
         }
-        if (lane == 0)
+        if (tid == 0)
         {
             rec->nv = room ? (uint32_t)nv : 0u;
             rec->ne = (uint32_t)ne;
@@ -502,9 +501,9 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
             }
             if (!room) atomicAdd(&a.ctl->n_fail, 1u);
         }
-        __syncwarp();
+        grp.sync();
     }
-    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+    if (seq_cuts && tid == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
 }
 
 // K3, unbounded tier: persistent warps over the pairs the on-chip tiers handed on (clip_global.cuh).

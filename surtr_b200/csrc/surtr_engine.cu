@@ -339,8 +339,7 @@ int launch_event(surtr_ctx* ctx)
     {
         ca.scratch = ctx->scratch2.as<unsigned char>();
         ca.slot_bytes = blob2_bytes();
-        const size_t smem = t2_ws_bytes() * T2_WARPS;
-        launch_pdl(clip_shared_kernel, dim3(ctx->num_sm), dim3(T2_WARPS * 32), smem, ctx->stream, ca);
+        launch_pdl(clip_shared_kernel, dim3(ctx->num_sm * T2_BLOCKS_PER_SM), dim3(T2_WARPS * 32), t2_ws_bytes(), ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->tier3_enabled)
@@ -496,7 +495,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
         delete ctx;
         return fail(nullptr, SURTR_ERR_NOMEM, "cudaMallocHost failed");
     }
-    cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(t2_ws_bytes() * T2_WARPS));
+    cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_ws_bytes());
     *out = ctx;
     return SURTR_OK;
 }
