@@ -270,7 +270,7 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             }
             int tot;
             int w = nnew + grp.exscan(cnt, tot);
-            if (nverts0 + nnew + tot > g.cap) return CLIP_OVERFLOW;
+            if (nverts0 + nnew + tot > g.cap) return CLIP_NEED_SLOTS;
             while (smask) { const int j = __ffs(smask) - 1; smask &= smask - 1; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
             nnew += tot;
         }

@@ -39,6 +39,8 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
     unsigned int tile_a, tile_b;
     unsigned int n_seq_cuts;
     unsigned int n_ovf3;        // pairs queued for the global-memory tier
+    unsigned int n_grow3;       // global-tier pairs whose workspace ran out of vertex slots (the host enlarges it and re-runs)
+    unsigned int pad;
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
         }
         bad = grp.any(bad);
         grp.sync();
-        int status = CLIP_OVERFLOW;
+        int status = nv > g.cap ? CLIP_NEED_SLOTS : CLIP_OVERFLOW;
         if (!bad)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
@@ -567,7 +569,9 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
             if (tid == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-                if (status != CLIP_OK) atomicAdd(&a.ctl->n_fail, 1u);   // !room alone: the host grows the slots and re-runs
+                // !room alone: the host grows the result slots and re-runs; out of vertex slots: it grows the workspace
+                if (status == CLIP_NEED_SLOTS) atomicAdd(&a.ctl->n_grow3, 1u);
+                else if (status != CLIP_OK) atomicAdd(&a.ctl->n_fail, 1u);
             }
             grp.sync();
             continue;

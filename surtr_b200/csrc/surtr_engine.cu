@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -218,7 +219,9 @@ int ensure_capacity(surtr_ctx* ctx)
     {
         // workspace: twice the largest piece (a cut adds at most one vertex per straddling edge), at least 4096 slots
         // (a multiple of 16 keeps every array of the workspace and of the result blobs 16-byte aligned)
-        const uint64_t want = std::min<uint64_t>(65520, (std::max<uint64_t>(4096, 2ull * ctx->max_piece_verts + 1024) + 15) / 16 * 16);
+        uint64_t want = std::min<uint64_t>(65520, (std::max<uint64_t>(4096, 2ull * ctx->max_piece_verts + 1024) + 15) / 16 * 16);
+        if (const char* e = std::getenv("SURTR_DEBUG_CAP3"))   // test hook: start with a small workspace to exercise its growth
+            want = std::min<uint64_t>(65520, (std::max<uint64_t>(64, std::strtoull(e, nullptr, 10)) + 15) / 16 * 16);
         ctx->cap3 = std::max<int>(ctx->cap3, (int)want);
         ctx->cap_tier3 = std::max<uint64_t>(ctx->cap_tier3, 8);
         const size_t stride = (global_poly_bytes((size_t)ctx->cap3) + 255) / 256 * 256;
@@ -416,6 +419,11 @@ int resolve_event(surtr_ctx* ctx)
         if (c.n_ovf && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
         if (c.n_ovf3 > ctx->cap_tier3) { ctx->cap_tier3 = (uint64_t)c.n_ovf3 + c.n_ovf3 / 4 + 8; grow = true; }
         if (c.n_ovf3 && !ctx->tier3_enabled) { ctx->tier3_enabled = true; grow = true; }  // re-run with the global tier
+        if (c.n_grow3 && ctx->cap3 < 65520)   // a global-tier workspace ran out of vertex slots: double it (up to the u16 index range)
+        {
+            ctx->cap3 = (int)std::min<uint64_t>(65520, 2ull * (uint64_t)ctx->cap3);
+            grow = true;
+        }
         if (!grow)
         {
             if (c.n_frag > ctx->cap_frag) { ctx->cap_frag = c.n_frag + c.n_frag / 8 + 64; grow = true; }
@@ -424,9 +432,9 @@ int resolve_event(surtr_ctx* ctx)
         }
         if (!grow)
         {
-            if (c.n_fail)
+            if (c.n_fail || c.n_grow3)
                 return fail(ctx, SURTR_ERR_OVERFLOW,
-                            std::to_string(c.n_fail) + " pair(s) cannot be cut: malformed rings, ring degree above 16, or more than " +
+                            std::to_string(c.n_fail + c.n_grow3) + " pair(s) cannot be cut: malformed rings, ring degree above 16, or more than " +
                                 std::to_string(ctx->cap3 ? ctx->cap3 : 65520) + " vertex slots needed");
             ctx->last.n_pairs = ctx->n_pairs;
             ctx->last.n_candidates = c.n_cand;

@@ -426,3 +426,20 @@ def test_async_download_and_contexts_in_flight():
     finally:
         for cx, st, b in pipes:
             cx.close()
+
+
+def test_global_tier_workspace_grows(monkeypatch):
+    """A global-tier workspace that runs out of vertex slots is doubled and the event re-run (never a failed pair): the
+    bunny mesh (2503 vertices) starting from a 1024-slot workspace (test hook SURTR_DEBUG_CAP3)."""
+    from surtr_b200 import FractureContext
+    monkeypatch.setenv("SURTR_DEBUG_CAP3", "1024")
+    d = np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz"))
+    mesh, want = load_polyset(d, "mesh_"), load_polyset(d, "frag_")
+    cx = FractureContext(0)
+    try:
+        cx.upload_pieces(mesh.verts, mesh.vert_off, mesh.ring_off, mesh.ring)
+        cx.upload_cells(d["planes"], d["plane_off"], d["cell_verts"], d["cell_vert_off"])
+        cx.fracture_event()
+        common.assert_fragments_equal(cx.download(), want)
+    finally:
+        cx.close()
