@@ -6,8 +6,9 @@ K4 assembly) over one batch of synthetic input.  Workload at every N: BASELINE.j
 unit-cube VMACH (1 piece) fractured by 4096 Voronoi seeds, one independent event per rank (rank r uses seed
 46354 + r): events shard across GPUs with no data-path collective (weak scaling).
 
-  value   whole-job fragments/s with inputs resident in HBM, timed per step with CUDA events on the launching stream,
-          L2 flushed between steps (flush outside the events), max over ranks;
+  value   whole-job fragments/s with inputs resident in HBM: K events issued over several streams, CUDA events around
+          the whole region on stream 0, max over ranks.  The resident inputs are LARGER THAN THE L2: every step runs on
+          another of N_SETS resident input sets (own inputs, scratch and outputs), so no step finds its data cached;
   e2e     the same metric through the C ABI with HOST buffers: pinned-host -> device upload of the event's pieces
           and cells, the event, and the device -> pinned-host download of every fragment, all inside the timed region;
   roofline  dominant kernel (K3 clip, tier 1): algorithmic bytes / its CUDA-event duration
@@ -34,8 +35,10 @@ sys.path.insert(0, ROOT)
 N_SEEDS = 4096
 BASE_SEED = 46354
 WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fracture event per step per GPU"
-FLUSH_MIB = 160   # L2 flush buffer (B200 L2 = 126 MB), rewritten before every step
-E2E_DEPTH = 6     # events in flight in the end-to-end loop (contexts driven round-robin)
+FLUSH_MIB = 160   # L2 flush buffer (B200 L2 = 126 MB) for the one-event-at-a-time latency loops
+L2_MIB = 126      # B200 L2
+INPUT_X_L2 = 1.3  # the resident input sets of the throughput loops add up to at least this many L2 sizes
+E2E_DEPTH = 6     # events in flight (streams) in the throughput loops
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -175,7 +178,10 @@ def main():
     ap.add_argument("--kdop", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events in flight in the end-to-end loop")
+    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events in flight (streams) in the throughput loops")
+    ap.add_argument("--input-sets", type=int, default=0,
+                    help="resident input sets cycled by the throughput loops (0 = as many as make the inputs exceed 1.3 x L2; "
+                         "a smaller number is for profiler runs only and is reported in config)")
     args = ap.parse_args()
     globals()["E2E_DEPTH"] = max(1, args.e2e_depth)
     args.warmup = max(args.warmup, 3)
@@ -215,14 +221,18 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t
 
-    h_in = {k: pin(v) for k, v in dict(pv=cube_v, pvo=cube_vo, pro=cube_ro, pr=cube_r, planes=cells.planes,
-                                       plane_off=cells.plane_off, cverts=cells.verts, cvo=cells.vert_off).items()}
+    def host_inputs(cs):
+        return {k: pin(v) for k, v in dict(pv=cube_v, pvo=cube_vo, pro=cube_ro, pr=cube_r, planes=cs.planes,
+                                           plane_off=cs.plane_off, cverts=cs.verts, cvo=cs.vert_off).items()}
+
+    h_in = host_inputs(cells)
     h2d_bytes = sum(t.numel() * t.element_size() for t in h_in.values())
 
-    def upload_to(cx):
-        cx.upload_pieces_ptr(h_in["pv"].data_ptr(), h_in["pvo"].data_ptr(), h_in["pro"].data_ptr(), h_in["pr"].data_ptr(), 1)
-        cx.upload_cells_ptr(h_in["planes"].data_ptr(), h_in["plane_off"].data_ptr(), h_in["cverts"].data_ptr(),
-                            h_in["cvo"].data_ptr(), N_SEEDS)
+    def upload_to(cx, hi=None):
+        hi = hi or h_in
+        cx.upload_pieces_ptr(hi["pv"].data_ptr(), hi["pvo"].data_ptr(), hi["pro"].data_ptr(), hi["pr"].data_ptr(), 1)
+        cx.upload_cells_ptr(hi["planes"].data_ptr(), hi["plane_off"].data_ptr(), hi["cverts"].data_ptr(),
+                            hi["cvo"].data_ptr(), N_SEEDS)
 
     upload_to(ctx)
     ctx.fracture_event()
@@ -251,20 +261,38 @@ def main():
     if world > 1:
         dist.barrier()
 
-    # ---- contexts for the throughput loops: E2E_DEPTH events in flight, one context (= one stream) each ----
-    pipes = [(ctx, stream)]
-    for d in range(1, E2E_DEPTH):
-        st = torch.cuda.Stream(device=dev)
-        cx = FractureContext(local, st.cuda_stream)
-        cx.set_kdop_directions(args.kdop)
-        pipes.append((cx, st))
+    # ---- resident input sets for the throughput loops: MORE INPUT THAN THE L2 HOLDS ----
+    # N_SETS contexts, each with its own resident inputs (the pattern with its cells renumbered, so every set is a
+    # different byte stream), scratch and output arrays, bound round-robin to E2E_DEPTH streams.  Step i runs on set
+    # i mod N_SETS: by the time a set comes round again, N_SETS - 1 other sets (inputs alone > 1.3 x L2, plus their
+    # scratch and outputs) have gone through the L2, so nothing of it is cached -- no flush kernel inside the loop.
+    n_sets = int(np.ceil(INPUT_X_L2 * L2_MIB * 1024 * 1024 / h2d_bytes / E2E_DEPTH)) * E2E_DEPTH
+    if args.input_sets > 0:
+        n_sets = args.input_sets
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(1, E2E_DEPTH)]
+    import hashlib
 
-    for cx, st in pipes[1:]:
-        upload_to(cx)
+    class InputSet:
+        pass
+
+    sets = []
+    for j in range(n_sets):
+        s_ = InputSet()
+        s_.st = streams[j % E2E_DEPTH]
+        if j == 0:
+            s_.cx, s_.h_in = ctx, h_in
+        else:
+            s_.cx = FractureContext(local, s_.st.cuda_stream)
+            s_.cx.set_kdop_directions(args.kdop)
+            s_.h_in = host_inputs(synth.roll_cells(cells, j * (N_SEEDS // n_sets)))
+            upload_to(s_.cx, s_.h_in)
         for _ in range(args.warmup):
-            cx.fracture_event()
-        assert int(cx.counts().n_fragments) == n_frag
+            s_.cx.fracture_event()
+        assert int(s_.cx.counts().n_fragments) == n_frag
+        s_.rec_sha = hashlib.sha1(s_.cx.download(geometry=False).rec.tobytes()).hexdigest()
+        sets.append(s_)
     torch.cuda.synchronize()
+    resident_input_mib = n_sets * h2d_bytes / 2 ** 20
 
     # ---- latency: K single events back to back on one stream, device-resident inputs ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -277,11 +305,10 @@ def main():
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
 
-    # ---- timed region: K steps, device-resident inputs, E2E_DEPTH events in flight ----
+    # ---- timed region: K steps, device-resident inputs, E2E_DEPTH streams ----
     # One event does not fill the GPU (4096 warps of K3 = 28 per SM, issue-latency bound), so a job of K independent
-    # events is issued round-robin over the contexts.  Every stream rewrites the flush buffer before each of its steps
-    # (inside the timed region), so no step finds its inputs in L2.  Timed with CUDA events on stream 0: the start
-    # event gates the other streams, the stop event waits for all of them.
+    # events is issued round-robin over the input sets and their streams.  Timed with CUDA events on stream 0: the
+    # start event gates the other streams, the stop event waits for all of them.
     launches = 0
     if world > 1:
         dist.barrier()
@@ -289,23 +316,21 @@ def main():
     t_wall0 = time.perf_counter()
     t0_ev, t1_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0_ev.record(stream)
-    for cx, st in pipes[1:]:
+    for st in streams[1:]:
         st.wait_event(t0_ev)
     for i in range(args.steps):
-        cx, st = pipes[i % E2E_DEPTH]
-        with torch.cuda.stream(st):
-            flush.zero_()
+        cx = sets[i % n_sets].cx
         cx.fracture_event()
         launches += cx.last_event_launches()
-    for cx, st in pipes[1:]:
+    for st in streams[1:]:
         done = torch.cuda.Event()
         done.record(st)
         stream.wait_event(done)
     t1_ev.record(stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
-    for cx, st in pipes:
-        assert int(cx.counts().n_fragments) == n_frag
+    for s_ in sets[:min(n_sets, args.steps)]:
+        assert int(s_.cx.counts().n_fragments) == n_frag
     # dominant-kernel duration for the roofline: single events again with the engine's per-kernel CUDA events on
     # (they sit between the kernels of an event and serialise the programmatic dependent launches, so the
     # loops above run without them)
@@ -327,11 +352,11 @@ def main():
     value = float(frags.item()) / (total_ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, every step ----
-    # A caller that streams events keeps a few of them in flight: E2E_DEPTH contexts (one stream each) are driven
-    # round-robin from this one host thread through the C ABI -- download step i-DEPTH (blocks on that stream only),
-    # then upload + launch step i -- so the PCIe copies of one event overlap the kernels of the others.  Every step
-    # still moves its own inputs host->device and its own fragments device->host, and each stream first rewrites the
-    # flush buffer so that no step finds its working set in L2.
+    # A caller that streams events keeps a few of them in flight: the input sets (one context each, E2E_DEPTH
+    # streams) are driven round-robin from this one host thread through the C ABI -- download step i-DEPTH (blocks
+    # on that event only), then upload + launch step i -- so the PCIe copies of one event overlap the kernels of the
+    # others.  Every step moves its own inputs host->device from its set's pinned buffers and its own fragments
+    # device->host; the device-side arrays it touches belong to a set last used N_SETS steps ago (cold L2).
     c = ctx.counts()
     from surtr_b200 import FRAGMENT_DTYPE
 
@@ -362,24 +387,25 @@ def main():
     assert got.tobytes() == fr0.rec.tobytes(), "e2e result differs from the resident-input result"
 
     # (2) E2E_DEPTH events in flight: the throughput number
-    pipes = [(cx, st, h_out if d == 0 else out_buffers()) for d, (cx, st) in enumerate(pipes)]
+    for j, s_ in enumerate(sets):
+        s_.h_out = h_out if j == 0 else out_buffers()
 
     def pipelined(n_steps):
         for i in range(n_steps + E2E_DEPTH):
-            cx, st, ho = pipes[i % E2E_DEPTH]
             if i >= E2E_DEPTH:
                 # waits for event i-DEPTH (long finished when the depth is enough), then only ENQUEUES its device->host
-                # copies: the next upload + event are ordered behind them on the stream, the host moves on
-                cx.download_into_async(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
+                # copies on that context's copy stream; the host moves on
+                s_ = sets[(i - E2E_DEPTH) % n_sets]
+                ho = s_.h_out
+                s_.cx.download_into_async(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
             if i < n_steps:
-                with torch.cuda.stream(st):
-                    flush.zero_()
-                upload_to(cx)
-                cx.fracture_event()
-        for cx, st, ho in pipes:
-            cx.sync()                       # drain: the last copies have landed in the host buffers
+                s_ = sets[i % n_sets]
+                upload_to(s_.cx, s_.h_in)
+                s_.cx.fracture_event()
+        for s_ in sets:
+            s_.cx.sync()                    # drain: the last copies have landed in the host buffers
 
-    pipelined(2 * E2E_DEPTH)                # warm-up: every context grows its buffers once
+    pipelined(n_sets)                       # warm-up: every context grows its buffers once
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -388,9 +414,9 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     torch.cuda.set_stream(stream)
-    for cx, st, ho in pipes:
-        got = np.frombuffer(ho["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
-        assert got.tobytes() == fr0.rec.tobytes(), "pipelined e2e result differs from the resident-input result"
+    for s_ in sets:
+        got = s_.h_out["rec"].numpy().tobytes()
+        assert hashlib.sha1(got).hexdigest() == s_.rec_sha, "pipelined e2e result differs from the resident-input result"
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -446,7 +472,13 @@ def main():
             "config": {"workload": WORKLOAD, "fragments_per_step_per_gpu": n_frag, "pairs_per_step": int(c0.n_pairs),
                        "candidates_per_step": int(c0.n_candidates), "kdop_directions": args.kdop,
                        "events_in_flight": E2E_DEPTH,
-                       "l2": f"flushed before every step ({FLUSH_MIB} MiB rewritten on the step's own stream, inside the timed region)",
+                       "input_sets": n_sets, "resident_input_mib": round(resident_input_mib, 1),
+                       "l2": (f"PROFILER RUN, NOT a bench value: only {n_sets} input sets ({resident_input_mib:.0f} MiB < L2)"
+                              if resident_input_mib < L2_MIB else
+                              f"inputs larger than L2: {n_sets} resident input sets ({resident_input_mib:.0f} MiB of inputs > "
+                              f"{L2_MIB} MB L2, each with its own scratch and output arrays) cycled step by step, so a set is "
+                              f"revisited only after {n_sets - 1} other events; no flush kernel in the timed region "
+                              f"(the one-event-at-a-time figures flush {FLUSH_MIB} MiB between steps, outside their timers)"),
                        "timing": "CUDA events on stream 0 around the K steps (start gates, stop joins all streams), max over ranks",
                        "parallelism": f"events sharded over {world} GPU(s), no data-path collective"},
             "p50_event_ms": float(np.median(step_ms)),
@@ -457,8 +489,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
                     "events_in_flight": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
                     "timing": "wall clock around K x (upload + event + download) through the C ABI, pinned host buffers, "
-                              f"{E2E_DEPTH} contexts round-robin from one host thread, L2 flush on every stream inside the "
-                              "timed region; single_event_ms = the same with one event at a time (flush outside)"},
+                              f"{n_sets} input sets (own pinned host buffers) over {E2E_DEPTH} streams from one host thread, inputs "
+                              "larger than L2 as in the timed region; single_event_ms = the same with one event at a time "
+                              "(L2 flushed between events, outside the timer)"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
             "clocks": clocks, "roofline": roofline,
             # secondary roofline the north star asks for: algorithmic FP32 work of the whole job against the FFMA rate
@@ -476,8 +509,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    for cx, st, ho in pipes[1:]:
-        cx.close()
+    for s_ in sets[1:]:
+        s_.cx.close()
     ctx.close()
 
 

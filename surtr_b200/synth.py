@@ -155,6 +155,33 @@ def voronoi_cells(ctx, seeds: np.ndarray, nb_off=None, nb_idx=None) -> CellSet:
     return CellSet(fr.verts, fr.vert_off, fr.ring_off, fr.ring, planes, plane_off)
 
 
+def roll_cells(cs: CellSet, r: int) -> CellSet:
+    """The same pattern with its cells renumbered: new cell i = old cell (i + r) mod n (CSR arrays rotated).
+    bench.py uses it to lay out many distinct resident input sets (more input than the L2 holds)."""
+    n = cs.n
+    r %= n
+    if r == 0:
+        return cs
+
+    def rot(data, off):
+        off = off.astype(np.int64)
+        cut = int(off[r])
+        new_off = np.concatenate([off[r:] - cut, off[1:r + 1] + (int(off[-1]) - cut)]).astype(np.uint32)
+        return np.concatenate([data[cut:], data[:cut]]), new_off
+
+    verts, vert_off = rot(cs.verts, cs.vert_off)
+    ro = cs.ring_off.astype(np.int64)
+    lens = np.diff(ro)
+    cutv = int(cs.vert_off[r])
+    ring_len = np.concatenate([lens[cutv:], lens[:cutv]])
+    ring_off = np.concatenate([[0], np.cumsum(ring_len)]).astype(np.uint32)
+    cute = int(ro[cutv])
+    ring = np.concatenate([cs.ring[cute:], cs.ring[:cute]])
+    planes, plane_off = rot(cs.planes, cs.plane_off)
+    return CellSet(np.ascontiguousarray(verts), vert_off, ring_off, np.ascontiguousarray(ring),
+                   np.ascontiguousarray(planes), plane_off)
+
+
 def algorithmic_bytes(pieces_vert_off, pieces_ring_off, plane_off, rec) -> int:
     """compulsory traffic of the clip + assembly per surviving pair:
     16*V_in + 4*E2_in + 16*P_cell + 16*V_out + 4*E2_out + 64."""
