@@ -38,7 +38,8 @@ WORKLOAD = "config2: unit-cube VMACH (1 piece) x 4096 Voronoi cells, one fractur
 FLUSH_MIB = 160   # L2 flush buffer (B200 L2 = 126 MB) for the one-event-at-a-time latency loops
 L2_MIB = 126      # B200 L2
 INPUT_X_L2 = 1.3  # the resident input sets of the throughput loops add up to at least this many L2 sizes
-E2E_DEPTH = 6     # events in flight (streams) in the throughput loops
+E2E_DEPTH = 6     # end-to-end loop: the download of event i is enqueued when event i + E2E_DEPTH is issued
+STREAMS = 12      # streams the input sets are bound to round-robin = independent events the GPU may overlap
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -178,12 +179,14 @@ def main():
     ap.add_argument("--kdop", type=int, default=3)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events in flight (streams) in the throughput loops")
+    ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events between launch and download in the end-to-end loop")
+    ap.add_argument("--streams", type=int, default=STREAMS, help="streams of the throughput loops")
     ap.add_argument("--input-sets", type=int, default=0,
                     help="resident input sets cycled by the throughput loops (0 = as many as make the inputs exceed 1.3 x L2; "
                          "a smaller number is for profiler runs only and is reported in config)")
     args = ap.parse_args()
     globals()["E2E_DEPTH"] = max(1, args.e2e_depth)
+    globals()["STREAMS"] = max(1, args.streams)
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
@@ -263,13 +266,13 @@ def main():
 
     # ---- resident input sets for the throughput loops: MORE INPUT THAN THE L2 HOLDS ----
     # N_SETS contexts, each with its own resident inputs (the pattern with its cells renumbered, so every set is a
-    # different byte stream), scratch and output arrays, bound round-robin to E2E_DEPTH streams.  Step i runs on set
+    # different byte stream), scratch and output arrays, bound round-robin to STREAMS streams.  Step i runs on set
     # i mod N_SETS: by the time a set comes round again, N_SETS - 1 other sets (inputs alone > 1.3 x L2, plus their
     # scratch and outputs) have gone through the L2, so nothing of it is cached -- no flush kernel inside the loop.
-    n_sets = int(np.ceil(INPUT_X_L2 * L2_MIB * 1024 * 1024 / h2d_bytes / E2E_DEPTH)) * E2E_DEPTH
+    n_sets = int(np.ceil(INPUT_X_L2 * L2_MIB * 1024 * 1024 / h2d_bytes / STREAMS)) * STREAMS
     if args.input_sets > 0:
         n_sets = args.input_sets
-    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(1, E2E_DEPTH)]
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(1, STREAMS)]
     import hashlib
 
     class InputSet:
@@ -278,7 +281,7 @@ def main():
     sets = []
     for j in range(n_sets):
         s_ = InputSet()
-        s_.st = streams[j % E2E_DEPTH]
+        s_.st = streams[j % STREAMS]
         if j == 0:
             s_.cx, s_.h_in = ctx, h_in
         else:
@@ -305,7 +308,7 @@ def main():
     torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
 
-    # ---- timed region: K steps, device-resident inputs, E2E_DEPTH streams ----
+    # ---- timed region: K steps, device-resident inputs, STREAMS streams ----
     # One event does not fill the GPU (4096 warps of K3 = 28 per SM, issue-latency bound), so a job of K independent
     # events is issued round-robin over the input sets and their streams.  Timed with CUDA events on stream 0: the
     # start event gates the other streams, the stop event waits for all of them.
@@ -352,7 +355,7 @@ def main():
     value = float(frags.item()) / (total_ms * 1e-3)
 
     # ---- e2e: host buffers in, host buffers out, every step ----
-    # A caller that streams events keeps a few of them in flight: the input sets (one context each, E2E_DEPTH
+    # A caller that streams events keeps a few of them in flight: the input sets (one context each, STREAMS
     # streams) are driven round-robin from this one host thread through the C ABI -- download step i-DEPTH (blocks
     # on that event only), then upload + launch step i -- so the PCIe copies of one event overlap the kernels of the
     # others.  Every step moves its own inputs host->device from its set's pinned buffers and its own fragments
@@ -471,7 +474,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "fragments_per_step_per_gpu": n_frag, "pairs_per_step": int(c0.n_pairs),
                        "candidates_per_step": int(c0.n_candidates), "kdop_directions": args.kdop,
-                       "events_in_flight": E2E_DEPTH,
+                       "streams": STREAMS,
                        "input_sets": n_sets, "resident_input_mib": round(resident_input_mib, 1),
                        "l2": (f"PROFILER RUN, NOT a bench value: only {n_sets} input sets ({resident_input_mib:.0f} MiB < L2)"
                               if resident_input_mib < L2_MIB else
@@ -487,9 +490,10 @@ def main():
             "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
-                    "events_in_flight": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
+                    "streams": STREAMS, "download_lag_events": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
                     "timing": "wall clock around K x (upload + event + download) through the C ABI, pinned host buffers, "
-                              f"{n_sets} input sets (own pinned host buffers) over {E2E_DEPTH} streams from one host thread, inputs "
+                              f"{n_sets} input sets (own pinned host buffers) over {STREAMS} streams from one host thread, the download of "
+                              f"an event enqueued {E2E_DEPTH} events after its launch, inputs "
                               "larger than L2 as in the timed region; single_event_ms = the same with one event at a time "
                               "(L2 flushed between events, outside the timer)"},
             "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
