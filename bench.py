@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events between launch and download in the end-to-end loop")
     ap.add_argument("--streams", type=int, default=STREAMS, help="streams of the throughput loops")
+    ap.add_argument("--wire", default="packed", choices=["packed", "float4"],
+                    help="host<->device format of the end-to-end loop: packed = surtr_upload_*3 + surtr_download_fragments_packed")
     ap.add_argument("--input-sets", type=int, default=0,
                     help="resident input sets cycled by the throughput loops (0 = as many as make the inputs exceed 1.3 x L2; "
                          "a smaller number is for profiler runs only and is reported in config)")
@@ -224,20 +226,32 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t
 
+    PACKED = args.wire == "packed"
+
     def host_inputs(cs):
-        return {k: pin(v) for k, v in dict(pv=cube_v, pvo=cube_vo, pro=cube_ro, pr=cube_r, planes=cs.planes,
-                                           plane_off=cs.plane_off, cverts=cs.verts, cvo=cs.vert_off).items()}
+        """Pinned host buffers of one event in the PCIe wire format of the C ABI (float3 vertex streams when packed)."""
+        nc = 3 if PACKED else 4
+        return {k: pin(v) for k, v in dict(pv=cube_v[:, :nc], pvo=cube_vo, pro=cube_ro, pr=cube_r, planes=cs.planes,
+                                           plane_off=cs.plane_off, cverts=cs.verts[:, :nc], cvo=cs.vert_off).items()}
+
+    def resident_bytes(cs):
+        return sum(a.nbytes for a in (cube_v, cube_vo, cube_ro, cube_r, cs.planes, cs.plane_off, cs.verts, cs.vert_off))
 
     h_in = host_inputs(cells)
     h2d_bytes = sum(t.numel() * t.element_size() for t in h_in.values())
+    set_bytes = resident_bytes(cells)          # float4 streams as they lie in HBM
+
+    def upload_resident(cx, cs):
+        cx.upload_pieces(cube_v, cube_vo, cube_ro, cube_r)
+        cx.upload_cells(cs.planes, cs.plane_off, cs.verts, cs.vert_off)
 
     def upload_to(cx, hi=None):
         hi = hi or h_in
-        cx.upload_pieces_ptr(hi["pv"].data_ptr(), hi["pvo"].data_ptr(), hi["pro"].data_ptr(), hi["pr"].data_ptr(), 1)
-        cx.upload_cells_ptr(hi["planes"].data_ptr(), hi["plane_off"].data_ptr(), hi["cverts"].data_ptr(),
-                            hi["cvo"].data_ptr(), N_SEEDS)
+        up_p, up_c = (cx.upload_pieces3_ptr, cx.upload_cells3_ptr) if PACKED else (cx.upload_pieces_ptr, cx.upload_cells_ptr)
+        up_p(hi["pv"].data_ptr(), hi["pvo"].data_ptr(), hi["pro"].data_ptr(), hi["pr"].data_ptr(), 1)
+        up_c(hi["planes"].data_ptr(), hi["plane_off"].data_ptr(), hi["cverts"].data_ptr(), hi["cvo"].data_ptr(), N_SEEDS)
 
-    upload_to(ctx)
+    upload_resident(ctx, cells)
     ctx.fracture_event()
     c0 = ctx.counts()
     n_frag = int(c0.n_fragments)
@@ -269,7 +283,7 @@ def main():
     # different byte stream), scratch and output arrays, bound round-robin to STREAMS streams.  Step i runs on set
     # i mod N_SETS: by the time a set comes round again, N_SETS - 1 other sets (inputs alone > 1.3 x L2, plus their
     # scratch and outputs) have gone through the L2, so nothing of it is cached -- no flush kernel inside the loop.
-    n_sets = int(np.ceil(INPUT_X_L2 * L2_MIB * 1024 * 1024 / h2d_bytes / STREAMS)) * STREAMS
+    n_sets = int(np.ceil(INPUT_X_L2 * L2_MIB * 1024 * 1024 / set_bytes / STREAMS)) * STREAMS
     if args.input_sets > 0:
         n_sets = args.input_sets
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(1, STREAMS)]
@@ -287,15 +301,16 @@ def main():
         else:
             s_.cx = FractureContext(local, s_.st.cuda_stream)
             s_.cx.set_kdop_directions(args.kdop)
-            s_.h_in = host_inputs(synth.roll_cells(cells, j * (N_SEEDS // n_sets)))
-            upload_to(s_.cx, s_.h_in)
+            rolled = synth.roll_cells(cells, j * (N_SEEDS // n_sets))
+            s_.h_in = host_inputs(rolled)
+            upload_resident(s_.cx, rolled)
         for _ in range(args.warmup):
             s_.cx.fracture_event()
         assert int(s_.cx.counts().n_fragments) == n_frag
         s_.rec_sha = hashlib.sha1(s_.cx.download(geometry=False).rec.tobytes()).hexdigest()
         sets.append(s_)
     torch.cuda.synchronize()
-    resident_input_mib = n_sets * h2d_bytes / 2 ** 20
+    resident_input_mib = n_sets * set_bytes / 2 ** 20
 
     # ---- latency: K single events back to back on one stream, device-resident inputs ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -364,16 +379,18 @@ def main():
     from surtr_b200 import FRAGMENT_DTYPE
 
     def out_buffers():
+        # wire format of the fragments: records, float3 positions, one byte of ring length per vertex, ring entries
         return dict(rec=torch.empty(int(c.n_fragments) * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
-                    verts=torch.empty(int(c.n_verts) * 4, dtype=torch.float32).pin_memory(),
-                    ring_off=torch.empty(int(c.n_verts) + 1, dtype=torch.int32).pin_memory(),
+                    verts=torch.empty(int(c.n_verts) * (3 if PACKED else 4), dtype=torch.float32).pin_memory(),
+                    ring_len=torch.empty(int(c.n_verts) if PACKED else 4 * (int(c.n_verts) + 1), dtype=torch.uint8).pin_memory(),
                     ring=torch.empty(int(c.n_ring), dtype=torch.int16).pin_memory())
 
     h_out = out_buffers()
     d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
 
     def download_from(cx, ho):
-        cx.download_into(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
+        (cx.download_packed_into if PACKED else cx.download_into)(ho["rec"].data_ptr(), ho["verts"].data_ptr(),
+                                                                   ho["ring_len"].data_ptr(), ho["ring"].data_ptr())
 
     # (1) one event at a time: the latency a single synchronous caller sees
     for _ in range(3):
@@ -400,7 +417,8 @@ def main():
                 # copies on that context's copy stream; the host moves on
                 s_ = sets[(i - E2E_DEPTH) % n_sets]
                 ho = s_.h_out
-                s_.cx.download_into_async(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
+                (s_.cx.download_packed_into_async if PACKED else s_.cx.download_into_async)(
+                    ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_len"].data_ptr(), ho["ring"].data_ptr())
             if i < n_steps:
                 s_ = sets[i % n_sets]
                 upload_to(s_.cx, s_.h_in)
@@ -420,6 +438,14 @@ def main():
     for s_ in sets:
         got = s_.h_out["rec"].numpy().tobytes()
         assert hashlib.sha1(got).hexdigest() == s_.rec_sha, "pipelined e2e result differs from the resident-input result"
+    # geometry of the last download of set 0 against the resident-input result of the same set
+    v3 = sets[0].h_out["verts"].numpy().reshape(-1, 3 if PACKED else 4)[:, :3]
+    assert np.ascontiguousarray(v3).tobytes() == np.ascontiguousarray(fr0.verts[:, :3]).tobytes(), "e2e vertex positions differ"
+    if PACKED:
+        assert np.array_equal(sets[0].h_out["ring_len"].numpy(), np.diff(fr0.ring_off).astype(np.uint8)), "e2e ring lengths differ"
+    else:
+        assert sets[0].h_out["ring_len"].numpy().view(np.uint32).tobytes() == fr0.ring_off.tobytes(), "e2e ring offsets differ"
+    assert sets[0].h_out["ring"].numpy().tobytes() == fr0.ring.tobytes(), "e2e ring entries differ"
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -491,6 +517,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps,
                     "streams": STREAMS, "download_lag_events": E2E_DEPTH, "single_event_ms": 1e3 * sync_s / args.steps,
+                    "wire_format": ("surtr_upload_pieces3 / surtr_upload_cells3 (float3 vertex streams, widened to float4 on the "
+                                    "device) and surtr_download_fragments_packed (float3 + one byte of ring length per vertex)")
+                                   if PACKED else "float4 vertex streams and 32-bit ring offsets (the resident layout)",
                     "timing": "wall clock around K x (upload + event + download) through the C ABI, pinned host buffers, "
                               f"{n_sets} input sets (own pinned host buffers) over {STREAMS} streams from one host thread, the download of "
                               f"an event enqueued {E2E_DEPTH} events after its launch, inputs "

@@ -105,6 +105,14 @@ int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* ver
                         const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events);
 int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4,
                        const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events);
+/* PCIe wire format.  The same two calls with tightly packed float3 vertex streams (xyz, 12 bytes per vertex, the
+ * size of the reference's Poly::Vertex::Position / VMACH vertex, Inc/Poly.h:15-21) instead of the resident float4
+ * layout: a quarter fewer bytes cross the bus, and one small kernel on the context stream widens them to float4
+ * (w = 0) in HBM, so every kernel of the event still reads aligned float4 streams.  Results are identical. */
+int surtr_upload_pieces3(surtr_ctx* ctx, const float* verts3, const uint32_t* vert_off, const uint32_t* ring_off,
+                         const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events);
+int surtr_upload_cells3(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts3,
+                        const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events);
 /* Recursive re-fracture: make the last event's fragments the piece set of the next event (device side, no
  * copy through the host).  Every fragment becomes one piece; ev_piece_off (host, n_events+1) regroups them, or
  * NULL to keep one event. */
@@ -153,6 +161,15 @@ int surtr_download_fragments(surtr_ctx* ctx, surtr_fragment* fragments, float* v
  * without ever blocking on PCIe. */
 int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off,
                                    uint16_t* ring);
+/* PCIe wire format of the fragments: float3 positions (n_verts x 3 floats) and ONE BYTE per vertex for its ring
+ * length (ring_off is their exclusive prefix sum; a Poly::Vertex::NeighborVertexVec never exceeds 16 entries on
+ * this path) instead of float4 + a 32-bit offset: 13 instead of 20 bytes per vertex.  A small kernel on the
+ * context's copy stream packs the resident arrays before the copies; records and ring entries travel unchanged.
+ * Same completion rules as surtr_download_fragments(_async). */
+int surtr_download_fragments_packed(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len,
+                                    uint16_t* ring);
+int surtr_download_fragments_packed_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len,
+                                          uint16_t* ring);
 int surtr_sync(surtr_ctx* ctx);
 int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out);
 

@@ -155,6 +155,25 @@ __global__ void __launch_bounds__(256) place_pattern_kernel(const float4* __rest
     c_planes[(size_t)p * n_faces + f] = plane_from_points(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8]);
 }
 
+// PCIe wire format (surtr_upload_pieces3 / surtr_upload_cells3): float3 stream -> resident float4 stream, w = 0.
+__global__ void __launch_bounds__(256) widen3_kernel(const float* __restrict__ in3, float4* __restrict__ out4, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out4[i] = make_float4(__ldg(in3 + 3 * i), __ldg(in3 + 3 * i + 1), __ldg(in3 + 3 * i + 2), 0.f);
+}
+
+// PCIe wire format of the fragments (surtr_download_fragments_packed): float3 positions, one byte of ring length per vertex.
+__global__ void __launch_bounds__(256) pack_fragments_kernel(const float4* __restrict__ verts4, const uint32_t* __restrict__ ring_off,
+                                                             float* __restrict__ verts3, uint8_t* __restrict__ ring_len, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const float4 v = verts4[i];
+        verts3[3 * i] = v.x; verts3[3 * i + 1] = v.y; verts3[3 * i + 2] = v.z;
+        ring_len[i] = (uint8_t)(ring_off[i + 1] - ring_off[i]);
+    }
+}
+
 // Poly::Transform (Poly.cpp:580-585) over the resident pieces: position = XMVector3TransformCoord(position, M^T) with the
 // piece's world matrix M (row-major as the caller holds it; the reference transposes before use), i.e. per output
 // component c: ((z*M[c][2] + M[c][3]) + y*M[c][1]) + x*M[c][0], then a division by the w component.  One warp per piece.

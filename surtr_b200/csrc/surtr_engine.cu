@@ -105,6 +105,7 @@ struct surtr_ctx
 
     // outputs
     DevBuf f_rec, f_verts, f_ring_off, f_ring;
+    DevBuf wire_p3, wire_c3, wire_f3, wire_flen;   // float3 / u8 staging of the PCIe wire format
     uint64_t cap_frag = 0, cap_fverts = 0, cap_fring = 0;
 
     Ctl* h_ctl = nullptr;   // pinned
@@ -459,7 +460,25 @@ int upload(surtr_ctx* ctx, DevBuf& b, const void* src, size_t bytes)
     if (bytes && src) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return SURTR_OK;
 }
+// float3 stream from the host -> staging buffer -> widened to the resident float4 buffer on the context stream
+int upload3(surtr_ctx* ctx, DevBuf& stage, DevBuf& dst4, const float* src3, uint64_t n)
+{
+    CK(dst4.reserve(std::max<size_t>(16 * n, 16)));
+    if (!n || !src3) return SURTR_OK;
+    const int rc = upload(ctx, stage, src3, 12 * n);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sm * 8);
+    widen3_kernel<<<blocks, 256, 0, ctx->stream>>>(stage.as<float>(), dst4.as<float4>(), n);
+    CK(cudaGetLastError());
+    return SURTR_OK;
+}
 } // namespace
+
+static int upload_pieces_impl(surtr_ctx* ctx, const float* verts, bool packed3, const uint32_t* vert_off, const uint32_t* ring_off,
+                              const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events);
+static int upload_cells_impl(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts, bool packed3,
+                             const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events);
+static int download_impl(surtr_ctx* ctx, surtr_fragment* fragments, void* verts, void* ring_off_or_len, uint16_t* ring, bool packed);
 
 extern "C"
 {
@@ -518,7 +537,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
-                      &ctx->f_ring_off, &ctx->f_ring, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
+                      &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
                       &ctx->xf_idx };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -540,13 +559,38 @@ int surtr_set_kdop_directions(surtr_ctx* ctx, int k)
 int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,
                         const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events)
 {
+    return upload_pieces_impl(ctx, verts4, false, vert_off, ring_off, ring, n_pieces, ev_piece_off, n_events);
+}
+
+int surtr_upload_pieces3(surtr_ctx* ctx, const float* verts3, const uint32_t* vert_off, const uint32_t* ring_off,
+                         const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events)
+{
+    return upload_pieces_impl(ctx, verts3, true, vert_off, ring_off, ring, n_pieces, ev_piece_off, n_events);
+}
+
+int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4,
+                       const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
+{
+    return upload_cells_impl(ctx, planes4, plane_off, cell_verts4, false, cvert_off, n_cells, ev_cell_off, n_events);
+}
+
+int surtr_upload_cells3(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts3,
+                        const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
+{
+    return upload_cells_impl(ctx, planes4, plane_off, cell_verts3, true, cvert_off, n_cells, ev_cell_off, n_events);
+}
+} // extern "C"
+
+static int upload_pieces_impl(surtr_ctx* ctx, const float* verts4, bool packed3, const uint32_t* vert_off, const uint32_t* ring_off,
+                              const uint16_t* ring, uint32_t n_pieces, const uint32_t* ev_piece_off, uint32_t n_events)
+{
     if (!ctx) return SURTR_ERR_INVALID;
     if (!vert_off || (vert_off[n_pieces] && (!verts4 || !ring_off || !ring))) return fail(ctx, SURTR_ERR_INVALID, "NULL piece array");
     CK(cudaSetDevice(ctx->device));
     const uint64_t nv = vert_off[n_pieces];
     const uint64_t ne = nv ? ring_off[nv] : 0;
     int rc;
-    if ((rc = upload(ctx, ctx->p_verts, verts4, 16 * nv))) return rc;
+    if ((rc = packed3 ? upload3(ctx, ctx->wire_p3, ctx->p_verts, verts4, nv) : upload(ctx, ctx->p_verts, verts4, 16 * nv))) return rc;
     if ((rc = upload(ctx, ctx->p_vert_off, vert_off, 4 * ((size_t)n_pieces + 1)))) return rc;
     if ((rc = upload(ctx, ctx->p_ring_off, ring_off, 4 * (nv + 1)))) return rc;
     if ((rc = upload(ctx, ctx->p_ring, ring, 2 * ne))) return rc;
@@ -572,8 +616,8 @@ int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* ver
     return SURTR_OK;
 }
 
-int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4,
-                       const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
+static int upload_cells_impl(surtr_ctx* ctx, const float* planes4, const uint32_t* plane_off, const float* cell_verts4, bool packed3,
+                             const uint32_t* cvert_off, uint32_t n_cells, const uint32_t* ev_cell_off, uint32_t n_events)
 {
     if (!ctx) return SURTR_ERR_INVALID;
     if (!plane_off || (plane_off[n_cells] && !planes4)) return fail(ctx, SURTR_ERR_INVALID, "NULL cell array");
@@ -586,7 +630,7 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
     if (ctx->cells_bounded)
     {
         const uint64_t ncv = cvert_off[n_cells];
-        if ((rc = upload(ctx, ctx->c_verts, cell_verts4, 16 * ncv))) return rc;
+        if ((rc = packed3 ? upload3(ctx, ctx->wire_c3, ctx->c_verts, cell_verts4, ncv) : upload(ctx, ctx->c_verts, cell_verts4, 16 * ncv))) return rc;
         if ((rc = upload(ctx, ctx->c_vert_off, cvert_off, 4 * ((size_t)n_cells + 1)))) return rc;
         ctx->n_cverts = ncv;
     }
@@ -607,6 +651,8 @@ int surtr_upload_cells(surtr_ctx* ctx, const float* planes4, const uint32_t* pla
     return SURTR_OK;
 }
 
+extern "C"
+{
 int surtr_fracture_event(surtr_ctx* ctx)
 {
     if (!ctx) return SURTR_ERR_INVALID;
@@ -627,6 +673,23 @@ int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out)
 
 int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts4, uint32_t* ring_off, uint16_t* ring)
 {
+    return download_impl(ctx, fragments, verts4, ring_off, ring, false);
+}
+
+int surtr_download_fragments_packed_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len, uint16_t* ring)
+{
+    return download_impl(ctx, fragments, verts3, ring_len, ring, true);
+}
+
+int surtr_download_fragments_packed(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len, uint16_t* ring)
+{
+    const int rc = download_impl(ctx, fragments, verts3, ring_len, ring, true);
+    return rc ? rc : surtr_sync(ctx);
+}
+} // extern "C"
+
+static int download_impl(surtr_ctx* ctx, surtr_fragment* fragments, void* verts4, void* ring_off, uint16_t* ring, bool packed)
+{
     if (!ctx) return SURTR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->event_resolved && ctx->copy_pending) ctx->copy_pending = false;   // (re-issued below; the stream keeps them ordered)
@@ -636,9 +699,21 @@ int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, fl
     cudaStream_t cs = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
     if (fragments && c.n_fragments)
         CK(cudaMemcpyAsync(fragments, ctx->f_rec.p, sizeof(surtr_fragment) * c.n_fragments, cudaMemcpyDeviceToHost, cs));
-    if (verts4 && c.n_verts)
+    if (packed && c.n_verts && (verts4 || ring_off))
+    {
+        // wire format: float3 + one byte of ring length per vertex, packed on the copy stream (the event is complete)
+        CK(ctx->wire_f3.reserve(12 * c.n_verts));
+        CK(ctx->wire_flen.reserve(c.n_verts));
+        const unsigned blocks = (unsigned)std::min<uint64_t>((c.n_verts + 255) / 256, (uint64_t)ctx->num_sm * 8);
+        pack_fragments_kernel<<<blocks, 256, 0, cs>>>(ctx->f_verts.as<float4>(), ctx->f_ring_off.as<uint32_t>(), ctx->wire_f3.as<float>(),
+                                                      ctx->wire_flen.as<uint8_t>(), c.n_verts);
+        CK(cudaGetLastError());
+        if (verts4) CK(cudaMemcpyAsync(verts4, ctx->wire_f3.p, 12 * c.n_verts, cudaMemcpyDeviceToHost, cs));
+        if (ring_off) CK(cudaMemcpyAsync(ring_off, ctx->wire_flen.p, c.n_verts, cudaMemcpyDeviceToHost, cs));
+    }
+    if (!packed && verts4 && c.n_verts)
         CK(cudaMemcpyAsync(verts4, ctx->f_verts.p, 16 * c.n_verts, cudaMemcpyDeviceToHost, cs));
-    if (ring_off)
+    if (!packed && ring_off)
         CK(cudaMemcpyAsync(ring_off, ctx->f_ring_off.p, 4 * (c.n_verts + 1), cudaMemcpyDeviceToHost, cs));
     if (ring && c.n_ring)
         CK(cudaMemcpyAsync(ring, ctx->f_ring.p, 2 * c.n_ring, cudaMemcpyDeviceToHost, cs));
@@ -650,6 +725,8 @@ int surtr_download_fragments_async(surtr_ctx* ctx, surtr_fragment* fragments, fl
     return SURTR_OK;
 }
 
+extern "C"
+{
 int surtr_sync(surtr_ctx* ctx)
 {
     if (!ctx) return SURTR_ERR_INVALID;

@@ -34,6 +34,7 @@ EXPORTS = [
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
     "surtr_transform_pieces", "surtr_download_pieces", "surtr_measure_fp32_peak",
+    "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
 ]
 
 
@@ -74,6 +75,10 @@ def load_library():
     lib.surtr_set_kdop_directions.argtypes = [vp, i32]
     lib.surtr_upload_pieces.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
     lib.surtr_upload_cells.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
+    lib.surtr_upload_pieces3.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
+    lib.surtr_upload_cells3.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
+    lib.surtr_download_fragments_packed.argtypes = [vp, vp, vp, vp, vp]
+    lib.surtr_download_fragments_packed_async.argtypes = [vp, vp, vp, vp, vp]
     lib.surtr_fragments_to_pieces.argtypes = [vp, vp, u32]
     lib.surtr_upload_pattern.argtypes = [vp, vp, vp, u32, vp, u32]
     lib.surtr_place_pattern.argtypes = [vp, vp, vp, u32]
@@ -261,6 +266,54 @@ class FractureContext:
                                               C.c_void_p(cell_verts4) if cell_verts4 else None,
                                               C.c_void_p(cvert_off) if cvert_off else None, n_cells,
                                               C.c_void_p(ev) if ev else None, n_events))
+
+    # ---- PCIe wire format: float3 vertex streams up, float3 + one byte of ring length per vertex down ----
+    def upload_pieces3_ptr(self, verts3, vert_off, ring_off, ring, n_pieces, ev=None, n_events=0):
+        self._ck(self._lib.surtr_upload_pieces3(self._h, C.c_void_p(verts3), C.c_void_p(vert_off), C.c_void_p(ring_off),
+                                                C.c_void_p(ring), n_pieces, C.c_void_p(ev) if ev else None, n_events))
+
+    def upload_cells3_ptr(self, planes4, plane_off, cell_verts3, cvert_off, n_cells, ev=None, n_events=0):
+        self._ck(self._lib.surtr_upload_cells3(self._h, C.c_void_p(planes4), C.c_void_p(plane_off),
+                                               C.c_void_p(cell_verts3) if cell_verts3 else None,
+                                               C.c_void_p(cvert_off) if cvert_off else None, n_cells,
+                                               C.c_void_p(ev) if ev else None, n_events))
+
+    def upload_pieces3(self, verts3, vert_off, ring_off, ring, ev_piece_off=None):
+        verts3 = _arr(np.asarray(verts3, np.float32)[:, :3], np.float32)
+        vert_off, ring_off, ring = _arr(vert_off, np.uint32), _arr(ring_off, np.uint32), _arr(ring, np.uint16)
+        ev = _arr(ev_piece_off, np.uint32)
+        self._ck(self._lib.surtr_upload_pieces3(self._h, _p(verts3), _p(vert_off), _p(ring_off), _p(ring),
+                                                len(vert_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def upload_cells3(self, planes4, plane_off, cell_verts3=None, cvert_off=None, ev_cell_off=None):
+        planes4, plane_off = _arr(planes4, np.float32), _arr(plane_off, np.uint32)
+        cell_verts3 = None if cell_verts3 is None else _arr(np.asarray(cell_verts3, np.float32)[:, :3], np.float32)
+        cvert_off = _arr(cvert_off, np.uint32)
+        ev = _arr(ev_cell_off, np.uint32)
+        self._ck(self._lib.surtr_upload_cells3(self._h, _p(planes4), _p(plane_off), _p(cell_verts3), _p(cvert_off),
+                                               len(plane_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def download_packed(self) -> Fragments:
+        """Fragments through the packed wire format, unpacked to the usual arrays (float4 with w = 0, ring_off as the
+        prefix sum of the ring lengths)."""
+        c = self.counts()
+        rec = np.zeros(c.n_fragments, FRAGMENT_DTYPE)
+        v3 = np.zeros((c.n_verts, 3), np.float32)
+        rl = np.zeros(c.n_verts, np.uint8)
+        ring = np.zeros(c.n_ring, np.uint16)
+        self._ck(self._lib.surtr_download_fragments_packed(self._h, _p(rec), _p(v3), _p(rl), _p(ring)))
+        verts = np.zeros((c.n_verts, 4), np.float32)
+        verts[:, :3] = v3
+        ring_off = np.concatenate([[0], np.cumsum(rl, dtype=np.uint64)]).astype(np.uint32)
+        return Fragments(rec, verts, ring_off, ring)
+
+    def download_packed_into(self, rec, verts3, ring_len, ring):
+        self._ck(self._lib.surtr_download_fragments_packed(self._h, C.c_void_p(rec), C.c_void_p(verts3), C.c_void_p(ring_len),
+                                                           C.c_void_p(ring)))
+
+    def download_packed_into_async(self, rec, verts3, ring_len, ring):
+        self._ck(self._lib.surtr_download_fragments_packed_async(self._h, C.c_void_p(rec), C.c_void_p(verts3),
+                                                                 C.c_void_p(ring_len), C.c_void_p(ring)))
 
     def device_view(self) -> DeviceView:
         v = DeviceView()

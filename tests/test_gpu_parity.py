@@ -428,6 +428,29 @@ def test_async_download_and_contexts_in_flight():
             cx.close()
 
 
+def test_packed_wire_format(ctx):
+    """surtr_upload_pieces3 / surtr_upload_cells3 / surtr_download_fragments_packed: float3 streams up, float3 + one
+    byte of ring length per vertex down -- the same fragments, bit for bit, as the float4 calls and as the oracle
+    (config 4's first event: 1000 pieces x 64 cells, and the unit cube x 256 cells)."""
+    for pieces, cells in ((common.voronoi(1234, 1000), common.voronoi(46354, 64)), (common.unit_cube(), common.voronoi(46354, 256))):
+        ref = common.run_gpu(ctx, pieces, cells)
+        want = P.apply_fracture(pieces, cells.planes, cells.plane_off)
+        common.assert_fragments_equal(ref, want)
+        ctx.upload_pieces3(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+        ctx.upload_cells3(cells.planes, cells.plane_off, cells.verts, cells.vert_off)
+        ctx.fracture_event()
+        got = ctx.download_packed()
+        common.assert_fragments_equal(got, want)
+        assert got.rec.tobytes() == ref.rec.tobytes()
+        assert np.array_equal(bits(got.verts[:, :3]), bits(ref.verts[:, :3]))
+        assert np.array_equal(got.ring_off, ref.ring_off) and np.array_equal(got.ring, ref.ring)
+        # mixed use: a packed download after a float4 upload, and the plain download after a packed one
+        common.run_gpu(ctx, pieces, cells)
+        assert ctx.download_packed().rec.tobytes() == ref.rec.tobytes()
+        again = ctx.download()
+        assert np.array_equal(bits(again.verts), bits(ref.verts)) and np.array_equal(again.ring_off, ref.ring_off)
+
+
 def test_global_tier_workspace_grows(monkeypatch):
     """A global-tier workspace that runs out of vertex slots is doubled and the event re-run (never a failed pair): the
     bunny mesh (2503 vertices) starting from a 1024-slot workspace (test hook SURTR_DEBUG_CAP3)."""

@@ -29,25 +29,30 @@ def timed(name, f, *a):
     t0 = time.perf_counter(); f(*a); T[name] += time.perf_counter() - t0
 import os
 NO_UP, NO_DOWN = bool(os.environ.get('NO_UP')), bool(os.environ.get('NO_DOWN'))
+NO_UP_PIECES = bool(os.environ.get('NO_UP_PIECES'))   # drops the four tiny piece copies (220 bytes): per-copy overhead?
+ONE_DOWN = bool(os.environ.get('ONE_DOWN'))           # downloads only the vertex array (one copy instead of four)
 def run(n, with_flush):
     for i in range(n + D):
         cx, st, ho = pipes[i % D]
         if i >= D and NO_DOWN:
             timed("counts only", cx.counts)
         elif i >= D:
-            timed("download_async (incl. wait for the event)", cx.download_into_async, ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
+            if ONE_DOWN:
+                timed("download_async (verts only)", cx.download_into_async, None, ho["verts"].data_ptr(), None, None)
+            else:
+                timed("download_async (incl. wait for the event)", cx.download_into_async, ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_off"].data_ptr(), ho["ring"].data_ptr())
         if i < n:
             if with_flush:
                 def fl():
                     with torch.cuda.stream(st):
                         flush.zero_()
                 timed("flush launch", fl)
-            if not NO_UP: timed("upload_pieces", cx.upload_pieces_ptr, h["pv"].data_ptr(), h["pvo"].data_ptr(), h["pro"].data_ptr(), h["pr"].data_ptr(), 1)
+            if not NO_UP and not NO_UP_PIECES: timed("upload_pieces", cx.upload_pieces_ptr, h["pv"].data_ptr(), h["pvo"].data_ptr(), h["pro"].data_ptr(), h["pr"].data_ptr(), 1)
             if not NO_UP: timed("upload_cells", cx.upload_cells_ptr, h["planes"].data_ptr(), h["plane_off"].data_ptr(), h["cverts"].data_ptr(), h["cvo"].data_ptr(), N)
             timed("fracture_event (6 launches)", cx.fracture_event)
     for cx, st, ho in pipes:
         cx.sync()
-for with_flush in (True, False):
+for with_flush in (False,):
     run(2 * D, with_flush); torch.cuda.synchronize(); T.clear()
     t0 = time.perf_counter(); run(K, with_flush); torch.cuda.synchronize(); tot = time.perf_counter() - t0
     print(f"depth {D} flush {with_flush}: {1e6 * tot / K:.1f} us/step wall;  host time per step:",
