@@ -176,7 +176,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="surtr_b200", choices=["surtr_b200", "reference"])
-    ap.add_argument("--kdop", type=int, default=3)
+    ap.add_argument("--kdop", type=int, default=3,
+                    help="broad-phase direction set; the workload's single piece contains every cell, so no pair can be "
+                         "culled and the cheapest set (AABB) is used -- the library default is 13")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU-baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=E2E_DEPTH, help="events between launch and download in the end-to-end loop")

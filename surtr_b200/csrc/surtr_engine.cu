@@ -74,7 +74,7 @@ struct surtr_ctx
     cudaEvent_t copy_done = nullptr;
     bool copy_pending = false;
     std::string err;
-    int kdirs = 3;
+    int kdirs = 13;   // 26-DOP: 10 % faster events than the AABB on configs 3 and 4 (profiles/r1_kdop_sweep.json)
 
     // inputs
     uint32_t n_pieces = 0, n_cells = 0, n_events_p = 0, n_events_c = 0;

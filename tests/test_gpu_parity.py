@@ -30,7 +30,7 @@ def test_golden_fixture_events(ctx, name):
         ctx.set_kdop_directions(k)
         got = common.run_gpu(ctx, pieces, cells)
         common.assert_fragments_equal(got, want)
-    ctx.set_kdop_directions(3)
+    ctx.set_kdop_directions(13)    # the default
     got = common.run_gpu(ctx, pieces, cells, bounded=False)     # no cell bounds: every pair reaches the clipper
     common.assert_fragments_equal(got, want)
     assert ctx.counts().n_candidates == pieces.n * cells.n
