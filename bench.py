@@ -462,19 +462,20 @@ def main():
         d_out = {k: v.to(dev, non_blocking=True) for k, v in h_out.items()}
         torch.cuda.synchronize()
         dist.barrier()
-        sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_off"], d_out["ring"], dst=0)   # NCCL warm-up
+        sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_len"], d_out["ring"], dst=0)   # NCCL warm-up
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        parts = sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_off"], d_out["ring"], dst=0)
+        parts = sharding.gather_fragments(d_out["rec"], d_out["verts"], d_out["ring_len"], d_out["ring"], dst=0)
         g1.record()
         torch.cuda.synchronize()
         if rank == 0:
             assert len(parts) == world and all(p[0].numel() == d_out["rec"].numel() or True for p in parts)
             gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank": int(d2h_bytes),
                       "fragments_gathered": int(sum(p[0].numel() for p in parts) // FRAGMENT_DTYPE.itemsize),
-                      "backend": "nccl all_gather(counts) + padded gather to rank 0"}
+                      "backend": "nccl all_gather(counts) + padded gather to rank 0",
+                      "arrays": "records, vertex positions, ring lengths / offsets, ring entries as downloaded (wire format)"}
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0) ----
     if rank == 0:
