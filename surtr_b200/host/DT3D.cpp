@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <set>
@@ -70,8 +71,57 @@ struct Tet
 	bool alive;
 };
 
-// Index-based Bowyer-Watson.  Points 0..n-1 are the input, n..n+3 a far super-tetrahedron.
-std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points)
+// Uniform grid over the points' bounding box that finds the tets whose circumsphere may contain a query point: a tet
+// is listed in every grid cell its circumsphere's bounding box touches (in `big` when that is more than a few dozen
+// cells, or when the sphere is not finite -- those are tested for every point).  A point inside a sphere is inside the
+// sphere's box, so the list of the point's cell plus `big` is a superset of the tets the full scan would find, and the
+// SAME predicate then picks exactly the same ones.  Dead tets are dropped from a list when it is next scanned.
+struct SphereGrid
+{
+	int G = 1;
+	double lo[3] = { 0, 0, 0 }, inv[3] = { 0, 0, 0 };
+	std::vector<std::vector<int>> cell;
+	std::vector<int> big;
+	static constexpr long BIG_CELLS = 128;
+
+	void init(const double lo_[3], const double hi_[3], int n)
+	{
+		G = std::max(1, (int)std::cbrt((double)n / 32.0));
+		for (int k = 0; k < 3; k++)
+		{
+			lo[k] = lo_[k];
+			inv[k] = hi_[k] > lo_[k] ? G / (hi_[k] - lo_[k]) : 0.0;
+		}
+		cell.assign((size_t)G * G * G, {});
+		big.clear();
+	}
+	int coord(double x, int k) const   // monotone in x; NaN and anything below the box -> 0, above -> G - 1
+	{
+		const double f = (x - lo[k]) * inv[k];
+		if (!(f > 0.0)) return 0;
+		if (f >= (double)G) return G - 1;
+		return (int)f;
+	}
+	void add(int id, const Tet& t)
+	{
+		const bool finite = std::isfinite(t.c[0]) && std::isfinite(t.c[1]) && std::isfinite(t.c[2]) && std::isfinite(t.r2);
+		if (!finite) { big.push_back(id); return; }
+		const double r = std::sqrt(t.r2 * (1.0 + 1e-12)) * (1.0 + 1e-9) + 1e-300;
+		int a[3], b[3];
+		for (int k = 0; k < 3; k++) { a[k] = coord(t.c[k] - r, k); b[k] = coord(t.c[k] + r, k); }
+		if ((long)(b[0] - a[0] + 1) * (b[1] - a[1] + 1) * (b[2] - a[2] + 1) > BIG_CELLS) { big.push_back(id); return; }
+		for (int z = a[2]; z <= b[2]; z++)
+			for (int y = a[1]; y <= b[1]; y++)
+				for (int x = a[0]; x <= b[0]; x++)
+					cell[((size_t)z * G + y) * G + x].push_back(id);
+	}
+	std::vector<int>& at(const double p[3]) { return cell[((size_t)coord(p[2], 2) * G + coord(p[1], 1)) * G + coord(p[0], 0)]; }
+};
+
+// Index-based Bowyer-Watson.  Points 0..n-1 are the input, n..n+3 a far super-tetrahedron.  `use_grid` = false is the
+// plain scan over every live tet per inserted point (quadratic, as the reference's Inc/DT3D.h:198-246); true finds the
+// same tets through the SphereGrid -- identical output, tet for tet (tests/test_host.py), 1.6 s -> tens of ms at 4096 seeds.
+std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points, bool use_grid = true)
 {
 	const int n = (int)points.size();
 	std::vector<std::array<double, 3>> P(n + 4);
@@ -99,19 +149,42 @@ std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points)
 		t.alive = true;
 		return t;
 	};
+	SphereGrid grid;
+	if (use_grid) grid.init(lo, hi, n);
 	std::vector<Tet> tets;
 	tets.push_back(make(n, n + 1, n + 2, n + 3));
+	if (use_grid) grid.add(0, tets[0]);
 	std::vector<int> bad;
 	std::map<std::array<int, 3>, int> faces;
+	size_t n_alive = 1;
 	for (int i = 0; i < n; i++)
 	{
 		bad.clear();
-		for (int t = 0; t < (int)tets.size(); t++)
-		{
-			if (!tets[t].alive) continue;
+		auto inside = [&](int t) {
 			const double dx = P[i][0] - tets[t].c[0], dy = P[i][1] - tets[t].c[1], dz = P[i][2] - tets[t].c[2];
-			if (dx * dx + dy * dy + dz * dz <= tets[t].r2 * (1.0 + 1e-12))
-				bad.push_back(t);
+			return dx * dx + dy * dy + dz * dz <= tets[t].r2 * (1.0 + 1e-12);
+		};
+		if (use_grid)
+		{
+			for (std::vector<int>* list : { &grid.at(P[i].data()), &grid.big })
+			{
+				size_t w = 0;
+				for (size_t r = 0; r < list->size(); r++)
+				{
+					const int t = (*list)[r];
+					if (!tets[t].alive) continue;   // dropped from the list
+					(*list)[w++] = t;
+					if (inside(t)) bad.push_back(t);
+				}
+				list->resize(w);
+			}
+			std::sort(bad.begin(), bad.end());      // the order of the scan
+		}
+		else
+		{
+			for (int t = 0; t < (int)tets.size(); t++)
+				if (tets[t].alive && inside(t))
+					bad.push_back(t);
 		}
 		faces.clear();
 		for (int t : bad)
@@ -126,11 +199,23 @@ std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points)
 			}
 			tets[t].alive = false;
 		}
+		n_alive -= bad.size();
 		for (const auto& kv : faces)
 			if (kv.second == 1)   // boundary of the cavity
+			{
 				tets.push_back(make(kv.first[0], kv.first[1], kv.first[2], i));
-		if (tets.size() > 4096 && tets.size() > 8 * (size_t)std::count_if(tets.begin(), tets.end(), [](const Tet& t) { return t.alive; }))
+				if (use_grid) grid.add((int)tets.size() - 1, tets.back());
+				n_alive++;
+			}
+		if (tets.size() > 4096 && tets.size() > 8 * n_alive)
+		{
 			tets.erase(std::remove_if(tets.begin(), tets.end(), [](const Tet& t) { return !t.alive; }), tets.end());
+			if (use_grid)   // the ids changed: list the survivors again
+			{
+				grid.init(lo, hi, n);
+				for (int t = 0; t < (int)tets.size(); t++) grid.add(t, tets[t]);
+			}
+		}
 	}
 	tets.erase(std::remove_if(tets.begin(), tets.end(),
 							  [&](const Tet& t) { return !t.alive || t.v[0] >= n || t.v[1] >= n || t.v[2] >= n || t.v[3] >= n; }),
@@ -138,6 +223,19 @@ std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points)
 	return tets;
 }
 } // namespace
+
+namespace detail
+{
+// Test hook: the tets (point indices, in construction order) of the accelerated or of the plain-scan triangulation.
+std::vector<std::array<int, 4>> TetIndices(const std::vector<Vector3>& points, bool use_grid)
+{
+	std::vector<std::array<int, 4>> out;
+	if (points.size() >= 4)
+		for (const Tet& t : bowyer_watson(points, use_grid))
+			out.push_back({ t.v[0], t.v[1], t.v[2], t.v[3] });
+	return out;
+}
+} // namespace detail
 
 Delaunay Triangulate(const std::vector<Vector3>& points)
 {

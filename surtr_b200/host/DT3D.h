@@ -10,6 +10,7 @@
 
 #include "VMACH.h"
 
+#include <array>
 #include <vector>
 
 namespace DT3D
@@ -55,6 +56,13 @@ std::vector<Edge> Voronoi(const Delaunay& dt);             // unique circumcentr
 
 // Delaunay neighbour lists (CSR, ascending seed index) without materialising tets by value.
 void Neighbors(const std::vector<Vector3>& points, std::vector<uint32_t>& off, std::vector<uint32_t>& idx);
+
+namespace detail
+{
+// Test hook: tets as point indices, in construction order; use_grid = false is the quadratic scan of every live tet per
+// inserted point (the reference's search, Inc/DT3D.h:198-246), true the grid-accelerated search -- same output.
+std::vector<std::array<int, 4>> TetIndices(const std::vector<Vector3>& points, bool use_grid);
+}
 
 // NEW (replaces Surtr::GenerateVoronoi, Surtr.cpp:2003-2070): cells in seed order, faces outward, bounded by the
 // unit container box [-0.5, 0.5]^3.  The clipping runs on the GPU.

@@ -93,6 +93,18 @@ uint64_t hosttest_dt3d_neighbors(const float* seeds, uint32_t n, uint32_t* off, 
 	return x.size();
 }
 
+// Tets (4 point indices each, construction order) of the grid-accelerated (use_grid = 1) or plain-scan triangulation
+uint64_t hosttest_dt3d_tets(const float* seeds, uint32_t n, int use_grid, int32_t* out, uint64_t cap)
+{
+	std::vector<Vector3> s;
+	for (uint32_t i = 0; i < n; i++) s.emplace_back(seeds[3 * i], seeds[3 * i + 1], seeds[3 * i + 2]);
+	const auto tets = DT3D::detail::TetIndices(s, use_grid != 0);
+	if (tets.size() <= cap)
+		for (size_t i = 0; i < tets.size(); i++)
+			for (int k = 0; k < 4; k++) out[4 * i + k] = tets[i][k];
+	return tets.size();
+}
+
 // DT3D::Triangulate by value: returns the tet count and the number of tets whose circumsphere contains another seed
 int hosttest_dt3d_triangulate(const float* seeds, uint32_t n, uint32_t* n_tets, uint32_t* n_faces, uint32_t* n_voronoi_edges)
 {

@@ -60,6 +60,20 @@ def dt3d_neighbors(s):
     return off, idx[:int(n)].copy()
 
 
+def dt3d_tets(s, use_grid=True):
+    """Tets as point indices in construction order (grid-accelerated or plain-scan Bowyer-Watson)."""
+    s = np.ascontiguousarray(s, np.float32)
+    L = lib()
+    L.hosttest_dt3d_tets.restype = C.c_uint64
+    L.hosttest_dt3d_tets.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]
+    out = np.zeros((16 * len(s) + 64, 4), np.int32)
+    n = int(L.hosttest_dt3d_tets(_p(s), len(s), int(use_grid), _p(out), len(out)))
+    if n > len(out):      # degenerate inputs (lattices, coplanar points) can leave many more tets: size and repeat
+        out = np.zeros((n, 4), np.int32)
+        n = int(L.hosttest_dt3d_tets(_p(s), len(s), int(use_grid), _p(out), len(out)))
+    return out[:n].copy()
+
+
 def dt3d_triangulate(s):
     s = np.ascontiguousarray(s, np.float32)
     nt, nf, ne = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)

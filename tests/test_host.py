@@ -41,6 +41,30 @@ def test_host_dt3d_against_reference_and_qhull():
     assert H.dt3d_triangulate(common.seeds_uniform(1, 2))[0] == 0     # < 3 points -> empty (DT3D.h:161-162)
 
 
+def test_host_dt3d_grid_search_equals_the_full_scan():
+    """The grid-accelerated cavity search of the host DT3D (surtr_b200/host/DT3D.cpp, SphereGrid) must produce the
+    triangulation of the plain scan over every live tet (the reference's search, Inc/DT3D.h:198-246) TET FOR TET, in
+    the same order -- on uniform seeds, clustered seeds, a lattice (co-spherical points), coplanar points, duplicates
+    and the exponential radial pattern of GenerateFracturePattern."""
+    rng = np.random.RandomState(7)
+    cases = {
+        "uniform_5": common.seeds_uniform(3, 5),
+        "uniform_64": common.seeds_uniform(46354, 64),
+        "uniform_1000": common.seeds_uniform(1234, 1000),
+        "uniform_4096": common.seeds_uniform(46354, 4096),
+        "clustered": (rng.normal(0, 0.02, (600, 3)) + rng.choice([-0.3, 0.0, 0.3], (600, 1))).astype(np.float32),
+        "lattice_6x6x6": (np.stack(np.meshgrid(*[np.arange(6)] * 3, indexing="ij"), -1).reshape(-1, 3) / 5.0 - 0.5).astype(np.float32),
+        "coplanar": np.concatenate([rng.uniform(-0.5, 0.5, (200, 2)), np.zeros((200, 1))], 1).astype(np.float32),
+        "duplicates": np.repeat(common.seeds_uniform(5, 100), 2, axis=0),
+        "radial": (rng.standard_normal((800, 3)) * rng.exponential(0.05, (800, 1))).astype(np.float32),
+        "far_from_origin": common.seeds_uniform(9, 300) * np.float32(1e-3) + np.float32(1000.0),
+    }
+    for name, s in cases.items():
+        a, b = H.dt3d_tets(s, True), H.dt3d_tets(s, False)
+        assert a.shape == b.shape and np.array_equal(a, b), name
+    assert len(H.dt3d_tets(common.seeds_uniform(46354, 4096), True)) > 26000
+
+
 def test_host_extract_faces_matches_reference_loops():
     d = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
     fr = load_polyset(d, "frag_")
