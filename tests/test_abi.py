@@ -48,6 +48,48 @@ def test_no_device_fails_loudly():
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
 
 
+def test_plain_c_caller_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (what a cgo / JNI / ctypes stub sees) must compile against
+    include/surtr_b200.h with -pedantic, link libsurtr_b200.so, and -- on a machine without a GPU -- get
+    SURTR_ERR_NO_DEVICE and an error text from surtr_ctx_create instead of any CPU fallback."""
+    src = tmp_path / "caller.c"
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "surtr_b200.h"
+int main(void)
+{
+    surtr_ctx* ctx = NULL;
+    surtr_counts counts;
+    surtr_fragment frag;
+    int rc;
+    memset(&counts, 0, sizeof counts);
+    memset(&frag, 0, sizeof frag);
+    if (sizeof(surtr_fragment) != 64) return 10;
+    if (!strstr(surtr_version(), "sm_100a")) return 11;
+    rc = surtr_ctx_create(0, NULL, &ctx);
+    if (rc == SURTR_OK) { surtr_ctx_destroy(ctx); puts("device"); return 0; }
+    if (rc != SURTR_ERR_NO_DEVICE || ctx != NULL) return 12;
+    if (!strstr(surtr_last_error(NULL), "no CPU fallback")) return 13;
+    /* every entry point refuses a NULL context instead of touching memory */
+    if (surtr_fracture_event(NULL) == SURTR_OK || surtr_upload_pieces3(NULL, NULL, NULL, NULL, NULL, 0, NULL, 0) == SURTR_OK ||
+        surtr_download_fragments_packed(NULL, NULL, NULL, NULL, NULL) == SURTR_OK || surtr_event_counts(NULL, &counts) == SURTR_OK)
+        return 14;
+    puts("no device");
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.join(ROOT, "surtr_b200")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", libdir, "-lsurtr_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    import torch
+    assert run.stdout.strip() == ("device" if torch.cuda.is_available() else "no device")
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under surtr_b200/ or include/ may reference it."""
     bad = []
