@@ -155,7 +155,7 @@ std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points, bool use_grid
 	tets.push_back(make(n, n + 1, n + 2, n + 3));
 	if (use_grid) grid.add(0, tets[0]);
 	std::vector<int> bad;
-	std::map<std::array<int, 3>, int> faces;
+	std::vector<std::array<int, 3>> faces;   // the cavity's faces; sorted, a face met once is on its boundary
 	size_t n_alive = 1;
 	for (int i = 0; i < n; i++)
 	{
@@ -195,18 +195,24 @@ std::vector<Tet> bowyer_watson(const std::vector<Vector3>& points, bool use_grid
 			{
 				std::array<int, 3> key = { tri[0], tri[1], tri[2] };
 				std::sort(key.begin(), key.end());
-				faces[key]++;
+				faces.push_back(key);
 			}
 			tets[t].alive = false;
 		}
 		n_alive -= bad.size();
-		for (const auto& kv : faces)
-			if (kv.second == 1)   // boundary of the cavity
+		std::sort(faces.begin(), faces.end());   // new tets are made in ascending face order
+		for (size_t a = 0; a < faces.size();)
+		{
+			size_t b = a + 1;
+			while (b < faces.size() && faces[b] == faces[a]) b++;
+			if (b - a == 1)   // boundary of the cavity
 			{
-				tets.push_back(make(kv.first[0], kv.first[1], kv.first[2], i));
+				tets.push_back(make(faces[a][0], faces[a][1], faces[a][2], i));
 				if (use_grid) grid.add((int)tets.size() - 1, tets.back());
 				n_alive++;
 			}
+			a = b;
+		}
 		if (tets.size() > 4096 && tets.size() > 8 * n_alive)
 		{
 			tets.erase(std::remove_if(tets.begin(), tets.end(), [](const Tet& t) { return !t.alive; }), tets.end());
