@@ -1,0 +1,131 @@
+// k3_emu.cpp -- TEST INFRASTRUCTURE: the small tier of K3 (sub_clip_by_planes<32>, surtr_b200/csrc/clip_sub.cuh) and the
+// K4 moments (sub_fragment_moments<16>, two fragments per warp in lock step, as assemble_gather_kernel runs them) compiled
+// for the HOST over the SIMT shim, behind a flat C interface for tests/test_k3_emulation.py.  The staging of a pair
+// into the shared-memory image and the write-out by rank in the live mask restate the few lines of clip_sub_kernel /
+// assemble_gather_kernel around those calls (surtr_b200/csrc/kernels.cuh).
+#include "simt_shim.h"
+
+#include <memory>
+
+#define __noinline__ __attribute__((noinline))
+#include "../../surtr_b200/csrc/clip_sub.cuh"
+#undef __noinline__
+
+using namespace surtr;
+
+extern "C"
+{
+// One (piece, plane list) pair through the device code of the small tier.
+//   verts4[nv_in][4], ring_off[nv_in + 1] (relative to ring[0]), ring[...]: the piece;  planes4[npl][4]: the cell.
+//   out_verts4[64][4], out_ring_off[65], out_ring[512]: the fragment, numbered as the kernel writes it.
+//   out_info[8]: status (0 ok, 2 overflow = the pair would go to the large tier), nv, ne, sequential cuts, cuts,
+//                collectives executed, n_faces, 0.
+//   out_volume[1], out_centroid[3], out_inertia[6]: the K4 record fields (only when nv > 0).
+int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in, const float* planes4, int npl,
+               float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring, int* out_info, double* out_volume, float* out_centroid,
+               float* out_inertia)
+{
+    for (int k = 0; k < 8; k++) out_info[k] = 0;
+    auto sp = std::make_unique<SubPoly>();
+    bool bad = nv_in > 64;
+    if (!bad)
+        for (int v = 0; v < nv_in; v++)   // clip_sub_kernel, staging (kernels.cuh): positions + one ring word per vertex
+        {
+            const int d = (int)(ring_off[v + 1] - ring_off[v]);
+            sp->x[v] = verts4[4 * v]; sp->y[v] = verts4[4 * v + 1]; sp->z[v] = verts4[4 * v + 2];
+            u64 rw = ~0ull;
+            if (d > 8 || d == 0) bad = true;
+            else
+                for (int j = 0; j < d; j++)
+                {
+                    const int idx = ring[ring_off[v] + j];
+                    bad = bad || idx >= nv_in;
+                    rw = rset(rw, j, idx);
+                }
+            sp->ring[v] = rw;
+        }
+    if (bad) { out_info[0] = CLIP_OVERFLOW; return 0; }
+
+    std::vector<float4> planes(std::max(npl, 1));
+    for (int p = 0; p < npl; p++) planes[p] = make_float4(planes4[4 * p], planes4[4 * p + 1], planes4[4 * p + 2], planes4[4 * p + 3]);
+
+    CutState cs[32];
+    int nv[32], status[32];
+    unsigned seq[32], cuts[32];
+    const unsigned long n_coll = simt::run_warp([&](int lane) {
+        const Sub<32> sub(lane);
+        nv[lane] = nv_in;
+        seq[lane] = cuts[lane] = 0;
+        status[lane] = sub_clip_by_planes<32>(*sp, cs[lane], nv[lane], planes.data(), npl, sub, true, seq[lane], cuts[lane]);
+    });
+    for (int l = 1; l < 32; l++)   // warp-uniform by construction
+        if (cs[l].live != cs[0].live || cs[l].hi != cs[0].hi || nv[l] != nv[0] || status[l] != status[0] || seq[l] != seq[0])
+            return -1;
+    out_info[0] = status[0];
+    out_info[3] = (int)seq[0];
+    out_info[4] = (int)cuts[0];
+    out_info[5] = (int)n_coll;
+    if (status[0] != CLIP_OK || nv[0] == 0) return 0;
+
+    // write-out of clip_sub_kernel: final number of a live slot = its rank in the live mask
+    const u64 live = cs[0].live;
+    int ne = 0, n = 0;
+    for (int v = 0; v < cs[0].hi; v++)
+    {
+        if (!bit64(live, v)) continue;
+        const int t = rank64(live, v);
+        if (t != n) return -2;
+        out_verts4[4 * t] = sp->x[v]; out_verts4[4 * t + 1] = sp->y[v]; out_verts4[4 * t + 2] = sp->z[v]; out_verts4[4 * t + 3] = 0.f;
+        out_ring_off[t] = (uint32_t)ne;
+        const u64 rw = sp->ring[v];
+        const int d = rdeg(rw);
+        for (int j = 0; j < d; j++)
+        {
+            const int nb = rget(rw, j);
+            if (nb >= 64 || !bit64(live, nb)) return -3;   // a ring entry that points at a dead slot
+            out_ring[ne++] = (uint16_t)rank64(live, nb);
+        }
+        n++;
+    }
+    out_ring_off[n] = (uint32_t)ne;
+    if (n != nv[0]) return -4;
+    out_info[1] = n;
+    out_info[2] = ne;
+
+    // K4 (assemble_gather_kernel, tier 1): the fragment is rebuilt in shared memory numbered 0..nv-1 and its face count,
+    // volume, centroid and inertia come from sub_fragment_moments<16>, two fragments per warp in lock step.  Both halves
+    // of the emulated warp get this fragment; they must agree.
+    auto mp = std::make_unique<MomPoly[]>(2);
+    for (int h = 0; h < 2; h++)
+        for (int v = 0; v < n; v++)
+        {
+            mp[h].x[v] = out_verts4[4 * v]; mp[h].y[v] = out_verts4[4 * v + 1]; mp[h].z[v] = out_verts4[4 * v + 2];
+            u64 rw = ~0ull;
+            const int r0 = (int)out_ring_off[v], r1 = (int)out_ring_off[v + 1];
+            for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, out_ring[r0 + j]);
+            mp[h].ring[v] = rw;
+        }
+    Moments mo[32];
+    simt::run_warp([&](int lane) {
+        const Sub<16> sub(lane);
+        CutState c;
+        c.hi = n;
+        c.live = lowmask64(n);
+        c.c = c.k = 0ull;
+        if (sub.any_warp(true))
+        {
+            sub.sync();
+            sub_fragment_moments<16>(mp[lane / 16], c, sub, true, mo[lane]);
+        }
+    });
+    for (int l = 1; l < 32; l++)
+        if (std::memcmp(&mo[l].volume, &mo[0].volume, 8) || mo[l].n_faces != mo[0].n_faces || std::memcmp(&mo[l].cx, &mo[0].cx, 12) ||
+            std::memcmp(mo[l].inertia, mo[0].inertia, 24))
+            return -5;
+    out_info[6] = mo[0].n_faces;
+    *out_volume = mo[0].volume;
+    out_centroid[0] = mo[0].cx; out_centroid[1] = mo[0].cy; out_centroid[2] = mo[0].cz;
+    for (int k = 0; k < 6; k++) out_inertia[k] = mo[0].inertia[k];
+    return 0;
+}
+}

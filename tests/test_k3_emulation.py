@@ -1,0 +1,186 @@
+"""The DEVICE code of the hot path checked WITHOUT a GPU: surtr_b200/csrc/clip_sub.cuh (K3's small tier,
+sub_clip_by_planes<32>, and K4's sub_fragment_moments<16>) is compiled for the host over a SIMT shim (tests/emu/: 32
+lanes as coroutines that meet at every warp collective) and run pair by pair against the committed outputs of the
+reference build and against the oracle port -- bitwise, like the GPU parity tests.  This is test infrastructure: it
+executes the kernel SOURCE on the CPU to catch a regression before GPU time is spent; the product never uses it
+(surtr_b200/ has no CPU path) and the -m gpu tests remain the parity proof for the compiled kernels."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from common import GOLDEN, bits
+from oracle import portapi as P
+from test_oracle_port import load_polyset
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU, "_build", "libk3emu.so")
+SRC = [os.path.join(EMU, "k3_emu.cpp"), os.path.join(EMU, "simt_shim.h")] + \
+      [os.path.join(HERE, "..", "surtr_b200", "csrc", f) for f in ("clip_sub.cuh", "clip_warp.cuh", "surtr_math.cuh")]
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found (vector types for the host compile)")
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRC):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                            "-I", CUDA_INC, SRC[0], "-o", LIB], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    lib = C.CDLL(LIB)
+    lib.k3emu_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Out:
+    def __init__(self):
+        self.verts = np.zeros((64, 4), np.float32)
+        self.ring_off = np.zeros(65, np.uint32)
+        self.ring = np.zeros(512, np.uint16)
+        self.info = np.zeros(8, np.int32)
+        self.volume = np.zeros(1, np.float64)
+        self.centroid = np.zeros(3, np.float32)
+        self.inertia = np.zeros(6, np.float32)
+
+
+def run_pair(lib, ps, p, planes):
+    """Piece p of the PolySet through the emulated kernels.  Returns (status, Out)."""
+    v0, v1 = int(ps.vert_off[p]), int(ps.vert_off[p + 1])
+    r0, r1 = int(ps.ring_off[v0]), int(ps.ring_off[v1])
+    verts = np.ascontiguousarray(ps.verts[v0:v1], np.float32)
+    roff = np.ascontiguousarray(ps.ring_off[v0:v1 + 1] - r0, np.uint32)
+    ring = np.ascontiguousarray(ps.ring[r0:r1], np.uint16)
+    planes = np.ascontiguousarray(planes, np.float32).reshape(-1, 4)
+    o = Out()
+    rc = lib.k3emu_pair(_p(verts), _p(roff), _p(ring), v1 - v0, _p(planes), len(planes), _p(o.verts), _p(o.ring_off), _p(o.ring),
+                        _p(o.info), _p(o.volume), _p(o.centroid), _p(o.inertia))
+    assert rc == 0, f"emulation inconsistency {rc}"
+    return int(o.info[0]), o
+
+
+def check_against(want, i, o):
+    """Emulated fragment == fragment i of the expected PolySet, bit for bit."""
+    v0, v1 = int(want.vert_off[i]), int(want.vert_off[i + 1])
+    nv, ne = int(o.info[1]), int(o.info[2])
+    assert nv == v1 - v0, "vertex count"
+    assert np.array_equal(bits(o.verts[:nv, :3]), bits(want.verts[v0:v1, :3])), "vertex positions (bitwise)"
+    r0 = int(want.ring_off[v0])
+    assert np.array_equal(o.ring_off[:nv + 1], want.ring_off[v0:v1 + 1] - r0), "ring offsets"
+    assert np.array_equal(o.ring[:ne], want.ring[r0:r0 + ne]), "rings"
+    assert int(o.info[6]) == int(want.nfaces[i]), "face count"
+    if want.volume is not None:
+        assert bits(o.volume)[0] == bits(want.volume[i:i + 1])[0], "volume (bitwise)"
+        assert np.array_equal(bits(o.centroid), bits(want.centroid[i])), "centroid (bitwise)"
+
+
+def run_event(lib, pieces, planes, plane_off, want, stats):
+    index = {(int(c), int(p)): i for i, (c, p) in enumerate(zip(want.cell, want.piece))}
+    seen = 0
+    for c in range(len(plane_off) - 1):
+        pl = planes[int(plane_off[c]):int(plane_off[c + 1])]
+        for p in range(pieces.n):
+            status, o = run_pair(lib, pieces, p, pl)
+            stats["pairs"] += 1
+            stats["seq_cuts"] += int(o.info[3])
+            stats["cuts"] += int(o.info[4])
+            if status != 0:
+                stats["overflow"] += 1      # the pair belongs to the large tier: not this code
+                seen += (c, p) in index
+                continue
+            if (c, p) in index:
+                assert o.info[1] > 0, f"pair ({c}, {p}) lost its fragment"
+                check_against(want, index[(c, p)], o)
+                seen += 1
+            else:
+                assert o.info[1] == 0, f"pair ({c}, {p}) produced a fragment the reference does not have"
+    assert seen == want.n
+
+
+@pytest.mark.parametrize("name", ["cube_x64", "pieces200_x32"])
+def test_emulated_kernels_on_reference_fixtures(emu, name):
+    """Committed outputs of the REFERENCE build (tests/golden/make_golden.py): every (piece, cell) pair of the event."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, pieces, cells.planes, cells.plane_off, want, stats)
+    assert stats["pairs"] == pieces.n * cells.n and stats["overflow"] == 0 and stats["cuts"] > 5 * want.n
+
+
+def test_emulated_kernels_on_degenerate_cuts(emu):
+    """Planes through vertices, along edges and coincident with faces (the in-plane band, the sequential replay, the
+    degree-2 splice, the all-in-plane box test): expected = the reference build's output."""
+    d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+    pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, pieces, d["planes"], d["plane_off"], want, stats)
+    assert stats["seq_cuts"] > 100 and stats["overflow"] == 0
+
+
+def test_emulated_kernels_against_the_oracle_port(emu):
+    """Config-4-shaped pairs (Voronoi pieces x Voronoi cells) and config 2's first cells against the oracle port, plus
+    the lazy compaction: a 40-plane cell drives the slot counter past 64 and forces the in-kernel renumbering."""
+    pieces, cells = common.voronoi(1234, 150), common.voronoi(46354, 24)
+    want = P.apply_fracture(pieces, cells.planes, cells.plane_off)
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, pieces, cells.planes, cells.plane_off, want, stats)
+    assert stats["overflow"] == 0
+
+    cube = common.unit_cube()
+    big = common.voronoi(46354, 4096)
+    sel = np.argsort(-np.diff(big.plane_off.astype(np.int64)))[:48]      # the cells with the most planes
+    planes = np.concatenate([big.planes[big.plane_off[c]:big.plane_off[c + 1]] for c in sel])
+    off = np.concatenate([[0], np.cumsum([big.plane_off[c + 1] - big.plane_off[c] for c in sel])]).astype(np.uint32)
+    want = P.apply_fracture(cube, planes, off)
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, cube, planes, off, want, stats)
+    assert want.n == 48 and stats["cuts"] > 48 * 20
+
+
+def test_shim_collectives():
+    """The shim's own semantics on a known case: widths, segment boundaries and byte intrinsics are what CUDA documents."""
+    src = os.path.join(EMU, "_build", "shim_selftest.cpp")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    open(src, "w").write(r'''
+#include "../simt_shim.h"
+int main()
+{
+    unsigned ballots[32]; int up[32], xr[32], idx[32], mx[32];
+    simt::run_warp([&](int lane) {
+        ballots[lane] = __ballot_sync(0xffffffffu, lane % 3 == 0);
+        up[lane] = __shfl_up_sync(0xffffffffu, lane, 2, 16);
+        xr[lane] = __shfl_xor_sync(0xffffffffu, lane, 4, 16);
+        idx[lane] = __shfl_sync(0xffffffffu, lane * 10, 5, 16);
+        if (lane & 1) __syncwarp(); else __syncwarp();
+        mx[lane] = __reduce_max_sync(0xffffffffu, lane ^ 21);
+    });
+    for (int l = 0; l < 32; l++)
+    {
+        if (ballots[l] != 0x49249249u) return 1;
+        if (up[l] != ((l & 15) >= 2 ? l - 2 : l)) return 2;
+        if (xr[l] != (l ^ 4)) return 3;
+        if (idx[l] != ((l & 16) | 5) * 10) return 4;
+        if (mx[l] != 31) return 5;
+    }
+    if (__byte_perm(0x33221100u, 0x77665544u, 0x6u) != 0x00000066u) return 6;      /* byte 6, then byte 0 three times */
+    if (__byte_perm(0x33221100u, 0x77665544u, 0x3210u) != 0x33221100u) return 7;
+    if (__vcmpeq4(0x11223344u, 0x11AA33BBu) != 0xff00ff00u) return 8;
+    if (__ffs(0) != 0 || __ffs(8) != 4 || __clzll(0) != 64 || __clzll(1) != 63 || __popcll(~0ull) != 64) return 9;
+    return 0;
+}
+''')
+    exe = os.path.join(EMU, "_build", "shim_selftest")
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", CUDA_INC, src, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([exe]).returncode == 0
