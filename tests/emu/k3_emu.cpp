@@ -1,3 +1,5 @@
+// (second entry point below: the large / unbounded tier, global_clip_by_planes<NW> + global_fragment_moments<NW> of
+// clip_global.cuh, as a block of NW warps -- NW = 4 is clip_shared_kernel, NW = 8 clip_global_kernel, NW = 1 one warp)
 // k3_emu.cpp -- TEST INFRASTRUCTURE: the small tier of K3 (sub_clip_by_planes<32>, surtr_b200/csrc/clip_sub.cuh) and the
 // K4 moments (sub_fragment_moments<16>, two fragments per warp in lock step, as assemble_gather_kernel runs them) compiled
 // for the HOST over the SIMT shim, behind a flat C interface for tests/test_k3_emulation.py.  The staging of a pair
@@ -9,6 +11,7 @@
 
 #define __noinline__ __attribute__((noinline))
 #include "../../surtr_b200/csrc/clip_sub.cuh"
+#include "../../surtr_b200/csrc/clip_global.cuh"
 #undef __noinline__
 
 using namespace surtr;
@@ -128,4 +131,83 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     for (int k = 0; k < 6; k++) out_inertia[k] = mo[0].inertia[k];
     return 0;
 }
+}
+
+namespace
+{
+template <int NW>
+int run_large(const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in, const float* planes4, int npl, int cap,
+              float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring, int* out_info, double* out_volume, float* out_centroid,
+              float* out_inertia)
+{
+    constexpr int N = NW * 32;
+    for (int k = 0; k < 8; k++) out_info[k] = 0;
+    std::vector<float4> ws((global_poly_bytes((size_t)cap) + 15) / 16 + 1);          // 16-byte aligned workspace
+    GlobalPoly g0 = global_poly_carve(reinterpret_cast<unsigned char*>(ws.data()), cap);
+    bool bad = nv_in > cap;
+    if (!bad)
+        for (int v = 0; v < nv_in; v++)   // staging of clip_shared_kernel / clip_global_kernel (kernels.cuh)
+        {
+            g0.x[v] = verts4[4 * v]; g0.y[v] = verts4[4 * v + 1]; g0.z[v] = verts4[4 * v + 2];
+            const int d = (int)(ring_off[v + 1] - ring_off[v]);
+            if (d > GD || d == 0) { bad = true; continue; }
+            g0.deg[v] = (uint8_t)d;
+            for (int j = 0; j < d; j++)
+            {
+                const int idx = ring[ring_off[v] + j];
+                if (idx >= nv_in) bad = true;
+                g0.ring[(size_t)v * GD + j] = (uint16_t)idx;
+            }
+        }
+    if (bad) { out_info[0] = nv_in > cap ? CLIP_NEED_SLOTS : CLIP_OVERFLOW; return 0; }
+    std::vector<float4> planes(std::max(npl, 1));
+    for (int p = 0; p < npl; p++) planes[p] = make_float4(planes4[4 * p], planes4[4 * p + 1], planes4[4 * p + 2], planes4[4 * p + 3]);
+
+    int s_scan[NW + 1] = { 0 };
+    float s_cov[NW * 10] = { 0.f };
+    std::vector<int> nv(N), status(N);
+    std::vector<unsigned> seq(N, 0u);
+    std::vector<Moments> mo(N);
+    const unsigned long n_coll = simt::run_block(N, [&](int tid) {
+        GlobalPoly g = g0;                                  // every thread holds its own views, as in the kernels
+        const Grp<NW> grp{ tid, tid & 31, s_scan };
+        nv[tid] = nv_in;
+        status[tid] = global_clip_by_planes<NW>(g, nv[tid], planes.data(), npl, grp, seq[tid]);
+        if (status[tid] == CLIP_OK && nv[tid] > 0) global_fragment_moments<NW>(g, nv[tid], grp, mo[tid], s_cov);
+    });
+    for (int t = 1; t < N; t++)
+        if (nv[t] != nv[0] || status[t] != status[0]) return -1;
+    out_info[0] = status[0];
+    out_info[3] = (int)seq[0];
+    out_info[5] = (int)n_coll;
+    if (status[0] != CLIP_OK || nv[0] == 0) return 0;
+    int ne = 0;
+    for (int v = 0; v < nv[0]; v++)   // the tiers compact after every cut: the result is vertices 0 .. nv-1 of the workspace
+    {
+        out_verts4[4 * v] = g0.x[v]; out_verts4[4 * v + 1] = g0.y[v]; out_verts4[4 * v + 2] = g0.z[v]; out_verts4[4 * v + 3] = 0.f;
+        out_ring_off[v] = (uint32_t)ne;
+        for (int j = 0; j < g0.deg[v]; j++) out_ring[ne++] = g0.ring[(size_t)v * GD + j];
+    }
+    out_ring_off[nv[0]] = (uint32_t)ne;
+    out_info[1] = nv[0];
+    out_info[2] = ne;
+    out_info[6] = mo[0].n_faces;       // thread 0 writes the record in the kernels
+    *out_volume = mo[0].volume;
+    out_centroid[0] = mo[0].cx; out_centroid[1] = mo[0].cy; out_centroid[2] = mo[0].cz;
+    for (int k = 0; k < 6; k++) out_inertia[k] = mo[0].inertia[k];
+    return 0;
+}
+} // namespace
+
+extern "C" int k3emu_pair_large(int nw, int cap, const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in,
+                                const float* planes4, int npl, float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring,
+                                int* out_info, double* out_volume, float* out_centroid, float* out_inertia)
+{
+    switch (nw)
+    {
+    case 1: return run_large<1>(verts4, ring_off, ring, nv_in, planes4, npl, cap, out_verts4, out_ring_off, out_ring, out_info, out_volume, out_centroid, out_inertia);
+    case 4: return run_large<4>(verts4, ring_off, ring, nv_in, planes4, npl, cap, out_verts4, out_ring_off, out_ring, out_info, out_volume, out_centroid, out_inertia);
+    case 8: return run_large<8>(verts4, ring_off, ring, nv_in, planes4, npl, cap, out_verts4, out_ring_off, out_ring, out_info, out_volume, out_centroid, out_inertia);
+    default: return -9;
+    }
 }

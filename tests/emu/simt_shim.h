@@ -2,7 +2,7 @@
 // and the K4 moments) on the HOST, one warp at a time, so that the kernel source itself can be checked against the
 // oracle without a GPU (tests/test_k3_emulation.py).
 //
-// The 32 lanes of a warp are 32 ucontext coroutines on one OS thread.  A lane runs until it reaches a warp collective
+// The threads of a block (one warp, or several for the block-per-pair tiers) are ucontext coroutines on one OS thread.  A lane runs until it reaches a warp collective
 // (__ballot_sync, __shfl_*_sync, __any_sync, __reduce_max_sync, __syncwarp -- the kernels only ever use the full member
 // mask), deposits its operand and yields; when all 32 lanes have arrived at the SAME collective they are resumed and
 // each reads what it needs from the deposited operands.  Between two collectives the lanes therefore run one after the
@@ -36,29 +36,33 @@
 namespace simt
 {
 constexpr int WARP = 32;
-enum Kind : int { K_NONE, K_SYNC, K_BALLOT, K_ANY, K_SHFL, K_SHFL_UP, K_SHFL_XOR, K_REDUCE_MAX };
+enum Kind : int { K_NONE, K_SYNC, K_BALLOT, K_ANY, K_SHFL, K_SHFL_UP, K_SHFL_XOR, K_REDUCE_MAX, K_SYNCTHREADS, K_SYNCTHREADS_OR };
+enum Scope : int { S_WARP, S_BLOCK };
 
-struct Warp
+struct Block
 {
+    int n = 0;                                  // threads (a multiple of 32)
     ucontext_t sched;
-    ucontext_t lane[WARP];
-    std::vector<char> stack[WARP];
-    bool done[WARP];
+    std::vector<ucontext_t> ctx;
+    std::vector<std::vector<char>> stack;
+    std::vector<char> done, waiting;
+    std::vector<int> kind, scope;
+    std::vector<uint64_t> op;                   // operand deposited by a waiting thread
+    std::vector<uint64_t> wsnap;                // [warp][32] operands of the warp collective just released
+    std::vector<uint64_t> bsnap;                // [n] operands of the block collective just released
     int cur = 0;
-    unsigned long seq[WARP];      // collectives this lane has arrived at
-    uint64_t buf[2][WARP];        // operands, double buffered by collective parity
-    int kind[2][WARP];
     unsigned long n_collectives = 0;
     std::function<void(int)> body;
 };
 
-inline Warp*& current()
+inline Block*& current()
 {
-    static thread_local Warp* w = nullptr;
-    return w;
+    static thread_local Block* b = nullptr;
+    return b;
 }
 
-inline int lane_id() { return current()->cur; }
+inline int thread_id() { return current()->cur; }
+inline int lane_id() { return current()->cur & 31; }
 
 [[noreturn]] inline void die(const char* msg)
 {
@@ -66,66 +70,109 @@ inline int lane_id() { return current()->cur; }
     std::abort();
 }
 
-// deposit an operand, wait for the other 31 lanes, return the slot parity to read from
-inline int arrive(int kind, uint64_t operand)
+// deposit an operand and wait until every thread of the scope (the caller's warp, or the block) has arrived
+inline void arrive(int scope, int kind, uint64_t operand)
 {
-    Warp& w = *current();
-    const int l = w.cur;
-    const int par = (int)(w.seq[l] & 1ul);
-    w.buf[par][l] = operand;
-    w.kind[par][l] = kind;
-    w.seq[l]++;
-    swapcontext(&w.lane[l], &w.sched);
-    return par;
+    Block& b = *current();
+    const int t = b.cur;
+    b.op[t] = operand;
+    b.kind[t] = kind;
+    b.scope[t] = scope;
+    b.waiting[t] = 1;
+    swapcontext(&b.ctx[t], &b.sched);
 }
+inline const uint64_t* warp_operands() { return current()->wsnap.data() + (size_t)(current()->cur >> 5) * WARP; }
+inline const uint64_t* block_operands() { return current()->bsnap.data(); }
 
 inline void trampoline()
 {
-    Warp& w = *current();
-    const int l = w.cur;
-    w.body(l);
-    w.done[l] = true;
-    swapcontext(&w.lane[l], &w.sched);
+    Block& b = *current();
+    const int t = b.cur;
+    b.body(t);
+    b.done[t] = 1;
+    swapcontext(&b.ctx[t], &b.sched);
 }
 
-// Runs body(lane) for the 32 lanes of one warp in lock step at the collectives.  Returns the number of collectives.
-inline unsigned long run_warp(const std::function<void(int)>& body)
+// Runs body(tid) for the n threads of one block.  Threads run one after the other until each waits at a collective
+// (or returns); a warp is released when its 32 lanes wait at the same warp collective, the block when all its threads
+// wait at the same block collective.  Returns the number of collectives released.
+inline unsigned long run_block(int n, const std::function<void(int)>& body)
 {
-    Warp w;
-    w.body = body;
-    Warp* saved = current();
-    current() = &w;
-    for (int l = 0; l < WARP; l++)
+    if (n <= 0 || n % WARP) die("block size must be a positive multiple of 32");
+    Block b;
+    b.n = n;
+    b.body = body;
+    b.ctx.resize(n); b.stack.resize(n);
+    b.done.assign(n, 0); b.waiting.assign(n, 0); b.kind.assign(n, K_NONE); b.scope.assign(n, S_WARP); b.op.assign(n, 0);
+    b.wsnap.assign(n, 0); b.bsnap.assign(n, 0);
+    Block* saved = current();
+    current() = &b;
+    for (int t = 0; t < n; t++)
     {
-        w.stack[l].resize(256 * 1024);
-        w.done[l] = false;
-        w.seq[l] = 0;
-        getcontext(&w.lane[l]);
-        w.lane[l].uc_stack.ss_sp = w.stack[l].data();
-        w.lane[l].uc_stack.ss_size = w.stack[l].size();
-        w.lane[l].uc_link = nullptr;
-        makecontext(&w.lane[l], (void (*)())trampoline, 0);
+        b.stack[t].resize(192 * 1024);
+        getcontext(&b.ctx[t]);
+        b.ctx[t].uc_stack.ss_sp = b.stack[t].data();
+        b.ctx[t].uc_stack.ss_size = b.stack[t].size();
+        b.ctx[t].uc_link = nullptr;
+        makecontext(&b.ctx[t], (void (*)())trampoline, 0);
     }
     while (true)
     {
+        bool progressed = false;
         int n_done = 0;
-        for (int l = 0; l < WARP; l++)
+        for (int t = 0; t < n; t++)
         {
-            if (w.done[l]) { n_done++; continue; }
-            w.cur = l;
-            swapcontext(&w.sched, &w.lane[l]);
-            if (w.done[l]) n_done++;
+            if (b.done[t]) { n_done++; continue; }
+            if (b.waiting[t]) continue;
+            b.cur = t;
+            swapcontext(&b.sched, &b.ctx[t]);
+            progressed = true;
+            if (b.done[t]) n_done++;
         }
-        if (n_done == WARP) break;
-        if (n_done != 0) die("some lanes returned while others wait at a warp collective");
-        const int par = (int)((w.seq[0] - 1) & 1ul);
-        for (int l = 1; l < WARP; l++)
-            if (w.seq[l] != w.seq[0] || w.kind[par][l] != w.kind[par][0]) die("lanes met at different warp collectives");
-        w.n_collectives++;
+        if (n_done == n) break;
+        // warp collectives
+        for (int w = 0; w < n / WARP; w++)
+        {
+            int waiting = 0, finished = 0;
+            for (int l = 0; l < WARP; l++)
+            {
+                const int t = w * WARP + l;
+                finished += b.done[t];
+                waiting += b.waiting[t] && b.scope[t] == S_WARP;
+            }
+            if (!waiting) continue;
+            if (finished) die("some lanes of a warp returned while others wait at a warp collective");
+            if (waiting != WARP) continue;   // the rest of the warp waits at a block collective or has not run yet
+            for (int l = 1; l < WARP; l++)
+                if (b.kind[w * WARP + l] != b.kind[w * WARP]) die("the lanes of a warp met at different collectives");
+            for (int l = 0; l < WARP; l++)
+            {
+                b.wsnap[(size_t)w * WARP + l] = b.op[w * WARP + l];
+                b.waiting[w * WARP + l] = 0;
+            }
+            b.n_collectives++;
+            progressed = true;
+        }
+        // block collectives
+        {
+            int waiting = 0;
+            for (int t = 0; t < n; t++) waiting += b.waiting[t] && b.scope[t] == S_BLOCK;
+            if (waiting == n)
+            {
+                for (int t = 1; t < n; t++)
+                    if (b.kind[t] != b.kind[0]) die("the threads of a block met at different barriers");
+                for (int t = 0; t < n; t++) { b.bsnap[t] = b.op[t]; b.waiting[t] = 0; }
+                b.n_collectives++;
+                progressed = true;
+            }
+            else if (waiting && n_done) die("some threads returned while others wait at __syncthreads");
+        }
+        if (!progressed) die("deadlock: threads wait at collectives that can never complete");
     }
     current() = saved;
-    return w.n_collectives;
+    return b.n_collectives;
 }
+inline unsigned long run_warp(const std::function<void(int)>& body) { return run_block(WARP, body); }
 
 template <class T> inline uint64_t pack(T v)
 {
@@ -150,57 +197,70 @@ inline void require_full(unsigned mask)
 inline void __syncwarp(unsigned mask = 0xffffffffu)
 {
     require_full(mask);
-    simt::arrive(simt::K_SYNC, 0);
+    simt::arrive(simt::S_WARP, simt::K_SYNC, 0);
 }
 inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_BALLOT, pred ? 1u : 0u);
+    simt::arrive(simt::S_WARP, simt::K_BALLOT, pred ? 1u : 0u);
+    const uint64_t* in = simt::warp_operands();
     unsigned b = 0;
-    for (int l = 0; l < simt::WARP; l++) b |= (unsigned)(simt::current()->buf[par][l] & 1u) << l;
+    for (int l = 0; l < simt::WARP; l++) b |= (unsigned)(in[l] & 1u) << l;
     return b;
 }
 inline int __any_sync(unsigned mask, int pred)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_ANY, pred ? 1u : 0u);
+    simt::arrive(simt::S_WARP, simt::K_ANY, pred ? 1u : 0u);
+    const uint64_t* in = simt::warp_operands();
     for (int l = 0; l < simt::WARP; l++)
-        if (simt::current()->buf[par][l]) return 1;
+        if (in[l]) return 1;
     return 0;
 }
 inline int __reduce_max_sync(unsigned mask, int v)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_REDUCE_MAX, simt::pack(v));
-    int m = simt::unpack<int>(simt::current()->buf[par][0]);
-    for (int l = 1; l < simt::WARP; l++) m = std::max(m, simt::unpack<int>(simt::current()->buf[par][l]));
+    simt::arrive(simt::S_WARP, simt::K_REDUCE_MAX, simt::pack(v));
+    const uint64_t* in = simt::warp_operands();
+    int m = simt::unpack<int>(in[0]);
+    for (int l = 1; l < simt::WARP; l++) m = std::max(m, simt::unpack<int>(in[l]));
     return m;
 }
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_SHFL, simt::pack(v));
+    simt::arrive(simt::S_WARP, simt::K_SHFL, simt::pack(v));
     const int me = simt::lane_id();
     const int from = (me & ~(width - 1)) | (src & (width - 1));
-    return simt::unpack<T>(simt::current()->buf[par][from]);
+    return simt::unpack<T>(simt::warp_operands()[from]);
 }
 template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_SHFL_UP, simt::pack(v));
+    simt::arrive(simt::S_WARP, simt::K_SHFL_UP, simt::pack(v));
     const int me = simt::lane_id();
     const int from = me - (int)delta;
     if (from < (me & ~(width - 1))) return v;   // below the segment: the lane keeps its own value
-    return simt::unpack<T>(simt::current()->buf[par][from]);
+    return simt::unpack<T>(simt::warp_operands()[from]);
 }
 template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int width = 32)
 {
     require_full(mask);
-    const int par = simt::arrive(simt::K_SHFL_XOR, simt::pack(v));
+    simt::arrive(simt::S_WARP, simt::K_SHFL_XOR, simt::pack(v));
     const int me = simt::lane_id();
     const int from = me ^ lane_mask;
     if ((from & ~(width - 1)) != (me & ~(width - 1))) return v;
-    return simt::unpack<T>(simt::current()->buf[par][from]);
+    return simt::unpack<T>(simt::warp_operands()[from]);
+}
+// ---- block barriers ----
+inline void __syncthreads() { simt::arrive(simt::S_BLOCK, simt::K_SYNCTHREADS, 0); }
+inline int __syncthreads_or(int pred)
+{
+    simt::arrive(simt::S_BLOCK, simt::K_SYNCTHREADS_OR, pred ? 1u : 0u);
+    const uint64_t* in = simt::block_operands();
+    for (int t = 0; t < simt::current()->n; t++)
+        if (in[t]) return 1;
+    return 0;
 }
 
 // ---- integer / bit intrinsics ----

@@ -35,6 +35,7 @@ def emu():
         assert r.returncode == 0, r.stderr
     lib = C.CDLL(LIB)
     lib.k3emu_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+    lib.k3emu_pair_large.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
     return lib
 
 
@@ -43,27 +44,34 @@ def _p(a):
 
 
 class Out:
-    def __init__(self):
-        self.verts = np.zeros((64, 4), np.float32)
-        self.ring_off = np.zeros(65, np.uint32)
-        self.ring = np.zeros(512, np.uint16)
+    def __init__(self, cap=64, deg=8):
+        self.verts = np.zeros((cap, 4), np.float32)
+        self.ring_off = np.zeros(cap + 1, np.uint32)
+        self.ring = np.zeros(cap * deg, np.uint16)
         self.info = np.zeros(8, np.int32)
         self.volume = np.zeros(1, np.float64)
         self.centroid = np.zeros(3, np.float32)
         self.inertia = np.zeros(6, np.float32)
 
 
-def run_pair(lib, ps, p, planes):
-    """Piece p of the PolySet through the emulated kernels.  Returns (status, Out)."""
+def run_pair(lib, ps, p, planes, tier=None):
+    """Piece p of the PolySet through the emulated kernels.  tier = None: the small tier (one warp, clip_sub.cuh);
+    tier = (warps, vertex slots): the large / unbounded tier of clip_global.cuh as a block of that many warps.
+    Returns (status, Out)."""
     v0, v1 = int(ps.vert_off[p]), int(ps.vert_off[p + 1])
     r0, r1 = int(ps.ring_off[v0]), int(ps.ring_off[v1])
     verts = np.ascontiguousarray(ps.verts[v0:v1], np.float32)
     roff = np.ascontiguousarray(ps.ring_off[v0:v1 + 1] - r0, np.uint32)
     ring = np.ascontiguousarray(ps.ring[r0:r1], np.uint16)
     planes = np.ascontiguousarray(planes, np.float32).reshape(-1, 4)
-    o = Out()
-    rc = lib.k3emu_pair(_p(verts), _p(roff), _p(ring), v1 - v0, _p(planes), len(planes), _p(o.verts), _p(o.ring_off), _p(o.ring),
-                        _p(o.info), _p(o.volume), _p(o.centroid), _p(o.inertia))
+    if tier is None:
+        o = Out()
+        rc = lib.k3emu_pair(_p(verts), _p(roff), _p(ring), v1 - v0, _p(planes), len(planes), _p(o.verts), _p(o.ring_off), _p(o.ring),
+                            _p(o.info), _p(o.volume), _p(o.centroid), _p(o.inertia))
+    else:
+        o = Out(tier[1], 16)
+        rc = lib.k3emu_pair_large(tier[0], tier[1], _p(verts), _p(roff), _p(ring), v1 - v0, _p(planes), len(planes), _p(o.verts),
+                                  _p(o.ring_off), _p(o.ring), _p(o.info), _p(o.volume), _p(o.centroid), _p(o.inertia))
     assert rc == 0, f"emulation inconsistency {rc}"
     return int(o.info[0]), o
 
@@ -83,13 +91,13 @@ def check_against(want, i, o):
         assert np.array_equal(bits(o.centroid), bits(want.centroid[i])), "centroid (bitwise)"
 
 
-def run_event(lib, pieces, planes, plane_off, want, stats):
+def run_event(lib, pieces, planes, plane_off, want, stats, tier=None, cells=None):
     index = {(int(c), int(p)): i for i, (c, p) in enumerate(zip(want.cell, want.piece))}
     seen = 0
-    for c in range(len(plane_off) - 1):
+    for c in (range(len(plane_off) - 1) if cells is None else cells):
         pl = planes[int(plane_off[c]):int(plane_off[c + 1])]
         for p in range(pieces.n):
-            status, o = run_pair(lib, pieces, p, pl)
+            status, o = run_pair(lib, pieces, p, pl, tier)
             stats["pairs"] += 1
             stats["seq_cuts"] += int(o.info[3])
             stats["cuts"] += int(o.info[4])
@@ -103,7 +111,7 @@ def run_event(lib, pieces, planes, plane_off, want, stats):
                 seen += 1
             else:
                 assert o.info[1] == 0, f"pair ({c}, {p}) produced a fragment the reference does not have"
-    assert seen == want.n
+    assert seen == (want.n if cells is None else sum(1 for c in want.cell if int(c) in set(cells)))
 
 
 @pytest.mark.parametrize("name", ["cube_x64", "pieces200_x32"])
@@ -146,6 +154,37 @@ def test_emulated_kernels_against_the_oracle_port(emu):
     assert want.n == 48 and stats["cuts"] > 48 * 20
 
 
+@pytest.mark.parametrize("warps", [1, 4, 8])
+def test_emulated_large_tiers_on_reference_fixtures(emu, warps):
+    """clip_global.cuh (global_clip_by_planes + global_fragment_moments) as one warp, as the four-warp block of
+    clip_shared_kernel and as the eight-warp block of clip_global_kernel: the cube event and the degenerate sequences
+    (this tier has its own sequential patch / splice code) against the reference build's outputs."""
+    d = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
+    cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, pieces, cells.planes, cells.plane_off, want, stats, tier=(warps, 256), cells=range(0, 64, 4))
+    d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+    pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    run_event(emu, pieces, d["planes"], d["plane_off"], want, stats, tier=(warps, 256), cells=range(0, 400, 5))
+    assert stats["overflow"] == 0 and stats["seq_cuts"] > 20
+
+
+def test_emulated_global_tier_on_the_bunny_mesh(emu):
+    """Row f-1: the 2503-vertex non-convex mesh polyhedron x cells of the 32-cell pattern, eight warps per pair and a
+    workspace as the engine sizes it -- expected fragments from the REFERENCE build (bunny_mesh_x32.npz); and the
+    107-vertex ACH in the four-warp large tier against the oracle port."""
+    d = np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz"))
+    mesh, want = load_polyset(d, "mesh_"), load_polyset(d, "frag_")
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(emu, mesh, d["planes"], d["plane_off"], want, stats, tier=(8, 4096), cells=[0, 5, 11, 17, 23, 31])
+    assert stats["overflow"] == 0
+    a = np.load(os.path.join(GOLDEN, "config1_bunny32.npz"))
+    ach = common.PolySet(a["ach_verts"], a["ach_vert_off"], a["ach_ring_off"], a["ach_ring"])
+    want = P.apply_fracture(ach, d["planes"], d["plane_off"])
+    run_event(emu, ach, d["planes"], d["plane_off"], want, stats, tier=(4, 256))
+    assert stats["overflow"] == 0 and want.n > 20
+
+
 def test_shim_collectives():
     """The shim's own semantics on a known case: widths, segment boundaries and byte intrinsics are what CUDA documents."""
     src = os.path.join(EMU, "_build", "shim_selftest.cpp")
@@ -163,6 +202,21 @@ int main()
         if (lane & 1) __syncwarp(); else __syncwarp();
         mx[lane] = __reduce_max_sync(0xffffffffu, lane ^ 21);
     });
+    /* a block of four warps: per-warp collectives interleaved with block barriers */
+    int wsum[128], any[128], shared[4] = { 0, 0, 0, 0 };
+    simt::run_block(128, [&](int tid) {
+        const int w = tid >> 5, l = tid & 31;
+        int v = l;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (l == 0) shared[w] = v + w;
+        __syncthreads();
+        wsum[tid] = shared[0] + shared[1] + shared[2] + shared[3];
+        any[tid] = __syncthreads_or(tid == 77);
+        if (w == 2) __syncwarp();          /* only one warp takes this collective: legal */
+        __syncthreads();
+    });
+    for (int t = 0; t < 128; t++)
+        if (wsum[t] != 4 * 496 + 6 || any[t] != 1) return 10;
     for (int l = 0; l < 32; l++)
     {
         if (ballots[l] != 0x49249249u) return 1;
