@@ -18,6 +18,9 @@ using namespace surtr;
 
 extern "C"
 {
+// Thread order between collectives: 0 ascending, 1 descending, other = seeded random permutation per pass.
+void k3emu_set_schedule(unsigned mode) { simt::schedule() = mode; }
+
 // One (piece, plane list) pair through the device code of the small tier.
 //   verts4[nv_in][4], ring_off[nv_in + 1] (relative to ring[0]), ring[...]: the piece;  planes4[npl][4]: the cell.
 //   out_verts4[64][4], out_ring_off[65], out_ring[512]: the fragment, numbered as the kernel writes it.

@@ -61,6 +61,15 @@ inline Block*& current()
     return b;
 }
 
+// Order in which the runnable threads are resumed between two collectives: 0 = ascending thread id, 1 = descending,
+// any other value = a fresh pseudo-random permutation per pass seeded with it.  Code that is free of races between
+// its barriers gives the same result under every order; a missing __syncwarp / __syncthreads shows up as a difference.
+inline unsigned& schedule()
+{
+    static thread_local unsigned mode = 0;
+    return mode;
+}
+
 inline int thread_id() { return current()->cur; }
 inline int lane_id() { return current()->cur & 31; }
 
@@ -116,12 +125,22 @@ inline unsigned long run_block(int n, const std::function<void(int)>& body)
         b.ctx[t].uc_link = nullptr;
         makecontext(&b.ctx[t], (void (*)())trampoline, 0);
     }
+    std::vector<int> order(n);
+    for (int t = 0; t < n; t++) order[t] = schedule() == 1 ? n - 1 - t : t;
+    unsigned rng = schedule() * 2654435761u + 12345u;
     while (true)
     {
         bool progressed = false;
         int n_done = 0;
-        for (int t = 0; t < n; t++)
+        if (schedule() > 1)
+            for (int i = n - 1; i > 0; i--)   // Fisher-Yates with an xorshift generator
+            {
+                rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
+                std::swap(order[i], order[rng % (unsigned)(i + 1)]);
+            }
+        for (int k = 0; k < n; k++)
         {
+            const int t = order[k];
             if (b.done[t]) { n_done++; continue; }
             if (b.waiting[t]) continue;
             b.cur = t;

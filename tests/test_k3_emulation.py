@@ -185,6 +185,31 @@ def test_emulated_global_tier_on_the_bunny_mesh(emu):
     assert stats["overflow"] == 0 and want.n > 20
 
 
+@pytest.mark.parametrize("schedule", [1, 7, 2026])
+def test_emulated_kernels_do_not_depend_on_the_lane_order(emu, schedule):
+    """Between two collectives the emulated lanes run one after the other; on the GPU they run in any order.  Code whose
+    conflicting shared-memory accesses are all separated by __syncwarp / __syncthreads gives the same result for every
+    order: descending lanes and two random permutations per pass must reproduce the reference fixtures as well (small
+    tier incl. the concurrent ring-byte updates of the vertex insertion, the four-warp and the eight-warp tier)."""
+    emu.k3emu_set_schedule(schedule)
+    try:
+        stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+        d = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
+        cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+        run_event(emu, pieces, cells.planes, cells.plane_off, want, stats)
+        run_event(emu, pieces, cells.planes, cells.plane_off, want, stats, tier=(4, 256), cells=range(0, 64, 8))
+        d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+        pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+        run_event(emu, pieces, d["planes"], d["plane_off"], want, stats, cells=range(0, 400, 3))
+        run_event(emu, pieces, d["planes"], d["plane_off"], want, stats, tier=(8, 256), cells=range(1, 400, 16))
+        d = np.load(os.path.join(GOLDEN, "pieces200_x32.npz"))
+        cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+        run_event(emu, pieces, cells.planes, cells.plane_off, want, stats, cells=[schedule % 32])
+        assert stats["overflow"] == 0 and stats["seq_cuts"] > 30
+    finally:
+        emu.k3emu_set_schedule(0)
+
+
 def test_shim_collectives():
     """The shim's own semantics on a known case: widths, segment boundaries and byte intrinsics are what CUDA documents."""
     src = os.path.join(EMU, "_build", "shim_selftest.cpp")
