@@ -136,6 +136,51 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
 }
 }
 
+// K4's moments for TWO different fragments that share a warp (lanes 0-15 / 16-31 in lock step), as assemble_gather_kernel
+// pairs neighbouring fragments.  n[2] vertices each (<= 64, ring degree <= 8; a fragment with n = 0 idles, `has` false);
+// out: n_faces[2], volume[2], centroid[2][3], inertia[2][6].
+extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* const* ring_off, const uint16_t* const* ring, const int* n,
+                                 int* out_faces, double* out_volume, float* out_centroid, float* out_inertia)
+{
+    auto mp = std::make_unique<MomPoly[]>(2);
+    for (int h = 0; h < 2; h++)
+        for (int v = 0; v < n[h]; v++)
+        {
+            mp[h].x[v] = verts4[h][4 * v]; mp[h].y[v] = verts4[h][4 * v + 1]; mp[h].z[v] = verts4[h][4 * v + 2];
+            u64 rw = ~0ull;
+            const int r0 = (int)ring_off[h][v], r1 = (int)ring_off[h][v + 1];
+            if (r1 - r0 > 8) return -1;
+            for (int j = 0; j < r1 - r0; j++) rw = rset(rw, j, ring[h][r0 + j]);
+            mp[h].ring[v] = rw;
+        }
+    Moments mo[32];
+    simt::run_warp([&](int lane) {
+        const Sub<16> sub(lane);
+        const int h = lane / 16;
+        const bool do_mo = n[h] > 0;
+        if (sub.any_warp(do_mo))     // assemble_gather_kernel: the warp enters when either fragment needs it
+        {
+            sub.sync();
+            CutState c;
+            c.hi = do_mo ? n[h] : 0;
+            c.live = lowmask64(c.hi);
+            c.c = c.k = 0ull;
+            sub_fragment_moments<16>(mp[h], c, sub, do_mo, mo[lane]);
+        }
+    });
+    for (int h = 0; h < 2; h++)
+    {
+        if (n[h] <= 0) continue;
+        for (int l = 1; l < 16; l++)
+            if (std::memcmp(&mo[16 * h + l].volume, &mo[16 * h].volume, 8) || mo[16 * h + l].n_faces != mo[16 * h].n_faces) return -5;
+        out_faces[h] = mo[16 * h].n_faces;
+        out_volume[h] = mo[16 * h].volume;
+        out_centroid[3 * h] = mo[16 * h].cx; out_centroid[3 * h + 1] = mo[16 * h].cy; out_centroid[3 * h + 2] = mo[16 * h].cz;
+        for (int k = 0; k < 6; k++) out_inertia[6 * h + k] = mo[16 * h].inertia[k];
+    }
+    return 0;
+}
+
 namespace
 {
 template <int NW>

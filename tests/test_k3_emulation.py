@@ -185,6 +185,46 @@ def test_emulated_global_tier_on_the_bunny_mesh(emu):
     assert stats["overflow"] == 0 and want.n > 20
 
 
+def test_emulated_moments_of_two_different_fragments_per_warp(emu):
+    """assemble_gather_kernel gives every fragment 16 lanes: two NEIGHBOURING fragments of different size share a warp
+    and run sub_fragment_moments<16> in lock step.  Every consecutive pair of the reference's pieces200_x32 fragments
+    (and a lone last fragment next to an idle half-warp): face count, volume and centroid bitwise; inertia against the
+    oracle's double-precision integral."""
+    d = np.load(os.path.join(GOLDEN, "pieces200_x32.npz"))
+    cells, pieces = load_polyset(d, "cells_"), load_polyset(d, "pieces_")
+    want = P.apply_fracture(pieces, cells.planes, cells.plane_off, inertia=True)
+    ref = load_polyset(d, "frag_")
+    assert np.array_equal(bits(want.volume), bits(ref.volume)) and np.array_equal(want.nfaces, ref.nfaces)
+    emu.k3emu_moments_two.argtypes = [C.c_void_p] * 8
+    pairs = [(i, i + 1) for i in range(0, want.n - 1, 2)] + [(want.n - 1, None), (None, 0)]
+    worst = 0.0
+    for a, b in pairs:
+        vs, ros, rs, ns = [], [], [], []
+        for i in (a, b):
+            if i is None:
+                vs.append(np.zeros((1, 4), np.float32)); ros.append(np.zeros(2, np.uint32)); rs.append(np.zeros(1, np.uint16)); ns.append(0)
+                continue
+            v0, v1 = int(want.vert_off[i]), int(want.vert_off[i + 1])
+            r0, r1 = int(want.ring_off[v0]), int(want.ring_off[v1])
+            vs.append(np.ascontiguousarray(want.verts[v0:v1], np.float32))
+            ros.append(np.ascontiguousarray(want.ring_off[v0:v1 + 1] - r0, np.uint32))
+            rs.append(np.ascontiguousarray(want.ring[r0:r1], np.uint16))
+            ns.append(v1 - v0)
+        ptr = lambda arrs: (C.c_void_p * 2)(*[x.ctypes.data for x in arrs])
+        n = np.asarray(ns, np.int32)
+        faces, vol, cen, ine = np.zeros(2, np.int32), np.zeros(2, np.float64), np.zeros((2, 3), np.float32), np.zeros((2, 6), np.float32)
+        assert emu.k3emu_moments_two(ptr(vs), ptr(ros), ptr(rs), _p(n), _p(faces), _p(vol), _p(cen), _p(ine)) == 0
+        for h, i in enumerate((a, b)):
+            if i is None:
+                continue
+            assert faces[h] == want.nfaces[i] and bits(vol[h:h + 1])[0] == bits(want.volume[i:i + 1])[0], (a, b)
+            assert np.array_equal(bits(cen[h]), bits(want.centroid[i])), (a, b)
+            if want.volume[i] > 1e-9:
+                scale = max(np.abs(want.inertia[i, :3]).max(), 1e-300)
+                worst = max(worst, float(np.abs(ine[h].astype(np.float64) - want.inertia[i]).max() / scale))
+    assert worst < 1e-4
+
+
 @pytest.mark.parametrize("schedule", [1, 7, 2026])
 def test_emulated_kernels_do_not_depend_on_the_lane_order(emu, schedule):
     """Between two collectives the emulated lanes run one after the other; on the GPU they run in any order.  Code whose
