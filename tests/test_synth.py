@@ -41,3 +41,28 @@ def test_algorithmic_bytes_formula():
     po = np.array([0, 5, 12], np.uint32)
     want = (16 * 8 + 4 * 24 + 16 * 5 + 16 * 10 + 4 * 30 + 64) + (16 * 8 + 4 * 24 + 16 * 7 + 16 * 12 + 4 * 36 + 64)
     assert synth.algorithmic_bytes(vo, ro, po, rec) == want
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_lines():
+    """bench.py's clocks object: median SM clock under load, the maximum clock and the throttle reasons seen."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = ["0, 1965, 1965, 412.3, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+               "0, 1950, 1965, 690.1, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+               "0, 1965, 1965, 500.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+               "garbage line", "0, [N/A], 1965, 1, 0, Not Active, Not Active, Not Active, Not Active"]
+    c = s.stop()
+    assert c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0 and c["samples"] == 3 and c["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]
