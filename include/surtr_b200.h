@@ -193,6 +193,11 @@ int surtr_kdop_calc_batch(surtr_ctx* ctx, const float* verts4, const uint32_t* v
  * event and serialise their programmatic dependent launches, so they are off by default. */
 int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms);
 int surtr_set_profiling(surtr_ctx* ctx, int on);
+/* Per-kernel durations of the last event in milliseconds (profiling must have been on; measurement only, SURVEY.md
+ * section 8d): ms8[0] K1 k-DOP extents, [1] K2a broad-phase masks, [2] K2b pair compaction, [3] K3 small tier
+ * (clip_sub_kernel), [4] K3 large + global tiers (0 when not launched), [5] K4 scan, [6] K4 gather, [7] counters to
+ * the host + reset.  CUDA events on the context stream between the launches. */
+int surtr_last_event_phases(surtr_ctx* ctx, float* ms8);
 /* Number of kernels the last surtr_fracture_event launched. */
 /* Measurement helper: FP32 FMA throughput of the device (TFLOP/s) from a register-resident FFMA kernel on the context
  * stream -- the denominator of the secondary (FP32 pipe) roofline in bench.py. */

@@ -992,6 +992,21 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
     }
 }
 
+// Last kernel of an event: the counters go to the host through mapped pinned memory (no copy-engine queueing behind
+// other contexts' downloads) and the control block -- counters, tile tickets, scan flags -- is zeroed for the next event.
+__global__ void __launch_bounds__(256) finish_event_kernel(const Ctl* __restrict__ ctl, Ctl* host_ctl, uint4* zero, unsigned n16)
+{
+    __shared__ Ctl s;
+    if (threadIdx.x == 0) s = *ctl;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        *host_ctl = s;
+        __threadfence_system();
+    }
+    for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // closes the per-vertex ring offsets (ring_off[n_fverts] = n_fring) and the piece tables used by recursion
 __global__ void finish_offsets_kernel(const Ctl* ctl, uint32_t* f_ring_off, uint64_t cap_fverts)
 {

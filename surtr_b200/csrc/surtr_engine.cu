@@ -108,8 +108,12 @@ struct surtr_ctx
     DevBuf wire_p3, wire_c3, wire_f3, wire_flen;   // float3 / u8 staging of the PCIe wire format
     uint64_t cap_frag = 0, cap_fverts = 0, cap_fring = 0;
 
-    Ctl* h_ctl = nullptr;   // pinned
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    Ctl* h_ctl = nullptr;       // pinned + mapped: the event's last kernel writes the counters straight into it
+    Ctl* h_ctl_dev = nullptr;   // device-side alias of h_ctl
+    // [0] start, [NPH] end; with profiling on also the phase boundaries in between (see surtr_last_event_phases)
+    static constexpr int NPH = 8;
+    cudaEvent_t ev[NPH + 1] = {};
+    cudaEvent_t ev_done = nullptr;   // after the counters of the event have reached h_ctl
     int launches = 0;
     uint32_t ctl_layout_a = 0xffffffffu, ctl_layout_b = 0xffffffffu;
     void* ctl_ptr = nullptr;
@@ -294,10 +298,11 @@ int launch_event(surtr_ctx* ctx)
     // K1
     switch (ctx->kdirs)
     {
-    case 3: launch_extents<3>(ctx); launch_masks<3>(ctx); break;
-    case 7: launch_extents<7>(ctx); launch_masks<7>(ctx); break;
-    default: launch_extents<13>(ctx); launch_masks<13>(ctx); break;
+    case 3: launch_extents<3>(ctx); if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], ctx->stream)); launch_masks<3>(ctx); break;
+    case 7: launch_extents<7>(ctx); if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], ctx->stream)); launch_masks<7>(ctx); break;
+    default: launch_extents<13>(ctx); if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], ctx->stream)); launch_masks<13>(ctx); break;
     }
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     // K2 compaction
     if (ctx->n_tiles_a)
     {
@@ -308,7 +313,7 @@ int launch_event(surtr_ctx* ctx)
                    ctx->n_masks, et, st, d_ctl, ctx->cand.as<uint2>(), ctx->cap_cand);
         ctx->launches++;
     }
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[3], ctx->stream));
 
     // K3
     ClipArgs ca;
@@ -339,6 +344,7 @@ int launch_event(surtr_ctx* ctx)
         launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (ctx->tier2_enabled)
     {
         ca.scratch = ctx->scratch2.as<unsigned char>();
@@ -353,7 +359,7 @@ int launch_event(surtr_ctx* ctx)
         launch_pdl(clip_global_kernel, dim3(ctx->num_sm * T3_BLOCKS_PER_SM), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[5], ctx->stream));
 
     // K4
     {
@@ -387,15 +393,20 @@ int launch_event(surtr_ctx* ctx)
         }
         launch_pdl(assemble_scan_kernel, dim3(blocks), dim3(AS_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
         constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
         const uint64_t gblocks = std::max<uint64_t>(1, (std::min(ctx->cap_cand, ctx->cap_frag) + cand_per_block - 1) / cand_per_block);
         launch_pdl(assemble_gather_kernel<GATHER_LANES>, dim3((unsigned)gblocks), dim3(GATHER_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
     }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_ctl, d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemsetAsync(ctl_base, 0, zero_bytes, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    // counters -> mapped host memory and reset for the next event, by a kernel: a D2H copy of 64 bytes would queue on
+    // the copy engine behind megabytes of other contexts' downloads, and the host waits on exactly this read-back
+    finish_event_kernel<<<1, 256, 0, ctx->stream>>>(d_ctl, ctx->h_ctl_dev, reinterpret_cast<uint4*>(ctl_base), (unsigned)(zero_bytes / 16));
     CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[surtr_ctx::NPH], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     ctx->profiled_last = ctx->profile;
     ctx->event_launched = true;
     ctx->event_resolved = false;
@@ -405,14 +416,19 @@ int launch_event(surtr_ctx* ctx)
 int resolve_event(surtr_ctx* ctx)
 {
     if (!ctx->event_launched) return fail(ctx, SURTR_ERR_INVALID, "no fracture event has been launched");
+    CK(cudaSetDevice(ctx->device));   // a re-run allocates and launches: every entry point that lands here may be on another device
     if (ctx->event_resolved)
     {
         if (ctx->copy_pending) { CK(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
         return SURTR_OK;
     }
-    for (int attempt = 0; attempt < 6; attempt++)
+    // Growth reasons surface one after another (candidates, tier 2, tier 3, its workspace up to four doublings, the
+    // fragment arrays): re-run until an event asks for nothing more.  Every re-run strictly enlarges something that is
+    // bounded (by the pair count, 65520 slots, or device memory -> SURTR_ERR_NOMEM), so the bound below is never the
+    // reason a legitimate event fails.
+    for (int attempt = 0; attempt < 64; attempt++)
     {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev_done));
         const Ctl c = *ctx->h_ctl;
         bool grow = false;
         if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
@@ -451,7 +467,19 @@ int resolve_event(surtr_ctx* ctx)
         const int rc = launch_event(ctx);
         if (rc) return rc;
     }
-    return fail(ctx, SURTR_ERR_NOMEM, "buffers still too small after repeated growth");
+    return fail(ctx, SURTR_ERR_NOMEM, "buffers still too small after 64 rounds of growth");
+}
+
+// Event layout of an upload: n_events + 1 offsets, first 0, non-decreasing, last == n.  Checked BEFORE the context is
+// touched, so a rejected call leaves it exactly as it was.
+bool make_layout(const uint32_t* ev_off, uint32_t n_events, uint32_t n, std::vector<uint32_t>& layout)
+{
+    if (ev_off && n_events) layout.assign(ev_off, ev_off + n_events + 1);
+    else layout = { 0u, n };
+    if (layout.front() != 0u || layout.back() != n) return false;
+    for (size_t i = 1; i < layout.size(); i++)
+        if (layout[i] < layout[i - 1]) return false;
+    return true;
 }
 
 int upload(surtr_ctx* ctx, DevBuf& b, const void* src, size_t bytes)
@@ -517,10 +545,12 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming);
-    if (cudaMallocHost(&ctx->h_ctl, sizeof(Ctl)) != cudaSuccess)
+    cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
+    if (cudaHostAlloc(&ctx->h_ctl, sizeof(Ctl), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&ctx->h_ctl_dev, ctx->h_ctl, 0) != cudaSuccess)
     {
         delete ctx;
-        return fail(nullptr, SURTR_ERR_NOMEM, "cudaMallocHost failed");
+        return fail(nullptr, SURTR_ERR_NOMEM, "cudaHostAlloc (mapped) failed");
     }
     cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_ws_bytes());
     *out = ctx;
@@ -543,6 +573,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -586,6 +617,12 @@ static int upload_pieces_impl(surtr_ctx* ctx, const float* verts4, bool packed3,
 {
     if (!ctx) return SURTR_ERR_INVALID;
     if (!vert_off || (vert_off[n_pieces] && (!verts4 || !ring_off || !ring))) return fail(ctx, SURTR_ERR_INVALID, "NULL piece array");
+    std::vector<uint32_t> layout;
+    if (!make_layout(ev_piece_off, n_events, n_pieces, layout))
+        return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off must start at 0, be non-decreasing and end at n_pieces");
+    for (uint32_t i = 0; i < n_pieces; i++)
+        if (vert_off[i + 1] < vert_off[i] || vert_off[i + 1] - vert_off[i] > 65520u)
+            return fail(ctx, SURTR_ERR_INVALID, "vert_off must be non-decreasing and a piece may have at most 65520 vertices (ring entries are 16-bit local indices)");
     CK(cudaSetDevice(ctx->device));
     const uint64_t nv = vert_off[n_pieces];
     const uint64_t ne = nv ? ring_off[nv] : 0;
@@ -601,10 +638,6 @@ static int upload_pieces_impl(surtr_ctx* ctx, const float* verts4, bool packed3,
     for (uint32_t i = 0; i < n_pieces; i++) ctx->max_piece_verts = std::max(ctx->max_piece_verts, vert_off[i + 1] - vert_off[i]);
     // the tile tables depend only on the event layout: an upload of the same shape (the steady state of a caller
     // that streams events) keeps them, and with them the whole upload -> event sequence free of host synchronisation
-    std::vector<uint32_t> layout;
-    if (ev_piece_off && n_events) layout.assign(ev_piece_off, ev_piece_off + n_events + 1);
-    else layout = { 0u, n_pieces };
-    if (layout.back() != n_pieces) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at n_pieces");
     if (layout != ctx->h_ev_piece_off)
     {
         ctx->h_ev_piece_off.swap(layout);
@@ -621,6 +654,9 @@ static int upload_cells_impl(surtr_ctx* ctx, const float* planes4, const uint32_
 {
     if (!ctx) return SURTR_ERR_INVALID;
     if (!plane_off || (plane_off[n_cells] && !planes4)) return fail(ctx, SURTR_ERR_INVALID, "NULL cell array");
+    std::vector<uint32_t> layout;
+    if (!make_layout(ev_cell_off, n_events, n_cells, layout))
+        return fail(ctx, SURTR_ERR_INVALID, "ev_cell_off must start at 0, be non-decreasing and end at n_cells");
     CK(cudaSetDevice(ctx->device));
     const uint64_t np = plane_off[n_cells];
     int rc;
@@ -636,10 +672,6 @@ static int upload_cells_impl(surtr_ctx* ctx, const float* planes4, const uint32_
     }
     ctx->n_cells = n_cells;
     ctx->n_planes = np;
-    std::vector<uint32_t> layout;
-    if (ev_cell_off && n_events) layout.assign(ev_cell_off, ev_cell_off + n_events + 1);
-    else layout = { 0u, n_cells };
-    if (layout.back() != n_cells) return fail(ctx, SURTR_ERR_INVALID, "ev_cell_off does not end at n_cells");
     if (layout != ctx->h_ev_cell_off)
     {
         ctx->h_ev_cell_off.swap(layout);
@@ -871,6 +903,9 @@ int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint
     const surtr_counts c = ctx->last;
     if (c.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
     const uint32_t n = (uint32_t)c.n_fragments;
+    std::vector<uint32_t> layout;
+    if (!make_layout(ev_piece_off, n_events, n, layout))
+        return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off must start at 0, be non-decreasing and end at the fragment count");
     CK(ctx->p_vert_off.reserve(4 * ((size_t)n + 1)));
     fragments_vert_off_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->f_rec.as<surtr_fragment>(), n, (uint32_t)c.n_verts,
                                                                              ctx->p_vert_off.as<uint32_t>());
@@ -886,10 +921,8 @@ int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint
     ctx->n_pieces = n;
     ctx->n_pverts = c.n_verts;
     ctx->n_pring = c.n_ring;
-    if (ev_piece_off && n_events) ctx->h_ev_piece_off.assign(ev_piece_off, ev_piece_off + n_events + 1);
-    else ctx->h_ev_piece_off = { 0u, n };
+    ctx->h_ev_piece_off.swap(layout);
     ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
-    if (ctx->h_ev_piece_off.back() != n) return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off does not end at the fragment count");
     ctx->have_pieces = true;
     ctx->tables_dirty = true;
     ctx->event_launched = false;
@@ -957,12 +990,22 @@ int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms)
     if (!ctx) return SURTR_ERR_INVALID;
     const int rc = resolve_event(ctx);
     if (rc) return rc;
-    if (total_ms) CK(cudaEventElapsedTime(total_ms, ctx->ev[0], ctx->ev[3]));
+    if (total_ms) CK(cudaEventElapsedTime(total_ms, ctx->ev[0], ctx->ev[surtr_ctx::NPH]));
     if (clip_ms)
     {
         *clip_ms = 0.f;
-        if (ctx->profiled_last) CK(cudaEventElapsedTime(clip_ms, ctx->ev[1], ctx->ev[2]));
+        if (ctx->profiled_last) CK(cudaEventElapsedTime(clip_ms, ctx->ev[3], ctx->ev[4]));
     }
+    return SURTR_OK;
+}
+
+int surtr_last_event_phases(surtr_ctx* ctx, float* ms8)
+{
+    if (!ctx || !ms8) return SURTR_ERR_INVALID;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    if (!ctx->profiled_last) return fail(ctx, SURTR_ERR_INVALID, "the last event ran without profiling (surtr_set_profiling)");
+    for (int i = 0; i < surtr_ctx::NPH; i++) CK(cudaEventElapsedTime(ms8 + i, ctx->ev[i], ctx->ev[i + 1]));
     return SURTR_OK;
 }
 

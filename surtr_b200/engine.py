@@ -34,7 +34,7 @@ EXPORTS = [
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
     "surtr_transform_pieces", "surtr_download_pieces", "surtr_measure_fp32_peak",
-    "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
+    "surtr_last_event_phases", "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
 ]
 
 
@@ -95,6 +95,7 @@ def load_library():
     lib.surtr_last_event_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.surtr_last_event_launches.argtypes = [vp]
     lib.surtr_set_profiling.argtypes = [vp, i32]
+    lib.surtr_last_event_phases.argtypes = [vp, vp]
     lib.surtr_kdop_calc_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
@@ -345,6 +346,14 @@ class FractureContext:
         t, c = C.c_float(0), C.c_float(0)
         self._ck(self._lib.surtr_last_event_ms(self._h, C.byref(t), C.byref(c)))
         return t.value, c.value
+
+    PHASES = ("k1_extents", "k2a_masks", "k2b_compact", "k3_clip_small", "k3_clip_large", "k4_scan", "k4_gather", "finish")
+
+    def last_event_phases(self) -> dict:
+        """Per-kernel milliseconds of the last event (needs set_profiling(True) before it was launched)."""
+        ms = (C.c_float * 8)()
+        self._ck(self._lib.surtr_last_event_phases(self._h, ms))
+        return dict(zip(self.PHASES, (float(x) for x in ms)))
 
     def set_profiling(self, on: bool):
         self._ck(self._lib.surtr_set_profiling(self._h, int(on)))

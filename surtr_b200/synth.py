@@ -206,3 +206,72 @@ def algorithmic_flops(pieces_vert_off, plane_off, rec) -> int:
     pl = (plane_off[c + 1] - plane_off[c]).astype(np.int64)
     v_out = rec["n_verts"].astype(np.int64)
     return int(np.sum(6 * pl * (v_in + v_out) // 2 + 13 * 2 * v_out + 84 * np.maximum(2 * v_out - 4, 0)))
+
+
+# ------------------------------------------------------------------------------------------------ batch generation
+def voronoi_cells_batch(ctx, seeds: np.ndarray, set_off: np.ndarray, planes: bool = True):
+    """Voronoi cell sets of MANY seed sets at once (BASELINE config 4: 4096 x (1000 + 64) cells).  Product path only:
+    Delaunay neighbours on the host worker pool (host/DT3D.cpp through hostlib), the container box cut by every cell's
+    bisector half-spaces in ONE GPU event, face planes on the host worker pool (VMACH::PolygonFace semantics).
+    Returns one CellSet holding all sets back to back; set s owns cells [set_off[s], set_off[s+1])."""
+    from . import hostlib
+    seeds = np.ascontiguousarray(seeds, f32).reshape(-1, 3)
+    set_off = np.asarray(set_off, np.uint32)
+    nb_off, nb_local = hostlib.dt3d_neighbors_batch(seeds, set_off)
+    per_seed_base = np.repeat(set_off[:-1].astype(np.int64), np.diff(set_off.astype(np.int64)))
+    nb_idx = (nb_local.astype(np.int64) + np.repeat(per_seed_base, np.diff(nb_off.astype(np.int64)))).astype(np.uint32)
+    cv, cvo, cro, cr = unit_cube()
+    ctx.upload_pieces(cv, cvo, cro, cr)
+    ctx.upload_cells(bisector_planes(seeds, nb_off, nb_idx), nb_off)     # unbounded cells: every pair is clipped
+    ctx.fracture_event()
+    fr = ctx.download()
+    if fr.n != len(seeds):
+        raise RuntimeError("degenerate seed set: some Voronoi cell is empty")
+    if planes:
+        pl, po = hostlib.face_planes(fr.verts, fr.vert_off, fr.ring_off, fr.ring)
+    else:
+        pl, po = np.zeros((0, 4), f32), np.zeros(len(seeds) + 1, np.uint32)
+    return CellSet(fr.verts, fr.vert_off, fr.ring_off, fr.ring, pl, po)
+
+
+def slice_sets(cs: CellSet, c0: int, c1: int) -> CellSet:
+    """Cells [c0, c1) of a CellSet as a CellSet of its own (offsets rebased; views where possible)."""
+    v0, v1 = int(cs.vert_off[c0]), int(cs.vert_off[c1])
+    e0, e1 = int(cs.ring_off[v0]), int(cs.ring_off[v1])
+    has_planes = len(cs.planes) > 0
+    p0, p1 = (int(cs.plane_off[c0]), int(cs.plane_off[c1])) if has_planes else (0, 0)
+    return CellSet(cs.verts[v0:v1], (cs.vert_off[c0:c1 + 1] - np.uint32(v0)).astype(np.uint32),
+                   (cs.ring_off[v0:v1 + 1] - np.uint32(e0)).astype(np.uint32), cs.ring[e0:e1], cs.planes[p0:p1],
+                   (cs.plane_off[c0:c1 + 1] - np.uint32(p0)).astype(np.uint32) if has_planes else np.zeros(c1 - c0 + 1, np.uint32))
+
+
+def config4_events(ctx, event_ids, n_pieces: int = 1000, n_cells: int = 64, chunk: int = 128):
+    """BASELINE config 4 inputs for the given global event ids: event e cuts the Voronoi cells
+    of mt19937(1234 + e) (n_pieces seeds) by the Voronoi cells of mt19937(46354 + e) (n_cells seeds).  Returns
+    (pieces: CellSet without planes, cells: CellSet with planes, ev_piece_off, ev_cell_off)."""
+    parts_p, parts_c = [], []
+    event_ids = list(event_ids)
+    for i in range(0, len(event_ids), chunk):
+        ids = event_ids[i:i + chunk]
+        sp = np.concatenate([seeds_uniform(1234 + e, n_pieces) for e in ids])
+        sc = np.concatenate([seeds_uniform(46354 + e, n_cells) for e in ids])
+        parts_p.append(voronoi_cells_batch(ctx, sp, np.arange(len(ids) + 1, dtype=np.uint32) * n_pieces, planes=False))
+        parts_c.append(voronoi_cells_batch(ctx, sc, np.arange(len(ids) + 1, dtype=np.uint32) * n_cells, planes=True))
+    pieces, cells = concat_sets(parts_p), concat_sets(parts_c)
+    ev_p = (np.arange(len(event_ids) + 1, dtype=np.uint64) * n_pieces).astype(np.uint32)
+    ev_c = (np.arange(len(event_ids) + 1, dtype=np.uint64) * n_cells).astype(np.uint32)
+    return pieces, cells, ev_p, ev_c
+
+
+def concat_sets(parts) -> CellSet:
+    """Concatenate CellSets (offsets shifted)."""
+    if len(parts) == 1:
+        return parts[0]
+    vo, ro, po = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)]
+    for p in parts:
+        vo.append(p.vert_off[1:].astype(np.uint64) + vo[-1][-1])
+        ro.append(p.ring_off[1:].astype(np.uint64) + ro[-1][-1])
+        po.append(p.plane_off[1:].astype(np.uint64) + po[-1][-1])
+    return CellSet(np.concatenate([p.verts for p in parts]), np.concatenate(vo).astype(np.uint32),
+                   np.concatenate(ro).astype(np.uint32), np.concatenate([p.ring for p in parts]),
+                   np.concatenate([p.planes for p in parts]), np.concatenate(po).astype(np.uint32))
