@@ -24,10 +24,13 @@ def _pinned(torch, a: np.ndarray):
 # ------------------------------------------------------------------------------------------------ headline e2e
 def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res, n_my, barrier, allreduce, dist):
     """The whole job through the C ABI with HOST buffers: every pass uploads every event of the rank from pinned host
-    memory (float3 wire format), cuts it and downloads every fragment into pinned host memory.  Batches of
-    --e2e-batch events rotate over --e2e-contexts contexts (own stream + copy stream each): while one batch is cut,
-    the next is uploaded and the previous one is downloaded.  ONE host thread drives it; it blocks only in
-    surtr_download_fragments_packed_async, on the event whose fragments it is about to copy."""
+    memory and downloads every fragment into pinned host memory, ONE blob per direction and batch (surtr_upload_blob /
+    surtr_download_blob_async: float3 wire format; copy rates on these boxes depend strongly on the copy size).
+    Batches of --e2e-batch events rotate over --e2e-contexts contexts (own stream + copy stream each).  The kernels of
+    consecutive batches are ordered by a CUDA event between the contexts' streams (batch i+1's kernels wait for batch
+    i's), its upload is not: so the upload of batch i+1 and the download of batch i-1 run under the kernels of batch i
+    instead of all contexts uploading, computing and downloading in a convoy.  ONE host thread drives it; it blocks
+    only in surtr_download_blob_async, on the event whose fragments it is about to copy."""
     from surtr_b200 import FractureContext, FRAGMENT_DTYPE
     nctx = max(1, args.e2e_contexts)
     est = [torch.cuda.Stream(device=dev) for _ in range(nctx)]
@@ -37,6 +40,7 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
     ev_frags = np.concatenate([b.ev_frags for b in res])
     ev_verts = np.concatenate([b.ev_verts for b in res])
     ev_ring = np.concatenate([b.ev_ring for b in res])
+    al = lambda x: (int(x) + 255) // 256 * 256
 
     class B:
         pass
@@ -46,41 +50,33 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
         b = B()
         b.e0, b.e1 = e0, min(n_my, e0 + args.e2e_batch)
         p, c, evp, evc = batch_views(b.e0, b.e1)
-        b.n_pieces, b.n_cells, b.n_ev = p.n, c.n, b.e1 - b.e0
-        b.evp, b.evc = np.ascontiguousarray(evp), np.ascontiguousarray(evc)
-        b.h_in = {k: _pinned(torch, np.ascontiguousarray(v)) for k, v in dict(
-            pv=p.verts[:, :3], pvo=p.vert_off, pro=p.ring_off, pr=p.ring, planes=c.planes, plane_off=c.plane_off,
-            cverts=c.verts[:, :3], cvo=c.vert_off).items()}
-        nf, nv, nr = int(ev_frags[b.e0:b.e1].sum()), int(ev_verts[b.e0:b.e1].sum()), int(ev_ring[b.e0:b.e1].sum())
-        b.nf, b.nv, b.nr = nf, nv, nr
-        b.h_out = dict(rec=torch.empty(nf * FRAGMENT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True),
-                       verts=torch.empty(nv * 3, dtype=torch.float32, pin_memory=True),
-                       ring_len=torch.empty(nv, dtype=torch.uint8, pin_memory=True),
-                       ring=torch.empty(nr, dtype=torch.int16, pin_memory=True))
-        h2d += sum(t.numel() * t.element_size() for t in b.h_in.values())
-        d2h += sum(t.numel() * t.element_size() for t in b.h_out.values())
+        b.sizes, total = FractureContext.fill_input_blob(None, p, c, evp, evc)
+        b.h_in = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        FractureContext.fill_input_blob(b.h_in.numpy(), p, c, evp, evc)
+        b.nf, b.nv, b.nr = int(ev_frags[b.e0:b.e1].sum()), int(ev_verts[b.e0:b.e1].sum()), int(ev_ring[b.e0:b.e1].sum())
+        b.cap = al(FRAGMENT_DTYPE.itemsize * b.nf) + al(12 * b.nv) + al(b.nv) + al(2 * b.nr)
+        b.h_out = torch.empty(b.cap, dtype=torch.uint8, pin_memory=True)
+        h2d += total
+        d2h += b.cap
         batches.append(b)
 
-    def upload(cx, b):
-        hi = b.h_in
-        cx.upload_pieces3_ptr(hi["pv"].data_ptr(), hi["pvo"].data_ptr(), hi["pro"].data_ptr(), hi["pr"].data_ptr(), b.n_pieces,
-                              b.evp.ctypes.data, b.n_ev)
-        cx.upload_cells3_ptr(hi["planes"].data_ptr(), hi["plane_off"].data_ptr(), hi["cverts"].data_ptr(), hi["cvo"].data_ptr(),
-                             b.n_cells, b.evc.ctypes.data, b.n_ev)
-
     def download(cx, b):
-        ho = b.h_out
-        cx.download_packed_into_async(ho["rec"].data_ptr(), ho["verts"].data_ptr(), ho["ring_len"].data_ptr(), ho["ring"].data_ptr())
+        b.L = cx.download_blob_into_async(b.h_out.data_ptr(), b.cap)
 
     def passes(k):
         pending = [None] * nctx
+        prev_done = None
         for i in range(k * len(batches)):
             b = batches[i % len(batches)]
             s = i % nctx
             if pending[s] is not None:
                 download(ctxs[s], pending[s])
-            upload(ctxs[s], b)
+            ctxs[s].upload_blob_ptr(b.h_in.data_ptr(), b.sizes)
+            if prev_done is not None:
+                est[s].wait_event(prev_done)
             ctxs[s].fracture_event()
+            prev_done = torch.cuda.Event()
+            prev_done.record(est[s])
             pending[s] = b
         for s in range(nctx):
             if pending[s] is not None:
@@ -91,7 +87,7 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
     passes(1)                    # warm-up: every context grows its buffers once
     # single synchronous batch: what one blocking caller sees
     t0 = time.perf_counter()
-    upload(ctxs[0], batches[0]); ctxs[0].fracture_event(); download(ctxs[0], batches[0]); ctxs[0].sync()
+    ctxs[0].upload_blob_ptr(batches[0].h_in.data_ptr(), batches[0].sizes); ctxs[0].fracture_event(); download(ctxs[0], batches[0]); ctxs[0].sync()
     sync_batch_s = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
@@ -108,15 +104,17 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
         fo = vo = ro = 0
         while bi < len(batches) and batches[bi].e1 <= rb.e1:
             b = batches[bi]
-            got = np.frombuffer(b.h_out["rec"].numpy().tobytes(), dtype=FRAGMENT_DTYPE)
+            L, out = b.L, b.h_out.numpy()
+            assert (int(L.n_fragments), int(L.n_verts), int(L.n_ring)) == (b.nf, b.nv, b.nr), "e2e fragment counts differ"
+            got = np.frombuffer(out[L.fragments:L.fragments + 64 * b.nf].tobytes(), dtype=FRAGMENT_DTYPE)
             want = fr.rec[fo:fo + b.nf]
             for f in ("n_verts", "n_faces", "volume", "centroid", "inertia", "n_ring"):
                 assert got[f].tobytes() == want[f].tobytes(), f"e2e fragment records differ from the resident-input result ({f})"
             assert np.array_equal(got["piece"], want["piece"] - np.uint32((b.e0 - rb.e0) * PIECES_PER_EVENT)), "e2e piece ids differ"
             assert np.array_equal(got["cell"], want["cell"] - np.uint32((b.e0 - rb.e0) * CELLS_PER_EVENT)), "e2e cell ids differ"
-            assert b.h_out["verts"].numpy().tobytes() == v3[vo:vo + b.nv].tobytes(), "e2e vertex positions differ"
-            assert np.array_equal(b.h_out["ring_len"].numpy(), rl[vo:vo + b.nv]), "e2e ring lengths differ"
-            assert b.h_out["ring"].numpy().tobytes() == fr.ring[ro:ro + b.nr].tobytes(), "e2e ring entries differ"
+            assert out[L.verts3:L.verts3 + 12 * b.nv].tobytes() == v3[vo:vo + b.nv].tobytes(), "e2e vertex positions differ"
+            assert np.array_equal(out[L.ring_len:L.ring_len + b.nv], rl[vo:vo + b.nv]), "e2e ring lengths differ"
+            assert out[L.ring:L.ring + 2 * b.nr].tobytes() == fr.ring[ro:ro + b.nr].tobytes(), "e2e ring entries differ"
             fo, vo, ro = fo + b.nf, vo + b.nv, ro + b.nr
             bi += 1
         assert fo == fr.n
@@ -137,10 +135,12 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
             "batch_events": args.e2e_batch, "contexts_in_flight": nctx, "batches_per_rank": len(batches),
             "single_sync_batch_ms": 1e3 * sync_batch_s,
             "checked": "every fragment of the last pass (records, float3 positions, ring lengths, ring entries) equals the resident-input result bit for bit",
-            "wire_format": "surtr_upload_pieces3 / surtr_upload_cells3 (float3 vertex streams, widened to float4 on the device) and "
-                           "surtr_download_fragments_packed_async (64-byte records, float3 positions, one byte of ring length per vertex, 16-bit ring entries)",
+            "wire_format": "one blob per direction and batch: surtr_upload_blob (float3 vertex streams, widened to float4 on the device; index arrays "
+                           "used in place) and surtr_download_blob_async (64-byte records, float3 positions, one byte of ring length per vertex, "
+                           "16-bit ring entries, assembled on the device)",
             "timing": f"wall clock (barrier + synchronize on both sides, max over ranks) around K passes of upload + event + download of every "
-                      f"event of the rank, pinned host buffers, batches of {args.e2e_batch} events over {nctx} contexts from one host thread"}
+                      f"event of the rank, pinned host buffers, batches of {args.e2e_batch} events over {nctx} contexts from one host thread, "
+                      "kernels of consecutive batches ordered by a CUDA event"}
 
 
 # ------------------------------------------------------------------------------------------------ DMA ceiling

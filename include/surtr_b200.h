@@ -172,6 +172,31 @@ int surtr_download_fragments_packed(surtr_ctx* ctx, surtr_fragment* fragments, f
                                     uint16_t* ring);
 int surtr_download_fragments_packed_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len,
                                           uint16_t* ring);
+/* One-copy transfers.  Host<->device copy rates on PCIe depend strongly on the size of each copy (measured on the B200
+ * boxes: 4 MB copies reach a third of the rate of 64 MB copies when both directions are busy, profiles/r2_pcie.txt), so
+ * a caller that streams event batches moves ONE blob per direction instead of 8 + 4 arrays.
+ *
+ * Input blob = the arrays of surtr_upload_pieces3 + surtr_upload_cells3 back to back at the byte offsets
+ * surtr_input_blob_layout returns (every section 256-byte aligned; ev_* sections hold n_events + 1 offsets, ignored when
+ * n_events == 0 = one event; n_cell_verts == 0 = unbounded cells).  The blob is copied with one cudaMemcpyAsync on the
+ * context stream (pinned memory for it to be asynchronous; offsets are also read on the host for validation) and the
+ * index arrays are used in place on the device. */
+typedef struct surtr_in_layout {
+    uint64_t verts3, vert_off, ring_off, ring, planes4, plane_off, cell_verts3, cvert_off, ev_piece_off, ev_cell_off, total;
+} surtr_in_layout;
+int surtr_input_blob_layout(uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring, uint32_t n_cells, uint64_t n_planes,
+                            uint64_t n_cell_verts, uint32_t n_events, surtr_in_layout* out);
+int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring,
+                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events);
+/* Output blob = the arrays of surtr_download_fragments_packed (records | float3 positions | one byte of ring length per
+ * vertex | ring entries) at the byte offsets returned in *out, assembled on the device and moved with ONE copy on the
+ * context's copy stream.  Waits for the event (which sizes the blob); SURTR_ERR_INVALID with *out filled in when
+ * `capacity` is too small.  Completion rules as surtr_download_fragments_async. */
+typedef struct surtr_out_layout {
+    uint64_t fragments, verts3, ring_len, ring, total;   /* byte offsets, total size */
+    uint64_t n_fragments, n_verts, n_ring;
+} surtr_out_layout;
+int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity, surtr_out_layout* out);
 int surtr_sync(surtr_ctx* ctx);
 int surtr_device_fragments(surtr_ctx* ctx, surtr_device_view* out);
 

@@ -162,6 +162,40 @@ __global__ void __launch_bounds__(256) widen3_kernel(const float* __restrict__ i
         out4[i] = make_float4(__ldg(in3 + 3 * i), __ldg(in3 + 3 * i + 1), __ldg(in3 + 3 * i + 2), 0.f);
 }
 
+// surtr_upload_blob: both float3 streams of the input blob (pieces, cell vertices) in one launch.
+__global__ void __launch_bounds__(256) widen3x2_kernel(const float* __restrict__ a3, float4* __restrict__ a4, uint64_t na,
+                                                       const float* __restrict__ b3, float4* __restrict__ b4, uint64_t nb)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        if (i < na) a4[i] = make_float4(__ldg(a3 + 3 * i), __ldg(a3 + 3 * i + 1), __ldg(a3 + 3 * i + 2), 0.f);
+        else { const uint64_t j = i - na; b4[j] = make_float4(__ldg(b3 + 3 * j), __ldg(b3 + 3 * j + 1), __ldg(b3 + 3 * j + 2), 0.f); }
+    }
+}
+
+// surtr_download_blob_async: the four fragment arrays into ONE contiguous device blob in the packed wire format
+// (records and ring entries copied, positions narrowed to float3, ring offsets turned into one length byte per vertex).
+__global__ void __launch_bounds__(256) pack_blob_kernel(const uint4* __restrict__ rec16, uint64_t n_rec16, const float4* __restrict__ verts4,
+                                                        const uint32_t* __restrict__ ring_off, uint64_t n_verts,
+                                                        const uint16_t* __restrict__ ring, uint64_t n_ring, uint4* __restrict__ o_rec16,
+                                                        float* __restrict__ o_verts3, uint8_t* __restrict__ o_len, uint16_t* __restrict__ o_ring)
+{
+    const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = t0; i < n_rec16; i += stride) o_rec16[i] = rec16[i];
+    for (uint64_t i = t0; i < n_verts; i += stride)
+    {
+        const float4 v = verts4[i];
+        o_verts3[3 * i] = v.x; o_verts3[3 * i + 1] = v.y; o_verts3[3 * i + 2] = v.z;
+        o_len[i] = (uint8_t)(ring_off[i + 1] - ring_off[i]);
+    }
+    // ring entries: 16 bytes per thread where both sides are aligned (f_ring is a cudaMalloc'd array, the section 256-byte aligned)
+    const uint64_t n8 = n_ring / 8;
+    const uint4* r16 = reinterpret_cast<const uint4*>(ring);
+    uint4* o16 = reinterpret_cast<uint4*>(o_ring);
+    for (uint64_t i = t0; i < n8; i += stride) o16[i] = r16[i];
+    for (uint64_t i = 8 * n8 + t0; i < n_ring; i += stride) o_ring[i] = ring[i];
+}
+
 // PCIe wire format of the fragments (surtr_download_fragments_packed): float3 positions, one byte of ring length per vertex.
 __global__ void __launch_bounds__(256) pack_fragments_kernel(const float4* __restrict__ verts4, const uint32_t* __restrict__ ring_off,
                                                              float* __restrict__ verts3, uint8_t* __restrict__ ring_len, uint64_t n)

@@ -41,12 +41,14 @@ struct DevBuf
 {
     void* p = nullptr;
     size_t cap = 0;
+    bool view = false;   // points into another buffer (a section of the input blob): never freed, never grown in place
     cudaError_t reserve(size_t bytes)
     {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (bytes <= cap && !view) return cudaSuccess;
+        if (p && !view) cudaFree(p);
         p = nullptr;
         cap = 0;
+        view = false;
         const size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
@@ -54,9 +56,17 @@ struct DevBuf
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && !view) cudaFree(p);
         p = nullptr;
         cap = 0;
+        view = false;
+    }
+    void set_view(void* ptr, size_t bytes)
+    {
+        release();
+        p = ptr;
+        cap = bytes;
+        view = true;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -106,6 +116,7 @@ struct surtr_ctx
     // outputs
     DevBuf f_rec, f_verts, f_ring_off, f_ring;
     DevBuf wire_p3, wire_c3, wire_f3, wire_flen;   // float3 / u8 staging of the PCIe wire format
+    DevBuf in_blob, out_blob;                      // one-copy transfers (surtr_upload_blob / surtr_download_blob_async)
     uint64_t cap_frag = 0, cap_fverts = 0, cap_fring = 0;
 
     Ctl* h_ctl = nullptr;       // pinned + mapped: the event's last kernel writes the counters straight into it
@@ -567,7 +578,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
-                      &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
+                      &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->in_blob, &ctx->out_blob, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
                       &ctx->xf_idx };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -759,6 +770,124 @@ static int download_impl(surtr_ctx* ctx, surtr_fragment* fragments, void* verts4
 
 extern "C"
 {
+static inline uint64_t blob_align(uint64_t x) { return (x + 255ull) & ~255ull; }
+
+int surtr_input_blob_layout(uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring, uint32_t n_cells, uint64_t n_planes,
+                            uint64_t n_cell_verts, uint32_t n_events, surtr_in_layout* out)
+{
+    if (!out) return SURTR_ERR_INVALID;
+    uint64_t at = 0;
+    out->verts3 = at;       at = blob_align(at + 12 * n_piece_verts);
+    out->vert_off = at;     at = blob_align(at + 4 * ((uint64_t)n_pieces + 1));
+    out->ring_off = at;     at = blob_align(at + 4 * (n_piece_verts + 1));
+    out->ring = at;         at = blob_align(at + 2 * n_piece_ring);
+    out->planes4 = at;      at = blob_align(at + 16 * n_planes);
+    out->plane_off = at;    at = blob_align(at + 4 * ((uint64_t)n_cells + 1));
+    out->cell_verts3 = at;  at = blob_align(at + 12 * n_cell_verts);
+    out->cvert_off = at;    at = blob_align(at + 4 * ((uint64_t)n_cells + 1));
+    out->ev_piece_off = at; at = blob_align(at + 4 * ((uint64_t)n_events + 1));
+    out->ev_cell_off = at;  at = blob_align(at + 4 * ((uint64_t)n_events + 1));
+    out->total = at;
+    return SURTR_OK;
+}
+
+int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring,
+                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (!blob) return fail(ctx, SURTR_ERR_INVALID, "NULL blob");
+    surtr_in_layout L;
+    surtr_input_blob_layout(n_pieces, n_piece_verts, n_piece_ring, n_cells, n_planes, n_cell_verts, n_events, &L);
+    const unsigned char* h = static_cast<const unsigned char*>(blob);
+    const uint32_t* vert_off = reinterpret_cast<const uint32_t*>(h + L.vert_off);
+    const uint32_t* ring_off = reinterpret_cast<const uint32_t*>(h + L.ring_off);
+    const uint32_t* plane_off = reinterpret_cast<const uint32_t*>(h + L.plane_off);
+    const uint32_t* cvert_off = reinterpret_cast<const uint32_t*>(h + L.cvert_off);
+    // everything is validated against the host copy BEFORE the context is touched
+    std::vector<uint32_t> lp, lc;
+    if (!make_layout(n_events ? reinterpret_cast<const uint32_t*>(h + L.ev_piece_off) : nullptr, n_events, n_pieces, lp) ||
+        !make_layout(n_events ? reinterpret_cast<const uint32_t*>(h + L.ev_cell_off) : nullptr, n_events, n_cells, lc))
+        return fail(ctx, SURTR_ERR_INVALID, "event offsets must start at 0, be non-decreasing and end at the piece / cell count");
+    if (vert_off[n_pieces] != n_piece_verts || (n_piece_verts && ring_off[n_piece_verts] != n_piece_ring) ||
+        plane_off[n_cells] != n_planes || (n_cell_verts && cvert_off[n_cells] != n_cell_verts))
+        return fail(ctx, SURTR_ERR_INVALID, "blob offsets do not match the stated sizes");
+    uint32_t max_verts = 0;
+    for (uint32_t i = 0; i < n_pieces; i++)
+    {
+        if (vert_off[i + 1] < vert_off[i] || vert_off[i + 1] - vert_off[i] > 65520u)
+            return fail(ctx, SURTR_ERR_INVALID, "vert_off must be non-decreasing and a piece may have at most 65520 vertices");
+        max_verts = std::max(max_verts, vert_off[i + 1] - vert_off[i]);
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->in_blob.reserve(std::max<uint64_t>(L.total, 256)));
+    CK(ctx->p_verts.reserve(std::max<size_t>(16 * n_piece_verts, 16)));
+    if (n_cell_verts) CK(ctx->c_verts.reserve(16 * n_cell_verts));
+    // ONE host -> device copy; the float3 streams are widened to the resident float4 arrays, every other array is used in place
+    CK(cudaMemcpyAsync(ctx->in_blob.p, blob, L.total, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned char* d = ctx->in_blob.as<unsigned char>();
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_piece_verts + n_cell_verts + 255) / 256 + 1, (uint64_t)ctx->num_sm * 8);
+    widen3x2_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + L.verts3), ctx->p_verts.as<float4>(), n_piece_verts,
+                                                    reinterpret_cast<const float*>(d + L.cell_verts3), ctx->c_verts.as<float4>(), n_cell_verts);
+    CK(cudaGetLastError());
+    ctx->p_vert_off.set_view(d + L.vert_off, 4 * ((size_t)n_pieces + 1));
+    ctx->p_ring_off.set_view(d + L.ring_off, 4 * (n_piece_verts + 1));
+    ctx->p_ring.set_view(d + L.ring, 2 * n_piece_ring);
+    ctx->c_planes.set_view(d + L.planes4, 16 * n_planes);
+    ctx->c_plane_off.set_view(d + L.plane_off, 4 * ((size_t)n_cells + 1));
+    ctx->c_vert_off.set_view(d + L.cvert_off, 4 * ((size_t)n_cells + 1));
+    ctx->n_pieces = n_pieces;
+    ctx->n_pverts = n_piece_verts;
+    ctx->n_pring = n_piece_ring;
+    ctx->max_piece_verts = max_verts;
+    ctx->n_cells = n_cells;
+    ctx->n_planes = n_planes;
+    ctx->n_cverts = n_cell_verts;
+    ctx->cells_bounded = n_cell_verts != 0;
+    if (lp != ctx->h_ev_piece_off) { ctx->h_ev_piece_off.swap(lp); ctx->tables_dirty = true; }
+    if (lc != ctx->h_ev_cell_off) { ctx->h_ev_cell_off.swap(lc); ctx->tables_dirty = true; }
+    ctx->n_events_p = (uint32_t)ctx->h_ev_piece_off.size() - 1;
+    ctx->n_events_c = (uint32_t)ctx->h_ev_cell_off.size() - 1;
+    ctx->have_pieces = ctx->have_cells = true;
+    ctx->event_launched = false;
+    return SURTR_OK;
+}
+
+int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity, surtr_out_layout* out)
+{
+    if (!ctx || !out) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->event_resolved && ctx->copy_pending) ctx->copy_pending = false;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    const surtr_counts& c = ctx->last;
+    uint64_t at = 0;
+    out->n_fragments = c.n_fragments; out->n_verts = c.n_verts; out->n_ring = c.n_ring;
+    out->fragments = at; at = blob_align(at + sizeof(surtr_fragment) * c.n_fragments);
+    out->verts3 = at;    at = blob_align(at + 12 * c.n_verts);
+    out->ring_len = at;  at = blob_align(at + c.n_verts);
+    out->ring = at;      at = blob_align(at + 2 * c.n_ring);
+    out->total = at;
+    if (!host_blob || capacity < at) return fail(ctx, SURTR_ERR_INVALID, "host blob too small: " + std::to_string(at) + " bytes needed");
+    if (!at) return SURTR_OK;
+    cudaStream_t cs = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
+    CK(ctx->out_blob.reserve(at));
+    unsigned char* d = ctx->out_blob.as<unsigned char>();
+    const uint64_t work = std::max<uint64_t>(c.n_verts, std::max<uint64_t>(c.n_fragments * 4, c.n_ring / 8));
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((work + 255) / 256, (uint64_t)ctx->num_sm * 8));
+    pack_blob_kernel<<<blocks, 256, 0, cs>>>(ctx->f_rec.as<uint4>(), c.n_fragments * (sizeof(surtr_fragment) / 16), ctx->f_verts.as<float4>(),
+                                            ctx->f_ring_off.as<uint32_t>(), c.n_verts, ctx->f_ring.as<uint16_t>(), c.n_ring,
+                                            reinterpret_cast<uint4*>(d + out->fragments), reinterpret_cast<float*>(d + out->verts3),
+                                            d + out->ring_len, reinterpret_cast<uint16_t*>(d + out->ring));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_blob, d, at, cudaMemcpyDeviceToHost, cs));   // ONE device -> host copy
+    if (ctx->copy_stream)
+    {
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        ctx->copy_pending = true;
+    }
+    return SURTR_OK;
+}
+
 int surtr_sync(surtr_ctx* ctx)
 {
     if (!ctx) return SURTR_ERR_INVALID;
@@ -911,6 +1040,8 @@ int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint
                                                                              ctx->p_vert_off.as<uint32_t>());
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->p_ring_off.view) ctx->p_ring_off.release();   // sections of the input blob are never recycled as output arrays
+    if (ctx->p_ring.view) ctx->p_ring.release();
     std::swap(ctx->p_verts, ctx->f_verts);
     std::swap(ctx->p_ring_off, ctx->f_ring_off);
     std::swap(ctx->p_ring, ctx->f_ring);
@@ -1047,6 +1178,8 @@ int surtr_debug_enable(surtr_ctx* ctx, int on)
     ctx->debug = on != 0;
     return SURTR_OK;
 }
+
+void* surtr_debug_copy_stream(surtr_ctx* ctx) { return ctx ? (void*)ctx->copy_stream : nullptr; }
 
 int surtr_debug_read(surtr_ctx* ctx, uint32_t* out, uint64_t n_cand)
 {

@@ -34,7 +34,7 @@ EXPORTS = [
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
     "surtr_transform_pieces", "surtr_download_pieces", "surtr_measure_fp32_peak",
-    "surtr_last_event_phases", "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
+    "surtr_last_event_phases", "surtr_input_blob_layout", "surtr_upload_blob", "surtr_download_blob_async", "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
 ]
 
 
@@ -47,6 +47,15 @@ class SurtrError(RuntimeError):
 class Counts(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_candidates", "n_fragments", "n_verts", "n_ring",
                                           "n_seq_cuts", "n_tier2", "n_tier3")]
+
+
+class InLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("verts3", "vert_off", "ring_off", "ring", "planes4", "plane_off", "cell_verts3",
+                                          "cvert_off", "ev_piece_off", "ev_cell_off", "total")]
+
+
+class OutLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("fragments", "verts3", "ring_len", "ring", "total", "n_fragments", "n_verts", "n_ring")]
 
 
 class DeviceView(C.Structure):
@@ -96,6 +105,10 @@ def load_library():
     lib.surtr_last_event_launches.argtypes = [vp]
     lib.surtr_set_profiling.argtypes = [vp, i32]
     lib.surtr_last_event_phases.argtypes = [vp, vp]
+    u64 = C.c_uint64
+    lib.surtr_input_blob_layout.argtypes = [u32, u64, u64, u32, u64, u64, u32, C.POINTER(InLayout)]
+    lib.surtr_upload_blob.argtypes = [vp, vp, u32, u64, u64, u32, u64, u64, u32]
+    lib.surtr_download_blob_async.argtypes = [vp, vp, u64, C.POINTER(OutLayout)]
     lib.surtr_kdop_calc_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
@@ -293,6 +306,64 @@ class FractureContext:
         ev = _arr(ev_cell_off, np.uint32)
         self._ck(self._lib.surtr_upload_cells3(self._h, _p(planes4), _p(plane_off), _p(cell_verts3), _p(cvert_off),
                                                len(plane_off) - 1, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    # ---- one-copy transfers: one blob per direction (include/surtr_b200.h) ----
+    @staticmethod
+    def input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events) -> InLayout:
+        L = InLayout()
+        load_library().surtr_input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events, C.byref(L))
+        return L
+
+    @staticmethod
+    def fill_input_blob(buf: np.ndarray, pieces, cells, ev_piece_off=None, ev_cell_off=None, bounded=True):
+        """Lays the arrays of one batch out in `buf` (uint8, e.g. a view of pinned memory; None = only size it).
+        pieces / cells: objects with verts, vert_off, ring_off, ring / planes, plane_off, verts, vert_off.
+        Returns (sizes tuple for upload_blob, total bytes)."""
+        n_ev = 0 if ev_piece_off is None else len(ev_piece_off) - 1
+        n_cv = len(cells.verts) if bounded else 0
+        sizes = (len(pieces.vert_off) - 1, len(pieces.verts), len(pieces.ring), len(cells.plane_off) - 1, len(cells.planes), n_cv, n_ev)
+        L = FractureContext.input_blob_layout(*sizes)
+        if buf is None:
+            return sizes, int(L.total)
+
+        def put(off, a, dt):
+            a = np.ascontiguousarray(a, dt).reshape(-1).view(np.uint8)
+            buf[off:off + a.size] = a
+
+        put(L.verts3, np.asarray(pieces.verts)[:, :3], np.float32)
+        put(L.vert_off, pieces.vert_off, np.uint32)
+        put(L.ring_off, pieces.ring_off, np.uint32)
+        put(L.ring, pieces.ring, np.uint16)
+        put(L.planes4, cells.planes, np.float32)
+        put(L.plane_off, cells.plane_off, np.uint32)
+        if n_cv:
+            put(L.cell_verts3, np.asarray(cells.verts)[:, :3], np.float32)
+            put(L.cvert_off, cells.vert_off, np.uint32)
+        if n_ev:
+            put(L.ev_piece_off, ev_piece_off, np.uint32)
+            put(L.ev_cell_off, ev_cell_off, np.uint32)
+        return sizes, int(L.total)
+
+    def upload_blob_ptr(self, blob_ptr, sizes):
+        self._ck(self._lib.surtr_upload_blob(self._h, C.c_void_p(blob_ptr), *sizes))
+
+    def download_blob_into_async(self, blob_ptr, capacity) -> OutLayout:
+        L = OutLayout()
+        self._ck(self._lib.surtr_download_blob_async(self._h, C.c_void_p(blob_ptr), capacity, C.byref(L)))
+        return L
+
+    @staticmethod
+    def unpack_output_blob(buf: np.ndarray, L: OutLayout) -> Fragments:
+        """Host-side view of an output blob as the usual arrays (float4 with w = 0, ring_off as prefix sum)."""
+        nf, nv, nr = int(L.n_fragments), int(L.n_verts), int(L.n_ring)
+        rec = np.frombuffer(buf[L.fragments:L.fragments + 64 * nf].tobytes(), dtype=FRAGMENT_DTYPE)
+        v3 = np.frombuffer(buf[L.verts3:L.verts3 + 12 * nv].tobytes(), dtype=np.float32).reshape(nv, 3)
+        rl = np.frombuffer(buf[L.ring_len:L.ring_len + nv].tobytes(), dtype=np.uint8)
+        ring = np.frombuffer(buf[L.ring:L.ring + 2 * nr].tobytes(), dtype=np.uint16)
+        verts = np.zeros((nv, 4), np.float32)
+        verts[:, :3] = v3
+        ring_off = np.concatenate([[0], np.cumsum(rl, dtype=np.uint64)]).astype(np.uint32)
+        return Fragments(rec, verts, ring_off, ring)
 
     def download_packed(self) -> Fragments:
         """Fragments through the packed wire format, unpacked to the usual arrays (float4 with w = 0, ring_off as the

@@ -451,6 +451,55 @@ def test_packed_wire_format(ctx):
         assert np.array_equal(bits(again.verts), bits(ref.verts)) and np.array_equal(again.ring_off, ref.ring_off)
 
 
+def test_one_copy_blob_transfers(ctx):
+    """surtr_upload_blob / surtr_download_blob_async: one blob per direction.  Same fragments, bit for bit, as the plain
+    calls and the oracle, for a batch of independent events (config 4 shape), a single event, unbounded cells, and a
+    plain upload after a blob upload (the index arrays were views into the blob)."""
+    import ctypes as C
+    from surtr_b200 import FractureContext
+    psets = [common.voronoi(1234 + e, 1000) for e in range(3)]
+    csets = [common.voronoi(46354 + e, 64) for e in range(3)]
+    pieces, ev_p = common.concat(psets)
+    cells, ev_c = common.concat(csets)
+    for kw in (dict(ev_piece_off=ev_p, ev_cell_off=ev_c), dict(), dict(bounded=False)):
+        if "ev_piece_off" in kw:
+            ref = common.run_gpu(ctx, pieces, cells, ev_p, ev_c)
+        else:
+            ref = common.run_gpu(ctx, pieces, cells, bounded=kw.get("bounded", True))
+        sizes, total = FractureContext.fill_input_blob(None, pieces, cells, **kw)
+        buf = np.zeros(total, np.uint8)
+        FractureContext.fill_input_blob(buf, pieces, cells, **kw)
+        ctx.upload_blob_ptr(buf.ctypes.data, sizes)
+        ctx.fracture_event()
+        c = ctx.counts()
+        out = np.zeros(64 * c.n_fragments + 13 * c.n_verts + 2 * c.n_ring + 4 * 256, np.uint8)
+        L = ctx.download_blob_into_async(out.ctypes.data, len(out))
+        ctx.sync()
+        got = FractureContext.unpack_output_blob(out, L)
+        assert got.rec.tobytes() == ref.rec.tobytes()
+        assert np.array_equal(bits(got.verts), bits(ref.verts))
+        assert np.array_equal(got.ring_off, ref.ring_off) and np.array_equal(got.ring, ref.ring)
+        # too small a host blob is refused with the needed size reported
+        with pytest.raises(Exception):
+            ctx.download_blob_into_async(out.ctypes.data, 16)
+    want = P.apply_fracture(psets[0], csets[0].planes, csets[0].plane_off)
+    again = common.run_gpu(ctx, psets[0], csets[0])          # plain upload over the blob's views
+    common.assert_fragments_equal(again, want)
+    # recursion after a blob upload: the blob's index arrays are not recycled as output arrays
+    sizes, total = FractureContext.fill_input_blob(None, psets[0], csets[0])
+    buf = np.zeros(total, np.uint8)
+    FractureContext.fill_input_blob(buf, psets[0], csets[0])
+    ctx.upload_blob_ptr(buf.ctypes.data, sizes)
+    ctx.fracture_event()
+    lvl1 = ctx.download()
+    ctx.fragments_to_pieces()
+    ctx.upload_cells(csets[1].planes, csets[1].poly_face_off, csets[1].verts, csets[1].vert_off)
+    ctx.fracture_event()
+    lvl2 = ctx.download()
+    want2 = P.apply_fracture(common.fragments_as_polyset(lvl1), csets[1].planes, csets[1].poly_face_off)
+    common.assert_fragments_equal(lvl2, want2)
+
+
 def test_global_tier_workspace_grows(monkeypatch):
     """A global-tier workspace that runs out of vertex slots is doubled and the event re-run (never a failed pair): the
     bunny mesh (2503 vertices) starting from a 1024-slot workspace (test hook SURTR_DEBUG_CAP3)."""
