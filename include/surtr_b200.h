@@ -78,8 +78,9 @@ typedef struct surtr_counts {
     uint64_t n_verts;       /* total fragment vertices */
     uint64_t n_ring;        /* total fragment ring entries */
     uint64_t n_seq_cuts;    /* cuts that took the sequential in-plane/anomaly path (diagnostic) */
-    uint64_t n_tier2;       /* pairs re-run in the large on-chip tier (diagnostic) */
-    uint64_t n_tier3;       /* pairs cut in the global-memory tier: > 256 vertex slots or ring degree > 16 (diagnostic) */
+    uint64_t n_tier2;       /* pairs cut in the large on-chip tier: 65..256 vertex slots or ring degree 9..16 (diagnostic) */
+    uint64_t n_tier3;       /* pairs cut in the global-memory tier: more than 256 vertex slots (diagnostic) */
+    uint64_t n_tier1b;      /* pairs re-run in the 128-slot warp-per-pair tier (diagnostic) */
 } surtr_counts;
 
 /* Device-side view of the last event's fragments (pointers stay valid until the next event / upload). */

@@ -1,0 +1,438 @@
+// clip_fast.cuh -- small-tier clipper, round 2: ONE warp clips one (piece, cell) pair; 32 * G vertex slots (G = 2: the
+// main tier, G = 4: the 128-slot tier for pieces whose cut transiently needs more than 64 slots), ring degree <= 8.
+//
+// Same algorithm and the same exactness argument as clip_sub.cuh -- ring words, ballots instead
+// of a per-vertex comp array, new vertices in the reference's append order, lazy compaction, sequential replay of the
+// reference loop for in-plane / anomalous cuts -- but written for exactly one pair per warp, which is what K3 launches:
+//   * every mask (live, clipped, kept) is G 32-bit words, word g = the ballot of vertex group g: no 64-bit shifts, no
+//     sub-warp bookkeeping, and every branch on them is warp-uniform by construction -- no votes to agree on a branch;
+//   * the plane of the current iteration is ONE broadcast LDG.128 (prefetched one plane ahead) instead of four shuffles;
+//   * a plane that does not cut (4 of 5 on the Voronoi-on-Voronoi configs) costs a signed distance, two compares and
+//     two ballots per vertex group and touches no shared memory and no __syncwarp;
+//   * the prefix sum that places new vertices in append order is built from ballots of the count bits (popc against
+//     the lane mask) instead of a five-step shuffle scan.
+// Profiles: profiles/r2_k3_*.txt (instruction count per pair and per cut before / after).
+#pragma once
+
+#include "clip_sub.cuh"
+
+namespace surtr
+{
+template <int G>
+struct FastPoly   // one per warp in shared memory: 31 bytes per slot (G = 2: 1984 bytes, G = 4: 3968 bytes)
+{
+    static constexpr int S = 32 * G;
+    float x[S], y[S], z[S];
+    u64 ring[S];          // 8 x u8, 0xFF = empty slot
+    u64 old_ring[S];      // snapshot for the sequential replay (Poly.cpp:367-369)
+    uint16_t list[S];     // straddling half-edges of the current cut: slot | ring slot << 8; then walk targets
+    uint8_t id[S];        // walk-target probe: id[X(w)] = w; final numbering at write-out
+};
+
+template <int G>
+struct FastMasks   // warp-uniform
+{
+    unsigned live[G], c[G], k[G];
+};
+
+// word g of a register-resident mask array, g not a compile-time constant (a dynamic index would spill the array)
+template <int G>
+__device__ __forceinline__ unsigned mword(const unsigned (&m)[G], int g)
+{
+    unsigned w = m[0];
+#pragma unroll
+    for (int i = 1; i < G; i++) w = g == i ? m[i] : w;
+    return w;
+}
+template <int G>
+__device__ __forceinline__ bool mbit(const unsigned (&m)[G], int v) { return (mword<G>(m, v >> 5) >> (v & 31)) & 1u; }
+template <int G>
+__device__ __forceinline__ int mrank(const unsigned (&m)[G], int v)   // set bits below v
+{
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < G; i++)
+    {
+        const int g = v >> 5;
+        r += i < g ? __popc(m[i]) : (i == g ? __popc(m[i] & ((1u << (v & 31)) - 1u)) : 0);
+    }
+    return r;
+}
+template <int G>
+__device__ __forceinline__ int mcount(const unsigned (&m)[G])
+{
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < G; i++) r += __popc(m[i]);
+    return r;
+}
+__device__ __forceinline__ unsigned lowmask32(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+// comp of the reference for the sequential replay: 2 = new, -1 clipped / gone, +1 kept, 0 in-plane
+template <int G>
+__device__ __forceinline__ int fast_comp_of(const FastMasks<G>& m, const unsigned (&dead)[G], int hi0, int j)
+{
+    if (mbit<G>(dead, j)) return -1;   // spliced away (Poly.cpp:459)
+    if (j >= hi0) return 2;
+    if (mbit<G>(m.c, j) || !mbit<G>(m.live, j)) return -1;
+    return mbit<G>(m.k, j) ? 1 : 0;
+}
+
+// Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) by lane 0 after the new vertices have
+// been inserted.  Visiting order = the reference's: new vertices first, then the pre-existing ones, both ascending.
+// Returns 0 on ring overflow; dead = the vertices spliced away.  Called by all lanes.
+template <int G>
+__device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, int hi0, int nnew, int lane, unsigned (&dead)[G])
+{
+    const int hi1 = hi0 + nnew;
+    for (int v = lane; v < hi1; v += 32) sp.old_ring[v] = sp.ring[v];
+    __syncwarp();
+    int ok = 1;
+    unsigned dd[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) dd[g] = 0u;
+    if (lane == 0)
+    {
+        unsigned none[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) none[g] = 0u;
+        const int nverts = mcount<G>(m.live) + nnew;   // the reference's vertex count (walk bound)
+        for (int ii = 0; ii < hi1 && ok; ii++)
+        {
+            const int i = ii < nnew ? hi0 + ii : ii - nnew;
+            const int ci = fast_comp_of<G>(m, none, hi0, i);
+            if (!(ci == 0 || ci == 2)) continue;
+            const int nneigh = rdeg(sp.ring[i]);
+            for (int j = 0; j < nneigh; j++)
+            {
+                const int jn = rget(sp.ring[i], j);
+                if (jn >= R_MARK || fast_comp_of<G>(m, none, hi0, jn) != -1) continue;
+                int iprev = i, inext = jn, itmp, k = 0;
+                while (fast_comp_of<G>(m, none, hi0, inext) == -1 && k++ < nverts)
+                {
+                    itmp = inext;
+                    inext = rface_loop(sp.ring[inext], iprev);
+                    iprev = itmp;
+                }
+                const u64 wi = sp.ring[i];
+                if (rget(wi, (j + 1) % rdeg(wi)) == inext || inext == i)
+                {
+                    sp.ring[i] = rset(wi, j, R_MARK);
+                }
+                else
+                {
+                    sp.ring[i] = rset(wi, j, inext);
+                    const u64 wn = sp.ring[inext], on = sp.old_ring[inext];
+                    if (rdeg(wn) >= 8 || rdeg(on) >= 8) { ok = 0; break; }
+                    int off = 0, mark = i;
+                    if (fast_comp_of<G>(m, none, hi0, inext) == 2) mark = R_MARK;   // Poly.cpp:409 inserts -1 in the snapshot
+                    else { off = rfind(on, iprev); if (off > rdeg(on)) off = rdeg(on); }
+                    sp.ring[inext] = rinsert(wn, off, i);
+                    sp.old_ring[inext] = rinsert(on, off, mark);
+                }
+            }
+        }
+        for (int i = 0; i < hi1; i++)   // Poly.cpp:426-431
+        {
+            const u64 w = sp.ring[i];
+            u64 o = ~0ull;
+            int n = 0;
+            for (int k = 0; k < 8; k++)
+            {
+                const int b = rget(w, k);
+                if (b == R_NONE) break;
+                if (b != R_MARK) o = rset(o, n++, b);
+            }
+            sp.ring[i] = o;
+        }
+        bool updated = ok != 0;   // Poly.cpp:433-462
+        while (updated)
+        {
+            updated = false;
+            for (int i = 0; i < hi1; i++)
+            {
+                if (fast_comp_of<G>(m, dd, hi0, i) >= 0 && rdeg(sp.ring[i]) == 2)
+                {
+                    updated = true;
+                    const int iprev = rget(sp.ring[i], 0), inext = rget(sp.ring[i], 1);
+                    int k = rfind(sp.ring[iprev], i);
+                    if (k < rdeg(sp.ring[iprev])) sp.ring[iprev] = rset(sp.ring[iprev], k, inext);
+                    k = rfind(sp.ring[inext], i);
+                    if (k < rdeg(sp.ring[inext])) sp.ring[inext] = rset(sp.ring[inext], k, iprev);
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if ((i >> 5) == g) dd[g] |= 1u << (i & 31);
+                }
+            }
+        }
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+#pragma unroll
+    for (int g = 0; g < G; g++) dead[g] = __shfl_sync(FULL, dd[g], 0);
+    __syncwarp();
+    return ok;
+}
+
+// Renumber the live vertices to 0..n-1 keeping their order (the reference's compaction, Poly.cpp:464-495).
+template <int G>
+__device__ __noinline__ void fast_compact(FastPoly<G>& sp, unsigned (&live)[G], int& hi, int lane)
+{
+    u64 r[G];
+    float vx[G], vy[G], vz[G];
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        const int v = lane + 32 * g;
+        r[g] = ~0ull;
+        vx[g] = vy[g] = vz[g] = 0.f;
+        if ((live[g] >> lane) & 1u)
+        {
+            vx[g] = sp.x[v]; vy[g] = sp.y[v]; vz[g] = sp.z[v];
+            const u64 rw = sp.ring[v];
+            for (int j = 0; j < 8; j++)
+            {
+                const int b = rget(rw, j);
+                if (b == R_NONE) break;
+                r[g] = rset(r[g], j, mrank<G>(live, b));
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        const int v = lane + 32 * g;
+        if ((live[g] >> lane) & 1u)
+        {
+            const int t = mrank<G>(live, v);
+            sp.x[t] = vx[g]; sp.y[t] = vy[g]; sp.z[t] = vz[g]; sp.ring[t] = r[g];
+        }
+    }
+    __syncwarp();
+    const int n = mcount<G>(live);
+    hi = n;
+#pragma unroll
+    for (int g = 0; g < G; g++) live[g] = lowmask32(n - 32 * g);
+}
+
+// Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).  Called by all lanes.
+template <int G>
+__device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly<G>& sp, const unsigned (&live)[G], int hi, const float4 pl, int lane)
+{
+    float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
+    float hv[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
+    for (int v = lane; v < hi; v += 32)
+    {
+        if (!mbit<G>(live, v)) continue;
+        lo[0] = fminf(lo[0], sp.x[v]); hv[0] = fmaxf(hv[0], sp.x[v]);
+        lo[1] = fminf(lo[1], sp.y[v]); hv[1] = fmaxf(hv[1], sp.y[v]);
+        lo[2] = fminf(lo[2], sp.z[v]); hv[2] = fmaxf(hv[2], sp.z[v]);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++)
+        {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hv[k] = fmaxf(hv[k], __shfl_xor_sync(FULL, hv[k], o));
+        }
+    const int k = lane & 7;
+    const int c = classify(signed_dist(pl, (k & 1) ? hv[0] : lo[0], (k & 2) ? hv[1] : lo[1], (k & 4) ? hv[2] : lo[2]));
+    return __ballot_sync(FULL, c == -1) == 0u;
+}
+
+// Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1, positions of the lane's own slots also in px/py/pz) by
+// planes[0..npl).  Called by the 32 lanes of the pair's warp.  On return live = the live slots (not renumbered), hi the
+// allocated slots, nv the live count (0 = no fragment); returns the pair's status.
+template <int G>
+__device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi, int& nv, float (&px)[G], float (&py)[G], float (&pz)[G],
+                                   const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts, unsigned& n_cuts)
+{
+    constexpr int S = 32 * G;
+    const unsigned lm = 1u << lane, lt = lm - 1u;
+    FastMasks<G> m;
+    hi = nv;
+#pragma unroll
+    for (int g = 0; g < G; g++) { m.live[g] = lowmask32(nv - 32 * g); m.c[g] = m.k[g] = 0u; }
+    int status = CLIP_OK;
+    float4 cur = npl > 0 ? __ldg(planes) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = 0;
+    while (p < npl && nv > 0)
+    {
+        const float4 pl = cur;
+        const float4 nxt = __ldg(planes + (p + 1 < npl ? p + 1 : p));   // broadcast load, one plane ahead
+
+        // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per vertex group ----
+        unsigned anyc = 0u, anyk = 0u;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            m.c[g] = m.k[g] = 0u;
+            if (g == 0 || hi > 32 * g)   // warp-uniform
+            {
+                const float d = signed_dist(pl, px[g], py[g], pz[g]);
+                const bool off = (m.live[g] & lm) && !(fabsf(d) < __uint_as_float(0x2EDBE6FFu));   // live and not in-plane (a NaN distance is in-plane)
+                m.c[g] = __ballot_sync(FULL, off && d > 0.f);
+                m.k[g] = __ballot_sync(FULL, off && d < 0.f);
+                anyc |= m.c[g];
+                anyk |= m.k[g];
+            }
+        }
+        if (!anyc)
+        {
+            // nothing clipped: "above" (Poly.cpp:328) -- unless every vertex is in-plane and the box test says "below"
+            if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m.live, hi, pl, lane)) { nv = 0; break; }
+            cur = nxt;
+            p++;
+            continue;
+        }
+        if (!anyk) { nv = 0; break; }   // "below" (Poly.cpp:322-327)
+
+        // ---- the plane cuts: straddling half-edges (clipped vertex -> kept neighbour) in the reference's append order ----
+        unsigned smk = 0u;      // 8 ring-slot bits per owned vertex group
+        int cnt[G];
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            cnt[g] = 0;
+            if (m.c[g] & lm)
+            {
+                const u64 rw = sp.ring[lane + 32 * g];
+#pragma unroll 1
+                for (int j = 0; j < 8; j++)
+                {
+                    const int b = rget(rw, j);
+                    if (b == R_NONE) break;
+                    if (mbit<G>(m.k, b)) { smk |= 1u << (j + 8 * g); cnt[g]++; }
+                }
+            }
+        }
+        // exclusive prefix in (group, lane) order from ballots of the count bits
+        int pos[G], nnew = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            pos[g] = nnew;
+            if (m.c[g])   // warp-uniform: some vertex of this group is clipped
+            {
+                const unsigned b0 = __ballot_sync(FULL, cnt[g] & 1), b1 = __ballot_sync(FULL, cnt[g] & 2), b23 = __ballot_sync(FULL, cnt[g] & 12);
+                pos[g] += __popc(b0 & lt) + 2 * __popc(b1 & lt);
+                nnew += __popc(b0) + 2 * __popc(b1);
+                if (b23)   // a clipped vertex with four or more kept neighbours: rare
+                {
+                    const unsigned b2 = __ballot_sync(FULL, cnt[g] & 4), b3 = __ballot_sync(FULL, cnt[g] & 8);
+                    pos[g] += 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+                    nnew += 4 * __popc(b2) + 8 * __popc(b3);
+                }
+            }
+        }
+        if (hi + nnew > S)
+        {
+            // out of slots: renumber the live vertices (exactly the reference's compaction) and redo this plane
+            if (mcount<G>(m.live) + nnew > S) { status = CLIP_OVERFLOW; break; }
+            fast_compact<G>(sp, m.live, hi, lane);
+#pragma unroll
+            for (int g = 0; g < G; g++)
+            {
+                const int v = lane + 32 * g;
+                if (v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+            }
+            continue;
+        }
+        n_cuts++;
+        const int hi0 = hi;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            unsigned mm = (smk >> (8 * g)) & 0xffu;
+            int w = pos[g];   // (already offset by the totals of the earlier groups)
+            while (mm) { const int j = __ffs(mm) - 1; mm &= mm - 1; sp.list[w++] = (uint16_t)((lane + 32 * g) | (j << 8)); }
+        }
+        __syncwarp();
+        // insert: one new vertex per lane (Poly.cpp:345-354).  Lanes may touch the same ring WORD concurrently, but never
+        // the same BYTE: lane t replaces exactly slot j of ring[v] and the slot of ring[jn] that holds v (see clip_sub.cuh).
+        for (int t = lane; t < nnew; t += 32)
+        {
+            const int e = sp.list[t], v = e & 0xff, j = e >> 8, w = hi0 + t;
+            const int jn = rget(sp.ring[v], j);
+            const float ax = sp.x[v], ay = sp.y[v], az = sp.z[v], bx = sp.x[jn], by = sp.y[jn], bz = sp.z[jn];
+            const float sa = signed_dist(pl, ax, ay, az), sb = signed_dist(pl, bx, by, bz);
+            float ox, oy, oz;
+            plane_line_intersection(ax, ay, az, sa, bx, by, bz, sb, ox, oy, oz);
+            sp.x[w] = ox; sp.y[w] = oy; sp.z[w] = oz;
+            sp.ring[w] = 0xffffffffffff0000ull | (u64)(unsigned)v | ((u64)(unsigned)jn << 8);
+            reinterpret_cast<uint8_t*>(&sp.ring[v])[j] = (uint8_t)w;
+            const int k = rfind(sp.ring[jn], v);
+            if (k < 8) reinterpret_cast<uint8_t*>(&sp.ring[jn])[k] = (uint8_t)w;
+        }
+        __syncwarp();
+
+        // patch (Poly.cpp:365-431): walk from each new vertex through clipped vertices to the next new one
+        bool inplane = false;
+#pragma unroll
+        for (int g = 0; g < G; g++) inplane |= (m.live[g] & ~(m.c[g] | m.k[g])) != 0u;
+        bool need_seq = inplane;   // warp-uniform
+        if (!need_seq)
+        {
+            bool ok = true;
+            for (int t = lane; t < nnew; t += 32)
+            {
+                const int w = hi0 + t;
+                // first step without a search: w sits in slot j of its clipped end point v, so FaceLoop(v, w) is simply
+                // the slot before j (list[t] still holds v | j << 8 from the insertion)
+                const int e = sp.list[t], v = e & 0xff, j = e >> 8;
+                const u64 rv = sp.ring[v];
+                int iprev = v, inext = rget(rv, (j == 0 ? rdeg(rv) : j) - 1), itmp, k = 1;
+                while (inext < hi0 && mbit<G>(m.c, inext) && k++ < S)
+                {
+                    itmp = inext;
+                    inext = rface_loop(sp.ring[inext], iprev);
+                    iprev = itmp;
+                }
+                const bool okt = inext >= hi0 && inext < hi0 + nnew && inext != w;
+                if (okt) sp.id[inext] = (uint8_t)w;
+                sp.list[t] = (uint16_t)inext;
+                ok = ok && okt;
+            }
+            __syncwarp();
+            for (int t = lane; t < nnew; t += 32)
+                if (ok) ok = sp.id[sp.list[t]] == (uint8_t)(hi0 + t);
+            need_seq = __ballot_sync(FULL, !ok) != 0u;
+            if (!need_seq)
+            {
+                // the walk targets are a permutation of the new vertices: ring(w) = [pusher, walked, kept]
+                for (int t = lane; t < nnew; t += 32)
+                {
+                    const int w = hi0 + t;
+                    const int kept = rget(sp.ring[w], 1);
+                    sp.ring[w] = 0xffffffffff000000ull | (u64)sp.id[w] | ((u64)sp.list[t] << 8) | ((u64)(unsigned)kept << 16);
+                }
+            }
+        }
+        unsigned dead[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) dead[g] = 0u;
+        if (need_seq)
+        {
+            seq_cuts++;
+            if (!fast_seq_cut<G>(sp, m, hi0, nnew, lane, dead)) { status = CLIP_OVERFLOW; break; }
+        }
+        // lazy compaction: clipped vertices leave the live set, new ones join it
+        hi = hi0 + nnew;
+        nv = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            m.live[g] = ((m.live[g] & ~m.c[g]) | (lowmask32(hi - 32 * g) & ~lowmask32(hi0 - 32 * g))) & ~dead[g];
+            nv += __popc(m.live[g]);
+            const int v = lane + 32 * g;
+            if (v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+        }
+        if (nv < 4) nv = 0;   // Poly.cpp:498-499
+        __syncwarp();         // ring words composed above are visible to the next cut
+        cur = nxt;
+        p++;
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) live[g] = m.live[g];
+    return status;
+}
+} // namespace surtr

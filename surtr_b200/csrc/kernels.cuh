@@ -9,6 +9,7 @@
 #pragma once
 
 #include "clip_sub.cuh"
+#include "clip_fast.cuh"
 #include "clip_global.cuh"
 
 #include <type_traits>
@@ -40,7 +41,7 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
     unsigned int n_seq_cuts;
     unsigned int n_ovf3;        // pairs queued for the global-memory tier
     unsigned int n_grow3;       // global-tier pairs whose workspace ran out of vertex slots (the host enlarges it and re-runs)
-    unsigned int pad;
+    unsigned int n_ovf2;        // pairs the 128-slot tier handed on to the large on-chip tier
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -408,9 +409,10 @@ struct ClipArgs
     unsigned char* scratch;       // this tier's blob area
     uint64_t slot_bytes;
     unsigned char* scratch1;      // small-tier blob area (one slot per candidate): tier 2 hands small results to K4's moments
-    uint32_t* ovf_list;           // tier 1 appends, tier 2 consumes
+    uint32_t* ovf_list;           // tier 1 (64 slots) appends, tier 1b (128 slots) consumes
+    uint32_t* ovf2_list;          // tier 1b appends, tier 2 consumes
     uint64_t cap_tier2;           // slots available to tier 2
-    uint32_t* ovf3_list;          // tier 2 appends, tier 3 consumes
+    uint32_t* ovf3_list;          // tiers 1 / 1b / 2 append, tier 3 consumes
     unsigned char* ws3;           // tier 3: one workspace per warp
     uint64_t ws3_stride;
     int cap3;                     // tier 3: vertex slots per workspace
@@ -438,13 +440,13 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
     __shared__ int s_scan[T2_WARPS + 1];
     __shared__ float s_cov[T2_WARPS * 10];
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
-    const unsigned long long n_items = a.ctl->n_ovf;
+    const unsigned long long n_items = a.ctl->n_ovf2;
     GlobalPoly g = global_poly_carve(smem_raw, T2_CAP);   // one pair per block: the block's T2_WARPS warps share the workspace
     const Grp<T2_WARPS> grp{ tid, lane, s_scan };
     unsigned seq_cuts = 0;
     for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
     {
-        const uint32_t q = a.ovf_list[it];
+        const uint32_t q = a.ovf2_list[it];
         const uint2 pr = a.cand[q];
         const uint32_t v0 = a.p_vert_off[pr.x];
         int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
@@ -674,9 +676,163 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
     if (seq_cuts && tid == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
 }
 
-// K3, small tier: L lanes per candidate pair (clip_sub.cuh), one pair per sub-warp, no persistent loop (the
-// hardware scheduler balances the very uneven pair costs).
+
+// K3, small tier (round 2): ONE warp per candidate pair, clip_fast.cuh.  G = 2 (64 vertex slots) is the main launch: warp
+// w of the grid cuts candidate w, no persistent loop (the hardware scheduler balances the very uneven pair costs).
+// G = 4 (128 slots, LIST = true) is a second, small launch over the pairs the main launch could not finish -- pieces of
+// 50-60 vertices whose cut transiently needs more than 64 slots (clipped vertices keep their slots until the patch has
+// walked through them) -- so that they do not detour through the block-per-pair large tier.
+template <int G, bool LIST>
+__device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, uint32_t q, int lane)
+{
+    constexpr int S = 32 * G;
+    const long long t0 = a.dbg ? clock64() : 0;
+    const uint2 pr = a.cand[q];
+    const uint32_t v0 = a.p_vert_off[pr.x];
+    int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+    const uint32_t pl0 = a.c_plane_off[pr.y];
+    const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+    const int nv_in = nv;
+    float px[G], py[G], pz[G];
+    bool bad = nv > S;
+    if (!bad)
+    {
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            const int v = lane + 32 * g;
+            px[g] = py[g] = pz[g] = 0.f;
+            if (v < nv)
+            {
+                const float4 p = __ldg(a.p_verts + v0 + v);
+                const uint32_t r0 = a.p_ring_off[v0 + v];
+                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
+                px[g] = p.x; py[g] = p.y; pz[g] = p.z;
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                u64 rw = ~0ull;
+                if (d > 8 || d == 0) bad = true;
+                else
+                    for (int j = 0; j < d; j++)
+                    {
+                        const int idx = a.p_ring[r0 + j];
+                        bad = bad || idx >= nv;
+                        rw = rset(rw, j, idx);
+                    }
+                sp.ring[v] = rw;
+            }
+        }
+    }
+    bad = __ballot_sync(FULL, bad) != 0u;
+    __syncwarp();
+    const long long t1 = a.dbg ? clock64() : 0;
+    unsigned seq_cuts = 0, n_cuts = 0;
+    unsigned live[G];
+    int hi = 0, status = CLIP_OVERFLOW;
+    if (!bad) status = fast_clip_by_planes<G>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
+    const long long t2 = a.dbg ? clock64() : 0;
+    if (a.dbg && lane == 0)
+    {
+        uint32_t* d = a.dbg + (size_t)q * 8;
+        d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
+        d[4] = seq_cuts; d[5] = n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl;
+    }
+    if (seq_cuts && lane == 0) atomicAdd(&a.ctl->n_seq_cuts, seq_cuts);
+    CandRec* rec = a.rec + q;
+    if (status == CLIP_OK && nv > 64) status = CLIP_OVERFLOW;   // (G = 4 only) the result does not fit the small tier's blob
+    if (status != CLIP_OK)
+    {
+        if (lane == 0)
+        {
+            // too large for this tier (or a ring outgrew 8 slots): hand the pair on
+            rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+            if (nv_in > T2_CAP) a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;
+            else if (LIST) a.ovf2_list[atomicAdd(&a.ctl->n_ovf2, 1u)] = q;
+            else a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
+        }
+        return;
+    }
+    if (nv == 0)
+    {
+        if (lane == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
+        return;
+    }
+    // result blob, renumbered to the reference's final order (rank in the live mask):
+    // float4 verts[64] | u16 ring_start[64] | u8 ring[packed].  Face count and moments are K4's (assemble_gather_kernel).
+    const unsigned long long blob = (unsigned long long)q * FAST_BLOB_BYTES;
+    unsigned char* b = a.scratch1 + blob;
+    float4* bv = reinterpret_cast<float4*>(b);
+    uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
+    uint8_t* br = b + 64 * 18;
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        const int v = lane + 32 * g;
+        if ((g == 0 || hi > 32 * g) && ((live[g] >> lane) & 1u)) sp.id[v] = (uint8_t)mrank<G>(live, v);
+    }
+    __syncwarp();
+    int ne = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++)
+    {
+        if (g == 0 || hi > 32 * g)
+        {
+            const int v = lane + 32 * g;
+            const bool lv = (live[g] >> lane) & 1u;
+            const u64 rw = lv ? sp.ring[v] : ~0ull;
+            const int d = rdeg(rw);
+            int tot;
+            const int off = ne + warp_exscan(d, lane, tot);
+            ne += tot;
+            if (lv)
+            {
+                const int t = sp.id[v];
+                bv[t] = make_float4(px[g], py[g], pz[g], 0.f);
+                bo[t] = (uint16_t)off;
+#pragma unroll 1
+                for (int j = 0; j < d; j++) br[off + j] = sp.id[rget(rw, j)];
+            }
+        }
+    }
+    if (lane == 0)
+    {
+        rec->nv = (uint32_t)nv;
+        rec->ne = (uint32_t)ne;
+        rec->nf = 0;
+        rec->tier = 1;
+        rec->blob = blob;
+        if (a.dbg) a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t2);
+    }
+}
+
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
+template <int G, bool LIST>
+__global__ void __launch_bounds__(FAST_WARPS * 32, G == 2 ? 32 / FAST_WARPS : 8) clip_fast_kernel(ClipArgs a)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ FastPoly<G> s_poly[FAST_WARPS];
+    const int lane = threadIdx.x & 31;
+    FastPoly<G>& sp = s_poly[threadIdx.x >> 5];
+    const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (!LIST)
+    {
+        unsigned long long n_items = a.ctl->n_cand;
+        if (n_items > a.cap_cand) n_items = a.cap_cand;
+        if (wid < n_items) fast_pair<G, LIST>(a, sp, (uint32_t)wid, lane);
+    }
+    else
+    {
+        const unsigned long long n_items = a.ctl->n_ovf, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+        for (unsigned long long it = wid; it < n_items; it += nw)
+        {
+            fast_pair<G, LIST>(a, sp, a.ovf_list[it], lane);
+            __syncwarp();
+        }
+    }
+}
+
+// K3, small tier, round-1 version (kept for A/B profiles: SURTR_K3=sub selects it): L lanes per candidate pair
+// (clip_sub.cuh), one pair per sub-warp, no persistent loop.
 constexpr int FAST_LANES = 32;   // lanes per pair; 16 (two pairs per warp in lock step) is correct but measured slower, see DESIGN.md section 7
 constexpr size_t FAST_BLOB = FAST_BLOB_BYTES;
 

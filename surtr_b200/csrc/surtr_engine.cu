@@ -106,7 +106,7 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off, frag_cand;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf2_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off, frag_cand;
     bool debug = false;
     uint64_t cap_cand = 0, cap_tier2 = 0, cap_tier3 = 0;
     int cap3 = 0;                 // vertex slots of a tier-3 workspace (from the largest uploaded piece)
@@ -130,6 +130,8 @@ struct surtr_ctx
     void* ctl_ptr = nullptr;
     bool profile = false;         // per-kernel CUDA events inside an event (they serialise the PDL chain)
     bool profiled_last = false;
+    bool tier1b_enabled = false;  // the 128-slot warp-per-pair tier is launched once an event needed it
+    bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
     bool tier3_enabled = false;   // likewise the global-memory tier
     bool event_launched = false, event_resolved = false;
@@ -226,6 +228,7 @@ int ensure_capacity(surtr_ctx* ctx)
     CK(ctx->cand.reserve(sizeof(uint2) * ctx->cap_cand));
     CK(ctx->cand_rec.reserve(sizeof(CandRec) * ctx->cap_cand));
     CK(ctx->ovf_list.reserve(4 * ctx->cap_cand));
+    CK(ctx->ovf2_list.reserve(4 * ctx->cap_cand));
     CK(ctx->out_off.reserve(16 * ctx->cap_cand));
     if (ctx->debug) CK(ctx->dbg.reserve(32 * ctx->cap_cand));
     CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
@@ -338,6 +341,7 @@ int launch_event(surtr_ctx* ctx)
     ca.cap_cand = ctx->cap_cand;
     ca.rec = ctx->cand_rec.as<CandRec>();
     ca.ovf_list = ctx->ovf_list.as<uint32_t>();
+    ca.ovf2_list = ctx->ovf2_list.as<uint32_t>();
     ca.cap_tier2 = ctx->cap_tier2;
     ca.ovf3_list = ctx->ovf3_list.as<uint32_t>();
     ca.ws3 = ctx->ws3.as<unsigned char>();
@@ -352,10 +356,17 @@ int launch_event(surtr_ctx* ctx)
         ca.slot_bytes = FAST_BLOB;
         constexpr uint64_t pairs_per_block = FAST_WARPS * 32 / FAST_LANES;
         const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + pairs_per_block - 1) / pairs_per_block);
-        launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
+        if (ctx->k3_round1) launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
+        else launch_pdl(clip_fast_kernel<2, false>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (ctx->tier1b_enabled)
+    {
+        // the pairs the 64-slot launch could not finish, in 128 slots (still one warp per pair)
+        launch_pdl(clip_fast_kernel<4, true>, dim3(ctx->num_sm * 2), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
+        ctx->launches++;
+    }
     if (ctx->tier2_enabled)
     {
         ca.scratch = ctx->scratch2.as<unsigned char>();
@@ -443,8 +454,9 @@ int resolve_event(surtr_ctx* ctx)
         const Ctl c = *ctx->h_ctl;
         bool grow = false;
         if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
-        if (c.n_ovf > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf + c.n_ovf / 4 + 16; grow = true; }
-        if (c.n_ovf && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
+        if (c.n_ovf && !ctx->tier1b_enabled) { ctx->tier1b_enabled = true; grow = true; }   // re-run with the 128-slot tier
+        if (c.n_ovf2 > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf2 + c.n_ovf2 / 4 + 16; grow = true; }
+        if (c.n_ovf2 && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
         if (c.n_ovf3 > ctx->cap_tier3) { ctx->cap_tier3 = (uint64_t)c.n_ovf3 + c.n_ovf3 / 4 + 8; grow = true; }
         if (c.n_ovf3 && !ctx->tier3_enabled) { ctx->tier3_enabled = true; grow = true; }  // re-run with the global tier
         if (c.n_grow3 && ctx->cap3 < 65520)   // a global-tier workspace ran out of vertex slots: double it (up to the u16 index range)
@@ -470,8 +482,9 @@ int resolve_event(surtr_ctx* ctx)
             ctx->last.n_verts = c.n_fverts;
             ctx->last.n_ring = c.n_fring;
             ctx->last.n_seq_cuts = c.n_seq_cuts;
-            ctx->last.n_tier2 = c.n_ovf;
+            ctx->last.n_tier2 = c.n_ovf2;
             ctx->last.n_tier3 = c.n_ovf3;
+            ctx->last.n_tier1b = c.n_ovf;
             ctx->event_resolved = true;
             return SURTR_OK;
         }
@@ -564,6 +577,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
         return fail(nullptr, SURTR_ERR_NOMEM, "cudaHostAlloc (mapped) failed");
     }
     cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_ws_bytes());
+    if (const char* e = std::getenv("SURTR_K3")) ctx->k3_round1 = std::string(e) == "sub";
     *out = ctx;
     return SURTR_OK;
 }
@@ -577,7 +591,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
-                      &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf2_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->in_blob, &ctx->out_blob, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
                       &ctx->xf_idx };
     for (DevBuf* b : all) b->release();

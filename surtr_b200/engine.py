@@ -46,7 +46,7 @@ class SurtrError(RuntimeError):
 
 class Counts(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_candidates", "n_fragments", "n_verts", "n_ring",
-                                          "n_seq_cuts", "n_tier2", "n_tier3")]
+                                          "n_seq_cuts", "n_tier2", "n_tier3", "n_tier1b")]
 
 
 class InLayout(C.Structure):

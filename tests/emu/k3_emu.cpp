@@ -11,6 +11,7 @@
 
 #define __noinline__ __attribute__((noinline))
 #include "../../surtr_b200/csrc/clip_sub.cuh"
+#include "../../surtr_b200/csrc/clip_fast.cuh"
 #include "../../surtr_b200/csrc/clip_global.cuh"
 #undef __noinline__
 
@@ -21,6 +22,99 @@ extern "C"
 // Thread order between collectives: 0 ascending, 1 descending, other = seeded random permutation per pass.
 void k3emu_set_schedule(unsigned mode) { simt::schedule() = mode; }
 
+}   // extern "C"
+
+// Which small-tier clipper k3emu_pair runs: 2 / 4 = fast_clip_by_planes<G> of clip_fast.cuh (64 / 128 vertex slots: the
+// kernels that ship, clip_fast_kernel<2,false> and <4,true>), 0 = sub_clip_by_planes<32> of clip_sub.cuh (round 1).
+static int g_variant = 2;
+extern "C" void k3emu_set_variant(int v) { g_variant = v; }
+
+// The staging, clip and write-out of fast_pair<G> (kernels.cuh) for one pair.  Returns < 0 on an emulation inconsistency.
+template <int G>
+static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in, const std::vector<float4>& planes,
+                         int npl, float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring, int* out_info)
+{
+    constexpr int S = 32 * G;
+    auto sp = std::make_unique<FastPoly<G>>();
+    bool bad = nv_in > S;
+    float px[32][G], py[32][G], pz[32][G];
+    if (!bad)
+        for (int v = 0; v < nv_in; v++)
+        {
+            const int d = (int)(ring_off[v + 1] - ring_off[v]);
+            sp->x[v] = verts4[4 * v]; sp->y[v] = verts4[4 * v + 1]; sp->z[v] = verts4[4 * v + 2];
+            u64 rw = ~0ull;
+            if (d > 8 || d == 0) bad = true;
+            else
+                for (int j = 0; j < d; j++)
+                {
+                    const int idx = ring[ring_off[v] + j];
+                    bad = bad || idx >= nv_in;
+                    rw = rset(rw, j, idx);
+                }
+            sp->ring[v] = rw;
+        }
+    if (bad) { out_info[0] = CLIP_OVERFLOW; return 0; }
+    for (int l = 0; l < 32; l++)
+        for (int g = 0; g < G; g++)
+        {
+            const int v = l + 32 * g;
+            px[l][g] = py[l][g] = pz[l][g] = 0.f;
+            if (v < nv_in) { px[l][g] = sp->x[v]; py[l][g] = sp->y[v]; pz[l][g] = sp->z[v]; }
+        }
+    unsigned live[32][G];
+    int hi[32], nv[32], status[32];
+    unsigned seq[32], cuts[32];
+    const unsigned long n_coll = simt::run_warp([&](int lane) {
+        nv[lane] = nv_in;
+        seq[lane] = cuts[lane] = 0;
+        hi[lane] = 0;
+        status[lane] = fast_clip_by_planes<G>(*sp, live[lane], hi[lane], nv[lane], px[lane], py[lane], pz[lane], planes.data(), npl, lane,
+                                              seq[lane], cuts[lane]);
+    });
+    for (int l = 1; l < 32; l++)   // warp-uniform by construction
+    {
+        if (hi[l] != hi[0] || nv[l] != nv[0] || status[l] != status[0] || seq[l] != seq[0]) return -1;
+        if (status[0] == CLIP_OK && nv[0] > 0)
+            for (int g = 0; g < G; g++)
+                if (live[l][g] != live[0][g]) return -1;
+    }
+    out_info[0] = status[0];
+    out_info[3] = (int)seq[0];
+    out_info[4] = (int)cuts[0];
+    out_info[5] = (int)n_coll;
+    if (status[0] == CLIP_OK && nv[0] > 64) out_info[0] = CLIP_OVERFLOW;   // fast_pair: the result must fit the small blob
+    if (out_info[0] != CLIP_OK || nv[0] == 0) return 0;
+    // write-out of fast_pair: final number of a live slot = its rank in the live mask; positions from the owner lane's registers
+    int ne = 0, n = 0;
+    for (int v = 0; v < hi[0]; v++)
+    {
+        if (!mbit<G>(live[0], v)) continue;
+        const int t = mrank<G>(live[0], v);
+        if (t != n) return -2;
+        const int l = v & 31, g = v >> 5;
+        if (px[l][g] != sp->x[v] && !(px[l][g] != px[l][g])) return -6;   // the register copy is the shared-memory copy
+        out_verts4[4 * t] = px[l][g]; out_verts4[4 * t + 1] = py[l][g]; out_verts4[4 * t + 2] = pz[l][g]; out_verts4[4 * t + 3] = 0.f;
+        out_ring_off[t] = (uint32_t)ne;
+        const u64 rw = sp->ring[v];
+        const int d = rdeg(rw);
+        for (int j = 0; j < d; j++)
+        {
+            const int nb = rget(rw, j);
+            if (nb >= S || !mbit<G>(live[0], nb)) return -3;   // a ring entry that points at a dead slot
+            out_ring[ne++] = (uint16_t)mrank<G>(live[0], nb);
+        }
+        n++;
+    }
+    out_ring_off[n] = (uint32_t)ne;
+    if (n != nv[0]) return -4;
+    out_info[1] = n;
+    out_info[2] = ne;
+    return 0;
+}
+
+extern "C"
+{
 // One (piece, plane list) pair through the device code of the small tier.
 //   verts4[nv_in][4], ring_off[nv_in + 1] (relative to ring[0]), ring[...]: the piece;  planes4[npl][4]: the cell.
 //   out_verts4[64][4], out_ring_off[65], out_ring[512]: the fragment, numbered as the kernel writes it.
@@ -32,6 +126,19 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
                float* out_inertia)
 {
     for (int k = 0; k < 8; k++) out_info[k] = 0;
+    std::vector<float4> planes(std::max(npl, 1));
+    for (int p = 0; p < npl; p++) planes[p] = make_float4(planes4[4 * p], planes4[4 * p + 1], planes4[4 * p + 2], planes4[4 * p + 3]);
+    int n = 0;
+    if (g_variant != 0)
+    {
+        const int rc = g_variant == 4 ? fast_pair_emu<4>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
+                                      : fast_pair_emu<2>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info);
+        if (rc) return rc;
+        if (out_info[0] != CLIP_OK || out_info[1] == 0) return 0;
+        n = out_info[1];
+    }
+    else
+    {
     auto sp = std::make_unique<SubPoly>();
     bool bad = nv_in > 64;
     if (!bad)
@@ -51,9 +158,6 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
             sp->ring[v] = rw;
         }
     if (bad) { out_info[0] = CLIP_OVERFLOW; return 0; }
-
-    std::vector<float4> planes(std::max(npl, 1));
-    for (int p = 0; p < npl; p++) planes[p] = make_float4(planes4[4 * p], planes4[4 * p + 1], planes4[4 * p + 2], planes4[4 * p + 3]);
 
     CutState cs[32];
     int nv[32], status[32];
@@ -75,7 +179,7 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
 
     // write-out of clip_sub_kernel: final number of a live slot = its rank in the live mask
     const u64 live = cs[0].live;
-    int ne = 0, n = 0;
+    int ne = 0;
     for (int v = 0; v < cs[0].hi; v++)
     {
         if (!bit64(live, v)) continue;
@@ -97,6 +201,7 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     if (n != nv[0]) return -4;
     out_info[1] = n;
     out_info[2] = ne;
+    }
 
     // K4 (assemble_gather_kernel, tier 1): the fragment is rebuilt in shared memory numbered 0..nv-1 and its face count,
     // volume, centroid and inertia come from sub_fragment_moments<16>, two fragments per warp in lock step.  Both halves

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU, "_build", "libk3emu.so")
 SRC = [os.path.join(EMU, "k3_emu.cpp"), os.path.join(EMU, "simt_shim.h")] + \
-      [os.path.join(HERE, "..", "surtr_b200", "csrc", f) for f in ("clip_sub.cuh", "clip_warp.cuh", "surtr_math.cuh")]
+      [os.path.join(HERE, "..", "surtr_b200", "csrc", f) for f in ("clip_sub.cuh", "clip_fast.cuh", "clip_global.cuh", "clip_warp.cuh", "surtr_math.cuh")]
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 
@@ -37,6 +37,15 @@ def emu():
     lib.k3emu_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
     lib.k3emu_pair_large.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
     return lib
+
+
+@pytest.fixture(params=[2, 4, 0], ids=["fast64", "fast128", "round1"])
+def small(emu, request):
+    """The small-tier clipper k3emu_pair runs: clip_fast.cuh with 64 slots (clip_fast_kernel<2,false>, the main K3
+    launch), with 128 slots (clip_fast_kernel<4,true>), and round 1's clip_sub.cuh (kept for A/B profiles)."""
+    emu.k3emu_set_variant(request.param)
+    yield emu
+    emu.k3emu_set_variant(2)
 
 
 def _p(a):
@@ -115,32 +124,32 @@ def run_event(lib, pieces, planes, plane_off, want, stats, tier=None, cells=None
 
 
 @pytest.mark.parametrize("name", ["cube_x64", "pieces200_x32"])
-def test_emulated_kernels_on_reference_fixtures(emu, name):
+def test_emulated_kernels_on_reference_fixtures(small, name):
     """Committed outputs of the REFERENCE build (tests/golden/make_golden.py): every (piece, cell) pair of the event."""
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
     cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
     stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
-    run_event(emu, pieces, cells.planes, cells.plane_off, want, stats)
+    run_event(small, pieces, cells.planes, cells.plane_off, want, stats)
     assert stats["pairs"] == pieces.n * cells.n and stats["overflow"] == 0 and stats["cuts"] > 5 * want.n
 
 
-def test_emulated_kernels_on_degenerate_cuts(emu):
+def test_emulated_kernels_on_degenerate_cuts(small):
     """Planes through vertices, along edges and coincident with faces (the in-plane band, the sequential replay, the
     degree-2 splice, the all-in-plane box test): expected = the reference build's output."""
     d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
     pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
     stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
-    run_event(emu, pieces, d["planes"], d["plane_off"], want, stats)
+    run_event(small, pieces, d["planes"], d["plane_off"], want, stats)
     assert stats["seq_cuts"] > 100 and stats["overflow"] == 0
 
 
-def test_emulated_kernels_against_the_oracle_port(emu):
+def test_emulated_kernels_against_the_oracle_port(small):
     """Config-4-shaped pairs (Voronoi pieces x Voronoi cells) and config 2's first cells against the oracle port, plus
     the lazy compaction: a 40-plane cell drives the slot counter past 64 and forces the in-kernel renumbering."""
     pieces, cells = common.voronoi(1234, 150), common.voronoi(46354, 24)
     want = P.apply_fracture(pieces, cells.planes, cells.plane_off)
     stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
-    run_event(emu, pieces, cells.planes, cells.plane_off, want, stats)
+    run_event(small, pieces, cells.planes, cells.plane_off, want, stats)
     assert stats["overflow"] == 0
 
     cube = common.unit_cube()
@@ -150,7 +159,7 @@ def test_emulated_kernels_against_the_oracle_port(emu):
     off = np.concatenate([[0], np.cumsum([big.plane_off[c + 1] - big.plane_off[c] for c in sel])]).astype(np.uint32)
     want = P.apply_fracture(cube, planes, off)
     stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
-    run_event(emu, cube, planes, off, want, stats)
+    run_event(small, cube, planes, off, want, stats)
     assert want.n == 48 and stats["cuts"] > 48 * 20
 
 

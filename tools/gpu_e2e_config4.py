@@ -62,7 +62,10 @@ def make_batches(bs):
         b.np, b.nc, b.ne, b.evp, b.evc = p.n, c.n, b.e1 - b.e0, np.ascontiguousarray(evp), np.ascontiguousarray(evc)
         b.h_in = {k: pin(v) for k, v in dict(pv=p.verts[:, :3], pvo=p.vert_off, pro=p.ring_off, pr=p.ring, planes=c.planes,
                                              plane_off=c.plane_off, cverts=c.verts[:, :3], cvo=c.vert_off).items()}
-        nf, nv, nr = int(ev_frags[b.e0:b.e1].sum()), int(ev_verts[b.e0:b.e1].sum()), int(ev_ring[b.e0:b.e1].sum())
+        # (sized for the largest batch: the ablation modes without uploads cut whatever batch the context last received)
+        nf = max(int(ev_frags[e:e + bs].sum()) for e in range(0, n_events, bs))
+        nv = max(int(ev_verts[e:e + bs].sum()) for e in range(0, n_events, bs))
+        nr = max(int(ev_ring[e:e + bs].sum()) for e in range(0, n_events, bs))
         b.h_out = dict(rec=torch.empty(nf * 64, dtype=torch.uint8, pin_memory=True), verts=torch.empty(nv * 3, dtype=torch.float32, pin_memory=True),
                        ring_len=torch.empty(nv, dtype=torch.uint8, pin_memory=True), ring=torch.empty(nr, dtype=torch.int16, pin_memory=True))
         b.sizes, total = FractureContext.fill_input_blob(None, p, c, evp, evc)
