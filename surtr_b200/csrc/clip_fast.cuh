@@ -29,6 +29,25 @@ struct FastPoly   // one per warp in shared memory: 31 bytes per slot (G = 2: 19
     uint8_t id[S];        // walk-target probe: id[X(w)] = w; final numbering at write-out
 };
 
+constexpr int FAST_MAX_PLANES = 64;   // planes the prefilter keeps a bit for (cells beyond it: every plane takes the exact path)
+
+// smallest plane index >= from whose bit is set in the visit words (npl if none); warp-uniform
+__device__ __forceinline__ int fast_next_plane(const unsigned (&visit)[(FAST_MAX_PLANES + 31) / 32], int from, int npl)
+{
+    if (npl > FAST_MAX_PLANES) return from < npl ? from : npl;
+#pragma unroll
+    for (int w = 0; w < (FAST_MAX_PLANES + 31) / 32; w++)
+    {
+        if (from < 32 * (w + 1))
+        {
+            const int lo = from > 32 * w ? from - 32 * w : 0;
+            const unsigned rest = visit[w] & (0xffffffffu << lo);
+            if (rest) { const int p = 32 * w + __ffs((int)rest) - 1; return p < npl ? p : npl; }
+        }
+    }
+    return npl;
+}
+
 template <int G>
 struct FastMasks   // warp-uniform
 {
@@ -78,9 +97,11 @@ __device__ __forceinline__ int fast_comp_of(const FastMasks<G>& m, const unsigne
     return mbit<G>(m.k, j) ? 1 : 0;
 }
 
-// Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) by lane 0 after the new vertices have
-// been inserted.  Visiting order = the reference's: new vertices first, then the pre-existing ones, both ascending.
-// Returns 0 on ring overflow; dead = the vertices spliced away.  Called by all lanes.
+// Sequential replay of Poly.cpp:365-462 (patch, erase marks, degree-2 splice) after the new vertices have been
+// inserted.  Only the patch itself is order dependent: lane 0 replays it over the vertices it can touch (comp 2 = the
+// new ones first, then comp 0 = the in-plane ones, both ascending -- the reference's visiting order); erasing the marks
+// is per vertex (all lanes), and the splice loop runs only if some vertex was left with two neighbours (never seen on
+// the BASELINE configs).  Returns 0 on ring overflow; dead = the vertices spliced away.  Called by all lanes.
 template <int G>
 __device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, int hi0, int nnew, int lane, unsigned (&dead)[G])
 {
@@ -88,20 +109,28 @@ __device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, 
     for (int v = lane; v < hi1; v += 32) sp.old_ring[v] = sp.ring[v];
     __syncwarp();
     int ok = 1;
-    unsigned dd[G];
+    unsigned none[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) dd[g] = 0u;
+    for (int g = 0; g < G; g++) none[g] = 0u;
     if (lane == 0)
     {
-        unsigned none[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) none[g] = 0u;
         const int nverts = mcount<G>(m.live) + nnew;   // the reference's vertex count (walk bound)
-        for (int ii = 0; ii < hi1 && ok; ii++)
+        // visiting order: new vertices hi0 .. hi1-1, then the in-plane ones (live, neither clipped nor kept) ascending
+        int i = hi0, g_in = 0;
+        unsigned in_w = m.live[0] & ~(m.c[0] | m.k[0]);
+        while (ok)
         {
-            const int i = ii < nnew ? hi0 + ii : ii - nnew;
-            const int ci = fast_comp_of<G>(m, none, hi0, i);
-            if (!(ci == 0 || ci == 2)) continue;
+            if (i >= hi0)
+            {
+                if (i >= hi1) i = -1;      // new vertices done: switch to the in-plane ones
+            }
+            if (i < 0)
+            {
+                while (!in_w && ++g_in < G) in_w = mword<G>(m.live, g_in) & ~(mword<G>(m.c, g_in) | mword<G>(m.k, g_in));
+                if (!in_w) break;
+                i = 32 * g_in + __ffs((int)in_w) - 1;
+                in_w &= in_w - 1;
+            }
             const int nneigh = rdeg(sp.ring[i]);
             for (int j = 0; j < nneigh; j++)
             {
@@ -131,44 +160,60 @@ __device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, 
                     sp.old_ring[inext] = rinsert(on, off, mark);
                 }
             }
-        }
-        for (int i = 0; i < hi1; i++)   // Poly.cpp:426-431
-        {
-            const u64 w = sp.ring[i];
-            u64 o = ~0ull;
-            int n = 0;
-            for (int k = 0; k < 8; k++)
-            {
-                const int b = rget(w, k);
-                if (b == R_NONE) break;
-                if (b != R_MARK) o = rset(o, n++, b);
-            }
-            sp.ring[i] = o;
-        }
-        bool updated = ok != 0;   // Poly.cpp:433-462
-        while (updated)
-        {
-            updated = false;
-            for (int i = 0; i < hi1; i++)
-            {
-                if (fast_comp_of<G>(m, dd, hi0, i) >= 0 && rdeg(sp.ring[i]) == 2)
-                {
-                    updated = true;
-                    const int iprev = rget(sp.ring[i], 0), inext = rget(sp.ring[i], 1);
-                    int k = rfind(sp.ring[iprev], i);
-                    if (k < rdeg(sp.ring[iprev])) sp.ring[iprev] = rset(sp.ring[iprev], k, inext);
-                    k = rfind(sp.ring[inext], i);
-                    if (k < rdeg(sp.ring[inext])) sp.ring[inext] = rset(sp.ring[inext], k, iprev);
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        if ((i >> 5) == g) dd[g] |= 1u << (i & 31);
-                }
-            }
+            i = i >= hi0 ? i + 1 : -1;
         }
     }
     ok = __shfl_sync(FULL, ok, 0);
+    __syncwarp();
+    bool two = false;   // a surviving vertex left with exactly two neighbours (Poly.cpp:433-462 would splice it)
+    for (int i = lane; i < hi1; i += 32)   // Poly.cpp:426-431, per vertex
+    {
+        const u64 w = sp.ring[i];
+        u64 o = ~0ull;
+        int n = 0;
+        for (int k = 0; k < 8; k++)
+        {
+            const int b = rget(w, k);
+            if (b == R_NONE) break;
+            if (b != R_MARK) o = rset(o, n++, b);
+        }
+        sp.ring[i] = o;
+        two |= n == 2 && fast_comp_of<G>(m, none, hi0, i) >= 0;
+    }
+    unsigned dd[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) dead[g] = __shfl_sync(FULL, dd[g], 0);
+    for (int g = 0; g < G; g++) dd[g] = 0u;
+    if (__ballot_sync(FULL, two) != 0u && ok)
+    {
+        __syncwarp();
+        if (lane == 0)
+        {
+            bool updated = true;   // Poly.cpp:433-462
+            while (updated)
+            {
+                updated = false;
+                for (int i = 0; i < hi1; i++)
+                {
+                    if (fast_comp_of<G>(m, dd, hi0, i) >= 0 && rdeg(sp.ring[i]) == 2)
+                    {
+                        updated = true;
+                        const int iprev = rget(sp.ring[i], 0), inext = rget(sp.ring[i], 1);
+                        int k = rfind(sp.ring[iprev], i);
+                        if (k < rdeg(sp.ring[iprev])) sp.ring[iprev] = rset(sp.ring[iprev], k, inext);
+                        k = rfind(sp.ring[inext], i);
+                        if (k < rdeg(sp.ring[inext])) sp.ring[inext] = rset(sp.ring[inext], k, iprev);
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+                            if ((i >> 5) == g) dd[g] |= 1u << (i & 31);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) dd[g] = __shfl_sync(FULL, dd[g], 0);
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) dead[g] = dd[g];
     __syncwarp();
     return ok;
 }
@@ -253,12 +298,67 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
 #pragma unroll
     for (int g = 0; g < G; g++) { m.live[g] = lowmask32(nv - 32 * g); m.c[g] = m.k[g] = 0u; }
     int status = CLIP_OK;
+
+    // ---- plane prefilter on the INITIAL vertices ----
+    // Every vertex a cut creates lies on an edge of the current polytope, hence (up to rounding, ~1e-6 of the coordinate
+    // scale per generation) in the convex hull of the initial vertices.  So a plane whose signed distance is below
+    // -margin at EVERY initial vertex, margin = 5e-4 * (|n|_1 * Lmax + |d|) -- hundreds of times that rounding -- classifies
+    // every later vertex as kept as well: the reference's loop would find it "above" whenever it gets there, and the
+    // plane is skipped without being classified again.  Likewise a plane above +margin at every initial vertex clips
+    // every vertex the reference could ever hold when it reaches that plane: the result is empty (Poly.cpp:322-327),
+    // whatever the planes before it did.  Planes within the margin of some vertex take the exact path below.
+    unsigned visit[(FAST_MAX_PLANES + 31) / 32];
+    {
+        float lm_abs = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            if (m.live[g] & lm) lm_abs = fmaxf(lm_abs, fmaxf(fabsf(px[g]), fmaxf(fabsf(py[g]), fabsf(pz[g]))));
+        const float lmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lm_abs)));   // non-negative floats order like their bits (NaN: largest)
+        bool kill = false;
+#pragma unroll
+        for (int w = 0; w < (FAST_MAX_PLANES + 31) / 32; w++)
+        {
+            visit[w] = 0u;
+            if (32 * w < npl && npl <= FAST_MAX_PLANES)   // warp-uniform
+            {
+                unsigned near_kept = 0u, near_clip = 0u;   // bit p: this lane has a vertex NOT safely kept / NOT safely clipped by plane p
+                const int n = npl - 32 * w < 32 ? npl - 32 * w : 32;
+                for (int q = 0; q < n; q++)
+                {
+                    const float4 pl = __ldg(planes + 32 * w + q);
+                    const float margin = __fmul_rn(5.0e-4f, __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(fabsf(pl.x), fabsf(pl.y)), fabsf(pl.z)), lmax), fabsf(pl.w)));
+                    bool nk = false, nc = false;
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if ((g == 0 || hi > 32 * g) && (m.live[g] & lm))
+                        {
+                            const float d = signed_dist(pl, px[g], py[g], pz[g]);
+                            nk |= !(d < -margin);
+                            nc |= !(d > margin);
+                        }
+                    near_kept |= (nk ? 1u : 0u) << q;
+                    near_clip |= (nc ? 1u : 0u) << q;
+                }
+                // (lanes without a vertex contribute no bit: they neither force a visit nor prevent a kill)
+                visit[w] = __reduce_or_sync(FULL, near_kept);
+                const unsigned nc_all = __reduce_or_sync(FULL, near_clip);
+                kill |= (~nc_all & (n == 32 ? 0xffffffffu : ((1u << n) - 1u))) != 0u;
+            }
+            else if (32 * w < npl) visit[w] = 0xffffffffu;   // more planes than the filter holds: every plane takes the exact path
+        }
+        if (kill) { nv = 0; npl = 0; }
+    }
+
     float4 cur = npl > 0 ? __ldg(planes) : make_float4(0.f, 0.f, 0.f, 0.f);
     int p = 0;
+    // first plane to visit
+    p = fast_next_plane(visit, 0, npl);
+    if (p < npl) cur = __ldg(planes + p);
     while (p < npl && nv > 0)
     {
         const float4 pl = cur;
-        const float4 nxt = __ldg(planes + (p + 1 < npl ? p + 1 : p));   // broadcast load, one plane ahead
+        const int pn = fast_next_plane(visit, p + 1, npl);                    // next plane the exact path has to look at
+        const float4 nxt = __ldg(planes + (pn < npl ? pn : p));                // broadcast load, one plane ahead
 
         // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per vertex group ----
         unsigned anyc = 0u, anyk = 0u;
@@ -281,7 +381,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             // nothing clipped: "above" (Poly.cpp:328) -- unless every vertex is in-plane and the box test says "below"
             if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m.live, hi, pl, lane)) { nv = 0; break; }
             cur = nxt;
-            p++;
+            p = pn;
             continue;
         }
         if (!anyk) { nv = 0; break; }   // "below" (Poly.cpp:322-327)
@@ -418,10 +518,12 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         // lazy compaction: clipped vertices leave the live set, new ones join it
         hi = hi0 + nnew;
         nv = 0;
+        const u64 fresh = ((nnew >= 64 ? 0ull : (1ull << nnew)) - 1ull) << (hi0 & 63);   // slots hi0 .. hi-1 (G = 2: as one 64-bit mask)
 #pragma unroll
         for (int g = 0; g < G; g++)
         {
-            m.live[g] = ((m.live[g] & ~m.c[g]) | (lowmask32(hi - 32 * g) & ~lowmask32(hi0 - 32 * g))) & ~dead[g];
+            const unsigned nm = G == 2 ? (unsigned)(fresh >> (32 * (g & 1))) : (lowmask32(hi - 32 * g) & ~lowmask32(hi0 - 32 * g));
+            m.live[g] = ((m.live[g] & ~m.c[g]) | nm) & ~dead[g];
             nv += __popc(m.live[g]);
             const int v = lane + 32 * g;
             if (v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
@@ -429,7 +531,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         if (nv < 4) nv = 0;   // Poly.cpp:498-499
         __syncwarp();         // ring words composed above are visible to the next cut
         cur = nxt;
-        p++;
+        p = pn;
     }
 #pragma unroll
     for (int g = 0; g < G; g++) live[g] = m.live[g];

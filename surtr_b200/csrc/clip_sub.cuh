@@ -42,18 +42,27 @@ struct SubPoly   // one per pair in shared memory (4032 bytes)
 constexpr int R_NONE = 0xff;   // empty slot
 constexpr int R_MARK = 0xfe;   // the reference's "-1, to be removed" (Poly.cpp:400)
 
+// Bit 7 of every zero byte of x (exact for the LOWEST zero byte, which is all the callers use; bytes above it may be
+// flagged falsely).  The SIMD-in-a-word compare __vcmpeq4 is emulated on sm_100 (a dozen instructions per word).
+__device__ __forceinline__ unsigned zero_bytes(unsigned x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
+__device__ __forceinline__ int first_flag(unsigned z) { return (__ffs((int)z) - 1) >> 3; }   // byte index of the lowest flag
+
 __device__ __forceinline__ int rdeg(u64 w)
 {
-    // empty slots (0xFF) are the trailing bytes; every other value (< 64, or the 0xFE mark) has a zero bit
-    return 8 - (__clzll((long long)~w) >> 3);
+    // empty slots (0xFF) are the trailing bytes: the degree is the index of the first 0xFF byte; the low word decides for
+    // every ring of up to three entries (the generic vertex)
+    const unsigned zl = zero_bytes(~(unsigned)w);
+    if (zl) return first_flag(zl);
+    const unsigned zh = zero_bytes(~(unsigned)(w >> 32));
+    return zh ? 4 + first_flag(zh) : 8;
 }
 __device__ __forceinline__ int rfind(u64 w, int val)   // first slot holding val, 8 if absent
 {
-    const unsigned pat = (unsigned)val * 0x01010101u;
-    const unsigned mlo = __vcmpeq4((unsigned)w, pat);
-    if (mlo) return (__ffs(mlo) - 1) >> 3;
-    const unsigned mhi = __vcmpeq4((unsigned)(w >> 32), pat);
-    return mhi ? 4 + ((__ffs(mhi) - 1) >> 3) : 8;
+    const unsigned pat = __byte_perm((unsigned)val, 0u, 0u);   // val in all four bytes
+    const unsigned zl = zero_bytes((unsigned)w ^ pat);
+    if (zl) return first_flag(zl);
+    const unsigned zh = zero_bytes((unsigned)(w >> 32) ^ pat);
+    return zh ? 4 + first_flag(zh) : 8;
 }
 __device__ __forceinline__ int rget(u64 w, int k) { return (int)(__byte_perm((unsigned)w, (unsigned)(w >> 32), (unsigned)k) & 0xffu); }
 __device__ __forceinline__ u64 rset(u64 w, int k, int val)

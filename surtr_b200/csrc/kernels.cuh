@@ -411,6 +411,7 @@ struct ClipArgs
     unsigned char* scratch1;      // small-tier blob area (one slot per candidate): tier 2 hands small results to K4's moments
     uint32_t* ovf_list;           // tier 1 (64 slots) appends, tier 1b (128 slots) consumes
     uint32_t* ovf2_list;          // tier 1b appends, tier 2 consumes
+    int skip_tier1b;              // test hook / round-1 kernel: tier 1 hands its overflows straight to tier 2
     uint64_t cap_tier2;           // slots available to tier 2
     uint32_t* ovf3_list;          // tiers 1 / 1b / 2 append, tier 3 consumes
     unsigned char* ws3;           // tier 3: one workspace per warp
@@ -746,7 +747,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
             // too large for this tier (or a ring outgrew 8 slots): hand the pair on
             rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
             if (nv_in > T2_CAP) a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;
-            else if (LIST) a.ovf2_list[atomicAdd(&a.ctl->n_ovf2, 1u)] = q;
+            else if (LIST || a.skip_tier1b) a.ovf2_list[atomicAdd(&a.ctl->n_ovf2, 1u)] = q;
             else a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
         }
         return;
@@ -910,7 +911,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, L == 32 ? 32 / FAST_WARPS : 4
         // global-memory tier when the piece cannot fit the large tier's 256 slots either
         rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
         if (nv_in > T2_CAP) a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;
-        else a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
+        else a.ovf2_list[atomicAdd(&a.ctl->n_ovf2, 1u)] = q;
     }
     if (have && status == CLIP_OK && nv == 0 && sub.sl == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
     const bool has = have && status == CLIP_OK && nv > 0;

@@ -132,6 +132,7 @@ struct surtr_ctx
     bool profiled_last = false;
     bool tier1b_enabled = false;  // the 128-slot warp-per-pair tier is launched once an event needed it
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
+    bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
     bool tier3_enabled = false;   // likewise the global-memory tier
     bool event_launched = false, event_resolved = false;
@@ -342,6 +343,7 @@ int launch_event(surtr_ctx* ctx)
     ca.rec = ctx->cand_rec.as<CandRec>();
     ca.ovf_list = ctx->ovf_list.as<uint32_t>();
     ca.ovf2_list = ctx->ovf2_list.as<uint32_t>();
+    ca.skip_tier1b = ctx->no_tier1b || ctx->k3_round1 ? 1 : 0;
     ca.cap_tier2 = ctx->cap_tier2;
     ca.ovf3_list = ctx->ovf3_list.as<uint32_t>();
     ca.ws3 = ctx->ws3.as<unsigned char>();
@@ -454,7 +456,7 @@ int resolve_event(surtr_ctx* ctx)
         const Ctl c = *ctx->h_ctl;
         bool grow = false;
         if (c.n_cand > ctx->cap_cand) { ctx->cap_cand = c.n_cand + c.n_cand / 8 + 64; grow = true; }
-        if (c.n_ovf && !ctx->tier1b_enabled) { ctx->tier1b_enabled = true; grow = true; }   // re-run with the 128-slot tier
+        if (c.n_ovf && !ctx->tier1b_enabled && !ctx->no_tier1b && !ctx->k3_round1) { ctx->tier1b_enabled = true; grow = true; }   // re-run with the 128-slot tier
         if (c.n_ovf2 > ctx->cap_tier2) { ctx->cap_tier2 = (uint64_t)c.n_ovf2 + c.n_ovf2 / 4 + 16; grow = true; }
         if (c.n_ovf2 && !ctx->tier2_enabled) { ctx->tier2_enabled = true; grow = true; }   // re-run with the large tier
         if (c.n_ovf3 > ctx->cap_tier3) { ctx->cap_tier3 = (uint64_t)c.n_ovf3 + c.n_ovf3 / 4 + 8; grow = true; }
@@ -578,6 +580,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
     }
     cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_ws_bytes());
     if (const char* e = std::getenv("SURTR_K3")) ctx->k3_round1 = std::string(e) == "sub";
+    if (const char* e = std::getenv("SURTR_DEBUG_NO_TIER1B")) ctx->no_tier1b = e[0] == '1';
     *out = ctx;
     return SURTR_OK;
 }

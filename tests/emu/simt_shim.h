@@ -36,7 +36,7 @@
 namespace simt
 {
 constexpr int WARP = 32;
-enum Kind : int { K_NONE, K_SYNC, K_BALLOT, K_ANY, K_SHFL, K_SHFL_UP, K_SHFL_XOR, K_REDUCE_MAX, K_SYNCTHREADS, K_SYNCTHREADS_OR };
+enum Kind : int { K_NONE, K_SYNC, K_BALLOT, K_ANY, K_SHFL, K_SHFL_UP, K_SHFL_XOR, K_REDUCE_MAX, K_REDUCE_OR, K_SYNCTHREADS, K_SYNCTHREADS_OR };
 enum Scope : int { S_WARP, S_BLOCK };
 
 struct Block
@@ -243,6 +243,24 @@ inline int __reduce_max_sync(unsigned mask, int v)
     const uint64_t* in = simt::warp_operands();
     int m = simt::unpack<int>(in[0]);
     for (int l = 1; l < simt::WARP; l++) m = std::max(m, simt::unpack<int>(in[l]));
+    return m;
+}
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
+{
+    require_full(mask);
+    simt::arrive(simt::S_WARP, simt::K_REDUCE_MAX, simt::pack(v));
+    const uint64_t* in = simt::warp_operands();
+    unsigned m = simt::unpack<unsigned>(in[0]);
+    for (int l = 1; l < simt::WARP; l++) m = std::max(m, simt::unpack<unsigned>(in[l]));
+    return m;
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    require_full(mask);
+    simt::arrive(simt::S_WARP, simt::K_REDUCE_OR, simt::pack(v));
+    const uint64_t* in = simt::warp_operands();
+    unsigned m = 0;
+    for (int l = 0; l < simt::WARP; l++) m |= simt::unpack<unsigned>(in[l]);
     return m;
 }
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)

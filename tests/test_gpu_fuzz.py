@@ -112,4 +112,22 @@ def test_random_pairs_large_tiers_match_oracle(ctx, seed):
     got = ctx.download()
     c = ctx.counts()
     common.assert_fragments_equal(got, want)
-    assert c.n_tier2 == 96 and c.n_tier3 >= 96 and want.n > 20
+    # ACH pairs: 128-slot warp tier, the few whose result outgrows the small blob go on to the large tier; mesh pairs: global tier
+    assert c.n_tier1b == 96 and c.n_tier2 < 96 and c.n_tier3 >= 96 and want.n > 20
+    if seed == 20:
+        # the same event with the 128-slot tier switched off (test hook): every ACH pair is cut by the large tier's own code
+        import os as _os
+        from surtr_b200 import FractureContext
+        _os.environ["SURTR_DEBUG_NO_TIER1B"] = "1"
+        try:
+            cx = FractureContext(0)
+        finally:
+            del _os.environ["SURTR_DEBUG_NO_TIER1B"]
+        try:
+            cx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+            cx.upload_cells(planes, off)
+            cx.fracture_event()
+            common.assert_fragments_equal(cx.download(), want)
+            assert cx.counts().n_tier2 == 96 and cx.counts().n_tier1b == 0
+        finally:
+            cx.close()

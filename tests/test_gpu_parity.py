@@ -171,7 +171,7 @@ def test_large_tier_pieces_and_kdop_clip(ctx):
             ctx.fracture_event()
             got = ctx.download()
             common.assert_fragments_equal(got, want_fr)
-            assert ctx.counts().n_tier2 > 0
+            assert ctx.counts().n_tier1b + ctx.counts().n_tier2 > 0
 
 
 def test_global_tier_mesh_polyhedron(ctx):
@@ -363,7 +363,26 @@ def test_degenerate_cuts_large_tiers(ctx):
     s["ring"] = common.digest(np.asarray(got.ring, np.uint16))
     assert s == _summaries()["degenerate_large"]
     c = ctx.counts()
-    assert c.n_tier2 == 48 and c.n_tier3 == 48 and c.n_seq_cuts > 50     # ACH pairs: large tier; mesh pairs: straight to the global tier
+    # ACH pairs: the 128-slot warp tier (results beyond 64 vertices go on to the large tier); mesh pairs: straight to the global tier
+    assert c.n_tier1b == 48 and c.n_tier3 == 48 and c.n_seq_cuts > 50
+    # and with the 128-slot tier switched off (test hook) the large tier's own sequential patch code cuts all 48 ACH pairs
+    from surtr_b200 import FractureContext
+    os.environ["SURTR_DEBUG_NO_TIER1B"] = "1"
+    try:
+        cx = FractureContext(0)
+    finally:
+        del os.environ["SURTR_DEBUG_NO_TIER1B"]
+    try:
+        cx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+        cx.upload_cells(planes, off)
+        cx.fracture_event()
+        got2 = cx.download()
+        s2 = common.summary_of_fragments(got2)
+        s2["ring"] = common.digest(np.asarray(got2.ring, np.uint16))
+        assert s2 == _summaries()["degenerate_large"]
+        assert cx.counts().n_tier2 == 48 and cx.counts().n_tier1b == 0
+    finally:
+        cx.close()
 
 
 def test_transform_pieces_on_device(ctx):

@@ -130,7 +130,7 @@ def test_emulated_kernels_on_reference_fixtures(small, name):
     cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
     stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
     run_event(small, pieces, cells.planes, cells.plane_off, want, stats)
-    assert stats["pairs"] == pieces.n * cells.n and stats["overflow"] == 0 and stats["cuts"] > 5 * want.n
+    assert stats["pairs"] == pieces.n * cells.n and stats["overflow"] == 0 and stats["cuts"] > 2 * want.n   # (pairs the plane prefilter kills never cut)
 
 
 def test_emulated_kernels_on_degenerate_cuts(small):
