@@ -289,7 +289,8 @@ __device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly<G>& s
 // allocated slots, nv the live count (0 = no fragment); returns the pair's status.
 template <int G>
 __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi, int& nv, float (&px)[G], float (&py)[G], float (&pz)[G],
-                                   const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts, unsigned& n_cuts)
+                                   const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts, unsigned& n_cuts,
+                                   const float (&box)[6], bool use_box)
 {
     constexpr int S = 32 * G;
     const unsigned lm = 1u << lane, lt = lm - 1u;
@@ -299,52 +300,43 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
     for (int g = 0; g < G; g++) { m.live[g] = lowmask32(nv - 32 * g); m.c[g] = m.k[g] = 0u; }
     int status = CLIP_OK;
 
-    // ---- plane prefilter on the INITIAL vertices ----
+    // ---- plane prefilter against the piece's bounding box (lane = plane) ----
     // Every vertex a cut creates lies on an edge of the current polytope, hence (up to rounding, ~1e-6 of the coordinate
-    // scale per generation) in the convex hull of the initial vertices.  So a plane whose signed distance is below
-    // -margin at EVERY initial vertex, margin = 5e-4 * (|n|_1 * Lmax + |d|) -- hundreds of times that rounding -- classifies
-    // every later vertex as kept as well: the reference's loop would find it "above" whenever it gets there, and the
-    // plane is skipped without being classified again.  Likewise a plane above +margin at every initial vertex clips
-    // every vertex the reference could ever hold when it reaches that plane: the result is empty (Poly.cpp:322-327),
-    // whatever the planes before it did.  Planes within the margin of some vertex take the exact path below.
+    // scale per generation) inside the piece's axis-aligned box [lo, hi] (K1 wrote it: the first three k-DOP slabs).  A
+    // plane whose signed distance is below -margin over the WHOLE box, margin = 5e-4 * (sum |n_i| (|c_i| + h_i) + |d|)
+    // -- hundreds of times that rounding -- classifies every vertex the reference could ever hold as kept: its loop would
+    // find the plane "above" whenever it gets there, and the plane is skipped without touching the vertices.  Likewise a
+    // plane above +margin over the whole box clips every such vertex: the result is empty (Poly.cpp:322-327) whatever the
+    // planes before it did.  Planes that come within the margin of the box take the exact path below.
     unsigned visit[(FAST_MAX_PLANES + 31) / 32];
     {
-        float lm_abs = 0.f;
-#pragma unroll
-        for (int g = 0; g < G; g++)
-            if (m.live[g] & lm) lm_abs = fmaxf(lm_abs, fmaxf(fabsf(px[g]), fmaxf(fabsf(py[g]), fabsf(pz[g]))));
-        const float lmax = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lm_abs)));   // non-negative floats order like their bits (NaN: largest)
+        const float cx = __fmul_rn(0.5f, __fadd_rn(box[0], box[1])), hx = __fmul_rn(0.5f, __fsub_rn(box[1], box[0]));
+        const float cy = __fmul_rn(0.5f, __fadd_rn(box[2], box[3])), hy = __fmul_rn(0.5f, __fsub_rn(box[3], box[2]));
+        const float cz = __fmul_rn(0.5f, __fadd_rn(box[4], box[5])), hz = __fmul_rn(0.5f, __fsub_rn(box[5], box[4]));
         bool kill = false;
 #pragma unroll
         for (int w = 0; w < (FAST_MAX_PLANES + 31) / 32; w++)
         {
-            visit[w] = 0u;
-            if (32 * w < npl && npl <= FAST_MAX_PLANES)   // warp-uniform
+            visit[w] = 0xffffffffu;
+            if (32 * w < npl && npl <= FAST_MAX_PLANES && use_box)   // warp-uniform
             {
-                unsigned near_kept = 0u, near_clip = 0u;   // bit p: this lane has a vertex NOT safely kept / NOT safely clipped by plane p
-                const int n = npl - 32 * w < 32 ? npl - 32 * w : 32;
-                for (int q = 0; q < n; q++)
+                const int q = 32 * w + lane;
+                bool near = false, dead = false;
+                if (q < npl)
                 {
-                    const float4 pl = __ldg(planes + 32 * w + q);
-                    const float margin = __fmul_rn(5.0e-4f, __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(fabsf(pl.x), fabsf(pl.y)), fabsf(pl.z)), lmax), fabsf(pl.w)));
-                    bool nk = false, nc = false;
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        if ((g == 0 || hi > 32 * g) && (m.live[g] & lm))
-                        {
-                            const float d = signed_dist(pl, px[g], py[g], pz[g]);
-                            nk |= !(d < -margin);
-                            nc |= !(d > margin);
-                        }
-                    near_kept |= (nk ? 1u : 0u) << q;
-                    near_clip |= (nc ? 1u : 0u) << q;
+                    const float4 pl = __ldg(planes + q);
+                    const float ax = fabsf(pl.x), ay = fabsf(pl.y), az = fabsf(pl.z);
+                    const float mid = signed_dist(pl, cx, cy, cz);
+                    const float ext = __fadd_rn(__fadd_rn(__fmul_rn(ax, hx), __fmul_rn(ay, hy)), __fmul_rn(az, hz));
+                    const float scale = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, fabsf(cx)), __fmul_rn(ay, fabsf(cy))), __fmul_rn(az, fabsf(cz))),
+                                                  __fadd_rn(ext, fabsf(pl.w)));
+                    const float margin = __fmul_rn(5.0e-4f, scale);
+                    near = !(__fadd_rn(mid, ext) < -margin);     // (a NaN anywhere: near)
+                    dead = __fsub_rn(mid, ext) > margin;
                 }
-                // (lanes without a vertex contribute no bit: they neither force a visit nor prevent a kill)
-                visit[w] = __reduce_or_sync(FULL, near_kept);
-                const unsigned nc_all = __reduce_or_sync(FULL, near_clip);
-                kill |= (~nc_all & (n == 32 ? 0xffffffffu : ((1u << n) - 1u))) != 0u;
+                visit[w] = __ballot_sync(FULL, near);
+                kill |= __ballot_sync(FULL, dead) != 0u;
             }
-            else if (32 * w < npl) visit[w] = 0xffffffffu;   // more planes than the filter holds: every plane takes the exact path
         }
         if (kill) { nv = 0; npl = 0; }
     }
@@ -449,6 +441,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         __syncwarp();
         // insert: one new vertex per lane (Poly.cpp:345-354).  Lanes may touch the same ring WORD concurrently, but never
         // the same BYTE: lane t replaces exactly slot j of ring[v] and the slot of ring[jn] that holds v (see clip_sub.cuh).
+#pragma unroll 1
         for (int t = lane; t < nnew; t += 32)
         {
             const int e = sp.list[t], v = e & 0xff, j = e >> 8, w = hi0 + t;
@@ -473,6 +466,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         if (!need_seq)
         {
             bool ok = true;
+#pragma unroll 1
             for (int t = lane; t < nnew; t += 32)
             {
                 const int w = hi0 + t;
@@ -481,6 +475,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
                 const int e = sp.list[t], v = e & 0xff, j = e >> 8;
                 const u64 rv = sp.ring[v];
                 int iprev = v, inext = rget(rv, (j == 0 ? rdeg(rv) : j) - 1), itmp, k = 1;
+#pragma unroll 1
                 while (inext < hi0 && mbit<G>(m.c, inext) && k++ < S)
                 {
                     itmp = inext;
@@ -493,12 +488,14 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
                 ok = ok && okt;
             }
             __syncwarp();
+#pragma unroll 1
             for (int t = lane; t < nnew; t += 32)
                 if (ok) ok = sp.id[sp.list[t]] == (uint8_t)(hi0 + t);
             need_seq = __ballot_sync(FULL, !ok) != 0u;
             if (!need_seq)
             {
                 // the walk targets are a permutation of the new vertices: ring(w) = [pusher, walked, kept]
+#pragma unroll 1
                 for (int t = lane; t < nnew; t += 32)
                 {
                     const int w = hi0 + t;

@@ -403,6 +403,8 @@ struct ClipArgs
     const uint16_t* p_ring;
     const float4* c_planes;
     const uint32_t* c_plane_off;
+    const float* ext_p;           // K1's slab extents of the pieces ([piece][2k]; slabs 0-2 = x, y, z): the small tier's plane prefilter
+    int kdirs;
     const uint2* cand;
     uint64_t cap_cand;
     CandRec* rec;
@@ -729,7 +731,11 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
     unsigned seq_cuts = 0, n_cuts = 0;
     unsigned live[G];
     int hi = 0, status = CLIP_OVERFLOW;
-    if (!bad) status = fast_clip_by_planes<G>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts);
+    // the piece's axis-aligned box for the plane prefilter: the first three slabs K1 wrote (x, y, z of every direction set)
+    float box[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) box[k] = a.ext_p ? __ldg(a.ext_p + (size_t)pr.x * 2 * a.kdirs + k) : 0.f;
+    if (!bad) status = fast_clip_by_planes<G>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts, box, a.ext_p != nullptr);
     const long long t2 = a.dbg ? clock64() : 0;
     if (a.dbg && lane == 0)
     {

@@ -338,6 +338,8 @@ int launch_event(surtr_ctx* ctx)
     ca.p_ring = ctx->p_ring.as<uint16_t>();
     ca.c_planes = ctx->c_planes.as<float4>();
     ca.c_plane_off = ctx->c_plane_off.as<uint32_t>();
+    ca.ext_p = ctx->ext_p.as<float>();
+    ca.kdirs = ctx->kdirs;
     ca.cand = ctx->cand.as<uint2>();
     ca.cap_cand = ctx->cap_cand;
     ca.rec = ctx->cand_rec.as<CandRec>();

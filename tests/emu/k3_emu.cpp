@@ -65,12 +65,20 @@ static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const ui
     unsigned live[32][G];
     int hi[32], nv[32], status[32];
     unsigned seq[32], cuts[32];
+    // K1's box of the piece (kdop_extents_kernel: plain min / max of the coordinates)
+    float box[6] = { 3.402823466e+38f, -3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f };
+    for (int v = 0; v < nv_in; v++)
+        for (int k = 0; k < 3; k++)
+        {
+            box[2 * k] = std::min(box[2 * k], verts4[4 * v + k]);
+            box[2 * k + 1] = std::max(box[2 * k + 1], verts4[4 * v + k]);
+        }
     const unsigned long n_coll = simt::run_warp([&](int lane) {
         nv[lane] = nv_in;
         seq[lane] = cuts[lane] = 0;
         hi[lane] = 0;
         status[lane] = fast_clip_by_planes<G>(*sp, live[lane], hi[lane], nv[lane], px[lane], py[lane], pz[lane], planes.data(), npl, lane,
-                                              seq[lane], cuts[lane]);
+                                              seq[lane], cuts[lane], box, true);
     });
     for (int l = 1; l < 32; l++)   // warp-uniform by construction
     {
