@@ -79,13 +79,16 @@ __device__ __forceinline__ u64 rinsert(u64 w, int k, int val)   // shift slots >
     return low | ((u64)(unsigned)val << (8 * k)) | (k == 7 ? 0ull : (high << (8 * k + 8)));
 }
 // FaceLoop (Src/Poly.cpp:34-41) on a ring word: entry just before vprev (wrapping); absent vprev -> last entry.
+// The degree is only needed for the wrap (vprev in slot 0) and for an absent vprev: two steps in three skip it.
 __device__ __forceinline__ int rface_loop(u64 w, int vprev)
 {
-    const int d = rdeg(w);
-    if (d == 0) return vprev;   // malformed input (vertex without neighbours): callers' loop bounds end the walk
     int k = rfind(w, vprev);
-    if (k > d) k = d;
-    return rget(w, (k == 0 ? d : k) - 1);
+    if (k == 0 || k == 8)
+    {
+        k = rdeg(w);
+        if (k == 0) return vprev;   // malformed input (vertex without neighbours): callers' loop bounds end the walk
+    }
+    return rget(w, k - 1);
 }
 
 __device__ __forceinline__ bool bit64(u64 m, int j) { return (m >> j) & 1ull; }
