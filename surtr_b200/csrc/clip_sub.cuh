@@ -753,4 +753,231 @@ __device__ void sub_fragment_moments(MomPoly& sp, const CutState& s, const Sub<L
         out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Round 2: face count + moments with every FaceLoop search done ONCE per directed edge.
+//
+// sub_fragment_moments walks face loops three times over (every local-minimum vertex probes its loops for a smaller
+// vertex, then the fan pass walks each face again) and every step is a byte search in a ring word (rfind + rget:
+// ~25 instructions): ~170 searches for a 16-vertex fragment, 40 % of K4's instructions (profiles/r2_k4_lines.txt).
+// Here the successor of every directed edge on its face loop is computed once (phase 1: 3 V searches) into a table in
+// shared memory -- edge id = the vertex's ring start + slot, entry = next edge | source vertex << 10 -- and the probe
+// and the fan pass follow table entries (one LDS.U16 per step).  Order, operands and accumulation are unchanged:
+// faces in Poly::ExtractFaces order (a face starts at its smallest vertex; vertices ascending, ring slots ascending),
+// fan triangles (p0, p_k, p_k+1) written to their slot in that order, ordered accumulation by four lanes.
+struct MomPoly2   // 4736 bytes per fragment
+{
+    float x[64], y[64], z[64];
+    u64 ring[64];           // 8 x u8, 0xFF = empty slot
+    uint16_t estart[64];    // first directed-edge id of vertex v = its ring start
+    uint16_t en[512];       // directed edge e = (v -> ring[v][j]), e = estart[v] + j: next edge of the face loop | v << 10
+    float4 tri[128];        // ordered fan-triangle records (dV, mx, my, mz); its first 512 bytes double as per-edge triangle counts before
+    uint16_t flist[128];    // one entry per face, in Poly::ExtractFaces order: start edge | first triangle << 9
+};
+
+template <int L>
+__device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bool has, Moments& out)
+{
+    constexpr int G = Sub<L>::G;
+    if (!has) nv = 0;
+    const int gmax = L == 32 ? (nv + L - 1) / L : sub.max_warp((nv + L - 1) / L);
+    const float ox = sp.x[0], oy = sp.y[0], oz = sp.z[0];
+    uint8_t* ecnt = reinterpret_cast<uint8_t*>(sp.tri);   // fan triangles of the face that starts at edge e (phases 2-3 only)
+
+    // ---- phase 1: successor of every directed edge (FaceLoop, Poly.cpp:34-41): (v -> a) is followed by (a -> entry before v in ring[a]) ----
+#pragma unroll 1
+    for (int g = 0; g < G; g++)
+    {
+        const int v = sub.sl + L * g;
+        if (g < gmax && v < nv)
+        {
+            const u64 rw = sp.ring[v];
+            const int d = rdeg(rw), e0 = sp.estart[v];
+#pragma unroll 1
+            for (int j = 0; j < d; j++)
+            {
+                const int a = rget(rw, j);
+                const u64 wa = sp.ring[a];
+                int k = rfind(wa, v);
+                if (k == 0 || k == 8) k = rdeg(wa);          // wrap, or v absent from ring[a] (malformed): the last entry, as FaceLoop does
+                sp.en[e0 + j] = (uint16_t)((sp.estart[a] + (k > 0 ? k - 1 : 0)) | (v << 10));
+            }
+        }
+    }
+    sub.sync();
+
+    // ---- phase 2: which edges start a face (their source is the smallest vertex of the loop), and its fan-triangle count ----
+    u64 start_mask = 0ull;   // 8 slot bits per owned group
+    int cntg[G], facg[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) cntg[g] = facg[g] = 0;
+#pragma unroll 1
+    for (int g = 0; g < G; g++)
+    {
+        int tris = 0, faces = 0;
+        const int v = sub.sl + L * g;
+        if (g < gmax && v < nv)
+        {
+            const u64 rw = sp.ring[v];
+            const int d = rdeg(rw), e0 = sp.estart[v];
+#pragma unroll 1
+            for (int j = 0; j < d; j++)
+            {
+                // v can only be the smallest vertex of the loop through (v -> a) if both loop neighbours of v are larger:
+                // a, and the vertex the loop arrives from = the ring entry after a (FaceLoop inverted)
+                if (rget(rw, j) < v || rget(rw, j + 1 == d ? 0 : j + 1) < v) continue;
+                unsigned e = sp.en[e0 + j] & 1023u;
+                int n = 1;
+                bool is_start = true;
+                while (true)
+                {
+                    const unsigned en = sp.en[e];
+                    const int at = (int)(en >> 10);
+                    if (at == v) break;
+                    if (at < v || n > nv) { is_start = false; break; }
+                    e = en & 1023u;
+                    n++;
+                }
+                if (is_start)
+                {
+                    start_mask |= 1ull << (j + 8 * g);
+                    faces++;
+                    tris += max(n - 2, 0);
+                    ecnt[e0 + j] = (uint8_t)max(n - 2, 0);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < G; h++)
+            if (h == g) { cntg[h] = tris; facg[h] = faces; }
+    }
+
+    // ---- phase 3: list the faces in order (vertex order = group-major, lane-minor; slots ascending) with their first triangle slot ----
+    int n_tri = 0, n_faces = 0;
+#pragma unroll 1
+    for (int g = 0; g < G; g++)
+    {
+        if (g < gmax)
+        {
+            int tris = 0, faces = 0;
+#pragma unroll
+            for (int h = 0; h < G; h++)
+                if (h == g) { tris = cntg[h]; faces = facg[h]; }
+            int ttot, ftot;
+            int tpos = n_tri + sub.exscan(tris, ttot);
+            int fpos = n_faces + sub.exscan(faces, ftot);
+            n_tri += ttot;
+            n_faces += ftot;
+            unsigned m = (unsigned)(start_mask >> (8 * g)) & 0xffu;
+            const int v = sub.sl + L * g;
+            const int e0 = m ? sp.estart[v] : 0;
+            while (m)
+            {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (fpos < 128) sp.flist[fpos] = (uint16_t)((e0 + j) | (min(tpos, 127) << 9));
+                fpos++;
+                tpos += ecnt[e0 + j];
+            }
+        }
+    }
+    n_tri = min(n_tri, 128);
+    sub.sync();
+
+    // ---- phase 4: lane = face: the fan triangles of a face, written to their slots; second moments on the fly ----
+    float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
+    const int n_listed = has ? min(n_faces, 128) : 0;
+#pragma unroll 1
+    for (int t = sub.sl; t < n_listed; t += L)
+    {
+        const unsigned f = sp.flist[t];
+        unsigned en = sp.en[f & 511u];
+        int w = (int)(f >> 9);
+        const int v = (int)(en >> 10);
+        const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
+        en = sp.en[en & 1023u];
+        int at = (int)(en >> 10);
+        float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
+        en = sp.en[en & 1023u];
+        at = (int)(en >> 10);
+        int guard = 0;
+        while (at != v && guard++ < 64)
+        {
+            const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
+            float cx, cy, cz;
+            cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
+            const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
+            const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
+            const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
+            const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
+            if (w < 128) sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
+            w++;
+            // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
+            cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
+            cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
+            cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
+            cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
+            cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
+            cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
+            cov[6] += dV;
+            cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
+            p1x = p2x; p1y = p2y; p1z = p2z;
+            en = sp.en[en & 1023u];
+            at = (int)(en >> 10);
+        }
+    }
+    sub.sync();
+
+    // ---- phase 5: ordered accumulation (Poly.cpp:77-85), as sub_fragment_moments ----
+    double zeroth = 0.0;
+    float fsum = 0.f;
+    if (sub.sl < 4)
+    {
+        const float* comp = reinterpret_cast<const float*>(sp.tri) + sub.sl;
+        int t = 0;
+        for (; t + 4 <= n_tri; t += 4)   // the loads do not depend on the accumulation chain
+        {
+            const float r0 = comp[4 * t], r1 = comp[4 * t + 4], r2 = comp[4 * t + 8], r3 = comp[4 * t + 12];
+            zeroth += (double)r0; zeroth += (double)r1; zeroth += (double)r2; zeroth += (double)r3;
+            fsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fsum, r0), r1), r2), r3);
+        }
+        for (; t < n_tri; t++)
+        {
+            const float r = comp[4 * t];
+            zeroth += (double)r;
+            fsum = __fadd_rn(fsum, r);
+        }
+    }
+    zeroth = sub.shfl(zeroth, 0) / 6.0;
+    float fx = sub.shfl(fsum, 1), fy = sub.shfl(fsum, 2), fz = sub.shfl(fsum, 3);
+    {
+        const double q = 24.0 * zeroth;
+        const double inv = (q >= 0.0 ? 1.0 : -1.0) / fmax(1.0e-30, fabs(q));   // safeInv, Poly.cpp:33
+        const float sc = (float)inv;
+        fx = __fmul_rn(fx, sc); fy = __fmul_rn(fy, sc); fz = __fmul_rn(fz, sc);
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++)
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1)
+            cov[k] += sub.shfl_xor(cov[k], o);
+
+    out.n_faces = n_faces;
+    out.volume = zeroth;
+    out.cx = __fadd_rn(fx, ox); out.cy = __fadd_rn(fy, oy); out.cz = __fadd_rn(fz, oz);
+    {
+        // shift from the origin vertex to the centroid (all from the same sums), then I = tr(C) 1 - C
+        const float V = cov[6] * (1.f / 6.f);
+        const float iv = V != 0.f ? 1.f / (24.f * V) : 0.f;
+        const float c0 = cov[7] * iv, c1 = cov[8] * iv, c2 = cov[9] * iv;
+        const float k120 = 1.f / 120.f;
+        const float Cxx = cov[0] * k120 - V * c0 * c0, Cyy = cov[1] * k120 - V * c1 * c1, Czz = cov[2] * k120 - V * c2 * c2;
+        out.inertia[0] = Cyy + Czz;
+        out.inertia[1] = Cxx + Czz;
+        out.inertia[2] = Cxx + Cyy;
+        out.inertia[3] = -(cov[3] * k120 - V * c0 * c1);
+        out.inertia[4] = -(cov[4] * k120 - V * c0 * c2);
+        out.inertia[5] = -(cov[5] * k120 - V * c1 * c2);
+    }
+}
 } // namespace surtr

@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
 {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ MomPoly s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
+    __shared__ MomPoly2 s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
     // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) have = false;   // the host grows and re-runs
     }
     const int tier = have ? (int)r->tier : 0;
-    MomPoly& sp = s_poly[threadIdx.x / L];
+    MomPoly2& sp = s_poly[threadIdx.x / L];
     if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
@@ -1133,6 +1133,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
                 a.f_verts[cvb + v] = p;
                 a.f_ring_off[cvb + v] = (uint32_t)(crb + r0);
                 sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                sp.estart[v] = (uint16_t)r0;
                 u64 rw = ~0ull;
                 for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, br[r0 + j]);
                 sp.ring[v] = rw;
@@ -1155,11 +1156,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
     if (sub.any_warp(do_mo))
     {
         sub.sync();
-        CutState cs;
-        cs.hi = do_mo ? cnv : 0;
-        cs.live = lowmask64(cs.hi);
-        cs.c = cs.k = 0ull;
-        sub_fragment_moments<L>(sp, cs, sub, do_mo, mo);
+        sub_fragment_moments2<L>(sp, do_mo ? cnv : 0, sub, do_mo, mo);
     }
     if (have && lane == 0)
     {

@@ -214,7 +214,7 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     // K4 (assemble_gather_kernel, tier 1): the fragment is rebuilt in shared memory numbered 0..nv-1 and its face count,
     // volume, centroid and inertia come from sub_fragment_moments<16>, two fragments per warp in lock step.  Both halves
     // of the emulated warp get this fragment; they must agree.
-    auto mp = std::make_unique<MomPoly[]>(2);
+    auto mp = std::make_unique<MomPoly2[]>(2);
     for (int h = 0; h < 2; h++)
         for (int v = 0; v < n; v++)
         {
@@ -223,18 +223,15 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
             const int r0 = (int)out_ring_off[v], r1 = (int)out_ring_off[v + 1];
             for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, out_ring[r0 + j]);
             mp[h].ring[v] = rw;
+            mp[h].estart[v] = (uint16_t)r0;
         }
     Moments mo[32];
     simt::run_warp([&](int lane) {
         const Sub<16> sub(lane);
-        CutState c;
-        c.hi = n;
-        c.live = lowmask64(n);
-        c.c = c.k = 0ull;
         if (sub.any_warp(true))
         {
             sub.sync();
-            sub_fragment_moments<16>(mp[lane / 16], c, sub, true, mo[lane]);
+            sub_fragment_moments2<16>(mp[lane / 16], n, sub, true, mo[lane]);
         }
     });
     for (int l = 1; l < 32; l++)
@@ -255,7 +252,7 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
 extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* const* ring_off, const uint16_t* const* ring, const int* n,
                                  int* out_faces, double* out_volume, float* out_centroid, float* out_inertia)
 {
-    auto mp = std::make_unique<MomPoly[]>(2);
+    auto mp = std::make_unique<MomPoly2[]>(2);
     for (int h = 0; h < 2; h++)
         for (int v = 0; v < n[h]; v++)
         {
@@ -265,6 +262,7 @@ extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* con
             if (r1 - r0 > 8) return -1;
             for (int j = 0; j < r1 - r0; j++) rw = rset(rw, j, ring[h][r0 + j]);
             mp[h].ring[v] = rw;
+            mp[h].estart[v] = (uint16_t)r0;
         }
     Moments mo[32];
     simt::run_warp([&](int lane) {
@@ -274,11 +272,7 @@ extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* con
         if (sub.any_warp(do_mo))     // assemble_gather_kernel: the warp enters when either fragment needs it
         {
             sub.sync();
-            CutState c;
-            c.hi = do_mo ? n[h] : 0;
-            c.live = lowmask64(c.hi);
-            c.c = c.k = 0ull;
-            sub_fragment_moments<16>(mp[h], c, sub, do_mo, mo[lane]);
+            sub_fragment_moments2<16>(mp[h], do_mo ? n[h] : 0, sub, do_mo, mo[lane]);
         }
     });
     for (int h = 0; h < 2; h++)
