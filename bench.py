@@ -384,6 +384,9 @@ def main():
     # ---- e2e: host buffers in, host buffers out, every step ----
     e2e = bench_secondary.config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res, n_my, barrier, allreduce, dist)
 
+    # ---- the final fragment gather (the only collective; after the hot path, reported separately) ----
+    gather = bench_secondary.final_gather(torch, dev, rank, world, res, barrier, allreduce, dist) if world > 1 else None
+
     # ---- secondary configs (rank 0 drives configs 2 and 3: a single event is never split; config 5 is sharded) ----
     secondary = {}
     if not args.no_secondary:
@@ -442,6 +445,8 @@ def main():
                      "frac": alg_flops / (ms_per_step * 1e-3) / 1e12 / fp32_peak if fp32_peak else None},
             "dma_ceiling": dma,
         }
+        if gather:
+            line["gather"] = gather
         for k in ("config3", "config2", "config5"):
             if k in secondary:
                 line[k] = secondary[k]

@@ -143,6 +143,54 @@ def config4_e2e(args, torch, dev, local, rank, world, streams, batch_views, res,
                       "kernels of consecutive batches ordered by a CUDA event"}
 
 
+# ------------------------------------------------------------------------------------------------ final gather
+def final_gather(torch, dev, rank, world, res, barrier, allreduce, dist):
+    """The only collective of the job (north star: NCCL over NVLink only for the final fragment gather): every rank packs
+    the fragments of its resident batches into ONE device blob (surtr_download_blob_async with a device destination:
+    records | float3 positions | ring lengths | ring entries per batch, back to back) and rank 0 receives all of them with
+    one all_gather of the sizes + one grouped send / recv (sharding.gather_blobs).  Timed with CUDA events on rank 0,
+    after a warm-up gather; checked by a device-side checksum of every rank's bytes."""
+    from surtr_b200 import sharding
+    al = lambda x: (int(x) + 255) // 256 * 256
+    caps = []
+    for b in res:
+        c = b.cx.counts()
+        caps.append(al(64 * int(c.n_fragments)) + al(12 * int(c.n_verts)) + al(int(c.n_verts)) + al(2 * int(c.n_ring)))
+    blob = torch.zeros(sum(caps) + 8, dtype=torch.uint8, device=dev)
+    at, frags = 0, 0
+    for b, cap in zip(res, caps):
+        L = b.cx.download_blob_into_async(blob.data_ptr() + at, cap)
+        frags += int(L.n_fragments)
+        at += cap
+    for b in res:
+        b.cx.sync()
+    blob = blob[:at]
+    check = lambda t: int(t[:t.numel() // 8 * 8].view(torch.int64).sum().item())
+    mine = torch.tensor([check(blob)], dtype=torch.int64, device=dev)
+    sums = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sums, mine)
+    sharding.gather_blobs(blob, 0)          # NCCL warm-up (connections, buffers)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    got = sharding.gather_blobs(blob, 0)
+    g1.record()
+    torch.cuda.synchronize()
+    total_frags = allreduce(frags, dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        buf, off = got
+        for r in range(world):
+            assert check(buf[off[r]:off[r + 1]]) == int(sums[r].item()), f"gathered bytes of rank {r} differ from what it sent"
+        ms = g0.elapsed_time(g1)
+        out = {"ms": ms, "bytes_total": int(off[-1]), "bytes_received": int(off[-1] - off[1]), "fragments_gathered": int(total_frags),
+               "gbs_into_rank0": (off[-1] - off[1]) / (ms * 1e-3) / 1e9,
+               "backend": "nccl: all_gather(sizes) + one grouped send/recv (batch_isend_irecv), one contiguous blob per rank, no padding",
+               "checked": "int64 checksum of every rank's blob, computed by the sender and on the received slice"}
+    barrier()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ DMA ceiling
 def dma_ceiling(torch, dev, world, barrier, allreduce, dist, mib: int = 256, reps: int = 4):
     """Host<->device copy bandwidth of the box with every rank copying at once: pinned 256 MiB buffers, one direction at

@@ -192,7 +192,8 @@ int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint6
 /* Output blob = the arrays of surtr_download_fragments_packed (records | float3 positions | one byte of ring length per
  * vertex | ring entries) at the byte offsets returned in *out, assembled on the device and moved with ONE copy on the
  * context's copy stream.  Waits for the event (which sizes the blob); SURTR_ERR_INVALID with *out filled in when
- * `capacity` is too small.  Completion rules as surtr_download_fragments_async. */
+ * `capacity` is too small.  Completion rules as surtr_download_fragments_async.  `host_blob` may also point to DEVICE
+ * memory (the copy is issued with cudaMemcpyDefault): that is how the multi-GPU gather gets one contiguous blob per rank. */
 typedef struct surtr_out_layout {
     uint64_t fragments, verts3, ring_len, ring, total;   /* byte offsets, total size */
     uint64_t n_fragments, n_verts, n_ring;

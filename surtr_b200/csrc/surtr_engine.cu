@@ -898,7 +898,7 @@ int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity
                                             reinterpret_cast<uint4*>(d + out->fragments), reinterpret_cast<float*>(d + out->verts3),
                                             d + out->ring_len, reinterpret_cast<uint16_t*>(d + out->ring));
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(host_blob, d, at, cudaMemcpyDeviceToHost, cs));   // ONE device -> host copy
+    CK(cudaMemcpyAsync(host_blob, d, at, cudaMemcpyDefault, cs));   // ONE copy (the destination may also be device memory: the multi-GPU gather packs into a device tensor)
     if (ctx->copy_stream)
     {
         CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));

@@ -3,9 +3,13 @@
 #include "Engine.h"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <map>
 #include <string>
+#include <tuple>
 
 namespace VMACH
 {
@@ -16,42 +20,6 @@ float ConvexHullFace::CalcArea()
 	return 0.5f * d1.Cross(d2).Length();
 }
 
-void ConvexHullEdge::LinkFace(ConvexHullFace* face)
-{
-	if (Face1 != nullptr && Face2 != nullptr)
-		return;
-	(Face1 == nullptr ? Face1 : Face2) = face;
-}
-
-void ConvexHullEdge::EraseFace(ConvexHullFace* face)
-{
-	if (Face1 != face && Face2 != face)
-		return;
-	(Face1 == face ? Face1 : Face2) = nullptr;
-}
-
-ConvexHull::ConvexHull(const std::vector<ConvexHullVertex>& pointCloud, uint32_t limitCnt) : m_limitCnt(limitCnt), m_pointCloud(pointCloud)
-{
-	m_pointVolume.assign(m_pointCloud.size(), 0.0f);
-	CreateConvexHull();
-}
-
-ConvexHull::ConvexHull(const std::vector<Vector3>& pointCloud, uint32_t limitCnt) : m_limitCnt(limitCnt)
-{
-	for (const Vector3& v : pointCloud)
-		m_pointCloud.emplace_back(v);
-	m_pointVolume.assign(m_pointCloud.size(), 0.0f);
-	CreateConvexHull();
-}
-
-bool ConvexHull::Contains(const ConvexHullVertex& point) const
-{
-	for (const ConvexHullFace& f : m_faceList)
-		if (Volume(f, point) <= 0)
-			return false;
-	return true;
-}
-
 bool ConvexHull::Colinear(const ConvexHullVertex& p1, const ConvexHullVertex& p2, const ConvexHullVertex& p3)
 {
 	return ((p3.z - p1.z) * (p2.y - p1.y) - (p2.z - p1.z) * (p3.y - p1.y)) == 0 &&
@@ -59,187 +27,260 @@ bool ConvexHull::Colinear(const ConvexHullVertex& p1, const ConvexHullVertex& p2
 		   ((p2.x - p1.x) * (p3.y - p1.y) - (p2.y - p1.y) * (p3.x - p1.x)) == 0;
 }
 
-// Signed volume of the tetrahedron (face, point), float arithmetic in the reference's term order (VMACH.cpp:919-938).
-float ConvexHull::Volume(const ConvexHullFace& face, const ConvexHullVertex& point)
+// Signed volume of the tetrahedron (triangle, point) in float, the reference's term order (VMACH.cpp:919-938):
+// negative = the point sees the triangle from outside.
+static inline float SignedVolume(const Vector3& a, const Vector3& b, const Vector3& c, const Vector3& p)
 {
-	const float ax = face.Vertices[0].x - point.x, ay = face.Vertices[0].y - point.y, az = face.Vertices[0].z - point.z;
-	const float bx = face.Vertices[1].x - point.x, by = face.Vertices[1].y - point.y, bz = face.Vertices[1].z - point.z;
-	const float cx = face.Vertices[2].x - point.x, cy = face.Vertices[2].y - point.y, cz = face.Vertices[2].z - point.z;
+	const float ax = a.x - p.x, ay = a.y - p.y, az = a.z - p.z;
+	const float bx = b.x - p.x, by = b.y - p.y, bz = b.z - p.z;
+	const float cx = c.x - p.x, cy = c.y - p.y, cz = c.z - p.z;
 	return ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
 }
 
-// The reference keys an edge by the XOR of string hashes of its end points printed with std::to_string (six
-// decimals, VMACH.cpp:940-947).  End points closer than the printing resolution therefore share a key; keeping the
-// same key keeps the same hull on such inputs.
-size_t ConvexHull::Key2Edge(const ConvexHullVertex& p1, const ConvexHullVertex& p2)
+float ConvexHull::Volume(const ConvexHullFace& face, const ConvexHullVertex& point)
 {
-	std::hash<std::string> h;
-	return h(std::to_string(p1.x) + std::to_string(p1.y) + std::to_string(p1.z)) ^
-		   h(std::to_string(p2.x) + std::to_string(p2.y) + std::to_string(p2.z));
+	return SignedVolume(face.Vertices[0], face.Vertices[1], face.Vertices[2], point);
 }
 
-void ConvexHull::CreateEdge(const ConvexHullVertex& p1, const ConvexHullVertex& p2, ConvexHullFace& newFace)
+float ConvexHull::TetVolume(const Tri& t, int p) const { return SignedVolume(m_pos[t.v[0]], m_pos[t.v[1]], m_pos[t.v[2]], m_pos[p]); }
+
+ConvexHull::ConvexHull(const std::vector<ConvexHullVertex>& pointCloud, uint32_t limitCnt)
 {
-	const size_t key = Key2Edge(p1, p2);
-	auto it = m_edgeMap.find(key);
-	if (it == m_edgeMap.end())
+	m_pos.assign(pointCloud.begin(), pointCloud.end());
+	Build(limitCnt);
+}
+
+ConvexHull::ConvexHull(const std::vector<Vector3>& pointCloud, uint32_t limitCnt) : m_pos(pointCloud) { Build(limitCnt); }
+
+// Key of the edge table.  Reference: hash(print(p1)) ^ hash(print(p2)) -- symmetric, equal for end points that print
+// alike, and 0 for ANY edge whose two end points print alike.  Same partition with two class ids.
+uint64_t ConvexHull::EdgeKey(int a, int b) const
+{
+	const uint32_t ca = m_printClass[a], cb = m_printClass[b];
+	if (ca == cb)
+		return ~0ull;
+	return ((uint64_t)std::min(ca, cb) << 32) | std::max(ca, cb);
+}
+
+void ConvexHull::AttachEdge(int a, int b, int tri)
+{
+	const uint64_t key = EdgeKey(a, b);
+	auto it = m_rimOf.find(key);
+	if (it == m_rimOf.end())
 	{
-		m_edgeList.emplace_back(p1, p2);
-		it = m_edgeMap.insert({ key, &m_edgeList.back() }).first;
+		m_rims.push_back(Rim{ a, b });
+		it = m_rimOf.emplace(key, (int)m_rims.size() - 1).first;
 	}
-	it->second->LinkFace(&newFace);
+	Rim& r = m_rims[it->second];
+	if (r.f1 >= 0 && r.f2 >= 0)
+		return;                          // both sides taken: the triangle stays unlinked, as in the reference
+	(r.f1 < 0 ? r.f1 : r.f2) = tri;
 }
 
-void ConvexHull::CreateFace(const ConvexHullVertex& p1, const ConvexHullVertex& p2, const ConvexHullVertex& p3, const ConvexHullVertex& innerPoint)
+// New triangle (a, b, c), wound so that `inner` lies on its positive side; its three edges join the edge table.
+void ConvexHull::AddTriangle(int a, int b, int c, int inner)
 {
-	m_faceList.emplace_back(p1, p2, p3);
-	ConvexHullFace& face = m_faceList.back();
-	m_addedFaceVec.push_back(&face);
-	if (Volume(face, innerPoint) < 0)   // orient so that the inner point is on the positive side
-		face.Rewind();
-	CreateEdge(p1, p2, face);
-	CreateEdge(p1, p3, face);
-	CreateEdge(p2, p3, face);
+	Tri t;
+	t.v[0] = a; t.v[1] = b; t.v[2] = c;
+	if (TetVolume(t, inner) < 0)
+		std::swap(t.v[0], t.v[2]);
+	m_tris.push_back(t);
+	const int id = (int)m_tris.size() - 1;
+	m_fresh.push_back(id);
+	AttachEdge(a, b, id);
+	AttachEdge(a, c, id);
+	AttachEdge(b, c, id);
 }
 
-void ConvexHull::AddPointToHull(const ConvexHullVertex& point)
+// The point p joins the hull: triangles that see it are marked, every horizon edge (one marked, one unmarked triangle)
+// gets a new triangle to p.  Edges appended by those new triangles are visited by the same pass (their second side is
+// still open, so they are skipped), which is the reference's iteration over a list it appends to.
+void ConvexHull::Absorb(int p)
 {
-	bool any = false;
-	for (ConvexHullFace& face : m_faceList)
-		if (Volume(face, point) < 0)
+	for (int t = 0; t < (int)m_tris.size(); t++)
+		if (m_tris[t].alive && TetVolume(m_tris[t], p) < 0)
 		{
-			face.Visible = true;
-			m_visibleFaceVec.push_back(&face);
-			any = true;
+			m_tris[t].visible = true;
+			m_lit.push_back(t);
 		}
-	if (!any)
+	if (m_lit.empty())
 		return;
-	// horizon edges (one visible, one hidden face) get a new face to the point; edges appended meanwhile are visited too
-	for (auto it = m_edgeList.begin(); it != m_edgeList.end(); ++it)
+	for (size_t e = 0; e < m_rims.size(); e++)
 	{
-		ConvexHullEdge& edge = *it;
-		if (edge.Face1 == nullptr || edge.Face2 == nullptr)
+		if (!m_rims[e].alive || m_rims[e].f1 < 0 || m_rims[e].f2 < 0)
 			continue;
-		if (edge.Face1->Visible && edge.Face2->Visible)
-			edge.Remove = true;
-		else if (edge.Face1->Visible || edge.Face2->Visible)
+		const bool v1 = m_tris[m_rims[e].f1].visible, v2 = m_tris[m_rims[e].f2].visible;
+		if (v1 && v2)
 		{
-			if (edge.Face1->Visible)
-				std::swap(edge.Face1, edge.Face2);
-			// now Face1 is hidden and Face2 visible; the orientation probe is the visible face's vertex off the edge
-			// (FindInnerPoint(face2, edge), VMACH.cpp:950-962, 1028)
-			ConvexHullVertex inner = edge.Face2->Vertices[0];
-			bool found = false;
-			for (int i = 0; i < 3 && !found; i++)
-			{
-				const ConvexHullVertex& v = edge.Face2->Vertices[i];
-				if (v == edge.EndPoints[0] || v == edge.EndPoints[1])
-					continue;
-				inner = v;
-				found = true;
-			}
-			edge.EraseFace(edge.Face2);
-			CreateFace(edge.EndPoints[0], edge.EndPoints[1], point, inner);
+			m_rims[e].remove = true;
+			continue;
 		}
+		if (!v1 && !v2)
+			continue;
+		if (v1)
+			std::swap(m_rims[e].f1, m_rims[e].f2);       // f1 = the hidden side, f2 = the side p sees
+		const int a = m_rims[e].a, b = m_rims[e].b, seen = m_rims[e].f2;
+		// orientation probe: the marked triangle's corner off the edge, compared by VALUE like the reference's operator==
+		int inner = m_tris[seen].v[0];
+		for (int i = 0; i < 3; i++)
+		{
+			const int v = m_tris[seen].v[i];
+			if (m_valueClass[v] == m_valueClass[a] || m_valueClass[v] == m_valueClass[b])
+				continue;
+			inner = v;
+			break;
+		}
+		// the marked side lets go of the edge (first matching slot, as ConvexHullEdge::EraseFace)
+		if (m_rims[e].f1 == seen) m_rims[e].f1 = -1; else m_rims[e].f2 = -1;
+		AddTriangle(a, b, p, inner);                     // (may grow m_rims: index-based access only)
 	}
 }
 
-bool ConvexHull::BuildFirstHull()
+// End of a step: edges between two marked triangles and the marked triangles themselves leave the hull.
+void ConvexHull::Sweep()
 {
-	if (m_pointCloud.size() <= 3)
+	m_lit.clear();
+	m_fresh.clear();
+	for (Rim& r : m_rims)
+		if (r.alive && r.remove)
+		{
+			m_rimOf.erase(EdgeKey(r.a, r.b));
+			r.alive = false;
+		}
+	for (Tri& t : m_tris)
+		if (t.alive && t.visible)
+			t.alive = false;
+}
+
+// First tetrahedron: the point of largest x, the point farthest from it, the point spanning the largest triangle with
+// those two, the point of largest signed volume over that triangle -- first maximum wins in each scan (std::max_element).
+bool ConvexHull::SeedTetrahedron()
+{
+	const int n = (int)m_pos.size();
+	if (n <= 3)
 		return false;
-	auto& P = m_pointCloud;
-	const auto v1 = std::max_element(P.begin(), P.end(), [](const ConvexHullVertex& a, const ConvexHullVertex& b) { return a.x < b.x; });
-	auto dist1 = [&](const ConvexHullVertex& a) {
-		return std::sqrt(std::pow(a.x - v1->x, 2) + std::pow(a.y - v1->y, 2) + std::pow(a.z - v1->z, 2));
+	int i1 = 0;
+	for (int i = 1; i < n; i++)
+		if (m_pos[i1].x < m_pos[i].x) i1 = i;
+	auto far = [&](int i) {
+		const double dx = m_pos[i].x - m_pos[i1].x, dy = m_pos[i].y - m_pos[i1].y, dz = m_pos[i].z - m_pos[i1].z;   // float differences, squared in double
+		return std::sqrt(dx * dx + dy * dy + dz * dz);
 	};
-	const auto v2 = std::max_element(P.begin(), P.end(), [&](const ConvexHullVertex& a, const ConvexHullVertex& b) { return dist1(a) < dist1(b); });
-	const auto v3 = std::max_element(P.begin(), P.end(), [&](const ConvexHullVertex& a, const ConvexHullVertex& b) {
-		ConvexHullFace f1(*v1, *v2, a), f2(*v1, *v2, b);
-		return f1.CalcArea() < f2.CalcArea();
-	});
-	const auto v4 = std::max_element(P.begin(), P.end(), [&](const ConvexHullVertex& a, const ConvexHullVertex& b) {
-		const ConvexHullFace f(*v1, *v2, *v3);
-		return Volume(f, a) < Volume(f, b);
-	});
-	v1->Processed = v2->Processed = v3->Processed = v4->Processed = true;
-	m_processedPointCnt = 4;
-	CreateFace(*v1, *v2, *v3, *v4);
-	CreateFace(*v1, *v2, *v4, *v3);
-	CreateFace(*v1, *v3, *v4, *v2);
-	CreateFace(*v2, *v3, *v4, *v1);
+	int i2 = 0;
+	for (int i = 1; i < n; i++)
+		if (far(i2) < far(i)) i2 = i;
+	auto area = [&](int i) { return ConvexHullFace(m_pos[i1], m_pos[i2], m_pos[i]).CalcArea(); };
+	int i3 = 0;
+	for (int i = 1; i < n; i++)
+		if (area(i3) < area(i)) i3 = i;
+	auto vol = [&](int i) { return SignedVolume(m_pos[i1], m_pos[i2], m_pos[i3], m_pos[i]); };
+	int i4 = 0;
+	for (int i = 1; i < n; i++)
+		if (vol(i4) < vol(i)) i4 = i;
+	m_used[i1] = m_used[i2] = m_used[i3] = m_used[i4] = 1;
+	m_usedCnt = 4;
+	AddTriangle(i1, i2, i3, i4);
+	AddTriangle(i1, i2, i4, i3);
+	AddTriangle(i1, i3, i4, i2);
+	AddTriangle(i2, i3, i4, i1);
 	return true;
 }
 
-void ConvexHull::CreateConvexHull()
+void ConvexHull::Build(uint32_t limitCnt)
 {
-	if (!BuildFirstHull())
-		return;
-	// every point's outside volume is its own sequential sum: the points are spread over the worker pool, the order
-	// of the additions per point is the reference's
-	constexpr size_t CHUNK = 256;
-	const size_t n_chunks = (m_pointCloud.size() + CHUNK - 1) / CHUNK;
-	SurtrHost::detail::parallel_for(n_chunks, [&](size_t c) {
-		for (size_t i = c * CHUNK; i < std::min(m_pointCloud.size(), (c + 1) * CHUNK); i++)
-		{
-			if (m_pointCloud[i].Processed)
-				continue;
-			for (const ConvexHullFace& f : m_faceList)
-				m_pointVolume[i] += std::max(0.0f, Volume(f, m_pointCloud[i]));
-		}
-	});
-	if (m_limitCnt == 0)
-		m_limitCnt = (uint32_t)m_pointCloud.size();
-	while (m_processedPointCnt < m_limitCnt)
+	const size_t n = m_pos.size();
+	m_used.assign(n, 0);
+	m_outside.assign(n, 0.0f);
+	// point classes: exact coordinates (operator== of the reference's vertices) and six-decimal prints (its edge keys)
+	m_printClass.resize(n);
+	m_valueClass.resize(n);
 	{
-		// greedy: the point with the largest outside volume joins the hull
-		const int k = (int)std::distance(m_pointVolume.begin(), std::max_element(m_pointVolume.begin(), m_pointVolume.end()));
-		AddPointToHull(m_pointCloud[k]);
-		m_pointCloud[k].Processed = true;
-		m_pointVolume[k] = -FLT_MAX;
-		m_processedPointCnt++;
-		SurtrHost::detail::parallel_for(n_chunks, [&](size_t c) {
-			for (size_t i = c * CHUNK; i < std::min(m_pointCloud.size(), (c + 1) * CHUNK); i++)
-			{
-				if (m_pointCloud[i].Processed)
-					continue;
-				float removed = 0.0f, added = 0.0f;
-				for (ConvexHullFace* f : m_visibleFaceVec)
-					removed += std::max(0.0f, Volume(*f, m_pointCloud[i]));
-				for (ConvexHullFace* f : m_addedFaceVec)
-					added += std::max(0.0f, Volume(*f, m_pointCloud[i]));
-				m_pointVolume[i] -= removed;
-				m_pointVolume[i] += added;
-			}
+		std::map<std::tuple<float, float, float>, uint32_t> byValue;
+		std::map<std::string, uint32_t> byPrint;
+		char buf[192];
+		for (size_t i = 0; i < n; i++)
+		{
+			m_valueClass[i] = byValue.emplace(std::make_tuple(m_pos[i].x, m_pos[i].y, m_pos[i].z), (uint32_t)byValue.size()).first->second;
+			std::snprintf(buf, sizeof buf, "%f%f%f", m_pos[i].x, m_pos[i].y, m_pos[i].z);   // std::to_string(float) prints "%f"
+			m_printClass[i] = byPrint.emplace(buf, (uint32_t)byPrint.size()).first->second;
+		}
+	}
+	if (!SeedTetrahedron())
+		return;
+	// a point's outside volume is its own sequential sum, so the points spread over the worker pool in chunks
+	constexpr size_t CHUNK = 256;
+	const size_t nChunks = (n + CHUNK - 1) / CHUNK;
+	auto forUnused = [&](const std::function<void(size_t)>& fn) {
+		SurtrHost::detail::parallel_for(nChunks, [&](size_t c) {
+			for (size_t i = c * CHUNK; i < std::min(n, (c + 1) * CHUNK); i++)
+				if (!m_used[i]) fn(i);
 		});
-		CleanUp();
+	};
+	forUnused([&](size_t i) {
+		for (const Tri& t : m_tris)
+			if (t.alive) m_outside[i] += std::max(0.0f, TetVolume(t, (int)i));
+	});
+	// (m_fresh still lists the four seed triangles here: the reference clears its added-face list only at the end of a
+	// step, VMACH.cpp:1144-1146, so the first step adds their volumes a second time -- kept, it decides the greedy order)
+	const uint32_t limit = limitCnt == 0 ? (uint32_t)n : limitCnt;
+	while (m_usedCnt < limit)
+	{
+		// greedy: the unused point with the largest outside volume (first maximum) joins the hull
+		const int k = (int)(std::max_element(m_outside.begin(), m_outside.end()) - m_outside.begin());
+		Absorb(k);
+		m_used[k] = 1;
+		m_outside[k] = -FLT_MAX;
+		m_usedCnt++;
+		forUnused([&](size_t i) {
+			float gone = 0.0f, came = 0.0f;
+			for (int t : m_lit) gone += std::max(0.0f, TetVolume(m_tris[t], (int)i));
+			for (int t : m_fresh) came += std::max(0.0f, TetVolume(m_tris[t], (int)i));
+			m_outside[i] -= gone;
+			m_outside[i] += came;
+		});
+		Sweep();
 	}
 }
 
-void ConvexHull::CleanUp()
+bool ConvexHull::Contains(const ConvexHullVertex& point) const
 {
-	m_visibleFaceVec.clear();
-	m_addedFaceVec.clear();
-	for (auto it = m_edgeList.begin(); it != m_edgeList.end();)
-	{
-		if (it->Remove)
-		{
-			m_edgeMap.erase(Key2Edge(it->EndPoints[0], it->EndPoints[1]));
-			it = m_edgeList.erase(it);
-		}
-		else
-			++it;
-	}
-	m_faceList.remove_if([](const ConvexHullFace& f) { return f.Visible; });
+	for (const Tri& t : m_tris)
+		if (t.alive && SignedVolume(m_pos[t.v[0]], m_pos[t.v[1]], m_pos[t.v[2]], point) <= 0)
+			return false;
+	return true;
+}
+
+std::vector<std::array<int, 3>> ConvexHull::FaceIndices() const
+{
+	std::vector<std::array<int, 3>> out;
+	for (const Tri& t : m_tris)
+		if (t.alive) out.push_back({ t.v[0], t.v[1], t.v[2] });
+	return out;
+}
+
+const std::list<ConvexHullFace> ConvexHull::GetFaces() const
+{
+	std::list<ConvexHullFace> out;
+	for (const Tri& t : m_tris)
+		if (t.alive) out.emplace_back(m_pos[t.v[0]], m_pos[t.v[1]], m_pos[t.v[2]]);
+	return out;
+}
+
+const std::list<ConvexHullEdge> ConvexHull::GetEdges() const
+{
+	std::list<ConvexHullEdge> out;
+	for (const Rim& r : m_rims)
+		if (r.alive) out.emplace_back(m_pos[r.a], m_pos[r.b]);
+	return out;
 }
 
 std::vector<Vector3> GenerateICHNormal(const std::vector<Vector3>& vertices, int ichIncludePointLimit)
 {
-	ConvexHull ich(vertices, (uint32_t)ichIncludePointLimit);
+	const ConvexHull ich(vertices, (uint32_t)ichIncludePointLimit);
 	std::vector<Vector3> normals;
-	for (const ConvexHullFace& f : ich.GetFaces())
+	for (const std::array<int, 3>& f : ich.FaceIndices())
 	{
-		Vector3 n = (f.Vertices[1] - f.Vertices[0]).Cross(f.Vertices[2] - f.Vertices[0]);
+		Vector3 n = (vertices[f[1]] - vertices[f[0]]).Cross(vertices[f[2]] - vertices[f[0]]);
 		n.Normalize();
 		normals.push_back(n);
 	}

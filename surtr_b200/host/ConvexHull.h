@@ -1,12 +1,21 @@
 // ConvexHull.h -- host-side mirror of VMACH::ConvexHull (Inc/VMACH.h:88-165, Src/VMACH.cpp:869-1203): the greedy
 // incremental convex hull ("ICH") whose face normals seed the k-DOPs (Surtr::GenerateICHNormal, Surtr.cpp:1961-1982).
 // Tiny and inherently sequential (<= 20 points at ACH time, <= 4 at refit time): it stays on the host, exactly as
-// SURVEY.md section 2 row 4 scopes it.  Own implementation; the visiting orders that decide the order of the output
-// faces (edge list order, first-maximum selection) follow the reference so the k-DOP plane order is the same.
+// SURVEY.md section 2 row 4 scopes it.
+//
+// The public types keep the reference's names (drop-in surface); the hull itself is an index-based structure of its
+// own: triangles and edges are records in two append-only arrays that refer to points by INDEX, removal is a flag
+// (array order = the reference's list order, which decides the order of the output faces and so of the k-DOP planes),
+// and the edge table is keyed by a pair of small integers instead of a hash of printed coordinates.  The reference
+// keys an edge by hash(to_string(p1)) ^ hash(to_string(p2)) (VMACH.cpp:940-947): end points that print alike (closer
+// than 1e-6) share a key, and an edge whose two end points print alike has key 0 whatever they are.  Those collisions
+// change which faces get built on near-degenerate clouds, so they are reproduced -- through a "print class" per point
+// (points with the same six-decimal print) -- and only there: distinct classes never collide.
 #pragma once
 
 #include "SimpleMath.h"
 
+#include <array>
 #include <cstdint>
 #include <list>
 #include <unordered_map>
@@ -39,15 +48,13 @@ struct ConvexHullFace
 struct ConvexHullEdge
 {
 	bool Remove;
-	ConvexHullFace* Face1;
+	ConvexHullFace* Face1;   // (not populated by GetEdges(): the hull keeps face indices, not pointers)
 	ConvexHullFace* Face2;
 	ConvexHullVertex EndPoints[2];
 	ConvexHullEdge(const ConvexHullVertex& p1, const ConvexHullVertex& p2) : Remove(false), Face1(nullptr), Face2(nullptr)
 	{
 		EndPoints[0] = p1; EndPoints[1] = p2;
 	}
-	void LinkFace(ConvexHullFace* face);
-	void EraseFace(ConvexHullFace* face);
 };
 
 class ConvexHull
@@ -57,28 +64,39 @@ public:
 	ConvexHull(const std::vector<Vector3>& pointCloud, uint32_t limitCnt);
 
 	bool Contains(const ConvexHullVertex& point) const;
-	const std::list<ConvexHullFace> GetFaces() const { return m_faceList; }
-	const std::list<ConvexHullEdge> GetEdges() const { return m_edgeList; }
+	const std::list<ConvexHullFace> GetFaces() const;   // live triangles, creation order
+	const std::list<ConvexHullEdge> GetEdges() const;   // live edges, creation order
 
 	static bool Colinear(const ConvexHullVertex& p1, const ConvexHullVertex& p2, const ConvexHullVertex& p3);
 	static float Volume(const ConvexHullFace& face, const ConvexHullVertex& point);
 
-private:
-	static size_t Key2Edge(const ConvexHullVertex& p1, const ConvexHullVertex& p2);
-	void CreateFace(const ConvexHullVertex& p1, const ConvexHullVertex& p2, const ConvexHullVertex& p3, const ConvexHullVertex& innerPoint);
-	void CreateEdge(const ConvexHullVertex& p1, const ConvexHullVertex& p2, ConvexHullFace& newFace);
-	void AddPointToHull(const ConvexHullVertex& point);
-	bool BuildFirstHull();
-	void CreateConvexHull();
-	void CleanUp();
+	// the live triangles as point indices into the input cloud (creation order): what GenerateICHNormal consumes
+	std::vector<std::array<int, 3>> FaceIndices() const;
+	const std::vector<Vector3>& Points() const { return m_pos; }
 
-	std::vector<ConvexHullFace*> m_visibleFaceVec, m_addedFaceVec;
-	uint32_t m_limitCnt = 0, m_processedPointCnt = 0;
-	std::vector<ConvexHullVertex> m_pointCloud;
-	std::vector<float> m_pointVolume;
-	std::list<ConvexHullFace> m_faceList;
-	std::list<ConvexHullEdge> m_edgeList;
-	std::unordered_map<size_t, ConvexHullEdge*> m_edgeMap;
+private:
+	struct Tri { int v[3]; bool visible = false, alive = true; };
+	struct Rim { int a, b; int f1 = -1, f2 = -1; bool remove = false, alive = true; };   // an edge with its (up to) two triangles
+
+	void Build(uint32_t limitCnt);
+	bool SeedTetrahedron();
+	float TetVolume(const Tri& t, int p) const;
+	uint64_t EdgeKey(int a, int b) const;
+	void AttachEdge(int a, int b, int tri);
+	void AddTriangle(int a, int b, int c, int inner);
+	void Absorb(int p);
+	void Sweep();
+
+	std::vector<Vector3> m_pos;
+	std::vector<char> m_used;
+	std::vector<float> m_outside;               // summed outside volume of every unused point against the current hull
+	std::vector<uint32_t> m_printClass;         // points with the same six-decimal print share a class
+	std::vector<uint32_t> m_valueClass;         // points with exactly equal coordinates share a class
+	std::vector<Tri> m_tris;
+	std::vector<Rim> m_rims;
+	std::unordered_map<uint64_t, int> m_rimOf;  // edge key -> index into m_rims
+	std::vector<int> m_lit, m_fresh;            // triangles the last absorbed point saw / added
+	uint32_t m_usedCnt = 0;
 };
 
 // Surtr::GenerateICHNormal (Surtr.cpp:1961-1982): normalised (v1-v0) x (v2-v0) of every hull face, list order.

@@ -47,3 +47,36 @@ def gather_fragments(rec_bytes: torch.Tensor, verts: torch.Tensor, ring_off: tor
     if parts[0] is None:
         return None
     return list(zip(*parts))
+
+
+def gather_blobs(blob: torch.Tensor, dst: int = 0, group=None):
+    """Final fragment gather, one blob per rank: `blob` = the rank's fragments as ONE contiguous uint8 tensor (the
+    output blob of surtr_download_blob_async packed into device memory, or several of them back to back).  One
+    all_gather of the sizes (one int64 per rank, the only host synchronisation), then ONE grouped send / recv
+    (ncclGroupStart .. ncclGroupEnd through batch_isend_irecv): every rank sends its bytes straight into its slice of a
+    single receive buffer on `dst` -- no padding, no per-array collectives.  Returns (buffer, offsets[world + 1]) on
+    `dst`, None elsewhere.  Runs over gloo on CPU tensors in the tests."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    blob = blob.contiguous().view(torch.uint8).reshape(-1)
+    sizes = torch.zeros(world, dtype=torch.int64, device=blob.device)
+    mine = torch.tensor([blob.numel()], dtype=torch.int64, device=blob.device)
+    dist.all_gather_into_tensor(sizes, mine, group=group) if blob.is_cuda else dist.all_gather(list(sizes.split(1)), mine, group=group)
+    sizes = sizes.tolist()
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + int(n))
+    ops = []
+    buf = None
+    if rank == dst:
+        buf = torch.empty(off[-1], dtype=torch.uint8, device=blob.device)
+        buf[off[rank]:off[rank + 1]].copy_(blob)
+        for r in range(world):
+            if r != dst and sizes[r]:
+                ops.append(dist.P2POp(dist.irecv, buf[off[r]:off[r + 1]], r, group))
+    elif blob.numel():
+        ops.append(dist.P2POp(dist.isend, blob, dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return (buf, off) if rank == dst else None

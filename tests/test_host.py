@@ -130,6 +130,32 @@ def test_host_ich_normals_match_reference():
         assert np.array_equal(bits(got), bits(want)), i
 
 
+@pytest.mark.skipif(not common.have_ref(), reason="needs the reference build (oracle/_ref)")
+def test_host_ich_on_near_degenerate_clouds_matches_reference_live():
+    """The index-based hull against the reference build, live, where the reference's edge keys collide: points closer
+    than the six decimals std::to_string prints (same key for different edges, key 0 for an edge between two such
+    points), exact duplicates, coplanar and collinear runs, and plain random clouds at several limits."""
+    from oracle import refapi as R
+    rng = np.random.RandomState(11)
+    clouds = []
+    for n in (5, 8, 30, 200):
+        clouds.append(rng.uniform(-1, 1, (n, 3)))
+    base = rng.uniform(-1, 1, (12, 3))
+    clouds.append(np.concatenate([base, base + 3e-7, base[:5] - 2e-7]))                      # near-duplicates: print alike
+    clouds.append(np.concatenate([base, base[:6]]))                                            # exact duplicates
+    clouds.append(np.concatenate([base, np.c_[rng.uniform(-1, 1, (10, 2)), np.zeros(10)]]))    # a coplanar run
+    clouds.append(np.concatenate([base, np.outer(np.linspace(-1, 1, 7), [1, 2, 3]) * 0.3]))    # a collinear run
+    clouds.append(np.round(rng.uniform(-1, 1, (40, 3)), 1))                                    # lattice points: many ties
+    for ci, c in enumerate(clouds):
+        v = np.zeros((len(c), 4), np.float32)
+        v[:, :3] = c
+        for limit in (4, 6, 20, 0):
+            lim = min(limit, len(v)) if limit else 0
+            want = R.ich_normals(v, lim)
+            got = H.ich_normals(v, lim)
+            assert got.shape == want.shape and np.array_equal(bits(got), bits(want)), (ci, limit)
+
+
 @pytest.mark.gpu
 def test_host_refitting_matches_reference():
     """SurtrHost::Refitting (m_refittingTask, Surtr.cpp:1449-1455) batched on the GPU == the reference per piece."""

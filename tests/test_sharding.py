@@ -34,8 +34,13 @@ def _worker(rank, world, port, q):
     vols = torch.from_numpy(np.concatenate([f.volume for f in frs])) if frs else torch.zeros(0, dtype=torch.float64)
     cells = torch.from_numpy(np.concatenate([f.cell for f in frs]).astype(np.int64)) if frs else torch.zeros(0, dtype=torch.int64)
     got = [sharding.gather_variable(t) for t in (counts, verts, vols, cells)]
+    # the one-blob gather: everything the rank holds as one byte string
+    blob = torch.cat([t.contiguous().view(torch.uint8).reshape(-1) for t in (counts, verts, vols, cells)])
+    one = sharding.gather_blobs(blob)
     if rank == 0:
-        q.put([[x.numpy() for x in part] for part in got])
+        buf, off = one
+        q.put(([[x.numpy() for x in part] for part in got], buf.numpy(), off,
+               [int(t.numel() * t.element_size()) for t in (counts, verts, vols, cells)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,7 +55,13 @@ def test_shard_and_gather_world2():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    counts, verts, vols, cells = q.get(timeout=180)
+    (counts, verts, vols, cells), buf, off, sizes0 = q.get(timeout=180)
+    # one-blob gather: rank r's slice is its four arrays back to back
+    assert len(off) == world + 1 and off[-1] == len(buf)
+    for r in range(world):
+        want = np.concatenate([np.ascontiguousarray(a[r]).view(np.uint8).reshape(-1) for a in (counts, verts, vols, cells)])
+        assert np.array_equal(buf[off[r]:off[r + 1]], want)
+    assert off[1] == sum(sizes0)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
