@@ -53,7 +53,7 @@ extern "C" {
 #define SURTR_ERR_CUDA 1        /* a CUDA runtime call failed */
 #define SURTR_ERR_INVALID 2     /* bad argument / call order */
 #define SURTR_ERR_NO_DEVICE 3   /* no usable sm_100 device: the product path has no CPU fallback */
-#define SURTR_ERR_OVERFLOW 4    /* a (piece, cell) pair outgrew the largest on-chip clip tier */
+#define SURTR_ERR_OVERFLOW 4    /* some (piece, cell) pairs could not be cut: malformed rings or beyond the 16-bit index range */
 #define SURTR_ERR_NOMEM 5       /* device or pinned-host allocation failed */
 
 typedef struct surtr_ctx surtr_ctx;
@@ -81,6 +81,7 @@ typedef struct surtr_counts {
     uint64_t n_tier2;       /* pairs cut in the large on-chip tier: 65..256 vertex slots or ring degree 9..16 (diagnostic) */
     uint64_t n_tier3;       /* pairs cut in the global-memory tier: more than 256 vertex slots (diagnostic) */
     uint64_t n_tier1b;      /* pairs re-run in the 128-slot warp-per-pair tier (diagnostic) */
+    uint64_t n_failed;      /* pairs that could not be cut (malformed rings, > 65520 vertex slots): see surtr_failed_pairs */
 } surtr_counts;
 
 /* Device-side view of the last event's fragments (pointers stay valid until the next event / upload). */
@@ -149,8 +150,15 @@ int surtr_place_pattern(surtr_ctx* ctx, const float* scale3, const float* transl
 /* Asynchronous on the context stream: K1 k-DOP extents -> K2 broad phase + ordered compaction ->
  * K3 one-warp-per-pair half-space clipping -> K4 fragment assembly with moments. */
 int surtr_fracture_event(surtr_ctx* ctx);
-/* Waits for the event; grows internal buffers and re-runs once if a capacity estimate was too small. */
+/* Waits for the event; grows internal buffers (candidate list, clip tiers, the global tier's vertex and ring slots,
+ * fragment arrays) and re-runs it until nothing more is asked for.  The reference's Poly::ClipPolyhedron has no limit on
+ * vertex count or valence; here a piece may have up to 65520 vertices (ring entries are 16-bit) and ANY valence.
+ * Returns SURTR_ERR_OVERFLOW -- with *out filled in and the event complete -- when some pairs could not be cut
+ * (malformed rings, more than 65520 vertex slots during a cut, more than 65535 faces): they are listed by
+ * surtr_failed_pairs and produce no fragment; every other fragment of the event is valid and the downloads succeed. */
 int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out);
+/* (piece, cell) of every failed pair of the last event, 2 x uint32 per pair; *n_pairs = how many there are. */
+int surtr_failed_pairs(surtr_ctx* ctx, uint32_t* piece_cell, uint64_t capacity_pairs, uint64_t* n_pairs);
 
 /* --- outputs ------------------------------------------------------------------------------------------ */
 /* Any pointer may be NULL to skip that array.  Sizes come from surtr_event_counts. */

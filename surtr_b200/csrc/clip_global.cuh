@@ -14,41 +14,44 @@
 
 namespace surtr
 {
-constexpr int GD = 16;                  // ring slots per vertex in this tier
+constexpr int GD = 16;                  // ring slots per vertex in the large on-chip tier (shared-memory workspace)
 constexpr uint16_t G_NONE = 0xffffu;    // the reference's "-1" ring mark
+constexpr int8_t G_GONE = -2;           // comp of a slot whose vertex left the polyhedron in an EARLIER cut (lazy compaction)
 
-struct GlobalPoly   // views into one warp's workspace
+struct GlobalPoly   // views into one group's workspace
 {
     float *x, *y, *z;
-    uint16_t *ring, *old_ring;   // GD per vertex
-    uint8_t *deg, *old_deg;
+    uint16_t *ring, *old_ring;   // gd per vertex (old_ring: snapshot of the sequential replay, and the target of a compaction)
+    uint16_t *deg, *old_deg;
     int8_t* comp;
     uint16_t* id;                // renumbering / walk-target probe / face-start masks
     uint32_t* list;              // straddling half-edges (v | slot << 16), then walk targets; triangle bases
     float4* tri;                 // 2 per vertex slot: ordered fan-triangle records
-    int cap;
+    int cap;                     // vertex slots
+    int gd;                      // ring slots per vertex: GD in the on-chip tier, whatever the largest ring needs in the global-memory tier
 };
 
-__host__ __device__ constexpr size_t global_poly_bytes(size_t cap)
+__host__ __device__ constexpr size_t global_poly_bytes(size_t cap, size_t gd = GD)
 {
-    return cap * (3 * 4 + 2 * GD * 2 + 3 + 2 + 4 + 2 * 16) + 256;
+    return cap * (3 * 4 + 2 * gd * 2 + 2 * 2 + 1 + 2 + 4 + 2 * 16) + 256;
 }
 
-__device__ inline GlobalPoly global_poly_carve(unsigned char* base, int cap)
+__device__ inline GlobalPoly global_poly_carve(unsigned char* base, int cap, int gd = GD)
 {
     GlobalPoly g;
     g.cap = cap;
+    g.gd = gd;
     unsigned char* p = base;
     g.tri = reinterpret_cast<float4*>(p); p += (size_t)cap * 32;
     g.x = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
     g.y = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
     g.z = reinterpret_cast<float*>(p); p += (size_t)cap * 4;
     g.list = reinterpret_cast<uint32_t*>(p); p += (size_t)cap * 4;
-    g.ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * GD * 2;
-    g.old_ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * GD * 2;
+    g.ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * gd * 2;
+    g.old_ring = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * gd * 2;
     g.id = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * 2;
-    g.deg = p; p += cap;
-    g.old_deg = p; p += cap;
+    g.deg = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * 2;
+    g.old_deg = reinterpret_cast<uint16_t*>(p); p += (size_t)cap * 2;
     g.comp = reinterpret_cast<int8_t*>(p);
     return g;
 }
@@ -56,7 +59,7 @@ __device__ inline GlobalPoly global_poly_carve(unsigned char* base, int cap)
 // FaceLoop (Src/Poly.cpp:34-41)
 __device__ __forceinline__ int g_face_loop(const GlobalPoly& g, int v, int vprev)
 {
-    const uint16_t* r = g.ring + (size_t)v * GD;
+    const uint16_t* r = g.ring + (size_t)v * g.gd;
     const int d = g.deg[v];
     if (d == 0) return vprev;
     int k = 0;
@@ -64,9 +67,12 @@ __device__ __forceinline__ int g_face_loop(const GlobalPoly& g, int v, int vprev
     return k == 0 ? r[d - 1] : r[k - 1];
 }
 
-// Sequential replay of Poly.cpp:365-462 by lane 0 (patch, erase marks, splice).  false = ring overflow.
-__device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int nverts)
+// Sequential replay of Poly.cpp:365-462 by lane 0 (patch, erase marks, splice) over the slots [0, nverts): the new
+// vertices [nverts0, nverts) first, then the older ones ascending (the reference's visiting order); slots of vertices that
+// left in earlier cuts (comp == G_GONE) are never touched.  false = a ring ran out of slots.
+__device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int nverts, int nlive)
 {
+    const size_t GS = (size_t)g.gd;
     for (int ii = 0; ii < nverts; ii++)
     {
         const int i = (ii + nverts0) % nverts;
@@ -75,47 +81,48 @@ __device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int 
         const int nneigh = g.deg[i];
         for (int j = 0; j < nneigh; j++)
         {
-            const uint16_t jn = g.ring[(size_t)i * GD + j];
+            const uint16_t jn = g.ring[(size_t)i * GS + j];
             if (jn == G_NONE || g.comp[jn] != -1) continue;
             int iprev = i, inext = jn, itmp, k = 0;
-            while (g.comp[inext] == -1 && k++ < nverts)
+            while (g.comp[inext] == -1 && k++ < nlive)
             {
                 itmp = inext;
                 inext = g_face_loop(g, inext, iprev);
                 iprev = itmp;
             }
-            if (g.ring[(size_t)i * GD + (j + 1) % g.deg[i]] == (uint16_t)inext || inext == i)
+            if (g.ring[(size_t)i * GS + (j + 1) % g.deg[i]] == (uint16_t)inext || inext == i)
             {
-                g.ring[(size_t)i * GD + j] = G_NONE;
+                g.ring[(size_t)i * GS + j] = G_NONE;
             }
             else
             {
-                g.ring[(size_t)i * GD + j] = (uint16_t)inext;
+                g.ring[(size_t)i * GS + j] = (uint16_t)inext;
                 const int dn = g.deg[inext], od = g.old_deg[inext];
-                if (dn >= GD || od >= GD) return false;
-                uint16_t* rn = g.ring + (size_t)inext * GD;
-                uint16_t* on = g.old_ring + (size_t)inext * GD;
+                if (dn >= g.gd || od >= g.gd) return false;
+                uint16_t* rn = g.ring + (size_t)inext * GS;
+                uint16_t* on = g.old_ring + (size_t)inext * GS;
                 int off = 0;
                 uint16_t mark = (uint16_t)i;
                 if (g.comp[inext] == 2) mark = G_NONE;   // Poly.cpp:409 inserts -1 into the snapshot
                 else while (off < od && on[off] != (uint16_t)iprev) off++;
                 for (int q = dn; q > off; q--) rn[q] = rn[q - 1];
                 rn[off] = (uint16_t)i;
-                g.deg[inext] = (uint8_t)(dn + 1);
+                g.deg[inext] = (uint16_t)(dn + 1);
                 for (int q = od; q > off; q--) on[q] = on[q - 1];
                 on[off] = mark;
-                g.old_deg[inext] = (uint8_t)(od + 1);
+                g.old_deg[inext] = (uint16_t)(od + 1);
             }
         }
     }
     for (int i = 0; i < nverts; i++)   // Poly.cpp:426-431
     {
-        uint16_t* r = g.ring + (size_t)i * GD;
+        if (g.comp[i] == G_GONE) continue;
+        uint16_t* r = g.ring + (size_t)i * GS;
         int w = 0;
         const int d = g.deg[i];
         for (int k = 0; k < d; k++)
             if (r[k] != G_NONE) r[w++] = r[k];
-        g.deg[i] = (uint8_t)w;
+        g.deg[i] = (uint16_t)w;
     }
     bool updated = true;   // Poly.cpp:433-462
     while (updated)
@@ -126,13 +133,13 @@ __device__ __noinline__ bool g_seq_patch_splice(GlobalPoly& g, int nverts0, int 
             if (g.comp[i] >= 0 && g.deg[i] == 2)
             {
                 updated = true;
-                const int iprev = g.ring[(size_t)i * GD], inext = g.ring[(size_t)i * GD + 1];
+                const int iprev = g.ring[(size_t)i * GS], inext = g.ring[(size_t)i * GS + 1];
                 int k = 0;
-                while (k < g.deg[iprev] && g.ring[(size_t)iprev * GD + k] != (uint16_t)i) ++k;
-                if (k < g.deg[iprev]) g.ring[(size_t)iprev * GD + k] = (uint16_t)inext;
+                while (k < g.deg[iprev] && g.ring[(size_t)iprev * GS + k] != (uint16_t)i) ++k;
+                if (k < g.deg[iprev]) g.ring[(size_t)iprev * GS + k] = (uint16_t)inext;
                 k = 0;
-                while (k < g.deg[inext] && g.ring[(size_t)inext * GD + k] != (uint16_t)i) ++k;
-                if (k < g.deg[inext]) g.ring[(size_t)inext * GD + k] = (uint16_t)iprev;
+                while (k < g.deg[inext] && g.ring[(size_t)inext * GS + k] != (uint16_t)i) ++k;
+                if (k < g.deg[inext]) g.ring[(size_t)inext * GS + k] = (uint16_t)iprev;
                 g.comp[i] = -1;
             }
         }
@@ -203,6 +210,7 @@ __device__ bool g_all_inplane_box_says_skip(const GlobalPoly& g, int nv, const f
         float hi[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
         for (int v = lane; v < nv; v += 32)
         {
+            if (g.comp[v] == G_GONE) continue;
             lo[0] = fminf(lo[0], g.x[v]); hi[0] = fmaxf(hi[0], g.x[v]);
             lo[1] = fminf(lo[1], g.y[v]); hi[1] = fmaxf(hi[1], g.y[v]);
             lo[2] = fminf(lo[2], g.z[v]); hi[2] = fmaxf(hi[2], g.z[v]);
@@ -220,12 +228,73 @@ __device__ bool g_all_inplane_box_says_skip(const GlobalPoly& g, int nv, const f
     return grp.bcast0(skip) != 0;
 }
 
-// Clip the polyhedron in the workspace (nv vertices) by planes[0..npl).  All threads of the group call this together.
+// Stable renumbering of the live slots to 0..n-1 (the reference's compaction, Poly.cpp:464-495): rings are rewritten
+// into the OTHER ring array (old_ring, free outside the sequential replay) and the two views swap, so no thread holds a
+// ring in registers and the stride may be anything.  Returns false if a live ring points at an erased vertex.
+template <int NW>
+__device__ bool g_compact(GlobalPoly& g, int hi, int& n_out, const Grp<NW>& grp)
+{
+    constexpr int N = Grp<NW>::N;
+    const int tid = grp.tid;
+    const size_t GS = (size_t)g.gd;
+    int kept_before = 0;
+#pragma unroll 2
+    for (int base = 0; base < hi; base += N)
+    {
+        const int v = base + tid;
+        const bool live = v < hi && g.comp[v] >= 0;
+        int tot;
+        const int ex = grp.exscan(live ? 1 : 0, tot);
+        if (v < hi) g.id[v] = live ? (uint16_t)(kept_before + ex) : G_NONE;
+        kept_before += tot;
+    }
+    grp.sync();
+    bool dangling = false;
+    for (int v = tid; v < hi; v += N)   // rings: renumbered copy into the other array (no hazards: disjoint source and target)
+    {
+        if (g.comp[v] < 0) continue;
+        const int d = g.deg[v], t = g.id[v];
+        const uint16_t* src = g.ring + (size_t)v * GS;
+        uint16_t* dst = g.old_ring + (size_t)t * GS;
+        for (int j = 0; j < d; j++)
+        {
+            const uint16_t r = src[j] < hi ? g.id[src[j]] : G_NONE;
+            dangling |= r == G_NONE;
+            dst[j] = r;
+        }
+    }
+    for (int base = 0; base < hi; base += N)   // positions, degrees: in place, slot t <= v, chunk by chunk in ascending order
+    {
+        const int v = base + tid;
+        const bool live = v < hi && g.comp[v] >= 0;
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        int d = 0, t = 0;
+        if (live) { vx = g.x[v]; vy = g.y[v]; vz = g.z[v]; d = g.deg[v]; t = g.id[v]; }
+        grp.sync();
+        if (live) { g.x[t] = vx; g.y[t] = vy; g.z[t] = vz; g.deg[t] = (uint16_t)d; }
+        grp.sync();
+    }
+    uint16_t* sw = g.ring; g.ring = g.old_ring; g.old_ring = sw;
+    for (int v = tid; v < kept_before; v += N) g.comp[v] = 1;
+    grp.sync();
+    n_out = kept_before;
+    return !grp.any(dangling);
+}
+
+// Clip the polyhedron in the workspace (nv vertices in slots 0..nv-1) by planes[0..npl).  All threads of the group call
+// this together.  Compaction is LAZY, as in the small tier: a clipped vertex keeps its slot (comp = G_GONE) and new
+// vertices are appended; the slots are renumbered -- stably, so to exactly the reference's numbering -- only when they
+// run out and once at the end.  On return the polyhedron is dense again: nv vertices in slots 0..nv-1.
 template <int NW>
 __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __restrict__ planes, int npl, const Grp<NW>& grp, unsigned& seq_cuts)
 {
     constexpr int N = Grp<NW>::N;
     const int tid = grp.tid;
+    const size_t GS = (size_t)g.gd;
+    int hi = nv;          // allocated slots
+    bool dense = true;    // no G_GONE slot below hi
+    for (int v = tid; v < nv; v += N) g.comp[v] = 1;
+    grp.sync();
     for (int kp = 0; kp < npl && nv > 0; kp++)
     {
         const float4 pl = __ldg(planes + kp);
@@ -234,8 +303,9 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
         bool t_clip = false, t_keep = false, t_zero = false;
         // (unrolled a little: the iterations are independent loads -- memory-level parallelism)
 #pragma unroll 4
-        for (int v = tid; v < nv; v += N)
+        for (int v = tid; v < hi; v += N)
         {
+            if (g.comp[v] == G_GONE) continue;
             const int c = classify(signed_dist(pl, g.x[v], g.y[v], g.z[v]));
             g.comp[v] = (int8_t)c;
             t_clip |= c == -1;
@@ -247,33 +317,52 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
         const bool any_zero = grp.any(t_zero);
         if (!any_keep)
         {
-            if (!any_clip && g_all_inplane_box_says_skip<NW>(g, nv, pl, grp)) continue;
+            if (!any_clip && g_all_inplane_box_says_skip<NW>(g, hi, pl, grp)) continue;
             nv = 0;
             break;
         }
         if (!any_clip) continue;
 
         // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
-        const int nverts0 = nv;
         int nnew = 0;
+        bool redo = false;
 #pragma unroll 2
-        for (int base = 0; base < nverts0; base += N)
+        for (int base = 0; base < hi; base += N)
         {
             const int v = base + tid;
             int cnt = 0;
-            unsigned smask = 0u;
-            if (v < nverts0 && g.comp[v] == -1)
+            if (v < hi && g.comp[v] == -1)
             {
                 const int d = g.deg[v];
                 for (int j = 0; j < d; j++)
-                    if (g.comp[g.ring[(size_t)v * GD + j]] > 0) { cnt++; smask |= 1u << j; }
+                    if (g.comp[g.ring[(size_t)v * GS + j]] > 0) cnt++;
             }
             int tot;
             int w = nnew + grp.exscan(cnt, tot);
-            if (nverts0 + nnew + tot > g.cap) return CLIP_NEED_SLOTS;
-            while (smask) { const int j = __ffs(smask) - 1; smask &= smask - 1; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
+            if (hi + nnew + tot > g.cap) { redo = true; break; }   // (uniform: nnew, tot and hi are)
+            if (cnt)
+            {
+                const int d = g.deg[v];
+                for (int j = 0; j < d; j++)
+                    if (g.comp[g.ring[(size_t)v * GS + j]] > 0) g.list[w++] = (uint32_t)v | ((uint32_t)j << 16);
+            }
             nnew += tot;
         }
+        if (redo)
+        {
+            // out of slots: renumber the live vertices and apply this plane again -- unless they really do not fit
+            if (dense) return CLIP_NEED_SLOTS;
+            for (int v = tid; v < hi; v += N)
+                if (g.comp[v] == 0 || g.comp[v] == -1) g.comp[v] = 1;   // every non-gone slot is live for the renumbering
+            grp.sync();
+            int n;
+            if (!g_compact<NW>(g, hi, n, grp)) return CLIP_OVERFLOW;
+            hi = n;
+            dense = true;
+            kp--;
+            continue;
+        }
+        const int nverts0 = hi;
         const int nverts = nverts0 + nnew;
         grp.sync();
         // insert (Poly.cpp:345-354): one new vertex per thread and iteration
@@ -281,7 +370,7 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
         {
             const uint32_t e = g.list[t];
             const int v = (int)(e & 0xffffu), j = (int)(e >> 16), w = nverts0 + t;
-            const int jn = g.ring[(size_t)v * GD + j];
+            const int jn = g.ring[(size_t)v * GS + j];
             const float ax = g.x[v], ay = g.y[v], az = g.z[v], bx = g.x[jn], by = g.y[jn], bz = g.z[jn];
             const float sa = signed_dist(pl, ax, ay, az), sb = signed_dist(pl, bx, by, bz);
             float ox, oy, oz;
@@ -289,17 +378,17 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             g.x[w] = ox; g.y[w] = oy; g.z[w] = oz;
             g.comp[w] = 2;
             g.deg[w] = 2;
-            g.ring[(size_t)w * GD] = (uint16_t)v;
-            g.ring[(size_t)w * GD + 1] = (uint16_t)jn;
+            g.ring[(size_t)w * GS] = (uint16_t)v;
+            g.ring[(size_t)w * GS + 1] = (uint16_t)jn;
             // several threads may patch the ring of the same kept vertex jn at once: each replaces only the entry holding
             // ITS clipped vertex v, and an entry another thread is rewriting (v' -> w') equals v neither before nor after
             // -- entry-disjoint by construction (compute-sanitizer racecheck warns at word level, profiles/r1_sanitizer.txt)
-            uint16_t* rj = g.ring + (size_t)jn * GD;
+            uint16_t* rj = g.ring + (size_t)jn * GS;
             const int dj = g.deg[jn];
             int k = 0;
             while (k < dj && rj[k] != (uint16_t)v) k++;
             if (k < dj) rj[k] = (uint16_t)w;
-            g.ring[(size_t)v * GD + j] = (uint16_t)w;
+            g.ring[(size_t)v * GS + j] = (uint16_t)w;
         }
         grp.sync();
 
@@ -311,7 +400,7 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             for (int t = tid; t < nnew; t += N)
             {
                 const int w = nverts0 + t;
-                int iprev = w, inext = g.ring[(size_t)w * GD], itmp, k = 0;
+                int iprev = w, inext = g.ring[(size_t)w * GS], itmp, k = 0;
                 while (g.comp[inext] == -1 && k++ < nverts)
                 {
                     itmp = inext;
@@ -332,10 +421,10 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
                 for (int t = tid; t < nnew; t += N)   // ring(w) = [pusher, walked, kept]
                 {
                     const int w = nverts0 + t;
-                    const uint16_t kept = g.ring[(size_t)w * GD + 1];
-                    g.ring[(size_t)w * GD] = g.id[w];
-                    g.ring[(size_t)w * GD + 1] = (uint16_t)g.list[t];
-                    g.ring[(size_t)w * GD + 2] = kept;
+                    const uint16_t kept = g.ring[(size_t)w * GS + 1];
+                    g.ring[(size_t)w * GS] = g.id[w];
+                    g.ring[(size_t)w * GS + 1] = (uint16_t)g.list[t];
+                    g.ring[(size_t)w * GS + 2] = kept;
                     g.deg[w] = 3;
                 }
             }
@@ -345,65 +434,49 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
             if (tid == 0) seq_cuts++;
             for (int v = tid; v < nverts; v += N)
             {
+                if (g.comp[v] == G_GONE) continue;
                 const int d = g.deg[v];
-                g.old_deg[v] = (uint8_t)d;
-                for (int j = 0; j < d; j++) g.old_ring[(size_t)v * GD + j] = g.ring[(size_t)v * GD + j];
+                g.old_deg[v] = (uint16_t)d;
+                for (int j = 0; j < d; j++) g.old_ring[(size_t)v * GS + j] = g.ring[(size_t)v * GS + j];
             }
             grp.sync();
             int okflag = 1;
-            if (tid == 0) okflag = g_seq_patch_splice(g, nverts0, nverts) ? 1 : 0;
+            if (tid == 0) okflag = g_seq_patch_splice(g, nverts0, nverts, nv + nnew) ? 1 : 0;
             okflag = grp.bcast0(okflag);
-            if (!okflag) return CLIP_OVERFLOW;
+            if (!okflag) return CLIP_NEED_DEG;
         }
         grp.sync();
 
-        // compaction (Poly.cpp:464-499)
-        int kept_before = 0;
+        // lazy compaction (Poly.cpp:464-499): clipped and spliced vertices only give up their slot's liveness
+        int live_now = 0;
 #pragma unroll 2
         for (int base = 0; base < nverts; base += N)
         {
             const int v = base + tid;
-            const bool live = v < nverts && g.comp[v] >= 0;
+            bool live = false;
+            if (v < nverts)
+            {
+                const int c = g.comp[v];
+                if (c == -1) g.comp[v] = G_GONE;
+                live = c >= 0;
+            }
             int tot;
-            const int ex = grp.exscan(live ? 1 : 0, tot);
-            if (v < nverts) g.id[v] = live ? (uint16_t)(kept_before + ex) : G_NONE;
-            kept_before += tot;
+            grp.exscan(live ? 1 : 0, tot);
+            live_now += tot;
         }
+        hi = nverts;
+        dense = false;
+        nv = live_now < 4 ? 0 : live_now;   // Poly.cpp:498-499
         grp.sync();
-        bool dangling = false;   // a live ring pointing at an erased vertex: not a polyhedron (the reference would store -1)
-        for (int base = 0; base < nverts; base += N)
-        {
-            const int v = base + tid;
-            const bool live = v < nverts && g.comp[v] >= 0;
-            float vx = 0.f, vy = 0.f, vz = 0.f;
-            uint16_t r[GD];
-            int d = 0, t = 0;
-            if (live)
-            {
-                vx = g.x[v]; vy = g.y[v]; vz = g.z[v];
-                d = g.deg[v];
-                t = g.id[v];
-#pragma unroll
-                for (int j = 0; j < GD; j++)
-                    if (j < d)
-                    {
-                        r[j] = g.id[g.ring[(size_t)v * GD + j]];
-                        dangling |= r[j] == G_NONE;
-                    }
-            }
-            grp.sync();
-            if (live)
-            {
-                g.x[t] = vx; g.y[t] = vy; g.z[t] = vz;
-                g.deg[t] = (uint8_t)d;
-#pragma unroll
-                for (int j = 0; j < GD; j++)
-                    if (j < d) g.ring[(size_t)t * GD + j] = r[j];
-            }
-            grp.sync();
-        }
-        if (grp.any(dangling)) return CLIP_OVERFLOW;   // keeps every later index inside the workspace
-        nv = kept_before < 4 ? 0 : kept_before;   // Poly.cpp:498-499
+    }
+    if (nv > 0 && !dense)
+    {
+        for (int v = tid; v < hi; v += N)
+            if (g.comp[v] == 0) g.comp[v] = 1;
+        grp.sync();
+        int n;
+        if (!g_compact<NW>(g, hi, n, grp)) return CLIP_OVERFLOW;   // a live ring pointing at an erased vertex: not a polyhedron
+        nv = n;
     }
     grp.sync();
     return CLIP_OK;
@@ -428,8 +501,8 @@ __device__ void global_fragment_moments(GlobalPoly& g, int nv, const Grp<NW>& gr
             const int d = g.deg[v];
             for (int j = 0; j < d; j++)
             {
-                int at = g.ring[(size_t)v * GD + j];
-                if (at < v || (int)g.ring[(size_t)v * GD + (j + 1 == d ? 0 : j + 1)] < v) continue;
+                int at = g.ring[(size_t)v * g.gd + j];
+                if (at < v || (int)g.ring[(size_t)v * g.gd + (j + 1 == d ? 0 : j + 1)] < v) continue;
                 int prev = v, n = 1;
                 bool is_start = true;
                 while (at != v)
@@ -464,7 +537,7 @@ __device__ void global_fragment_moments(GlobalPoly& g, int nv, const Grp<NW>& gr
         {
             const int j = __ffs(m) - 1;
             m &= m - 1;
-            int prev = v, at = g.ring[(size_t)v * GD + j];
+            int prev = v, at = g.ring[(size_t)v * g.gd + j];
             float p1x = __fsub_rn(g.x[at], ox), p1y = __fsub_rn(g.y[at], oy), p1z = __fsub_rn(g.z[at], oz);
             int nxt = g_face_loop(g, at, prev);
             prev = at;

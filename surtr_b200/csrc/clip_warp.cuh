@@ -24,7 +24,7 @@ namespace surtr
 {
 constexpr unsigned FULL = 0xffffffffu;
 
-enum ClipStatus : int { CLIP_OK = 0, CLIP_OVERFLOW = 2, CLIP_NEED_SLOTS = 3 };   // 3: only the vertex slots ran out (a larger workspace would do)
+enum ClipStatus : int { CLIP_OK = 0, CLIP_OVERFLOW = 2, CLIP_NEED_SLOTS = 3, CLIP_NEED_DEG = 4 };   // 3 / 4: only the vertex slots / the ring slots of a vertex ran out (a larger workspace would do)
 
 __device__ __forceinline__ int warp_exscan(int v, int lane, int& total)
 {

@@ -42,6 +42,9 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
     unsigned int n_ovf3;        // pairs queued for the global-memory tier
     unsigned int n_grow3;       // global-tier pairs whose workspace ran out of vertex slots (the host enlarges it and re-runs)
     unsigned int n_ovf2;        // pairs the 128-slot tier handed on to the large on-chip tier
+    unsigned int n_growdeg;     // global-tier pairs with a ring that outgrew the workspace's ring slots (the host enlarges them and re-runs)
+    unsigned int max_deg;       // largest ring such a pair needed at staging time
+    unsigned int pad[2];
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -419,7 +422,9 @@ struct ClipArgs
     unsigned char* ws3;           // tier 3: one workspace per warp
     uint64_t ws3_stride;
     int cap3;                     // tier 3: vertex slots per workspace
+    int gd3;                      // tier 3: ring slots per vertex of the workspace (grown by the host on demand, never a hard limit)
     uint64_t cap_tier3;           // result slots available to tier 3
+    uint32_t* fail_list;          // candidates that cannot be cut (malformed rings): reported per pair, the rest of the event is valid
     Ctl* ctl;
     uint32_t* dbg;                // optional: 8 words per candidate (cycles per phase, cut counts); NULL = off
 };
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
                 if (d > GD) too_big = true;
                 else
                 {
-                    g.deg[v] = (uint8_t)d;
+                    g.deg[v] = (uint16_t)d;
                     if (d == 0) malformed = true;   // a vertex without neighbours is not a polyhedron vertex
                     for (int j = 0; j < d; j++)
                     {
@@ -492,8 +497,8 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
             if (tid == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-                if (malformed) atomicAdd(&a.ctl->n_fail, 1u);
-                else a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier
+                if (malformed) a.fail_list[atomicAdd(&a.ctl->n_fail, 1u)] = q;
+                else a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;   // on to the global-memory tier (more slots, wider rings)
             }
             grp.sync();
             continue;
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
 #pragma unroll
                 for (int k = 0; k < 6; k++) rec->inertia[k] = mo.inertia[k];
             }
-            if (!room) atomicAdd(&a.ctl->n_fail, 1u);
+            // (!room: the host sees n_ovf2 > cap_tier2, grows the result slots and re-runs the event)
         }
         grp.sync();
     }
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
 // K3, unbounded tier: persistent warps over the pairs the on-chip tiers handed on (clip_global.cuh).
 constexpr int T3_WARPS = 8;            // warps per pair (= per block) in the unbounded tier
 constexpr int T3_BLOCKS_PER_SM = 2;    // persistent blocks, one workspace each
-__host__ __device__ constexpr size_t blob3_bytes(size_t cap) { return cap * (16 + 4 + GD * 2); }   // float4 verts | u32 ring_start | u16 ring
+__host__ __device__ constexpr size_t blob3_bytes(size_t cap, size_t gd) { return cap * (16 + 4 + gd * 2); }   // float4 verts | u32 ring_start | u16 ring
 
 __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 {
@@ -581,7 +586,8 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
     const int tid = threadIdx.x;
     const Grp<T3_WARPS> grp{ tid, tid & 31, s_scan };
     const unsigned long long n_items = a.ctl->n_ovf3;
-    GlobalPoly g = global_poly_carve(a.ws3 + (size_t)blockIdx.x * a.ws3_stride, a.cap3);
+    GlobalPoly g = global_poly_carve(a.ws3 + (size_t)blockIdx.x * a.ws3_stride, a.cap3, a.gd3);
+    const size_t GS = (size_t)a.gd3;
     unsigned seq_cuts = 0;
     for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
     {
@@ -589,7 +595,8 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
         const uint2 pr = a.cand[q];
         const uint32_t v0 = a.p_vert_off[pr.x];
         int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
-        bool bad = nv > g.cap;
+        bool bad = nv > g.cap, wide = false;
+        unsigned need_deg = 0;
         if (!bad)
         {
             for (int v = tid; v < nv; v += N)
@@ -598,23 +605,26 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
                 g.x[v] = p.x; g.y[v] = p.y; g.z[v] = p.z;
                 const uint32_t r0 = a.p_ring_off[v0 + v];
                 const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
-                if (d > GD || d == 0) bad = true;
+                if (d == 0) bad = true;
+                else if (d > g.gd) { wide = true; need_deg = max(need_deg, (unsigned)d); }   // the workspace's rings are too narrow: the host widens them
                 else
                 {
-                    g.deg[v] = (uint8_t)d;
+                    g.deg[v] = (uint16_t)d;
                     for (int j = 0; j < d; j++)
                     {
                         const int idx = a.p_ring[r0 + j];
                         if (idx >= nv) bad = true;
-                        g.ring[(size_t)v * GD + j] = (uint16_t)idx;
+                        g.ring[v * GS + j] = (uint16_t)idx;
                     }
                 }
             }
         }
         bad = grp.any(bad);
+        wide = grp.any(wide);
+        if (need_deg) atomicMax(&a.ctl->max_deg, need_deg);
         grp.sync();
-        int status = nv > g.cap ? CLIP_NEED_SLOTS : CLIP_OVERFLOW;
-        if (!bad)
+        int status = nv > g.cap ? CLIP_NEED_SLOTS : (wide && !bad ? CLIP_NEED_DEG : CLIP_OVERFLOW);
+        if (!bad && !wide)
         {
             const uint32_t pl0 = a.c_plane_off[pr.y];
             const int npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
@@ -627,9 +637,11 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
             if (tid == 0)
             {
                 rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
-                // !room alone: the host grows the result slots and re-runs; out of vertex slots: it grows the workspace
-                if (status == CLIP_NEED_SLOTS) atomicAdd(&a.ctl->n_grow3, 1u);
-                else if (status != CLIP_OK) atomicAdd(&a.ctl->n_fail, 1u);
+                // !room alone: the host grows the result slots and re-runs; out of vertex / ring slots: it grows the workspace
+                // (at the end of the 16-bit index range nothing is left to grow: the pair is reported as failed)
+                if (status == CLIP_NEED_SLOTS && g.cap < 65520) atomicAdd(&a.ctl->n_grow3, 1u);
+                else if (status == CLIP_NEED_DEG && g.gd < 65520) atomicAdd(&a.ctl->n_growdeg, 1u);
+                else if (status != CLIP_OK) a.fail_list[atomicAdd(&a.ctl->n_fail, 1u)] = q;
             }
             grp.sync();
             continue;
@@ -642,6 +654,13 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
         }
         Moments mo;
         global_fragment_moments<T3_WARPS>(g, nv, grp, mo, s_cov);
+        if (grp.bcast0(mo.n_faces) > 65535)
+        {
+            // surtr_fragment::n_faces is 16 bits wide: reported as a failed pair, never truncated
+            if (tid == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0; a.fail_list[atomicAdd(&a.ctl->n_fail, 1u)] = q; }
+            grp.sync();
+            continue;
+        }
         const unsigned long long blob = it * a.slot_bytes;
         unsigned char* b = a.scratch + blob;
         float4* bv = reinterpret_cast<float4*>(b);
@@ -659,7 +678,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
             {
                 bv[v] = make_float4(g.x[v], g.y[v], g.z[v], 0.f);
                 bo[v] = (uint32_t)off;
-                for (int j = 0; j < d; j++) br[off + j] = g.ring[(size_t)v * GD + j];
+                for (int j = 0; j < d; j++) br[off + j] = g.ring[v * GS + j];
             }
         }
         if (tid == 0)

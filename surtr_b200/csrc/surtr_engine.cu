@@ -106,10 +106,13 @@ struct surtr_ctx
     uint64_t n_pairs = 0;
 
     // work buffers
-    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf2_list, ovf3_list, ws3, scratch3, ctl, dbg, out_off, frag_cand;
+    DevBuf ext_p, ext_c, masks, cand, cand_rec, scratch1, scratch2, ovf_list, ovf2_list, ovf3_list, fail_list, ws3, scratch3, ctl, dbg, out_off, frag_cand;
     bool debug = false;
     uint64_t cap_cand = 0, cap_tier2 = 0, cap_tier3 = 0;
     int cap3 = 0;                 // vertex slots of a tier-3 workspace (from the largest uploaded piece)
+    int gd3 = 16;                 // ring slots per vertex of a tier-3 workspace (doubled whenever a ring outgrows them)
+    uint32_t n_ws3 = 0;           // tier-3 workspaces = persistent blocks (fewer when the workspaces get large)
+    std::vector<uint32_t> h_failed;   // candidates of the last event that could not be cut
     uint32_t max_piece_verts = 0;
     uint32_t n_tiles_a = 0, n_tiles_b = 0;
 
@@ -235,6 +238,7 @@ int ensure_capacity(surtr_ctx* ctx)
     CK(ctx->scratch1.reserve(FAST_BLOB * ctx->cap_cand));
     CK(ctx->scratch2.reserve(blob2_bytes() * ctx->cap_tier2));
     CK(ctx->ovf3_list.reserve(4 * ctx->cap_cand));   // tiers 1 and 2 hand pairs on to the global tier through this list
+    CK(ctx->fail_list.reserve(4 * ctx->cap_cand));
     if (ctx->tier3_enabled)
     {
         // workspace: twice the largest piece (a cut adds at most one vertex per straddling edge), at least 4096 slots
@@ -244,9 +248,11 @@ int ensure_capacity(surtr_ctx* ctx)
             want = std::min<uint64_t>(65520, (std::max<uint64_t>(64, std::strtoull(e, nullptr, 10)) + 15) / 16 * 16);
         ctx->cap3 = std::max<int>(ctx->cap3, (int)want);
         ctx->cap_tier3 = std::max<uint64_t>(ctx->cap_tier3, 8);
-        const size_t stride = (global_poly_bytes((size_t)ctx->cap3) + 255) / 256 * 256;
-        CK(ctx->ws3.reserve(stride * (size_t)ctx->num_sm * T3_BLOCKS_PER_SM));
-        CK(ctx->scratch3.reserve(blob3_bytes((size_t)ctx->cap3) * ctx->cap_tier3));
+        const size_t stride = (global_poly_bytes((size_t)ctx->cap3, (size_t)ctx->gd3) + 255) / 256 * 256;
+        // one workspace per persistent block; at most 8 GB of them (a 65 520-slot workspace with 1024-wide rings is 270 MB)
+        ctx->n_ws3 = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)ctx->num_sm * T3_BLOCKS_PER_SM, ((size_t)8 << 30) / stride));
+        CK(ctx->ws3.reserve(stride * ctx->n_ws3));
+        CK(ctx->scratch3.reserve(blob3_bytes((size_t)ctx->cap3, (size_t)ctx->gd3) * ctx->cap_tier3));
     }
     // Ctl | flagsA | flagsB, then the (never zeroed) aggregate / inclusive arrays
     const size_t zero_bytes = (ctl_bytes(ctx) + 15) / 16 * 16;
@@ -349,8 +355,10 @@ int launch_event(surtr_ctx* ctx)
     ca.cap_tier2 = ctx->cap_tier2;
     ca.ovf3_list = ctx->ovf3_list.as<uint32_t>();
     ca.ws3 = ctx->ws3.as<unsigned char>();
-    ca.ws3_stride = (global_poly_bytes((size_t)std::max(1, ctx->cap3)) + 255) / 256 * 256;
+    ca.ws3_stride = (global_poly_bytes((size_t)std::max(1, ctx->cap3), (size_t)ctx->gd3) + 255) / 256 * 256;
     ca.cap3 = ctx->cap3;
+    ca.gd3 = ctx->gd3;
+    ca.fail_list = ctx->fail_list.as<uint32_t>();
     ca.cap_tier3 = ctx->cap_tier3;
     ca.ctl = d_ctl;
     ca.dbg = ctx->debug ? ctx->dbg.as<uint32_t>() : nullptr;
@@ -381,8 +389,8 @@ int launch_event(surtr_ctx* ctx)
     if (ctx->tier3_enabled)
     {
         ca.scratch = ctx->scratch3.as<unsigned char>();
-        ca.slot_bytes = blob3_bytes((size_t)ctx->cap3);
-        launch_pdl(clip_global_kernel, dim3(ctx->num_sm * T3_BLOCKS_PER_SM), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
+        ca.slot_bytes = blob3_bytes((size_t)ctx->cap3, (size_t)ctx->gd3);
+        launch_pdl(clip_global_kernel, dim3(ctx->n_ws3), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -468,6 +476,11 @@ int resolve_event(surtr_ctx* ctx)
             ctx->cap3 = (int)std::min<uint64_t>(65520, 2ull * (uint64_t)ctx->cap3);
             grow = true;
         }
+        if (c.n_growdeg && ctx->gd3 < 65520)  // a ring outgrew the workspace's ring slots: widen them (a vertex may have any number of neighbours)
+        {
+            ctx->gd3 = (int)std::min<uint64_t>(65520, std::max<uint64_t>(2ull * (uint64_t)ctx->gd3, ((uint64_t)c.max_deg + 8 + 7) / 8 * 8));
+            grow = true;
+        }
         if (!grow)
         {
             if (c.n_frag > ctx->cap_frag) { ctx->cap_frag = c.n_frag + c.n_frag / 8 + 64; grow = true; }
@@ -476,10 +489,26 @@ int resolve_event(surtr_ctx* ctx)
         }
         if (!grow)
         {
-            if (c.n_fail || c.n_grow3)
-                return fail(ctx, SURTR_ERR_OVERFLOW,
-                            std::to_string(c.n_fail + c.n_grow3) + " pair(s) cannot be cut: malformed rings, ring degree above 16, or more than " +
-                                std::to_string(ctx->cap3 ? ctx->cap3 : 65520) + " vertex slots needed");
+            // what is left are pairs that no workspace can help: malformed rings, or beyond the 16-bit index range.  They
+            // are reported PER PAIR (surtr_failed_pairs); every other fragment of the event is valid and can be read.
+            const uint32_t n_bad = c.n_fail;
+            ctx->h_failed.clear();
+            if (c.n_fail)
+            {
+                std::vector<uint32_t> q(c.n_fail);
+                CK(cudaMemcpy(q.data(), ctx->fail_list.p, 4 * (size_t)c.n_fail, cudaMemcpyDeviceToHost));
+                for (uint32_t i = 0; i < c.n_fail; i++)
+                {
+                    uint2 one;
+                    CK(cudaMemcpy(&one, ctx->cand.as<uint2>() + q[i], sizeof(uint2), cudaMemcpyDeviceToHost));
+                    ctx->h_failed.push_back(one.x);
+                    ctx->h_failed.push_back(one.y);
+                }
+            }
+            ctx->last.n_failed = n_bad;
+            if (n_bad)
+                ctx->err = std::to_string(n_bad) + " pair(s) cannot be cut (malformed rings, or more than 65520 vertex / ring slots needed); "
+                           "see surtr_failed_pairs -- all other fragments of the event are valid";
             ctx->last.n_pairs = ctx->n_pairs;
             ctx->last.n_candidates = c.n_cand;
             ctx->last.n_fragments = c.n_frag;
@@ -596,7 +625,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
     DevBuf* all[] = { &ctx->p_verts, &ctx->p_vert_off, &ctx->p_ring_off, &ctx->p_ring, &ctx->c_planes, &ctx->c_plane_off,
                       &ctx->c_verts, &ctx->c_vert_off, &ctx->d_tiles, &ctx->d_ev_mask_base, &ctx->d_ev_piece_off,
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
-                      &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf2_list, &ctx->ovf3_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
+                      &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf2_list, &ctx->ovf3_list, &ctx->fail_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->in_blob, &ctx->out_blob, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
                       &ctx->xf_idx };
     for (DevBuf* b : all) b->release();
@@ -730,6 +759,17 @@ int surtr_event_counts(surtr_ctx* ctx, surtr_counts* out)
     const int rc = resolve_event(ctx);
     if (rc) return rc;
     if (out) *out = ctx->last;
+    return ctx->last.n_failed ? SURTR_ERR_OVERFLOW : SURTR_OK;   // (the event IS complete: counts are filled in, downloads work)
+}
+
+int surtr_failed_pairs(surtr_ctx* ctx, uint32_t* piece_cell, uint64_t capacity_pairs, uint64_t* n_pairs)
+{
+    if (!ctx || !n_pairs) return SURTR_ERR_INVALID;
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    *n_pairs = ctx->h_failed.size() / 2;
+    if (piece_cell)
+        for (size_t i = 0; i < ctx->h_failed.size() && i < 2 * capacity_pairs; i++) piece_cell[i] = ctx->h_failed[i];
     return SURTR_OK;
 }
 

@@ -34,7 +34,7 @@ EXPORTS = [
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
     "surtr_transform_pieces", "surtr_download_pieces", "surtr_measure_fp32_peak",
-    "surtr_last_event_phases", "surtr_input_blob_layout", "surtr_upload_blob", "surtr_download_blob_async", "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
+    "surtr_last_event_phases", "surtr_failed_pairs", "surtr_input_blob_layout", "surtr_upload_blob", "surtr_download_blob_async", "surtr_upload_pieces3", "surtr_upload_cells3", "surtr_download_fragments_packed", "surtr_download_fragments_packed_async",
 ]
 
 
@@ -46,7 +46,7 @@ class SurtrError(RuntimeError):
 
 class Counts(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_pairs", "n_candidates", "n_fragments", "n_verts", "n_ring",
-                                          "n_seq_cuts", "n_tier2", "n_tier3", "n_tier1b")]
+                                          "n_seq_cuts", "n_tier2", "n_tier3", "n_tier1b", "n_failed")]
 
 
 class InLayout(C.Structure):
@@ -105,6 +105,7 @@ def load_library():
     lib.surtr_last_event_launches.argtypes = [vp]
     lib.surtr_set_profiling.argtypes = [vp, i32]
     lib.surtr_last_event_phases.argtypes = [vp, vp]
+    lib.surtr_failed_pairs.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     u64 = C.c_uint64
     lib.surtr_input_blob_layout.argtypes = [u32, u64, u64, u32, u64, u64, u32, C.POINTER(InLayout)]
     lib.surtr_upload_blob.argtypes = [vp, vp, u32, u64, u64, u32, u64, u64, u32]
@@ -237,13 +238,27 @@ class FractureContext:
     def fracture_event(self):
         self._ck(self._lib.surtr_fracture_event(self._h))
 
-    def counts(self) -> Counts:
+    def counts(self, allow_failed: bool = False) -> Counts:
+        """Counters of the last event.  Pairs that cannot be cut (malformed rings ...) raise SurtrError(4) unless
+        allow_failed: then the counters (n_failed > 0) are returned and failed_pairs() lists them."""
         c = Counts()
-        self._ck(self._lib.surtr_event_counts(self._h, C.byref(c)))
+        rc = self._lib.surtr_event_counts(self._h, C.byref(c))
+        if rc == 4 and allow_failed and c.n_failed:
+            return c
+        self._ck(rc)
         return c
 
-    def download(self, geometry: bool = True) -> Fragments:
-        c = self.counts()
+    def failed_pairs(self) -> np.ndarray:
+        """(piece, cell) of every pair of the last event that could not be cut."""
+        n = C.c_uint64(0)
+        self._ck(self._lib.surtr_failed_pairs(self._h, None, 0, C.byref(n)))
+        out = np.zeros((int(n.value), 2), np.uint32)
+        if n.value:
+            self._ck(self._lib.surtr_failed_pairs(self._h, _p(out), int(n.value), C.byref(n)))
+        return out
+
+    def download(self, geometry: bool = True, allow_failed: bool = False) -> Fragments:
+        c = self.counts(allow_failed)
         rec = np.zeros(c.n_fragments, FRAGMENT_DTYPE)
         if geometry:
             verts = np.zeros((c.n_verts, 4), np.float32)

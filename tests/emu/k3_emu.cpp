@@ -288,6 +288,9 @@ extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* con
     return 0;
 }
 
+static int g_large_gd = GD;   // ring slots per vertex of the emulated workspace (GD = the on-chip tier; the global tier's is a run-time value)
+extern "C" void k3emu_set_gd(int gd) { g_large_gd = gd; }
+
 namespace
 {
 template <int NW>
@@ -297,21 +300,22 @@ int run_large(const float* verts4, const uint32_t* ring_off, const uint16_t* rin
 {
     constexpr int N = NW * 32;
     for (int k = 0; k < 8; k++) out_info[k] = 0;
-    std::vector<float4> ws((global_poly_bytes((size_t)cap) + 15) / 16 + 1);          // 16-byte aligned workspace
-    GlobalPoly g0 = global_poly_carve(reinterpret_cast<unsigned char*>(ws.data()), cap);
+    const int gd = g_large_gd;
+    std::vector<float4> ws((global_poly_bytes((size_t)cap, (size_t)gd) + 15) / 16 + 1);          // 16-byte aligned workspace
+    GlobalPoly g0 = global_poly_carve(reinterpret_cast<unsigned char*>(ws.data()), cap, gd);
     bool bad = nv_in > cap;
     if (!bad)
         for (int v = 0; v < nv_in; v++)   // staging of clip_shared_kernel / clip_global_kernel (kernels.cuh)
         {
             g0.x[v] = verts4[4 * v]; g0.y[v] = verts4[4 * v + 1]; g0.z[v] = verts4[4 * v + 2];
             const int d = (int)(ring_off[v + 1] - ring_off[v]);
-            if (d > GD || d == 0) { bad = true; continue; }
-            g0.deg[v] = (uint8_t)d;
+            if (d > gd || d == 0) { bad = true; continue; }
+            g0.deg[v] = (uint16_t)d;
             for (int j = 0; j < d; j++)
             {
                 const int idx = ring[ring_off[v] + j];
                 if (idx >= nv_in) bad = true;
-                g0.ring[(size_t)v * GD + j] = (uint16_t)idx;
+                g0.ring[(size_t)v * gd + j] = (uint16_t)idx;
             }
         }
     if (bad) { out_info[0] = nv_in > cap ? CLIP_NEED_SLOTS : CLIP_OVERFLOW; return 0; }
@@ -323,13 +327,16 @@ int run_large(const float* verts4, const uint32_t* ring_off, const uint16_t* rin
     std::vector<int> nv(N), status(N);
     std::vector<unsigned> seq(N, 0u);
     std::vector<Moments> mo(N);
+    GlobalPoly gfin = g0;
     const unsigned long n_coll = simt::run_block(N, [&](int tid) {
         GlobalPoly g = g0;                                  // every thread holds its own views, as in the kernels
         const Grp<NW> grp{ tid, tid & 31, s_scan };
         nv[tid] = nv_in;
         status[tid] = global_clip_by_planes<NW>(g, nv[tid], planes.data(), npl, grp, seq[tid]);
         if (status[tid] == CLIP_OK && nv[tid] > 0) global_fragment_moments<NW>(g, nv[tid], grp, mo[tid], s_cov);
+        if (tid == 0) gfin = g;                             // (a compaction swaps the two ring views)
     });
+    g0 = gfin;
     for (int t = 1; t < N; t++)
         if (nv[t] != nv[0] || status[t] != status[0]) return -1;
     out_info[0] = status[0];
@@ -341,7 +348,7 @@ int run_large(const float* verts4, const uint32_t* ring_off, const uint16_t* rin
     {
         out_verts4[4 * v] = g0.x[v]; out_verts4[4 * v + 1] = g0.y[v]; out_verts4[4 * v + 2] = g0.z[v]; out_verts4[4 * v + 3] = 0.f;
         out_ring_off[v] = (uint32_t)ne;
-        for (int j = 0; j < g0.deg[v]; j++) out_ring[ne++] = g0.ring[(size_t)v * GD + j];
+        for (int j = 0; j < g0.deg[v]; j++) out_ring[ne++] = g0.ring[(size_t)v * gd + j];
     }
     out_ring_off[nv[0]] = (uint32_t)ne;
     out_info[1] = nv[0];

@@ -103,3 +103,110 @@ def test_product_never_imports_oracle():
                             continue
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_runs_an_event_and_matches_the_reference_fixture(tmp_path):
+    """A C99 program -- nothing but include/surtr_b200.h and libc -- runs the committed reference event (unit cube x 64
+    Voronoi cells, tests/golden/cube_x64.npz, written out as raw arrays) through upload -> fracture_event -> counts ->
+    download, and again through the one-blob calls, and compares every output array with the reference build's bytes."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_port import load_polyset
+    d = np.load(os.path.join(ROOT, "tests", "golden", "cube_x64.npz"))
+    cells, pieces, want = load_polyset(d, "cells_"), load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    raw = tmp_path / "event.bin"
+    arrays = [np.ascontiguousarray(pieces.verts, np.float32), np.ascontiguousarray(pieces.vert_off, np.uint32),
+              np.ascontiguousarray(pieces.ring_off, np.uint32), np.ascontiguousarray(pieces.ring, np.uint16),
+              np.ascontiguousarray(cells.planes, np.float32), np.ascontiguousarray(cells.plane_off, np.uint32),
+              np.ascontiguousarray(cells.verts, np.float32), np.ascontiguousarray(cells.vert_off, np.uint32),
+              # expected
+              np.ascontiguousarray(want.cell, np.uint32), np.ascontiguousarray(want.piece, np.uint32),
+              np.ascontiguousarray(want.nverts, np.uint32), np.ascontiguousarray(want.nfaces, np.uint32),
+              np.ascontiguousarray(want.volume, np.float64), np.ascontiguousarray(want.centroid, np.float32),
+              np.ascontiguousarray(want.verts, np.float32), np.ascontiguousarray(want.ring_off, np.uint32),
+              np.ascontiguousarray(want.ring, np.uint16)]
+    with open(raw, "wb") as f:
+        f.write(np.array([a.nbytes for a in arrays], np.uint64).tobytes())
+        for a in arrays:
+            f.write(a.tobytes())
+    src = tmp_path / "event.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "surtr_b200.h"
+#define NA 17
+static void* arr[NA];
+static unsigned long long nbytes[NA];
+#define CK(x) do { int rc_ = (x); if (rc_ != SURTR_OK) { printf("%s -> %d: %s\n", #x, rc_, surtr_last_error(ctx)); return 20; } } while (0)
+int main(int argc, char** argv)
+{
+    FILE* f = fopen(argv[1], "rb");
+    int i;
+    surtr_ctx* ctx = NULL;
+    surtr_counts c;
+    surtr_fragment* rec;
+    float* verts;
+    unsigned* ring_off;
+    unsigned short* ring;
+    unsigned n_pieces, n_cells, n;
+    (void)argc;
+    if (!f || fread(nbytes, 8, NA, f) != NA) return 1;
+    for (i = 0; i < NA; i++) { arr[i] = malloc(nbytes[i] + 16); if (fread(arr[i], 1, nbytes[i], f) != nbytes[i]) return 2; }
+    fclose(f);
+    n_pieces = (unsigned)(nbytes[1] / 4 - 1);
+    n_cells = (unsigned)(nbytes[5] / 4 - 1);
+    CK(surtr_ctx_create(0, NULL, &ctx));
+    CK(surtr_upload_pieces(ctx, arr[0], arr[1], arr[2], arr[3], n_pieces, NULL, 0));
+    CK(surtr_upload_cells(ctx, arr[4], arr[5], arr[6], arr[7], n_cells, NULL, 0));
+    CK(surtr_fracture_event(ctx));
+    CK(surtr_event_counts(ctx, &c));
+    n = (unsigned)c.n_fragments;
+    if (n != nbytes[8] / 4 || c.n_verts * 16 != nbytes[14] || c.n_ring * 2 != nbytes[16]) { puts("counts differ"); return 3; }
+    rec = malloc(sizeof(surtr_fragment) * n);
+    verts = malloc(16 * c.n_verts);
+    ring_off = malloc(4 * (c.n_verts + 1));
+    ring = malloc(2 * c.n_ring + 2);
+    CK(surtr_download_fragments(ctx, rec, verts, ring_off, ring));
+    for (i = 0; i < (int)n; i++)
+    {
+        if (rec[i].cell != ((unsigned*)arr[8])[i] || rec[i].piece != ((unsigned*)arr[9])[i] || rec[i].n_verts != ((unsigned*)arr[10])[i] ||
+            rec[i].n_faces != ((unsigned*)arr[11])[i] || memcmp(&rec[i].volume, (double*)arr[12] + i, 8) ||
+            memcmp(rec[i].centroid, (float*)arr[13] + 3 * i, 12)) { printf("fragment %d differs\n", i); return 4; }
+    }
+    if (memcmp(verts, arr[14], nbytes[14]) || memcmp(ring_off, arr[15], nbytes[15]) || memcmp(ring, arr[16], nbytes[16])) { puts("geometry differs"); return 5; }
+    /* the one-blob calls: same fragments */
+    {
+        surtr_in_layout L;
+        surtr_out_layout O;
+        unsigned char *in, *out;
+        unsigned long long npv = nbytes[0] / 16, npr = nbytes[3] / 2, npl = nbytes[4] / 16, ncv = nbytes[6] / 16, k;
+        CK(surtr_input_blob_layout(n_pieces, npv, npr, n_cells, npl, ncv, 0, &L));
+        in = calloc(1, L.total);
+        for (k = 0; k < npv; k++) memcpy(in + L.verts3 + 12 * k, (float*)arr[0] + 4 * k, 12);
+        memcpy(in + L.vert_off, arr[1], nbytes[1]); memcpy(in + L.ring_off, arr[2], nbytes[2]); memcpy(in + L.ring, arr[3], nbytes[3]);
+        memcpy(in + L.planes4, arr[4], nbytes[4]); memcpy(in + L.plane_off, arr[5], nbytes[5]);
+        for (k = 0; k < ncv; k++) memcpy(in + L.cell_verts3 + 12 * k, (float*)arr[6] + 4 * k, 12);
+        memcpy(in + L.cvert_off, arr[7], nbytes[7]);
+        CK(surtr_upload_blob(ctx, in, n_pieces, npv, npr, n_cells, npl, ncv, 0));
+        CK(surtr_fracture_event(ctx));
+        out = malloc(64 * (size_t)n + 13 * c.n_verts + 2 * c.n_ring + 1024);
+        CK(surtr_download_blob_async(ctx, out, 64 * (unsigned long long)n + 13 * c.n_verts + 2 * c.n_ring + 1024, &O));
+        CK(surtr_sync(ctx));
+        if (O.n_fragments != n || memcmp(out + O.fragments, rec, sizeof(surtr_fragment) * n) || memcmp(out + O.ring, ring, 2 * c.n_ring)) { puts("blob differs"); return 6; }
+        for (k = 0; k < c.n_verts; k++)
+            if (memcmp(out + O.verts3 + 12 * k, verts + 4 * k, 12) || out[O.ring_len + k] != ring_off[k + 1] - ring_off[k]) { puts("blob geometry differs"); return 7; }
+    }
+    surtr_ctx_destroy(ctx);
+    printf("ok %u fragments\n", n);
+    return 0;
+}
+''')
+    exe = tmp_path / "event"
+    libdir = os.path.join(ROOT, "surtr_b200")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", libdir, "-lsurtr_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe), str(raw)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.startswith("ok 64"), (run.returncode, run.stdout, run.stderr)

@@ -297,6 +297,75 @@ def test_malformed_and_oversize_inputs_fail_loudly(ctx):
     common.assert_fragments_equal(got, want)
 
 
+def _cone_mesh(n, height=1.3, radius=0.9):
+    """A triangulated cone: apex and base centre both have n neighbours (fan poles, the valence ADVICE.md warns about)."""
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    verts = np.zeros((n + 2, 4), np.float32)
+    verts[0, :3] = (0.05, height, -0.02)                        # apex
+    verts[1, :3] = (0.0, 0.0, 0.0)                              # base centre
+    verts[2:, 0], verts[2:, 2] = radius * np.cos(ang), radius * np.sin(ang)
+    verts[2:, 1] = 0.01 * np.sin(3 * ang)                       # (not exactly coplanar: no degenerate planes)
+    tri = []
+    for i in range(n):
+        a, b = 2 + i, 2 + (i + 1) % n
+        tri += [0, b, a, 1, a, b]
+    return verts, np.asarray(tri, np.int32)
+
+
+@pytest.mark.parametrize("n", [40, 150])
+def test_high_valence_pieces_have_no_ring_limit(ctx, n):
+    """Poly::ClipPolyhedron has no limit on the number of neighbours of a vertex; the global-memory tier widens its ring
+    slots on demand (16 -> 32 -> ...).  A cone whose apex and base centre have n neighbours, as a mesh polyhedron
+    (ExtractNeighborFromMesh rings), cut by a 24-cell pattern: n = 40 against the oracle port (rings of up to 64),
+    n = 150 against the reference build itself."""
+    import hostapi as H
+    from oracle import refapi as R
+    if n > 60 and not common.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    verts, tri = _cone_mesh(n)
+    mesh = (R.mesh_polyhedron if common.have_ref() else H.mesh_polyhedron)(verts, tri)
+    assert int(np.diff(mesh.ring_off).max()) == n
+    cells = common.voronoi(46354, 24)
+    cp = cells.subset(range(cells.n))
+    cp.verts = cells.verts.copy()
+    cp.verts[:, :3] = cells.verts[:, :3] * np.float32(2.2) + np.array([0.0, 0.6, 0.0], np.float32)
+    planes, off = P.face_planes(cp)
+    want = (R.apply_fracture(mesh, planes, off, 8) if n > 60 else P.apply_fracture(mesh, planes, off, cap_frags=256, cap_verts=20000))
+    ctx.upload_pieces(mesh.verts, mesh.vert_off, mesh.ring_off, mesh.ring)
+    ctx.upload_cells(planes, off, cp.verts, cp.vert_off)
+    ctx.fracture_event()
+    got = ctx.download()
+    common.assert_fragments_equal(got, want, moments=(n <= 60))
+    assert want.n >= 8 and ctx.counts().n_tier3 > 0 and ctx.counts().n_failed == 0
+
+
+def test_failed_pairs_are_reported_per_pair(ctx):
+    """A malformed piece next to healthy ones: its pairs are listed by surtr_failed_pairs, surtr_event_counts says
+    SURTR_ERR_OVERFLOW, and every other fragment of the event is there and correct."""
+    from surtr_b200 import SurtrError
+    good = common.voronoi(1234, 30)
+    cells = common.voronoi(46354, 8)
+    bad = common.unit_cube()
+    bad.ring = bad.ring.copy()
+    bad.ring[5] = 200
+    pieces, _ = common.concat([good, bad, good])
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)
+    ctx.upload_cells(cells.planes, cells.plane_off)          # unbounded: every pair reaches the clipper
+    ctx.fracture_event()
+    with pytest.raises(SurtrError) as e:
+        ctx.counts()
+    assert e.value.code == 4
+    c = ctx.counts(allow_failed=True)
+    failed = ctx.failed_pairs()
+    assert c.n_failed == 8 and sorted(map(tuple, failed.tolist())) == [(30, k) for k in range(8)]
+    got = ctx.download(allow_failed=True)
+    want = P.apply_fracture(good, cells.planes, cells.plane_off)
+    sel = got.rec["piece"] < 30
+    assert sel.sum() == want.n and np.array_equal(got.rec["n_verts"][sel], want.nverts)
+    assert np.array_equal(bits(got.rec["volume"][sel]), bits(want.volume))
+    assert not np.any(got.rec["piece"] == 30) and (got.rec["piece"] > 30).sum() == want.n
+
+
 def test_resident_pattern_placement(ctx):
     """Row f-4: a pattern uploaded once in its own frame and placed on the device (surtr_place_pattern = Polygon3D::Scale +
     Translate with the face planes re-derived from the moved vertices, VMACH.cpp:303-310, 506-534), three placements in

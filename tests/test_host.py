@@ -268,6 +268,27 @@ def test_do_fracture_bunny(mode):
             c_ref = (want_c.volume[sel, None] * want_c.centroid[sel]).sum(0) / want_c.volume[sel].sum()
             assert np.abs(mass[b, 1:4] - c_ref).max() < 1e-4
             assert mass[b, 4:7].min() > 0
+    # ... and the compound INERTIA (PhysX's updateMassAndInertia, Surtr.cpp:2520, is not in the reference tree, so the
+    # yardstick is the oracle's double-precision polyhedral integral of every piece, combined over the compound in double
+    # with the parallel-axis theorem): all six terms of every compound within 1e-4 of the tensor's largest term
+    far = np.array([[1.0, 0.0, 0.0, -1.0e6]], np.float32)                      # a plane nothing reaches: pieces pass uncut
+    exact = P.apply_fracture(want_c, far, np.array([0, 1], np.uint32), inertia=True, cap_frags=want_c.n + 8, cap_verts=len(want_c.verts) + 64)
+    assert exact.n == want_c.n and np.array_equal(bits(exact.volume), bits(want_c.volume))
+    worst = 0.0
+    for b in range(ncomp):
+        sel = np.nonzero(want_c.cell == b)[0]
+        V, c, I = exact.volume[sel], exact.centroid[sel].astype(np.float64), exact.inertia[sel]
+        if V.sum() <= 0:
+            continue
+        com = (V[:, None] * c).sum(0) / V.sum()
+        d = c - com
+        want_I = np.array([
+            (I[:, 0] + V * (d[:, 1] ** 2 + d[:, 2] ** 2)).sum(), (I[:, 1] + V * (d[:, 0] ** 2 + d[:, 2] ** 2)).sum(),
+            (I[:, 2] + V * (d[:, 0] ** 2 + d[:, 1] ** 2)).sum(), (I[:, 3] - V * d[:, 0] * d[:, 1]).sum(),
+            (I[:, 4] - V * d[:, 0] * d[:, 2]).sum(), (I[:, 5] - V * d[:, 1] * d[:, 2]).sum()]) * 10.0
+        scale = np.abs(want_I[:3]).max()
+        worst = max(worst, float(np.abs(mass[b, 4:10].astype(np.float64) - want_I).max() / scale))
+    assert worst < 1e-4, worst
 
 
 def test_host_worker_pool():

@@ -194,6 +194,39 @@ def test_emulated_global_tier_on_the_bunny_mesh(emu):
     assert stats["overflow"] == 0 and want.n > 20
 
 
+def test_emulated_global_tier_with_wide_rings_and_lazy_compaction(emu):
+    """The global tier's ring stride is a run-time value (a vertex may have any number of neighbours) and its slots are
+    renumbered lazily: (a) the degenerate sequences again with 24 ring slots per vertex (not a power of two) and a
+    workspace so small (40 slots for 8-vertex pieces cut up to four times) that the renumbering runs inside the plane
+    loop; (b) a cone whose apex has 40 neighbours, cut by Voronoi cells, with 48 ring slots -- against the oracle port."""
+    emu.k3emu_set_gd.argtypes = [C.c_int]
+    d = np.load(os.path.join(GOLDEN, "degenerate_x400.npz"))
+    pieces, want = load_polyset(d, "pieces_"), load_polyset(d, "frag_")
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    try:
+        emu.k3emu_set_gd(24)
+        run_event(emu, pieces, d["planes"], d["plane_off"], want, stats, tier=(4, 40), cells=range(0, 400, 7))
+        d2 = np.load(os.path.join(GOLDEN, "cube_x64.npz"))
+        cells, cube, want2 = load_polyset(d2, "cells_"), load_polyset(d2, "pieces_"), load_polyset(d2, "frag_")
+        run_event(emu, cube, cells.planes, cells.plane_off, want2, stats, tier=(1, 64), cells=range(0, 64, 3))   # 20+ cuts in 64 slots
+        assert stats["overflow"] == 0 and stats["seq_cuts"] > 10
+        import test_gpu_parity as T
+        import hostapi as H
+        verts, tri = T._cone_mesh(40)
+        mesh = H.mesh_polyhedron(verts, tri)
+        vc = common.voronoi(46354, 24)
+        cp = vc.subset(range(vc.n))
+        cp.verts = vc.verts.copy()
+        cp.verts[:, :3] = vc.verts[:, :3] * np.float32(2.2) + np.array([0.0, 0.6, 0.0], np.float32)
+        planes, off = P.face_planes(cp)
+        wantc = P.apply_fracture(mesh, planes, off, cap_frags=256, cap_verts=20000)
+        emu.k3emu_set_gd(48)
+        run_event(emu, mesh, planes, off, wantc, stats, tier=(8, 256), cells=range(0, 24, 2))
+        assert stats["overflow"] == 0 and wantc.n >= 8
+    finally:
+        emu.k3emu_set_gd(16)
+
+
 def test_emulated_moments_of_two_different_fragments_per_warp(emu):
     """assemble_gather_kernel gives every fragment 16 lanes: two NEIGHBOURING fragments of different size share a warp
     and run sub_fragment_moments<16> in lock step.  Every consecutive pair of the reference's pieces200_x32 fragments
