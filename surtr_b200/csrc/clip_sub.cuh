@@ -765,14 +765,15 @@ __device__ void sub_fragment_moments(MomPoly& sp, const CutState& s, const Sub<L
 // and the fan pass follow table entries (one LDS.U16 per step).  Order, operands and accumulation are unchanged:
 // faces in Poly::ExtractFaces order (a face starts at its smallest vertex; vertices ascending, ring slots ascending),
 // fan triangles (p0, p_k, p_k+1) written to their slot in that order, ordered accumulation by four lanes.
-struct MomPoly2   // 4736 bytes per fragment
+struct __align__(16) MomPoly2   // 4736 bytes per fragment
 {
-    float x[64], y[64], z[64];
-    u64 ring[64];           // 8 x u8, 0xFF = empty slot
-    uint16_t estart[64];    // first directed-edge id of vertex v = its ring start
-    uint16_t en[512];       // directed edge e = (v -> ring[v][j]), e = estart[v] + j: next edge of the face loop | v << 10
+    float4 p[64];           // positions as the blob / the fragment array hold them (x, y, z, 0): one LDS.128 per vertex, and
+                            // the unit of the bulk-copy staging variant (cp.async.bulk global -> shared -> global)
     float4 tri[128];        // ordered fan-triangle records (dV, mx, my, mz); its first 512 bytes double as per-edge triangle counts before
-    uint16_t flist[128];    // one entry per face, in Poly::ExtractFaces order: start edge | first triangle << 9
+    u64 ring[64];           // 8 x u8, 0xFF = empty slot (phases 1-2); then flist: one u16 per face in Poly::ExtractFaces
+                            // order, start edge | first triangle << 9
+    uint16_t en[512];       // directed edge e = (v -> ring[v][j]), e = estart[v] + j: next edge of the face loop | v << 10
+    uint16_t estart[64];    // first directed-edge id of vertex v = its ring start
 };
 
 template <int L>
@@ -781,8 +782,9 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
     constexpr int G = Sub<L>::G;
     if (!has) nv = 0;
     const int gmax = L == 32 ? (nv + L - 1) / L : sub.max_warp((nv + L - 1) / L);
-    const float ox = sp.x[0], oy = sp.y[0], oz = sp.z[0];
+    const float ox = sp.p[0].x, oy = sp.p[0].y, oz = sp.p[0].z;
     uint8_t* ecnt = reinterpret_cast<uint8_t*>(sp.tri);   // fan triangles of the face that starts at edge e (phases 2-3 only)
+    uint16_t* flist = reinterpret_cast<uint16_t*>(sp.ring);   // (the ring words are dead once phase 2 is through)
 
     // ---- phase 1: successor of every directed edge (FaceLoop, Poly.cpp:34-41): (v -> a) is followed by (a -> entry before v in ring[a]) ----
 #pragma unroll 1
@@ -852,6 +854,8 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
             if (h == g) { cntg[h] = tris; facg[h] = faces; }
     }
 
+    sub.sync();   // every lane is through with the ring words: the face list takes their place
+
     // ---- phase 3: list the faces in order (vertex order = group-major, lane-minor; slots ascending) with their first triangle slot ----
     int n_tri = 0, n_faces = 0;
 #pragma unroll 1
@@ -875,7 +879,7 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
             {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                if (fpos < 128) sp.flist[fpos] = (uint16_t)((e0 + j) | (min(tpos, 127) << 9));
+                if (fpos < 128) flist[fpos] = (uint16_t)((e0 + j) | (min(tpos, 127) << 9));
                 fpos++;
                 tpos += ecnt[e0 + j];
             }
@@ -890,20 +894,23 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
 #pragma unroll 1
     for (int t = sub.sl; t < n_listed; t += L)
     {
-        const unsigned f = sp.flist[t];
+        const unsigned f = flist[t];
         unsigned en = sp.en[f & 511u];
         int w = (int)(f >> 9);
         const int v = (int)(en >> 10);
-        const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
+        const float4 q0 = sp.p[v];
+        const float p0x = __fsub_rn(q0.x, ox), p0y = __fsub_rn(q0.y, oy), p0z = __fsub_rn(q0.z, oz);
         en = sp.en[en & 1023u];
         int at = (int)(en >> 10);
-        float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
+        const float4 q1 = sp.p[at];
+        float p1x = __fsub_rn(q1.x, ox), p1y = __fsub_rn(q1.y, oy), p1z = __fsub_rn(q1.z, oz);
         en = sp.en[en & 1023u];
         at = (int)(en >> 10);
         int guard = 0;
         while (at != v && guard++ < 64)
         {
-            const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
+            const float4 q2 = sp.p[at];
+            const float p2x = __fsub_rn(q2.x, ox), p2y = __fsub_rn(q2.y, oy), p2z = __fsub_rn(q2.z, oz);
             float cx, cy, cz;
             cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
             const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);

@@ -1091,14 +1091,49 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs 
 // L lanes per candidate (L = 16: two candidates per warp, in lock step -- every candidate that reaches the moments is a
 // live fragment of similar size, so the lock step costs little and the face walks of sub_fragment_moments use twice the
 // lanes).  All lanes stay to the end: the collectives of the moments use the full warp mask.
+// ---- 1-D bulk copies of the TMA unit (cp.async.bulk, sm_90+) for the staging A/B of the gather (profiles/r2_staging_ab.txt) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy before a copy signals it
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void bulk_global_to_shared(void* dst, const void* src, unsigned bytes, uint64_t* bar)   // 16-byte aligned, bytes % 16 == 0
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_shared_to_global(void* dst, const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 constexpr int GATHER_LANES = 16;
 constexpr int GATHER_THREADS = 128;
-template <int L>
+// BULK = false: the fragment's positions travel blob -> registers -> (shared memory, fragment array) with one LDG.128,
+// one STS.128 and one STG.128 per vertex.  BULK = true: one elected lane per fragment hands both moves to the TMA unit --
+// cp.async.bulk global -> shared (mbarrier complete_tx) and shared -> global (bulk group) of the contiguous nv * 16 bytes.
+// Same results; which one ships is decided by the measurement in profiles/r2_staging_ab.txt (SURTR_K4_BULK selects).
+template <int L, bool BULK>
 __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(AssembleArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ MomPoly2 s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
+    __shared__ __align__(8) uint64_t s_bar[GATHER_THREADS / L];
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
     // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
@@ -1121,6 +1156,14 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
     }
     const int tier = have ? (int)r->tier : 0;
     MomPoly2& sp = s_poly[threadIdx.x / L];
+    uint64_t* bar = &s_bar[threadIdx.x / L];
+    if (BULK && have && tier == 1 && lane == 0)
+    {
+        // the TMA unit fetches the positions while the lanes below stage the rings
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (unsigned)cnv * 16u);
+        bulk_global_to_shared(sp.p, a.scratch1 + r->blob, (unsigned)cnv * 16u, bar);
+    }
     if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
@@ -1147,11 +1190,14 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
             const uint8_t* br = b + (size_t)cap * 18;
             for (int v = lane; v < cnv; v += L)
             {
-                const float4 p = bv[v];
                 const int r0 = bo[v], r1 = v + 1 < cnv ? (int)bo[v + 1] : cne;
-                a.f_verts[cvb + v] = p;
+                if (!BULK)
+                {
+                    const float4 p = bv[v];
+                    a.f_verts[cvb + v] = p;
+                    sp.p[v] = p;
+                }
                 a.f_ring_off[cvb + v] = (uint32_t)(crb + r0);
-                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
                 sp.estart[v] = (uint16_t)r0;
                 u64 rw = ~0ull;
                 for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, br[r0 + j]);
@@ -1171,6 +1217,12 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         }
     }
     const bool do_mo = have && tier == 1;
+    if (BULK) sub.sync();   // the barrier lane 0 initialised is visible to the lanes that now wait on it
+    if (BULK && do_mo)
+    {
+        while (!mbar_try_wait(bar, 0u)) { }                    // the positions have landed in shared memory
+        if (lane == 0) bulk_shared_to_global(a.f_verts + cvb, sp.p, (unsigned)cnv * 16u);   // ... and leave for the fragment array
+    }
     Moments mo;
     if (sub.any_warp(do_mo))
     {
@@ -1203,6 +1255,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         f.n_ring = (uint32_t)cne;
         a.f_rec[cfi] = f;
     }
+    if (BULK && do_mo && lane == 0) bulk_wait_all();   // the shared-memory source must outlive the copy
 }
 
 // Last kernel of an event: the counters go to the host through mapped pinned memory (no copy-engine queueing behind
