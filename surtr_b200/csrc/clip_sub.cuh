@@ -765,14 +765,14 @@ __device__ void sub_fragment_moments(MomPoly& sp, const CutState& s, const Sub<L
 // and the fan pass follow table entries (one LDS.U16 per step).  Order, operands and accumulation are unchanged:
 // faces in Poly::ExtractFaces order (a face starts at its smallest vertex; vertices ascending, ring slots ascending),
 // fan triangles (p0, p_k, p_k+1) written to their slot in that order, ordered accumulation by four lanes.
-struct __align__(16) MomPoly2   // 4736 bytes per fragment
+struct __align__(16) MomPoly2   // 3456 bytes per fragment: eight 128-thread blocks of the gather per SM
 {
-    float4 p[64];           // positions as the blob / the fragment array hold them (x, y, z, 0): one LDS.128 per vertex, and
-                            // the unit of the bulk-copy staging variant (cp.async.bulk global -> shared -> global)
-    float4 tri[128];        // ordered fan-triangle records (dV, mx, my, mz); its first 512 bytes double as per-edge triangle counts before
+    float x[64], y[64], z[64];
+    float4 tri[64];         // a window of 64 ordered fan-triangle records (dV, mx, my, mz); its first 512 bytes double as per-edge triangle counts before
     u64 ring[64];           // 8 x u8, 0xFF = empty slot (phases 1-2); then flist: one u16 per face in Poly::ExtractFaces
                             // order, start edge | first triangle << 9
     uint16_t en[512];       // directed edge e = (v -> ring[v][j]), e = estart[v] + j: next edge of the face loop | v << 10
+                            // (before phase 1: the staging area of the fragment's ring bytes, assemble_gather_kernel)
     uint16_t estart[64];    // first directed-edge id of vertex v = its ring start
 };
 
@@ -782,7 +782,7 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
     constexpr int G = Sub<L>::G;
     if (!has) nv = 0;
     const int gmax = L == 32 ? (nv + L - 1) / L : sub.max_warp((nv + L - 1) / L);
-    const float ox = sp.p[0].x, oy = sp.p[0].y, oz = sp.p[0].z;
+    const float ox = sp.x[0], oy = sp.y[0], oz = sp.z[0];
     uint8_t* ecnt = reinterpret_cast<uint8_t*>(sp.tri);   // fan triangles of the face that starts at edge e (phases 2-3 only)
     uint16_t* flist = reinterpret_cast<uint16_t*>(sp.ring);   // (the ring words are dead once phase 2 is through)
 
@@ -888,72 +888,81 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
     n_tri = min(n_tri, 128);
     sub.sync();
 
-    // ---- phase 4: lane = face: the fan triangles of a face, written to their slots; second moments on the fly ----
+    // ---- phases 4 + 5, over windows of 64 triangle slots (one window for fragments of up to 34 vertices) ----
+    // phase 4: lane = face: the fan triangles of a face, written to their slots; second moments on the fly
+    // phase 5: ordered accumulation (Poly.cpp:77-85), as sub_fragment_moments
     float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
     const int n_listed = has ? min(n_faces, 128) : 0;
-#pragma unroll 1
-    for (int t = sub.sl; t < n_listed; t += L)
-    {
-        const unsigned f = flist[t];
-        unsigned en = sp.en[f & 511u];
-        int w = (int)(f >> 9);
-        const int v = (int)(en >> 10);
-        const float4 q0 = sp.p[v];
-        const float p0x = __fsub_rn(q0.x, ox), p0y = __fsub_rn(q0.y, oy), p0z = __fsub_rn(q0.z, oz);
-        en = sp.en[en & 1023u];
-        int at = (int)(en >> 10);
-        const float4 q1 = sp.p[at];
-        float p1x = __fsub_rn(q1.x, ox), p1y = __fsub_rn(q1.y, oy), p1z = __fsub_rn(q1.z, oz);
-        en = sp.en[en & 1023u];
-        at = (int)(en >> 10);
-        int guard = 0;
-        while (at != v && guard++ < 64)
-        {
-            const float4 q2 = sp.p[at];
-            const float p2x = __fsub_rn(q2.x, ox), p2y = __fsub_rn(q2.y, oy), p2z = __fsub_rn(q2.z, oz);
-            float cx, cy, cz;
-            cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
-            const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
-            const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
-            const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
-            const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
-            if (w < 128) sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
-            w++;
-            // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
-            cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
-            cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
-            cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
-            cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
-            cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
-            cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
-            cov[6] += dV;
-            cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
-            p1x = p2x; p1y = p2y; p1z = p2z;
-            en = sp.en[en & 1023u];
-            at = (int)(en >> 10);
-        }
-    }
-    sub.sync();
-
-    // ---- phase 5: ordered accumulation (Poly.cpp:77-85), as sub_fragment_moments ----
     double zeroth = 0.0;
     float fsum = 0.f;
-    if (sub.sl < 4)
+    const int n_win = L == 32 ? n_tri : sub.max_warp(n_tri);
+#pragma unroll 1
+    for (int base = 0; base == 0 || base < n_win; base += 64)
     {
-        const float* comp = reinterpret_cast<const float*>(sp.tri) + sub.sl;
-        int t = 0;
-        for (; t + 4 <= n_tri; t += 4)   // the loads do not depend on the accumulation chain
+#pragma unroll 1
+        for (int t = sub.sl; t < n_listed; t += L)
         {
-            const float r0 = comp[4 * t], r1 = comp[4 * t + 4], r2 = comp[4 * t + 8], r3 = comp[4 * t + 12];
-            zeroth += (double)r0; zeroth += (double)r1; zeroth += (double)r2; zeroth += (double)r3;
-            fsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fsum, r0), r1), r2), r3);
+            const unsigned f = flist[t];
+            int w = (int)(f >> 9) - base;
+            const int w_end = (t + 1 < n_listed ? (int)(flist[t + 1] >> 9) : n_tri) - base;
+            if (w >= 64 || w_end <= 0) continue;   // no slot of this face in the window
+            unsigned en = sp.en[f & 511u];
+            const int v = (int)(en >> 10);
+            const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
+            en = sp.en[en & 1023u];
+            int at = (int)(en >> 10);
+            float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
+            en = sp.en[en & 1023u];
+            at = (int)(en >> 10);
+            int guard = 0;
+            while (at != v && guard++ < 64)
+            {
+                const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
+                if (w >= 0 && w < 64 && w + base < 128)
+                {
+                    float cx, cy, cz;
+                    cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
+                    const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
+                    const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
+                    const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
+                    const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
+                    sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
+                    // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
+                    cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
+                    cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
+                    cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
+                    cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
+                    cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
+                    cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
+                    cov[6] += dV;
+                    cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
+                }
+                w++;
+                p1x = p2x; p1y = p2y; p1z = p2z;
+                en = sp.en[en & 1023u];
+                at = (int)(en >> 10);
+            }
         }
-        for (; t < n_tri; t++)
+        sub.sync();
+        if (sub.sl < 4)
         {
-            const float r = comp[4 * t];
-            zeroth += (double)r;
-            fsum = __fadd_rn(fsum, r);
+            const float* comp = reinterpret_cast<const float*>(sp.tri) + sub.sl;
+            const int n_here = min(64, n_tri - base);
+            int t = 0;
+            for (; t + 4 <= n_here; t += 4)   // the loads do not depend on the accumulation chain
+            {
+                const float r0 = comp[4 * t], r1 = comp[4 * t + 4], r2 = comp[4 * t + 8], r3 = comp[4 * t + 12];
+                zeroth += (double)r0; zeroth += (double)r1; zeroth += (double)r2; zeroth += (double)r3;
+                fsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(fsum, r0), r1), r2), r3);
+            }
+            for (; t < n_here; t++)
+            {
+                const float r = comp[4 * t];
+                zeroth += (double)r;
+                fsum = __fadd_rn(fsum, r);
+            }
         }
+        if (base + 64 < n_win) sub.sync();   // the next window overwrites the records
     }
     zeroth = sub.shfl(zeroth, 0) / 6.0;
     float fx = sub.shfl(fsum, 1), fy = sub.shfl(fsum, 2), fz = sub.shfl(fsum, 3);

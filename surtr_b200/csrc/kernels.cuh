@@ -44,7 +44,8 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
     unsigned int n_ovf2;        // pairs the 128-slot tier handed on to the large on-chip tier
     unsigned int n_growdeg;     // global-tier pairs with a ring that outgrew the workspace's ring slots (the host enlarges them and re-runs)
     unsigned int max_deg;       // largest ring such a pair needed at staging time
-    unsigned int pad[2];
+    unsigned int k3_ticket;     // next candidate of the small tier's persistent launch
+    unsigned int pad;
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -719,30 +720,64 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
     bool bad = nv > S;
     if (!bad)
     {
+        // The piece's ring entries are ONE contiguous u16 stream (p_ring_off[v0] .. p_ring_off[v0 + nv]): the lanes load it
+        // coalesced and stage it as bytes in old_ring (unused until a sequential replay), then every lane assembles the
+        // 64-bit ring words of its vertices from shared memory -- instead of a chain of per-lane global loads, one per
+        // ring entry (the long-scoreboard stall at the head of every pair in profiles/r2_k3_cfg4.txt).
+        uint8_t* stage = reinterpret_cast<uint8_t*>(sp.old_ring);
+        const uint32_t rb = __ldg(a.p_ring_off + v0), re = __ldg(a.p_ring_off + v0 + nv);
+        int ne = (int)(re - rb);
+        if (re < rb || ne > 8 * S) { bad = true; ne = 0; }
+#pragma unroll 4
+        for (int e = lane; e < ne; e += 32)
+        {
+            const int idx = __ldg(a.p_ring + rb + e);
+            bad = bad || idx >= nv;
+            stage[e] = (uint8_t)idx;
+        }
+        float4 pp[G];
+        uint32_t r0[G], r1[G];
 #pragma unroll
         for (int g = 0; g < G; g++)
         {
             const int v = lane + 32 * g;
-            px[g] = py[g] = pz[g] = 0.f;
+            pp[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r0[g] = r1[g] = rb;
             if (v < nv)
             {
-                const float4 p = __ldg(a.p_verts + v0 + v);
-                const uint32_t r0 = a.p_ring_off[v0 + v];
-                const int d = (int)(a.p_ring_off[v0 + v + 1] - r0);
-                px[g] = p.x; py[g] = p.y; pz[g] = p.z;
-                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                pp[g] = __ldg(a.p_verts + v0 + v);
+                r0[g] = __ldg(a.p_ring_off + v0 + v);
+                r1[g] = __ldg(a.p_ring_off + v0 + v + 1);
+            }
+        }
+        __syncwarp();
+        const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(sp.old_ring);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            const int v = lane + 32 * g;
+            px[g] = pp[g].x; py[g] = pp[g].y; pz[g] = pp[g].z;
+            if (v < nv)
+            {
+                sp.x[v] = px[g]; sp.y[v] = py[g]; sp.z[v] = pz[g];
+                const int d = (int)(r1[g] - r0[g]);
+                const uint32_t o = r0[g] - rb;
                 u64 rw = ~0ull;
-                if (d > 8 || d == 0) bad = true;
+                if (r0[g] < rb || r1[g] > re || d > 8 || d <= 0) bad = true;
                 else
-                    for (int j = 0; j < d; j++)
-                    {
-                        const int idx = a.p_ring[r0 + j];
-                        bad = bad || idx >= nv;
-                        rw = rset(rw, j, idx);
-                    }
+                {
+                    // eight bytes from byte offset o (unaligned): three aligned words through the funnel shifter; the
+                    // read may run up to 11 bytes past the stream's end, which is still inside this FastPoly
+                    const uint32_t w0 = stage32[o >> 2], w1 = stage32[(o >> 2) + 1], w2 = stage32[(o >> 2) + 2];
+                    const unsigned sh = (o & 3u) * 8u;
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi2 = __funnelshift_r(w1, w2, sh);
+                    rw = (u64)lo | ((u64)hi2 << 32);
+                    if (d < 8) rw |= ~0ull << (8 * d);
+                }
                 sp.ring[v] = rw;
             }
         }
+        __syncwarp();   // old_ring is free again (fast_seq_cut snapshots into it)
     }
     bad = __ballot_sync(FULL, bad) != 0u;
     __syncwarp();
@@ -831,16 +866,37 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
 }
 
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
-template <int G, bool LIST>
-__global__ void __launch_bounds__(FAST_WARPS * 32, G == 2 ? 32 / FAST_WARPS : 8) clip_fast_kernel(ClipArgs a)
+// W = warps (= pairs) per block of the main launch.  The register file holds 32 of these warps per SM and a block's slots
+// are released only when its slowest pair is through, so W = 2 keeps about 0.7 x 32 warps resident on uneven pairs; W = 1
+// (32 blocks of one warp, the SM's block limit) releases every warp's slots on its own (SURTR_K3_WARPS selects, A/B in
+// profiles/r2_k3_block_ab.txt).
+template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false>
+__global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ FastPoly<G> s_poly[FAST_WARPS];
+    __shared__ FastPoly<G> s_poly[W];
     const int lane = threadIdx.x & 31;
     FastPoly<G>& sp = s_poly[threadIdx.x >> 5];
     const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (!LIST)
+    if (!LIST && PERSIST)
+    {
+        // resident warps pull candidates from a ticket counter (the next ticket is requested before the current pair is
+        // cut, so its round trip to the L2 hides behind the cut): no block launches, no ragged tail
+        unsigned long long n_items = a.ctl->n_cand;
+        if (n_items > a.cap_cand) n_items = a.cap_cand;
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(&a.ctl->k3_ticket, 1u);
+        for (;;)
+        {
+            const unsigned q = __shfl_sync(FULL, next, 0);
+            if (q >= n_items) break;
+            if (lane == 0) next = atomicAdd(&a.ctl->k3_ticket, 1u);
+            fast_pair<G, LIST>(a, sp, q, lane);
+            __syncwarp();
+        }
+    }
+    else if (!LIST)
     {
         unsigned long long n_items = a.ctl->n_cand;
         if (n_items > a.cap_cand) n_items = a.cap_cand;
@@ -1091,49 +1147,20 @@ __global__ void __launch_bounds__(AS_THREADS) assemble_scan_kernel(AssembleArgs 
 // L lanes per candidate (L = 16: two candidates per warp, in lock step -- every candidate that reaches the moments is a
 // live fragment of similar size, so the lock step costs little and the face walks of sub_fragment_moments use twice the
 // lanes).  All lanes stay to the end: the collectives of the moments use the full warp mask.
-// ---- 1-D bulk copies of the TMA unit (cp.async.bulk, sm_90+) for the staging A/B of the gather (profiles/r2_staging_ab.txt) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy before a copy signals it
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0u;
-}
-__device__ __forceinline__ void bulk_global_to_shared(void* dst, const void* src, unsigned bytes, uint64_t* bar)   // 16-byte aligned, bytes % 16 == 0
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_shared_to_global(void* dst, const void* src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 constexpr int GATHER_LANES = 16;
 constexpr int GATHER_THREADS = 128;
-// BULK = false: the fragment's positions travel blob -> registers -> (shared memory, fragment array) with one LDG.128,
-// one STS.128 and one STG.128 per vertex.  BULK = true: one elected lane per fragment hands both moves to the TMA unit --
-// cp.async.bulk global -> shared (mbarrier complete_tx) and shared -> global (bulk group) of the contiguous nv * 16 bytes.
-// Same results; which one ships is decided by the measurement in profiles/r2_staging_ab.txt (SURTR_K4_BULK selects).
-template <int L, bool BULK>
-__global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(AssembleArgs a)
+// Staging of the blob (north star: TMA versus plain loads, by measurement): a variant that handed the positions of a
+// fragment to the TMA unit -- cp.async.bulk global -> shared with an mbarrier, then shared -> global as a bulk group, one
+// elected lane per fragment -- was built (commit 4cd4327, SURTR_K4_BULK=1) and measured against the plain LDG.128 / STS /
+// STG.128 path below: 1.896 vs 1.597 ms on a 256-event config-4 batch, 73.8 vs 65.5 us on config 3, equal on config 2
+// (profiles/r2_staging_ab.md).  The copy is 0.2-0.4 KB per fragment: the mbarrier round trip costs more than the loads it
+// replaces, so the plain path ships.
+template <int L>
+__global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(AssembleArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ MomPoly2 s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
-    __shared__ __align__(8) uint64_t s_bar[GATHER_THREADS / L];
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
     // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
@@ -1156,14 +1183,6 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
     }
     const int tier = have ? (int)r->tier : 0;
     MomPoly2& sp = s_poly[threadIdx.x / L];
-    uint64_t* bar = &s_bar[threadIdx.x / L];
-    if (BULK && have && tier == 1 && lane == 0)
-    {
-        // the TMA unit fetches the positions while the lanes below stage the rings
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (unsigned)cnv * 16u);
-        bulk_global_to_shared(sp.p, a.scratch1 + r->blob, (unsigned)cnv * 16u, bar);
-    }
     if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
@@ -1177,52 +1196,78 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         }
         for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
     }
-    else if (have)
+    else if (have && tier != 1)
     {
-        const int cap = tier == 1 ? a.cap1 : a.cap2;
-        const unsigned char* b = (tier == 1 ? a.scratch1 : a.scratch2) + r->blob;
+        const unsigned char* b = a.scratch2 + r->blob;
         const float4* bv = reinterpret_cast<const float4*>(b);
-        const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 16);
-        if (tier == 1)
+        const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)a.cap2 * 16);
+        const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)a.cap2 * 18);
+        for (int v = lane; v < cnv; v += L)
         {
-            // copy out, and at the same time put positions and ring words back into shared memory, numbered as in the
-            // result (live slots = 0..nv-1), for Poly::ExtractFaces' count + Poly::Moments + inertia (Poly.cpp:55-126)
-            const uint8_t* br = b + (size_t)cap * 18;
-            for (int v = lane; v < cnv; v += L)
+            a.f_verts[cvb + v] = bv[v];
+            a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
+        }
+        for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
+    }
+    // Small tier: copy out, and at the same time put positions and ring words back into shared memory, numbered as in the
+    // result (live slots = 0..nv-1), for Poly::ExtractFaces' count + Poly::Moments + inertia (Poly.cpp:55-126).  The ring
+    // bytes are one contiguous stream: copied out coalesced and staged in shared memory (the edge table's space), from
+    // where every lane assembles its ring words -- not one global byte load per ring entry.
+    const bool t1 = have && tier == 1;
+    int r0v[64 / L], r1v[64 / L];
+    if (t1)
+    {
+        const unsigned char* b = a.scratch1 + r->blob;
+        const float4* bv = reinterpret_cast<const float4*>(b);
+        const uint16_t* bo = reinterpret_cast<const uint16_t*>(b + (size_t)a.cap1 * 16);
+        const uint8_t* br = b + (size_t)a.cap1 * 18;
+        uint8_t* stage = reinterpret_cast<uint8_t*>(sp.en);
+        for (int k = lane; k < cne; k += L)
+        {
+            const uint8_t x = br[k];
+            a.f_ring[crb + k] = x;
+            if (k < 512) stage[k] = x;
+        }
+#pragma unroll
+        for (int g = 0; g < 64 / L; g++)
+        {
+            const int v = lane + L * g;
+            r0v[g] = r1v[g] = 0;
+            if (v < cnv)
             {
-                const int r0 = bo[v], r1 = v + 1 < cnv ? (int)bo[v + 1] : cne;
-                if (!BULK)
-                {
-                    const float4 p = bv[v];
-                    a.f_verts[cvb + v] = p;
-                    sp.p[v] = p;
-                }
-                a.f_ring_off[cvb + v] = (uint32_t)(crb + r0);
-                sp.estart[v] = (uint16_t)r0;
-                u64 rw = ~0ull;
-                for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, br[r0 + j]);
+                const float4 p = bv[v];
+                r0v[g] = bo[v];
+                r1v[g] = v + 1 < cnv ? (int)bo[v + 1] : cne;
+                a.f_verts[cvb + v] = p;
+                a.f_ring_off[cvb + v] = (uint32_t)(crb + r0v[g]);
+                sp.x[v] = p.x; sp.y[v] = p.y; sp.z[v] = p.z;
+                sp.estart[v] = (uint16_t)r0v[g];
+            }
+        }
+    }
+    sub.sync();   // (all lanes of the warp: the staged bytes are visible)
+    if (t1)
+    {
+        const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(sp.en);
+#pragma unroll
+        for (int g = 0; g < 64 / L; g++)
+        {
+            const int v = lane + L * g;
+            if (v < cnv)
+            {
+                // eight bytes from byte offset o (unaligned): three aligned words through the funnel shifter
+                const int d = min(max(r1v[g] - r0v[g], 0), 8);
+                const unsigned o = (unsigned)min(r0v[g], 511);
+                const uint32_t w0 = stage32[o >> 2], w1 = stage32[(o >> 2) + 1], w2 = stage32[(o >> 2) + 2];
+                const unsigned sh = (o & 3u) * 8u;
+                u64 rw = (u64)__funnelshift_r(w0, w1, sh) | ((u64)__funnelshift_r(w1, w2, sh) << 32);
+                if (d < 8) rw |= ~0ull << (8 * d);
                 sp.ring[v] = rw;
             }
-            for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
         }
-        else
-        {
-            const uint16_t* br = reinterpret_cast<const uint16_t*>(b + (size_t)cap * 18);
-            for (int v = lane; v < cnv; v += L)
-            {
-                a.f_verts[cvb + v] = bv[v];
-                a.f_ring_off[cvb + v] = (uint32_t)(crb + bo[v]);
-            }
-            for (int k = lane; k < cne; k += L) a.f_ring[crb + k] = br[k];
-        }
+        // (the sub.sync() before the moments orders these reads before phase 1 rewrites the edge table)
     }
     const bool do_mo = have && tier == 1;
-    if (BULK) sub.sync();   // the barrier lane 0 initialised is visible to the lanes that now wait on it
-    if (BULK && do_mo)
-    {
-        while (!mbar_try_wait(bar, 0u)) { }                    // the positions have landed in shared memory
-        if (lane == 0) bulk_shared_to_global(a.f_verts + cvb, sp.p, (unsigned)cnv * 16u);   // ... and leave for the fragment array
-    }
     Moments mo;
     if (sub.any_warp(do_mo))
     {
@@ -1255,7 +1300,6 @@ __global__ void __launch_bounds__(GATHER_THREADS) assemble_gather_kernel(Assembl
         f.n_ring = (uint32_t)cne;
         a.f_rec[cfi] = f;
     }
-    if (BULK && do_mo && lane == 0) bulk_wait_all();   // the shared-memory source must outlive the copy
 }
 
 // Last kernel of an event: the counters go to the host through mapped pinned memory (no copy-engine queueing behind

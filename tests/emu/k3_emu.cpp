@@ -218,7 +218,7 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     for (int h = 0; h < 2; h++)
         for (int v = 0; v < n; v++)
         {
-            mp[h].p[v] = make_float4(out_verts4[4 * v], out_verts4[4 * v + 1], out_verts4[4 * v + 2], 0.f);
+            mp[h].x[v] = out_verts4[4 * v]; mp[h].y[v] = out_verts4[4 * v + 1]; mp[h].z[v] = out_verts4[4 * v + 2];
             u64 rw = ~0ull;
             const int r0 = (int)out_ring_off[v], r1 = (int)out_ring_off[v + 1];
             for (int j = 0; j < r1 - r0 && j < 8; j++) rw = rset(rw, j, out_ring[r0 + j]);
@@ -256,7 +256,7 @@ extern "C" int k3emu_moments_two(const float* const* verts4, const uint32_t* con
     for (int h = 0; h < 2; h++)
         for (int v = 0; v < n[h]; v++)
         {
-            mp[h].p[v] = make_float4(verts4[h][4 * v], verts4[h][4 * v + 1], verts4[h][4 * v + 2], 0.f);
+            mp[h].x[v] = verts4[h][4 * v]; mp[h].y[v] = verts4[h][4 * v + 1]; mp[h].z[v] = verts4[h][4 * v + 2];
             u64 rw = ~0ull;
             const int r0 = (int)ring_off[h][v], r1 = (int)ring_off[h][v + 1];
             if (r1 - r0 > 8) return -1;
