@@ -101,9 +101,15 @@ __device__ __forceinline__ int fast_comp_of(const FastMasks<G>& m, const unsigne
 // inserted.  Only the patch itself is order dependent: lane 0 replays it over the vertices it can touch (comp 2 = the
 // new ones first, then comp 0 = the in-plane ones, both ascending -- the reference's visiting order); erasing the marks
 // is per vertex (all lanes), and the splice loop runs only if some vertex was left with two neighbours (never seen on
-// the BASELINE configs).  Returns 0 on ring overflow; dead = the vertices spliced away.  Called by all lanes.
+// the BASELINE configs).  Returns ok = 0 on ring overflow; dead = the vertices spliced away.  Called by all lanes.
 template <int G>
-__device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, int hi0, int nnew, int lane, unsigned (&dead)[G])
+struct SeqResult   // by value: nothing of the caller's mask registers has its address taken
+{
+    int ok;
+    unsigned dead[G];
+};
+template <int G>
+__device__ __noinline__ SeqResult<G> fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, int hi0, int nnew, int lane)
 {
     const int hi1 = hi0 + nnew;
     for (int v = lane; v < hi1; v += 32) sp.old_ring[v] = sp.ring[v];
@@ -212,16 +218,21 @@ __device__ __noinline__ int fast_seq_cut(FastPoly<G>& sp, const FastMasks<G> m, 
 #pragma unroll
         for (int g = 0; g < G; g++) dd[g] = __shfl_sync(FULL, dd[g], 0);
     }
+    SeqResult<G> res;
+    res.ok = ok;
 #pragma unroll
-    for (int g = 0; g < G; g++) dead[g] = dd[g];
+    for (int g = 0; g < G; g++) res.dead[g] = dd[g];
     __syncwarp();
-    return ok;
+    return res;
 }
 
 // Renumber the live vertices to 0..n-1 keeping their order (the reference's compaction, Poly.cpp:464-495).
 template <int G>
-__device__ __noinline__ void fast_compact(FastPoly<G>& sp, unsigned (&live)[G], int& hi, int lane)
+__device__ __noinline__ int fast_compact(FastPoly<G>& sp, const FastMasks<G> m, int lane)   // returns the live count n: slots 0..n-1 are live afterwards
 {
+    unsigned live[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) live[g] = m.live[g];
     u64 r[G];
     float vx[G], vy[G], vz[G];
 #pragma unroll
@@ -254,21 +265,18 @@ __device__ __noinline__ void fast_compact(FastPoly<G>& sp, unsigned (&live)[G], 
         }
     }
     __syncwarp();
-    const int n = mcount<G>(live);
-    hi = n;
-#pragma unroll
-    for (int g = 0; g < G; g++) live[g] = lowmask32(n - 32 * g);
+    return mcount<G>(live);
 }
 
 // Every vertex in-plane: the reference's box test decides (Poly.cpp:297-299, 725-744).  Called by all lanes.
 template <int G>
-__device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly<G>& sp, const unsigned (&live)[G], int hi, const float4 pl, int lane)
+__device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly<G>& sp, const FastMasks<G> m, int hi, const float4 pl, int lane)
 {
     float lo[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f };
     float hv[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
     for (int v = lane; v < hi; v += 32)
     {
-        if (!mbit<G>(live, v)) continue;
+        if (!mbit<G>(m.live, v)) continue;
         lo[0] = fminf(lo[0], sp.x[v]); hv[0] = fmaxf(hv[0], sp.x[v]);
         lo[1] = fminf(lo[1], sp.y[v]); hv[1] = fmaxf(hv[1], sp.y[v]);
         lo[2] = fminf(lo[2], sp.z[v]); hv[2] = fmaxf(hv[2], sp.z[v]);
@@ -371,7 +379,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         if (!anyc)
         {
             // nothing clipped: "above" (Poly.cpp:328) -- unless every vertex is in-plane and the box test says "below"
-            if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m.live, hi, pl, lane)) { nv = 0; break; }
+            if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m, hi, pl, lane)) { nv = 0; break; }
             cur = nxt;
             p = pn;
             continue;
@@ -420,7 +428,9 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         {
             // out of slots: renumber the live vertices (exactly the reference's compaction) and redo this plane
             if (mcount<G>(m.live) + nnew > S) { status = CLIP_OVERFLOW; break; }
-            fast_compact<G>(sp, m.live, hi, lane);
+            hi = fast_compact<G>(sp, m, lane);
+#pragma unroll
+            for (int g = 0; g < G; g++) m.live[g] = lowmask32(hi - 32 * g);
 #pragma unroll
             for (int g = 0; g < G; g++)
             {
@@ -510,7 +520,10 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         if (need_seq)
         {
             seq_cuts++;
-            if (!fast_seq_cut<G>(sp, m, hi0, nnew, lane, dead)) { status = CLIP_OVERFLOW; break; }
+            const SeqResult<G> sr = fast_seq_cut<G>(sp, m, hi0, nnew, lane);
+            if (!sr.ok) { status = CLIP_OVERFLOW; break; }
+#pragma unroll
+            for (int g = 0; g < G; g++) dead[g] = sr.dead[g];
         }
         // lazy compaction: clipped vertices leave the live set, new ones join it
         hi = hi0 + nnew;

@@ -866,10 +866,10 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
 }
 
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
-// W = warps (= pairs) per block of the main launch.  The register file holds 32 of these warps per SM and a block's slots
-// are released only when its slowest pair is through, so W = 2 keeps about 0.7 x 32 warps resident on uneven pairs; W = 1
-// (32 blocks of one warp, the SM's block limit) releases every warp's slots on its own (SURTR_K3_WARPS selects, A/B in
-// profiles/r2_k3_block_ab.txt).
+// W = warps (= pairs) per block, PERSIST = resident warps with a ticket counter (the main launch; measured against one
+// block per one / two pairs in profiles/r2_k3_launch_shape.md: 2.50 vs 4.04 / 3.41 ms on a 256-event config-4 batch -- the
+// register file holds 32 of these warps per SM, a two-pair block keeps its slots until its slower pair is through, and
+// one-pair blocks are bound by the block launch rate).
 template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false>
 __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(ClipArgs a)
 {
@@ -881,19 +881,24 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(
     const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (!LIST && PERSIST)
     {
-        // resident warps pull candidates from a ticket counter (the next ticket is requested before the current pair is
-        // cut, so its round trip to the L2 hides behind the cut): no block launches, no ragged tail
+        // Resident warps (one block = one warp, 32 per SM): warp w cuts candidate w, then pulls further candidates from a
+        // ticket counter.  The next ticket is requested before the current pair is cut, so its round trip to the L2 hides
+        // behind the cut; an event of a single wave (config 2: 4096 pairs) never touches the counter.  Against one block
+        // per pair (SURTR_K3_WARPS=2) this removes the block launches -- the grid is sized by capacity, more than half
+        // of its blocks find no pair -- and the ragged tail: 3.41 -> 2.50 ms on a 256-event config-4 batch
+        // (profiles/r2_k3_launch_shape.md).
         unsigned long long n_items = a.ctl->n_cand;
         if (n_items > a.cap_cand) n_items = a.cap_cand;
-        unsigned next = 0;
-        if (lane == 0) next = atomicAdd(&a.ctl->k3_ticket, 1u);
-        for (;;)
+        const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+        const bool more = nw < n_items;
+        unsigned q = (unsigned)wid;
+        while (q < n_items)
         {
-            const unsigned q = __shfl_sync(FULL, next, 0);
-            if (q >= n_items) break;
-            if (lane == 0) next = atomicAdd(&a.ctl->k3_ticket, 1u);
+            unsigned next = 0xffffffffu;
+            if (more && lane == 0) next = nw + atomicAdd(&a.ctl->k3_ticket, 1u);
             fast_pair<G, LIST>(a, sp, q, lane);
             __syncwarp();
+            q = __shfl_sync(FULL, next, 0);
         }
     }
     else if (!LIST)
@@ -1163,11 +1168,17 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(Asse
     __shared__ MomPoly2 s_poly[GATHER_THREADS / L];   // a small-tier fragment is rebuilt here for its face count and moments
     const Sub<L> sub(threadIdx.x & 31);
     const int lane = sub.sl;
-    // one sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and two
-    // fragments that share a warp are of similar size
-    const unsigned long long f = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+    MomPoly2& sp = s_poly[threadIdx.x / L];
     unsigned long long n_frag = a.ctl->n_frag;
     if (n_frag > a.cap_frag) n_frag = a.cap_frag;
+    // One sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and the
+    // fragments that share a warp are neighbours of similar size.  The grid is resident (8 blocks per SM) and strides over
+    // the fragments: the fragment count is only known on the device, and a grid sized by capacity launched two empty
+    // blocks for every useful one.  The trip count is warp-uniform (the collectives below use the full mask).
+    const unsigned long long per_warp = 32 / L, stride = (unsigned long long)gridDim.x * (GATHER_THREADS / L);
+    for (unsigned long long fw = ((unsigned long long)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5)) * per_warp; fw < n_frag; fw += stride)
+    {
+    const unsigned long long f = fw + (threadIdx.x & 31) / L;
     bool have = f < n_frag;
     const unsigned long long q = have ? a.frag_cand[f] : 0ull;
     const CandRec* r = a.rec + q;
@@ -1182,7 +1193,6 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(Asse
         if (cfi >= a.cap_frag || cvb + cnv > a.cap_fverts || crb + cne > a.cap_fring) have = false;   // the host grows and re-runs
     }
     const int tier = have ? (int)r->tier : 0;
-    MomPoly2& sp = s_poly[threadIdx.x / L];
     if (have && tier == 3)
     {
         const unsigned char* b = a.scratch3 + r->blob;
@@ -1299,6 +1309,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(Asse
         }
         f.n_ring = (uint32_t)cne;
         a.f_rec[cfi] = f;
+    }
+    __syncwarp();   // the workspace is reused by the next fragment
     }
 }
 

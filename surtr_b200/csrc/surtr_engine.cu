@@ -135,7 +135,7 @@ struct surtr_ctx
     bool profiled_last = false;
     bool tier1b_enabled = false;  // the 128-slot warp-per-pair tier is launched once an event needed it
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
-    int k3_warps = 1;             // SURTR_K3_WARPS=1|2: pairs per block of the small tier's main launch; 0: persistent warps + ticket
+    int k3_warps = 0;             // small tier's main launch: 0 = persistent warps + ticket (default); SURTR_K3_WARPS=2: one block of two pairs per two candidates (A/B)
     bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
     bool tier3_enabled = false;   // likewise the global-memory tier
@@ -372,7 +372,6 @@ int launch_event(surtr_ctx* ctx)
         if (ctx->k3_round1) launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         else if (ctx->k3_warps == 0)
             launch_pdl(clip_fast_kernel<2, false, 1, true>, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, ctx->cap_cand), (uint64_t)ctx->num_sm * 32)), dim3(32), 0, ctx->stream, ca);
-        else if (ctx->k3_warps == 1) launch_pdl(clip_fast_kernel<2, false, 1>, dim3((unsigned)std::max<uint64_t>(1, ctx->cap_cand)), dim3(32), 0, ctx->stream, ca);
         else launch_pdl(clip_fast_kernel<2, false, 2>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
@@ -433,7 +432,8 @@ int launch_event(surtr_ctx* ctx)
         ctx->launches++;
         if (ctx->profile) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
         constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
-        const uint64_t gblocks = std::max<uint64_t>(1, (std::min(ctx->cap_cand, ctx->cap_frag) + cand_per_block - 1) / cand_per_block);
+        const uint64_t gblocks = std::min<uint64_t>(std::max<uint64_t>(1, (std::min(ctx->cap_cand, ctx->cap_frag) + cand_per_block - 1) / cand_per_block),
+                                                    (uint64_t)ctx->num_sm * 8);   // resident grid, strides over the fragments
         launch_pdl(assemble_gather_kernel<GATHER_LANES>, dim3((unsigned)gblocks), dim3(GATHER_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
     }
@@ -616,7 +616,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
     cudaFuncSetAttribute(clip_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_ws_bytes());
     if (const char* e = std::getenv("SURTR_K3")) ctx->k3_round1 = std::string(e) == "sub";
     if (const char* e = std::getenv("SURTR_DEBUG_NO_TIER1B")) ctx->no_tier1b = e[0] == '1';
-    if (const char* e = std::getenv("SURTR_K3_WARPS")) ctx->k3_warps = e[0] == '2' ? 2 : (e[0] == '0' ? 0 : 1);
+    if (const char* e = std::getenv("SURTR_K3_WARPS")) ctx->k3_warps = e[0] == '2' ? 2 : 0;
     *out = ctx;
     return SURTR_OK;
 }

@@ -6,7 +6,7 @@ mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/${T}_pytest.log 2>&1
 tail -1 $O/${T}_pytest.log
 for rep in 1 2 3; do
-for k in 2 1 0; do
+for k in 2 0; do
   for w in config4 config3 config2; do
     SURTR_K3_WARPS=$k EVENTS=256 python tools/gpu_profile_workloads.py $w 1 2>&1 | tail -1 >> $O/${T}_k3warps${k}_$w.jsonl
   done
