@@ -12,7 +12,7 @@ of the 4096 events, issued as batches of independent events through ev_piece_off
             CUDA events around K steps on the engine's stream, max over ranks;
   e2e       the same job through the C ABI with HOST buffers: every step uploads every event (pinned host memory, float3
             wire format), cuts it and downloads every fragment, batches pipelined over a few contexts;
-  roofline  K3 small tier (clip_sub_kernel), the dominant kernel: algorithmic bytes of the launch /
+  roofline  K3 small tier (clip_fast_kernel), the dominant kernel: algorithmic bytes of the launch /
             its duration from CUDA events between the kernels, against the measured HBM peak (MEASURED_PEAKS.json);
   kernels   the same for every kernel of the event (share of the step, GB/s of its own algorithmic bytes);
   config3 / config2 / config5   the other BASELINE configs as secondary results: p50 latency of the 10 000 x 256 event,
@@ -415,7 +415,7 @@ def main():
         kernels = {k: {"ms": round(v, 4), "share_of_step": round(v / step_ms_rank, 4)} for k, v in phases.items()}
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic["bytes_per_launch"] if traffic else None,
-                    "kernel": "clip_sub_kernel<32> (K3, small tier: one warp per candidate pair)",
+                    "kernel": "clip_fast_kernel<2> (K3, small tier: one warp per candidate pair, resident warps)",
                     "kernel_ms": k3_ms, "launches": len(res),
                     "algorithmic_bytes_per_launch": alg_bytes / len(res),
                     "units_per_launch": f"{frags_rank // len(res)} surviving pairs x (16 V_in + 4 E2_in + 16 P + 16 V_out + 4 E2_out + 64) bytes",

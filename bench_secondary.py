@@ -226,7 +226,7 @@ def dma_ceiling(torch, dev, world, barrier, allreduce, dist, mib: int = 256, rep
 # ------------------------------------------------------------------------------------------------ ncu traffic
 def kernel_source_sha() -> str:
     h = hashlib.sha1()
-    for f in ("clip_sub.cuh", "clip_warp.cuh", "kernels.cuh", "surtr_math.cuh"):
+    for f in ("clip_fast.cuh", "clip_sub.cuh", "clip_warp.cuh", "kernels.cuh", "surtr_math.cuh"):
         h.update(open(os.path.join(ROOT, "surtr_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

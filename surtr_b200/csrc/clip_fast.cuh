@@ -31,22 +31,25 @@ struct FastPoly   // one per warp in shared memory: 31 bytes per slot (G = 2: 19
 
 constexpr int FAST_MAX_PLANES = 64;   // planes the prefilter keeps a bit for (cells beyond it: every plane takes the exact path)
 
-// smallest plane index >= from whose bit is set in the visit words (npl if none); warp-uniform
-__device__ __forceinline__ int fast_next_plane(const unsigned (&visit)[(FAST_MAX_PLANES + 31) / 32], int from, int npl)
+// The planes the exact path still has to look at, as a bit set that is consumed from the bottom: bits 0..63 = planes
+// 0..63 (cleared by the prefilter for planes it proved irrelevant), `tail` = the next plane >= 64 (cells with more than
+// FAST_MAX_PLANES planes visit those one after the other).  Warp-uniform.
+struct PlaneQueue
 {
-    if (npl > FAST_MAX_PLANES) return from < npl ? from : npl;
-#pragma unroll
-    for (int w = 0; w < (FAST_MAX_PLANES + 31) / 32; w++)
+    unsigned w0, w1;
+    int tail;
+    __device__ __forceinline__ int peek(int npl) const   // smallest plane left (npl if none)
     {
-        if (from < 32 * (w + 1))
-        {
-            const int lo = from > 32 * w ? from - 32 * w : 0;
-            const unsigned rest = visit[w] & (0xffffffffu << lo);
-            if (rest) { const int p = 32 * w + __ffs((int)rest) - 1; return p < npl ? p : npl; }
-        }
+        const int p = w0 ? __ffs((int)w0) - 1 : (w1 ? 31 + __ffs((int)w1) : tail);
+        return p < npl ? p : npl;
     }
-    return npl;
-}
+    __device__ __forceinline__ void pop()
+    {
+        if (w0) w0 &= w0 - 1u;
+        else if (w1) w1 &= w1 - 1u;
+        else tail++;
+    }
+};
 
 template <int G>
 struct FastMasks   // warp-uniform
@@ -349,15 +352,18 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         if (kill) { nv = 0; npl = 0; }
     }
 
-    float4 cur = npl > 0 ? __ldg(planes) : make_float4(0.f, 0.f, 0.f, 0.f);
-    int p = 0;
-    // first plane to visit
-    p = fast_next_plane(visit, 0, npl);
+    PlaneQueue pq;
+    pq.w0 = visit[0] & lowmask32(npl);
+    pq.w1 = visit[1] & lowmask32(npl - 32);
+    pq.tail = FAST_MAX_PLANES;
+    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = pq.peek(npl);   // first plane to visit
+    pq.pop();
     if (p < npl) cur = __ldg(planes + p);
     while (p < npl && nv > 0)
     {
         const float4 pl = cur;
-        const int pn = fast_next_plane(visit, p + 1, npl);                    // next plane the exact path has to look at
+        const int pn = pq.peek(npl);                                           // next plane the exact path has to look at
         const float4 nxt = __ldg(planes + (pn < npl ? pn : p));                // broadcast load, one plane ahead
 
         // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per vertex group ----
@@ -382,6 +388,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m, hi, pl, lane)) { nv = 0; break; }
             cur = nxt;
             p = pn;
+            pq.pop();
             continue;
         }
         if (!anyk) { nv = 0; break; }   // "below" (Poly.cpp:322-327)
@@ -542,6 +549,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         __syncwarp();         // ring words composed above are visible to the next cut
         cur = nxt;
         p = pn;
+        pq.pop();
     }
 #pragma unroll
     for (int g = 0; g < G; g++) live[g] = m.live[g];

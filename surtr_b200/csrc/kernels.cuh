@@ -866,6 +866,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
 }
 
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
+constexpr int FAST_PERSIST_WARPS = 4;   // warps per block of the resident launch (each warp pulls its own candidates; fewer, larger blocks = fewer block launches on a one-wave event)
 // W = warps (= pairs) per block, PERSIST = resident warps with a ticket counter (the main launch; measured against one
 // block per one / two pairs in profiles/r2_k3_launch_shape.md: 2.50 vs 4.04 / 3.41 ms on a 256-event config-4 batch -- the
 // register file holds 32 of these warps per SM, a two-pair block keeps its slots until its slower pair is through, and
@@ -1172,9 +1173,11 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(Asse
     unsigned long long n_frag = a.ctl->n_frag;
     if (n_frag > a.cap_frag) n_frag = a.cap_frag;
     // One sub-warp per FRAGMENT (the scan listed the candidates that produced one): every sub-warp has work, and the
-    // fragments that share a warp are neighbours of similar size.  The grid is resident (8 blocks per SM) and strides over
-    // the fragments: the fragment count is only known on the device, and a grid sized by capacity launched two empty
-    // blocks for every useful one.  The trip count is warp-uniform (the collectives below use the full mask).
+    // fragments that share a warp are neighbours of similar size.  The grid is capped at four waves of blocks (8 resident
+    // per SM) and strides over the fragments: the fragment count is only known on the device, and a grid sized by capacity
+    // launched two empty blocks for every useful one (1.34 -> 1.26 ms on a 256-event config-4 batch); a single resident
+    // wave was slower on small events (config 3: 57 -> 64 us -- all warps in the same phase at the same time).
+    // The trip count is warp-uniform (the collectives below use the full mask).
     const unsigned long long per_warp = 32 / L, stride = (unsigned long long)gridDim.x * (GATHER_THREADS / L);
     for (unsigned long long fw = ((unsigned long long)blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5)) * per_warp; fw < n_frag; fw += stride)
     {

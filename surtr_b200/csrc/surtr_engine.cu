@@ -371,7 +371,9 @@ int launch_event(surtr_ctx* ctx)
         const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + pairs_per_block - 1) / pairs_per_block);
         if (ctx->k3_round1) launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         else if (ctx->k3_warps == 0)
-            launch_pdl(clip_fast_kernel<2, false, 1, true>, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, ctx->cap_cand), (uint64_t)ctx->num_sm * 32)), dim3(32), 0, ctx->stream, ca);
+            launch_pdl(clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true>,
+                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * (32 / FAST_PERSIST_WARPS))),
+                       dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
         else launch_pdl(clip_fast_kernel<2, false, 2>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
@@ -433,7 +435,7 @@ int launch_event(surtr_ctx* ctx)
         if (ctx->profile) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
         constexpr uint64_t cand_per_block = GATHER_THREADS / GATHER_LANES;
         const uint64_t gblocks = std::min<uint64_t>(std::max<uint64_t>(1, (std::min(ctx->cap_cand, ctx->cap_frag) + cand_per_block - 1) / cand_per_block),
-                                                    (uint64_t)ctx->num_sm * 8);   // resident grid, strides over the fragments
+                                                    (uint64_t)ctx->num_sm * 32);  // at most four waves of blocks, striding over the fragments
         launch_pdl(assemble_gather_kernel<GATHER_LANES>, dim3((unsigned)gblocks), dim3(GATHER_THREADS), 0, ctx->stream, aa);
         ctx->launches++;
     }

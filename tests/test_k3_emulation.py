@@ -163,6 +163,28 @@ def test_emulated_kernels_against_the_oracle_port(small):
     assert want.n == 48 and stats["cuts"] > 48 * 20
 
 
+def test_emulated_plane_queue_beyond_one_and_two_words(small):
+    """Cells of 40, 64, 65 and 150 planes (tangent planes of a sphere, most of them far from the piece): the plane
+    prefilter keeps one bit per plane in two 32-bit words and visits planes beyond the 64th one after the other
+    (clip_fast.cuh, PlaneQueue); expected = the oracle port."""
+    pieces = common.voronoi(1234, 40)
+    rng = np.random.default_rng(5)
+    planes, off = [], [0]
+    for n in (40, 64, 65, 150):
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = rng.uniform(0.25, 0.9, size=n)           # the sphere sits at the box centre; small r cuts, large r only touches the prefilter
+        c = np.array([0.5, 0.5, 0.5])
+        pl = np.concatenate([d, -(d @ c + r)[:, None]], axis=1).astype(np.float32)
+        planes.append(pl)
+        off.append(off[-1] + n)
+    planes, off = np.concatenate(planes), np.array(off, np.uint32)
+    want = P.apply_fracture(pieces, planes, off)
+    stats = dict(pairs=0, seq_cuts=0, cuts=0, overflow=0)
+    run_event(small, pieces, planes, off, want, stats)
+    assert want.n >= 10 and stats["cuts"] > 50
+
+
 @pytest.mark.parametrize("warps", [1, 4, 8])
 def test_emulated_large_tiers_on_reference_fixtures(emu, warps):
     """clip_global.cuh (global_clip_by_planes + global_fragment_moments) as one warp, as the four-warp block of
