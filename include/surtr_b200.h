@@ -185,26 +185,40 @@ int surtr_download_fragments_packed_async(surtr_ctx* ctx, surtr_fragment* fragme
  * boxes: 4 MB copies reach a third of the rate of 64 MB copies when both directions are busy, profiles/r2_pcie.txt), so
  * a caller that streams event batches moves ONE blob per direction instead of 8 + 4 arrays.
  *
- * Input blob = the arrays of surtr_upload_pieces3 + surtr_upload_cells3 back to back at the byte offsets
- * surtr_input_blob_layout returns (every section 256-byte aligned; ev_* sections hold n_events + 1 offsets, ignored when
- * n_events == 0 = one event; n_cell_verts == 0 = unbounded cells).  The blob is copied with one cudaMemcpyAsync on the
- * context stream (pinned memory for it to be asynchronous; offsets are also read on the host for validation) and the
- * index arrays are used in place on the device. */
+ * Both blobs are COMPACT wire formats -- the loop is bound by the bytes that cross PCIe (bench.py: e2e.achieved_gbs
+ * against dma_ceiling), so nothing travels wider than it has to: float3 positions, ONE length byte per vertex instead
+ * of a 32-bit ring offset, and one-byte ring entries whenever no polyhedron of the batch has more than 256 vertices
+ * (ring_entry_bytes = 1; a Poly::Vertex::NeighborVertexVec entry is a vertex index local to its polyhedron).  One small
+ * kernel per direction converts between the wire format and the resident arrays (float4, 32-bit offsets, 16-bit entries).
+ *
+ * Input blob, sections at the byte offsets surtr_input_blob_layout returns (every section 256-byte aligned):
+ *   verts3       float[3 * n_piece_verts]   piece vertices
+ *   vert_off     u32[n_pieces + 1]          first vertex of every piece
+ *   ring_base    u32[n_pieces + 1]          first ring entry of every piece (ring_base[n_pieces] = n_piece_ring)
+ *   ring_len     u8[n_piece_verts]          neighbours of every vertex
+ *   ring         u8 | u16 [n_piece_ring]    neighbour ids, local to the piece (ring_entry_bytes = 1 needs pieces of <= 256 vertices)
+ *   planes4, plane_off, cell_verts3, cvert_off   as surtr_upload_cells3 (n_cell_verts == 0 = unbounded cells)
+ *   ev_piece_off, ev_cell_off   u32[n_events + 1] each, ignored when n_events == 0 = one event
+ * The blob is copied with one cudaMemcpyAsync on the context stream (pinned memory for it to be asynchronous; the per-piece
+ * and per-event offsets are also read on the host for validation before the context is touched). */
 typedef struct surtr_in_layout {
-    uint64_t verts3, vert_off, ring_off, ring, planes4, plane_off, cell_verts3, cvert_off, ev_piece_off, ev_cell_off, total;
+    uint64_t verts3, vert_off, ring_base, ring_len, ring, planes4, plane_off, cell_verts3, cvert_off, ev_piece_off, ev_cell_off, total;
 } surtr_in_layout;
 int surtr_input_blob_layout(uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring, uint32_t n_cells, uint64_t n_planes,
-                            uint64_t n_cell_verts, uint32_t n_events, surtr_in_layout* out);
+                            uint64_t n_cell_verts, uint32_t n_events, uint32_t ring_entry_bytes, surtr_in_layout* out);
 int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring,
-                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events);
-/* Output blob = the arrays of surtr_download_fragments_packed (records | float3 positions | one byte of ring length per
- * vertex | ring entries) at the byte offsets returned in *out, assembled on the device and moved with ONE copy on the
- * context's copy stream.  Waits for the event (which sizes the blob); SURTR_ERR_INVALID with *out filled in when
- * `capacity` is too small.  Completion rules as surtr_download_fragments_async.  `host_blob` may also point to DEVICE
- * memory (the copy is issued with cudaMemcpyDefault): that is how the multi-GPU gather gets one contiguous blob per rank. */
+                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events, uint32_t ring_entry_bytes);
+/* Output blob = records | float3 positions | one byte of ring length per vertex | ring entries (one byte each when no
+ * fragment of the event has more than 256 vertices, else two: out->ring_entry_bytes says which) at the byte offsets
+ * returned in *out, assembled on the device and moved with ONE copy on the context's copy stream.  Waits for the event
+ * (which sizes the blob); SURTR_ERR_INVALID with *out filled in when `capacity` is too small (64 n_fragments + 13 n_verts
+ * + 2 n_ring + 1024 always suffices).  Completion rules as surtr_download_fragments_async.  `host_blob` may also point
+ * to DEVICE memory (the copy is issued with cudaMemcpyDefault): that is how the multi-GPU gather gets one contiguous
+ * blob per rank. */
 typedef struct surtr_out_layout {
     uint64_t fragments, verts3, ring_len, ring, total;   /* byte offsets, total size */
     uint64_t n_fragments, n_verts, n_ring;
+    uint64_t ring_entry_bytes;                           /* 1 or 2 */
 } surtr_out_layout;
 int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity, surtr_out_layout* out);
 int surtr_sync(surtr_ctx* ctx);

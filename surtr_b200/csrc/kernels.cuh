@@ -45,7 +45,7 @@ struct Ctl   // device-side counters of one event (zeroed before every event)
     unsigned int n_growdeg;     // global-tier pairs with a ring that outgrew the workspace's ring slots (the host enlarges them and re-runs)
     unsigned int max_deg;       // largest ring such a pair needed at staging time
     unsigned int k3_ticket;     // next candidate of the small tier's persistent launch
-    unsigned int pad;
+    unsigned int max_big_verts; // largest vertex count among the fragments of the larger tiers (small-tier fragments have <= 64): picks the ring entry width of the output blob
 };
 
 struct BpTile   // one broad-phase tile: <= 256 pieces x <= 32 cells of one event
@@ -167,23 +167,63 @@ __global__ void __launch_bounds__(256) widen3_kernel(const float* __restrict__ i
         out4[i] = make_float4(__ldg(in3 + 3 * i), __ldg(in3 + 3 * i + 1), __ldg(in3 + 3 * i + 2), 0.f);
 }
 
-// surtr_upload_blob: both float3 streams of the input blob (pieces, cell vertices) in one launch.
-__global__ void __launch_bounds__(256) widen3x2_kernel(const float* __restrict__ a3, float4* __restrict__ a4, uint64_t na,
-                                                       const float* __restrict__ b3, float4* __restrict__ b4, uint64_t nb)
+// surtr_upload_blob: the compact input blob -> the resident arrays, one launch.  Both float3 streams (pieces, cell
+// vertices) are widened to float4; the ring offsets are rebuilt from one LENGTH byte per vertex (a warp per piece: its
+// first ring entry comes with the blob, the rest is a warp prefix sum); RB = 1: the ring entries travel as bytes (every
+// piece has at most 256 vertices) and are widened to the resident 16-bit entries.
+template <int RB>
+__global__ void __launch_bounds__(256) expand_blob_kernel(const float* __restrict__ a3, float4* __restrict__ a4, uint64_t na,
+                                                          const float* __restrict__ b3, float4* __restrict__ b4, uint64_t nb,
+                                                          const uint32_t* __restrict__ vert_off, const uint32_t* __restrict__ ring_base,
+                                                          const uint8_t* __restrict__ ring_len, uint32_t n_pieces, uint32_t* __restrict__ ring_off,
+                                                          const uint8_t* __restrict__ ring8, uint16_t* __restrict__ ring16, uint64_t n_ring)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (uint64_t)gridDim.x * blockDim.x)
+    const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = t0; i < na + nb; i += stride)
     {
         if (i < na) a4[i] = make_float4(__ldg(a3 + 3 * i), __ldg(a3 + 3 * i + 1), __ldg(a3 + 3 * i + 2), 0.f);
         else { const uint64_t j = i - na; b4[j] = make_float4(__ldg(b3 + 3 * j), __ldg(b3 + 3 * j + 1), __ldg(b3 + 3 * j + 2), 0.f); }
     }
+    const int lane = threadIdx.x & 31;
+    for (uint64_t p = t0 >> 5; p < n_pieces; p += stride >> 5)
+    {
+        const uint32_t v0 = vert_off[p], v1 = vert_off[p + 1];
+        uint32_t run = ring_base[p];
+        for (uint32_t v = v0; v < v1; v += 32)   // (v0 and v1 are warp-uniform)
+        {
+            const uint32_t len = v + lane < v1 ? ring_len[v + lane] : 0u;
+            int tot;
+            const uint32_t ex = (uint32_t)warp_exscan((int)len, lane, tot);
+            if (v + lane < v1) ring_off[v + lane] = run + ex;
+            run += (uint32_t)tot;
+        }
+        if (p + 1 == n_pieces && lane == 0) ring_off[v1] = ring_base[n_pieces];
+    }
+    if (n_pieces == 0 && t0 == 0) ring_off[0] = 0u;
+    if (RB == 1)
+    {
+        // 16 entries per thread where both sides are aligned (both arrays start on a 256-byte boundary)
+        const uint64_t n16 = n_ring / 16;
+        const uint4* in16 = reinterpret_cast<const uint4*>(ring8);
+        uint4* out16 = reinterpret_cast<uint4*>(ring16);
+        for (uint64_t i = t0; i < n16; i += stride)
+        {
+            const uint4 x = __ldg(in16 + i);
+            out16[2 * i] = make_uint4(__byte_perm(x.x, 0u, 0x4140), __byte_perm(x.x, 0u, 0x4342), __byte_perm(x.y, 0u, 0x4140), __byte_perm(x.y, 0u, 0x4342));
+            out16[2 * i + 1] = make_uint4(__byte_perm(x.z, 0u, 0x4140), __byte_perm(x.z, 0u, 0x4342), __byte_perm(x.w, 0u, 0x4140), __byte_perm(x.w, 0u, 0x4342));
+        }
+        for (uint64_t i = 16 * n16 + t0; i < n_ring; i += stride) ring16[i] = ring8[i];
+    }
 }
 
 // surtr_download_blob_async: the four fragment arrays into ONE contiguous device blob in the packed wire format
-// (records and ring entries copied, positions narrowed to float3, ring offsets turned into one length byte per vertex).
+// (records copied, positions narrowed to float3, ring offsets turned into one length byte per vertex; RB = 1: no fragment
+// of the event has more than 256 vertices and the ring entries travel as bytes, RB = 2: copied as they are).
+template <int RB>
 __global__ void __launch_bounds__(256) pack_blob_kernel(const uint4* __restrict__ rec16, uint64_t n_rec16, const float4* __restrict__ verts4,
                                                         const uint32_t* __restrict__ ring_off, uint64_t n_verts,
                                                         const uint16_t* __restrict__ ring, uint64_t n_ring, uint4* __restrict__ o_rec16,
-                                                        float* __restrict__ o_verts3, uint8_t* __restrict__ o_len, uint16_t* __restrict__ o_ring)
+                                                        float* __restrict__ o_verts3, uint8_t* __restrict__ o_len, void* __restrict__ o_ring)
 {
     const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = t0; i < n_rec16; i += stride) o_rec16[i] = rec16[i];
@@ -193,12 +233,29 @@ __global__ void __launch_bounds__(256) pack_blob_kernel(const uint4* __restrict_
         o_verts3[3 * i] = v.x; o_verts3[3 * i + 1] = v.y; o_verts3[3 * i + 2] = v.z;
         o_len[i] = (uint8_t)(ring_off[i + 1] - ring_off[i]);
     }
-    // ring entries: 16 bytes per thread where both sides are aligned (f_ring is a cudaMalloc'd array, the section 256-byte aligned)
-    const uint64_t n8 = n_ring / 8;
-    const uint4* r16 = reinterpret_cast<const uint4*>(ring);
-    uint4* o16 = reinterpret_cast<uint4*>(o_ring);
-    for (uint64_t i = t0; i < n8; i += stride) o16[i] = r16[i];
-    for (uint64_t i = 8 * n8 + t0; i < n_ring; i += stride) o_ring[i] = ring[i];
+    // ring entries: 16 bytes per store where both sides are aligned (f_ring is a cudaMalloc'd array, the section 256-byte aligned)
+    if (RB == 2)
+    {
+        const uint64_t n8 = n_ring / 8;
+        const uint4* r16 = reinterpret_cast<const uint4*>(ring);
+        uint4* o16 = reinterpret_cast<uint4*>(o_ring);
+        uint16_t* o1 = reinterpret_cast<uint16_t*>(o_ring);
+        for (uint64_t i = t0; i < n8; i += stride) o16[i] = r16[i];
+        for (uint64_t i = 8 * n8 + t0; i < n_ring; i += stride) o1[i] = ring[i];
+    }
+    else
+    {
+        const uint64_t n16 = n_ring / 16;
+        const uint4* r16 = reinterpret_cast<const uint4*>(ring);
+        uint4* o16 = reinterpret_cast<uint4*>(o_ring);
+        uint8_t* o1 = reinterpret_cast<uint8_t*>(o_ring);
+        for (uint64_t i = t0; i < n16; i += stride)
+        {
+            const uint4 a = r16[2 * i], b = r16[2 * i + 1];   // the low byte of each 16-bit entry
+            o16[i] = make_uint4(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420), __byte_perm(b.x, b.y, 0x6420), __byte_perm(b.z, b.w, 0x6420));
+        }
+        for (uint64_t i = 16 * n16 + t0; i < n_ring; i += stride) o1[i] = (uint8_t)ring[i];
+    }
 }
 
 // PCIe wire format of the fragments (surtr_download_fragments_packed): float3 positions, one byte of ring length per vertex.
@@ -1294,6 +1351,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 8) assemble_gather_kernel(Asse
         f.cell = pr.y; f.piece = pr.x;
         f.vert_off = (uint32_t)cvb;
         f.n_verts = (uint16_t)cnv;
+        if (!do_mo && cnv > 64) atomicMax(&a.ctl->max_big_verts, (unsigned)cnv);
         if (do_mo)
         {
             f.n_faces = (uint16_t)mo.n_faces;

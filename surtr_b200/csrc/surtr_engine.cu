@@ -135,6 +135,7 @@ struct surtr_ctx
     bool profiled_last = false;
     bool tier1b_enabled = false;  // the 128-slot warp-per-pair tier is launched once an event needed it
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
+    uint32_t last_ring_bytes = 2; // ring entry width of the last event's output blob (surtr_download_blob_async)
     int k3_warps = 0;             // small tier's main launch: 0 = persistent warps + ticket (default); SURTR_K3_WARPS=2: one block of two pairs per two candidates (A/B)
     bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
@@ -524,6 +525,7 @@ int resolve_event(surtr_ctx* ctx)
             ctx->last.n_tier2 = c.n_ovf2;
             ctx->last.n_tier3 = c.n_ovf3;
             ctx->last.n_tier1b = c.n_ovf;
+            ctx->last_ring_bytes = c.max_big_verts <= 256u ? 1u : 2u;   // (small-tier fragments have at most 64 vertices)
             ctx->event_resolved = true;
             return SURTR_OK;
         }
@@ -839,14 +841,15 @@ extern "C"
 static inline uint64_t blob_align(uint64_t x) { return (x + 255ull) & ~255ull; }
 
 int surtr_input_blob_layout(uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring, uint32_t n_cells, uint64_t n_planes,
-                            uint64_t n_cell_verts, uint32_t n_events, surtr_in_layout* out)
+                            uint64_t n_cell_verts, uint32_t n_events, uint32_t ring_entry_bytes, surtr_in_layout* out)
 {
-    if (!out) return SURTR_ERR_INVALID;
+    if (!out || (ring_entry_bytes != 1 && ring_entry_bytes != 2)) return SURTR_ERR_INVALID;
     uint64_t at = 0;
     out->verts3 = at;       at = blob_align(at + 12 * n_piece_verts);
     out->vert_off = at;     at = blob_align(at + 4 * ((uint64_t)n_pieces + 1));
-    out->ring_off = at;     at = blob_align(at + 4 * (n_piece_verts + 1));
-    out->ring = at;         at = blob_align(at + 2 * n_piece_ring);
+    out->ring_base = at;    at = blob_align(at + 4 * ((uint64_t)n_pieces + 1));
+    out->ring_len = at;     at = blob_align(at + n_piece_verts);
+    out->ring = at;         at = blob_align(at + ring_entry_bytes * n_piece_ring);
     out->planes4 = at;      at = blob_align(at + 16 * n_planes);
     out->plane_off = at;    at = blob_align(at + 4 * ((uint64_t)n_cells + 1));
     out->cell_verts3 = at;  at = blob_align(at + 12 * n_cell_verts);
@@ -858,23 +861,25 @@ int surtr_input_blob_layout(uint32_t n_pieces, uint64_t n_piece_verts, uint64_t 
 }
 
 int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint64_t n_piece_verts, uint64_t n_piece_ring,
-                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events)
+                      uint32_t n_cells, uint64_t n_planes, uint64_t n_cell_verts, uint32_t n_events, uint32_t ring_entry_bytes)
 {
     if (!ctx) return SURTR_ERR_INVALID;
     if (!blob) return fail(ctx, SURTR_ERR_INVALID, "NULL blob");
     surtr_in_layout L;
-    surtr_input_blob_layout(n_pieces, n_piece_verts, n_piece_ring, n_cells, n_planes, n_cell_verts, n_events, &L);
+    if (surtr_input_blob_layout(n_pieces, n_piece_verts, n_piece_ring, n_cells, n_planes, n_cell_verts, n_events, ring_entry_bytes, &L))
+        return fail(ctx, SURTR_ERR_INVALID, "ring_entry_bytes must be 1 or 2");
     const unsigned char* h = static_cast<const unsigned char*>(blob);
     const uint32_t* vert_off = reinterpret_cast<const uint32_t*>(h + L.vert_off);
-    const uint32_t* ring_off = reinterpret_cast<const uint32_t*>(h + L.ring_off);
+    const uint32_t* ring_base = reinterpret_cast<const uint32_t*>(h + L.ring_base);
     const uint32_t* plane_off = reinterpret_cast<const uint32_t*>(h + L.plane_off);
     const uint32_t* cvert_off = reinterpret_cast<const uint32_t*>(h + L.cvert_off);
-    // everything is validated against the host copy BEFORE the context is touched
+    // everything is validated against the host copy BEFORE the context is touched (per piece, not per vertex: a ring
+    // length that contradicts its piece's ring range is caught by the clipper, which reports the pair as failed)
     std::vector<uint32_t> lp, lc;
     if (!make_layout(n_events ? reinterpret_cast<const uint32_t*>(h + L.ev_piece_off) : nullptr, n_events, n_pieces, lp) ||
         !make_layout(n_events ? reinterpret_cast<const uint32_t*>(h + L.ev_cell_off) : nullptr, n_events, n_cells, lc))
         return fail(ctx, SURTR_ERR_INVALID, "event offsets must start at 0, be non-decreasing and end at the piece / cell count");
-    if (vert_off[n_pieces] != n_piece_verts || (n_piece_verts && ring_off[n_piece_verts] != n_piece_ring) ||
+    if (vert_off[n_pieces] != n_piece_verts || ring_base[0] != 0u || ring_base[n_pieces] != n_piece_ring ||
         plane_off[n_cells] != n_planes || (n_cell_verts && cvert_off[n_cells] != n_cell_verts))
         return fail(ctx, SURTR_ERR_INVALID, "blob offsets do not match the stated sizes");
     uint32_t max_verts = 0;
@@ -882,22 +887,30 @@ int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint6
     {
         if (vert_off[i + 1] < vert_off[i] || vert_off[i + 1] - vert_off[i] > 65520u)
             return fail(ctx, SURTR_ERR_INVALID, "vert_off must be non-decreasing and a piece may have at most 65520 vertices");
+        if (ring_base[i + 1] < ring_base[i]) return fail(ctx, SURTR_ERR_INVALID, "ring_base must be non-decreasing");
         max_verts = std::max(max_verts, vert_off[i + 1] - vert_off[i]);
     }
+    if (ring_entry_bytes == 1 && max_verts > 256u) return fail(ctx, SURTR_ERR_INVALID, "one-byte ring entries need pieces of at most 256 vertices");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->in_blob.reserve(std::max<uint64_t>(L.total, 256)));
     CK(ctx->p_verts.reserve(std::max<size_t>(16 * n_piece_verts, 16)));
+    CK(ctx->p_ring_off.reserve(4 * (n_piece_verts + 1)));
+    if (ring_entry_bytes == 1) CK(ctx->p_ring.reserve(std::max<size_t>(2 * n_piece_ring, 16)));
     if (n_cell_verts) CK(ctx->c_verts.reserve(16 * n_cell_verts));
-    // ONE host -> device copy; the float3 streams are widened to the resident float4 arrays, every other array is used in place
+    // ONE host -> device copy, then one kernel that widens / rebuilds the compact sections into the resident arrays; the
+    // remaining index arrays are used in place
     CK(cudaMemcpyAsync(ctx->in_blob.p, blob, L.total, cudaMemcpyHostToDevice, ctx->stream));
     unsigned char* d = ctx->in_blob.as<unsigned char>();
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n_piece_verts + n_cell_verts + 255) / 256 + 1, (uint64_t)ctx->num_sm * 8);
-    widen3x2_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + L.verts3), ctx->p_verts.as<float4>(), n_piece_verts,
-                                                    reinterpret_cast<const float*>(d + L.cell_verts3), ctx->c_verts.as<float4>(), n_cell_verts);
+    if (ring_entry_bytes == 2) ctx->p_ring.set_view(d + L.ring, 2 * n_piece_ring);
+    const uint64_t work = std::max<uint64_t>(n_piece_verts + n_cell_verts, std::max<uint64_t>((uint64_t)n_pieces * 32, n_piece_ring / 16));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((work + 255) / 256 + 1, (uint64_t)ctx->num_sm * 8);
+    auto kern = ring_entry_bytes == 1 ? expand_blob_kernel<1> : expand_blob_kernel<2>;
+    kern<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + L.verts3), ctx->p_verts.as<float4>(), n_piece_verts,
+                                          reinterpret_cast<const float*>(d + L.cell_verts3), ctx->c_verts.as<float4>(), n_cell_verts,
+                                          reinterpret_cast<const uint32_t*>(d + L.vert_off), reinterpret_cast<const uint32_t*>(d + L.ring_base),
+                                          d + L.ring_len, n_pieces, ctx->p_ring_off.as<uint32_t>(), d + L.ring, ctx->p_ring.as<uint16_t>(), n_piece_ring);
     CK(cudaGetLastError());
     ctx->p_vert_off.set_view(d + L.vert_off, 4 * ((size_t)n_pieces + 1));
-    ctx->p_ring_off.set_view(d + L.ring_off, 4 * (n_piece_verts + 1));
-    ctx->p_ring.set_view(d + L.ring, 2 * n_piece_ring);
     ctx->c_planes.set_view(d + L.planes4, 16 * n_planes);
     ctx->c_plane_off.set_view(d + L.plane_off, 4 * ((size_t)n_cells + 1));
     ctx->c_vert_off.set_view(d + L.cvert_off, 4 * ((size_t)n_cells + 1));
@@ -931,7 +944,8 @@ int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity
     out->fragments = at; at = blob_align(at + sizeof(surtr_fragment) * c.n_fragments);
     out->verts3 = at;    at = blob_align(at + 12 * c.n_verts);
     out->ring_len = at;  at = blob_align(at + c.n_verts);
-    out->ring = at;      at = blob_align(at + 2 * c.n_ring);
+    out->ring_entry_bytes = ctx->last_ring_bytes;   // 1 when no fragment of the event has more than 256 vertices
+    out->ring = at;      at = blob_align(at + out->ring_entry_bytes * c.n_ring);
     out->total = at;
     if (!host_blob || capacity < at) return fail(ctx, SURTR_ERR_INVALID, "host blob too small: " + std::to_string(at) + " bytes needed");
     if (!at) return SURTR_OK;
@@ -940,10 +954,11 @@ int surtr_download_blob_async(surtr_ctx* ctx, void* host_blob, uint64_t capacity
     unsigned char* d = ctx->out_blob.as<unsigned char>();
     const uint64_t work = std::max<uint64_t>(c.n_verts, std::max<uint64_t>(c.n_fragments * 4, c.n_ring / 8));
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((work + 255) / 256, (uint64_t)ctx->num_sm * 8));
-    pack_blob_kernel<<<blocks, 256, 0, cs>>>(ctx->f_rec.as<uint4>(), c.n_fragments * (sizeof(surtr_fragment) / 16), ctx->f_verts.as<float4>(),
-                                            ctx->f_ring_off.as<uint32_t>(), c.n_verts, ctx->f_ring.as<uint16_t>(), c.n_ring,
-                                            reinterpret_cast<uint4*>(d + out->fragments), reinterpret_cast<float*>(d + out->verts3),
-                                            d + out->ring_len, reinterpret_cast<uint16_t*>(d + out->ring));
+    auto kern = out->ring_entry_bytes == 1 ? pack_blob_kernel<1> : pack_blob_kernel<2>;
+    kern<<<blocks, 256, 0, cs>>>(ctx->f_rec.as<uint4>(), c.n_fragments * (sizeof(surtr_fragment) / 16), ctx->f_verts.as<float4>(),
+                                 ctx->f_ring_off.as<uint32_t>(), c.n_verts, ctx->f_ring.as<uint16_t>(), c.n_ring,
+                                 reinterpret_cast<uint4*>(d + out->fragments), reinterpret_cast<float*>(d + out->verts3),
+                                 d + out->ring_len, d + out->ring);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host_blob, d, at, cudaMemcpyDefault, cs));   // ONE copy (the destination may also be device memory: the multi-GPU gather packs into a device tensor)
     if (ctx->copy_stream)

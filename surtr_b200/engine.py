@@ -50,12 +50,13 @@ class Counts(C.Structure):
 
 
 class InLayout(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("verts3", "vert_off", "ring_off", "ring", "planes4", "plane_off", "cell_verts3",
+    _fields_ = [(n, C.c_uint64) for n in ("verts3", "vert_off", "ring_base", "ring_len", "ring", "planes4", "plane_off", "cell_verts3",
                                           "cvert_off", "ev_piece_off", "ev_cell_off", "total")]
 
 
 class OutLayout(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("fragments", "verts3", "ring_len", "ring", "total", "n_fragments", "n_verts", "n_ring")]
+    _fields_ = [(n, C.c_uint64) for n in ("fragments", "verts3", "ring_len", "ring", "total", "n_fragments", "n_verts", "n_ring",
+                                          "ring_entry_bytes")]
 
 
 class DeviceView(C.Structure):
@@ -107,8 +108,8 @@ def load_library():
     lib.surtr_last_event_phases.argtypes = [vp, vp]
     lib.surtr_failed_pairs.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     u64 = C.c_uint64
-    lib.surtr_input_blob_layout.argtypes = [u32, u64, u64, u32, u64, u64, u32, C.POINTER(InLayout)]
-    lib.surtr_upload_blob.argtypes = [vp, vp, u32, u64, u64, u32, u64, u64, u32]
+    lib.surtr_input_blob_layout.argtypes = [u32, u64, u64, u32, u64, u64, u32, u32, C.POINTER(InLayout)]
+    lib.surtr_upload_blob.argtypes = [vp, vp, u32, u64, u64, u32, u64, u64, u32, u32]
     lib.surtr_download_blob_async.argtypes = [vp, vp, u64, C.POINTER(OutLayout)]
     lib.surtr_kdop_calc_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
     _lib = lib
@@ -324,19 +325,25 @@ class FractureContext:
 
     # ---- one-copy transfers: one blob per direction (include/surtr_b200.h) ----
     @staticmethod
-    def input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events) -> InLayout:
+    def input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events, ring_entry_bytes) -> InLayout:
         L = InLayout()
-        load_library().surtr_input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events, C.byref(L))
+        rc = load_library().surtr_input_blob_layout(n_pieces, n_pverts, n_pring, n_cells, n_planes, n_cverts, n_events, ring_entry_bytes, C.byref(L))
+        if rc:
+            raise SurtrError(rc, "surtr_input_blob_layout: ring_entry_bytes must be 1 or 2")
         return L
 
     @staticmethod
     def fill_input_blob(buf: np.ndarray, pieces, cells, ev_piece_off=None, ev_cell_off=None, bounded=True):
-        """Lays the arrays of one batch out in `buf` (uint8, e.g. a view of pinned memory; None = only size it).
+        """Lays the arrays of one batch out in `buf` (uint8, e.g. a view of pinned memory; None = only size it) in the
+        compact wire format of surtr_upload_blob: float3 positions, one ring-length byte per vertex, the first ring entry
+        of every piece, ring entries as bytes when no piece has more than 256 vertices.
         pieces / cells: objects with verts, vert_off, ring_off, ring / planes, plane_off, verts, vert_off.
         Returns (sizes tuple for upload_blob, total bytes)."""
         n_ev = 0 if ev_piece_off is None else len(ev_piece_off) - 1
         n_cv = len(cells.verts) if bounded else 0
-        sizes = (len(pieces.vert_off) - 1, len(pieces.verts), len(pieces.ring), len(cells.plane_off) - 1, len(cells.planes), n_cv, n_ev)
+        vo = np.asarray(pieces.vert_off, np.int64)
+        rb = 1 if len(vo) < 2 or int(np.diff(vo).max()) <= 256 else 2
+        sizes = (len(pieces.vert_off) - 1, len(pieces.verts), len(pieces.ring), len(cells.plane_off) - 1, len(cells.planes), n_cv, n_ev, rb)
         L = FractureContext.input_blob_layout(*sizes)
         if buf is None:
             return sizes, int(L.total)
@@ -345,10 +352,12 @@ class FractureContext:
             a = np.ascontiguousarray(a, dt).reshape(-1).view(np.uint8)
             buf[off:off + a.size] = a
 
+        ro = np.asarray(pieces.ring_off, np.int64)
         put(L.verts3, np.asarray(pieces.verts)[:, :3], np.float32)
         put(L.vert_off, pieces.vert_off, np.uint32)
-        put(L.ring_off, pieces.ring_off, np.uint32)
-        put(L.ring, pieces.ring, np.uint16)
+        put(L.ring_base, ro[vo], np.uint32)
+        put(L.ring_len, np.diff(ro), np.uint8)
+        put(L.ring, pieces.ring, np.uint8 if rb == 1 else np.uint16)
         put(L.planes4, cells.planes, np.float32)
         put(L.plane_off, cells.plane_off, np.uint32)
         if n_cv:
@@ -374,7 +383,10 @@ class FractureContext:
         rec = np.frombuffer(buf[L.fragments:L.fragments + 64 * nf].tobytes(), dtype=FRAGMENT_DTYPE)
         v3 = np.frombuffer(buf[L.verts3:L.verts3 + 12 * nv].tobytes(), dtype=np.float32).reshape(nv, 3)
         rl = np.frombuffer(buf[L.ring_len:L.ring_len + nv].tobytes(), dtype=np.uint8)
-        ring = np.frombuffer(buf[L.ring:L.ring + 2 * nr].tobytes(), dtype=np.uint16)
+        if int(L.ring_entry_bytes) == 1:
+            ring = np.frombuffer(buf[L.ring:L.ring + nr].tobytes(), dtype=np.uint8).astype(np.uint16)
+        else:
+            ring = np.frombuffer(buf[L.ring:L.ring + 2 * nr].tobytes(), dtype=np.uint16)
         verts = np.zeros((nv, 4), np.float32)
         verts[:, :3] = v3
         ring_off = np.concatenate([[0], np.cumsum(rl, dtype=np.uint64)]).astype(np.uint32)

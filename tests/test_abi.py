@@ -182,19 +182,23 @@ int main(int argc, char** argv)
         surtr_out_layout O;
         unsigned char *in, *out;
         unsigned long long npv = nbytes[0] / 16, npr = nbytes[3] / 2, npl = nbytes[4] / 16, ncv = nbytes[6] / 16, k;
-        CK(surtr_input_blob_layout(n_pieces, npv, npr, n_cells, npl, ncv, 0, &L));
+        CK(surtr_input_blob_layout(n_pieces, npv, npr, n_cells, npl, ncv, 0, 1, &L));   /* pieces of <= 256 vertices: ring entries as bytes */
         in = calloc(1, L.total);
         for (k = 0; k < npv; k++) memcpy(in + L.verts3 + 12 * k, (float*)arr[0] + 4 * k, 12);
-        memcpy(in + L.vert_off, arr[1], nbytes[1]); memcpy(in + L.ring_off, arr[2], nbytes[2]); memcpy(in + L.ring, arr[3], nbytes[3]);
+        memcpy(in + L.vert_off, arr[1], nbytes[1]);
+        for (k = 0; k <= n_pieces; k++) ((unsigned*)(in + L.ring_base))[k] = ((unsigned*)arr[2])[((unsigned*)arr[1])[k]];
+        for (k = 0; k < npv; k++) in[L.ring_len + k] = (unsigned char)(((unsigned*)arr[2])[k + 1] - ((unsigned*)arr[2])[k]);
+        for (k = 0; k < npr; k++) in[L.ring + k] = (unsigned char)((unsigned short*)arr[3])[k];
         memcpy(in + L.planes4, arr[4], nbytes[4]); memcpy(in + L.plane_off, arr[5], nbytes[5]);
         for (k = 0; k < ncv; k++) memcpy(in + L.cell_verts3 + 12 * k, (float*)arr[6] + 4 * k, 12);
         memcpy(in + L.cvert_off, arr[7], nbytes[7]);
-        CK(surtr_upload_blob(ctx, in, n_pieces, npv, npr, n_cells, npl, ncv, 0));
+        CK(surtr_upload_blob(ctx, in, n_pieces, npv, npr, n_cells, npl, ncv, 0, 1));
         CK(surtr_fracture_event(ctx));
         out = malloc(64 * (size_t)n + 13 * c.n_verts + 2 * c.n_ring + 1024);
         CK(surtr_download_blob_async(ctx, out, 64 * (unsigned long long)n + 13 * c.n_verts + 2 * c.n_ring + 1024, &O));
         CK(surtr_sync(ctx));
-        if (O.n_fragments != n || memcmp(out + O.fragments, rec, sizeof(surtr_fragment) * n) || memcmp(out + O.ring, ring, 2 * c.n_ring)) { puts("blob differs"); return 6; }
+        if (O.n_fragments != n || O.ring_entry_bytes != 1 || memcmp(out + O.fragments, rec, sizeof(surtr_fragment) * n)) { puts("blob differs"); return 6; }
+        for (k = 0; k < c.n_ring; k++) if (out[O.ring + k] != ring[k]) { puts("blob rings differ"); return 6; }
         for (k = 0; k < c.n_verts; k++)
             if (memcmp(out + O.verts3 + 12 * k, verts + 4 * k, 12) || out[O.ring_len + k] != ring_off[k + 1] - ring_off[k]) { puts("blob geometry differs"); return 7; }
     }

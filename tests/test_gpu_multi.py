@@ -38,11 +38,11 @@ def _worker(rank, world, port, q):
         ctx.fracture_event()
         c = ctx.counts()
         cap = 64 * c.n_fragments + 13 * c.n_verts + 2 * c.n_ring + 4 * 256
-        blob = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
-        hdr = 64                                         # first 64 bytes: the layout, so that rank 0 can unpack the slice
+        blob = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
+        hdr = 256                                        # first bytes: the layout, so that rank 0 can unpack the slice
         L = ctx.download_blob_into_async(blob.data_ptr() + hdr, cap)
         ctx.sync()
-        lay = np.array([L.fragments, L.verts3, L.ring_len, L.ring, L.total, L.n_fragments, L.n_verts, L.n_ring], np.uint64)
+        lay = np.array([L.fragments, L.verts3, L.ring_len, L.ring, L.total, L.n_fragments, L.n_verts, L.n_ring, L.ring_entry_bytes], np.uint64)
         blob[:hdr].copy_(torch.from_numpy(lay.view(np.uint8).copy()))
         blob = blob[:hdr + int(L.total)]
         got = sharding.gather_blobs(blob, 0)
@@ -54,7 +54,7 @@ def _worker(rank, world, port, q):
             per_rank = []
             for r in range(world):
                 sl = host[off[r]:off[r + 1]]
-                lay = sl[:hdr].view(np.uint64)
+                lay = sl[:hdr].view(np.uint64)[:9]
                 LL = OutLayout(*[int(x) for x in lay])
                 per_rank.append(FractureContext.unpack_output_blob(sl[hdr:], LL))
             # event e is the k-th event of rank r: its fragments are the k-th cell range of that rank's batch

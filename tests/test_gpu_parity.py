@@ -570,6 +570,30 @@ def test_one_copy_blob_transfers(ctx):
         # too small a host blob is refused with the needed size reported
         with pytest.raises(Exception):
             ctx.download_blob_into_async(out.ctypes.data, 16)
+    # a piece and fragments of more than 256 vertices (the bunny mesh in the global tier): two-byte ring entries both ways
+    d = np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz"))
+    mesh = load_polyset(d, "mesh_")
+    mcells = common.PolySet(d["cell_verts"], d["cell_vert_off"], None, None)
+    mcells.planes, mcells.plane_off = d["planes"], d["plane_off"]
+    ctx.upload_pieces(mesh.verts, mesh.vert_off, mesh.ring_off, mesh.ring)
+    ctx.upload_cells(mcells.planes, mcells.plane_off, mcells.verts, mcells.vert_off)
+    ctx.fracture_event()
+    ref = ctx.download()
+    sizes, total = FractureContext.fill_input_blob(None, mesh, mcells)
+    assert sizes[-1] == 2
+    buf = np.zeros(total, np.uint8)
+    FractureContext.fill_input_blob(buf, mesh, mcells)
+    ctx.upload_blob_ptr(buf.ctypes.data, sizes)
+    ctx.fracture_event()
+    c = ctx.counts()
+    out = np.zeros(64 * c.n_fragments + 13 * c.n_verts + 2 * c.n_ring + 4 * 256, np.uint8)
+    L = ctx.download_blob_into_async(out.ctypes.data, len(out))
+    ctx.sync()
+    assert int(L.ring_entry_bytes) == 2 and int(ref.rec["n_verts"].max()) > 256
+    got = FractureContext.unpack_output_blob(out, L)
+    assert got.rec.tobytes() == ref.rec.tobytes() and np.array_equal(bits(got.verts), bits(ref.verts))
+    assert np.array_equal(got.ring_off, ref.ring_off) and np.array_equal(got.ring, ref.ring)
+
     want = P.apply_fracture(psets[0], csets[0].planes, csets[0].plane_off)
     again = common.run_gpu(ctx, psets[0], csets[0])          # plain upload over the blob's views
     common.assert_fragments_equal(again, want)

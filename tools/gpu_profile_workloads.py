@@ -7,7 +7,7 @@ between cudaProfilerStart / cudaProfilerStop.  config4 = one batch of 64 indepen
 bench.py's end-to-end loop; config3 = the 10 000 x 256 event; config2 = unit cube x 4096 cells; mesh = the 2503-vertex
 bunny mesh x 32 cells (global tier).  Prints the event's counters and the algorithmic bytes of its K3 launch.
 BLOB=1: the profiled events go through the one-copy wire format (surtr_upload_blob -> event -> surtr_download_blob_async,
-pinned host buffers), so widen3x2_kernel and pack_blob_kernel are in the capture too, and the line carries the
+pinned host buffers), so expand_blob_kernel and pack_blob_kernel are in the capture too, and the line carries the
 algorithmic bytes of EVERY kernel (the formulas of DESIGN.md section 4) for the per-kernel roofline table."""
 import json, os, sys
 import numpy as np
@@ -73,14 +73,14 @@ if blob:
     S, F, NV, NE = int(c.n_candidates), int(c.n_fragments), int(c.n_verts), int(c.n_ring)
     words = int(c.n_pairs) // 32
     per_kernel = {   # compulsory bytes per launch (read + write), DESIGN.md section 4
-        "widen3x2_kernel": 28 * (nVp + nVc),
+        "expand_blob_kernel": 28 * (nVp + nVc) + 5 * nVp + 8 * nP + 3 * len(pieces.ring),
         "kdop_extents_kernel": 16 * (nVp + nVc) + 8 * k * (nP + nC),
         "broadphase_mask_kernel": 8 * k * (nP + nC) + 4 * words,
         "compact_pairs_kernel": 4 * words + 8 * S,
         "clip_fast_kernel": int(alg),
         "assemble_scan_kernel": 16 * S + 16 * S + 4 * F,
         "assemble_gather_kernel": F * 64 + NV * (16 + 2) + NE + NV * (16 + 4) + 2 * NE,
-        "pack_blob_kernel": F * 64 * 2 + NV * (16 + 4 + 12 + 1) + NE * 4,
+        "pack_blob_kernel": F * 64 * 2 + NV * (16 + 4 + 12 + 1) + NE * 3,
     }
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
