@@ -70,7 +70,11 @@ struct CandRec   // result of K3 for one candidate pair
 };
 
 // ---------------------------------------------------------------------------------------------- K1
-template <int K>
+// L lanes per object (pieces then cells, one launch for both): the objects of the BASELINE configs have 8-60 vertices,
+// and the cost of an object is the butterfly over its 2K extents (log2 L steps), not its vertex stream -- L = 8 does a
+// quarter of the shuffles of a full warp per object and keeps four objects' loads in flight per warp; L = 32 is used
+// when a piece is large (the host picks: max piece vertices > 128).
+template <int K, int L>
 __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const uint32_t* __restrict__ p_vert_off,
                                     uint32_t n_pieces, float* __restrict__ ext_p, const float4* __restrict__ c_verts,
                                     const uint32_t* __restrict__ c_vert_off, uint32_t n_cells, float* __restrict__ ext_c,
@@ -78,12 +82,15 @@ __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const ui
 {
     pdl_launch_dependents();
     pdl_wait();
-    // one warp per object; objects = the pieces followed by the cells (one launch for both)
-    const int lane = threadIdx.x & 31;
+    constexpr uint32_t PER_WARP = 32 / L;
+    const int lane = threadIdx.x & 31, sl = lane % L;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t obj = warp; obj < n_pieces + n_cells; obj += nwarps)
+    const uint32_t n_obj = n_pieces + n_cells;
+    for (uint32_t obj0 = warp * PER_WARP; obj0 < n_obj; obj0 += nwarps * PER_WARP)   // (warp-uniform trip count: the shuffles use the full mask)
     {
+        const uint32_t obj = obj0 + lane / L;
+        const bool have = obj < n_obj;
         const bool is_cell = obj >= n_pieces;
         const uint32_t o = is_cell ? obj - n_pieces : obj;
         const float4* verts = is_cell ? c_verts : p_verts;
@@ -92,15 +99,11 @@ __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const ui
         float mn[K], mx[K];
 #pragma unroll
         for (int d = 0; d < K; d++) { mn[d] = 3.402823466e+38f; mx[d] = -3.402823466e+38f; }
-        if (is_cell && cells_unbounded)
-        {
-#pragma unroll
-            for (int d = 0; d < K; d++) { mn[d] = -__int_as_float(0x7f800000); mx[d] = __int_as_float(0x7f800000); }
-        }
-        else
+        const bool unbounded = is_cell && cells_unbounded;
+        if (have && !unbounded)
         {
             const uint32_t v0 = vert_off[o], v1 = vert_off[o + 1];
-            for (uint32_t v = v0 + lane; v < v1; v += 32)
+            for (uint32_t v = v0 + sl; v < v1; v += L)
             {
                 const float4 p = __ldg(verts + v);   // coalesced float4 stream
 #pragma unroll
@@ -111,22 +114,28 @@ __global__ void kdop_extents_kernel(const float4* __restrict__ p_verts, const ui
                     mx[d] = fmaxf(mx[d], t);
                 }
             }
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1)
-#pragma unroll
-                for (int d = 0; d < K; d++)
-                {
-                    mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], s));
-                    mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], s));
-                }
         }
-        if (lane == 0)
-        {
+#pragma unroll
+        for (int s = L / 2; s > 0; s >>= 1)
 #pragma unroll
             for (int d = 0; d < K; d++)
             {
-                ext[(size_t)o * 2 * K + 2 * d] = mn[d];
-                ext[(size_t)o * 2 * K + 2 * d + 1] = mx[d];
+                mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], s));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], s));
+            }
+        if (unbounded)
+        {
+#pragma unroll
+            for (int d = 0; d < K; d++) { mn[d] = -__int_as_float(0x7f800000); mx[d] = __int_as_float(0x7f800000); }
+        }
+        if (have)
+        {
+            // the L lanes of the object write its 2K extents together
+#pragma unroll
+            for (int d = 0; d < K; d++)
+            {
+                if (sl == (2 * d) % L) ext[(size_t)o * 2 * K + 2 * d] = mn[d];
+                if (sl == (2 * d + 1) % L) ext[(size_t)o * 2 * K + 2 * d + 1] = mx[d];
             }
         }
     }

@@ -273,10 +273,17 @@ void launch_extents(surtr_ctx* ctx)
     const uint64_t n_obj = (uint64_t)ctx->n_pieces + ctx->n_cells;
     if (!n_obj) return;
     const int threads = 256;
-    const int blocks = (int)std::min<uint64_t>((n_obj * 32 + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
-    launch_pdl(kdop_extents_kernel<K>, dim3(blocks), dim3(threads), 0, ctx->stream, ctx->p_verts.as<float4>(),
-               ctx->p_vert_off.as<uint32_t>(), ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
-               ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(), ctx->cells_bounded ? 0 : 1);
+    const bool wide = ctx->max_piece_verts > 128;   // a full warp per object only when a piece is large (kernels.cuh)
+    const uint64_t lanes = wide ? 32 : 8;
+    const int blocks = (int)std::min<uint64_t>((n_obj * lanes + threads - 1) / threads, (uint64_t)ctx->num_sm * 8);
+    if (wide)
+        launch_pdl(kdop_extents_kernel<K, 32>, dim3(blocks), dim3(threads), 0, ctx->stream, ctx->p_verts.as<float4>(),
+                   ctx->p_vert_off.as<uint32_t>(), ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
+                   ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(), ctx->cells_bounded ? 0 : 1);
+    else
+        launch_pdl(kdop_extents_kernel<K, 8>, dim3(blocks), dim3(threads), 0, ctx->stream, ctx->p_verts.as<float4>(),
+                   ctx->p_vert_off.as<uint32_t>(), ctx->n_pieces, ctx->ext_p.as<float>(), ctx->c_verts.as<float4>(),
+                   ctx->c_vert_off.as<uint32_t>(), ctx->n_cells, ctx->ext_c.as<float>(), ctx->cells_bounded ? 0 : 1);
     ctx->launches++;
 }
 

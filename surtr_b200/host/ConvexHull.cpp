@@ -1,3 +1,4 @@
+#include <cstring>
 #include "ConvexHull.h"
 
 #include "Engine.h"
@@ -179,6 +180,20 @@ bool ConvexHull::SeedTetrahedron()
 		if (vol(i4) < vol(i)) i4 = i;
 	m_used[i1] = m_used[i2] = m_used[i3] = m_used[i4] = 1;
 	m_usedCnt = 4;
+	if (m_seedOnly)
+	{
+		// classes of the four seed points among themselves (all that the edge keys of the four triangles can see)
+		const int seed[4] = { i1, i2, i3, i4 };
+		char buf[4][192];
+		for (int k = 0; k < 4; k++)
+		{
+			std::snprintf(buf[k], sizeof buf[k], "%f%f%f", m_pos[seed[k]].x, m_pos[seed[k]].y, m_pos[seed[k]].z);
+			uint32_t cls = (uint32_t)k;
+			for (int j = 0; j < k; j++)
+				if (std::strcmp(buf[j], buf[k]) == 0) { cls = m_printClass[seed[j]]; break; }
+			m_printClass[seed[k]] = cls;
+		}
+	}
 	AddTriangle(i1, i2, i3, i4);
 	AddTriangle(i1, i2, i4, i3);
 	AddTriangle(i1, i3, i4, i2);
@@ -190,6 +205,19 @@ void ConvexHull::Build(uint32_t limitCnt)
 {
 	const size_t n = m_pos.size();
 	m_used.assign(n, 0);
+	if (limitCnt != 0 && limitCnt <= 4)
+	{
+		// A hull limited to four points is its seed tetrahedron (the greedy loop below never runs): the refit of every
+		// piece after every fracture (Surtr::Refitting, RefittingPointLimit = 4, Surtr.cpp:2405-2413) takes this path.
+		// No point classes over the whole cloud and no outside volumes: the four faces, their winding and their order
+		// depend on the four scans of SeedTetrahedron alone.  Classes are assigned among the four seed points only (the
+		// edge table keys them), found by a first pass without edges.
+		m_printClass.assign(n, 0);
+		m_valueClass.assign(n, 0);
+		m_seedOnly = true;
+		SeedTetrahedron();
+		return;
+	}
 	m_outside.assign(n, 0.0f);
 	// point classes: exact coordinates (operator== of the reference's vertices) and six-decimal prints (its edge keys)
 	m_printClass.resize(n);

@@ -97,6 +97,7 @@ private:
 	std::unordered_map<uint64_t, int> m_rimOf;  // edge key -> index into m_rims
 	std::vector<int> m_lit, m_fresh;            // triangles the last absorbed point saw / added
 	uint32_t m_usedCnt = 0;
+	bool m_seedOnly = false;      // limitCnt <= 4: the hull is its seed tetrahedron, nothing else is computed
 };
 
 // Surtr::GenerateICHNormal (Surtr.cpp:1961-1982): normalised (v1-v0) x (v2-v0) of every hull face, list order.

@@ -1,3 +1,5 @@
+#include <chrono>
+#include <memory>
 #include "Engine.h"
 
 #include <algorithm>
@@ -274,9 +276,27 @@ void place_pattern(const FlatPattern& pattern, const Vector3& scale, const Vecto
 	check(surtr_place_pattern(c, s3, t3, 1), "surtr_place_pattern");
 }
 
+namespace
+{
+// SURTR_TRACE=1: wall time of the three legs of an event (stderr), next to the orchestration phases of Fracture.cpp
+struct Leg
+{
+	const char* name;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	explicit Leg(const char* n) : name(n) {}
+	~Leg()
+	{
+		static const bool on = std::getenv("SURTR_TRACE") != nullptr;
+		if (on)
+			std::fprintf(stderr, "[surtr]       %-22s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+} // namespace
+
 void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry, bool upload_cells)
 {
 	surtr_ctx* c = context();
+	std::unique_ptr<Leg> leg(new Leg("upload"));
 	check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
 							  pieces.count(), pieces.ev_off.empty() ? nullptr : pieces.ev_off.data(),
 							  pieces.ev_off.empty() ? 0u : (uint32_t)pieces.ev_off.size() - 1), "surtr_upload_pieces");
@@ -285,9 +305,11 @@ void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, 
 								 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(),
 								 cells.ev_off.empty() ? nullptr : cells.ev_off.data(),
 								 cells.ev_off.empty() ? 0u : (uint32_t)cells.ev_off.size() - 1), "surtr_upload_cells");
+	leg.reset(new Leg("launch + wait"));
 	check(surtr_fracture_event(c), "surtr_fracture_event");
 	surtr_counts n;
 	check(surtr_event_counts(c, &n), "surtr_event_counts");
+	leg.reset(new Leg("download"));
 	static const bool trace = std::getenv("SURTR_TRACE") != nullptr;
 	if (trace)
 	{

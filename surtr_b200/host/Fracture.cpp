@@ -268,13 +268,16 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	if (n_in)
 	{
 		detail::FlatPolys pieces;
-		for (const int c : inside)
-			pieces.add(targetPieceVec[c]->Convex);
-		if (source.polys)
-			for (const VMACH::Polygon3D& cell : *source.polys)
-				cells.add(cell);
-		else
-			detail::place_pattern(*source.pattern, source.scale, source.translate);
+		{
+			Phase ph("  pack convex + cells");
+			for (const int c : inside)
+				pieces.add(targetPieceVec[c]->Convex);
+			if (source.polys)
+				for (const VMACH::Polygon3D& cell : *source.polys)
+					cells.add(cell);
+			else
+				detail::place_pattern(*source.pattern, source.scale, source.translate);
+		}
 		{
 			Phase ph("  convex event");
 			detail::run_event(pieces, cells, fr, true, source.polys != nullptr);
@@ -286,8 +289,11 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 			// cells.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
 			// its convex and its mesh fragment exist (:1466-1472).
 			detail::FlatPolys meshes;
-			for (const int c : inside)
-				meshes.add(targetPieceVec[c]->Mesh);
+			{
+				Phase ph2("    pack meshes");
+				for (const int c : inside)
+					meshes.add(targetPieceVec[c]->Mesh);
+			}
 			detail::run_event(meshes, cells, mfr, true, false);
 		}
 	}

@@ -574,7 +574,7 @@ def test_one_copy_blob_transfers(ctx):
     d = np.load(os.path.join(GOLDEN, "bunny_mesh_x32.npz"))
     mesh = load_polyset(d, "mesh_")
     mcells = common.PolySet(d["cell_verts"], d["cell_vert_off"], None, None)
-    mcells.planes, mcells.plane_off = d["planes"], d["plane_off"]
+    mcells.planes, mcells.poly_face_off = d["planes"], d["plane_off"]
     ctx.upload_pieces(mesh.verts, mesh.vert_off, mesh.ring_off, mesh.ring)
     ctx.upload_cells(mcells.planes, mcells.plane_off, mcells.verts, mcells.vert_off)
     ctx.fracture_event()
