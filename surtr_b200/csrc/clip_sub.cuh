@@ -914,10 +914,16 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
             float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
             en = sp.en[en & 1023u];
             at = (int)(en >> 10);
+            // Second moments (no reference arithmetic to match: PhysX is absent, DESIGN.md section 6 -- fused multiply-adds
+            // are fine here, unlike in dV and the first moments).  Products of the fan's fixed corner p0 are formed once per
+            // face, those of p1 are last triangle's p2 products.
+            const float a0 = p0x * p0x, a1 = p0y * p0y, a2 = p0z * p0z, a3 = p0x * p0y, a4 = p0x * p0z, a5 = p0y * p0z;
+            float b0 = p1x * p1x, b1 = p1y * p1y, b2 = p1z * p1z, b3 = p1x * p1y, b4 = p1x * p1z, b5 = p1y * p1z;
             int guard = 0;
             while (at != v && guard++ < 64)
             {
                 const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
+                const float c0 = p2x * p2x, c1 = p2y * p2y, c2 = p2z * p2z, c3 = p2x * p2y, c4 = p2x * p2z, c5 = p2y * p2z;
                 if (w >= 0 && w < 64 && w + base < 128)
                 {
                     float cx, cy, cz;
@@ -928,17 +934,18 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
                     const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
                     sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
                     // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
-                    cov[0] += dV * (sx * sx + p0x * p0x + p1x * p1x + p2x * p2x);
-                    cov[1] += dV * (sy * sy + p0y * p0y + p1y * p1y + p2y * p2y);
-                    cov[2] += dV * (sz * sz + p0z * p0z + p1z * p1z + p2z * p2z);
-                    cov[3] += dV * (sx * sy + p0x * p0y + p1x * p1y + p2x * p2y);
-                    cov[4] += dV * (sx * sz + p0x * p0z + p1x * p1z + p2x * p2z);
-                    cov[5] += dV * (sy * sz + p0y * p0z + p1y * p1z + p2y * p2z);
+                    cov[0] = fmaf(dV, fmaf(sx, sx, a0 + b0 + c0), cov[0]);
+                    cov[1] = fmaf(dV, fmaf(sy, sy, a1 + b1 + c1), cov[1]);
+                    cov[2] = fmaf(dV, fmaf(sz, sz, a2 + b2 + c2), cov[2]);
+                    cov[3] = fmaf(dV, fmaf(sx, sy, a3 + b3 + c3), cov[3]);
+                    cov[4] = fmaf(dV, fmaf(sx, sz, a4 + b4 + c4), cov[4]);
+                    cov[5] = fmaf(dV, fmaf(sy, sz, a5 + b5 + c5), cov[5]);
                     cov[6] += dV;
-                    cov[7] += dV * sx; cov[8] += dV * sy; cov[9] += dV * sz;
+                    cov[7] = fmaf(dV, sx, cov[7]); cov[8] = fmaf(dV, sy, cov[8]); cov[9] = fmaf(dV, sz, cov[9]);
                 }
                 w++;
                 p1x = p2x; p1y = p2y; p1z = p2z;
+                b0 = c0; b1 = c1; b2 = c2; b3 = c3; b4 = c4; b5 = c5;
                 en = sp.en[en & 1023u];
                 at = (int)(en >> 10);
             }

@@ -131,6 +131,15 @@ void check(int rc, const char* what)
 
 namespace
 {
+void check_on(surtr_ctx* c, int rc, const char* what)
+{
+	if (rc != SURTR_OK)
+		throw std::runtime_error(std::string(what) + ": " + surtr_last_error(c));
+}
+} // namespace
+
+namespace
+{
 class WorkerPool
 {
 	// one object per parallel_for call: a worker that wakes up late finds either a finished job (nothing left to take)
@@ -245,32 +254,34 @@ void parallel_for(size_t n, const std::function<void(size_t)>& fn)
 	pool.run(n, fn);
 }
 
-surtr_ctx* context()
+surtr_ctx* context(int slot)
 {
 	struct Holder
 	{
-		surtr_ctx* ctx = nullptr;
-		~Holder() { surtr_ctx_destroy(ctx); }
+		surtr_ctx* ctx[2] = { nullptr, nullptr };
+		~Holder() { surtr_ctx_destroy(ctx[0]); surtr_ctx_destroy(ctx[1]); }
 	};
 	static thread_local Holder h;
-	if (!h.ctx)
+	slot = slot ? 1 : 0;
+	if (!h.ctx[slot])
 	{
-		const int rc = surtr_ctx_create(0, nullptr, &h.ctx);
+		const int rc = surtr_ctx_create(0, nullptr, &h.ctx[slot]);
 		if (rc != SURTR_OK)
 			throw std::runtime_error(std::string("surtr_ctx_create: ") + surtr_last_error(nullptr));   // no CPU fallback
 	}
-	return h.ctx;
+	return h.ctx[slot];
 }
 
-void place_pattern(const FlatPattern& pattern, const Vector3& scale, const Vector3& translate)
+void place_pattern(const FlatPattern& pattern, const Vector3& scale, const Vector3& translate, int slot)
 {
-	static thread_local uint64_t resident_id = 0;
-	surtr_ctx* c = context();
-	if (resident_id != pattern.id)
+	static thread_local uint64_t resident_id[2] = { 0, 0 };
+	slot = slot ? 1 : 0;
+	surtr_ctx* c = context(slot);
+	if (resident_id[slot] != pattern.id)
 	{
 		check(surtr_upload_pattern(c, pattern.face_verts4.data(), pattern.face_vert_off.data(), (uint32_t)pattern.face_vert_off.size() - 1,
 								   pattern.cell_face_off.data(), pattern.count()), "surtr_upload_pattern");
-		resident_id = pattern.id;
+		resident_id[slot] = pattern.id;
 	}
 	const float s3[3] = { scale.x, scale.y, scale.z }, t3[3] = { translate.x, translate.y, translate.z };
 	check(surtr_place_pattern(c, s3, t3, 1), "surtr_place_pattern");
@@ -278,7 +289,7 @@ void place_pattern(const FlatPattern& pattern, const Vector3& scale, const Vecto
 
 namespace
 {
-// SURTR_TRACE=1: wall time of the three legs of an event (stderr), next to the orchestration phases of Fracture.cpp
+// SURTR_TRACE=1: wall time of the legs of an event (stderr), next to the orchestration phases of Fracture.cpp
 struct Leg
 {
 	const char* name;
@@ -293,22 +304,27 @@ struct Leg
 };
 } // namespace
 
-void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry, bool upload_cells)
+void begin_event(const FlatPolys& pieces, const FlatCells& cells, bool upload_cells, int slot)
 {
-	surtr_ctx* c = context();
-	std::unique_ptr<Leg> leg(new Leg("upload"));
-	check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
+	surtr_ctx* c = context(slot);
+	Leg leg("upload + launch");
+	check_on(c, surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(),
 							  pieces.count(), pieces.ev_off.empty() ? nullptr : pieces.ev_off.data(),
 							  pieces.ev_off.empty() ? 0u : (uint32_t)pieces.ev_off.size() - 1), "surtr_upload_pieces");
 	if (upload_cells)
-		check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
+		check_on(c, surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), cells.bounded ? cells.cverts4.data() : nullptr,
 								 cells.bounded ? cells.cvert_off.data() : nullptr, cells.count(),
 								 cells.ev_off.empty() ? nullptr : cells.ev_off.data(),
 								 cells.ev_off.empty() ? 0u : (uint32_t)cells.ev_off.size() - 1), "surtr_upload_cells");
-	leg.reset(new Leg("launch + wait"));
-	check(surtr_fracture_event(c), "surtr_fracture_event");
+	check_on(c, surtr_fracture_event(c), "surtr_fracture_event");
+}
+
+void end_event(Fragments& out, bool geometry, int slot)
+{
+	surtr_ctx* c = context(slot);
+	std::unique_ptr<Leg> leg(new Leg("wait"));
 	surtr_counts n;
-	check(surtr_event_counts(c, &n), "surtr_event_counts");
+	check_on(c, surtr_event_counts(c, &n), "surtr_event_counts");
 	leg.reset(new Leg("download"));
 	static const bool trace = std::getenv("SURTR_TRACE") != nullptr;
 	if (trace)
@@ -326,7 +342,7 @@ void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, 
 		out.ring_off.resize(n.n_verts + 1);
 		out.ring.resize(n.n_ring);
 	}
-	check(surtr_download_fragments(c, out.rec.data(), geometry ? out.verts4.data() : nullptr,
+	check_on(c, surtr_download_fragments(c, out.rec.data(), geometry ? out.verts4.data() : nullptr,
 								   geometry ? out.ring_off.data() : nullptr, geometry ? out.ring.data() : nullptr),
 		  "surtr_download_fragments");
 }

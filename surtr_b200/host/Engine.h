@@ -63,12 +63,22 @@ struct Fragments
 // all are done; the first exception thrown by a task is rethrown here.  Small n runs inline.
 void parallel_for(size_t n, const std::function<void(size_t)>& fn);
 
-surtr_ctx* context();                                            // throws std::runtime_error without a B200
+// One context per host thread and slot, created on first use (throws std::runtime_error without a B200).  Slot 1 exists so
+// that two independent events of one orchestration step (the convex and the mesh clip of ApplyFracture, Surtr.cpp:1461
+// and :1470) are in flight at the same time, on two streams.
+surtr_ctx* context(int slot = 0);
 void check(int rc, const char* what);                            // throws std::runtime_error with surtr_last_error
-// Makes `pattern` the resident pattern of this thread's context (no-op when it already is) and installs it, scaled and
+// Makes `pattern` the resident pattern of the slot's context (no-op when it already is) and installs it, scaled and
 // translated on the device, as the cell set of the next event (Polygon3D::Scale + Translate, VMACH.cpp:506-534).
-void place_pattern(const FlatPattern& pattern, const DirectX::SimpleMath::Vector3& scale, const DirectX::SimpleMath::Vector3& translate);
-// upload_cells = false: the cells of the previous event on this thread's context are still resident and are reused
-void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true, bool upload_cells = true);
+void place_pattern(const FlatPattern& pattern, const DirectX::SimpleMath::Vector3& scale, const DirectX::SimpleMath::Vector3& translate, int slot = 0);
+// An event in two halves: begin_event uploads and launches (returns while the GPU works), end_event waits and downloads.
+// upload_cells = false: the cells of the previous event on the slot's context are still resident and are reused.
+void begin_event(const FlatPolys& pieces, const FlatCells& cells, bool upload_cells = true, int slot = 0);
+void end_event(Fragments& out, bool geometry = true, int slot = 0);
+inline void run_event(const FlatPolys& pieces, const FlatCells& cells, Fragments& out, bool geometry = true, bool upload_cells = true)
+{
+	begin_event(pieces, cells, upload_cells, 0);
+	end_event(out, geometry, 0);
+}
 } // namespace detail
 } // namespace SurtrHost

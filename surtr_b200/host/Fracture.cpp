@@ -267,7 +267,13 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	detail::FlatCells cells;
 	if (n_in)
 	{
-		detail::FlatPolys pieces;
+		// The convex and the mesh clip are independent given the cells: they run on the thread's two contexts, so the
+		// host packs the meshes while the GPU cuts the convex pieces, and both events share the device afterwards.
+		detail::FlatPolys pieces, meshes;
+		const auto install_cells = [&](int slot) {
+			if (!source.polys)
+				detail::place_pattern(*source.pattern, source.scale, source.translate, slot);
+		};
 		{
 			Phase ph("  pack convex + cells");
 			for (const int c : inside)
@@ -275,26 +281,30 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 			if (source.polys)
 				for (const VMACH::Polygon3D& cell : *source.polys)
 					cells.add(cell);
-			else
-				detail::place_pattern(*source.pattern, source.scale, source.translate);
+			install_cells(0);
+		}
+		detail::begin_event(pieces, cells, source.polys != nullptr, 0);
+		if (meshBranch)
+		{
+			// event 2, the second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same cells.  The
+			// broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both its convex and
+			// its mesh fragment exist (:1466-1472).
+			{
+				Phase ph2("  pack meshes");
+				for (const int c : inside)
+					meshes.add(targetPieceVec[c]->Mesh);
+				install_cells(1);
+			}
+			detail::begin_event(meshes, cells, source.polys != nullptr, 1);
 		}
 		{
-			Phase ph("  convex event");
-			detail::run_event(pieces, cells, fr, true, source.polys != nullptr);
+			Phase ph("  convex event (rest)");
+			detail::end_event(fr, true, 0);
 		}
 		if (meshBranch)
 		{
-			Phase ph("  mesh event");
-			// event 2, the second clip of m_fractureTask (Surtr.cpp:1470): every Piece::Mesh against the same resident
-			// cells.  The broad phase culls with the mesh's own (tighter) extents; a pair yields pieces only when both
-			// its convex and its mesh fragment exist (:1466-1472).
-			detail::FlatPolys meshes;
-			{
-				Phase ph2("    pack meshes");
-				for (const int c : inside)
-					meshes.add(targetPieceVec[c]->Mesh);
-			}
-			detail::run_event(meshes, cells, mfr, true, false);
+			Phase ph("  mesh event (rest)");
+			detail::end_event(mfr, true, 1);
 		}
 	}
 	if (n_out)

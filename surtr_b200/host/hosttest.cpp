@@ -1,5 +1,6 @@
 // hosttest.cpp -- flat C entry points over the host-side mirror CLASSES, so the Python tests can drive the
 // class-level API (Poly / Kdop / VMACH / DT3D / SurtrHost) exactly as a C++ caller would.  Test harness only.
+#include <chrono>
 #include "ConvexHull.h"
 #include "DT3D.h"
 #include "Fracture.h"
@@ -410,6 +411,11 @@ void hosttest_combine_mass(uint32_t n, const double* volume, const float* centro
 // SurtrHost::DoFracture on one compound (convex_i, mesh_i).  g_out / g_mesh = Piece::Convex / Piece::Mesh in PieceVec order;
 // cell = index of the compound (bind set) a piece ends up in, piece = 1 for the caller's untouched pieces.
 // mass10 (optional, 10 floats per compound): CombineMass at density 10 = {mass, cx, cy, cz, Ixx, Iyy, Izz, Ixy, Ixz, Iyz}.
+// wall time of the SurtrHost::DoFracture call inside the last hosttest_do_fracture (without this wrapper's array <-> class
+// conversions and the pattern generation, which the reference does once at start-up, Surtr.cpp:1436-1450)
+static double g_do_fracture_ms = 0.0;
+double hosttest_last_do_fracture_ms() { return g_do_fracture_ms; }
+
 int hosttest_do_fracture(const float* cv, const uint32_t* cvo, const uint32_t* cro, const uint16_t* cr,
 						 const float* mv, const uint32_t* mvo, const uint32_t* mro, const uint16_t* mr, uint32_t n_pieces,
 						 const float* seeds, uint32_t n_seeds, const float* cloud3, uint32_t n_cloud, const float* impact3,
@@ -434,7 +440,9 @@ int hosttest_do_fracture(const float* cv, const uint32_t* cvo, const uint32_t* c
 		args.ImpactRadius = impact_radius;
 		args.PartialFracture = partial != 0;
 		SurtrHost::CompoundInfo info;
+		const auto t0 = std::chrono::steady_clock::now();
 		const std::vector<SurtrHost::Compound> result = SurtrHost::DoFracture(compound, storage, cloud, args, &info);
+		g_do_fracture_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		*n_compounds = (uint32_t)result.size();
 		std::vector<uint32_t> compound_of(info.PieceVec.size(), 0xffffffffu);
 		for (size_t b = 0; b < info.CompoundBind.size(); b++)

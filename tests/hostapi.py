@@ -172,6 +172,13 @@ def do_fracture(convex: PolySet, mesh: PolySet, seeds, cloud, impact, impact_rad
     return export(), export_mesh(), ncomp.value, mass[:ncomp.value].copy()
 
 
+def last_do_fracture_ms() -> float:
+    """Wall time of SurtrHost::DoFracture itself inside the last do_fracture call (no wrapper conversions)."""
+    L = lib()
+    L.hosttest_last_do_fracture_ms.restype = C.c_double
+    return float(L.hosttest_last_do_fracture_ms())
+
+
 def transform(verts4, matrix16):
     verts4 = np.ascontiguousarray(verts4, np.float32)
     m = np.ascontiguousarray(matrix16, np.float32).reshape(16)
