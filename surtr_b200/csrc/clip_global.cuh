@@ -238,15 +238,19 @@ __device__ bool g_compact(GlobalPoly& g, int hi, int& n_out, const Grp<NW>& grp)
     const int tid = grp.tid;
     const size_t GS = (size_t)g.gd;
     int kept_before = 0;
-#pragma unroll 2
-    for (int base = 0; base < hi; base += N)
     {
-        const int v = base + tid;
-        const bool live = v < hi && g.comp[v] >= 0;
-        int tot;
-        const int ex = grp.exscan(live ? 1 : 0, tot);
-        if (v < hi) g.id[v] = live ? (uint16_t)(kept_before + ex) : G_NONE;
-        kept_before += tot;
+        // new number of a live slot = live slots below it: a contiguous run per thread, one scan over the threads
+        const int chunk = (hi + N - 1) / N;
+        const int vb = min(hi, tid * chunk), ve = min(hi, vb + chunk);
+        int mine = 0;
+        for (int v = vb; v < ve; v++) mine += g.comp[v] >= 0 ? 1 : 0;
+        int rank = grp.exscan(mine, kept_before);
+        for (int v = vb; v < ve; v++)
+        {
+            const bool live = g.comp[v] >= 0;
+            g.id[v] = live ? (uint16_t)rank : G_NONE;
+            rank += live ? 1 : 0;
+        }
     }
     grp.sync();
     bool dangling = false;
@@ -323,30 +327,51 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
         }
         if (!any_clip) continue;
 
-        // straddling half-edges in the reference's append order (vertex ascending, slot ascending)
-        int nnew = 0;
-        bool redo = false;
-#pragma unroll 2
-        for (int base = 0; base < hi; base += N)
+        // straddling half-edges in the reference's append order (vertex ascending, slot ascending).  Three passes and ONE
+        // group scan (a scan per strided chunk cost two block barriers per 256 vertices: 22 per plane on the bunny mesh,
+        // most of the tier's time): (1) strided, the straddle count of every clipped vertex -> id[] (free until the patch);
+        // (2) blocked, every thread sums a contiguous run of counts, one scan over the threads, the run's counts become
+        // list positions; (3) strided, the entries are written at their positions.
+        for (int v = tid; v < hi; v += N)
         {
-            const int v = base + tid;
             int cnt = 0;
-            if (v < hi && g.comp[v] == -1)
+            if (g.comp[v] == -1)
             {
                 const int d = g.deg[v];
                 for (int j = 0; j < d; j++)
                     if (g.comp[g.ring[(size_t)v * GS + j]] > 0) cnt++;
             }
-            int tot;
-            int w = nnew + grp.exscan(cnt, tot);
-            if (hi + nnew + tot > g.cap) { redo = true; break; }   // (uniform: nnew, tot and hi are)
-            if (cnt)
+            g.id[v] = (uint16_t)cnt;
+        }
+        grp.sync();
+        int nnew = 0;
+        bool redo = false;
+        {
+            const int chunk = (hi + N - 1) / N;
+            const int vb = min(hi, tid * chunk), ve = min(hi, vb + chunk);
+            int mine = 0;
+            for (int v = vb; v < ve; v++) mine += g.id[v];
+            int off = grp.exscan(mine, nnew);
+            redo = hi + nnew > g.cap;   // (uniform)
+            if (!redo)
+                for (int v = vb; v < ve; v++)
+                {
+                    const int c = g.id[v];
+                    g.id[v] = (uint16_t)off;
+                    off += c;
+                }
+        }
+        if (!redo)
+        {
+            grp.sync();
+            for (int v = tid; v < hi; v += N)
             {
+                if (g.comp[v] != -1) continue;
+                int w = g.id[v];
                 const int d = g.deg[v];
                 for (int j = 0; j < d; j++)
                     if (g.comp[g.ring[(size_t)v * GS + j]] > 0) g.list[w++] = (uint32_t)v | ((uint32_t)j << 16);
             }
-            nnew += tot;
         }
         if (redo)
         {
@@ -449,20 +474,15 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
 
         // lazy compaction (Poly.cpp:464-499): clipped and spliced vertices only give up their slot's liveness
         int live_now = 0;
-#pragma unroll 2
-        for (int base = 0; base < nverts; base += N)
         {
-            const int v = base + tid;
-            bool live = false;
-            if (v < nverts)
+            int mine = 0;
+            for (int v = tid; v < nverts; v += N)
             {
                 const int c = g.comp[v];
                 if (c == -1) g.comp[v] = G_GONE;
-                live = c >= 0;
+                mine += c >= 0 ? 1 : 0;
             }
-            int tot;
-            grp.exscan(live ? 1 : 0, tot);
-            live_now += tot;
+            grp.exscan(mine, live_now);   // (one scan for the whole polyhedron: only the total is needed)
         }
         hi = nverts;
         dense = false;
