@@ -484,7 +484,6 @@ struct ClipArgs
     uint32_t* ovf_list;           // tier 1 (64 slots) appends, tier 1b (128 slots) consumes
     uint32_t* ovf2_list;          // tier 1b appends, tier 2 consumes
     int skip_tier1b;              // test hook / round-1 kernel: tier 1 hands its overflows straight to tier 2
-    int t3_hot;                   // global tier: positions / comp / degree / id of the workspace in (dynamic) shared memory
     uint64_t cap_tier2;           // slots available to tier 2
     uint32_t* ovf3_list;          // tiers 1 / 1b / 2 append, tier 3 consumes
     unsigned char* ws3;           // tier 3: one workspace per warp
@@ -642,7 +641,6 @@ __global__ void __launch_bounds__(T2_WARPS * 32) clip_shared_kernel(ClipArgs a)
 // K3, unbounded tier: persistent warps over the pairs the on-chip tiers handed on (clip_global.cuh).
 constexpr int T3_WARPS = 8;            // warps per pair (= per block) in the unbounded tier
 constexpr int T3_BLOCKS_PER_SM = 2;    // persistent blocks, one workspace each
-__host__ __device__ constexpr size_t t3_hot_bytes(size_t cap) { return cap * 17 + 16; }   // x, y, z, id, deg, comp
 __host__ __device__ constexpr size_t blob3_bytes(size_t cap, size_t gd) { return cap * (16 + 4 + gd * 2); }   // float4 verts | u32 ring_start | u16 ring
 
 __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
@@ -656,22 +654,6 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
     const Grp<T3_WARPS> grp{ tid, tid & 31, s_scan };
     const unsigned long long n_items = a.ctl->n_ovf3;
     GlobalPoly g = global_poly_carve(a.ws3 + (size_t)blockIdx.x * a.ws3_stride, a.cap3, a.gd3);
-    if (a.t3_hot)
-    {
-        // The arrays every pass over the vertices reads -- positions, comp, degree, id (17 bytes per slot) -- live in
-        // shared memory when the workspace's slot count allows (the host decides: <= 200 KB); the rings, snapshots and
-        // triangle records stay in the L2-resident global workspace.  Each plane costs about seven strided passes over
-        // the slots by one block per SM: with everything in global memory each pass was an exposed L2 round trip per
-        // iteration (profiles/r2_large_tiers.md).
-        extern __shared__ __align__(16) unsigned char t3_smem[];
-        unsigned char* p = t3_smem;
-        g.x = reinterpret_cast<float*>(p); p += (size_t)a.cap3 * 4;
-        g.y = reinterpret_cast<float*>(p); p += (size_t)a.cap3 * 4;
-        g.z = reinterpret_cast<float*>(p); p += (size_t)a.cap3 * 4;
-        g.id = reinterpret_cast<uint16_t*>(p); p += (size_t)a.cap3 * 2;
-        g.deg = reinterpret_cast<uint16_t*>(p); p += (size_t)a.cap3 * 2;
-        g.comp = reinterpret_cast<int8_t*>(p);
-    }
     const size_t GS = (size_t)a.gd3;
     unsigned seq_cuts = 0;
     for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)

@@ -135,7 +135,6 @@ struct surtr_ctx
     bool profiled_last = false;
     bool tier1b_enabled = false;  // the 128-slot warp-per-pair tier is launched once an event needed it
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
-    size_t t3_smem_set = 0;        // dynamic shared memory the global tier's kernel has been opted into
     uint32_t last_ring_bytes = 2; // ring entry width of the last event's output blob (surtr_download_blob_async)
     int k3_warps = 0;             // small tier's main launch: 0 = persistent warps + ticket (default); SURTR_K3_WARPS=2: one block of two pairs per two candidates (A/B)
     bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
@@ -362,7 +361,6 @@ int launch_event(surtr_ctx* ctx)
     ca.ovf_list = ctx->ovf_list.as<uint32_t>();
     ca.ovf2_list = ctx->ovf2_list.as<uint32_t>();
     ca.skip_tier1b = ctx->no_tier1b || ctx->k3_round1 ? 1 : 0;
-    ca.t3_hot = 0;
     ca.cap_tier2 = ctx->cap_tier2;
     ca.ovf3_list = ctx->ovf3_list.as<uint32_t>();
     ca.ws3 = ctx->ws3.as<unsigned char>();
@@ -405,14 +403,7 @@ int launch_event(surtr_ctx* ctx)
     {
         ca.scratch = ctx->scratch3.as<unsigned char>();
         ca.slot_bytes = blob3_bytes((size_t)ctx->cap3, (size_t)ctx->gd3);
-        const size_t hot = t3_hot_bytes((size_t)ctx->cap3);
-        ca.t3_hot = hot <= 200 * 1024 ? 1 : 0;
-        if (ca.t3_hot && hot > ctx->t3_smem_set)
-        {
-            CK(cudaFuncSetAttribute(clip_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-            ctx->t3_smem_set = 200 * 1024;
-        }
-        launch_pdl(clip_global_kernel, dim3(ctx->n_ws3), dim3(T3_WARPS * 32), ca.t3_hot ? hot : 0, ctx->stream, ca);
+        launch_pdl(clip_global_kernel, dim3(ctx->n_ws3), dim3(T3_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[5], ctx->stream));

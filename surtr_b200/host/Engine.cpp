@@ -98,6 +98,13 @@ void FlatPattern::build(const std::vector<VMACH::Polygon3D>& cells)
 	{
 		for (const VMACH::PolygonFace& f : cell.FaceVec)
 		{
+			// The device placement re-derives every face plane from the face's first three moved vertices, which is what
+			// Polygon3D::Scale / Translate do through ConstructFacePlane -- but only for GuaranteeConvex faces
+			// (VMACH.cpp:303-310): a face that carries a hand-set plane keeps it in the reference, so it cannot take this
+			// route (use the explicit cell list of ApplyFracture, which ships FacePlane as it is).
+			if (!f.GuaranteeConvex || f.VertexVec.size() < 3)
+				throw std::invalid_argument("FlatPattern: a resident pattern needs GuaranteeConvex faces of at least three vertices "
+											"(their planes are re-derived on the device after every placement)");
 			for (const Vector3& v : f.VertexVec)
 				face_verts4.insert(face_verts4.end(), { v.x, v.y, v.z, 0.f });
 			face_vert_off.push_back((uint32_t)(face_verts4.size() / 4));
