@@ -332,14 +332,31 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
         // most of the tier's time): (1) strided, the straddle count of every clipped vertex -> id[] (free until the patch);
         // (2) blocked, every thread sums a contiguous run of counts, one scan over the threads, the run's counts become
         // list positions; (3) strided, the entries are written at their positions.
+        // (the kept-neighbour test is a chain of two global loads per ring entry: four entries at a time, so that the
+        // comp loads of a group are in flight together; the result is kept as a slot MASK in old_deg -- free until a
+        // sequential replay -- and pass 3 expands the mask instead of walking the ring again)
         for (int v = tid; v < hi; v += N)
         {
+            unsigned mask = 0u;
             int cnt = 0;
             if (g.comp[v] == -1)
             {
                 const int d = g.deg[v];
-                for (int j = 0; j < d; j++)
-                    if (g.comp[g.ring[(size_t)v * GS + j]] > 0) cnt++;
+                const uint16_t* r = g.ring + (size_t)v * GS;
+                for (int j0 = 0; j0 < d; j0 += 4)
+                {
+                    // (GS is a multiple of 8: a ring row starts on a 16-byte boundary, four entries are one 8-byte load)
+                    const uint2 e = *reinterpret_cast<const uint2*>(r + j0);
+                    const int n0 = e.x & 0xffffu, n1 = e.x >> 16, n2 = e.y & 0xffffu, n3 = e.y >> 16;
+                    const int8_t c0 = g.comp[n0];
+                    const int8_t c1 = j0 + 1 < d ? g.comp[n1] : (int8_t)0;
+                    const int8_t c2 = j0 + 2 < d ? g.comp[n2] : (int8_t)0;
+                    const int8_t c3 = j0 + 3 < d ? g.comp[n3] : (int8_t)0;
+                    const unsigned m4 = (c0 > 0 ? 1u : 0u) | (c1 > 0 ? 2u : 0u) | (c2 > 0 ? 4u : 0u) | (c3 > 0 ? 8u : 0u);
+                    cnt += __popc(m4);
+                    if (j0 < 16) mask |= m4 << j0;
+                }
+                g.old_deg[v] = (uint16_t)mask;
             }
             g.id[v] = (uint16_t)cnt;
         }
@@ -369,7 +386,9 @@ __device__ int global_clip_by_planes(GlobalPoly& g, int& nv, const float4* __res
                 if (g.comp[v] != -1) continue;
                 int w = g.id[v];
                 const int d = g.deg[v];
-                for (int j = 0; j < d; j++)
+                unsigned mask = g.old_deg[v];
+                while (mask) { const int j = __ffs((int)mask) - 1; mask &= mask - 1u; g.list[w++] = (uint32_t)v | ((uint32_t)j << 16); }
+                for (int j = 16; j < d; j++)   // (rings wider than the mask: the global tier only)
                     if (g.comp[g.ring[(size_t)v * GS + j]] > 0) g.list[w++] = (uint32_t)v | ((uint32_t)j << 16);
             }
         }
