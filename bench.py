@@ -45,8 +45,8 @@ REF_THREADS = 16          # Src/Surtr.cpp:28: dp::thread_pool<> g_threadPool(16)
 L2_MIB = 126              # B200 L2
 FLUSH_MIB = 160           # L2 flush buffer for the one-event-at-a-time latency loops (configs 2, 3)
 RESIDENT_BATCH = 512      # events per resident batch (one context each)
-E2E_BATCH = 64            # events per end-to-end batch
-E2E_CONTEXTS = 3          # batches in flight in the end-to-end loop
+E2E_BATCH = 128           # events per end-to-end batch (sweep in profiles/r2_e2e_sweep.md: 128 x 4 contexts > 64 x 3 > 32 x 4)
+E2E_CONTEXTS = 4          # batches in flight in the end-to-end loop
 
 
 def workload_config(n_events: int) -> dict:

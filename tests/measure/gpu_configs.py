@@ -1,6 +1,6 @@
 """Measurement: BASELINE configs 1, 3, 4, 5 at (or near) full size on one GPU -- parity fingerprints, GPU timings and the
 reference build's CPU timings (oracle/_ref, dp::thread_pool(16) fan-out + SetExtract, the reference's own timer) on
-the same box.  Writes gpurun_out/configs_r1.json (copied to profiles/)."""
+the same box.  Writes gpurun_out/configs_r2.json (copied to profiles/)."""
 import json, os, sys, time, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')   # run from the repo root
 import torch
@@ -9,7 +9,7 @@ import common
 from oracle import refapi as R
 
 HAVE_REF = R.available()
-CPU_THREADS = max(16, os.cpu_count() or 1)
+CPU_THREADS = 16   # dp::thread_pool(16), Src/Surtr.cpp:28
 
 
 def cpu_seconds(pieces, cells, reps=1):
@@ -128,4 +128,4 @@ if HAVE_REF:
 out["config5"] = {"objects": n_obj, "reference_cpu_per_object_ms": None if cpu5 is None else 1e3 * cpu5, "fragments_per_level": counts, "per_object": [x // n_obj for x in counts],
                   "sum_event_ms": tot_ms, "final_fragments_per_s": counts[-1] / (tot_ms * 1e-3)}
 print(out["config5"], flush=True)
-json.dump(out, open("gpurun_out/configs_r1.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/configs_r2.json", "w"), indent=1)

@@ -39,3 +39,6 @@ python tools/ncu_traffic.py $G/${T}_k3_cfg4.ncu-rep $G/${T}_k3_cfg4.log clip_fas
 python tools/sass_histogram.py > $P/r2_sass_opcodes.txt
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared -Xptxas -v -o /tmp/ptxas_check.so surtr_b200/csrc/surtr_engine.cu 2>&1 | grep -E "Compiling entry|Used|spill" | sed 's/ptxas info    : //' > $P/r2_ptxas_resources.txt
 echo ok
+cp $G/configs_r2.json $P/r2_configs.json 2>/dev/null || true
+grep -v "^\[surtr\]       " $G/${T}_dofracture_trace.txt | tail -40 > $P/r2_dofracture_trace.txt
+for w in config4 config3 config2 mesh; do tail -1 $G/${T}_phases_$w.jsonl; done > $P/r2_phase_times.jsonl
