@@ -37,7 +37,7 @@ off1, idx1 = hostapi.dt3d_neighbors(d1["seeds"])
 cpu1 = None
 if HAVE_REF:
     t0 = time.perf_counter(); R.config1_full(d1["verts"], d1["indices"], d1["seeds"], off1, idx1); cpu1 = time.perf_counter() - t0
-out["config1"] = {"pieces": c1.n, "host_classes_wall_ms": 1e3 * float(np.median(ts)), "do_fracture_call_ms": float(np.median(inner)), "reference_cpu_wall_ms": None if cpu1 is None else 1e3 * cpu1,
+out["config1"] = {"pieces": c1.n, "host_classes_wall_ms": 1e3 * float(np.median(ts)), "reference_cpu_wall_ms": None if cpu1 is None else 1e3 * cpu1,
                   "note": "wall clock of the whole PrepareFracture (ICH, k-DOP, ACH, mesh rings, DT3D cells, convex + mesh clip, islands, refit, extract); reference: single thread, inline"}
 print(out["config1"], flush=True)
 

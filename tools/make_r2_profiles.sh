@@ -34,7 +34,7 @@ cat > /tmp/k3_ranges.txt <<'R'
 276 300 all-in-plane box test
 R
 python tools/ncu_callsite_buckets.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel clip_fast_kernelILi2ELb0ELi4ELb1 surtr_b200/libsurtr_b200.so clip_fast.cuh $N4 /tmp/k3_ranges.txt > $P/r2_k3_instruction_buckets.txt
-python tools/ncu_callsite_buckets.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel clip_fast_kernelILi2ELb0ELi4ELb1 surtr_b200/libsurtr_b200.so kernels.cuh $N4 | head -24 >> $P/r2_k3_instruction_buckets.txt
+python tools/ncu_callsite_buckets.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel clip_fast_kernelILi2ELb0ELi4ELb1 surtr_b200/libsurtr_b200.so kernels.cuh $N4 2>/dev/null | head -24 >> $P/r2_k3_instruction_buckets.txt || true
 python tools/ncu_traffic.py $G/${T}_k3_cfg4.ncu-rep $G/${T}_k3_cfg4.log clip_fast_kernel
 python tools/sass_histogram.py > $P/r2_sass_opcodes.txt
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared -Xptxas -v -o /tmp/ptxas_check.so surtr_b200/csrc/surtr_engine.cu 2>&1 | grep -E "Compiling entry|Used|spill" | sed 's/ptxas info    : //' > $P/r2_ptxas_resources.txt
