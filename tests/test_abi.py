@@ -214,3 +214,40 @@ int main(int argc, char** argv)
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([str(exe), str(raw)], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.startswith("ok 64"), (run.returncode, run.stdout, run.stderr)
+
+
+def test_input_blob_layout_and_packing_round_trip():
+    """The compact input blob of surtr_upload_blob (host side only, no GPU): sections are 256-byte aligned, disjoint and
+    in the documented order for both ring entry widths; fill_input_blob writes what the header says -- float3 positions,
+    one ring-length byte per vertex, the first ring entry of every piece, one- or two-byte ring entries -- and the arrays
+    can be read back from it."""
+    import common
+    from surtr_b200 import FractureContext
+    pieces, cells = common.voronoi(1234, 30), common.voronoi(46354, 6)
+    for rb in (1, 2):
+        L = FractureContext.input_blob_layout(pieces.n, len(pieces.verts), len(pieces.ring), cells.n, len(cells.planes), len(cells.verts), 0, rb)
+        offs = [L.verts3, L.vert_off, L.ring_base, L.ring_len, L.ring, L.planes4, L.plane_off, L.cell_verts3, L.cvert_off, L.ev_piece_off, L.ev_cell_off, L.total]
+        sizes = [12 * len(pieces.verts), 4 * (pieces.n + 1), 4 * (pieces.n + 1), len(pieces.verts), rb * len(pieces.ring), 16 * len(cells.planes),
+                 4 * (cells.n + 1), 12 * len(cells.verts), 4 * (cells.n + 1), 4, 4]
+        assert all(o % 256 == 0 for o in offs)
+        assert all(offs[i] + sizes[i] <= offs[i + 1] for i in range(len(sizes)))
+    with pytest.raises(Exception):
+        FractureContext.input_blob_layout(1, 1, 1, 1, 1, 1, 0, 3)
+    sizes, total = FractureContext.fill_input_blob(None, pieces, cells)
+    assert sizes[-1] == 1                                     # Voronoi cells: far fewer than 256 vertices each
+    buf = np.zeros(total, np.uint8)
+    FractureContext.fill_input_blob(buf, pieces, cells)
+    L = FractureContext.input_blob_layout(*sizes)
+    nv, ne = len(pieces.verts), len(pieces.ring)
+    assert np.array_equal(buf[L.verts3:L.verts3 + 12 * nv].view(np.float32).reshape(nv, 3), pieces.verts[:, :3])
+    ring_len = buf[L.ring_len:L.ring_len + nv]
+    ring_base = buf[L.ring_base:L.ring_base + 4 * (pieces.n + 1)].view(np.uint32)
+    assert np.array_equal(ring_len, np.diff(pieces.ring_off)) and ring_base[-1] == ne
+    # ring offsets as expand_blob_kernel rebuilds them: the piece's first entry + the running sum of its lengths
+    rebuilt = np.zeros(nv + 1, np.uint32)
+    for p in range(pieces.n):
+        v0, v1 = int(pieces.vert_off[p]), int(pieces.vert_off[p + 1])
+        rebuilt[v0:v1] = ring_base[p] + np.concatenate([[0], np.cumsum(ring_len[v0:v1 - 1], dtype=np.uint32)]) if v1 > v0 else 0
+    rebuilt[nv] = ring_base[-1]
+    assert np.array_equal(rebuilt, pieces.ring_off)
+    assert np.array_equal(buf[L.ring:L.ring + ne], pieces.ring.astype(np.uint8))
