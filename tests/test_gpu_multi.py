@@ -43,7 +43,7 @@ def _worker(rank, world, port, q):
         L = ctx.download_blob_into_async(blob.data_ptr() + hdr, cap)
         ctx.sync()
         lay = np.array([L.fragments, L.verts3, L.ring_len, L.ring, L.total, L.n_fragments, L.n_verts, L.n_ring, L.ring_entry_bytes], np.uint64)
-        blob[:hdr].copy_(torch.from_numpy(lay.view(np.uint8).copy()))
+        blob[:lay.nbytes].copy_(torch.from_numpy(lay.view(np.uint8).copy()))
         blob = blob[:hdr + int(L.total)]
         got = sharding.gather_blobs(blob, 0)
         if rank == 0:
@@ -88,8 +88,19 @@ def test_two_ranks_nccl_gather_matches_oracle():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    failures = q.get(timeout=300)
+    # a rank that dies leaves the queue empty: poll it and the processes, do not sit out a long timeout
+    import queue, time
+    failures, t_end = None, time.monotonic() + 240
+    while failures is None and time.monotonic() < t_end:
+        try:
+            failures = q.get(timeout=2)
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+        p.join(timeout=60)
+        if p.is_alive():
+            p.terminate()
+    assert failures is not None, f"a rank failed before the gather (exit codes {[p.exitcode for p in procs]})"
+    assert all(p.exitcode == 0 for p in procs)
     assert failures == [], f"events that differ from the oracle after the gather: {failures}"
