@@ -225,6 +225,8 @@ struct CellSource
 
 CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, const std::vector<Vector3>& spherePointCloud, bool partial,
 							const FractureArgs& args, bool meshBranch);
+bool refit_begin(const std::vector<Piece*>& targetPieceVec, const FractureArgs& args);
+void refit_end(std::vector<Piece*>& targetPieceVec, std::vector<MassProperties>* mass);
 } // namespace
 
 CompoundInfo ApplyFracture(const Compound& compound, const std::vector<VMACH::Polygon3D>& voroPolyVec, bool meshBranch)
@@ -265,6 +267,7 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	// event 1: the pieces inside the sphere x the cells (one pool task per cell in the reference, :2129-2131)
 	detail::Fragments fr, mfr, ofr;
 	detail::FlatCells cells;
+	std::vector<Poly::Polyhedron> convexPoly;   // mesh branch: fragment f of the convex event, unpacked early
 	if (n_in)
 	{
 		// The convex and the mesh clip are independent given the cells: they run on the thread's two contexts, so the
@@ -303,6 +306,12 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 		}
 		if (meshBranch)
 		{
+			{
+				// the convex fragments become Poly::Polyhedron objects while the GPU is still cutting the meshes
+				Phase ph("  unpack convex");
+				convexPoly.resize(fr.rec.size());
+				detail::parallel_for(fr.rec.size(), [&](size_t f) { convexPoly[f] = fr.polyhedron(f); });
+			}
 			Phase ph("  mesh event (rest)");
 			detail::end_event(mfr, true, 1);
 		}
@@ -361,7 +370,7 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	// ... build the pieces of every pair on the worker pool (AoS conversion + island split, Surtr.cpp:1474-1500) ...
 	std::vector<std::vector<Piece*>> built(matched.size());
 	detail::parallel_for(matched.size(), [&](size_t k) {
-		const Poly::Polyhedron convex = fr.polyhedron(matched[k].first);
+		const Poly::Polyhedron convex = convexPoly.empty() ? fr.polyhedron(matched[k].first) : std::move(convexPoly[matched[k].first]);
 		if (!meshBranch)
 		{
 			built[k].push_back(new Piece(convex, convex));
@@ -579,12 +588,17 @@ std::vector<Compound> DoFracture(const Compound& targetCompound, const FractureS
 		MergeOutOfImpact(second, localSpherePointCloud, args);
 	}
 	{
-		Phase ph("HandleConvexIsland");
-		HandleConvexIsland(second);
-	}
-	{
-		Phase ph("Refitting");
-		Refitting(second.PieceVec, args, &second.PieceMass);
+		// The refit's inputs (every piece's Mesh and Convex) are final after the merge, and HandleConvexIsland only regroups
+		// CompoundBind from the PRE-refit convexes (the reference's order, Surtr.cpp:1931-1944): the refit's GPU event is
+		// launched first and runs while the host does the grouping; its results replace the convexes afterwards.
+		Phase ph("HandleConvexIsland + Refitting");
+		const bool refit = refit_begin(second.PieceVec, args);
+		{
+			Phase ph2("  HandleConvexIsland");
+			HandleConvexIsland(second);
+		}
+		if (refit)
+			refit_end(second.PieceVec, &second.PieceMass);
 		SetExtract(second);
 	}
 
@@ -640,12 +654,16 @@ MassProperties CombineMass(const std::vector<MassProperties>& pieces, float dens
 	return total;
 }
 
-void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, std::vector<MassProperties>* mass)
+namespace
+{
+// Refitting in two halves, so that a caller can do host work (HandleConvexIsland) while the GPU clips:
+// refit_begin = ICH normals, k-DOP extents, upload + launch of the clip event; refit_end = wait, download, unpack.
+bool refit_begin(const std::vector<Piece*>& targetPieceVec, const FractureArgs& args)
 {
 	const uint32_t n = (uint32_t)targetPieceVec.size();
 	if (!n)
-		return;
-	// 1. ICH normals per piece (host; <= 4 points by default)
+		return false;
+	// 1. ICH normals per piece (host; <= 4 points by default: the seed tetrahedron)
 	Phase* ph = new Phase("  refit: ICH normals");
 	std::vector<std::vector<Vector3>> piece_normals(n);
 	detail::parallel_for(n, [&](size_t i) {   // one task per piece, like the reference's pool (Surtr.cpp:2405-2413)
@@ -675,11 +693,10 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, st
 	detail::check(surtr_kdop_calc_batch(detail::context(), verts4.data(), vert_off.data(), n, normals3.data(), normal_off.data(),
 										dist.data(), arg.data(), planes8.data()), "surtr_kdop_calc_batch");
 	delete ph;
-	ph = new Phase("  refit: clip event + unpack");
+	Phase ph3("  refit: pack + launch");
 	// 3. clip piece->Convex by its own plane list: n independent events of one piece x one cell
 	detail::FlatPolys pieces;
 	detail::FlatCells cells;
-	std::vector<uint32_t> ev(n + 1);
 	for (uint32_t i = 0; i < n; i++)
 	{
 		pieces.add(targetPieceVec[i]->Convex);
@@ -690,27 +707,24 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, st
 			pl.emplace_back(planes8[8 * e + 4], planes8[8 * e + 5], planes8[8 * e + 6], planes8[8 * e + 7]);   // MaxPlane
 		}
 		cells.add(pl);
-		ev[i] = i;
+		pieces.ev_off.push_back(i);
 	}
-	ev[n] = n;
-	surtr_ctx* c = detail::context();
-	detail::check(surtr_upload_pieces(c, pieces.verts4.data(), pieces.vert_off.data(), pieces.ring_off.data(), pieces.ring.data(), n, ev.data(), n),
-				  "surtr_upload_pieces");
-	detail::check(surtr_upload_cells(c, cells.planes4.data(), cells.plane_off.data(), nullptr, nullptr, n, ev.data(), n), "surtr_upload_cells");
-	detail::check(surtr_fracture_event(c), "surtr_fracture_event");
-	surtr_counts cnt;
-	detail::check(surtr_event_counts(c, &cnt), "surtr_event_counts");
+	pieces.ev_off.push_back(n);
+	cells.ev_off = pieces.ev_off;
+	detail::begin_event(pieces, cells, true, 0);   // (pageable uploads are staged before the call returns)
+	return true;
+}
+
+void refit_end(std::vector<Piece*>& targetPieceVec, std::vector<MassProperties>* mass)
+{
+	Phase ph("  refit: wait + unpack");
+	const uint32_t n = (uint32_t)targetPieceVec.size();
 	detail::Fragments fr;
-	fr.rec.resize(cnt.n_fragments);
-	fr.verts4.resize(4 * cnt.n_verts);
-	fr.ring_off.resize(cnt.n_verts + 1);
-	fr.ring.resize(cnt.n_ring);
-	detail::check(surtr_download_fragments(c, fr.rec.data(), fr.verts4.data(), fr.ring_off.data(), fr.ring.data()), "surtr_download_fragments");
+	detail::end_event(fr, true, 0);
 	for (Piece* p : targetPieceVec)
 		p->Convex.clear();
 	if (mass)
 		mass->assign(n, MassProperties());   // a convex that the refit clips away has no mass left
-	std::unique_ptr<Phase> ph_guard(ph);
 	detail::parallel_for(fr.rec.size(), [&](size_t f) { targetPieceVec[fr.rec[f].piece]->Convex = fr.polyhedron(f); });   // one fragment per piece
 	for (size_t f = 0; f < fr.rec.size(); f++)
 	{
@@ -724,6 +738,13 @@ void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, st
 			mp.FaceCount = r.n_faces;
 		}
 	}
+}
+} // namespace
+
+void Refitting(std::vector<Piece*>& targetPieceVec, const FractureArgs& args, std::vector<MassProperties>* mass)
+{
+	if (refit_begin(targetPieceVec, args))
+		refit_end(targetPieceVec, mass);
 }
 
 } // namespace SurtrHost
