@@ -144,6 +144,47 @@ PreparedObject PrepareFracture(const std::vector<Vector3>& vertices, const std::
 	return prepare(vertices, &indices, seeds, args);
 }
 
+namespace
+{
+// The islands of CheckMeshIsland as sorted vertex lists (no node-based sets: one flag array, one stack).
+std::vector<std::vector<int>> mesh_islands(const Poly::Polyhedron& polyhedron)
+{
+	std::vector<std::vector<int>> groups;
+	const int n = (int)polyhedron.size();
+	std::vector<char> grouped(n, 0);
+	std::vector<int> in_group(n, 0), stack;   // in_group[v] = stamp of the group that holds v (every group starts from an empty set)
+	int start = 0, stamp = 0;
+	while (n)
+	{
+		std::vector<int> group;
+		stamp++;
+		stack.assign(1, start);
+		while (!stack.empty())
+		{
+			const int v = stack.back();
+			stack.pop_back();
+			for (const int a : polyhedron[v].NeighborVertexVec)
+				if (a >= 0 && a < n && in_group[a] != stamp)
+				{
+					in_group[a] = stamp;
+					group.push_back(a);
+					stack.push_back(a);
+				}
+		}
+		std::sort(group.begin(), group.end());
+		for (const int v : group)
+			grouped[v] = 1;
+		groups.push_back(std::move(group));
+		grouped[start] = 1;   // a start vertex without neighbours is in no group (the reference would spin on it)
+		const auto rest = std::find(grouped.begin() + start, grouped.end(), 0);
+		if (rest == grouped.end())
+			break;
+		start = (int)(rest - grouped.begin());
+	}
+	return groups;
+}
+} // namespace
+
 std::vector<std::set<int>> CheckMeshIsland(const Poly::Polyhedron& polyhedron)
 {
 	// Surtr.cpp:2157-2199 recurses from an arbitrary vertex; an explicit stack reaches the same sets.  Groups come
@@ -370,18 +411,19 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 	// ... build the pieces of every pair on the worker pool (AoS conversion + island split, Surtr.cpp:1474-1500) ...
 	std::vector<std::vector<Piece*>> built(matched.size());
 	detail::parallel_for(matched.size(), [&](size_t k) {
-		const Poly::Polyhedron convex = convexPoly.empty() ? fr.polyhedron(matched[k].first) : std::move(convexPoly[matched[k].first]);
+		Poly::Polyhedron convex = convexPoly.empty() ? fr.polyhedron(matched[k].first) : std::move(convexPoly[matched[k].first]);
 		if (!meshBranch)
 		{
-			built[k].push_back(new Piece(convex, convex));
+			Poly::Polyhedron same = convex;
+			built[k].push_back(new Piece(std::move(convex), std::move(same)));
 			return;
 		}
-		const Poly::Polyhedron mesh = mfr.polyhedron(matched[k].second);
-		const std::vector<std::set<int>> groupVec = CheckMeshIsland(mesh);
+		Poly::Polyhedron mesh = mfr.polyhedron(matched[k].second);
+		const std::vector<std::vector<int>> groupVec = mesh_islands(mesh);   // = CheckMeshIsland(mesh), as sorted lists
 		if (groupVec.size() >= 2)
 		{
 			std::vector<int> mapping(mesh.size(), -1);
-			for (const std::set<int>& group : groupVec)
+			for (const std::vector<int>& group : groupVec)
 			{
 				Poly::Polyhedron island;
 				for (const int iVert : group)
@@ -392,11 +434,11 @@ CompoundInfo apply_fracture(const Compound& compound, const CellSource& source, 
 				for (Poly::Vertex& vert : island)
 					for (int& iAdj : vert.NeighborVertexVec)
 						iAdj = mapping[iAdj];
-				built[k].push_back(new Piece(convex, island));
+				built[k].push_back(new Piece(convex, std::move(island)));
 			}
 		}
 		else
-			built[k].push_back(new Piece(convex, mesh));
+			built[k].push_back(new Piece(std::move(convex), std::move(mesh)));
 	});
 	// ... and bind them in order: one set per cell that produced pieces, cell order (Surtr.cpp:2133-2146)
 	int current_cell = -1;
@@ -475,11 +517,13 @@ void HandleConvexIsland(CompoundInfo& compoundInfo)
 		return false;
 	};
 
-	std::vector<std::set<int>> newBind;
-	for (std::set<int>& localBind : compoundInfo.CompoundBind)
-	{
+	// every bind set is split on its own: one pool task per set, applied in set order afterwards
+	const size_t nBind = compoundInfo.CompoundBind.size();
+	std::vector<std::vector<std::set<int>>> splitOf(nBind);
+	detail::parallel_for(nBind, [&](size_t iBind) {
+		const std::set<int>& localBind = compoundInfo.CompoundBind[iBind];
 		if (localBind.size() <= 1)
-			continue;
+			return;
 		std::vector<FaceNode> nodes;
 		for (const int cid : localBind)
 			for (const std::vector<int>& poly : *compoundInfo.PieceExtractedConvex[cid])
@@ -531,12 +575,15 @@ void HandleConvexIsland(CompoundInfo& compoundInfo)
 			}
 			splitGroup.push_back(std::move(split));
 		}
-		if (splitGroup.size() >= 2)
+		splitOf[iBind] = std::move(splitGroup);
+	});
+	std::vector<std::set<int>> newBind;
+	for (size_t iBind = 0; iBind < nBind; iBind++)
+		if (splitOf[iBind].size() >= 2)
 		{
-			localBind = splitGroup[0];
-			newBind.insert(newBind.end(), std::next(splitGroup.begin()), splitGroup.end());
+			compoundInfo.CompoundBind[iBind] = splitOf[iBind][0];
+			newBind.insert(newBind.end(), std::next(splitOf[iBind].begin()), splitOf[iBind].end());
 		}
-	}
 	compoundInfo.CompoundBind.insert(compoundInfo.CompoundBind.end(), newBind.begin(), newBind.end());
 }
 

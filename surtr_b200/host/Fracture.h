@@ -8,6 +8,7 @@
 // resident cells (Piece::Mesh polyhedra, cut in the global-memory tier of K3) followed by the island split on the host.
 #pragma once
 
+#include <utility>
 #include "Engine.h"
 #include "Poly.h"
 #include "VMACH.h"
@@ -43,6 +44,8 @@ struct Piece   // Inc/Surtr.h:113-119; always allocated on the heap
 	Poly::Polyhedron Convex;
 	Poly::Polyhedron Mesh;
 	Piece(const Poly::Polyhedron& convex, const Poly::Polyhedron& mesh) : Convex(convex), Mesh(mesh) {}
+	Piece(Poly::Polyhedron&& convex, Poly::Polyhedron&& mesh) : Convex(std::move(convex)), Mesh(std::move(mesh)) {}   // (a Vertex owns a heap vector: no deep copies on the fracture path)
+	Piece(const Poly::Polyhedron& convex, Poly::Polyhedron&& mesh) : Convex(convex), Mesh(std::move(mesh)) {}
 };
 
 typedef std::vector<std::vector<int>> Extract;
