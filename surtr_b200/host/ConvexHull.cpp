@@ -55,9 +55,22 @@ ConvexHull::ConvexHull(const std::vector<Vector3>& pointCloud, uint32_t limitCnt
 
 // Key of the edge table.  Reference: hash(print(p1)) ^ hash(print(p2)) -- symmetric, equal for end points that print
 // alike, and 0 for ANY edge whose two end points print alike.  Same partition with two class ids.
+// Print class of a point, computed when the point first becomes an end point of a hull edge (only the few points that
+// join the hull ever need one: formatting all 2503 bunny vertices was two thirds of the hull's time).
+uint32_t ConvexHull::PrintClass(int i) const
+{
+	if (m_printClass[i] == UNCLASSED)
+	{
+		char buf[192];
+		std::snprintf(buf, sizeof buf, "%f%f%f", m_pos[i].x, m_pos[i].y, m_pos[i].z);   // std::to_string(float) prints "%f"
+		m_printClass[i] = m_byPrint.emplace(buf, (uint32_t)m_byPrint.size()).first->second;
+	}
+	return m_printClass[i];
+}
+
 uint64_t ConvexHull::EdgeKey(int a, int b) const
 {
-	const uint32_t ca = m_printClass[a], cb = m_printClass[b];
+	const uint32_t ca = PrintClass(a), cb = PrintClass(b);
 	if (ca == cb)
 		return ~0ull;
 	return ((uint64_t)std::min(ca, cb) << 32) | std::max(ca, cb);
@@ -126,7 +139,7 @@ void ConvexHull::Absorb(int p)
 		for (int i = 0; i < 3; i++)
 		{
 			const int v = m_tris[seen].v[i];
-			if (m_valueClass[v] == m_valueClass[a] || m_valueClass[v] == m_valueClass[b])
+			if (m_pos[v] == m_pos[a] || m_pos[v] == m_pos[b])   // (exact coordinates: the reference's operator==)
 				continue;
 			inner = v;
 			break;
@@ -180,20 +193,6 @@ bool ConvexHull::SeedTetrahedron()
 		if (vol(i4) < vol(i)) i4 = i;
 	m_used[i1] = m_used[i2] = m_used[i3] = m_used[i4] = 1;
 	m_usedCnt = 4;
-	if (m_seedOnly)
-	{
-		// classes of the four seed points among themselves (all that the edge keys of the four triangles can see)
-		const int seed[4] = { i1, i2, i3, i4 };
-		char buf[4][192];
-		for (int k = 0; k < 4; k++)
-		{
-			std::snprintf(buf[k], sizeof buf[k], "%f%f%f", m_pos[seed[k]].x, m_pos[seed[k]].y, m_pos[seed[k]].z);
-			uint32_t cls = (uint32_t)k;
-			for (int j = 0; j < k; j++)
-				if (std::strcmp(buf[j], buf[k]) == 0) { cls = m_printClass[seed[j]]; break; }
-			m_printClass[seed[k]] = cls;
-		}
-	}
 	AddTriangle(i1, i2, i3, i4);
 	AddTriangle(i1, i2, i4, i3);
 	AddTriangle(i1, i3, i4, i2);
@@ -205,38 +204,23 @@ void ConvexHull::Build(uint32_t limitCnt)
 {
 	const size_t n = m_pos.size();
 	m_used.assign(n, 0);
+	m_printClass.assign(n, UNCLASSED);   // six-decimal print classes (the reference's edge keys), filled in on demand
+	m_byPrint.clear();
 	if (limitCnt != 0 && limitCnt <= 4)
 	{
 		// A hull limited to four points is its seed tetrahedron (the greedy loop below never runs): the refit of every
 		// piece after every fracture (Surtr::Refitting, RefittingPointLimit = 4, Surtr.cpp:2405-2413) takes this path.
-		// No point classes over the whole cloud and no outside volumes: the four faces, their winding and their order
-		// depend on the four scans of SeedTetrahedron alone.  Classes are assigned among the four seed points only (the
-		// edge table keys them), found by a first pass without edges.
-		m_printClass.assign(n, 0);
-		m_valueClass.assign(n, 0);
+		// No outside volumes: the four faces, their winding and their order depend on the four scans of SeedTetrahedron
+		// alone.
 		m_seedOnly = true;
 		SeedTetrahedron();
 		return;
 	}
 	m_outside.assign(n, 0.0f);
-	// point classes: exact coordinates (operator== of the reference's vertices) and six-decimal prints (its edge keys)
-	m_printClass.resize(n);
-	m_valueClass.resize(n);
-	{
-		std::map<std::tuple<float, float, float>, uint32_t> byValue;
-		std::map<std::string, uint32_t> byPrint;
-		char buf[192];
-		for (size_t i = 0; i < n; i++)
-		{
-			m_valueClass[i] = byValue.emplace(std::make_tuple(m_pos[i].x, m_pos[i].y, m_pos[i].z), (uint32_t)byValue.size()).first->second;
-			std::snprintf(buf, sizeof buf, "%f%f%f", m_pos[i].x, m_pos[i].y, m_pos[i].z);   // std::to_string(float) prints "%f"
-			m_printClass[i] = byPrint.emplace(buf, (uint32_t)byPrint.size()).first->second;
-		}
-	}
 	if (!SeedTetrahedron())
 		return;
 	// a point's outside volume is its own sequential sum, so the points spread over the worker pool in chunks
-	constexpr size_t CHUNK = 256;
+	constexpr size_t CHUNK = 128;
 	const size_t nChunks = (n + CHUNK - 1) / CHUNK;
 	auto forUnused = [&](const std::function<void(size_t)>& fn) {
 		SurtrHost::detail::parallel_for(nChunks, [&](size_t c) {

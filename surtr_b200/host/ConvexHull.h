@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <list>
 #include <unordered_map>
+#include <map>
+#include <string>
 #include <vector>
 
 namespace VMACH
@@ -90,8 +92,10 @@ private:
 	std::vector<Vector3> m_pos;
 	std::vector<char> m_used;
 	std::vector<float> m_outside;               // summed outside volume of every unused point against the current hull
-	std::vector<uint32_t> m_printClass;         // points with the same six-decimal print share a class
-	std::vector<uint32_t> m_valueClass;         // points with exactly equal coordinates share a class
+	static constexpr uint32_t UNCLASSED = 0xffffffffu;
+	mutable std::vector<uint32_t> m_printClass; // points with the same six-decimal print share a class (lazily, hull points only)
+	mutable std::map<std::string, uint32_t> m_byPrint;
+	uint32_t PrintClass(int i) const;
 	std::vector<Tri> m_tris;
 	std::vector<Rim> m_rims;
 	std::unordered_map<uint64_t, int> m_rimOf;  // edge key -> index into m_rims
