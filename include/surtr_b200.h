@@ -182,7 +182,7 @@ int surtr_download_fragments_packed(surtr_ctx* ctx, surtr_fragment* fragments, f
 int surtr_download_fragments_packed_async(surtr_ctx* ctx, surtr_fragment* fragments, float* verts3, uint8_t* ring_len,
                                           uint16_t* ring);
 /* One-copy transfers.  Host<->device copy rates on PCIe depend strongly on the size of each copy (measured on the B200
- * boxes: 4 MB copies reach a third of the rate of 64 MB copies when both directions are busy, profiles/r2_pcie.txt), so
+ * boxes: 4 MB copies reach a third of the rate of 64 MB copies when both directions are busy, profiles/r2_e2e_sweep.md), so
  * a caller that streams event batches moves ONE blob per direction instead of 8 + 4 arrays.
  *
  * Both blobs are COMPACT wire formats -- the loop is bound by the bytes that cross PCIe (bench.py: e2e.achieved_gbs
@@ -244,7 +244,7 @@ int surtr_last_event_ms(surtr_ctx* ctx, float* total_ms, float* clip_ms);
 int surtr_set_profiling(surtr_ctx* ctx, int on);
 /* Per-kernel durations of the last event in milliseconds (profiling must have been on; measurement only, SURVEY.md
  * section 8d): ms8[0] K1 k-DOP extents, [1] K2a broad-phase masks, [2] K2b pair compaction, [3] K3 small tier
- * (clip_sub_kernel), [4] K3 large + global tiers (0 when not launched), [5] K4 scan, [6] K4 gather, [7] counters to
+ * (clip_fast_kernel<2>), [4] the 128-slot, large and global tiers (0 when not launched), [5] K4 scan, [6] K4 gather, [7] counters to
  * the host + reset.  CUDA events on the context stream between the launches. */
 int surtr_last_event_phases(surtr_ctx* ctx, float* ms8);
 /* Number of kernels the last surtr_fracture_event launched. */

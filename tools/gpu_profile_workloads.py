@@ -99,4 +99,4 @@ torch.cuda.profiler.stop()
 print(json.dumps({"workload": what, "pairs": int(c.n_pairs), "candidates": int(c.n_candidates), "fragments": int(c.n_fragments),
                   "seq_cuts": int(c.n_seq_cuts), "tier1b": int(c.n_tier1b), "tier2": int(c.n_tier2), "tier3": int(c.n_tier3),
                   "k3_algorithmic_bytes": int(alg), "kernel_ms_unprofiled": ph, "k3": os.environ.get("SURTR_K3", "fast"),
-                  "k4_bulk": os.environ.get("SURTR_K4_BULK", "0"), "algorithmic_bytes_per_kernel": per_kernel}))
+                  "algorithmic_bytes_per_kernel": per_kernel}))
