@@ -769,11 +769,12 @@ struct __align__(16) MomPoly2   // 3456 bytes per fragment: eight 128-thread blo
 {
     float x[64], y[64], z[64];
     float4 tri[64];         // a window of 64 ordered fan-triangle records (dV, mx, my, mz); its first 512 bytes double as per-edge triangle counts before
-    u64 ring[64];           // 8 x u8, 0xFF = empty slot (phases 1-2); then flist: one u16 per face in Poly::ExtractFaces
-                            // order, start edge | first triangle << 9
+    u64 ring[64];           // 8 x u8, 0xFF = empty slot (phases 1-2); then, as 256 u16: [0, 128) flist, one entry per face in
+                            // Poly::ExtractFaces order, start edge | first triangle << 9; [128, 256) corners (v_k | v_k+1 << 8) of
+                            // every fan-triangle slot
     uint16_t en[512];       // directed edge e = (v -> ring[v][j]), e = estart[v] + j: next edge of the face loop | v << 10
                             // (before phase 1: the staging area of the fragment's ring bytes, assemble_gather_kernel)
-    uint16_t estart[64];    // first directed-edge id of vertex v = its ring start
+    uint16_t estart[64];    // first directed-edge id of vertex v = its ring start (phases 1-3); then, as 128 bytes: corner v0 of every fan-triangle slot
 };
 
 template <int L>
@@ -888,67 +889,72 @@ __device__ void sub_fragment_moments2(MomPoly2& sp, int nv, const Sub<L> sub, bo
     n_tri = min(n_tri, 128);
     sub.sync();
 
-    // ---- phases 4 + 5, over windows of 64 triangle slots (one window for fragments of up to 34 vertices) ----
-    // phase 4: lane = face: the fan triangles of a face, written to their slots; second moments on the fly
+    // ---- phase 4a: lane = face: one walk around the loop records the corners of every fan triangle at its slot ----
+    // (v0 in the bytes of estart, (v_k, v_k+1) in the upper half of the ring words: both are dead by now.)  The fan
+    // arithmetic itself then runs with lane = TRIANGLE (phase 4b): a face of eight vertices no longer holds the other
+    // lanes up for six rounds of cross products.
+    const int n_listed = has ? min(n_faces, 128) : 0;
+    uint8_t* tv0 = reinterpret_cast<uint8_t*>(sp.estart);
+    uint16_t* tpair = reinterpret_cast<uint16_t*>(sp.ring) + 128;
+#pragma unroll 1
+    for (int t = sub.sl; t < n_listed; t += L)
+    {
+        const unsigned f = flist[t];
+        int w = (int)(f >> 9);
+        unsigned en = sp.en[f & 511u];
+        const int v = (int)(en >> 10);
+        en = sp.en[en & 1023u];
+        int prev = (int)(en >> 10);
+        en = sp.en[en & 1023u];
+        int at = (int)(en >> 10);
+        int guard = 0;
+        while (at != v && guard++ < 64)
+        {
+            if (w < 128) { tv0[w] = (uint8_t)v; tpair[w] = (uint16_t)(prev | (at << 8)); }
+            w++;
+            prev = at;
+            en = sp.en[en & 1023u];
+            at = (int)(en >> 10);
+        }
+    }
+    sub.sync();
+
+    // ---- phases 4b + 5, over windows of 64 triangle slots (one window for fragments of up to 34 vertices) ----
+    // phase 4b: lane = fan triangle (p0, p_k, p_k+1): its record (dV, first moments) goes to its slot, second moments on the fly
     // phase 5: ordered accumulation (Poly.cpp:77-85), as sub_fragment_moments
     float cov[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // xx yy zz xy xz yz, 6V, first moments
-    const int n_listed = has ? min(n_faces, 128) : 0;
     double zeroth = 0.0;
     float fsum = 0.f;
     const int n_win = L == 32 ? n_tri : sub.max_warp(n_tri);
 #pragma unroll 1
     for (int base = 0; base == 0 || base < n_win; base += 64)
     {
+        const int w_end = has ? min(n_tri, base + 64) : 0;
 #pragma unroll 1
-        for (int t = sub.sl; t < n_listed; t += L)
+        for (int w = base + sub.sl; w < w_end; w += L)
         {
-            const unsigned f = flist[t];
-            int w = (int)(f >> 9) - base;
-            const int w_end = (t + 1 < n_listed ? (int)(flist[t + 1] >> 9) : n_tri) - base;
-            if (w >= 64 || w_end <= 0) continue;   // no slot of this face in the window
-            unsigned en = sp.en[f & 511u];
-            const int v = (int)(en >> 10);
-            const float p0x = __fsub_rn(sp.x[v], ox), p0y = __fsub_rn(sp.y[v], oy), p0z = __fsub_rn(sp.z[v], oz);
-            en = sp.en[en & 1023u];
-            int at = (int)(en >> 10);
-            float p1x = __fsub_rn(sp.x[at], ox), p1y = __fsub_rn(sp.y[at], oy), p1z = __fsub_rn(sp.z[at], oz);
-            en = sp.en[en & 1023u];
-            at = (int)(en >> 10);
-            // Second moments (no reference arithmetic to match: PhysX is absent, DESIGN.md section 6 -- fused multiply-adds
-            // are fine here, unlike in dV and the first moments).  Products of the fan's fixed corner p0 are formed once per
-            // face, those of p1 are last triangle's p2 products.
-            const float a0 = p0x * p0x, a1 = p0y * p0y, a2 = p0z * p0z, a3 = p0x * p0y, a4 = p0x * p0z, a5 = p0y * p0z;
-            float b0 = p1x * p1x, b1 = p1y * p1y, b2 = p1z * p1z, b3 = p1x * p1y, b4 = p1x * p1z, b5 = p1y * p1z;
-            int guard = 0;
-            while (at != v && guard++ < 64)
-            {
-                const float p2x = __fsub_rn(sp.x[at], ox), p2y = __fsub_rn(sp.y[at], oy), p2z = __fsub_rn(sp.z[at], oz);
-                const float c0 = p2x * p2x, c1 = p2y * p2y, c2 = p2z * p2z, c3 = p2x * p2y, c4 = p2x * p2z, c5 = p2y * p2z;
-                if (w >= 0 && w < 64 && w + base < 128)
-                {
-                    float cx, cy, cz;
-                    cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
-                    const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
-                    const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
-                    const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
-                    const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
-                    sp.tri[w] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
-                    // second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T)
-                    cov[0] = fmaf(dV, fmaf(sx, sx, a0 + b0 + c0), cov[0]);
-                    cov[1] = fmaf(dV, fmaf(sy, sy, a1 + b1 + c1), cov[1]);
-                    cov[2] = fmaf(dV, fmaf(sz, sz, a2 + b2 + c2), cov[2]);
-                    cov[3] = fmaf(dV, fmaf(sx, sy, a3 + b3 + c3), cov[3]);
-                    cov[4] = fmaf(dV, fmaf(sx, sz, a4 + b4 + c4), cov[4]);
-                    cov[5] = fmaf(dV, fmaf(sy, sz, a5 + b5 + c5), cov[5]);
-                    cov[6] += dV;
-                    cov[7] = fmaf(dV, sx, cov[7]); cov[8] = fmaf(dV, sy, cov[8]); cov[9] = fmaf(dV, sz, cov[9]);
-                }
-                w++;
-                p1x = p2x; p1y = p2y; p1z = p2z;
-                b0 = c0; b1 = c1; b2 = c2; b3 = c3; b4 = c4; b5 = c5;
-                en = sp.en[en & 1023u];
-                at = (int)(en >> 10);
-            }
+            const int v0 = tv0[w] & 63, pr = tpair[w], v1 = pr & 63, v2 = (pr >> 8) & 63;
+            const float p0x = __fsub_rn(sp.x[v0], ox), p0y = __fsub_rn(sp.y[v0], oy), p0z = __fsub_rn(sp.z[v0], oz);
+            const float p1x = __fsub_rn(sp.x[v1], ox), p1y = __fsub_rn(sp.y[v1], oy), p1z = __fsub_rn(sp.z[v1], oz);
+            const float p2x = __fsub_rn(sp.x[v2], ox), p2y = __fsub_rn(sp.y[v2], oy), p2z = __fsub_rn(sp.z[v2], oz);
+            float cx, cy, cz;
+            cross3(p1x, p1y, p1z, p2x, p2y, p2z, cx, cy, cz);
+            const float dV = dot3(p0x, p0y, p0z, cx, cy, cz);
+            const float sx = __fadd_rn(__fadd_rn(p0x, p1x), p2x);
+            const float sy = __fadd_rn(__fadd_rn(p0y, p1y), p2y);
+            const float sz = __fadd_rn(__fadd_rn(p0z, p1z), p2z);
+            sp.tri[w - base] = make_float4(dV, __fmul_rn(sx, dV), __fmul_rn(sy, dV), __fmul_rn(sz, dV));
+            // Second moments of the tetrahedron (origin, p0, p1, p2): dV/120 * (s s^T + sum p p^T).  No reference arithmetic
+            // to match here (PhysX is absent): fused multiply-adds are fine, unlike in dV and the
+            // first moments above.
+            cov[0] = fmaf(dV, fmaf(sx, sx, fmaf(p2x, p2x, fmaf(p1x, p1x, p0x * p0x))), cov[0]);
+            cov[1] = fmaf(dV, fmaf(sy, sy, fmaf(p2y, p2y, fmaf(p1y, p1y, p0y * p0y))), cov[1]);
+            cov[2] = fmaf(dV, fmaf(sz, sz, fmaf(p2z, p2z, fmaf(p1z, p1z, p0z * p0z))), cov[2]);
+            cov[3] = fmaf(dV, fmaf(sx, sy, fmaf(p2x, p2y, fmaf(p1x, p1y, p0x * p0y))), cov[3]);
+            cov[4] = fmaf(dV, fmaf(sx, sz, fmaf(p2x, p2z, fmaf(p1x, p1z, p0x * p0z))), cov[4]);
+            cov[5] = fmaf(dV, fmaf(sy, sz, fmaf(p2y, p2z, fmaf(p1y, p1z, p0y * p0z))), cov[5]);
+            cov[6] += dV;
+            cov[7] = fmaf(dV, sx, cov[7]); cov[8] = fmaf(dV, sy, cov[8]); cov[9] = fmaf(dV, sz, cov[9]);
         }
         sub.sync();
         if (sub.sl < 4)
