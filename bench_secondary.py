@@ -306,6 +306,30 @@ def config3(args, torch, ctx, synth, flush, stream, reps: int = 120):
         ctx.fracture_event()
         ctx.download_packed()
         t.append(time.perf_counter() - t0)
+    # the same through the one-blob wire format with PINNED host buffers: upload blob -> event -> download blob -> sync
+    from surtr_b200 import FractureContext
+    sizes, total = FractureContext.fill_input_blob(None, pieces, cells)
+    h_in = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    FractureContext.fill_input_blob(h_in.numpy(), pieces, cells)
+    al = lambda x: (int(x) + 255) // 256 * 256
+    cap = al(64 * int(c.n_fragments)) + al(12 * int(c.n_verts)) + al(int(c.n_verts)) + al(2 * int(c.n_ring)) + 4096
+    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    tb, L = [], None
+    for i in range(23):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.upload_blob_ptr(h_in.data_ptr(), sizes)
+        ctx.fracture_event()
+        L = ctx.download_blob_into_async(h_out.data_ptr(), cap)
+        ctx.sync()
+        if i >= 3:
+            tb.append(time.perf_counter() - t0)
+    got = FractureContext.unpack_output_blob(h_out.numpy(), L)
+    assert got.rec.tobytes() == fr.rec.tobytes() and got.verts.tobytes() == fr.verts.tobytes() and np.array_equal(got.ring, fr.ring), \
+        "config3: the blob round trip differs from the resident-input result"
+    ctx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring)   # (leave the context as the callers expect it)
+    ctx.upload_cells(cells.planes, cells.plane_off, cells.verts, cells.vert_off)
     return {"workload": "config3: 10000 Voronoi pieces (mt19937(1234)) x 256 Voronoi cells (mt19937(46354)), one event",
             "pairs": int(c.n_pairs), "candidates": int(c.n_candidates), "fragments": int(c.n_fragments),
             "tier2_pairs": int(c.n_tier2), "tier3_pairs": int(c.n_tier3),
@@ -313,9 +337,13 @@ def config3(args, torch, ctx, synth, flush, stream, reps: int = 120):
             "reps": reps, "fragments_per_s": int(c.n_fragments) / (float(np.median(ms)) * 1e-3),
             "kernel_ms": {k: round(v, 4) for k, v in ph.items()},
             "e2e_sync_event_ms": 1e3 * float(np.median(t)),
+            "e2e_blob_event_ms": {"p50": 1e3 * float(np.median(tb)), "min": 1e3 * float(np.min(tb)), "reps": len(tb),
+                                  "h2d_bytes": int(total), "d2h_bytes": int(L.total)},
             "sum_volume": float(np.sum(fr.rec["volume"])),
             "timing": "CUDA events on the context stream around the whole event, inputs resident, 160 MiB L2 flush before every event (outside the events); "
-                      "e2e_sync_event_ms = pageable host arrays in, event, pageable host arrays out, wall clock"}
+                      "e2e_sync_event_ms = pageable host arrays in, event, pageable host arrays out, wall clock; e2e_blob_event_ms = one pinned blob up "
+                      "(surtr_upload_blob), event, one pinned blob down (surtr_download_blob_async), sync: wall clock of the blocking caller, L2 flushed "
+                      "before each, result checked against the resident-input fragments bit for bit"}
 
 
 def config2(args, torch, dev, local, ctx, synth, flush, stream, n_streams: int = 12, depth: int = 6):
@@ -460,10 +488,7 @@ def config5(args, torch, local, rank, world, ctx, synth, stream, barrier, allred
             cc = ctx.counts()
             dev_ms += ctx.last_event_ms()[0]
             counts.append(int(cc.n_fragments))
-            rec = ctx.download(geometry=False).rec
-            ev_of = (rec["cell"] // seeds_per_level).astype(np.int64)
-            new_ev = np.concatenate([[0], np.cumsum(np.bincount(ev_of, minlength=n_obj))]).astype(np.uint32)
-            ctx.fragments_to_pieces(new_ev)
+            ctx.fragments_to_pieces_per_event()   # object o keeps its fragments: boundaries found on the device
         return dev_ms, counts
 
     recurse()
@@ -487,5 +512,6 @@ def config5(args, torch, local, rank, world, ctx, synth, stream, barrier, allred
             "device_ms_max_over_ranks": dev_max, "wall_ms_max_over_ranks": 1e3 * wall_max,
             "final_fragments_per_s_device": final / (dev_max * 1e-3), "fragments_all_levels_per_s_device": allf / (dev_max * 1e-3),
             "final_fragments_per_s_wall": final / wall_max,
-            "timing": "device = sum of the three events' CUDA-event times; wall = whole recursion incl. the host regrouping of fragments by object "
-                      "(records down, offsets up) between levels; median of 3, max over ranks"}
+            "timing": "device = sum of the three events' CUDA-event times; wall = whole recursion incl. the pattern uploads and the regrouping of fragments by object "
+                      "(surtr_fragments_to_pieces_per_event: the boundaries are found on the device, 4 bytes per object come back) "
+                      "between levels; median of 3, max over ranks"}

@@ -121,6 +121,11 @@ int surtr_upload_cells3(surtr_ctx* ctx, const float* planes4, const uint32_t* pl
  * copy through the host).  Every fragment becomes one piece; ev_piece_off (host, n_events+1) regroups them, or
  * NULL to keep one event. */
 int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events);
+/* The same with the grouping the recursion of the reference keeps (a compound's fragments stay with the compound,
+ * Src/Surtr.cpp:2133-2146 binds every result to the object that was hit): the fragments of event e become the pieces
+ * of event e.  The event boundaries are found on the device from the records' cell ids (fragments come in (event,
+ * cell, piece) order); n_events + 1 words cross the bus instead of every fragment record. */
+int surtr_fragments_to_pieces_per_event(surtr_ctx* ctx);
 
 /* World transform of the resident pieces, in place: replaces the host loop of Surtr::ExecuteFractureRoutine
  * (Src/Surtr.cpp:1846-1852) that runs Poly::Transform (Src/Poly.cpp:580-585) over every piece before DoFracture.

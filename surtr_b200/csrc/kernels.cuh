@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(256) widen3_kernel(const float* __restrict__ i
 }
 
 // surtr_upload_blob: the compact input blob -> the resident arrays, one launch.  Both float3 streams (pieces, cell
-// vertices) are widened to float4; the ring offsets are rebuilt from one LENGTH byte per vertex (a warp per piece: its
-// first ring entry comes with the blob, the rest is a warp prefix sum); RB = 1: the ring entries travel as bytes (every
+// vertices) are widened to float4; the ring offsets are rebuilt from one LENGTH byte per vertex (eight lanes per piece: its
+// first ring entry comes with the blob, the rest is a prefix sum); RB = 1: the ring entries travel as bytes (every
 // piece has at most 256 vertices) and are widened to the resident 16-bit entries.
 template <int RB>
 __global__ void __launch_bounds__(256) expand_blob_kernel(const float* __restrict__ a3, float4* __restrict__ a4, uint64_t na,
@@ -193,20 +193,31 @@ __global__ void __launch_bounds__(256) expand_blob_kernel(const float* __restric
         if (i < na) a4[i] = make_float4(__ldg(a3 + 3 * i), __ldg(a3 + 3 * i + 1), __ldg(a3 + 3 * i + 2), 0.f);
         else { const uint64_t j = i - na; b4[j] = make_float4(__ldg(b3 + 3 * j), __ldg(b3 + 3 * j + 1), __ldg(b3 + 3 * j + 2), 0.f); }
     }
-    const int lane = threadIdx.x & 31;
-    for (uint64_t p = t0 >> 5; p < n_pieces; p += stride >> 5)
+    // ring offsets: 8 lanes per piece (four pieces per warp: the pieces of the BASELINE configs have 8-60 vertices), an
+    // 8-wide prefix sum of the length bytes per round; the trip count is the warp's largest piece (full-mask shuffles)
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    for (uint64_t pw = (t0 >> 5) * 4; pw < n_pieces; pw += (stride >> 5) * 4)
     {
-        const uint32_t v0 = vert_off[p], v1 = vert_off[p + 1];
-        uint32_t run = ring_base[p];
-        for (uint32_t v = v0; v < v1; v += 32)   // (v0 and v1 are warp-uniform)
+        const uint64_t p = pw + (uint64_t)(lane >> 3);
+        const bool have = p < n_pieces;
+        const uint32_t v0 = have ? vert_off[p] : 0u, v1 = have ? vert_off[p + 1] : 0u;
+        uint32_t run = have ? ring_base[p] : 0u;
+        const uint32_t nmax = __reduce_max_sync(FULL, v1 - v0);
+        for (uint32_t i = 0; i < nmax; i += 8)
         {
-            const uint32_t len = v + lane < v1 ? ring_len[v + lane] : 0u;
-            int tot;
-            const uint32_t ex = (uint32_t)warp_exscan((int)len, lane, tot);
-            if (v + lane < v1) ring_off[v + lane] = run + ex;
-            run += (uint32_t)tot;
+            const uint32_t v = v0 + i + (uint32_t)sl;
+            const uint32_t len = v < v1 ? ring_len[v] : 0u;
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o, 8);
+                if (sl >= o) inc += t;
+            }
+            if (v < v1) ring_off[v] = run + inc - len;
+            run += __shfl_sync(FULL, inc, 7, 8);
         }
-        if (p + 1 == n_pieces && lane == 0) ring_off[v1] = ring_base[n_pieces];
+        if (have && p + 1 == n_pieces && sl == 0) ring_off[v1] = ring_base[n_pieces];
     }
     if (n_pieces == 0 && t0 == 0) ring_off[0] = 0u;
     if (RB == 1)
@@ -1412,6 +1423,26 @@ __global__ void fragments_vert_off_kernel(const surtr_fragment* f, uint32_t n, u
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vert_off[i] = f[i].vert_off;
     if (i == n) vert_off[n] = n_verts;
+}
+
+// surtr_fragments_to_pieces_per_event: first fragment of every event.  The fragment records are in (event, cell,
+// piece) order and the events own consecutive cell ranges, so record i belongs to event e iff ev_cell_off[e] <=
+// f[i].cell < ev_cell_off[e + 1]: one lower bound per event over the records' cell ids (strided 64-byte reads, log2 n
+// steps; 4096 events x 23 steps for the deepest level of BASELINE config 5).
+__global__ void event_fragment_off_kernel(const surtr_fragment* __restrict__ f, uint32_t n, const uint32_t* __restrict__ ev_cell_off,
+                                          uint32_t n_events, uint32_t* __restrict__ ev_frag_off)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n_events) return;
+    if (e == n_events) { ev_frag_off[e] = n; return; }
+    const uint32_t c0 = ev_cell_off[e];
+    uint32_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (f[mid].cell < c0) lo = mid + 1; else hi = mid;
+    }
+    ev_frag_off[e] = lo;
 }
 
 // ------------------------------------------------------------------------------- Kdop::Calc(Polyhedron)

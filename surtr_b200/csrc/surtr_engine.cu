@@ -101,7 +101,7 @@ struct surtr_ctx
     uint32_t pat_faces = 0, pat_cells = 0, pat_fverts = 0;
 
     // derived tables
-    DevBuf d_tiles, d_ev_mask_base, d_ev_piece_off, d_ev_cell_off;
+    DevBuf d_tiles, d_ev_mask_base, d_ev_piece_off, d_ev_cell_off, d_ev_frag_off;
     uint32_t n_tiles = 0, n_masks = 0;
     uint64_t n_pairs = 0;
 
@@ -643,7 +643,7 @@ void surtr_ctx_destroy(surtr_ctx* ctx)
                       &ctx->d_ev_cell_off, &ctx->ext_p, &ctx->ext_c, &ctx->masks, &ctx->cand, &ctx->cand_rec,
                       &ctx->scratch1, &ctx->scratch2, &ctx->scratch3, &ctx->ws3, &ctx->ovf_list, &ctx->ovf2_list, &ctx->ovf3_list, &ctx->fail_list, &ctx->ctl, &ctx->dbg, &ctx->out_off, &ctx->f_rec, &ctx->f_verts,
                       &ctx->f_ring_off, &ctx->f_ring, &ctx->wire_p3, &ctx->wire_c3, &ctx->wire_f3, &ctx->wire_flen, &ctx->in_blob, &ctx->out_blob, &ctx->frag_cand, &ctx->pat_verts, &ctx->pat_face_off, &ctx->pat_xform, &ctx->xf_mat,
-                      &ctx->xf_idx };
+                      &ctx->xf_idx, &ctx->d_ev_frag_off };
     for (DevBuf* b : all) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -909,7 +909,7 @@ int surtr_upload_blob(surtr_ctx* ctx, const void* blob, uint32_t n_pieces, uint6
     CK(cudaMemcpyAsync(ctx->in_blob.p, blob, L.total, cudaMemcpyHostToDevice, ctx->stream));
     unsigned char* d = ctx->in_blob.as<unsigned char>();
     if (ring_entry_bytes == 2) ctx->p_ring.set_view(d + L.ring, 2 * n_piece_ring);
-    const uint64_t work = std::max<uint64_t>(n_piece_verts + n_cell_verts, std::max<uint64_t>((uint64_t)n_pieces * 32, n_piece_ring / 16));
+    const uint64_t work = std::max<uint64_t>(n_piece_verts + n_cell_verts, std::max<uint64_t>((uint64_t)n_pieces * 8, n_piece_ring / 16));
     const unsigned blocks = (unsigned)std::min<uint64_t>((work + 255) / 256 + 1, (uint64_t)ctx->num_sm * 8);
     auto kern = ring_entry_bytes == 1 ? expand_blob_kernel<1> : expand_blob_kernel<2>;
     kern<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + L.verts3), ctx->p_verts.as<float4>(), n_piece_verts,
@@ -1111,18 +1111,12 @@ int surtr_download_pieces(surtr_ctx* ctx, float* verts4)
     return SURTR_OK;
 }
 
-int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events)
+namespace
 {
-    if (!ctx) return SURTR_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
-    const int rc = resolve_event(ctx);
-    if (rc) return rc;
+// the last event's fragment arrays become the piece arrays (buffers swapped, vert_off table rebuilt from the records)
+int fragments_to_pieces_impl(surtr_ctx* ctx, uint32_t n, std::vector<uint32_t>& layout)
+{
     const surtr_counts c = ctx->last;
-    if (c.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
-    const uint32_t n = (uint32_t)c.n_fragments;
-    std::vector<uint32_t> layout;
-    if (!make_layout(ev_piece_off, n_events, n, layout))
-        return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off must start at 0, be non-decreasing and end at the fragment count");
     CK(ctx->p_vert_off.reserve(4 * ((size_t)n + 1)));
     fragments_vert_off_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->f_rec.as<surtr_fragment>(), n, (uint32_t)c.n_verts,
                                                                              ctx->p_vert_off.as<uint32_t>());
@@ -1146,6 +1140,46 @@ int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint
     ctx->tables_dirty = true;
     ctx->event_launched = false;
     return SURTR_OK;
+}
+} // namespace
+
+int surtr_fragments_to_pieces(surtr_ctx* ctx, const uint32_t* ev_piece_off, uint32_t n_events)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    if (ctx->last.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
+    const uint32_t n = (uint32_t)ctx->last.n_fragments;
+    std::vector<uint32_t> layout;
+    if (!make_layout(ev_piece_off, n_events, n, layout))
+        return fail(ctx, SURTR_ERR_INVALID, "ev_piece_off must start at 0, be non-decreasing and end at the fragment count");
+    return fragments_to_pieces_impl(ctx, n, layout);
+}
+
+int surtr_fragments_to_pieces_per_event(surtr_ctx* ctx)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int rc = resolve_event(ctx);
+    if (rc) return rc;
+    if (ctx->last.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
+    const uint32_t n = (uint32_t)ctx->last.n_fragments;
+    const uint32_t ne = (uint32_t)ctx->h_ev_cell_off.size() - 1;   // the event layout the fragments were cut under
+    // event boundaries in the fragment list, found on the device (the records never travel): n_events + 1 words come back
+    CK(ctx->d_ev_frag_off.reserve(8 * ((size_t)ne + 1)));
+    uint32_t* d_cell_off = ctx->d_ev_frag_off.as<uint32_t>();
+    uint32_t* d_frag_off = d_cell_off + ne + 1;
+    CK(cudaMemcpyAsync(d_cell_off, ctx->h_ev_cell_off.data(), 4 * ((size_t)ne + 1), cudaMemcpyHostToDevice, ctx->stream));
+    event_fragment_off_kernel<<<(ne + 1 + 127) / 128, 128, 0, ctx->stream>>>(ctx->f_rec.as<surtr_fragment>(), n, d_cell_off, ne, d_frag_off);
+    CK(cudaGetLastError());
+    std::vector<uint32_t> layout((size_t)ne + 1);
+    CK(cudaMemcpyAsync(layout.data(), d_frag_off, 4 * ((size_t)ne + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> checked;
+    if (!make_layout(layout.data(), ne, n, checked))
+        return fail(ctx, SURTR_ERR_INVALID, "fragment records are not grouped by event");
+    return fragments_to_pieces_impl(ctx, n, checked);
 }
 
 int surtr_kdop_calc(surtr_ctx* ctx, const float* verts4, uint32_t n_verts, const float* normals3, uint32_t k, float* dist,

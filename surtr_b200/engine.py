@@ -29,7 +29,7 @@ assert FRAGMENT_DTYPE.itemsize == 64
 # every symbol include/surtr_b200.h declares
 EXPORTS = [
     "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions",
-    "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fracture_event",
+    "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fragments_to_pieces_per_event", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
     "surtr_upload_pattern", "surtr_place_pattern", "surtr_download_fragments_async", "surtr_sync",
@@ -90,6 +90,7 @@ def load_library():
     lib.surtr_download_fragments_packed.argtypes = [vp, vp, vp, vp, vp]
     lib.surtr_download_fragments_packed_async.argtypes = [vp, vp, vp, vp, vp]
     lib.surtr_fragments_to_pieces.argtypes = [vp, vp, u32]
+    lib.surtr_fragments_to_pieces_per_event.argtypes = [vp]
     lib.surtr_upload_pattern.argtypes = [vp, vp, vp, u32, vp, u32]
     lib.surtr_place_pattern.argtypes = [vp, vp, vp, u32]
     lib.surtr_fracture_event.argtypes = [vp]
@@ -235,6 +236,10 @@ class FractureContext:
     def fragments_to_pieces(self, ev_piece_off=None):
         ev = _arr(ev_piece_off, np.uint32)
         self._ck(self._lib.surtr_fragments_to_pieces(self._h, _p(ev), 0 if ev is None else len(ev) - 1))
+
+    def fragments_to_pieces_per_event(self):
+        """The fragments of event e become the pieces of event e (event boundaries found on the device)."""
+        self._ck(self._lib.surtr_fragments_to_pieces_per_event(self._h))
 
     def fracture_event(self):
         self._ck(self._lib.surtr_fracture_event(self._h))

@@ -104,6 +104,54 @@ def test_config5_recursive_refracture(ctx):
     assert got.n == 1620
 
 
+def test_fragments_to_pieces_per_event_matches_host_regrouping(ctx):
+    """surtr_fragments_to_pieces_per_event (event boundaries found on the device) against surtr_fragments_to_pieces with
+    the boundaries the host derives from the downloaded records: three events of different size -- the middle one's
+    piece lies outside every cell, so it has no fragments at all -- then one more level on both piece sets; every array
+    of the second level must be identical, and equal the oracle's."""
+    from surtr_b200 import FractureContext
+    cube = common.unit_cube()
+    far = common.PolySet(cube.verts + np.array([10, 0, 0, 0], np.float32), cube.vert_off, cube.ring_off, cube.ring)
+    pieces, ev_p = common.concat([cube, far, cube])
+    c0, c1, c2 = common.voronoi(46354, 64), common.voronoi(777, 8), common.voronoi(1001, 24)
+    cells, ev_c = common.concat([c0, c1, c2])
+    nxt, ev_n = common.concat([common.voronoi(1002, 16), common.voronoi(1003, 5), common.voronoi(1004, 40)])
+    other = FractureContext(0)
+    try:
+        results = []
+        for cx, per_event in ((ctx, True), (other, False)):
+            cx.upload_pieces(pieces.verts, pieces.vert_off, pieces.ring_off, pieces.ring, ev_p)
+            cx.upload_cells(cells.planes, cells.plane_off, cells.verts, cells.vert_off, ev_c)
+            cx.fracture_event()
+            rec = cx.download(geometry=False).rec
+            ev_of = np.searchsorted(np.asarray(ev_c, np.int64), rec["cell"].astype(np.int64), side="right") - 1
+            per_ev = np.bincount(ev_of, minlength=3)
+            assert per_ev[0] == 64 and per_ev[1] == 0 and per_ev[2] == 24
+            if per_event:
+                cx.fragments_to_pieces_per_event()
+            else:
+                cx.fragments_to_pieces(np.concatenate([[0], np.cumsum(per_ev)]).astype(np.uint32))
+            cx.upload_cells(nxt.planes, nxt.plane_off, nxt.verts, nxt.vert_off, ev_n)
+            cx.fracture_event()
+            results.append(cx.download())
+        a, b = results
+        assert a.n == b.n and a.n > 0
+        assert a.rec.tobytes() == b.rec.tobytes()
+        assert a.verts.tobytes() == b.verts.tobytes() and a.ring_off.tobytes() == b.ring_off.tobytes() and a.ring.tobytes() == b.ring.tobytes()
+        # and against the oracle: level 1 of events 0 and 2, then level 2
+        f0 = 0
+        for cube_cells, level2 in ((c0, common.voronoi(1002, 16)), (c2, common.voronoi(1004, 40))):
+            lvl1 = P.apply_fracture(cube, cube_cells.planes, cube_cells.plane_off)
+            want = P.apply_fracture(lvl1, level2.planes, level2.plane_off)
+            sl = slice(f0, f0 + want.n)
+            assert np.array_equal(a.rec["n_verts"][sl], want.nverts) and np.array_equal(a.rec["n_faces"][sl], want.nfaces)
+            assert a.rec["volume"][sl].tobytes() == np.asarray(want.volume, np.float64).tobytes()
+            f0 += want.n
+        assert f0 == a.n
+    finally:
+        other.close()
+
+
 def test_edge_cases(ctx):
     cube = common.unit_cube()
     cells = common.voronoi(46354, 64)
