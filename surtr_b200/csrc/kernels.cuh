@@ -10,6 +10,7 @@
 
 #include "clip_sub.cuh"
 #include "clip_fast.cuh"
+#include "clip_duo.cuh"
 #include "clip_global.cuh"
 
 #include <type_traits>
@@ -993,6 +994,186 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(
             fast_pair<G, LIST>(a, sp, a.ovf_list[it], lane);
             __syncwarp();
         }
+    }
+}
+
+// K3, small tier, TWO pairs per warp (clip_duo.cuh): lanes 0-15 stage, clip and write candidate q, lanes 16-31 candidate
+// q + 1 -- neighbours in the candidate list are neighbouring pieces against the same cell, so both halves read the same
+// planes and tend to cut equally often.  Staging, status handling and the result blob are fast_pair's; every
+// collective is executed by the whole warp.
+__device__ __forceinline__ void duo_pair(const ClipArgs& a, FastPoly<2>& sp, uint32_t q, bool act, int lane)
+{
+    constexpr int S = 64;
+    const int sl = lane & (DUO_L - 1), shift = lane & DUO_L;
+    uint2 pr = make_uint2(0u, 0u);
+    uint32_t v0 = 0, pl0 = 0;
+    int nv = 0, npl = 0;
+    if (act)
+    {
+        pr = a.cand[q];
+        v0 = a.p_vert_off[pr.x];
+        nv = (int)(a.p_vert_off[pr.x + 1] - v0);
+        pl0 = a.c_plane_off[pr.y];
+        npl = (int)(a.c_plane_off[pr.y + 1] - pl0);
+    }
+    const int nv_in = nv;
+    bool bad = nv > S;
+    uint32_t rb = 0, re = 0;
+    if (act && !bad)
+    {
+        // the piece's ring entries: one contiguous u16 stream, loaded coalesced and staged as bytes in old_ring (fast_pair)
+        uint8_t* stage = reinterpret_cast<uint8_t*>(sp.old_ring);
+        rb = __ldg(a.p_ring_off + v0); re = __ldg(a.p_ring_off + v0 + nv);
+        int ne = (int)(re - rb);
+        if (re < rb || ne > 8 * S) { bad = true; ne = 0; }
+#pragma unroll 4
+        for (int e = sl; e < ne; e += DUO_L)
+        {
+            const int idx = __ldg(a.p_ring + rb + e);
+            bad = bad || idx >= nv;
+            stage[e] = (uint8_t)idx;
+        }
+    }
+    __syncwarp();
+    if (act && nv <= S)
+    {
+        const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(sp.old_ring);
+#pragma unroll 2
+        for (int g = 0; g < DUO_G; g++)
+        {
+            const int v = sl + DUO_L * g;
+            if (v < nv)
+            {
+                const float4 pp = __ldg(a.p_verts + v0 + v);
+                const uint32_t r0 = __ldg(a.p_ring_off + v0 + v), r1 = __ldg(a.p_ring_off + v0 + v + 1);
+                sp.x[v] = pp.x; sp.y[v] = pp.y; sp.z[v] = pp.z;
+                const int d = (int)(r1 - r0);
+                const uint32_t o = r0 - rb;
+                u64 rw = ~0ull;
+                if (r0 < rb || r1 > re || d > 8 || d <= 0) bad = true;
+                else
+                {
+                    // eight bytes from byte offset o (unaligned): three aligned words through the funnel shifter (the read may
+                    // run up to 11 bytes past the stream's end, still inside this FastPoly)
+                    const uint32_t w0 = stage32[o >> 2], w1 = stage32[(o >> 2) + 1], w2 = stage32[(o >> 2) + 2];
+                    const unsigned sh = (o & 3u) * 8u;
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi2 = __funnelshift_r(w1, w2, sh);
+                    rw = (u64)lo | ((u64)hi2 << 32);
+                    if (d < 8) rw |= ~0ull << (8 * d);
+                }
+                sp.ring[v] = rw;
+            }
+        }
+    }
+    bad = duo_half(__ballot_sync(FULL, bad), shift) != 0u;
+    __syncwarp();   // old_ring is free again (duo_seq_cut snapshots into it)
+    float box[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) box[k] = a.ext_p && act ? __ldg(a.ext_p + (size_t)pr.x * 2 * a.kdirs + k) : 0.f;
+    DuoResult R;
+    duo_clip_by_planes(sp, act && !bad, nv, a.c_planes + pl0, npl, box, a.ext_p != nullptr, lane, R);
+    const int status = bad ? CLIP_OVERFLOW : R.status;
+    nv = R.nv;
+    CandRec* rec = a.rec + q;
+    if (act && a.dbg && sl == 0)
+    {
+        uint32_t* d = a.dbg + (size_t)q * 8;
+        d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 0;
+        d[4] = R.seq_cuts; d[5] = R.n_cuts; d[6] = (uint32_t)nv_in; d[7] = (uint32_t)npl;
+    }
+    const bool wr = act && status == CLIP_OK && nv > 0;
+    __syncwarp();
+    // result blob, renumbered to the reference's final order (rank in the live mask), as fast_pair writes it:
+    // float4 verts[64] | u16 ring_start[64] | u8 ring[packed]
+    const unsigned long long blob = (unsigned long long)q * FAST_BLOB_BYTES;
+    unsigned char* b = a.scratch1 + blob;
+    float4* bv = reinterpret_cast<float4*>(b);
+    uint16_t* bo = reinterpret_cast<uint16_t*>(b + 64 * 16);
+    uint8_t* br = b + 64 * 18;
+    const int hw = wr ? R.hi : 0;
+    const int himax = max(hw, __shfl_xor_sync(FULL, hw, DUO_L));
+#pragma unroll
+    for (int g = 0; g < DUO_G; g++)
+    {
+        const int v = sl + DUO_L * g;
+        if ((g == 0 || himax > DUO_L * g) && wr && duo_own(R.live, g, sl)) sp.id[v] = (uint8_t)mrank<2>(R.live, v);
+    }
+    __syncwarp();
+    int ne = 0;
+#pragma unroll
+    for (int g = 0; g < DUO_G; g++)
+    {
+        if (g == 0 || himax > DUO_L * g)   // warp-uniform
+        {
+            const int v = sl + DUO_L * g;
+            const bool lv = wr && duo_own(R.live, g, sl);
+            const u64 rw = lv ? sp.ring[v] : ~0ull;
+            const int d = rdeg(rw);
+            int inc = d;
+#pragma unroll
+            for (int o = 1; o < DUO_L; o <<= 1)
+            {
+                const int t = __shfl_up_sync(FULL, inc, o, DUO_L);
+                if (sl >= o) inc += t;
+            }
+            const int off = ne + inc - d;
+            ne += __shfl_sync(FULL, inc, DUO_L - 1, DUO_L);
+            if (lv)
+            {
+                const int t = sp.id[v];
+                bv[t] = make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+                bo[t] = (uint16_t)off;
+#pragma unroll 1
+                for (int j = 0; j < d; j++) br[off + j] = sp.id[rget(rw, j)];
+            }
+            __syncwarp();
+        }
+    }
+    if (wr && sl == 0)
+    {
+        rec->nv = (uint32_t)nv;
+        rec->ne = (uint32_t)ne;
+        rec->nf = 0;
+        rec->tier = 1;
+        rec->blob = blob;
+    }
+    if (act && R.seq_cuts && sl == 0) atomicAdd(&a.ctl->n_seq_cuts, R.seq_cuts);
+    if (act && sl == 0)
+    {
+        if (status != CLIP_OK)
+        {
+            // too large for this tier (or a ring outgrew 8 slots): hand the pair on
+            rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 0;
+            if (nv_in > T2_CAP) a.ovf3_list[atomicAdd(&a.ctl->n_ovf3, 1u)] = q;
+            else if (a.skip_tier1b) a.ovf2_list[atomicAdd(&a.ctl->n_ovf2, 1u)] = q;
+            else a.ovf_list[atomicAdd(&a.ctl->n_ovf, 1u)] = q;
+        }
+        else if (nv == 0) { rec->nv = 0; rec->ne = 0; rec->nf = 0; rec->tier = 1; }
+    }
+}
+
+// Resident warps, two candidates per warp and ticket (see clip_fast_kernel for the launch shape).
+__global__ void __launch_bounds__(FAST_PERSIST_WARPS * 32, 32 / FAST_PERSIST_WARPS) clip_duo_kernel(ClipArgs a)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ FastPoly<2> s_poly[FAST_PERSIST_WARPS][2];
+    const int lane = threadIdx.x & 31;
+    FastPoly<2>& sp = s_poly[threadIdx.x >> 5][lane >> 4];
+    const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long n_items = a.ctl->n_cand;
+    if (n_items > a.cap_cand) n_items = a.cap_cand;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    const bool more = 2ull * nw < n_items;
+    unsigned long long q0 = 2ull * wid;
+    while (q0 < n_items)
+    {
+        unsigned next = 0x7fffffffu;
+        if (more && lane == 0) next = nw + atomicAdd(&a.ctl->k3_ticket, 1u);
+        const unsigned long long q = q0 + (unsigned)(lane >> 4);
+        duo_pair(a, sp, (uint32_t)q, q < n_items, lane);
+        __syncwarp();
+        q0 = 2ull * __shfl_sync(FULL, next, 0);
     }
 }
 

@@ -137,6 +137,7 @@ struct surtr_ctx
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
     uint32_t last_ring_bytes = 2; // ring entry width of the last event's output blob (surtr_download_blob_async)
     int k3_warps = 0;             // small tier's main launch: 0 = persistent warps + ticket (default); SURTR_K3_WARPS=2: one block of two pairs per two candidates (A/B)
+    bool k3_duo = false;          // SURTR_K3_DUO=1: two candidate pairs per warp (clip_duo.cuh)
     bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
     bool tier3_enabled = false;   // likewise the global-memory tier
@@ -378,6 +379,10 @@ int launch_event(surtr_ctx* ctx)
         constexpr uint64_t pairs_per_block = FAST_WARPS * 32 / FAST_LANES;
         const uint64_t blocks = std::max<uint64_t>(1, (ctx->cap_cand + pairs_per_block - 1) / pairs_per_block);
         if (ctx->k3_round1) launch_pdl(clip_sub_kernel<FAST_LANES>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
+        else if (ctx->k3_duo)
+            launch_pdl(clip_duo_kernel,
+                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + 2 * FAST_PERSIST_WARPS - 1) / (2 * FAST_PERSIST_WARPS)), (uint64_t)ctx->num_sm * (32 / FAST_PERSIST_WARPS))),
+                       dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
         else if (ctx->k3_warps == 0)
             launch_pdl(clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true>,
                        dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * (32 / FAST_PERSIST_WARPS))),
@@ -628,6 +633,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
     if (const char* e = std::getenv("SURTR_K3")) ctx->k3_round1 = std::string(e) == "sub";
     if (const char* e = std::getenv("SURTR_DEBUG_NO_TIER1B")) ctx->no_tier1b = e[0] == '1';
     if (const char* e = std::getenv("SURTR_K3_WARPS")) ctx->k3_warps = e[0] == '2' ? 2 : 0;
+    if (const char* e = std::getenv("SURTR_K3_DUO")) ctx->k3_duo = e[0] == '1';
     *out = ctx;
     return SURTR_OK;
 }

@@ -12,6 +12,7 @@
 #define __noinline__ __attribute__((noinline))
 #include "../../surtr_b200/csrc/clip_sub.cuh"
 #include "../../surtr_b200/csrc/clip_fast.cuh"
+#include "../../surtr_b200/csrc/clip_duo.cuh"
 #include "../../surtr_b200/csrc/clip_global.cuh"
 #undef __noinline__
 
@@ -25,7 +26,8 @@ void k3emu_set_schedule(unsigned mode) { simt::schedule() = mode; }
 }   // extern "C"
 
 // Which small-tier clipper k3emu_pair runs: 2 / 4 = fast_clip_by_planes<G> of clip_fast.cuh (64 / 128 vertex slots: the
-// kernels that ship, clip_fast_kernel<2,false> and <4,true>), 0 = sub_clip_by_planes<32> of clip_sub.cuh (round 1).
+// kernels that ship, clip_fast_kernel<2,false> and <4,true>), 16 = duo_clip_by_planes of clip_duo.cuh (two pairs per warp,
+// clip_duo_kernel), 0 = sub_clip_by_planes<32> of clip_sub.cuh (round 1).
 static int g_variant = 2;
 extern "C" void k3emu_set_variant(int v) { g_variant = v; }
 
@@ -121,6 +123,152 @@ static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const ui
     return 0;
 }
 
+// The two-pairs-per-warp clipper (duo_clip_by_planes of clip_duo.cuh, clip_duo_kernel).  The pair handed in shares the
+// emulated warp with the pair of the PREVIOUS call (alternating between the lower and the upper half), so every pair is
+// cut twice -- next to two different neighbours, once in each half -- and the second result must equal the first bit for
+// bit; the caller compares the first with the oracle.  Staging and write-out restate duo_pair (kernels.cuh).
+namespace
+{
+struct DuoCase
+{
+    bool valid = false;
+    std::vector<float> verts4;
+    std::vector<uint32_t> ring_off;
+    std::vector<uint16_t> ring;
+    std::vector<float4> planes;
+    int nv_in = 0, npl = 0;
+    // result
+    int status = 0, nv = 0, ne = 0;
+    unsigned seq = 0, cuts = 0;
+    std::vector<float> out_verts4;
+    std::vector<uint32_t> out_ring_off;
+    std::vector<uint16_t> out_ring;
+};
+DuoCase g_duo_prev;
+unsigned g_duo_calls = 0;
+
+bool duo_stage(const DuoCase& c, FastPoly<2>& sp, float (&box)[6])
+{
+    bool bad = c.nv_in > 64;
+    if (!bad)
+        for (int v = 0; v < c.nv_in; v++)
+        {
+            const int d = (int)(c.ring_off[v + 1] - c.ring_off[v]);
+            sp.x[v] = c.verts4[4 * v]; sp.y[v] = c.verts4[4 * v + 1]; sp.z[v] = c.verts4[4 * v + 2];
+            u64 rw = ~0ull;
+            if (d > 8 || d == 0) bad = true;
+            else
+                for (int j = 0; j < d; j++)
+                {
+                    const int idx = c.ring[c.ring_off[v] + j];
+                    bad = bad || idx >= c.nv_in;
+                    rw = rset(rw, j, idx);
+                }
+            sp.ring[v] = rw;
+        }
+    const float big = 3.402823466e+38f;
+    box[0] = box[2] = box[4] = big; box[1] = box[3] = box[5] = -big;
+    for (int v = 0; v < c.nv_in; v++)
+        for (int k = 0; k < 3; k++)
+        {
+            box[2 * k] = std::min(box[2 * k], c.verts4[4 * v + k]);
+            box[2 * k + 1] = std::max(box[2 * k + 1], c.verts4[4 * v + k]);
+        }
+    return !bad;
+}
+
+// write-out of duo_pair: final number of a live slot = its rank in the live mask
+int duo_write(DuoCase& c, const FastPoly<2>& sp, const DuoResult& R)
+{
+    c.status = R.status; c.nv = 0; c.ne = 0; c.seq = R.seq_cuts; c.cuts = R.n_cuts;
+    c.out_verts4.assign(64 * 4, 0.f); c.out_ring_off.assign(65, 0u); c.out_ring.assign(512, 0);
+    if (R.status != CLIP_OK || R.nv == 0) return 0;
+    int ne = 0, n = 0;
+    for (int v = 0; v < R.hi; v++)
+    {
+        if (!mbit<2>(R.live, v)) continue;
+        const int t = mrank<2>(R.live, v);
+        if (t != n) return -2;
+        c.out_verts4[4 * t] = sp.x[v]; c.out_verts4[4 * t + 1] = sp.y[v]; c.out_verts4[4 * t + 2] = sp.z[v];
+        c.out_ring_off[t] = (uint32_t)ne;
+        const u64 rw = sp.ring[v];
+        const int d = rdeg(rw);
+        for (int j = 0; j < d; j++)
+        {
+            const int nb = rget(rw, j);
+            if (nb >= 64 || !mbit<2>(R.live, nb)) return -3;   // a ring entry that points at a dead slot
+            c.out_ring[ne++] = (uint16_t)mrank<2>(R.live, nb);
+        }
+        n++;
+    }
+    c.out_ring_off[n] = (uint32_t)ne;
+    if (n != R.nv) return -4;
+    c.nv = n; c.ne = ne;
+    return 0;
+}
+
+int duo_pair_emu(const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in, const std::vector<float4>& planes, int npl,
+                 float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring, int* out_info)
+{
+    DuoCase cur;
+    cur.valid = true;
+    cur.nv_in = nv_in; cur.npl = npl;
+    cur.verts4.assign(verts4, verts4 + 4 * (size_t)nv_in);
+    cur.ring_off.assign(ring_off, ring_off + nv_in + 1);
+    cur.ring.assign(ring, ring + ring_off[nv_in]);
+    cur.planes = planes;
+    const int hc = (int)(g_duo_calls++ & 1u);        // the half the new pair runs in; the previous pair takes the other
+    DuoCase* cs[2];
+    DuoCase again = g_duo_prev;
+    cs[hc] = &cur; cs[1 - hc] = &again;
+    auto sp = std::make_unique<FastPoly<2>[]>(2);
+    float box[2][6] = {};
+    bool act[2];
+    for (int h = 0; h < 2; h++) act[h] = cs[h]->valid && duo_stage(*cs[h], sp[h], box[h]);
+    DuoResult R[32];
+    const unsigned long n_coll = simt::run_warp([&](int lane) {
+        const int h = lane >> 4;
+        duo_clip_by_planes(sp[h], act[h], cs[h]->nv_in, cs[h]->planes.data(), cs[h]->npl, box[h], true, lane, R[lane]);
+    });
+    for (int h = 0; h < 2; h++)
+        for (int l = 1; l < 16; l++)   // uniform within a half by construction
+        {
+            const DuoResult &a = R[16 * h], &b = R[16 * h + l];
+            if (a.status != b.status || a.hi != b.hi || a.nv != b.nv || a.seq_cuts != b.seq_cuts || a.n_cuts != b.n_cuts) return -1;
+            if (a.status == CLIP_OK && a.nv > 0 && (a.live[0] != b.live[0] || a.live[1] != b.live[1])) return -1;
+        }
+    for (int h = 0; h < 2; h++)
+    {
+        if (!cs[h]->valid) continue;
+        if (!act[h]) { cs[h]->status = CLIP_OVERFLOW; cs[h]->nv = cs[h]->ne = 0; continue; }
+        const int rc = duo_write(*cs[h], sp[h], R[16 * h]);
+        if (rc) return rc;
+    }
+    if (again.valid)   // the previous pair, cut again next to a different neighbour and in the other half: the same fragment
+    {
+        const DuoCase& p = g_duo_prev;
+        if (again.status != p.status || again.nv != p.nv || again.ne != p.ne || again.seq != p.seq) return -7;
+        if (again.status == CLIP_OK && again.nv > 0 &&
+            (std::memcmp(again.out_verts4.data(), p.out_verts4.data(), 16 * (size_t)p.nv) || again.out_ring_off != p.out_ring_off || again.out_ring != p.out_ring))
+            return -7;
+    }
+    out_info[0] = cur.status;
+    out_info[3] = (int)cur.seq;
+    out_info[4] = (int)cur.cuts;
+    out_info[5] = (int)n_coll;
+    if (cur.status == CLIP_OK && cur.nv > 0)
+    {
+        std::memcpy(out_verts4, cur.out_verts4.data(), 16 * (size_t)cur.nv);
+        std::memcpy(out_ring_off, cur.out_ring_off.data(), 4 * ((size_t)cur.nv + 1));
+        std::memcpy(out_ring, cur.out_ring.data(), 2 * (size_t)cur.ne);
+        out_info[1] = cur.nv;
+        out_info[2] = cur.ne;
+    }
+    g_duo_prev = cur;
+    return 0;
+}
+} // namespace
+
 extern "C"
 {
 // One (piece, plane list) pair through the device code of the small tier.
@@ -139,7 +287,8 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     int n = 0;
     if (g_variant != 0)
     {
-        const int rc = g_variant == 4 ? fast_pair_emu<4>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
+        const int rc = g_variant == 16 ? duo_pair_emu(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
+                       : g_variant == 4 ? fast_pair_emu<4>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
                                       : fast_pair_emu<2>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info);
         if (rc) return rc;
         if (out_info[0] != CLIP_OK || out_info[1] == 0) return 0;

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 LIB = os.path.join(EMU, "_build", "libk3emu.so")
 SRC = [os.path.join(EMU, "k3_emu.cpp"), os.path.join(EMU, "simt_shim.h")] + \
-      [os.path.join(HERE, "..", "surtr_b200", "csrc", f) for f in ("clip_sub.cuh", "clip_fast.cuh", "clip_global.cuh", "clip_warp.cuh", "surtr_math.cuh")]
+      [os.path.join(HERE, "..", "surtr_b200", "csrc", f) for f in ("clip_sub.cuh", "clip_fast.cuh", "clip_duo.cuh", "clip_global.cuh", "clip_warp.cuh", "surtr_math.cuh")]
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 
@@ -39,7 +39,7 @@ def emu():
     return lib
 
 
-@pytest.fixture(params=[2, 4, 0], ids=["fast64", "fast128", "round1"])
+@pytest.fixture(params=[2, 16, 4, 0], ids=["fast64", "duo", "fast128", "round1"])
 def small(emu, request):
     """The small-tier clipper k3emu_pair runs: clip_fast.cuh with 64 slots (clip_fast_kernel<2,false>, the main K3
     launch), with 128 slots (clip_fast_kernel<4,true>), and round 1's clip_sub.cuh (kept for A/B profiles)."""
