@@ -783,11 +783,13 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 // G = 4 (128 slots, LIST = true) is a second, small launch over the pairs the main launch could not finish -- pieces of
 // 50-60 vertices whose cut transiently needs more than 64 slots (clipped vertices keep their slots until the patch has
 // walked through them) -- so that they do not detour through the block-per-pair large tier.
-template <int G, bool LIST>
+// DBG: the per-candidate cycle counters of csrc/surtr_debug.h (tests/measure/gpu_cycles.py).  A separate instantiation: in
+// the kernel that ships, three 64-bit time stamps and the cut counter would be live across the whole clip.
+template <int G, bool LIST, bool DBG = false>
 __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, uint32_t q, int lane)
 {
     constexpr int S = 32 * G;
-    const long long t0 = a.dbg ? clock64() : 0;
+    const long long t0 = DBG && a.dbg ? clock64() : 0;
     const uint2 pr = a.cand[q];
     const uint32_t v0 = a.p_vert_off[pr.x];
     int nv = (int)(a.p_vert_off[pr.x + 1] - v0);
@@ -859,7 +861,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
     }
     bad = __ballot_sync(FULL, bad) != 0u;
     __syncwarp();
-    const long long t1 = a.dbg ? clock64() : 0;
+    const long long t1 = DBG && a.dbg ? clock64() : 0;
     unsigned seq_cuts = 0, n_cuts = 0;
     unsigned live[G];
     int hi = 0, status = CLIP_OVERFLOW;
@@ -868,8 +870,8 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
 #pragma unroll
     for (int k = 0; k < 6; k++) box[k] = a.ext_p ? __ldg(a.ext_p + (size_t)pr.x * 2 * a.kdirs + k) : 0.f;
     if (!bad) status = fast_clip_by_planes<G>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts, box, a.ext_p != nullptr);
-    const long long t2 = a.dbg ? clock64() : 0;
-    if (a.dbg && lane == 0)
+    const long long t2 = DBG && a.dbg ? clock64() : 0;
+    if (DBG && a.dbg && lane == 0)
     {
         uint32_t* d = a.dbg + (size_t)q * 8;
         d[0] = (uint32_t)(t1 - t0); d[1] = (uint32_t)(t2 - t1); d[2] = 0; d[3] = 0;
@@ -939,7 +941,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
         rec->nf = 0;
         rec->tier = 1;
         rec->blob = blob;
-        if (a.dbg) a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t2);
+        if (DBG && a.dbg) a.dbg[(size_t)q * 8 + 3] = (uint32_t)(clock64() - t2);
     }
 }
 
@@ -949,7 +951,7 @@ constexpr int FAST_PERSIST_WARPS = 4;   // warps per block of the resident launc
 // block per one / two pairs in profiles/r2_k3_launch_shape.md: 2.50 vs 4.04 / 3.41 ms on a 256-event config-4 batch -- the
 // register file holds 32 of these warps per SM, a two-pair block keeps its slots until its slower pair is through, and
 // one-pair blocks are bound by the block launch rate).
-template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false>
+template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false, bool DBG = false>
 __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
@@ -975,7 +977,7 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(
         {
             unsigned next = 0xffffffffu;
             if (more && lane == 0) next = nw + atomicAdd(&a.ctl->k3_ticket, 1u);
-            fast_pair<G, LIST>(a, sp, q, lane);
+            fast_pair<G, LIST, DBG>(a, sp, q, lane);
             __syncwarp();
             q = __shfl_sync(FULL, next, 0);
         }
@@ -984,14 +986,14 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(
     {
         unsigned long long n_items = a.ctl->n_cand;
         if (n_items > a.cap_cand) n_items = a.cap_cand;
-        if (wid < n_items) fast_pair<G, LIST>(a, sp, (uint32_t)wid, lane);
+        if (wid < n_items) fast_pair<G, LIST, DBG>(a, sp, (uint32_t)wid, lane);
     }
     else
     {
         const unsigned long long n_items = a.ctl->n_ovf, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
         for (unsigned long long it = wid; it < n_items; it += nw)
         {
-            fast_pair<G, LIST>(a, sp, a.ovf_list[it], lane);
+            fast_pair<G, LIST, DBG>(a, sp, a.ovf_list[it], lane);
             __syncwarp();
         }
     }
