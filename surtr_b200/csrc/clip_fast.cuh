@@ -29,6 +29,16 @@ struct FastPoly   // one per warp in shared memory: 31 bytes per slot (G = 2: 19
     uint8_t id[S];        // walk-target probe: id[X(w)] = w; final numbering at write-out
 };
 
+#ifndef SURTR_K3_REG_GROUPS
+#define SURTR_K3_REG_GROUPS 0   // vertex groups whose positions the owner lane also keeps in registers; the others are read from shared
+                                // memory in the classification.  0 ships: three LDS per classified vertex group against six registers
+                                // of a 48-register budget (profiles/r3_k3_experiments.md, section 3)
+#endif
+constexpr int FAST_REG_GROUPS = SURTR_K3_REG_GROUPS;
+#ifndef SURTR_K3_PREFETCH
+#define SURTR_K3_PREFETCH 0   // 1: load the next plane of the queue one iteration ahead (four registers).  With 40 resident warps per SM
+                              // the other warps hide that load better than the registers would (same table)
+#endif
 constexpr int FAST_MAX_PLANES = 64;   // planes the prefilter keeps a bit for (cells beyond it: every plane takes the exact path)
 
 // The planes the exact path still has to look at, as a bit set that is consumed from the bottom: bits 0..63 = planes
@@ -364,7 +374,11 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
     {
         const float4 pl = cur;
         const int pn = pq.peek(npl);                                           // next plane the exact path has to look at
+#if SURTR_K3_PREFETCH
         const float4 nxt = __ldg(planes + (pn < npl ? pn : p));                // broadcast load, one plane ahead
+#else
+#define nxt __ldg(planes + (pn < npl ? pn : p))
+#endif
 
         // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per vertex group ----
         unsigned anyc = 0u, anyk = 0u;
@@ -374,7 +388,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             m.c[g] = m.k[g] = 0u;
             if (g == 0 || hi > 32 * g)   // warp-uniform
             {
-                const float d = signed_dist(pl, px[g], py[g], pz[g]);
+                const float d = g < FAST_REG_GROUPS ? signed_dist(pl, px[g], py[g], pz[g]) : signed_dist(pl, sp.x[lane + 32 * g], sp.y[lane + 32 * g], sp.z[lane + 32 * g]);
                 const bool off = (m.live[g] & lm) && !(fabsf(d) < __uint_as_float(0x2EDBE6FFu));   // live and not in-plane (a NaN distance is in-plane)
                 m.c[g] = __ballot_sync(FULL, off && d > 0.f);
                 m.k[g] = __ballot_sync(FULL, off && d < 0.f);
@@ -442,7 +456,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             for (int g = 0; g < G; g++)
             {
                 const int v = lane + 32 * g;
-                if (v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+                if (g < FAST_REG_GROUPS && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
             }
             continue;
         }
@@ -543,7 +557,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             m.live[g] = ((m.live[g] & ~m.c[g]) | nm) & ~dead[g];
             nv += __popc(m.live[g]);
             const int v = lane + 32 * g;
-            if (v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+            if (g < FAST_REG_GROUPS && v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
         }
         if (nv < 4) nv = 0;   // Poly.cpp:498-499
         __syncwarp();         // ring words composed above are visible to the next cut
@@ -555,4 +569,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
     for (int g = 0; g < G; g++) live[g] = m.live[g];
     return status;
 }
+#if !SURTR_K3_PREFETCH
+#undef nxt
+#endif
 } // namespace surtr

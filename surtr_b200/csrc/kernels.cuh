@@ -927,7 +927,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
             if (lv)
             {
                 const int t = sp.id[v];
-                bv[t] = make_float4(px[g], py[g], pz[g], 0.f);
+                bv[t] = g < FAST_REG_GROUPS ? make_float4(px[g], py[g], pz[g], 0.f) : make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
                 bo[t] = (uint16_t)off;
 #pragma unroll 1
                 for (int j = 0; j < d; j++) br[off + j] = sp.id[rget(rw, j)];
@@ -946,13 +946,18 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
 }
 
 constexpr int FAST_WARPS = 2;   // pairs per block: a block's slots are held until its slowest pair ends; 2 packs better than 4 (profiles/README.md)
+#ifndef SURTR_K3_RESIDENT_WARPS
+#define SURTR_K3_RESIDENT_WARPS 40   // resident warps per SM of the persistent small-tier launch = its register budget (40 -> 48 registers);
+                                     // measured 24 / 28 / 32 / 36 / 40 warps: profiles/r3_k3_experiments.md, section 3
+#endif
+constexpr int FAST_RESIDENT_WARPS = SURTR_K3_RESIDENT_WARPS;
 constexpr int FAST_PERSIST_WARPS = 4;   // warps per block of the resident launch (each warp pulls its own candidates; fewer, larger blocks = fewer block launches on a one-wave event)
 // W = warps (= pairs) per block, PERSIST = resident warps with a ticket counter (the main launch; measured against one
 // block per one / two pairs in profiles/r2_k3_launch_shape.md: 2.50 vs 4.04 / 3.41 ms on a 256-event config-4 batch -- the
 // register file holds 32 of these warps per SM, a two-pair block keeps its slots until its slower pair is through, and
 // one-pair blocks are bound by the block launch rate).
 template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false, bool DBG = false>
-__global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(ClipArgs a)
+__global__ void __launch_bounds__(W * 32, G == 2 ? (PERSIST ? FAST_RESIDENT_WARPS : 32) / W : 8) clip_fast_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
@@ -962,7 +967,7 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? 32 / W : 8) clip_fast_kernel(
     const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (!LIST && PERSIST)
     {
-        // Resident warps (one block = one warp, 32 per SM): warp w cuts candidate w, then pulls further candidates from a
+        // Resident warps (FAST_RESIDENT_WARPS per SM in blocks of four): warp w cuts candidate w, then pulls further candidates from a
         // ticket counter.  The next ticket is requested before the current pair is cut, so its round trip to the L2 hides
         // behind the cut; an event of a single wave (config 2: 4096 pairs) never touches the counter.  Against one block
         // per pair (SURTR_K3_WARPS=2) this removes the block launches -- the grid is sized by capacity, more than half

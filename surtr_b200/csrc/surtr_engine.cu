@@ -385,7 +385,7 @@ int launch_event(surtr_ctx* ctx)
                        dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
         else if (ctx->k3_warps == 0)
             launch_pdl(ctx->debug ? clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true, true> : clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true>,
-                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * (32 / FAST_PERSIST_WARPS))),
+                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * (FAST_RESIDENT_WARPS / FAST_PERSIST_WARPS))),
                        dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
         else launch_pdl(clip_fast_kernel<2, false, 2>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
