@@ -388,6 +388,7 @@ def config2(args, torch, dev, local, ctx, synth, flush, stream, n_streams: int =
         s = S()
         s.cx = FractureContext(local, sts[j % n_streams].cuda_stream)
         s.cx.set_kdop_directions(3)
+        s.cx.set_clip_build(1)            # several one-wave events in flight on different streams: the throughput build of K3
         rolled = synth.roll_cells(cells, j * (n_seeds // n_sets))
         s.h_in, s.h_out = host_inputs(rolled), out_buffers()
         s.cx.upload_pieces(cube_v, cube_vo, cube_ro, cube_r)

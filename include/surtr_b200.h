@@ -103,6 +103,11 @@ const char* surtr_version(void);
  * microseconds in K1 / K2 and keep 40 % of the AABB's dead candidates away from the clipper.  The set never changes
  * the fragments, only how many pairs reach K3. */
 int surtr_set_kdop_directions(surtr_ctx* ctx, int k);
+/* Which build of the small-tier clipper (K3) an event launches: 0 (default) = by the size of the context's previous event --
+ * the latency build (32 warps per SM, 64 registers, plane prefetch) when its candidate pairs fit one wave of warps, the
+ * throughput build (40 warps per SM, 48 registers) otherwise; 1 = always throughput (a caller that keeps several small
+ * events in flight on different streams), 2 = always latency.  Never changes a result, only the event time. */
+int surtr_set_clip_build(surtr_ctx* ctx, int mode);
 
 /* --- inputs (host -> device; replaces the per-task deep copies of Src/Poly.cpp:562, Surtr.cpp:2129-2131) - */
 int surtr_upload_pieces(surtr_ctx* ctx, const float* verts4, const uint32_t* vert_off, const uint32_t* ring_off,

@@ -29,15 +29,19 @@ struct FastPoly   // one per warp in shared memory: 31 bytes per slot (G = 2: 19
     uint8_t id[S];        // walk-target probe: id[X(w)] = w; final numbering at write-out
 };
 
+// Two builds of the clipper, chosen per launch (kernels.cuh, clip_fast_kernel<..., LAT>):
+//   LAT = false (throughput; events of more than one wave of warps): 40 resident warps per SM = 48 registers; the positions
+//     are read from shared memory in the classification (three LDS per vertex group against six registers) and the next
+//     plane of the queue is not loaded ahead (four registers) -- the other warps hide those latencies.  Config 4: K3 2.38 ->
+//     2.24 ms per 256-event batch against the 32-warp / 64-register build.
+//   LAT = true (latency; an event that fits one wave, BASELINE config 2): 32 warps, 64 registers, positions of the lane's
+//     own slots in registers, plane prefetch: the single warp's critical path decides (config 2 cold event 0.136 vs 0.149 ms).
+// Measured over 24-40 warps, 0 / 1 / all register groups, prefetch on / off: profiles/r3_k3_experiments.md, section 3.
 #ifndef SURTR_K3_REG_GROUPS
-#define SURTR_K3_REG_GROUPS 0   // vertex groups whose positions the owner lane also keeps in registers; the others are read from shared
-                                // memory in the classification.  0 ships: three LDS per classified vertex group against six registers
-                                // of a 48-register budget (profiles/r3_k3_experiments.md, section 3)
+#define SURTR_K3_REG_GROUPS 0   // (throughput build) vertex groups whose positions the owner lane keeps in registers
 #endif
-constexpr int FAST_REG_GROUPS = SURTR_K3_REG_GROUPS;
 #ifndef SURTR_K3_PREFETCH
-#define SURTR_K3_PREFETCH 0   // 1: load the next plane of the queue one iteration ahead (four registers).  With 40 resident warps per SM
-                              // the other warps hide that load better than the registers would (same table)
+#define SURTR_K3_PREFETCH 0     // (throughput build) 1: load the next plane of the queue one iteration ahead
 #endif
 constexpr int FAST_MAX_PLANES = 64;   // planes the prefilter keeps a bit for (cells beyond it: every plane takes the exact path)
 
@@ -308,7 +312,7 @@ __device__ __noinline__ bool fast_all_inplane_box_says_skip(const FastPoly<G>& s
 // Clip the polyhedron in `sp` (nv vertices in slots 0..nv-1, positions of the lane's own slots also in px/py/pz) by
 // planes[0..npl).  Called by the 32 lanes of the pair's warp.  On return live = the live slots (not renumbered), hi the
 // allocated slots, nv the live count (0 = no fragment); returns the pair's status.
-template <int G>
+template <int G, int RG = SURTR_K3_REG_GROUPS, bool PF = (SURTR_K3_PREFETCH != 0)>
 __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi, int& nv, float (&px)[G], float (&py)[G], float (&pz)[G],
                                    const float4* __restrict__ planes, int npl, int lane, unsigned& seq_cuts, unsigned& n_cuts,
                                    const float (&box)[6], bool use_box)
@@ -374,11 +378,8 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
     {
         const float4 pl = cur;
         const int pn = pq.peek(npl);                                           // next plane the exact path has to look at
-#if SURTR_K3_PREFETCH
-        const float4 nxt = __ldg(planes + (pn < npl ? pn : p));                // broadcast load, one plane ahead
-#else
-#define nxt __ldg(planes + (pn < npl ? pn : p))
-#endif
+        float4 nxt = cur;
+        if (PF) nxt = __ldg(planes + (pn < npl ? pn : p));                     // broadcast load, one plane ahead
 
         // ---- classify (Poly.cpp:303-319): one distance per owned live vertex, two ballots per vertex group ----
         unsigned anyc = 0u, anyk = 0u;
@@ -388,7 +389,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             m.c[g] = m.k[g] = 0u;
             if (g == 0 || hi > 32 * g)   // warp-uniform
             {
-                const float d = g < FAST_REG_GROUPS ? signed_dist(pl, px[g], py[g], pz[g]) : signed_dist(pl, sp.x[lane + 32 * g], sp.y[lane + 32 * g], sp.z[lane + 32 * g]);
+                const float d = g < RG ? signed_dist(pl, px[g], py[g], pz[g]) : signed_dist(pl, sp.x[lane + 32 * g], sp.y[lane + 32 * g], sp.z[lane + 32 * g]);
                 const bool off = (m.live[g] & lm) && !(fabsf(d) < __uint_as_float(0x2EDBE6FFu));   // live and not in-plane (a NaN distance is in-plane)
                 m.c[g] = __ballot_sync(FULL, off && d > 0.f);
                 m.k[g] = __ballot_sync(FULL, off && d < 0.f);
@@ -400,7 +401,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
         {
             // nothing clipped: "above" (Poly.cpp:328) -- unless every vertex is in-plane and the box test says "below"
             if (!anyk && !fast_all_inplane_box_says_skip<G>(sp, m, hi, pl, lane)) { nv = 0; break; }
-            cur = nxt;
+            cur = PF ? nxt : __ldg(planes + (pn < npl ? pn : p));
             p = pn;
             pq.pop();
             continue;
@@ -456,7 +457,7 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             for (int g = 0; g < G; g++)
             {
                 const int v = lane + 32 * g;
-                if (g < FAST_REG_GROUPS && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+                if (g < RG && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
             }
             continue;
         }
@@ -557,11 +558,11 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
             m.live[g] = ((m.live[g] & ~m.c[g]) | nm) & ~dead[g];
             nv += __popc(m.live[g]);
             const int v = lane + 32 * g;
-            if (g < FAST_REG_GROUPS && v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
+            if (g < RG && v >= hi0 && v < hi) { px[g] = sp.x[v]; py[g] = sp.y[v]; pz[g] = sp.z[v]; }
         }
         if (nv < 4) nv = 0;   // Poly.cpp:498-499
         __syncwarp();         // ring words composed above are visible to the next cut
-        cur = nxt;
+        cur = PF ? nxt : __ldg(planes + (pn < npl ? pn : p));
         p = pn;
         pq.pop();
     }
@@ -569,7 +570,4 @@ __device__ int fast_clip_by_planes(FastPoly<G>& sp, unsigned (&live)[G], int& hi
     for (int g = 0; g < G; g++) live[g] = m.live[g];
     return status;
 }
-#if !SURTR_K3_PREFETCH
-#undef nxt
-#endif
 } // namespace surtr

@@ -785,9 +785,10 @@ __global__ void __launch_bounds__(T3_WARPS * 32) clip_global_kernel(ClipArgs a)
 // walked through them) -- so that they do not detour through the block-per-pair large tier.
 // DBG: the per-candidate cycle counters of csrc/surtr_debug.h (tests/measure/gpu_cycles.py).  A separate instantiation: in
 // the kernel that ships, three 64-bit time stamps and the cut counter would be live across the whole clip.
-template <int G, bool LIST, bool DBG = false>
+template <int G, bool LIST, bool DBG = false, bool LAT = false>
 __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, uint32_t q, int lane)
 {
+    constexpr int RG = LAT ? G : SURTR_K3_REG_GROUPS;   // vertex groups with positions in registers (clip_fast.cuh)
     constexpr int S = 32 * G;
     const long long t0 = DBG && a.dbg ? clock64() : 0;
     const uint2 pr = a.cand[q];
@@ -869,7 +870,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
     float box[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) box[k] = a.ext_p ? __ldg(a.ext_p + (size_t)pr.x * 2 * a.kdirs + k) : 0.f;
-    if (!bad) status = fast_clip_by_planes<G>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts, box, a.ext_p != nullptr);
+    if (!bad) status = fast_clip_by_planes<G, RG, LAT || SURTR_K3_PREFETCH != 0>(sp, live, hi, nv, px, py, pz, a.c_planes + pl0, npl, lane, seq_cuts, n_cuts, box, a.ext_p != nullptr);
     const long long t2 = DBG && a.dbg ? clock64() : 0;
     if (DBG && a.dbg && lane == 0)
     {
@@ -927,7 +928,7 @@ __device__ __forceinline__ void fast_pair(const ClipArgs& a, FastPoly<G>& sp, ui
             if (lv)
             {
                 const int t = sp.id[v];
-                bv[t] = g < FAST_REG_GROUPS ? make_float4(px[g], py[g], pz[g], 0.f) : make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
+                bv[t] = g < RG ? make_float4(px[g], py[g], pz[g], 0.f) : make_float4(sp.x[v], sp.y[v], sp.z[v], 0.f);
                 bo[t] = (uint16_t)off;
 #pragma unroll 1
                 for (int j = 0; j < d; j++) br[off + j] = sp.id[rget(rw, j)];
@@ -956,8 +957,10 @@ constexpr int FAST_PERSIST_WARPS = 4;   // warps per block of the resident launc
 // block per one / two pairs in profiles/r2_k3_launch_shape.md: 2.50 vs 4.04 / 3.41 ms on a 256-event config-4 batch -- the
 // register file holds 32 of these warps per SM, a two-pair block keeps its slots until its slower pair is through, and
 // one-pair blocks are bound by the block launch rate).
-template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false, bool DBG = false>
-__global__ void __launch_bounds__(W * 32, G == 2 ? (PERSIST ? FAST_RESIDENT_WARPS : 32) / W : 8) clip_fast_kernel(ClipArgs a)
+// LAT: the latency build of the clipper for events that fit one wave of warps (clip_fast.cuh); the host picks it from the
+// candidate count of the context's previous event.
+template <int G, bool LIST, int W = FAST_WARPS, bool PERSIST = false, bool DBG = false, bool LAT = false>
+__global__ void __launch_bounds__(W * 32, G == 2 ? (PERSIST && !LAT ? FAST_RESIDENT_WARPS : 32) / W : 8) clip_fast_kernel(ClipArgs a)
 {
     pdl_launch_dependents();
     pdl_wait();
@@ -982,7 +985,7 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? (PERSIST ? FAST_RESIDENT_WARP
         {
             unsigned next = 0xffffffffu;
             if (more && lane == 0) next = nw + atomicAdd(&a.ctl->k3_ticket, 1u);
-            fast_pair<G, LIST, DBG>(a, sp, q, lane);
+            fast_pair<G, LIST, DBG, LAT>(a, sp, q, lane);
             __syncwarp();
             q = __shfl_sync(FULL, next, 0);
         }
@@ -991,14 +994,14 @@ __global__ void __launch_bounds__(W * 32, G == 2 ? (PERSIST ? FAST_RESIDENT_WARP
     {
         unsigned long long n_items = a.ctl->n_cand;
         if (n_items > a.cap_cand) n_items = a.cap_cand;
-        if (wid < n_items) fast_pair<G, LIST, DBG>(a, sp, (uint32_t)wid, lane);
+        if (wid < n_items) fast_pair<G, LIST, DBG, LAT>(a, sp, (uint32_t)wid, lane);
     }
     else
     {
         const unsigned long long n_items = a.ctl->n_ovf, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
         for (unsigned long long it = wid; it < n_items; it += nw)
         {
-            fast_pair<G, LIST, DBG>(a, sp, a.ovf_list[it], lane);
+            fast_pair<G, LIST, DBG, LAT>(a, sp, a.ovf_list[it], lane);
             __syncwarp();
         }
     }

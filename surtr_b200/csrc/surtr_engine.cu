@@ -137,6 +137,8 @@ struct surtr_ctx
     bool k3_round1 = false;       // SURTR_K3=sub: the round-1 small-tier kernel (A/B profiles only)
     uint32_t last_ring_bytes = 2; // ring entry width of the last event's output blob (surtr_download_blob_async)
     int k3_warps = 0;             // small tier's main launch: 0 = persistent warps + ticket (default); SURTR_K3_WARPS=2: one block of two pairs per two candidates (A/B)
+    int k3_build = 0;             // SURTR_K3_BUILD=throughput / latency pins the small tier's build (A/B); default: by the last event's candidate count
+    uint64_t last_n_cand = 0;     // candidates of the last resolved event
     bool k3_duo = false;          // SURTR_K3_DUO=1: two candidate pairs per warp (clip_duo.cuh)
     bool no_tier1b = false;       // SURTR_DEBUG_NO_TIER1B=1 (test hook): 64-slot overflows go straight to the large tier
     bool tier2_enabled = false;   // the large on-chip tier is launched once an event needed it
@@ -384,9 +386,18 @@ int launch_event(surtr_ctx* ctx)
                        dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + 2 * FAST_PERSIST_WARPS - 1) / (2 * FAST_PERSIST_WARPS)), (uint64_t)ctx->num_sm * (32 / FAST_PERSIST_WARPS))),
                        dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
         else if (ctx->k3_warps == 0)
-            launch_pdl(ctx->debug ? clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true, true> : clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true>,
-                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * (FAST_RESIDENT_WARPS / FAST_PERSIST_WARPS))),
+        {
+            // an event that fits one wave of warps is bound by its slowest pair, not by issue slots: the latency build
+            // (32 warps per SM, 64 registers); decided from the candidate count of this context's previous event
+            const bool lat = !ctx->debug && ctx->k3_build != 1 &&
+                             (ctx->k3_build == 2 || (ctx->last_n_cand > 0 && ctx->last_n_cand <= (uint64_t)ctx->num_sm * 32));
+            const unsigned per_sm = (lat ? 32 : FAST_RESIDENT_WARPS) / FAST_PERSIST_WARPS;
+            launch_pdl(ctx->debug ? clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true, true>
+                       : lat      ? clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true, false, true>
+                                  : clip_fast_kernel<2, false, FAST_PERSIST_WARPS, true>,
+                       dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ctx->cap_cand + FAST_PERSIST_WARPS - 1) / FAST_PERSIST_WARPS), (uint64_t)ctx->num_sm * per_sm)),
                        dim3(FAST_PERSIST_WARPS * 32), 0, ctx->stream, ca);
+        }
         else launch_pdl(clip_fast_kernel<2, false, 2>, dim3((unsigned)blocks), dim3(FAST_WARPS * 32), 0, ctx->stream, ca);
         ctx->launches++;
     }
@@ -530,6 +541,7 @@ int resolve_event(surtr_ctx* ctx)
                            "see surtr_failed_pairs -- all other fragments of the event are valid";
             ctx->last.n_pairs = ctx->n_pairs;
             ctx->last.n_candidates = c.n_cand;
+            ctx->last_n_cand = c.n_cand;
             ctx->last.n_fragments = c.n_frag;
             ctx->last.n_verts = c.n_fverts;
             ctx->last.n_ring = c.n_fring;
@@ -634,6 +646,7 @@ int surtr_ctx_create(int device, void* stream, surtr_ctx** out)
     if (const char* e = std::getenv("SURTR_DEBUG_NO_TIER1B")) ctx->no_tier1b = e[0] == '1';
     if (const char* e = std::getenv("SURTR_K3_WARPS")) ctx->k3_warps = e[0] == '2' ? 2 : 0;
     if (const char* e = std::getenv("SURTR_K3_DUO")) ctx->k3_duo = e[0] == '1';
+    if (const char* e = std::getenv("SURTR_K3_BUILD")) ctx->k3_build = e[0] == 't' ? 1 : (e[0] == 'l' ? 2 : 0);
     *out = ctx;
     return SURTR_OK;
 }
@@ -665,6 +678,14 @@ int surtr_set_kdop_directions(surtr_ctx* ctx, int k)
     if (!ctx) return SURTR_ERR_INVALID;
     if (k != 3 && k != 7 && k != 13) return fail(ctx, SURTR_ERR_INVALID, "k must be 3, 7 or 13");
     ctx->kdirs = k;
+    return SURTR_OK;
+}
+
+int surtr_set_clip_build(surtr_ctx* ctx, int mode)
+{
+    if (!ctx) return SURTR_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(ctx, SURTR_ERR_INVALID, "mode must be 0 (by event size), 1 (throughput) or 2 (latency)");
+    ctx->k3_build = mode;
     return SURTR_OK;
 }
 

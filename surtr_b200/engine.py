@@ -28,7 +28,7 @@ assert FRAGMENT_DTYPE.itemsize == 64
 
 # every symbol include/surtr_b200.h declares
 EXPORTS = [
-    "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions",
+    "surtr_ctx_create", "surtr_ctx_destroy", "surtr_last_error", "surtr_version", "surtr_set_kdop_directions", "surtr_set_clip_build",
     "surtr_upload_pieces", "surtr_upload_cells", "surtr_fragments_to_pieces", "surtr_fragments_to_pieces_per_event", "surtr_fracture_event",
     "surtr_event_counts", "surtr_download_fragments", "surtr_device_fragments", "surtr_kdop_calc",
     "surtr_last_event_ms", "surtr_last_event_launches", "surtr_set_profiling", "surtr_kdop_calc_batch",
@@ -83,6 +83,7 @@ def load_library():
     lib.surtr_last_error.restype = C.c_char_p
     lib.surtr_version.restype = C.c_char_p
     lib.surtr_set_kdop_directions.argtypes = [vp, i32]
+    lib.surtr_set_clip_build.argtypes = [vp, i32]
     lib.surtr_upload_pieces.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
     lib.surtr_upload_cells.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
     lib.surtr_upload_pieces3.argtypes = [vp, vp, vp, vp, vp, u32, vp, u32]
@@ -182,6 +183,10 @@ class FractureContext:
 
     def set_kdop_directions(self, k: int):
         self._ck(self._lib.surtr_set_kdop_directions(self._h, k))
+
+    def set_clip_build(self, mode: int):
+        """0 = by the size of the previous event (default), 1 = throughput build of K3's small tier, 2 = latency build."""
+        self._ck(self._lib.surtr_set_clip_build(self._h, mode))
 
     def upload_pieces(self, verts4, vert_off, ring_off, ring, ev_piece_off=None):
         verts4 = _arr(verts4, np.float32)

@@ -103,8 +103,8 @@ static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const ui
         const int t = mrank<G>(live[0], v);
         if (t != n) return -2;
         const int l = v & 31, g = v >> 5;
-        if (g < FAST_REG_GROUPS && px[l][g] != sp->x[v] && !(px[l][g] != px[l][g])) return -6;   // the register copy is the shared-memory copy
-        if (g < FAST_REG_GROUPS) { out_verts4[4 * t] = px[l][g]; out_verts4[4 * t + 1] = py[l][g]; out_verts4[4 * t + 2] = pz[l][g]; }
+        if (g < SURTR_K3_REG_GROUPS && px[l][g] != sp->x[v] && !(px[l][g] != px[l][g])) return -6;   // the register copy is the shared-memory copy
+        if (g < SURTR_K3_REG_GROUPS) { out_verts4[4 * t] = px[l][g]; out_verts4[4 * t + 1] = py[l][g]; out_verts4[4 * t + 2] = pz[l][g]; }
         else { out_verts4[4 * t] = sp->x[v]; out_verts4[4 * t + 1] = sp->y[v]; out_verts4[4 * t + 2] = sp->z[v]; }
         out_verts4[4 * t + 3] = 0.f;
         out_ring_off[t] = (uint32_t)ne;

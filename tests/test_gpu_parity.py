@@ -152,6 +152,21 @@ def test_fragments_to_pieces_per_event_matches_host_regrouping(ctx):
         other.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["throughput", "latency"])
+def test_both_builds_of_the_small_tier_match_the_oracle(ctx, mode):
+    """surtr_set_clip_build: the throughput build of K3's small tier (40 warps per SM, positions from shared memory, no plane
+    prefetch) and the latency build (32 warps, register copies, prefetch) cut the same fragments, bit for bit the oracle's."""
+    pieces, cells = common.voronoi(1234, 300), common.voronoi(46354, 40)
+    want = P.apply_fracture(pieces, cells.planes, cells.plane_off)
+    ctx.set_clip_build(mode)
+    try:
+        for _ in range(2):      # (the second event has a previous event to size itself by; the pinned build ignores it)
+            got = common.run_gpu(ctx, pieces, cells)
+            common.assert_fragments_equal(got, want)
+    finally:
+        ctx.set_clip_build(0)
+
+
 def test_edge_cases(ctx):
     cube = common.unit_cube()
     cells = common.voronoi(46354, 64)

@@ -16,22 +16,22 @@ python tools/ncu_k.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel $N4 40 > $P/r2_k3
 python tools/ncu_k.py $G/${T}_k4_cfg4.ncu-rep assemble_gather $F4 40 > $P/r2_k4_gather_metrics.txt
 python tools/ncu_k.py $G/${T}_k3_cfg2.ncu-rep clip_fast_kernel 4096 25 > $P/r2_k3_config2_metrics.txt
 cat > /tmp/k3_ranges.txt <<'R'
-302 354 prefilter (box vs planes) + setup
-355 368 plane queue: peek / pop, prefetch of the next plane
-369 395 classify + no-cut exits
-396 414 straddle loop (ring slots of clipped lanes)
-415 433 prefix by ballots
-434 448 overflow / compaction trigger
-449 458 list write
-459 477 insert new vertices
-478 508 patch walk
-509 512 probe check
-513 523 compose rings
-524 534 seq dispatch
-535 556 live update, refresh
-100 232 sequential replay (fast_seq_cut)
-233 275 compaction (fast_compact)
-276 300 all-in-plane box test
+312 364 prefilter (box vs planes) + setup
+365 382 plane queue: peek / pop
+383 409 classify + no-cut exits
+410 428 straddle loop (ring slots of clipped lanes)
+429 447 prefix by ballots
+448 462 overflow / compaction trigger
+463 472 list write
+473 491 insert new vertices
+492 522 patch walk
+523 526 probe check
+527 537 compose rings
+538 548 seq dispatch
+549 575 live update, refresh
+110 242 sequential replay (fast_seq_cut)
+243 284 compaction (fast_compact)
+285 310 all-in-plane box test
 R
 python tools/ncu_callsite_buckets.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel clip_fast_kernelILi2ELb0ELi4ELb1 surtr_b200/libsurtr_b200.so clip_fast.cuh $N4 /tmp/k3_ranges.txt > $P/r2_k3_instruction_buckets.txt
 python tools/ncu_callsite_buckets.py $G/${T}_k3_cfg4.ncu-rep clip_fast_kernel clip_fast_kernelILi2ELb0ELi4ELb1 surtr_b200/libsurtr_b200.so kernels.cuh $N4 2>/dev/null | head -24 >> $P/r2_k3_instruction_buckets.txt || true
