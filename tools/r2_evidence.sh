@@ -14,15 +14,18 @@ for w in config4 config3; do
 done
 # ---- unprofiled phase times of the same workloads (CUDA events)
 for rep in 1 2 3; do for w in config4 config3 config2 mesh; do EVENTS=256 python tools/gpu_profile_workloads.py $w 1 2>&1 | tail -1 >> $O/${T}_phases_$w.jsonl; done; done
+# ---- full capture of the dominant kernel on one resident batch of the bench (512 events) FIRST: its cold DRAM traffic is what
+#      the bench line reports as roofline.traffic (profiles/r2_k3_traffic.json, tied to the kernel sources by their hash)
+EVENTS=512 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:clip_fast_kernel -c 1 -f -o $O/${T}_k3_cfg4 \
+  python tools/gpu_profile_workloads.py config4 1 > $O/${T}_k3_cfg4.log 2>&1
+python tools/ncu_traffic.py $O/${T}_k3_cfg4.ncu-rep $O/${T}_k3_cfg4.log clip_fast_kernel > $O/${T}_k3_traffic.log 2>&1
 # ---- bench lines (never under a profiler)
 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err
 # ---- launch list of the bench command
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-secondary --no-cpu-baseline --events 1024 > $O/${T}_ncu_bench.log 2>&1
-# ---- full captures of the two dominant kernels: one resident batch of the bench (512 events), and config 2
-EVENTS=512 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:clip_fast_kernel -c 1 -f -o $O/${T}_k3_cfg4 \
-  python tools/gpu_profile_workloads.py config4 1 > $O/${T}_k3_cfg4.log 2>&1
+# ---- full captures of K4 on the same batch, and of K3 on config 2
 EVENTS=512 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:assemble_gather -c 1 -f -o $O/${T}_k4_cfg4 \
   python tools/gpu_profile_workloads.py config4 1 > $O/${T}_k4_cfg4.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:clip_fast_kernel -c 1 -f -o $O/${T}_k3_cfg2 \
