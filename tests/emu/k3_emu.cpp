@@ -25,14 +25,16 @@ void k3emu_set_schedule(unsigned mode) { simt::schedule() = mode; }
 
 }   // extern "C"
 
-// Which small-tier clipper k3emu_pair runs: 2 / 4 = fast_clip_by_planes<G> of clip_fast.cuh (64 / 128 vertex slots: the
+// Which small-tier clipper k3emu_pair runs: 2 / 4 = fast_clip_by_planes<G> of clip_fast.cuh (64 / 128 vertex slots, the
+// throughput build: positions from shared memory, no plane prefetch), 22 = its latency build (64 slots, positions of the
+// lane's own slots in registers, next plane loaded one iteration ahead: clip_fast_kernel<..., LAT = true>); (the
 // kernels that ship, clip_fast_kernel<2,false> and <4,true>), 16 = duo_clip_by_planes of clip_duo.cuh (two pairs per warp,
 // clip_duo_kernel), 0 = sub_clip_by_planes<32> of clip_sub.cuh (round 1).
 static int g_variant = 2;
 extern "C" void k3emu_set_variant(int v) { g_variant = v; }
 
 // The staging, clip and write-out of fast_pair<G> (kernels.cuh) for one pair.  Returns < 0 on an emulation inconsistency.
-template <int G>
+template <int G, int RG = SURTR_K3_REG_GROUPS, bool PF = (SURTR_K3_PREFETCH != 0)>
 static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const uint16_t* ring, int nv_in, const std::vector<float4>& planes,
                          int npl, float* out_verts4, uint32_t* out_ring_off, uint16_t* out_ring, int* out_info)
 {
@@ -79,7 +81,7 @@ static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const ui
         nv[lane] = nv_in;
         seq[lane] = cuts[lane] = 0;
         hi[lane] = 0;
-        status[lane] = fast_clip_by_planes<G>(*sp, live[lane], hi[lane], nv[lane], px[lane], py[lane], pz[lane], planes.data(), npl, lane,
+        status[lane] = fast_clip_by_planes<G, RG, PF>(*sp, live[lane], hi[lane], nv[lane], px[lane], py[lane], pz[lane], planes.data(), npl, lane,
                                               seq[lane], cuts[lane], box, true);
     });
     for (int l = 1; l < 32; l++)   // warp-uniform by construction
@@ -103,8 +105,8 @@ static int fast_pair_emu(const float* verts4, const uint32_t* ring_off, const ui
         const int t = mrank<G>(live[0], v);
         if (t != n) return -2;
         const int l = v & 31, g = v >> 5;
-        if (g < SURTR_K3_REG_GROUPS && px[l][g] != sp->x[v] && !(px[l][g] != px[l][g])) return -6;   // the register copy is the shared-memory copy
-        if (g < SURTR_K3_REG_GROUPS) { out_verts4[4 * t] = px[l][g]; out_verts4[4 * t + 1] = py[l][g]; out_verts4[4 * t + 2] = pz[l][g]; }
+        if (g < RG && px[l][g] != sp->x[v] && !(px[l][g] != px[l][g])) return -6;   // the register copy is the shared-memory copy
+        if (g < RG) { out_verts4[4 * t] = px[l][g]; out_verts4[4 * t + 1] = py[l][g]; out_verts4[4 * t + 2] = pz[l][g]; }
         else { out_verts4[4 * t] = sp->x[v]; out_verts4[4 * t + 1] = sp->y[v]; out_verts4[4 * t + 2] = sp->z[v]; }
         out_verts4[4 * t + 3] = 0.f;
         out_ring_off[t] = (uint32_t)ne;
@@ -289,7 +291,8 @@ int k3emu_pair(const float* verts4, const uint32_t* ring_off, const uint16_t* ri
     int n = 0;
     if (g_variant != 0)
     {
-        const int rc = g_variant == 16 ? duo_pair_emu(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
+        const int rc = g_variant == 22 ? fast_pair_emu<2, 2, true>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
+                       : g_variant == 16 ? duo_pair_emu(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
                        : g_variant == 4 ? fast_pair_emu<4>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info)
                                       : fast_pair_emu<2>(verts4, ring_off, ring, nv_in, planes, npl, out_verts4, out_ring_off, out_ring, out_info);
         if (rc) return rc;

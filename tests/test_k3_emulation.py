@@ -39,9 +39,9 @@ def emu():
     return lib
 
 
-@pytest.fixture(params=[2, 16, 4, 0], ids=["fast64", "duo", "fast128", "round1"])
+@pytest.fixture(params=[2, 22, 16, 4, 0], ids=["fast64", "fast64lat", "duo", "fast128", "round1"])
 def small(emu, request):
-    """The small-tier clipper k3emu_pair runs: clip_fast.cuh with 64 slots (clip_fast_kernel<2,false>, the main K3
+    """The small-tier clipper k3emu_pair runs: clip_fast.cuh with 64 slots in its throughput and its latency build (clip_fast_kernel<2,false>, the main K3
     launch), with 128 slots (clip_fast_kernel<4,true>), and round 1's clip_sub.cuh (kept for A/B profiles)."""
     emu.k3emu_set_variant(request.param)
     yield emu
