@@ -1192,6 +1192,7 @@ int surtr_fragments_to_pieces_per_event(surtr_ctx* ctx)
     if (rc) return rc;
     if (ctx->last.n_fragments > 0xfffffff0ull) return fail(ctx, SURTR_ERR_INVALID, "too many fragments");
     const uint32_t n = (uint32_t)ctx->last.n_fragments;
+    if (ctx->h_ev_cell_off.size() < 2) return fail(ctx, SURTR_ERR_INVALID, "no cell set: there is no event layout to regroup by");
     const uint32_t ne = (uint32_t)ctx->h_ev_cell_off.size() - 1;   // the event layout the fragments were cut under
     // event boundaries in the fragment list, found on the device (the records never travel): n_events + 1 words come back
     CK(ctx->d_ev_frag_off.reserve(8 * ((size_t)ne + 1)));
